@@ -1,0 +1,74 @@
+#!/usr/bin/env python3
+"""Generates the committed golden fixtures from the REFERENCE's own artefacts.  Run only in the build
+container (needs /root/reference); the outputs in tests/golden/ are what travel.
+
+ 1. gridmaker_golden.npz — sparse copy (non-zero voxels) of the reference's voxeliser goldens
+    test/gninagrid/files/cc_0.48.35.binmap and ccsmall_0.33.35.binmap (35 x N^3 fp32; inputs files/CC.xyz as
+    receptor AND ligand, files/recmap + files/ligmap; test/gninagrid/CMakeLists.txt grid2cmp/gridbincmp).
+ 2. cnn_kat.npz — known answers of the reference's TorchScript models (gninasrc/lib/models/*.pt, loaded with
+    torch.jit.load exactly as torch_model.cpp:55 does) on (a) the all-zero grid and (b) oracle-voxelised
+    synthetic poses, in fp32 and fp64, plus the head post-processing of torch_model.cpp:188-195.
+"""
+import json, os, sys
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+sys.path.insert(0, ROOT)
+from gnina_b200 import model_blob, synth  # noqa: E402
+from oracle import pipeline  # noqa: E402
+
+REF = "/root/reference"
+
+
+def sparse_golden():
+    out = {}
+    for tag, fn, n in (("cc48", "cc_0.48.35.binmap", 48), ("ccsmall33", "ccsmall_0.33.35.binmap", 33)):
+        g = np.fromfile(os.path.join(REF, "test/gninagrid/files", fn), np.float32)
+        assert g.size == 35 * n ** 3
+        idx = np.flatnonzero(g).astype(np.int32)
+        out[tag + "_idx"] = idx
+        out[tag + "_val"] = g[idx]
+        out[tag + "_shape"] = np.array([35, n, n, n], np.int32)
+    out["recmap"] = np.array(open(os.path.join(REF, "test/gninagrid/files/recmap")).read())
+    out["ligmap"] = np.array(open(os.path.join(REF, "test/gninagrid/files/ligmap")).read())
+    # files/CC.xyz heavy atoms (hydrogens carry no channel); both carbons type as AliphaticCarbonXSHydrophobe
+    out["cc_xyz"] = np.array([[1.06088, 0.05280, 0.06303], [2.57294, 0.05281, 0.06302]], np.float32)
+    np.savez_compressed(os.path.join(HERE, "gridmaker_golden.npz"), **out)
+
+
+MODELS = ["crossdock_default2018", "dense_1.3", "dense_1.3_PT_KD_3", "crossdock_default2018_KD_4",
+          "all_default_to_default_1.3_1", "default2017"]
+
+
+def cnn_kat(n_poses=6):
+    rec_xyz, rec_t = synth.make_receptor()
+    lig_xyz0, lig_t0 = synth.make_ligand()
+    lig_xyz, offs = synth.make_poses(lig_xyz0, n_poses, seed=11)
+    lig_t = np.tile(lig_t0, n_poses)
+    out = {"rec_xyz": rec_xyz, "rec_types": rec_t, "lig_xyz": lig_xyz, "lig_types": lig_t, "pose_offsets": offs,
+           "models": np.array(MODELS)}
+    for name in MODELS:
+        blob = model_blob.load_model(name)
+        om = pipeline.OracleModel(blob)
+        grids = om.grids(rec_xyz, rec_t, lig_xyz, lig_t, offs)
+        ts = torch.jit.load(os.path.join(REF, "gninasrc/lib/models", name + ".pt"), map_location="cpu")
+        key = name.replace(".", "_")
+        for dt, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+            m = ts.to(dt)
+            with torch.no_grad():
+                zp, za = m(torch.zeros(1, om.n_channels, 48, 48, 48, dtype=dt))
+                gp, ga = m(torch.from_numpy(grids).to(dt))
+            out["%s_zero_logp_%s" % (key, tag)] = zp.numpy()
+            out["%s_zero_aff_%s" % (key, tag)] = za.numpy()
+            out["%s_logp_%s" % (key, tag)] = gp.numpy()
+            out["%s_aff_%s" % (key, tag)] = ga.numpy()
+            out["%s_pose_%s" % (key, tag)] = torch.softmax(gp, 1)[:, 1].numpy()  # torch_model.cpp:189
+        print(key, "pose", out[key + "_pose_f32"], "aff", out[key + "_aff_f32"])
+    np.savez_compressed(os.path.join(HERE, "cnn_kat.npz"), **out)
+
+
+if __name__ == "__main__":
+    sparse_golden()
+    cnn_kat()
