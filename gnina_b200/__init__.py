@@ -1,0 +1,5 @@
+"""gnina_b200 — B200-native CNN-scoring hot path of gnina behind gnina's own scorer interface.
+
+Product code: CUDA kernels + C ABI in csrc/ (libgnina_b200.so), host mirror of the reference interface in
+scorer.py.  Nothing here imports the CPU oracle (oracle/ is test infrastructure)."""
+from .scorer import CNNScorer, usage_error, expand_model_names, builtin_models, PRECISION_FP32, PRECISION_FP16_TC  # noqa: F401

@@ -1,0 +1,73 @@
+"""ctypes binding of libgnina_b200.so — the same C ABI a C++/cgo/JNI host binds (include/gnina_b200.h).
+Fails loudly when the CUDA library is missing or no device is visible: there is NO CPU fallback."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgnina_b200.so")
+_lib = None
+
+SYMBOLS = ["gb_last_error", "gb_version", "gb_initialize_cuda", "gb_device_count", "gb_model_load", "gb_model_load_mem",
+           "gb_model_get_info", "gb_model_release", "gb_model_type_atoms", "gb_cnn_create", "gb_cnn_clone",
+           "gb_cnn_destroy", "gb_cnn_num_models", "gb_cnn_set_option", "gb_cnn_get_option", "gb_cnn_set_receptor",
+           "gb_cnn_score_batch", "gb_cnn_score_batch_models", "gb_cnn_stage_poses", "gb_cnn_run_staged",
+           "gb_cnn_fetch", "gb_cnn_stream", "gb_cnn_kernel_launches", "gb_cnn_voxelize"]
+
+
+class GbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("gnina_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class ModelInfo(C.Structure):
+    _fields_ = [("arch", C.c_int32), ("n_rec_channels", C.c_int32), ("n_lig_channels", C.c_int32),
+                ("grid_points", C.c_int32), ("resolution", C.c_float), ("dimension", C.c_float),
+                ("radius_scaling", C.c_float), ("apply_logistic_loss", C.c_int32), ("skip_softmax", C.c_int32),
+                ("name", C.c_char * 64)]
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("gnina_b200: %s is missing — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    fp, ip, vp = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_void_p
+    L.gb_last_error.restype = C.c_char_p
+    L.gb_version.restype = C.c_char_p
+    L.gb_initialize_cuda.argtypes = [C.c_int]
+    L.gb_model_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.gb_model_load_mem.argtypes = [vp, C.c_size_t, C.c_int, C.POINTER(vp)]
+    L.gb_model_get_info.argtypes = [vp, C.POINTER(ModelInfo)]
+    L.gb_model_release.argtypes = [vp]
+    L.gb_model_release.restype = None
+    L.gb_model_type_atoms.argtypes = [vp, C.c_int, ip, C.c_int, ip, fp]
+    L.gb_cnn_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(vp)]
+    L.gb_cnn_clone.argtypes = [vp, C.POINTER(vp)]
+    L.gb_cnn_destroy.argtypes = [vp]
+    L.gb_cnn_destroy.restype = None
+    L.gb_cnn_num_models.argtypes = [vp]
+    L.gb_cnn_set_option.argtypes = [vp, C.c_char_p, C.c_double]
+    L.gb_cnn_get_option.argtypes = [vp, C.c_char_p]
+    L.gb_cnn_get_option.restype = C.c_double
+    L.gb_cnn_set_receptor.argtypes = [vp, fp, ip, C.c_int]
+    L.gb_cnn_score_batch.argtypes = [vp, fp, ip, ip, C.c_int, fp, fp, fp, fp, fp]
+    L.gb_cnn_score_batch_models.argtypes = [vp, fp, ip, ip, C.c_int, fp, fp, fp, fp]
+    L.gb_cnn_stage_poses.argtypes = [vp, fp, ip, ip, C.c_int, fp]
+    L.gb_cnn_run_staged.argtypes = [vp]
+    L.gb_cnn_fetch.argtypes = [vp, fp, fp, fp, fp]
+    L.gb_cnn_stream.argtypes = [vp]
+    L.gb_cnn_stream.restype = vp
+    L.gb_cnn_kernel_launches.argtypes = [vp]
+    L.gb_cnn_kernel_launches.restype = C.c_int64
+    L.gb_cnn_voxelize.argtypes = [vp, C.c_int, fp, ip, ip, C.c_int, fp, fp]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise GbError(rc, lib().gb_last_error().decode(errors="replace"))

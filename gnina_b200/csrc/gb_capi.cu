@@ -1,0 +1,543 @@
+// C ABI of libgnina_b200.so (see include/gnina_b200.h for the reference interfaces each entry replaces).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <mutex>
+#include "gb_internal.h"
+#include "gb_tc.h"
+
+namespace gb {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& m) { g_last_error = m; }
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  void ensure(size_t n) {
+    if (cap >= n) return;
+    if (p) cudaFree(p);
+    p = nullptr;
+    GB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    cap = n;
+  }
+  ~DevBuf() { if (p) cudaFree(p); }
+};
+template <typename T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  void ensure(size_t n) {
+    if (cap >= n) return;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    GB_CUDA(cudaHostAlloc(&p, std::max<size_t>(n, 1) * sizeof(T), cudaHostAllocDefault));
+    cap = n;
+  }
+  ~PinBuf() { if (p) cudaFreeHost(p); }
+};
+
+// Models that voxelise identically (same type maps and grid metadata) share typed atoms, pose lists and grids.
+struct GridGroup {
+  GridSig sig;
+  TypeMap rec, lig;
+  int n_channels = 0;
+  std::vector<int> model_idx;
+  // receptor on device (typed atoms only, stably sorted by channel)
+  DevBuf<float4> rec_xyzr;
+  DevBuf<int> rec_ch;
+  int n_rec = 0;
+  // staged ligand atoms
+  PinBuf<float4> h_lig_xyzr;
+  PinBuf<int> h_lig_ch, h_lig_off;
+  DevBuf<float4> lig_xyzr;
+  DevBuf<int> lig_ch, lig_off;
+  int max_pose_atoms = 0;
+  // per-chunk workspaces
+  DevBuf<float4> list_xyzr;
+  DevBuf<int> list_ch, list_n;
+  DevBuf<float> grid;       // fp32 reference layout [chunk][C][N^3]
+  TcGridWorkspace tc_grid;  // fused pooled fp16 layout (fast path)
+};
+}  // namespace gb
+
+using namespace gb;
+
+struct gb_model {
+  Model* m;
+};
+
+struct gb_cnn {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<Model*> models;
+  std::vector<std::unique_ptr<GridGroup>> groups;
+  std::vector<int> model_group;
+  int precision = GB_PRECISION_FP32;
+  int max_batch = 0;  // 0 = per-precision default
+  std::vector<float> rec_xyz;
+  std::vector<int32_t> rec_type;
+  // staged poses
+  int n_staged = 0;
+  PinBuf<float> h_centers;
+  DevBuf<float> d_centers;
+  DevBuf<float> d_out3;                  // [chunk][3]
+  DevBuf<float> d_pose, d_aff, d_loss;   // [M][n_staged]
+  DevBuf<float> d_final;                 // [4][n_staged]
+  PinBuf<float> h_final;
+  Fp32Workspace ws32;
+  TcWorkspace ws_tc;
+  int64_t launches = 0;
+  ~gb_cnn() {
+    if (stream) cudaStreamDestroy(stream);
+    for (Model* m : models)
+      if (--m->refs == 0) delete m;
+  }
+};
+
+#define GB_API_BEGIN try {
+#define GB_API_END                          \
+  }                                         \
+  catch (const gb::Error& e) {              \
+    gb::set_last_error(e.what());           \
+    return e.code;                          \
+  }                                         \
+  catch (const std::exception& e) {         \
+    gb::set_last_error(e.what());           \
+    return GB_ERR_INTERNAL;                 \
+  }                                         \
+  return GB_OK;
+
+static void require_device() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    throw Error(GB_ERR_NO_DEVICE, "gnina_b200: no CUDA device visible — this library has no CPU fallback");
+  }
+}
+
+extern "C" {
+
+const char* gb_last_error(void) { return g_last_error.c_str(); }
+const char* gb_version(void) { return "gnina_b200 0.1 (sm_100a)"; }
+
+int gb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int gb_initialize_cuda(int device) {
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return (int)e;
+  if (prop.computeMode == cudaComputeModeProhibited) return -1;
+  return 0;
+}
+
+int gb_model_load_mem(const void* data, size_t nbytes, int device, gb_model** out) {
+  GB_API_BEGIN
+  GB_CHECK(out && data, "null argument");
+  require_device();
+  *out = new gb_model{load_model_from_memory(data, nbytes, device, "<memory>")};
+  GB_API_END
+}
+
+int gb_model_load(const char* path, int device, gb_model** out) {
+  GB_API_BEGIN
+  GB_CHECK(out && path, "null argument");
+  std::ifstream f(path, std::ios::binary);
+  if (!f) throw Error(GB_ERR_USAGE, std::string("Could not open file ") + path);  // cnn_torch_scorer.cpp:86-87
+  std::vector<char> raw((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  require_device();
+  *out = new gb_model{load_model_from_memory(raw.data(), raw.size(), device, path)};
+  GB_API_END
+}
+
+int gb_model_get_info(const gb_model* m, gb_model_info* info) {
+  GB_API_BEGIN
+  GB_CHECK(m && info, "null argument");
+  const Model& M = *m->m;
+  memset(info, 0, sizeof(*info));
+  info->arch = M.arch;
+  info->n_rec_channels = M.rec.n_channels;
+  info->n_lig_channels = M.lig.n_channels;
+  info->grid_points = M.npts;
+  info->resolution = M.resolution;
+  info->dimension = M.dimension;
+  info->radius_scaling = M.radius_scaling;
+  info->apply_logistic_loss = M.apply_logistic_loss;
+  info->skip_softmax = M.skip_softmax;
+  strncpy(info->name, M.name.c_str(), sizeof(info->name) - 1);
+  GB_API_END
+}
+
+void gb_model_release(gb_model* m) {
+  if (!m) return;
+  if (--m->m->refs == 0) delete m->m;
+  delete m;
+}
+
+int gb_model_type_atoms(const gb_model* m, int is_ligand, const int32_t* smina_type, int n, int32_t* channel,
+                        float* radius) {
+  GB_API_BEGIN
+  GB_CHECK(m && smina_type && channel && radius, "null argument");
+  const TypeMap& tm = is_ligand ? m->m->lig : m->m->rec;
+  const int off = is_ligand ? m->m->rec.n_channels : 0;
+  for (int i = 0; i < n; i++) {
+    const int t = smina_type[i];
+    const bool ok = t >= 0 && t < kNumSminaTypes;
+    const int c = ok ? tm.t2c[t] : -1;
+    channel[i] = c < 0 ? -1 : c + off;
+    radius[i] = ok ? kSminaXsRadius[t] : 0.f;
+  }
+  GB_API_END
+}
+
+static void build_groups(gb_cnn* h) {
+  h->groups.clear();
+  h->model_group.assign(h->models.size(), -1);
+  for (size_t i = 0; i < h->models.size(); i++) {
+    const Model& M = *h->models[i];
+    GridSig sig{M.recmap, M.ligmap, M.resolution, M.dimension, M.radius_scaling};
+    int g = -1;
+    for (size_t k = 0; k < h->groups.size(); k++)
+      if (h->groups[k]->sig == sig) g = (int)k;
+    if (g < 0) {
+      auto G = std::make_unique<GridGroup>();
+      G->sig = sig; G->rec = M.rec; G->lig = M.lig; G->n_channels = M.n_channels;
+      h->groups.push_back(std::move(G));
+      g = (int)h->groups.size() - 1;
+    }
+    h->groups[g]->model_idx.push_back((int)i);
+    h->model_group[i] = g;
+  }
+}
+
+int gb_cnn_create(gb_model* const* models, int n_models, int device, gb_cnn** out) {
+  GB_API_BEGIN
+  GB_CHECK(out && models && n_models > 0, "gb_cnn_create needs at least one model");
+  require_device();
+  GB_CUDA(cudaSetDevice(device));
+  std::unique_ptr<gb_cnn> h(new gb_cnn);
+  h->device = device;
+  for (int i = 0; i < n_models; i++) {
+    GB_CHECK(models[i] && models[i]->m->device == device, "model loaded on a different device");
+    models[i]->m->refs++;
+    h->models.push_back(models[i]->m);
+  }
+  GB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  build_groups(h.get());
+  h->precision = GB_PRECISION_FP16_TC;
+  for (Model* m : h->models)
+    if (!tc_supported(*m)) h->precision = GB_PRECISION_FP32;
+  *out = h.release();
+  GB_API_END
+}
+
+int gb_cnn_set_receptor(gb_cnn* h, const float* xyz, const int32_t* smina_type, int n);
+
+int gb_cnn_clone(const gb_cnn* src, gb_cnn** out) {
+  GB_API_BEGIN
+  GB_CHECK(src && out, "null argument");
+  GB_CUDA(cudaSetDevice(src->device));
+  std::unique_ptr<gb_cnn> h(new gb_cnn);
+  h->device = src->device;
+  for (Model* m : src->models) { m->refs++; h->models.push_back(m); }
+  GB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  build_groups(h.get());
+  h->precision = src->precision;
+  h->max_batch = src->max_batch;
+  gb_cnn* raw = h.release();
+  *out = raw;
+  if (!src->rec_type.empty())
+    return gb_cnn_set_receptor(raw, src->rec_xyz.data(), src->rec_type.data(), (int)src->rec_type.size());
+  GB_API_END
+}
+
+void gb_cnn_destroy(gb_cnn* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  delete h;
+}
+
+int gb_cnn_num_models(const gb_cnn* h) { return h ? (int)h->models.size() : 0; }
+
+int gb_cnn_set_option(gb_cnn* h, const char* key, double value) {
+  GB_API_BEGIN
+  GB_CHECK(h && key, "null argument");
+  const std::string k(key);
+  if (k == "precision") {
+    const int p = (int)value;
+    if (p != GB_PRECISION_FP32 && p != GB_PRECISION_FP16_TC) throw Error(GB_ERR_USAGE, "unknown precision");
+    if (p == GB_PRECISION_FP16_TC)
+      for (Model* m : h->models)
+        if (!tc_supported(*m)) throw Error(GB_ERR_USAGE, "model " + m->name + " has no tensor-core path yet");
+    h->precision = p;
+  } else if (k == "max_batch") {
+    GB_CHECK(value >= 0 && value <= 65536, "max_batch out of range");
+    h->max_batch = (int)value;
+  } else {
+    throw Error(GB_ERR_USAGE, "unknown option " + k);
+  }
+  GB_API_END
+}
+
+double gb_cnn_get_option(const gb_cnn* h, const char* key) {
+  if (!h || !key) return NAN;
+  const std::string k(key);
+  if (k == "precision") return h->precision;
+  if (k == "max_batch") return h->max_batch;
+  return NAN;
+}
+
+int gb_cnn_set_receptor(gb_cnn* h, const float* xyz, const int32_t* smina_type, int n) {
+  GB_API_BEGIN
+  GB_CHECK(h && (n == 0 || (xyz && smina_type)) && n >= 0, "bad receptor arguments");
+  GB_CUDA(cudaSetDevice(h->device));
+  h->rec_xyz.assign(xyz, xyz + 3 * (size_t)n);
+  h->rec_type.assign(smina_type, smina_type + n);
+  for (auto& Gp : h->groups) {
+    GridGroup& G = *Gp;
+    // make_coordset (torch_model.cpp:120-142) once; untyped atoms (channel -1: hydrogens) never contribute
+    std::vector<std::vector<int>> by_ch(G.rec.n_channels);
+    for (int i = 0; i < n; i++) {
+      const int t = smina_type[i];
+      if (t < 0 || t >= kNumSminaTypes) continue;
+      const int c = G.rec.t2c[t];
+      if (c >= 0) by_ch[c].push_back(i);
+    }
+    std::vector<float4> a;
+    std::vector<int> ch;
+    for (int c = 0; c < G.rec.n_channels; c++)
+      for (int i : by_ch[c]) {
+        a.push_back(make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2],
+                                kSminaXsRadius[smina_type[i]] * G.sig.radius_scaling));
+        ch.push_back(c);
+      }
+    G.n_rec = (int)a.size();
+    G.rec_xyzr.ensure(a.size());
+    G.rec_ch.ensure(ch.size());
+    if (G.n_rec) {
+      GB_CUDA(cudaMemcpyAsync(G.rec_xyzr.p, a.data(), a.size() * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+      GB_CUDA(cudaMemcpyAsync(G.rec_ch.p, ch.data(), ch.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      GB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    if (h->precision == GB_PRECISION_FP16_TC) G.tc_grid.receptor_changed();
+  }
+  GB_API_END
+}
+
+int gb_cnn_stage_poses(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, const int32_t* pose_offsets,
+                       int n_poses, const float* centers) {
+  GB_API_BEGIN
+  GB_CHECK(h && n_poses >= 0 && (n_poses == 0 || (lig_xyz && lig_type && pose_offsets)), "bad pose arguments");
+  GB_CUDA(cudaSetDevice(h->device));
+  // the previous batch may still be reading the pinned staging buffers
+  GB_CUDA(cudaStreamSynchronize(h->stream));
+  h->n_staged = n_poses;
+  if (n_poses == 0) return GB_OK;
+  const int total = pose_offsets[n_poses];
+  GB_CHECK(pose_offsets[0] == 0 && total >= 0, "pose_offsets must start at 0");
+  h->h_centers.ensure(3 * (size_t)n_poses);
+  h->d_centers.ensure(3 * (size_t)n_poses);
+  for (int p = 0; p < n_poses; p++) {
+    const int b = pose_offsets[p], e = pose_offsets[p + 1];
+    GB_CHECK(e >= b, "pose_offsets must be non-decreasing");
+    if (centers) {
+      for (int d = 0; d < 3; d++) h->h_centers.p[3 * p + d] = centers[3 * p + d];
+    } else {
+      // CoordinateSet::center(): float mean over ALL ligand atoms passed (torch_model.cpp:163-166)
+      float sx = 0, sy = 0, sz = 0;
+      for (int i = b; i < e; i++) { sx += lig_xyz[3 * i]; sy += lig_xyz[3 * i + 1]; sz += lig_xyz[3 * i + 2]; }
+      const int cnt = e - b;
+      if (cnt > 0) { sx /= cnt; sy /= cnt; sz /= cnt; }
+      h->h_centers.p[3 * p] = sx; h->h_centers.p[3 * p + 1] = sy; h->h_centers.p[3 * p + 2] = sz;
+    }
+  }
+  GB_CUDA(cudaMemcpyAsync(h->d_centers.p, h->h_centers.p, 3 * (size_t)n_poses * sizeof(float), cudaMemcpyHostToDevice,
+                          h->stream));
+  for (auto& Gp : h->groups) {
+    GridGroup& G = *Gp;
+    G.h_lig_xyzr.ensure((size_t)total);
+    G.h_lig_ch.ensure((size_t)total);
+    G.h_lig_off.ensure((size_t)n_poses + 1);
+    const int nrc = G.rec.n_channels, nlc = G.lig.n_channels;
+    int w = 0, maxp = 0;
+    int cnt[64], start[64];
+    for (int p = 0; p < n_poses; p++) {
+      const int b = pose_offsets[p], e = pose_offsets[p + 1];
+      G.h_lig_off.p[p] = w;
+      // counting sort by channel (stable): keeps the per-channel summation order of the reference
+      for (int c = 0; c < nlc; c++) cnt[c] = 0;
+      for (int i = b; i < e; i++) {
+        const int t = lig_type[i];
+        const int c = (t >= 0 && t < kNumSminaTypes) ? G.lig.t2c[t] : -1;
+        if (c >= 0) cnt[c]++;
+      }
+      int s = w;
+      for (int c = 0; c < nlc; c++) { start[c] = s; s += cnt[c]; }
+      for (int i = b; i < e; i++) {
+        const int t = lig_type[i];
+        const int c = (t >= 0 && t < kNumSminaTypes) ? G.lig.t2c[t] : -1;
+        if (c < 0) continue;
+        const int dst = start[c]++;
+        G.h_lig_xyzr.p[dst] = make_float4(lig_xyz[3 * i], lig_xyz[3 * i + 1], lig_xyz[3 * i + 2],
+                                          kSminaXsRadius[t] * G.sig.radius_scaling);
+        G.h_lig_ch.p[dst] = nrc + c;
+      }
+      maxp = std::max(maxp, s - w);
+      w = s;
+    }
+    G.h_lig_off.p[n_poses] = w;
+    G.max_pose_atoms = maxp;
+    G.lig_xyzr.ensure((size_t)total);
+    G.lig_ch.ensure((size_t)total);
+    G.lig_off.ensure((size_t)n_poses + 1);
+    if (w) {
+      GB_CUDA(cudaMemcpyAsync(G.lig_xyzr.p, G.h_lig_xyzr.p, (size_t)w * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+      GB_CUDA(cudaMemcpyAsync(G.lig_ch.p, G.h_lig_ch.p, (size_t)w * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    }
+    GB_CUDA(cudaMemcpyAsync(G.lig_off.p, G.h_lig_off.p, ((size_t)n_poses + 1) * sizeof(int), cudaMemcpyHostToDevice,
+                            h->stream));
+  }
+  GB_API_END
+}
+
+static int chunk_size(const gb_cnn* h) {
+  if (h->max_batch > 0) return h->max_batch;
+  return h->precision == GB_PRECISION_FP32 ? 16 : 512;
+}
+
+// voxelise poses [p0, p0+nb) of group G into the fp32 reference layout
+static void voxelize_chunk_f32(gb_cnn* h, GridGroup& G, int p0, int nb) {
+  const int cap = G.n_rec + G.max_pose_atoms;
+  G.list_xyzr.ensure((size_t)nb * std::max(cap, 1));
+  G.list_ch.ensure((size_t)nb * std::max(cap, 1));
+  G.list_n.ensure(nb);
+  const int npts = (int)std::lround(G.sig.dimension / G.sig.resolution) + 1;
+  G.grid.ensure((size_t)nb * G.n_channels * npts * npts * npts);
+  launch_build_pose_lists(G.rec_xyzr.p, G.rec_ch.p, G.n_rec, G.lig_xyzr.p, G.lig_ch.p, G.lig_off.p + p0,
+                          h->d_centers.p + 3 * (size_t)p0, nb, G.sig.dimension / 2.f, std::max(cap, 1), G.list_xyzr.p,
+                          G.list_ch.p, G.list_n.p, h->stream);
+  launch_voxelize_f32(G.list_xyzr.p, G.list_ch.p, G.list_n.p, std::max(cap, 1), h->d_centers.p + 3 * (size_t)p0, nb,
+                      G.n_channels, npts, G.sig.resolution, G.sig.dimension, G.grid.p, h->stream);
+  h->launches += 2;
+}
+
+int gb_cnn_run_staged(gb_cnn* h) {
+  GB_API_BEGIN
+  GB_CHECK(h, "null handle");
+  GB_CUDA(cudaSetDevice(h->device));
+  const int n = h->n_staged, M = (int)h->models.size();
+  if (n == 0) return GB_OK;
+  h->d_pose.ensure((size_t)M * n);
+  h->d_aff.ensure((size_t)M * n);
+  h->d_loss.ensure((size_t)M * n);
+  h->d_final.ensure(4 * (size_t)n);
+  const int chunk = chunk_size(h);
+  h->d_out3.ensure(3 * (size_t)chunk);
+  for (int p0 = 0; p0 < n; p0 += chunk) {
+    const int nb = std::min(chunk, n - p0);
+    for (auto& Gp : h->groups) {
+      GridGroup& G = *Gp;
+      if (h->precision == GB_PRECISION_FP32) {
+        voxelize_chunk_f32(h, G, p0, nb);
+        for (int mi : G.model_idx) {
+          const Model& Mo = *h->models[mi];
+          h->launches += forward_fp32(Mo, G.grid.p, nb, h->ws32, h->d_out3.p, h->stream);
+          launch_head_post(h->d_out3.p, nb, Mo.skip_softmax, Mo.apply_logistic_loss, h->d_pose.p + (size_t)mi * n + p0,
+                           h->d_aff.p + (size_t)mi * n + p0, h->d_loss.p + (size_t)mi * n + p0, h->stream);
+          h->launches++;
+        }
+      } else {
+        TcPoseBatch pb{G.rec_xyzr.p, G.rec_ch.p, G.n_rec, G.lig_xyzr.p, G.lig_ch.p, G.lig_off.p + p0,
+                       h->d_centers.p + 3 * (size_t)p0, nb, G.max_pose_atoms, G.n_channels, G.rec.n_channels,
+                       G.sig.resolution, G.sig.dimension};
+        for (int mi : G.model_idx) {
+          const Model& Mo = *h->models[mi];
+          h->launches += tc_forward(Mo, pb, G.tc_grid, h->ws_tc, h->d_out3.p, h->stream);
+          launch_head_post(h->d_out3.p, nb, Mo.skip_softmax, Mo.apply_logistic_loss, h->d_pose.p + (size_t)mi * n + p0,
+                           h->d_aff.p + (size_t)mi * n + p0, h->d_loss.p + (size_t)mi * n + p0, h->stream);
+          h->launches++;
+        }
+        G.tc_grid.batch_done();
+      }
+    }
+  }
+  launch_ensemble(h->d_pose.p, h->d_aff.p, h->d_loss.p, M, n, n, h->d_final.p, h->d_final.p + n, h->d_final.p + 2 * (size_t)n,
+                  h->d_final.p + 3 * (size_t)n, h->stream);
+  h->launches++;
+  GB_CUDA(cudaGetLastError());
+  GB_API_END
+}
+
+int gb_cnn_fetch(gb_cnn* h, float* score, float* affinity, float* loss, float* variance) {
+  GB_API_BEGIN
+  GB_CHECK(h, "null handle");
+  GB_CUDA(cudaSetDevice(h->device));
+  const int n = h->n_staged;
+  if (n == 0) return GB_OK;
+  h->h_final.ensure(4 * (size_t)n);
+  GB_CUDA(cudaMemcpyAsync(h->h_final.p, h->d_final.p, 4 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  GB_CUDA(cudaStreamSynchronize(h->stream));
+  float* dst[4] = {score, affinity, loss, variance};
+  for (int q = 0; q < 4; q++)
+    if (dst[q]) memcpy(dst[q], h->h_final.p + (size_t)q * n, (size_t)n * sizeof(float));
+  GB_API_END
+}
+
+int gb_cnn_score_batch(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, const int32_t* pose_offsets,
+                       int n_poses, const float* centers, float* score, float* affinity, float* loss,
+                       float* variance) {
+  int rc = gb_cnn_stage_poses(h, lig_xyz, lig_type, pose_offsets, n_poses, centers);
+  if (rc) return rc;
+  rc = gb_cnn_run_staged(h);
+  if (rc) return rc;
+  return gb_cnn_fetch(h, score, affinity, loss, variance);
+}
+
+int gb_cnn_score_batch_models(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, const int32_t* pose_offsets,
+                              int n_poses, const float* centers, float* pose, float* affinity, float* loss) {
+  int rc = gb_cnn_stage_poses(h, lig_xyz, lig_type, pose_offsets, n_poses, centers);
+  if (rc) return rc;
+  rc = gb_cnn_run_staged(h);
+  if (rc) return rc;
+  GB_API_BEGIN
+  const size_t cnt = (size_t)h->models.size() * n_poses;
+  if (cnt) {
+    if (pose) GB_CUDA(cudaMemcpyAsync(pose, h->d_pose.p, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (affinity) GB_CUDA(cudaMemcpyAsync(affinity, h->d_aff.p, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (loss) GB_CUDA(cudaMemcpyAsync(loss, h->d_loss.p, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  }
+  GB_CUDA(cudaStreamSynchronize(h->stream));
+  GB_API_END
+}
+
+void* gb_cnn_stream(gb_cnn* h) { return h ? (void*)h->stream : nullptr; }
+int64_t gb_cnn_kernel_launches(gb_cnn* h) { return h ? h->launches : 0; }
+
+int gb_cnn_voxelize(gb_cnn* h, int model_index, const float* lig_xyz, const int32_t* lig_type,
+                    const int32_t* pose_offsets, int n_poses, const float* centers, float* grid_out) {
+  int rc = gb_cnn_stage_poses(h, lig_xyz, lig_type, pose_offsets, n_poses, centers);
+  if (rc) return rc;
+  GB_API_BEGIN
+  GB_CHECK(model_index >= 0 && model_index < (int)h->models.size() && grid_out, "bad voxelize arguments");
+  GridGroup& G = *h->groups[h->model_group[model_index]];
+  const int npts = h->models[model_index]->npts;
+  const size_t per = (size_t)G.n_channels * npts * npts * npts;
+  const int chunk = 8;
+  for (int p0 = 0; p0 < n_poses; p0 += chunk) {
+    const int nb = std::min(chunk, n_poses - p0);
+    voxelize_chunk_f32(h, G, p0, nb);
+    GB_CUDA(cudaMemcpyAsync(grid_out + per * p0, G.grid.p, per * nb * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    GB_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  GB_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,333 @@
+// fp32 validation path of the CNN forward (N1/N2/N3 of SURVEY.md §8a): plain CUDA-core kernels on NCDHW fp32
+// tensors, numerically equivalent to the TorchScript graphs the reference runs at gninasrc/lib/torch_model.cpp:185
+// up to fp32 summation order.  It exists to (a) pin the fast tensor-core path, (b) provide a <=1e-4 validation mode.
+#include "gb_internal.h"
+
+namespace gb {
+
+void Fp32Workspace::ensure(int i, size_t n) {
+  if (cap[i] >= n) return;
+  if (buf[i]) cudaFree(buf[i]);
+  GB_CUDA(cudaMalloc(&buf[i], n * sizeof(float)));
+  cap[i] = n;
+}
+void Fp32Workspace::ensure_feat(size_t n) {
+  if (feat_cap >= n) return;
+  if (feat) cudaFree(feat);
+  GB_CUDA(cudaMalloc(&feat, n * sizeof(float)));
+  feat_cap = n;
+}
+Fp32Workspace::~Fp32Workspace() {
+  for (auto p : buf)
+    if (p) cudaFree(p);
+  if (feat) cudaFree(feat);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Direct 3D convolution, stride 1, "same" zero padding (KS=3,pad 1 | KS=1,pad 0), optional per-input-channel
+// affine (eval-mode BatchNorm folded to scale/shift, applied to in-bounds inputs only, so padded taps stay 0
+// exactly like BN -> conv(pad=1) in the dense blocks), bias + optional ReLU.
+// in : [B][in_ctot][D][D][D]  (first Cin channels are read)
+// out: [B][out_ctot][D][D][D] (channels [out_coff, out_coff+Cout) are written)
+// w  : [Cin][KS^3][Cout]
+// CTA = 8x8x8 output voxels x COT output channels; input channels streamed in chunks of CIC through smem.
+template <int KS, int COT>
+__global__ void __launch_bounds__(512) conv3d_f32_kernel(const float* __restrict__ in, int in_ctot, int Cin,
+                                                         const float* __restrict__ w, const float* __restrict__ bias,
+                                                         const float* __restrict__ bn_scale,
+                                                         const float* __restrict__ bn_shift, float* __restrict__ out,
+                                                         int out_ctot, int out_coff, int Cout, int D, int relu) {
+  constexpr int CIC = 4;
+  constexpr int H = KS / 2;
+  constexpr int TW = 8 + 2 * H;
+  constexpr int K3 = KS * KS * KS;
+  __shared__ float s_in[CIC][TW][TW][TW];
+  __shared__ __align__(16) float s_w[CIC][K3][COT];
+  const int tiles = (D + 7) / 8;
+  const int t = blockIdx.x;
+  const int ti = t / (tiles * tiles), tj = (t / tiles) % tiles, tk = t % tiles;
+  const int co0 = blockIdx.y * COT;
+  const int b = blockIdx.z;
+  const int li = threadIdx.x >> 6, lj = (threadIdx.x >> 3) & 7, lk = threadIdx.x & 7;
+  const int i = ti * 8 + li, j = tj * 8 + lj, k = tk * 8 + lk;
+  const size_t vol = (size_t)D * D * D;
+  const float* inb = in + (size_t)b * in_ctot * vol;
+  float acc[COT];
+#pragma unroll
+  for (int c = 0; c < COT; c++) acc[c] = 0.f;
+
+  for (int c0 = 0; c0 < Cin; c0 += CIC) {
+    // stage input tile (with halo) and weight slice
+    for (int e = threadIdx.x; e < CIC * TW * TW * TW; e += 512) {
+      const int ci = e / (TW * TW * TW);
+      int r = e % (TW * TW * TW);
+      const int a = r / (TW * TW), bb = (r / TW) % TW, cc = r % TW;
+      const int gi = ti * 8 + a - H, gj = tj * 8 + bb - H, gk = tk * 8 + cc - H;
+      float v = 0.f;
+      if (c0 + ci < Cin && gi >= 0 && gi < D && gj >= 0 && gj < D && gk >= 0 && gk < D) {
+        v = inb[(size_t)(c0 + ci) * vol + ((size_t)gi * D + gj) * D + gk];
+        if (bn_scale) v = fmaf(v, bn_scale[c0 + ci], bn_shift[c0 + ci]);
+      }
+      (&s_in[0][0][0][0])[e] = v;
+    }
+    for (int e = threadIdx.x; e < CIC * K3 * COT; e += 512) {
+      const int ci = e / (K3 * COT);
+      const int r = e % (K3 * COT);
+      const int tap = r / COT, co = r % COT;
+      float v = 0.f;
+      if (c0 + ci < Cin && co0 + co < Cout) v = w[((size_t)(c0 + ci) * K3 + tap) * Cout + co0 + co];
+      s_w[ci][tap][co] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ci = 0; ci < CIC; ci++) {
+#pragma unroll
+      for (int a = 0; a < KS; a++)
+#pragma unroll
+        for (int bb = 0; bb < KS; bb++)
+#pragma unroll
+          for (int cc = 0; cc < KS; cc++) {
+            const float v = s_in[ci][li + a][lj + bb][lk + cc];
+            const float4* wr = reinterpret_cast<const float4*>(&s_w[ci][(a * KS + bb) * KS + cc][0]);
+#pragma unroll
+            for (int q = 0; q < COT / 4; q++) {
+              const float4 ww = wr[q];
+              acc[4 * q + 0] = fmaf(v, ww.x, acc[4 * q + 0]);
+              acc[4 * q + 1] = fmaf(v, ww.y, acc[4 * q + 1]);
+              acc[4 * q + 2] = fmaf(v, ww.z, acc[4 * q + 2]);
+              acc[4 * q + 3] = fmaf(v, ww.w, acc[4 * q + 3]);
+            }
+          }
+    }
+    __syncthreads();
+  }
+  if (i < D && j < D && k < D) {
+    float* ob = out + ((size_t)b * out_ctot + out_coff + co0) * vol + ((size_t)i * D + j) * D + k;
+#pragma unroll
+    for (int c = 0; c < COT; c++) {
+      if (co0 + c < Cout) {
+        float v = acc[c] + bias[co0 + c];
+        if (relu) v = fmaxf(v, 0.f);
+        ob[(size_t)c * vol] = v;
+      }
+    }
+  }
+}
+
+static int launch_conv(const ConvF32& c, const float* in, int in_ctot, float* out, int out_ctot, int out_coff, int D,
+                       int B, bool relu, cudaStream_t s) {
+  const int tiles = (D + 7) / 8;
+  const int cot = (c.cout % 32 == 0) ? 32 : 16;
+  dim3 g(tiles * tiles * tiles, (c.cout + cot - 1) / cot, B);
+#define GB_LAUNCH(KS, COT)                                                                                        \
+  conv3d_f32_kernel<KS, COT><<<g, 512, 0, s>>>(in, in_ctot, c.cin, c.w, c.bias, c.bn_scale, c.bn_shift, out, out_ctot, \
+                                               out_coff, c.cout, D, relu ? 1 : 0)
+  if (c.ks == 3 && cot == 32) GB_LAUNCH(3, 32);
+  else if (c.ks == 3) GB_LAUNCH(3, 16);
+  else if (c.ks == 1 && cot == 32) GB_LAUNCH(1, 32);
+  else if (c.ks == 1) GB_LAUNCH(1, 16);
+  else throw Error(GB_ERR_INTERNAL, "unsupported conv kernel size");
+#undef GB_LAUNCH
+  return 1;
+}
+
+// 2x2x2 stride-2 pooling (avg: default2018; max: default2017 / dense), channel-strided in/out
+__global__ void pool2_f32_kernel(const float* __restrict__ in, int in_ctot, float* __restrict__ out, int out_ctot, int C,
+                                 int Din, int is_max, size_t total) {
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int Do = Din / 2;
+  size_t r = idx;
+  const int k = r % Do; r /= Do;
+  const int j = r % Do; r /= Do;
+  const int i = r % Do; r /= Do;
+  const int c = r % C;
+  const int b = r / C;
+  const float* p = in + (((size_t)b * in_ctot + c) * Din + 2 * i) * Din * Din + (size_t)(2 * j) * Din + 2 * k;
+  float v = is_max ? -INFINITY : 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int bb = 0; bb < 2; bb++)
+#pragma unroll
+      for (int cc = 0; cc < 2; cc++) {
+        const float x = p[(size_t)a * Din * Din + bb * Din + cc];
+        v = is_max ? fmaxf(v, x) : v + x;
+      }
+  if (!is_max) v *= 0.125f;
+  out[(((size_t)b * out_ctot + c) * Do + i) * Do * Do + (size_t)j * Do + k] = v;
+}
+
+static int launch_pool(const float* in, int in_ctot, float* out, int out_ctot, int C, int Din, int B, bool is_max,
+                       cudaStream_t s) {
+  const int Do = Din / 2;
+  const size_t total = (size_t)B * C * Do * Do * Do;
+  pool2_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, in_ctot, out, out_ctot, C, Din, is_max ? 1 : 0,
+                                                                    total);
+  return 1;
+}
+
+// global max over the D^3 volume: in [B][C][vol] -> feat [B][C]
+__global__ void global_max_kernel(const float* __restrict__ in, float* __restrict__ feat, int vol) {
+  const float* p = in + (size_t)blockIdx.x * vol;
+  float v = -INFINITY;
+  for (int e = threadIdx.x; e < vol; e += 32) v = fmaxf(v, p[e]);
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if (threadIdx.x == 0) feat[blockIdx.x] = v;
+}
+
+// heads: feat [B][F] x fc_w [3][F] + fc_b -> out3 [B][3]
+__global__ void __launch_bounds__(256) fc3_kernel(const float* __restrict__ feat, const float* __restrict__ w,
+                                                  const float* __restrict__ bias, int F, float* __restrict__ out3) {
+  __shared__ float red[3][8];
+  const float* f = feat + (size_t)blockIdx.x * F;
+  float a0 = 0, a1 = 0, a2 = 0;
+  for (int e = threadIdx.x; e < F; e += 256) {
+    const float x = f[e];
+    a0 = fmaf(x, w[e], a0);
+    a1 = fmaf(x, w[F + e], a1);
+    a2 = fmaf(x, w[2 * (size_t)F + e], a2);
+  }
+  for (int o = 16; o; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][warp] = a0; red[1][warp] = a1; red[2][warp] = a2; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float v = bias[threadIdx.x];
+    for (int q = 0; q < 8; q++) v += red[threadIdx.x][q];
+    out3[(size_t)blockIdx.x * 3 + threadIdx.x] = v;
+  }
+}
+
+// torch_model.cpp:188-195.  The TorchScript module returns log_softmax(logits); softmax(log_softmax(z)) ==
+// softmax(z), so pose = softmax(z)[1]; with skip_softmax the reference reads the module output [0,1] itself,
+// i.e. log_softmax(z)[1].  loss = CE(module output, label 1) = -log_softmax(z)[1]; with apply_logistic_loss
+// the reference takes -log(module output[0,1]) = -log(log_softmax(z)[1]).
+__global__ void head_post_kernel(const float* __restrict__ out3, int B, int skip_softmax, int logistic,
+                                 float* __restrict__ pose, float* __restrict__ aff, float* __restrict__ loss) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float z0 = out3[3 * b], z1 = out3[3 * b + 1];
+  const float m = fmaxf(z0, z1);
+  const float lse = m + logf(expf(z0 - m) + expf(z1 - m));
+  const float lp1 = z1 - lse;
+  pose[b] = skip_softmax ? lp1 : expf(lp1);
+  aff[b] = out3[3 * b + 2];
+  loss[b] = logistic ? -logf(lp1) : -lp1;
+}
+
+void launch_head_post(const float* out3, int B, bool skip_softmax, bool logistic, float* pose, float* aff, float* loss,
+                      cudaStream_t s) {
+  if (B <= 0) return;
+  head_post_kernel<<<(B + 127) / 128, 128, 0, s>>>(out3, B, skip_softmax, logistic, pose, aff, loss);
+}
+
+// CNNTorchScorer::score accumulation, cnn_torch_scorer.cpp:117-192: score accumulates in double, affinity/loss in
+// float in model order; variance = population variance of the per-model affinities around the float mean.
+__global__ void ensemble_kernel(const float* __restrict__ pose, const float* __restrict__ aff,
+                                const float* __restrict__ loss, int M, int B, int stride, float* __restrict__ o_score,
+                                float* __restrict__ o_aff, float* __restrict__ o_loss, float* __restrict__ o_var) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double sc = 0.0;
+  float a = 0.f, l = 0.f;
+  for (int m = 0; m < M; m++) {
+    sc += (double)pose[(size_t)m * stride + b];
+    a += aff[(size_t)m * stride + b];
+    l += loss[(size_t)m * stride + b];
+  }
+  a /= (float)M;
+  l /= (float)M;
+  float var = 0.f;
+  if (M > 1) {
+    float sum = 0.f;
+    for (int m = 0; m < M; m++) {
+      float d = a - aff[(size_t)m * stride + b];
+      sum += d * d;
+    }
+    var = sum / (float)M;
+  }
+  o_score[b] = (float)(sc / M);
+  o_aff[b] = a;
+  o_loss[b] = l;
+  o_var[b] = var;
+}
+
+void launch_ensemble(const float* pose, const float* aff, const float* loss, int M, int B, int stride, float* o_score,
+                     float* o_aff, float* o_loss, float* o_var, cudaStream_t s) {
+  if (B <= 0) return;
+  ensemble_kernel<<<(B + 127) / 128, 128, 0, s>>>(pose, aff, loss, M, B, stride, o_score, o_aff, o_loss, o_var);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+int forward_fp32(const Model& m, const float* grid, int B, Fp32Workspace& ws, float* out3, cudaStream_t s) {
+  int launches = 0;
+  const int C = m.n_channels;
+  GB_CHECK(m.npts == 48, "CNN graphs expect a 48^3 grid");
+  auto conv = [&](const std::string& k) -> const ConvF32& {
+    auto it = m.convs.find(k);
+    if (it == m.convs.end()) throw Error(GB_ERR_INTERNAL, "missing conv " + k);
+    return it->second;
+  };
+  const size_t v24 = 24 * 24 * 24, v12 = 12 * 12 * 12, v6 = 6 * 6 * 6;
+  const float* feat = nullptr;
+  if (m.arch == GB_ARCH_DEFAULT2018) {
+    ws.ensure(0, (size_t)B * 32 * v24);
+    ws.ensure(1, (size_t)B * 32 * v24);
+    launches += launch_pool(grid, C, ws.buf[0], C, C, 48, B, false, s);                       // [B][28][24^3]
+    launches += launch_conv(conv("unit1_conv"), ws.buf[0], C, ws.buf[1], 32, 0, 24, B, true, s);
+    launches += launch_conv(conv("unit2_conv"), ws.buf[1], 32, ws.buf[0], 32, 0, 24, B, true, s);
+    launches += launch_pool(ws.buf[0], 32, ws.buf[1], 32, 32, 24, B, false, s);               // [B][32][12^3]
+    launches += launch_conv(conv("unit3_conv"), ws.buf[1], 32, ws.buf[0], 64, 0, 12, B, true, s);
+    launches += launch_conv(conv("unit4_conv"), ws.buf[0], 64, ws.buf[1], 64, 0, 12, B, true, s);
+    launches += launch_pool(ws.buf[1], 64, ws.buf[0], 64, 64, 12, B, false, s);               // [B][64][6^3]
+    launches += launch_conv(conv("unit5_conv"), ws.buf[0], 64, ws.buf[1], 128, 0, 6, B, true, s);
+    feat = ws.buf[1];  // NCDHW flatten == view(-1, 27648)
+  } else if (m.arch == GB_ARCH_DEFAULT2017) {
+    ws.ensure(0, (size_t)B * 35 * v24);
+    ws.ensure(1, (size_t)B * 32 * v24);
+    launches += launch_pool(grid, C, ws.buf[0], C, C, 48, B, true, s);
+    launches += launch_conv(conv("unit1_conv1"), ws.buf[0], C, ws.buf[1], 32, 0, 24, B, true, s);
+    launches += launch_pool(ws.buf[1], 32, ws.buf[0], 32, 32, 24, B, true, s);
+    launches += launch_conv(conv("unit2_conv1"), ws.buf[0], 32, ws.buf[1], 64, 0, 12, B, true, s);
+    launches += launch_pool(ws.buf[1], 64, ws.buf[0], 64, 64, 12, B, true, s);
+    launches += launch_conv(conv("unit3_conv1"), ws.buf[0], 64, ws.buf[1], 128, 0, 6, B, true, s);
+    feat = ws.buf[1];
+  } else {
+    // dense: block buffers hold the running concatenation; each BN->conv3->ReLU layer appends 16 channels
+    ws.ensure(0, (size_t)B * 28 * v24);
+    ws.ensure(1, (size_t)B * 96 * v24);
+    ws.ensure(2, (size_t)B * 96 * v24);
+    launches += launch_pool(grid, C, ws.buf[0], C, C, 48, B, true, s);
+    launches += launch_conv(conv("data_enc_init_conv"), ws.buf[0], C, ws.buf[1], 96, 0, 24, B, true, s);
+    auto block = [&](int L, float* buf, int c0, int D) {
+      for (int i = 0; i < 4; i++) {
+        const ConvF32& c = conv("dense_block_" + std::to_string(L) + ".data_enc_level" + std::to_string(L) + "_conv" +
+                                std::to_string(i));
+        launches += launch_conv(c, buf, c0 + 64, buf, c0 + 64, c0 + 16 * i, D, B, true, s);
+      }
+    };
+    block(0, ws.buf[1], 32, 24);                                                                // [B][96][24^3]
+    launches += launch_conv(conv("data_enc_level0_bottleneck"), ws.buf[1], 96, ws.buf[2], 96, 0, 24, B, true, s);
+    // pool -> first 96 channels of the level-1 block buffer [B][160][12^3]
+    launches += launch_pool(ws.buf[2], 96, ws.buf[1], 160, 96, 24, B, true, s);
+    block(1, ws.buf[1], 96, 12);
+    launches += launch_conv(conv("data_enc_level1_bottleneck"), ws.buf[1], 160, ws.buf[2], 160, 0, 12, B, true, s);
+    launches += launch_pool(ws.buf[2], 160, ws.buf[1], 224, 160, 12, B, true, s);              // [B][224][6^3]
+    block(2, ws.buf[1], 160, 6);
+    ws.ensure_feat((size_t)B * 224);
+    global_max_kernel<<<B * 224, 32, 0, s>>>(ws.buf[1], ws.feat, (int)v6);
+    launches++;
+    feat = ws.feat;
+  }
+  (void)v12;
+  fc3_kernel<<<B, 256, 0, s>>>(feat, m.fc_w, m.fc_b, m.fc_features, out3);
+  launches++;
+  return launches;
+}
+
+}  // namespace gb

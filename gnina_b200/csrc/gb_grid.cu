@@ -1,0 +1,179 @@
+// Voxeliser, fp32 validation layout.  Replaces libmolgrid::GridMaker::forward as called at
+// gninasrc/lib/torch_model.cpp:181 (and the torch::zeros memset at :179): one launch voxelises a whole batch of
+// poses into float[B][C][N][N][N] (z fastest), every voxel written exactly once (no memset, no atomics).
+//
+// Two kernels:
+//  build_pose_lists : per pose, ordered compaction of the (channel-sorted) receptor atoms whose support can touch
+//                     the pose's grid box, followed by the pose's ligand atoms -> a channel-sorted atom list.
+//  voxelize_f32     : one CTA per (8x8x8-voxel tile, pose); ordered compaction of the pose list against the tile,
+//                     then each thread sums its voxel channel by channel (lists are channel-sorted, so a running
+//                     accumulator is flushed whenever the channel advances; empty channels get explicit zeros).
+// Arithmetic follows oracle/gridmaker_ref.c operation by operation (no FMA contraction) so that the validation
+// grid agrees with the oracle to a few ulp.
+#include "gb_internal.h"
+
+namespace gb {
+
+__device__ __forceinline__ int block_ordered_slot(bool pred, int* s_warp_counts, int& total) {
+  // returns the position of this thread's element among all threads with pred (ordered by tid), and the total
+  const unsigned mask = __ballot_sync(0xffffffffu, pred);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  if (lane == 0) s_warp_counts[warp] = __popc(mask);
+  __syncthreads();
+  int base = 0, tot = 0;
+  for (int w = 0; w < nwarps; w++) {
+    int c = s_warp_counts[w];
+    if (w < warp) base += c;
+    tot += c;
+  }
+  __syncthreads();
+  total = tot;
+  return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+__global__ void __launch_bounds__(256) build_pose_lists_kernel(const float4* __restrict__ rec_xyzr,
+                                                               const int* __restrict__ rec_ch, int n_rec,
+                                                               const float4* __restrict__ lig_xyzr,
+                                                               const int* __restrict__ lig_ch,
+                                                               const int* __restrict__ lig_off,
+                                                               const float* __restrict__ centers, float half_dim,
+                                                               int cap, float4* __restrict__ list_xyzr,
+                                                               int* __restrict__ list_ch, int* __restrict__ list_n) {
+  __shared__ int s_counts[8];
+  const int p = blockIdx.x;
+  const float cx = centers[3 * p], cy = centers[3 * p + 1], cz = centers[3 * p + 2];
+  float4* out_a = list_xyzr + (size_t)p * cap;
+  int* out_c = list_ch + (size_t)p * cap;
+  int n_out = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    const float4* src = pass == 0 ? rec_xyzr : lig_xyzr;
+    const int* srcc = pass == 0 ? rec_ch : lig_ch;
+    const int b = pass == 0 ? 0 : lig_off[p], e = pass == 0 ? n_rec : lig_off[p + 1];
+    for (int base = b; base < e; base += blockDim.x) {
+      const int i = base + threadIdx.x;
+      bool keep = false;
+      float4 a = make_float4(0, 0, 0, 0);
+      int ch = 0;
+      if (i < e) {
+        a = src[i];
+        ch = srcc[i];
+        const float reach = half_dim + 1.5f * a.w;
+        keep = fabsf(a.x - cx) <= reach && fabsf(a.y - cy) <= reach && fabsf(a.z - cz) <= reach;
+      }
+      int tot;
+      const int slot = block_ordered_slot(keep, s_counts, tot);
+      if (keep && n_out + slot < cap) {
+        out_a[n_out + slot] = a;
+        out_c[n_out + slot] = ch;
+      }
+      n_out += tot;
+    }
+  }
+  if (threadIdx.x == 0) list_n[p] = n_out < cap ? n_out : cap;
+}
+
+void launch_build_pose_lists(const float4* rec_xyzr, const int* rec_ch, int n_rec, const float4* lig_xyzr,
+                             const int* lig_ch, const int* lig_off, const float* centers, int n_poses, float half_dim,
+                             int cap, float4* list_xyzr, int* list_ch, int* list_n, cudaStream_t s) {
+  if (n_poses <= 0) return;
+  build_pose_lists_kernel<<<n_poses, 256, 0, s>>>(rec_xyzr, rec_ch, n_rec, lig_xyzr, lig_ch, lig_off, centers, half_dim,
+                                                  cap, list_xyzr, list_ch, list_n);
+}
+
+__device__ __forceinline__ float density_exact(float dx, float dy, float dz, float ar) {
+  // oracle/gridmaker_ref.c:density — libmolgrid GridMaker::calc_point, G = 1, final multiple 1.5
+  const float rsq = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+  const float dist = sqrtf(rsq);
+  if (dist >= __fmul_rn(ar, 1.5f)) return 0.f;
+  if (dist <= ar) return expf(__fdiv_rn(__fmul_rn(__fmul_rn(-2.f, dist), dist), __fmul_rn(ar, ar)));
+  const float e2 = 0.13533528323661270f;  // expf(-2)
+  const float A = 4.f * e2, B = -12.f * e2, C = 9.f * e2;
+  const float dr = __fdiv_rn(dist, ar);
+  const float q = __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(A, dr), B), dr), C);
+  return q > 0.f ? q : 0.f;
+}
+
+constexpr int kTile = 8;
+constexpr int kChunk = 512;
+
+__global__ void __launch_bounds__(512) voxelize_f32_kernel(const float4* __restrict__ list_xyzr,
+                                                           const int* __restrict__ list_ch,
+                                                           const int* __restrict__ list_n, int cap,
+                                                           const float* __restrict__ centers, int n_channels, int npts,
+                                                           float resolution, float dimension,
+                                                           float* __restrict__ grid) {
+  __shared__ float4 s_atom[kChunk];
+  __shared__ int s_ch[kChunk];
+  __shared__ int s_counts[16];
+  const int p = blockIdx.y;
+  const int tiles = (npts + kTile - 1) / kTile;
+  const int t = blockIdx.x;
+  const int ti = t / (tiles * tiles), tj = (t / tiles) % tiles, tk = t % tiles;
+  const int li = threadIdx.x >> 6, lj = (threadIdx.x >> 3) & 7, lk = threadIdx.x & 7;
+  const int i = ti * kTile + li, j = tj * kTile + lj, k = tk * kTile + lk;
+  const bool valid = i < npts && j < npts && k < npts;
+  const float half = dimension / 2.f;
+  const float ox = centers[3 * p] - half, oy = centers[3 * p + 1] - half, oz = centers[3 * p + 2] - half;
+  const float gx = __fadd_rn(ox, __fmul_rn((float)i, resolution));
+  const float gy = __fadd_rn(oy, __fmul_rn((float)j, resolution));
+  const float gz = __fadd_rn(oz, __fmul_rn((float)k, resolution));
+  // tile bounds (grid coordinates of first/last voxel of the tile)
+  const float lox = ox + ti * kTile * resolution, hix = lox + (kTile - 1) * resolution;
+  const float loy = oy + tj * kTile * resolution, hiy = loy + (kTile - 1) * resolution;
+  const float loz = oz + tk * kTile * resolution, hiz = loz + (kTile - 1) * resolution;
+  const size_t vol = (size_t)npts * npts * npts;
+  float* out = grid + (size_t)p * n_channels * vol + ((size_t)i * npts + j) * npts + k;
+  const float4* la = list_xyzr + (size_t)p * cap;
+  const int* lc = list_ch + (size_t)p * cap;
+  const int n = list_n[p];
+  int cur = 0;
+  float acc = 0.f;
+  for (int base = 0; base < n; base += kChunk) {
+    const int a_i = base + threadIdx.x;
+    bool keep = false;
+    float4 a = make_float4(0, 0, 0, 0);
+    int ch = 0;
+    if (a_i < n) {
+      a = la[a_i];
+      ch = lc[a_i];
+      const float reach = 1.5f * a.w + 1e-4f;
+      keep = a.x >= lox - reach && a.x <= hix + reach && a.y >= loy - reach && a.y <= hiy + reach &&
+             a.z >= loz - reach && a.z <= hiz + reach;
+    }
+    int tot;
+    const int slot = block_ordered_slot(keep, s_counts, tot);
+    if (keep) {
+      s_atom[slot] = a;
+      s_ch[slot] = ch;
+    }
+    __syncthreads();
+    for (int m = 0; m < tot; m++) {
+      const int ch_m = s_ch[m];
+      while (cur < ch_m) {  // uniform across the CTA
+        if (valid) out[(size_t)cur * vol] = acc;
+        acc = 0.f;
+        cur++;
+      }
+      const float4 am = s_atom[m];
+      acc += density_exact(gx - am.x, gy - am.y, gz - am.z, am.w);
+    }
+    __syncthreads();
+  }
+  while (cur < n_channels) {
+    if (valid) out[(size_t)cur * vol] = acc;
+    acc = 0.f;
+    cur++;
+  }
+}
+
+void launch_voxelize_f32(const float4* list_xyzr, const int* list_ch, const int* list_n, int cap, const float* centers,
+                         int n_poses, int n_channels, int npts, float resolution, float dimension, float* grid,
+                         cudaStream_t s) {
+  if (n_poses <= 0) return;
+  const int tiles = (npts + kTile - 1) / kTile;
+  dim3 g(tiles * tiles * tiles, n_poses);
+  voxelize_f32_kernel<<<g, 512, 0, s>>>(list_xyzr, list_ch, list_n, cap, centers, n_channels, npts, resolution,
+                                        dimension, grid);
+}
+
+}  // namespace gb

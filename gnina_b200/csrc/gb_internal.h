@@ -1,0 +1,128 @@
+// Internal declarations shared by the translation units of libgnina_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <atomic>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../../include/gnina_b200.h"
+
+namespace gb {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+void set_last_error(const std::string& m);
+
+#define GB_CUDA(expr)                                                                                  \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess)                                                                             \
+      throw gb::Error(GB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ")"); \
+  } while (0)
+#define GB_CHECK(cond, msg)                                                             \
+  do {                                                                                  \
+    if (!(cond)) throw gb::Error(GB_ERR_INTERNAL, std::string("check failed: ") + msg); \
+  } while (0)
+
+constexpr int kNumSminaTypes = 28;
+extern const char* const kSminaNames[kNumSminaTypes];
+extern const float kSminaXsRadius[kNumSminaTypes];
+
+// FileMappedGninaTyper equivalent: one channel per non-empty line of the map text.
+struct TypeMap {
+  int n_channels = 0;
+  int t2c[kNumSminaTypes];
+  void parse(const std::string& text);
+};
+
+struct HostTensor {
+  std::vector<int> shape;
+  const float* data = nullptr;  // into Model::raw
+  size_t nelem = 0;
+};
+
+// Device-side description of one convolution of the fp32 validation path.
+struct ConvF32 {
+  int cin = 0, cout = 0, ks = 1;
+  float* w = nullptr;     // [cin][ks^3][cout]
+  float* bias = nullptr;  // [cout]
+  float* bn_scale = nullptr;  // [cin] or null : y = x*scale + shift applied to in-bounds inputs
+  float* bn_shift = nullptr;
+};
+
+// fp16 tensor-core path weights (see gb_cnn_tc.cu)
+struct TcWeights;
+
+struct Model {
+  std::atomic<int> refs{1};
+  int device = 0;
+  int arch = 0;
+  float resolution = 0.5f, dimension = 23.5f, radius_scaling = 1.f;
+  bool apply_logistic_loss = false, skip_softmax = false;
+  std::string name, recmap, ligmap;
+  TypeMap rec, lig;
+  int n_channels = 0, npts = 48;
+  std::vector<char> raw;
+  std::map<std::string, HostTensor> tensors;
+  // device (fp32 path)
+  std::vector<float*> dev_allocs;
+  std::map<std::string, ConvF32> convs;
+  float* fc_w = nullptr;  // [3][F] rows: pose0, pose1, affinity
+  float* fc_b = nullptr;  // [3]
+  int fc_features = 0;
+  std::shared_ptr<TcWeights> tc;  // lazily built
+  const HostTensor& t(const std::string& n) const;
+  ~Model();
+};
+Model* load_model_from_memory(const void* data, size_t n, int device, const std::string& label);
+
+// ---------------------------------------------------------------------------------------------
+// Atoms on the device.  Receptor: filtered to typed atoms, stably sorted by channel.
+struct DevAtoms {
+  float4* xyzr = nullptr;  // x,y,z,radius*radius_scale
+  int* channel = nullptr;
+  int n = 0;
+};
+
+// Signature of a voxelisation setup: models with equal signatures share typed atoms and grids.
+struct GridSig {
+  std::string recmap, ligmap;
+  float resolution, dimension, radius_scaling;
+  bool operator==(const GridSig& o) const {
+    return recmap == o.recmap && ligmap == o.ligmap && resolution == o.resolution && dimension == o.dimension &&
+           radius_scaling == o.radius_scaling;
+  }
+};
+
+// kernels: gb_grid.cu
+void launch_build_pose_lists(const float4* rec_xyzr, const int* rec_ch, int n_rec, const float4* lig_xyzr,
+                             const int* lig_ch, const int* lig_off, const float* centers, int n_poses, float half_dim,
+                             int cap, float4* list_xyzr, int* list_ch, int* list_n, cudaStream_t s);
+void launch_voxelize_f32(const float4* list_xyzr, const int* list_ch, const int* list_n, int cap, const float* centers,
+                         int n_poses, int n_channels, int npts, float resolution, float dimension, float* grid,
+                         cudaStream_t s);
+
+// kernels: gb_cnn_fp32.cu
+struct Fp32Workspace {
+  float* buf[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t cap[4] = {0, 0, 0, 0};
+  float* feat = nullptr; size_t feat_cap = 0;
+  void ensure(int i, size_t nfloats);
+  void ensure_feat(size_t nfloats);
+  ~Fp32Workspace();
+};
+// grid [B][C][48^3] fp32 -> out3 [B][3] (pose logit0, logit1, affinity); returns #kernel launches
+int forward_fp32(const Model& m, const float* grid, int B, Fp32Workspace& ws, float* out3, cudaStream_t s);
+// [B][3] raw -> pose/aff/loss per torch_model.cpp:188-195
+void launch_head_post(const float* out3, int B, bool skip_softmax, bool logistic, float* pose, float* aff,
+                      float* loss, cudaStream_t s);
+// ensemble mean/variance (cnn_torch_scorer.cpp:117-192): per-model arrays [M][B] -> 4 x [B]
+void launch_ensemble(const float* pose, const float* aff, const float* loss, int M, int B, int stride, float* o_score,
+                     float* o_aff, float* o_loss, float* o_var, cudaStream_t s);
+
+}  // namespace gb

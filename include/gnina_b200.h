@@ -1,0 +1,123 @@
+/*
+ * gnina_b200.h — C ABI of the B200-native CNN-scoring hot path (libgnina_b200.so).
+ *
+ * Plain pointers and sizes only; no exceptions, torch or C++ types cross this boundary.  Every entry point
+ * returns 0 on success and a non-zero gb_status otherwise; gb_last_error() gives the message for the calling
+ * thread.  Each declaration cites the reference interface it replaces (paths relative to the gnina tree).
+ *
+ * Threading model (mirrors the reference): a gb_cnn handle is used by ONE host thread at a time (the reference
+ * serialises CNNTorchScorer::score with a recursive_mutex, lib/cnn_torch_scorer.cpp:106, and gives every worker
+ * thread its own fresh_copy(), main/main.cpp:1438).  gb_cnn_clone() is the fresh_copy() equivalent; clones share
+ * the read-only gb_model weights on the device.  All device work of a handle is ordered on its own CUDA stream.
+ */
+#ifndef GNINA_B200_H_
+#define GNINA_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  GB_OK = 0,
+  GB_ERR_USAGE = 1,    /* reference: usage_error (bad model name/file), lib/cnn_torch_scorer.cpp:71,87 */
+  GB_ERR_INTERNAL = 2, /* reference: internal_error / VINA_CHECK */
+  GB_ERR_CUDA = 3,     /* reference: abort() on CUDA failure, lib/gpu_util.h:20-26 — here reported, never fatal */
+  GB_ERR_NO_DEVICE = 4 /* no CUDA device: the product has NO CPU fallback (the reference silently falls back) */
+} gb_status;
+
+typedef struct gb_model gb_model; /* one CNN: weights + typing + grid metadata  (TorchModel<isCUDA>, lib/torch_model.h:22-47) */
+typedef struct gb_cnn gb_cnn;     /* an ensemble scorer                          (CNNTorchScorer<isCUDA>, lib/cnn_torch_scorer.h:25-57) */
+
+enum { GB_ARCH_DEFAULT2018 = 1, GB_ARCH_DENSE = 2, GB_ARCH_DEFAULT2017 = 3 };
+enum { GB_PRECISION_FP32 = 0, /* validation mode: fp32 CUDA-core kernels, reference-layout fp32 grid      */
+       GB_PRECISION_FP16_TC = 1 /* fast mode: fused pooled fp16 grid + tcgen05 fp16 convs, fp32 accumulate */ };
+
+typedef struct {
+  int32_t arch;            /* GB_ARCH_*                                                      */
+  int32_t n_rec_channels;  /* lines of recmap   (lib/torch_model.cpp:110-113)                */
+  int32_t n_lig_channels;  /* lines of ligmap                                                */
+  int32_t grid_points;     /* per axis: round(dimension/resolution)+1 (48)                   */
+  float resolution, dimension, radius_scaling; /* JSON metadata, lib/torch_model.cpp:57-106  */
+  int32_t apply_logistic_loss, skip_softmax;
+  char name[64];
+} gb_model_info;
+
+const char* gb_last_error(void);
+const char* gb_version(void);
+
+/* initializeCUDA(device), lib/dl_scorer.cpp:4-33: select the device for the calling thread; returns a
+ * cudaError_t-style code (0 ok).  Number of visible devices via gb_device_count. */
+int gb_initialize_cuda(int device);
+int gb_device_count(void);
+
+/* TorchModel ctor (lib/torch_model.cpp:49-118): read one model.  `path` is a GNB200W1 blob produced from the
+ * reference's embedded .pt by tools/extract_models.py (weights + JSON metadata + rec/lig type maps).
+ * Unknown file / malformed blob -> GB_ERR_USAGE ("Could not read torch model <name>"). */
+int gb_model_load(const char* path, int device, gb_model** out);
+int gb_model_load_mem(const void* data, size_t nbytes, int device, gb_model** out);
+int gb_model_get_info(const gb_model* m, gb_model_info* info);
+void gb_model_release(gb_model* m); /* reference-counted; handles keep their models alive */
+
+/* make_coordset / FileMappedGninaTyper::get_int_type (lib/torch_model.cpp:120-142): smina type -> (channel or
+ * -1, xs_radius of the original type).  is_ligand selects ligmap and offsets channels by n_rec_channels
+ * (lib/torch_model.cpp:168).  Host-only; used by parity tests. */
+int gb_model_type_atoms(const gb_model* m, int is_ligand, const int32_t* smina_type, int n, int32_t* channel,
+                        float* radius);
+
+/* CNNTorchScorer ctor (lib/cnn_torch_scorer.cpp:24-92) after name expansion: build an ensemble scorer over
+ * n_models models on `device`. */
+int gb_cnn_create(gb_model* const* models, int n_models, int device, gb_cnn** out);
+/* fresh_copy() (lib/cnn_torch_scorer.h:54): independent handle for another thread; shares device weights and
+ * the current receptor. */
+int gb_cnn_clone(const gb_cnn* h, gb_cnn** out);
+void gb_cnn_destroy(gb_cnn* h);
+int gb_cnn_num_models(const gb_cnn* h);
+
+/* Options: "precision" (GB_PRECISION_*), "max_batch" (poses per device pass). */
+int gb_cnn_set_option(gb_cnn* h, const char* key, double value);
+double gb_cnn_get_option(const gb_cnn* h, const char* key);
+
+/* DLScorer::setReceptor (lib/dl_scorer.cpp:93-193): upload receptor atoms ONCE (the reference re-types and
+ * re-uploads them for every pose, lib/torch_model.cpp:159,181).  xyz is n x 3 floats, smina_type the 28-value
+ * smina enum (lib/atom_constants.h:45-75). */
+int gb_cnn_set_receptor(gb_cnn* h, const float* xyz, const int32_t* smina_type, int n);
+
+/* The batch form of CNNTorchScorer::score(model&, false, aff, loss, var) (lib/cnn_torch_scorer.cpp:105-198) +
+ * TorchModel::forward (lib/torch_model.cpp:153-224) for n_poses ligand poses against the current receptor.
+ *   lig_xyz / lig_type : concatenated atoms of all poses (movable ligand atoms INCLUDING polar hydrogens, as
+ *                        DLScorer::setLigand passes them, lib/dl_scorer.cpp:72-87)
+ *   pose_offsets       : n_poses+1 prefix offsets into those arrays (ragged poses allowed)
+ *   centers            : n_poses x 3 grid centres, or NULL => mean of the pose's ligand atoms
+ *                        (lib/torch_model.cpp:163-166; --cnn_center otherwise)
+ * Outputs (host arrays of n_poses floats, any may be NULL): ensemble means of CNNscore, CNNaffinity, loss and
+ * the population variance of the affinities (0 for one model), exactly the four values score() yields. */
+int gb_cnn_score_batch(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, const int32_t* pose_offsets,
+                       int n_poses, const float* centers, float* score, float* affinity, float* loss,
+                       float* variance);
+
+/* Same, but un-averaged: outputs are [n_models][n_poses] (TorchModel::forward's {pose, affinity, loss}). */
+int gb_cnn_score_batch_models(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type,
+                              const int32_t* pose_offsets, int n_poses, const float* centers, float* pose,
+                              float* affinity, float* loss);
+
+/* Split form used for device-resident measurement: stage = host->device copy of the poses (pinned staging,
+ * async on the handle's stream); run = all kernels for the staged poses (no host<->device traffic);
+ * fetch = device->host copy of the per-pose ensemble results and stream sync. */
+int gb_cnn_stage_poses(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, const int32_t* pose_offsets,
+                       int n_poses, const float* centers);
+int gb_cnn_run_staged(gb_cnn* h);
+int gb_cnn_fetch(gb_cnn* h, float* score, float* affinity, float* loss, float* variance);
+void* gb_cnn_stream(gb_cnn* h);            /* cudaStream_t of the handle (for CUDA-event timing)            */
+int64_t gb_cnn_kernel_launches(gb_cnn* h); /* kernels launched by this handle so far                        */
+
+/* GridMaker::forward (libmolgrid; call site lib/torch_model.cpp:181) for parity tests: voxelise the poses for
+ * model `model_index` and copy the fp32 grids [n_poses][C][N][N][N] (reference layout, z fastest) to the host. */
+int gb_cnn_voxelize(gb_cnn* h, int model_index, const float* lig_xyz, const int32_t* lig_type,
+                    const int32_t* pose_offsets, int n_poses, const float* centers, float* grid_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNINA_B200_H_ */

@@ -1,0 +1,149 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  The CUDA path is called through the C ABI
+(gnina_b200.capi -> libgnina_b200.so) and compared with the CPU oracle and the committed golden fixtures."""
+import os
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def kat(golden_dir):
+    return np.load(os.path.join(golden_dir, "cnn_kat.npz"))
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "gridmaker_golden.npz"))
+
+
+def _scorer(names, precision):
+    from gnina_b200 import CNNScorer
+    return CNNScorer(names, precision=precision)
+
+
+def test_library_loaded_and_device():
+    from gnina_b200 import capi
+    assert capi.lib().gb_device_count() >= 1
+
+
+def test_voxeliser_reproduces_reference_golden(gold):
+    """default2017's rec/lig maps are exactly test/gninagrid/files/recmap + ligmap, so the CUDA voxeliser can be
+    held against the reference's own cc_0.48.35.binmap (comparator tolerance 1e-4, compare_bin.py:24)."""
+    s = _scorer(["default2017"], 0)
+    xyz = gold["cc_xyz"]
+    types = np.array([2, 2], np.int32)
+    s.set_receptor(np.round(xyz.astype(np.float64), 3).astype(np.float32), types)
+    g = s.voxelize(xyz, types, [0, 2])[0]
+    ref = np.zeros(g.size, np.float32)
+    ref[gold["cc48_idx"]] = gold["cc48_val"]
+    ref = ref.reshape(g.shape)
+    assert np.abs(g - ref).max() < 2e-6
+    assert np.count_nonzero(g) == np.count_nonzero(ref)
+
+
+@pytest.mark.parametrize("name", ["crossdock_default2018", "default2017"])
+def test_voxeliser_matches_oracle(kat, name):
+    from gnina_b200 import model_blob
+    from oracle import pipeline
+    s = _scorer([name], 0)
+    s.set_receptor(kat["rec_xyz"], kat["rec_types"])
+    offs = kat["pose_offsets"][:4]
+    lx, lt = kat["lig_xyz"][:offs[-1]], kat["lig_types"][:offs[-1]]
+    g = s.voxelize(lx, lt, offs)
+    om = pipeline.OracleModel(model_blob.load_model(name))
+    ref = om.grids(kat["rec_xyz"], kat["rec_types"], lx, lt, offs)
+    assert g.shape == ref.shape
+    assert np.abs(g - ref).max() < 5e-6
+    # typing (G0) goes through the library too
+    ch, rad = s.type_atoms(lt, True)
+    from oracle import gridmaker as gm
+    rc, rr = gm.type_atoms(lt, om.lig_t2c, om.n_rec)
+    assert np.array_equal(ch, rc) and np.array_equal(rad, rr)
+
+
+@pytest.mark.parametrize("name,tol_p,tol_a", [("crossdock_default2018", 2e-5, 1e-4), ("dense_1_3", 2e-5, 1e-4),
+                                              ("default2017", 2e-5, 1e-4),
+                                              ("all_default_to_default_1_3_1", 2e-5, 1e-4)])
+def test_fp32_scores_match_reference_pt(kat, name, tol_p, tol_a):
+    """fp32 validation mode vs the outputs of the reference's own TorchScript model (fp64 run of the .pt)."""
+    s = _scorer([name], 0)
+    s.set_receptor(kat["rec_xyz"], kat["rec_types"])
+    pose, aff, loss, var = s.score_batch(kat["lig_xyz"], kat["lig_types"], kat["pose_offsets"])
+    assert np.abs(pose - kat[name + "_pose_f64"]).max() < tol_p
+    assert np.abs(aff - kat[name + "_aff_f64"]).max() < tol_a
+    assert np.abs(loss + np.log(kat[name + "_pose_f64"])).max() < 1e-3 * max(1.0, np.abs(loss).max())
+    assert np.all(var == 0)
+
+
+def test_default_ensemble_matches_oracle(kat):
+    """default ensemble (dense_1_3, dense_1_3_PT_KD_3, crossdock_default2018_KD_4; cnn_torch_scorer.cpp:33-35):
+    mean score/affinity/loss and affinity variance as CNNTorchScorer::score computes them."""
+    from oracle import cnn_ref
+    s = _scorer([], 0)
+    assert s.model_names == ["dense_1_3", "dense_1_3_PT_KD_3", "crossdock_default2018_KD_4"]
+    s.set_receptor(kat["rec_xyz"], kat["rec_types"])
+    sc, aff, loss, var = s.score_batch(kat["lig_xyz"], kat["lig_types"], kat["pose_offsets"])
+    for i in range(len(sc)):
+        ps = [kat[m + "_pose_f64"][i] for m in s.model_names]
+        as_ = [kat[m + "_aff_f64"][i] for m in s.model_names]
+        es, ea, el, ev = cnn_ref.ensemble(ps, as_, [-np.log(p) for p in ps])
+        assert abs(sc[i] - es) < 2e-5 and abs(aff[i] - ea) < 1e-4 and abs(var[i] - ev) < 2e-4
+        assert abs(loss[i] - el) < 1e-3 * max(1.0, abs(el))
+    pm, am, lm = s.score_batch_models(kat["lig_xyz"], kat["lig_types"], kat["pose_offsets"])
+    assert pm.shape == (3, len(sc))
+    assert np.abs(pm.mean(0) - sc).max() < 1e-6
+
+
+def test_edge_cases_ragged_empty_hydrogen_only_and_centers(kat):
+    from gnina_b200 import model_blob
+    from oracle import pipeline
+    name = "crossdock_default2018"
+    s = _scorer([name], 0)
+    s.set_receptor(kat["rec_xyz"], kat["rec_types"])
+    o = kat["pose_offsets"]
+    na = o[1]
+    lx, lt = kat["lig_xyz"], kat["lig_types"]
+    # ragged: pose0 full, pose1 = first 5 atoms of pose 1, pose2 = empty, pose3 = hydrogens only
+    xs = np.concatenate([lx[:na], lx[na:na + 5], np.zeros((0, 3), np.float32), lx[2 * na:2 * na + 3]])
+    ts = np.concatenate([lt[:na], lt[na:na + 5], np.zeros(0, np.int32), np.array([1, 1, 0], np.int32)])
+    offs = np.array([0, na, na + 5, na + 5, na + 8], np.int32)
+    centers = np.array([[0, 0, 0], [1, 2, 3], [0.5, 0.5, 0.5], [-2, 1, 0]], np.float32)
+    for c in (centers, None):
+        if c is None:  # the empty pose has no ligand centre; give every pose atoms for the NULL-centre case
+            offs2 = np.array([0, na, na + 5, na + 8], np.int32)
+            got = s.score_batch(xs, ts, offs2, None)
+            om = pipeline.OracleModel(model_blob.load_model(name))
+            want = om.score(kat["rec_xyz"], kat["rec_types"], xs, ts, offs2, None, torch.float64)
+        else:
+            got = s.score_batch(xs, ts, offs, c)
+            om = pipeline.OracleModel(model_blob.load_model(name))
+            want = om.score(kat["rec_xyz"], kat["rec_types"], xs, ts, offs, c, torch.float64)
+        assert np.abs(got[0] - want[0]).max() < 2e-5
+        assert np.abs(got[1] - want[1]).max() < 1e-4
+    assert s.score_batch(np.zeros((0, 3), np.float32), np.zeros(0, np.int32), [0])[0].shape == (0,)
+
+
+def test_single_pose_score_and_fresh_copy(kat):
+    name = "crossdock_default2018"
+    s = _scorer([name], 0)
+    s.set_receptor(kat["rec_xyz"], kat["rec_types"])
+    o = kat["pose_offsets"]
+    one = s.score(kat["lig_xyz"][:o[1]], kat["lig_types"][:o[1]])
+    assert abs(one[0] - kat[name + "_pose_f64"][0]) < 2e-5 and abs(one[1] - kat[name + "_aff_f64"][0]) < 1e-4
+    c = s.fresh_copy()
+    two = c.score(kat["lig_xyz"][:o[1]], kat["lig_types"][:o[1]])
+    assert one == two
+    # batch > max_batch chunks identically
+    s.set_option("max_batch", 4)
+    many = s.score_batch(kat["lig_xyz"], kat["lig_types"], o)
+    s.set_option("max_batch", 2)
+    many2 = s.score_batch(kat["lig_xyz"], kat["lig_types"], o)
+    assert np.array_equal(many[0], many2[0]) and np.array_equal(many[1], many2[1])
+
+
+def test_errors_are_reported_not_fatal():
+    from gnina_b200 import CNNScorer, usage_error
+    with pytest.raises(usage_error, match="Invalid model name"):
+        CNNScorer(["no_such_model"])
