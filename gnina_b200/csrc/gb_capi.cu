@@ -11,6 +11,33 @@ namespace gb {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& m) { g_last_error = m; }
 
+void Profiler::begin(const char* name, cudaStream_t s) {
+  int id = -1;
+  for (size_t i = 0; i < names.size(); i++)
+    if (names[i] == name) id = (int)i;
+  if (id < 0) { names.push_back(name); total_ms.push_back(0); count.push_back(0); id = (int)names.size() - 1; }
+  auto get = [&]() { cudaEvent_t e; if (pool.empty()) { cudaEventCreate(&e); } else { e = pool.back(); pool.pop_back(); } return e; };
+  cur = id; cur_a = get();
+  cudaEventRecord(cur_a, s);
+}
+void Profiler::end(cudaStream_t s) {
+  if (cur < 0) return;
+  cudaEvent_t b; if (pool.empty()) cudaEventCreate(&b); else { b = pool.back(); pool.pop_back(); }
+  cudaEventRecord(b, s);
+  pending.push_back({cur, cur_a, b});
+  cur = -1;
+}
+void Profiler::resolve() {
+  for (auto& p : pending) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { total_ms[p.id] += ms; count[p.id]++; }
+    pool.push_back(p.a); pool.push_back(p.b);
+  }
+  pending.clear();
+}
+void Profiler::reset() { resolve(); for (auto& t : total_ms) t = 0; for (auto& c : count) c = 0; }
+Profiler::~Profiler() { for (auto& p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); } for (auto e : pool) cudaEventDestroy(e); }
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -89,6 +116,7 @@ struct gb_cnn {
   Fp32Workspace ws32;
   TcWorkspace ws_tc;
   int64_t launches = 0;
+  Profiler prof;
   ~gb_cnn() {
     if (stream) cudaStreamDestroy(stream);
     for (Model* m : models)
@@ -278,6 +306,8 @@ int gb_cnn_set_option(gb_cnn* h, const char* key, double value) {
       for (Model* m : h->models)
         if (!tc_supported(*m)) throw Error(GB_ERR_USAGE, "model " + m->name + " has no tensor-core path yet");
     h->precision = p;
+  } else if (k == "profile") {
+    h->prof.on = value != 0;
   } else if (k == "max_batch") {
     GB_CHECK(value >= 0 && value <= 65536, "max_batch out of range");
     h->max_batch = (int)value;
@@ -421,9 +451,13 @@ static void voxelize_chunk_f32(gb_cnn* h, GridGroup& G, int p0, int nb) {
   G.list_n.ensure(nb);
   const int npts = (int)std::lround(G.sig.dimension / G.sig.resolution) + 1;
   G.grid.ensure((size_t)nb * G.n_channels * npts * npts * npts);
+  {
+  ProfScope ps(&h->prof, "f32_build_pose_lists", h->stream);
   launch_build_pose_lists(G.rec_xyzr.p, G.rec_ch.p, G.n_rec, G.lig_xyzr.p, G.lig_ch.p, G.lig_off.p + p0,
                           h->d_centers.p + 3 * (size_t)p0, nb, G.sig.dimension / 2.f, std::max(cap, 1), G.list_xyzr.p,
                           G.list_ch.p, G.list_n.p, h->stream);
+  }
+  ProfScope ps2(&h->prof, "f32_voxelize", h->stream);
   launch_voxelize_f32(G.list_xyzr.p, G.list_ch.p, G.list_n.p, std::max(cap, 1), h->d_centers.p + 3 * (size_t)p0, nb,
                       G.n_channels, npts, G.sig.resolution, G.sig.dimension, G.grid.p, h->stream);
   h->launches += 2;
@@ -449,7 +483,7 @@ int gb_cnn_run_staged(gb_cnn* h) {
         voxelize_chunk_f32(h, G, p0, nb);
         for (int mi : G.model_idx) {
           const Model& Mo = *h->models[mi];
-          h->launches += forward_fp32(Mo, G.grid.p, nb, h->ws32, h->d_out3.p, h->stream);
+          h->launches += forward_fp32(Mo, G.grid.p, nb, h->ws32, h->d_out3.p, h->stream, &h->prof);
           launch_head_post(h->d_out3.p, nb, Mo.skip_softmax, Mo.apply_logistic_loss, h->d_pose.p + (size_t)mi * n + p0,
                            h->d_aff.p + (size_t)mi * n + p0, h->d_loss.p + (size_t)mi * n + p0, h->stream);
           h->launches++;
@@ -460,7 +494,7 @@ int gb_cnn_run_staged(gb_cnn* h) {
                        G.sig.resolution, G.sig.dimension};
         for (int mi : G.model_idx) {
           const Model& Mo = *h->models[mi];
-          h->launches += tc_forward(Mo, pb, G.tc_grid, h->ws_tc, h->d_out3.p, h->stream);
+          h->launches += tc_forward(Mo, pb, G.tc_grid, h->ws_tc, h->d_out3.p, h->stream, &h->prof);
           launch_head_post(h->d_out3.p, nb, Mo.skip_softmax, Mo.apply_logistic_loss, h->d_pose.p + (size_t)mi * n + p0,
                            h->d_aff.p + (size_t)mi * n + p0, h->d_loss.p + (size_t)mi * n + p0, h->stream);
           h->launches++;
@@ -515,6 +549,27 @@ int gb_cnn_score_batch_models(gb_cnn* h, const float* lig_xyz, const int32_t* li
     if (loss) GB_CUDA(cudaMemcpyAsync(loss, h->d_loss.p, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   }
   GB_CUDA(cudaStreamSynchronize(h->stream));
+  GB_API_END
+}
+
+int gb_cnn_profile_read(gb_cnn* h, int index, char* name, int name_cap, double* total_ms, int64_t* count) {
+  GB_API_BEGIN
+  GB_CHECK(h, "null handle");
+  GB_CUDA(cudaSetDevice(h->device));
+  GB_CUDA(cudaStreamSynchronize(h->stream));
+  h->prof.resolve();
+  if (index < 0 || index >= (int)h->prof.names.size()) return 1;
+  if (name && name_cap > 0) { strncpy(name, h->prof.names[index].c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (total_ms) *total_ms = h->prof.total_ms[index];
+  if (count) *count = h->prof.count[index];
+  GB_API_END
+}
+int gb_cnn_profile_reset(gb_cnn* h) {
+  GB_API_BEGIN
+  GB_CHECK(h, "null handle");
+  GB_CUDA(cudaSetDevice(h->device));
+  GB_CUDA(cudaStreamSynchronize(h->stream));
+  h->prof.reset();
   GB_API_END
 }
 

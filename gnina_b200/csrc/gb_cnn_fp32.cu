@@ -1,6 +1,7 @@
 // fp32 validation path of the CNN forward (N1/N2/N3 of SURVEY.md §8a): plain CUDA-core kernels on NCDHW fp32
 // tensors, numerically equivalent to the TorchScript graphs the reference runs at gninasrc/lib/torch_model.cpp:185
 // up to fp32 summation order.  It exists to (a) pin the fast tensor-core path, (b) provide a <=1e-4 validation mode.
+#include <cstdio>
 #include "gb_internal.h"
 
 namespace gb {
@@ -114,8 +115,12 @@ __global__ void __launch_bounds__(512) conv3d_f32_kernel(const float* __restrict
   }
 }
 
+static Profiler* g_prof_tls();
 static int launch_conv(const ConvF32& c, const float* in, int in_ctot, float* out, int out_ctot, int out_coff, int D,
                        int B, bool relu, cudaStream_t s) {
+  char nm[64];
+  snprintf(nm, sizeof nm, "f32_conv%d_%dx%d_d%d", c.ks, c.cin, c.cout, D);
+  ProfScope ps(g_prof_tls(), nm, s);
   const int tiles = (D + 7) / 8;
   const int cot = (c.cout % 32 == 0) ? 32 : 16;
   dim3 g(tiles * tiles * tiles, (c.cout + cot - 1) / cot, B);
@@ -160,6 +165,7 @@ __global__ void pool2_f32_kernel(const float* __restrict__ in, int in_ctot, floa
 
 static int launch_pool(const float* in, int in_ctot, float* out, int out_ctot, int C, int Din, int B, bool is_max,
                        cudaStream_t s) {
+  ProfScope ps(g_prof_tls(), "f32_pool", s);
   const int Do = Din / 2;
   const size_t total = (size_t)B * C * Do * Do * Do;
   pool2_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, in_ctot, out, out_ctot, C, Din, is_max ? 1 : 0,
@@ -263,10 +269,15 @@ void launch_ensemble(const float* pose, const float* aff, const float* loss, int
   ensemble_kernel<<<(B + 127) / 128, 128, 0, s>>>(pose, aff, loss, M, B, stride, o_score, o_aff, o_loss, o_var);
 }
 
+static thread_local Profiler* t_prof = nullptr;
+static Profiler* g_prof_tls() { return t_prof; }
+
 // ---------------------------------------------------------------------------------------------------------
-int forward_fp32(const Model& m, const float* grid, int B, Fp32Workspace& ws, float* out3, cudaStream_t s) {
+int forward_fp32(const Model& m, const float* grid, int B, Fp32Workspace& ws, float* out3, cudaStream_t s,
+                 Profiler* prof) {
   int launches = 0;
   const int C = m.n_channels;
+  t_prof = prof;
   GB_CHECK(m.npts == 48, "CNN graphs expect a 48^3 grid");
   auto conv = [&](const std::string& k) -> const ConvF32& {
     auto it = m.convs.find(k);
@@ -325,8 +336,12 @@ int forward_fp32(const Model& m, const float* grid, int B, Fp32Workspace& ws, fl
     feat = ws.feat;
   }
   (void)v12;
-  fc3_kernel<<<B, 256, 0, s>>>(feat, m.fc_w, m.fc_b, m.fc_features, out3);
+  {
+    ProfScope ps(prof, "f32_fc_heads", s);
+    fc3_kernel<<<B, 256, 0, s>>>(feat, m.fc_w, m.fc_b, m.fc_features, out3);
+  }
   launches++;
+  t_prof = nullptr;
   return launches;
 }
 

@@ -15,7 +15,7 @@ void TcWorkspace::ensure(int i, size_t bytes) {
 }
 TcWorkspace::~TcWorkspace() { for (auto p : buf) if (p) cudaFree(p); }
 bool tc_supported(const Model&) { return false; }
-int tc_forward(const Model&, const TcPoseBatch&, TcGridWorkspace&, TcWorkspace&, float*, cudaStream_t) {
+int tc_forward(const Model&, const TcPoseBatch&, TcGridWorkspace&, TcWorkspace&, float*, cudaStream_t, Profiler*) {
   throw Error(GB_ERR_INTERNAL, "tensor-core path not built");
 }
 }  // namespace gb

@@ -99,6 +99,29 @@ struct GridSig {
   }
 };
 
+// Optional per-kernel CUDA-event timing (bench.py reads it through gb_cnn_profile_read).
+struct Profiler {
+  bool on = false;
+  struct Pending { int id; cudaEvent_t a, b; };
+  std::vector<std::string> names;
+  std::vector<double> total_ms;
+  std::vector<long long> count;
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> pool;
+  int cur = -1;
+  cudaEvent_t cur_a = nullptr;
+  void begin(const char* name, cudaStream_t s);
+  void end(cudaStream_t s);
+  void resolve();  // call after the stream is synchronised
+  void reset();
+  ~Profiler();
+};
+struct ProfScope {
+  Profiler* p; cudaStream_t s;
+  ProfScope(Profiler* p_, const char* n, cudaStream_t s_) : p(p_), s(s_) { if (p && p->on) p->begin(n, s); }
+  ~ProfScope() { if (p && p->on) p->end(s); }
+};
+
 // kernels: gb_grid.cu
 void launch_build_pose_lists(const float4* rec_xyzr, const int* rec_ch, int n_rec, const float4* lig_xyzr,
                              const int* lig_ch, const int* lig_off, const float* centers, int n_poses, float half_dim,
@@ -117,7 +140,8 @@ struct Fp32Workspace {
   ~Fp32Workspace();
 };
 // grid [B][C][48^3] fp32 -> out3 [B][3] (pose logit0, logit1, affinity); returns #kernel launches
-int forward_fp32(const Model& m, const float* grid, int B, Fp32Workspace& ws, float* out3, cudaStream_t s);
+int forward_fp32(const Model& m, const float* grid, int B, Fp32Workspace& ws, float* out3, cudaStream_t s,
+                 Profiler* prof = nullptr);
 // [B][3] raw -> pose/aff/loss per torch_model.cpp:188-195
 void launch_head_post(const float* out3, int B, bool skip_softmax, bool logistic, float* pose, float* aff,
                       float* loss, cudaStream_t s);

@@ -33,6 +33,7 @@ struct TcWorkspace {
 
 bool tc_supported(const Model& m);
 // -> out3 [n_poses][3]; returns the number of kernel launches
-int tc_forward(const Model& m, const TcPoseBatch& pb, TcGridWorkspace& gw, TcWorkspace& ws, float* out3, cudaStream_t s);
+int tc_forward(const Model& m, const TcPoseBatch& pb, TcGridWorkspace& gw, TcWorkspace& ws, float* out3, cudaStream_t s,
+               Profiler* prof = nullptr);
 
 }  // namespace gb

@@ -169,6 +169,19 @@ class CNNScorer:
     def kernel_launches(self):
         return capi.lib().gb_cnn_kernel_launches(self._h)
 
+    def profile(self):
+        """-> {kernel class: (total_ms, launches)} accumulated since the last reset (option "profile" must be 1)."""
+        out, i = {}, 0
+        name = C.create_string_buffer(96)
+        ms, cnt = C.c_double(), C.c_int64()
+        while capi.lib().gb_cnn_profile_read(self._h, i, name, 96, C.byref(ms), C.byref(cnt)) == 0:
+            out[name.value.decode()] = (ms.value, cnt.value)
+            i += 1
+        return out
+
+    def profile_reset(self):
+        capi.check(capi.lib().gb_cnn_profile_reset(self._h))
+
     def voxelize(self, lig_xyz, lig_types, pose_offsets, centers=None, model_index=0):
         xyz, t, off, c = self._poses(lig_xyz, lig_types, pose_offsets, centers)
         info = self.model_info(model_index)

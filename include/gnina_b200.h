@@ -75,7 +75,7 @@ int gb_cnn_clone(const gb_cnn* h, gb_cnn** out);
 void gb_cnn_destroy(gb_cnn* h);
 int gb_cnn_num_models(const gb_cnn* h);
 
-/* Options: "precision" (GB_PRECISION_*), "max_batch" (poses per device pass). */
+/* Options: "precision" (GB_PRECISION_*), "max_batch" (poses per device pass), "profile" (0/1). */
 int gb_cnn_set_option(gb_cnn* h, const char* key, double value);
 double gb_cnn_get_option(const gb_cnn* h, const char* key);
 
@@ -111,6 +111,11 @@ int gb_cnn_run_staged(gb_cnn* h);
 int gb_cnn_fetch(gb_cnn* h, float* score, float* affinity, float* loss, float* variance);
 void* gb_cnn_stream(gb_cnn* h);            /* cudaStream_t of the handle (for CUDA-event timing)            */
 int64_t gb_cnn_kernel_launches(gb_cnn* h); /* kernels launched by this handle so far                        */
+
+/* Per-kernel CUDA-event timing (no reference counterpart; measurement only).  Enable with option "profile"=1;
+ * read entry `index` (0,1,...) until a non-zero return: kernel-class name, accumulated ms, launches. */
+int gb_cnn_profile_read(gb_cnn* h, int index, char* name, int name_cap, double* total_ms, int64_t* count);
+int gb_cnn_profile_reset(gb_cnn* h);
 
 /* GridMaker::forward (libmolgrid; call site lib/torch_model.cpp:181) for parity tests: voxelise the poses for
  * model `model_index` and copy the fp32 grids [n_poses][C][N][N][N] (reference layout, z fastest) to the host. */
