@@ -11,7 +11,7 @@ SYMBOLS = ["gb_last_error", "gb_version", "gb_initialize_cuda", "gb_device_count
            "gb_model_get_info", "gb_model_release", "gb_model_type_atoms", "gb_cnn_create", "gb_cnn_clone",
            "gb_cnn_destroy", "gb_cnn_num_models", "gb_cnn_set_option", "gb_cnn_get_option", "gb_cnn_set_receptor",
            "gb_cnn_score_batch", "gb_cnn_score_batch_models", "gb_cnn_stage_poses", "gb_cnn_run_staged",
-           "gb_cnn_fetch", "gb_cnn_profile_read", "gb_cnn_profile_reset", "gb_cnn_stream", "gb_cnn_kernel_launches", "gb_cnn_voxelize"]
+           "gb_cnn_fetch", "gb_cnn_profile_read", "gb_cnn_profile_reset", "gb_cnn_debug_read", "gb_cnn_stream", "gb_cnn_kernel_launches", "gb_cnn_voxelize"]
 
 
 class GbError(RuntimeError):
@@ -61,6 +61,7 @@ def lib():
     L.gb_cnn_fetch.argtypes = [vp, fp, fp, fp, fp]
     L.gb_cnn_profile_read.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.gb_cnn_profile_reset.argtypes = [vp]
+    L.gb_cnn_debug_read.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.gb_cnn_stream.argtypes = [vp]
     L.gb_cnn_stream.restype = vp
     L.gb_cnn_kernel_launches.argtypes = [vp]

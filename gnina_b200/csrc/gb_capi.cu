@@ -440,7 +440,7 @@ int gb_cnn_stage_poses(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type,
 
 static int chunk_size(const gb_cnn* h) {
   if (h->max_batch > 0) return h->max_batch;
-  return h->precision == GB_PRECISION_FP32 ? 16 : 512;
+  return h->precision == GB_PRECISION_FP32 ? 16 : 1024;
 }
 
 // voxelise poses [p0, p0+nb) of group G into the fp32 reference layout
@@ -570,6 +570,27 @@ int gb_cnn_profile_reset(gb_cnn* h) {
   GB_CUDA(cudaSetDevice(h->device));
   GB_CUDA(cudaStreamSynchronize(h->stream));
   h->prof.reset();
+  GB_API_END
+}
+
+int gb_cnn_debug_read(gb_cnn* h, const char* name, void* out, size_t cap_bytes, size_t* nbytes) {
+  GB_API_BEGIN
+  GB_CHECK(h && name && nbytes, "null argument");
+  static const char* const names[] = {"x0", "y3", "x2", "x4", "y5"};
+  int idx = -1;
+  for (int i = 0; i < 5; i++)
+    if (std::string(name) == names[i]) idx = i;
+  if (idx < 0) throw Error(GB_ERR_USAGE, "unknown debug buffer");
+  size_t bytes = 0;
+  const void* src = tc_debug_buffer(idx, &bytes);
+  GB_CHECK(src != nullptr, "no fast-path pass has run on this thread");
+  *nbytes = bytes;
+  if (out) {
+    GB_CHECK(cap_bytes >= bytes, "debug buffer too small");
+    GB_CUDA(cudaSetDevice(h->device));
+    GB_CUDA(cudaStreamSynchronize(h->stream));
+    GB_CUDA(cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
+  }
   GB_API_END
 }
 

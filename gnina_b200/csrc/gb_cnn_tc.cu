@@ -1,8 +1,155 @@
-// placeholder until the tcgen05 path lands
+// Fast path of the CNN forward for the default2018 family (N1 of SURVEY.md §8a), sm_100a only.
+//
+//   voxelise + avgpool (CUDA cores)  ->  X0   fp16, "chunk-planar padded" layout (below)
+//   conv 3^3 28(32)->32 @24^3        ->  Y1   tcgen05 implicit GEMM (this file, conv3_tc_kernel)
+//   conv 1^3 32->32 + ReLU + avgpool ->  X2   mma.sync pointwise + pooling + re-layout
+//   conv 3^3 32->64 @12^3            ->  Y3   tcgen05
+//   conv 1^3 64->64 + ReLU + avgpool ->  X4
+//   conv 3^3 64->128 @6^3            ->  Y5   tcgen05
+//   FC heads 27648 -> 3              ->  out3
+//
+// Activation layout consumed by the tcgen05 convolutions ("chunk-planar padded, grouped"):
+//   X[group][x: D][c8: C/8][pos: Lp][8 channels]  fp16,   pos = q*P*P + yp*P + zp,  P = D+2,
+//   q = pose within the group (G poses per group), (yp,zp) in [0,P) with a zero border, x planes unpadded.
+// A 3x3x3 tap (dx,dy,dz) is then a PLANE shift (dx) plus a constant offset dy*P+dz of the flat position index, so
+// the A operand of every tap is the same shared-memory slab addressed with a different descriptor start address
+// (no-swizzle K-major canonical layout: 16-byte rows, SBO = 128 B, LBO = slab row pitch) — im2col costs nothing.
+//
+// conv3_tc_kernel: one CTA owns 128 consecutive flat positions (M = 128) of one pose group and one block of 32
+// output channels, and marches over the D input planes.  For input plane xi it issues, per (dy,dz) tap and
+// 16-channel K step, ONE tcgen05.mma with N = 96 whose B operand stacks the three dx taps: the 96 accumulator
+// columns are the TMEM slots of output planes xi-1, xi, xi+1, i.e. the dx shift is done by WHERE the MMA
+// accumulates, not by moving data.  (Cout = 32 alone would make the MMA shared-memory-bound on A: N = 96 cuts the
+// A traffic per FLOP 3x.)  TMEM holds a ring of R plane slots x 32 fp32 columns; a slot is drained by the epilogue
+// warps (tcgen05.ld -> bias -> ReLU -> fp16 -> global) as soon as its third input plane has been accumulated.
+// Warp roles: warp 0 = bulk-copy (TMA unit) producer, warp 1 = MMA issuer, warps 2..5 = epilogue.
+#include <cstdio>
+#include <cstring>
+#include <cuda_fp16.h>
+#include <vector>
+#include "gb_ptx.cuh"
 #include "gb_tc.h"
+
 namespace gb {
+
+// ------------------------------------------------------------------------------------------------------------
+struct ActLayout {
+  int D, P, G, T, C8, Lp;
+  size_t group_u4() const { return (size_t)D * C8 * Lp; }  // uint4 per group
+};
+static ActLayout make_layout(int D, int G, int C) {
+  ActLayout L;
+  L.D = D; L.P = D + 2; L.G = G; L.C8 = C / 8;
+  const int span = (G - 1) * L.P * L.P + (D - 1) * L.P + D;
+  L.T = (span + 127) / 128;
+  L.Lp = 128 * L.T + 2 * (L.P + 1);
+  L.Lp = (L.Lp + 7) & ~7;
+  return L;
+}
+
+struct ConvTc {
+  int cin = 0, cout = 0;     // cin padded to a multiple of 16
+  uint4* wp = nullptr;       // [cout/32][9][cin/8][96] x 16 B
+  float* bias = nullptr;
+};
+struct PointwiseTc {
+  int c = 0;
+  __half* w = nullptr;       // [co][ci] row-major fp16
+  float* bias = nullptr;
+};
+struct TcWeights {
+  ConvTc conv1, conv3, conv5;
+  PointwiseTc pw2, pw4;
+  float* fcw = nullptr;      // [3][216*128] channels-last order
+  float* fcb = nullptr;
+  std::vector<void*> allocs;
+  ~TcWeights() { for (void* p : allocs) cudaFree(p); }
+};
+
+template <typename T>
+static T* tc_upload(TcWeights& w, const std::vector<T>& h) {
+  T* d = nullptr;
+  GB_CUDA(cudaMalloc(&d, h.size() * sizeof(T)));
+  w.allocs.push_back(d);
+  GB_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+
+static ConvTc prep_conv(TcWeights& tw, const Model& m, const std::string& key) {
+  const HostTensor& w = m.t(key + ".weight");
+  const HostTensor& b = m.t(key + ".bias");
+  ConvTc c;
+  const int cout = w.shape[0], cin = w.shape[1];
+  GB_CHECK(w.shape[2] == 3 && cout % 32 == 0, "tc conv shape");
+  c.cout = cout;
+  c.cin = (cin + 15) / 16 * 16;
+  const int C8 = c.cin / 8, NB = cout / 32;
+  std::vector<__half> h((size_t)NB * 9 * C8 * 96 * 8, __float2half(0.f));
+  for (int nb = 0; nb < NB; nb++)
+    for (int ky = 0; ky < 3; ky++)
+      for (int kz = 0; kz < 3; kz++)
+        for (int c8 = 0; c8 < C8; c8++)
+          for (int blk = 0; blk < 3; blk++) {
+            const int kx = 2 - blk;  // blk 0 <-> dx=+1 (output plane xi-1), blk 2 <-> dx=-1 (output plane xi+1)
+            for (int co = 0; co < 32; co++)
+              for (int e = 0; e < 8; e++) {
+                const int ci = c8 * 8 + e;
+                if (ci >= cin) continue;
+                const float v = w.data[((((size_t)(nb * 32 + co) * cin + ci) * 3 + kx) * 3 + ky) * 3 + kz];
+                h[((((size_t)nb * 9 + ky * 3 + kz) * C8 + c8) * 96 + blk * 32 + co) * 8 + e] = __float2half(v);
+              }
+          }
+  c.wp = reinterpret_cast<uint4*>(tc_upload(tw, h));
+  c.bias = tc_upload(tw, std::vector<float>(b.data, b.data + b.nelem));
+  return c;
+}
+
+static PointwiseTc prep_pw(TcWeights& tw, const Model& m, const std::string& key) {
+  const HostTensor& w = m.t(key + ".weight");
+  const HostTensor& b = m.t(key + ".bias");
+  PointwiseTc p;
+  p.c = w.shape[0];
+  GB_CHECK(w.shape[0] == w.shape[1] && w.shape[2] == 1, "pointwise shape");
+  std::vector<__half> h((size_t)p.c * p.c);
+  for (size_t i = 0; i < h.size(); i++) h[i] = __float2half(w.data[i]);
+  p.w = tc_upload(tw, h);
+  p.bias = tc_upload(tw, std::vector<float>(b.data, b.data + b.nelem));
+  return p;
+}
+
+bool tc_supported(const Model& m) { return m.arch == GB_ARCH_DEFAULT2018 && m.n_channels == 28 && m.npts == 48; }
+
+static std::shared_ptr<TcWeights> get_tc_weights(const Model& m) {
+  Model& mm = const_cast<Model&>(m);
+  if (mm.tc) return mm.tc;
+  auto tw = std::make_shared<TcWeights>();
+  tw->conv1 = prep_conv(*tw, m, "unit1_conv");
+  tw->pw2 = prep_pw(*tw, m, "unit2_conv");
+  tw->conv3 = prep_conv(*tw, m, "unit3_conv");
+  tw->pw4 = prep_pw(*tw, m, "unit4_conv");
+  tw->conv5 = prep_conv(*tw, m, "unit5_conv");
+  // FC heads read the NCDHW flatten idx = c*216 + pos (view(-1, 27648)); the device keeps conv5's output
+  // channels-last ([pos][c]), so permute the weights once.
+  const HostTensor &pw = m.t("pose_output.weight"), &pb = m.t("pose_output.bias"), &aw = m.t("affinity_output.weight"),
+                   &ab = m.t("affinity_output.bias");
+  const int F = 27648;
+  GB_CHECK(pw.shape[1] == F, "fc features");
+  std::vector<float> fw((size_t)3 * F), fb(3);
+  for (int r = 0; r < 3; r++) {
+    const float* src = r < 2 ? pw.data + (size_t)r * F : aw.data;
+    for (int c = 0; c < 128; c++)
+      for (int pos = 0; pos < 216; pos++) fw[(size_t)r * F + pos * 128 + c] = src[c * 216 + pos];
+  }
+  fb[0] = pb.data[0]; fb[1] = pb.data[1]; fb[2] = ab.data[0];
+  tw->fcw = tc_upload(*tw, fw);
+  tw->fcb = tc_upload(*tw, fb);
+  mm.tc = tw;
+  return tw;
+}
+
 TcGridWorkspace::~TcGridWorkspace() {
-  for (auto p : x0) if (p) cudaFree(p);
+  for (auto p : x0)
+    if (p) cudaFree(p);
   if (list_xyzr) cudaFree(list_xyzr);
   if (list_ch) cudaFree(list_ch);
   if (list_n) cudaFree(list_n);
@@ -10,12 +157,577 @@ TcGridWorkspace::~TcGridWorkspace() {
 void TcWorkspace::ensure(int i, size_t bytes) {
   if (cap[i] >= bytes) return;
   if (buf[i]) cudaFree(buf[i]);
+  buf[i] = nullptr;
   GB_CUDA(cudaMalloc(&buf[i], bytes));
+  GB_CUDA(cudaMemset(buf[i], 0, bytes));  // zero borders of the padded layouts; interiors are rewritten per chunk
   cap[i] = bytes;
 }
-TcWorkspace::~TcWorkspace() { for (auto p : buf) if (p) cudaFree(p); }
-bool tc_supported(const Model&) { return false; }
-int tc_forward(const Model&, const TcPoseBatch&, TcGridWorkspace&, TcWorkspace&, float*, cudaStream_t, Profiler*) {
-  throw Error(GB_ERR_INTERNAL, "tensor-core path not built");
+TcWorkspace::~TcWorkspace() {
+  for (auto p : buf)
+    if (p) cudaFree(p);
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Kernel A: voxelise + 2x2x2 average pool, fp16 output in the conv1 input layout.
+// CTA = 8x8x8 fine voxels (4x4x4 pooled) of one pose; thread = one fine voxel; the 8 fine voxels of a pooled
+// voxel are 8 lanes of one warp (xor-shuffle reduction).  Atoms: pose list (channel sorted) -> tile list (ordered
+// compaction in smem) -> per-warp cull (ballot) -> per-lane density.  Density: libmolgrid's piecewise function
+// with MUFU ex2 / rsqrt.
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rsqrt(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ int block_ordered_slot512(bool pred, int* s_warp_counts, int& total) {
+  const unsigned mask = __ballot_sync(0xffffffffu, pred);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_warp_counts[warp] = __popc(mask);
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < 16; w++) {
+    const int c = s_warp_counts[w];
+    if (w < warp) base += c;
+    tot += c;
+  }
+  __syncthreads();
+  total = tot;
+  return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+__global__ void __launch_bounds__(512) voxelize_pool_f16_kernel(const float4* __restrict__ list_xyzr,
+                                                                const int* __restrict__ list_ch,
+                                                                const int* __restrict__ list_n, int cap,
+                                                                const float* __restrict__ centers, float resolution,
+                                                                float dimension, uint4* __restrict__ x0, int Lp, int D,
+                                                                int P, int C8) {
+  __shared__ float4 s_atom[512];
+  __shared__ float s_inv[512];
+  __shared__ int s_ch[512];
+  __shared__ int s_counts[16];
+  __shared__ __align__(16) __half s_out[64 * 40];  // [pooled voxel][C8*8 <= 40 channels]
+  const int CH = C8 * 8;
+  const int p = blockIdx.y;
+  const int t = blockIdx.x;
+  const int tiles = (2 * D) / 8;
+  const int ti = t / (tiles * tiles), tj = (t / tiles) % tiles, tk = t % tiles;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = (lane & 1) | (((lane >> 3) & 3) << 1);
+  const int j = ((lane >> 1) & 1) | ((warp & 3) << 1);
+  const int i = ((lane >> 2) & 1) | ((warp >> 2) << 1);
+  const int pv = ((warp >> 2) * 4 + (warp & 3)) * 4 + ((lane >> 3) & 3);
+  for (int e = threadIdx.x; e < 64 * CH; e += 512) s_out[e] = __float2half(0.f);
+  const float half = dimension * 0.5f;
+  const float ox = centers[3 * p] - half, oy = centers[3 * p + 1] - half, oz = centers[3 * p + 2] - half;
+  const float gx = ox + (ti * 8 + i) * resolution, gy = oy + (tj * 8 + j) * resolution, gz = oz + (tk * 8 + k) * resolution;
+  const float lox = ox + ti * 8 * resolution, loy = oy + tj * 8 * resolution, loz = oz + tk * 8 * resolution;
+  const float span = 7.f * resolution;
+  // warp footprint: i in {2*(warp>>2), +1}, j in {2*(warp&3), +1}, k in 0..7
+  const float wlx = lox + 2 * (warp >> 2) * resolution, wly = loy + 2 * (warp & 3) * resolution, wlz = loz;
+  const float4* la = list_xyzr + (size_t)p * cap;
+  const int* lc = list_ch + (size_t)p * cap;
+  const int n = list_n[p];
+  int cur = -1;
+  float acc = 0.f;
+  const float kLog2e2 = -2.885390081777927f;  // -2*log2(e)
+  const float kA = 0.7357588823428847f;       // 2/e
+  const float kB = -1.1036383235143270f;      // -3/e
+  for (int base = 0; base < n; base += 512) {
+    const int ai = base + threadIdx.x;
+    bool keep = false;
+    float4 a = make_float4(0, 0, 0, 0);
+    int ch = 0;
+    if (ai < n) {
+      a = la[ai];
+      ch = lc[ai];
+      const float reach = 1.5f * a.w + 1e-4f;
+      keep = a.x >= lox - reach && a.x <= lox + span + reach && a.y >= loy - reach && a.y <= loy + span + reach &&
+             a.z >= loz - reach && a.z <= loz + span + reach;
+    }
+    int tot;
+    const int slot = block_ordered_slot512(keep, s_counts, tot);
+    if (keep) {
+      s_atom[slot] = a;
+      s_inv[slot] = 1.0f / (a.w * a.w);
+      s_ch[slot] = ch;
+    }
+    __syncthreads();
+    for (int wb = 0; wb < tot; wb += 32) {
+      const int m = wb + lane;
+      bool hit = false;
+      if (m < tot) {
+        const float4 b = s_atom[m];
+        const float reach = 1.5f * b.w + 1e-4f;
+        hit = b.x >= wlx - reach && b.x <= wlx + resolution + reach && b.y >= wly - reach &&
+              b.y <= wly + resolution + reach && b.z >= wlz - reach && b.z <= wlz + span + reach;
+      }
+      unsigned mask = __ballot_sync(0xffffffffu, hit);
+      while (mask) {
+        const int mm = wb + __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int chm = s_ch[mm];
+        if (chm != cur) {
+          if (cur >= 0) {
+            float v = acc;
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            if ((lane & 7) == 0) s_out[pv * CH + cur] = __float2half(v * 0.125f);
+          }
+          cur = chm;
+          acc = 0.f;
+        }
+        const float4 b = s_atom[mm];
+        const float dx = gx - b.x, dy = gy - b.y, dz = gz - b.z;
+        const float tt = (dx * dx + dy * dy + dz * dz) * s_inv[mm];  // (d/r)^2
+        if (__any_sync(0xffffffffu, tt < 2.25f)) {
+          const float g = fast_ex2(tt * kLog2e2);                    // exp(-2 d^2/r^2)
+          const float q = tt * fast_rsqrt(tt);                       // d/r
+          const float u = fmaf(q, kA, kB);                           // (2q-3)/e  ->  u^2 = e^-2 (4q^2-12q+9)
+          float val = tt <= 1.0f ? g : u * u;
+          val = tt < 2.25f ? val : 0.f;
+          acc += val;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (cur >= 0) {
+    float v = acc;
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    if ((lane & 7) == 0) s_out[pv * CH + cur] = __float2half(v * 0.125f);
+  }
+  __syncthreads();
+  // write the pooled tile: 64 pooled voxels x C8 chunks of 16 B
+  for (int e = threadIdx.x; e < 64 * C8; e += 512) {
+    const int c8 = e >> 6, q = e & 63;
+    const int pi = q >> 4, pj = (q >> 2) & 3, pk = q & 3;
+    const int x = ti * 4 + pi, y = tj * 4 + pj, z = tk * 4 + pk;
+    const uint4 v = *reinterpret_cast<const uint4*>(&s_out[q * CH + c8 * 8]);
+    x0[(((size_t)p * D + x) * C8 + c8) * Lp + (size_t)(y + 1) * P + (z + 1)] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Kernel B: 3x3x3 convolution as a tcgen05 implicit GEMM (see the header comment).
+struct ConvTcParams {
+  const uint4* xin;   // [group][x][c8][Lp]
+  const uint4* wp;    // [NB][9][C8][96]
+  const float* bias;  // [Cout]
+  __half* out;        // [pose][D][D][D][Cout]
+  int D, P, G, T, NB, Lp, Cout, n_poses, relu;
+};
+
+constexpr int kTcStages = 4;
+constexpr int kTcSlots = 8;       // TMEM ring: 8 plane slots x 32 fp32 columns = 256 columns
+constexpr int kSlabMax = 128 + 2 * 27;
+
+template <int CIN>
+struct ConvTcSmem {
+  static constexpr int C8 = CIN / 8;
+  static constexpr int kWBytes = 9 * C8 * 96 * 16;
+  static constexpr int kStageBytes = ((C8 * kSlabMax * 16) + 127) / 128 * 128;
+  static constexpr int kBarOff = kWBytes + kTcStages * kStageBytes;
+  static constexpr int kTotal = kBarOff + 512;
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
+  using S = ConvTcSmem<CIN>;
+  constexpr int C8 = S::C8;
+  constexpr int R = kTcSlots;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_w = smem;
+  uint8_t* s_stage = smem + S::kWBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
+  uint64_t* full = bars;                        // [kTcStages]
+  uint64_t* empty = bars + kTcStages;           // [kTcStages]
+  uint64_t* accf = bars + 2 * kTcStages;        // [R]
+  uint64_t* acce = bars + 2 * kTcStages + R;    // [R]
+  uint64_t* wbar = bars + 2 * kTcStages + 2 * R;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 2 * R + 1);
+  float* s_bias = reinterpret_cast<float*>(bars + 2 * kTcStages + 2 * R + 2);  // 32 floats
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = blockIdx.x % p.NB;
+  const int j = (blockIdx.x / p.NB) % p.T;
+  const int g = blockIdx.x / (p.NB * p.T);
+  const int D = p.D, P = p.P;
+  const int SL = 128 + 2 * (P + 1);
+  const uint32_t slab_row = (uint32_t)SL * 16u;  // bytes between K chunks of the A slab
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTcStages; s++) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < R; s++) { ptx::mbar_init(&accf[s], 1); ptx::mbar_init(&acce[s], 128); }
+    ptx::mbar_init(wbar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (threadIdx.x < 32) s_bias[threadIdx.x] = p.bias[nb * 32 + threadIdx.x];
+  if (warp == 1) {
+    ptx::tmem_alloc(s_tmem, R * 32);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===== producer: weights once, then one A slab per input plane =====
+    if (lane == 0) {
+      ptx::mbar_expect_tx(wbar, S::kWBytes);
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wp) + (size_t)nb * S::kWBytes;
+      for (int t9 = 0; t9 < 9; t9++)
+        ptx::bulk_g2s(s_w + t9 * (S::kWBytes / 9), wsrc + t9 * (S::kWBytes / 9), S::kWBytes / 9, wbar);
+      const uint4* xg = p.xin + (size_t)g * D * C8 * p.Lp + (size_t)128 * j;
+      for (int it = 0; it < D; it++) {
+        const int st = it % kTcStages, ph = (it / kTcStages) & 1;
+        ptx::mbar_wait(&empty[st], ph ^ 1);
+        ptx::mbar_expect_tx(&full[st], (uint32_t)C8 * slab_row);
+        uint8_t* dst = s_stage + (size_t)st * S::kStageBytes;
+        for (int c8 = 0; c8 < C8; c8++)
+          ptx::bulk_g2s(dst + (size_t)c8 * slab_row, xg + ((size_t)it * C8 + c8) * p.Lp, slab_row, &full[st]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      ptx::mbar_wait(wbar, 0);
+      const uint32_t w_base = ptx::smem_u32(s_w);
+      for (int it = 0; it < D; it++) {
+        const int xi = it + 1;
+        const int st = it % kTcStages, ph = (it / kTcStages) & 1;
+        const int lo = xi > 1 ? xi - 1 : 1, hi = xi < D ? xi + 1 : D;
+        const int fresh_lo = xi == 1 ? 1 : xi + 1;  // output planes >= fresh_lo get their first contribution now
+        for (int xo = fresh_lo; xo <= hi; xo++) {
+          const int u = (xo - 1) / R;
+          if (u > 0) ptx::mbar_wait(&acce[xo % R], (u - 1) & 1);
+        }
+        ptx::mbar_wait(&full[st], ph);
+        ptx::tc_fence_after();
+        // runs of output planes with consecutive TMEM slots (and, for the very first MMA of the plane, equal
+        // freshness): {first plane, #planes}
+        int run_a[2][3], run_n[2][3], nruns[2];
+        for (int first = 0; first < 2; first++) {
+          int nr = 0, rs = lo;
+          for (int xo = lo; xo <= hi; xo++) {
+            const bool last = xo == hi;
+            const bool brk = last || ((xo + 1) % R != (xo % R) + 1) || (first && ((xo + 1 >= fresh_lo) != (xo >= fresh_lo)));
+            if (brk) { run_a[first][nr] = rs; run_n[first][nr] = xo - rs + 1; nr++; rs = xo + 1; }
+          }
+          nruns[first] = nr;
+        }
+        const uint32_t a_stage = ptx::smem_u32(s_stage + (size_t)st * S::kStageBytes);
+        for (int t9 = 0; t9 < 9; t9++) {
+          const int off = (P + 1) + (t9 / 3 - 1) * P + (t9 % 3 - 1);
+          for (int ks = 0; ks < CIN / 16; ks++) {
+            const int first = (t9 == 0 && ks == 0) ? 1 : 0;
+            const uint64_t adesc = ptx::smem_desc(a_stage + (uint32_t)(2 * ks) * slab_row + (uint32_t)off * 16u, slab_row, 128);
+            const uint32_t b_addr = w_base + (uint32_t)((t9 * C8 + 2 * ks) * 96 * 16);
+            for (int r = 0; r < nruns[first]; r++) {
+              const int a0 = run_a[first][r], nn = run_n[first][r];
+              const uint64_t bdesc = ptx::smem_desc(b_addr + (uint32_t)(a0 - (xi - 1)) * 512u, 96 * 16, 128);
+              const uint32_t accum = (first && a0 >= fresh_lo) ? 0u : 1u;
+              ptx::mma_f16_ss(tmem_base + (uint32_t)(a0 % R) * 32u, adesc, bdesc, ptx::idesc_f16(128, 32 * nn), accum);
+            }
+          }
+        }
+        ptx::tc_commit(&empty[st]);                       // slab consumed
+        if (xi >= 2) ptx::tc_commit(&accf[(xi - 1) % R]);  // output plane xi-1 has all three input planes
+        if (xi == D) ptx::tc_commit(&accf[D % R]);
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> bias/ReLU -> fp16 -> global =====
+    const int q4 = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q4 * 32 + lane;
+    const int m = (P + 1) + 128 * j + row;
+    const int qpose = m / (P * P), rem = m % (P * P);
+    const int y = rem / P, z = rem % P;
+    const int pose = g * p.G + qpose;
+    const bool valid = qpose < p.G && pose < p.n_poses && y >= 1 && y <= D && z >= 1 && z <= D;
+    __half* obase = p.out + (((size_t)pose * D * D + (size_t)(y - 1)) * D + (z - 1)) * p.Cout + nb * 32;
+    const size_t plane_stride = (size_t)D * D * p.Cout;
+    for (int xo = 1; xo <= D; xo++) {
+      const int slot = xo % R, u = (xo - 1) / R;
+      ptx::mbar_wait(&accf[slot], u & 1);
+      ptx::tc_fence_after();
+      uint32_t v[32];
+      ptx::tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)slot * 32u, v);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&acce[slot]);
+      if (valid) {
+        uint4 o[4];
+        uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+          float f0 = __uint_as_float(v[2 * c]) + s_bias[2 * c];
+          float f1 = __uint_as_float(v[2 * c + 1]) + s_bias[2 * c + 1];
+          if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+          const __half2 h = __floats2half2_rn(f0, f1);
+          ow[c] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(obase + (size_t)(xo - 1) * plane_stride);
+        dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2]; dst[3] = o[3];
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, R * 32);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Kernel C: pointwise (1x1x1) convolution + bias + ReLU + 2x2x2 average pool + re-layout for the next conv.
+// in : Y [pose][D][D][D][C] fp16 (already ReLU'd output of the preceding 3^3 conv)
+// out: chunk-planar padded grouped layout with Dn = D/2.
+// One warp handles 2 pooled voxels = 16 fine voxels as the M dimension of mma.sync.m16n8k16 (fp32 accumulate).
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) pointwise_pool_kernel(const __half* __restrict__ yin, const __half* __restrict__ w,
+                                                             const float* __restrict__ bias, uint4* __restrict__ xout,
+                                                             int D, int n_poses, int Gn, int Lpn) {
+  constexpr int NT = C / 8, KS = C / 16;
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int Dn = D / 2, Pn = Dn + 2, C8n = C / 8;
+  uint32_t bf[NT][KS][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) {
+      const __half* wr = w + (size_t)(nt * 8 + g) * C + ks * 16 + 2 * t;
+      bf[nt][ks][0] = *reinterpret_cast<const uint32_t*>(wr);
+      bf[nt][ks][1] = *reinterpret_cast<const uint32_t*>(wr + 8);
+    }
+  float bs[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; nt++) { bs[nt][0] = bias[nt * 8 + 2 * t]; bs[nt][1] = bias[nt * 8 + 2 * t + 1]; }
+
+  const long long n_pairs = (long long)n_poses * Dn * Dn * Dn / 2;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int di = (g >> 2) & 1, dj = (g >> 1) & 1, dk = g & 1;
+  for (long long pair = warp_global; pair < n_pairs; pair += n_warps) {
+    // pooled voxels 2*pair (rows 0-7) and 2*pair+1 (rows 8-15); Dn is even so both share pose, x, y
+    const long long pvA = 2 * pair;
+    const int z0 = (int)(pvA % Dn);
+    long long r = pvA / Dn;
+    const int y0 = (int)(r % Dn); r /= Dn;
+    const int x0 = (int)(r % Dn);
+    const int pose = (int)(r / Dn);
+    const __half* rowA = yin + ((((size_t)pose * D + (2 * x0 + di)) * D + (2 * y0 + dj)) * D + (2 * z0 + dk)) * C;
+    const __half* rowB = rowA + (size_t)2 * C;  // next pooled voxel in z: fine z + 2
+    float acc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) {
+      uint32_t a[4];
+      a[0] = *reinterpret_cast<const uint32_t*>(rowA + ks * 16 + 2 * t);
+      a[1] = *reinterpret_cast<const uint32_t*>(rowB + ks * 16 + 2 * t);
+      a[2] = *reinterpret_cast<const uint32_t*>(rowA + ks * 16 + 8 + 2 * t);
+      a[3] = *reinterpret_cast<const uint32_t*>(rowB + ks * 16 + 8 + 2 * t);
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) mma_16816(acc[nt], a, bf[nt][ks][0], bf[nt][ks][1]);
+    }
+    const int grp = pose / Gn, q = pose % Gn;
+    const size_t posA = (size_t)q * Pn * Pn + (size_t)(y0 + 1) * Pn + (z0 + 1);
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        float x = fmaxf(acc[nt][e] + bs[nt][e & 1], 0.f);
+        x += __shfl_xor_sync(0xffffffffu, x, 4);
+        x += __shfl_xor_sync(0xffffffffu, x, 8);
+        x += __shfl_xor_sync(0xffffffffu, x, 16);
+        v[e] = x * 0.125f;
+      }
+      if (g == 0) {
+        uint32_t* base = reinterpret_cast<uint32_t*>(xout + (((size_t)grp * Dn + x0) * C8n + nt) * Lpn + posA);
+        const __half2 hA = __floats2half2_rn(v[0], v[1]);
+        const __half2 hB = __floats2half2_rn(v[2], v[3]);
+        base[t] = *reinterpret_cast<const uint32_t*>(&hA);      // pooled voxel A
+        base[4 + t] = *reinterpret_cast<const uint32_t*>(&hB);  // pooled voxel B = next position
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Kernel D: FC heads on conv5's channels-last fp16 output [pose][216][128].
+__global__ void __launch_bounds__(256) fc_heads_f16_kernel(const __half* __restrict__ y5, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ out3) {
+  constexpr int F = 27648;
+  __shared__ float red[3][8];
+  const __half2* f = reinterpret_cast<const __half2*>(y5 + (size_t)blockIdx.x * F);
+  float a0 = 0, a1 = 0, a2 = 0;
+  for (int e = threadIdx.x; e < F / 2; e += 256) {
+    const float2 x = __half22float2(f[e]);
+    const float2 w0 = *reinterpret_cast<const float2*>(w + 2 * e);
+    const float2 w1 = *reinterpret_cast<const float2*>(w + F + 2 * e);
+    const float2 w2 = *reinterpret_cast<const float2*>(w + 2 * (size_t)F + 2 * e);
+    a0 = fmaf(x.x, w0.x, fmaf(x.y, w0.y, a0));
+    a1 = fmaf(x.x, w1.x, fmaf(x.y, w1.y, a1));
+    a2 = fmaf(x.x, w2.x, fmaf(x.y, w2.y, a2));
+  }
+  for (int o = 16; o; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][warp] = a0; red[1][warp] = a1; red[2][warp] = a2; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float v = bias[threadIdx.x];
+    for (int q = 0; q < 8; q++) v += red[threadIdx.x][q];
+    out3[(size_t)blockIdx.x * 3 + threadIdx.x] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+template <int CIN>
+static void launch_conv_tc(const ConvTc& c, const ActLayout& L, const uint4* xin, __half* out, int n_poses, cudaStream_t s) {
+  using S = ConvTcSmem<CIN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GB_CUDA(cudaFuncSetAttribute(conv3_tc_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    attr_set = true;
+  }
+  GB_CHECK(c.cin == CIN, "conv cin");
+  ConvTcParams p;
+  p.xin = xin; p.wp = c.wp; p.bias = c.bias; p.out = out;
+  p.D = L.D; p.P = L.P; p.G = L.G; p.T = L.T; p.NB = c.cout / 32; p.Lp = L.Lp; p.Cout = c.cout; p.n_poses = n_poses;
+  p.relu = 1;
+  const int n_groups = (n_poses + L.G - 1) / L.G;
+  conv3_tc_kernel<CIN><<<n_groups * L.T * p.NB, 192, S::kTotal, s>>>(p);
+}
+
+static size_t act_bytes(const ActLayout& L, int n_poses) {
+  const size_t n_groups = (n_poses + L.G - 1) / L.G;
+  return (n_groups * L.group_u4() + 256) * sizeof(uint4);
+}
+
+struct TcDebug {
+  const void* ptr[8];
+  size_t bytes[8];
+};
+static thread_local TcDebug t_debug;
+const void* tc_debug_buffer(int i, size_t* bytes) {
+  if (i < 0 || i >= 8) return nullptr;
+  if (bytes) *bytes = t_debug.bytes[i];
+  return t_debug.ptr[i];
+}
+
+int tc_forward(const Model& m, const TcPoseBatch& pb, TcGridWorkspace& gw, TcWorkspace& ws, float* out3, cudaStream_t s,
+               Profiler* prof) {
+  GB_CHECK(tc_supported(m), "tensor-core path supports the default2018 family only (so far)");
+  auto tw = get_tc_weights(m);
+  int launches = 0;
+  const int nb = pb.n_poses;
+  const ActLayout L1 = make_layout(24, 1, 32), L3 = make_layout(12, 2, 32), L5 = make_layout(6, 2, 64);
+  // --- pose lists + pooled grid (shared by all models of the grid group that avg-pool) ---
+  if (!gw.valid[0]) {
+    const int cap = std::max(1, pb.n_rec + pb.max_pose_atoms);
+    if (!gw.lists_valid) {
+      const size_t need = (size_t)nb * cap;
+      if (gw.list_cap < need) {
+        if (gw.list_xyzr) cudaFree(gw.list_xyzr);
+        if (gw.list_ch) cudaFree(gw.list_ch);
+        GB_CUDA(cudaMalloc(&gw.list_xyzr, need * sizeof(float4)));
+        GB_CUDA(cudaMalloc(&gw.list_ch, need * sizeof(int)));
+        gw.list_cap = need;
+      }
+      if (gw.listn_cap < (size_t)nb) {
+        if (gw.list_n) cudaFree(gw.list_n);
+        GB_CUDA(cudaMalloc(&gw.list_n, (size_t)nb * sizeof(int)));
+        gw.listn_cap = nb;
+      }
+      {
+        ProfScope ps(prof, "tc_build_pose_lists", s);
+        launch_build_pose_lists(pb.rec_xyzr, pb.rec_ch, pb.n_rec, pb.lig_xyzr, pb.lig_ch, pb.lig_off, pb.centers, nb,
+                                pb.dimension / 2.f, cap, gw.list_xyzr, gw.list_ch, gw.list_n, s);
+      }
+      launches++;
+      gw.lists_valid = true;
+    }
+    const size_t need0 = act_bytes(L1, nb);
+    if (gw.cap[0] < need0) {
+      if (gw.x0[0]) cudaFree(gw.x0[0]);
+      GB_CUDA(cudaMalloc(&gw.x0[0], need0));
+      GB_CUDA(cudaMemsetAsync(gw.x0[0], 0, need0, s));
+      gw.cap[0] = need0;
+    }
+    {
+      ProfScope ps(prof, "tc_voxelize_pool", s);
+      voxelize_pool_f16_kernel<<<dim3(216, nb), 512, 0, s>>>(gw.list_xyzr, gw.list_ch, gw.list_n, cap, pb.centers,
+                                                             pb.resolution, pb.dimension,
+                                                             reinterpret_cast<uint4*>(gw.x0[0]), L1.Lp, L1.D, L1.P, L1.C8);
+    }
+    launches++;
+    gw.valid[0] = true;
+  }
+  const uint4* x0 = reinterpret_cast<const uint4*>(gw.x0[0]);
+  // --- workspaces: 0 = Y (conv outputs, reused), 1 = X2, 2 = X4 ---
+  ws.ensure(0, (size_t)nb * 24 * 24 * 24 * 32 * sizeof(__half) + 1024);
+  ws.ensure(1, act_bytes(L3, nb));
+  ws.ensure(2, act_bytes(L5, nb));
+  ws.ensure(3, (size_t)nb * 216 * 128 * sizeof(__half) + 1024);
+  __half* Y = reinterpret_cast<__half*>(ws.buf[0]);
+  uint4* X2 = reinterpret_cast<uint4*>(ws.buf[1]);
+  uint4* X4 = reinterpret_cast<uint4*>(ws.buf[2]);
+  __half* Y5 = reinterpret_cast<__half*>(ws.buf[3]);
+  const int pw_blocks = 148 * 8;
+  {
+    ProfScope ps(prof, "tc_conv1_3x3x3_28x32_d24", s);
+    launch_conv_tc<32>(tw->conv1, L1, x0, Y, nb, s);
+  }
+  {
+    ProfScope ps(prof, "tc_pw2_pool", s);
+    pointwise_pool_kernel<32><<<pw_blocks, 256, 0, s>>>(Y, tw->pw2.w, tw->pw2.bias, X2, 24, nb, L3.G, L3.Lp);
+  }
+  {
+    ProfScope ps(prof, "tc_conv3_3x3x3_32x64_d12", s);
+    launch_conv_tc<32>(tw->conv3, L3, X2, Y, nb, s);
+  }
+  {
+    ProfScope ps(prof, "tc_pw4_pool", s);
+    pointwise_pool_kernel<64><<<pw_blocks, 256, 0, s>>>(Y, tw->pw4.w, tw->pw4.bias, X4, 12, nb, L5.G, L5.Lp);
+  }
+  {
+    ProfScope ps(prof, "tc_conv5_3x3x3_64x128_d6", s);
+    launch_conv_tc<64>(tw->conv5, L5, X4, Y5, nb, s);
+  }
+  {
+    ProfScope ps(prof, "tc_fc_heads", s);
+    fc_heads_f16_kernel<<<nb, 256, 0, s>>>(Y5, tw->fcw, tw->fcb, out3);
+  }
+  launches += 6;
+  t_debug.ptr[0] = gw.x0[0]; t_debug.bytes[0] = act_bytes(L1, nb);
+  t_debug.ptr[1] = Y;        t_debug.bytes[1] = (size_t)nb * 1728 * 64 * sizeof(__half);  // holds Y3 after the pass
+  t_debug.ptr[2] = X2;       t_debug.bytes[2] = act_bytes(L3, nb);
+  t_debug.ptr[3] = X4;       t_debug.bytes[3] = act_bytes(L5, nb);
+  t_debug.ptr[4] = Y5;       t_debug.bytes[4] = (size_t)nb * 216 * 128 * sizeof(__half);
+  return launches;
+}
+
 }  // namespace gb

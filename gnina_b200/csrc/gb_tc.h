@@ -36,4 +36,7 @@ bool tc_supported(const Model& m);
 int tc_forward(const Model& m, const TcPoseBatch& pb, TcGridWorkspace& gw, TcWorkspace& ws, float* out3, cudaStream_t s,
                Profiler* prof = nullptr);
 
+// test-only access to the buffers of the most recent tc_forward on this thread: 0 x0, 1 y(3), 2 x2, 3 x4, 4 y5
+const void* tc_debug_buffer(int i, size_t* bytes);
+
 }  // namespace gb

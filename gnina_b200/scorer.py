@@ -182,6 +182,14 @@ class CNNScorer:
     def profile_reset(self):
         capi.check(capi.lib().gb_cnn_profile_reset(self._h))
 
+    def debug_read(self, name):
+        """test-only: raw fp16 view of an internal fast-path buffer of the last pass"""
+        n = C.c_size_t()
+        capi.check(capi.lib().gb_cnn_debug_read(self._h, name.encode(), None, 0, C.byref(n)))
+        buf = np.empty(n.value // 2, np.float16)
+        capi.check(capi.lib().gb_cnn_debug_read(self._h, name.encode(), buf.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
+        return buf
+
     def voxelize(self, lig_xyz, lig_types, pose_offsets, centers=None, model_index=0):
         xyz, t, off, c = self._poses(lig_xyz, lig_types, pose_offsets, centers)
         info = self.model_info(model_index)

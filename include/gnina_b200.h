@@ -117,6 +117,11 @@ int64_t gb_cnn_kernel_launches(gb_cnn* h); /* kernels launched by this handle so
 int gb_cnn_profile_read(gb_cnn* h, int index, char* name, int name_cap, double* total_ms, int64_t* count);
 int gb_cnn_profile_reset(gb_cnn* h);
 
+/* Test-only (no reference counterpart): raw copy of an internal fast-path buffer of the most recent pass on the
+ * calling thread: "x0" (pooled fp16 grid), "x2", "x4" (conv inputs), "y3", "y5" (conv outputs).  out == NULL
+ * just reports the size. */
+int gb_cnn_debug_read(gb_cnn* h, const char* name, void* out, size_t cap_bytes, size_t* nbytes);
+
 /* GridMaker::forward (libmolgrid; call site lib/torch_model.cpp:181) for parity tests: voxelise the poses for
  * model `model_index` and copy the fp32 grids [n_poses][C][N][N][N] (reference layout, z fastest) to the host. */
 int gb_cnn_voxelize(gb_cnn* h, int model_index, const float* lig_xyz, const int32_t* lig_type,

@@ -1,0 +1,76 @@
+"""GPU parity tests of the fast path (fused pooled voxeliser + tcgen05 fp16 convolutions), through the C ABI.
+
+Stated tolerance of the fast mode (fp16 operands, fp32 accumulation): |dCNNscore| <= 2e-3, |dCNNaffinity| <= 1e-2
+against the fp64 run of the reference's own TorchScript model (the reference accepts 1e-3 between its own CPU and
+GPU paths, test/gnina/test_cnn.py:43)."""
+import os
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL_SCORE, TOL_AFF = 2e-3, 1e-2
+
+
+@pytest.fixture(scope="module")
+def kat(golden_dir):
+    return np.load(os.path.join(golden_dir, "cnn_kat.npz"))
+
+
+def _fast(names):
+    from gnina_b200 import CNNScorer
+    s = CNNScorer(names)
+    s.set_option("precision", 1)
+    return s
+
+
+def test_fast_path_is_the_default_for_default2018():
+    from gnina_b200 import CNNScorer
+    assert CNNScorer(["crossdock_default2018"]).get_option("precision") == 1
+
+
+@pytest.mark.parametrize("name", ["crossdock_default2018", "crossdock_default2018_KD_4", "all_default_to_default_1_3_1"])
+def test_fast_scores_match_reference_pt(kat, name):
+    s = _fast([name])
+    s.set_receptor(kat["rec_xyz"], kat["rec_types"])
+    pose, aff, loss, var = s.score_batch(kat["lig_xyz"], kat["lig_types"], kat["pose_offsets"])
+    assert np.abs(pose - kat[name + "_pose_f64"]).max() < TOL_SCORE
+    assert np.abs(aff - kat[name + "_aff_f64"]).max() < TOL_AFF
+
+
+def test_fast_intermediates_match_oracle(kat):
+    import tc_layout as tl
+    from gnina_b200 import model_blob
+    from oracle import pipeline
+    name, n = "crossdock_default2018", 3
+    offs = kat["pose_offsets"][:n + 1]
+    lx, lt = kat["lig_xyz"][:offs[-1]], kat["lig_types"][:offs[-1]]
+    blob = model_blob.load_model(name)
+    ref = tl.oracle_intermediates(blob, pipeline.OracleModel(blob).grids(kat["rec_xyz"], kat["rec_types"], lx, lt, offs))
+    s = _fast([name])
+    s.set_receptor(kat["rec_xyz"], kat["rec_types"])
+    s.score_batch(lx, lt, offs)
+    x0, border = tl.decode_chunk_planar(s.debug_read("x0"), n, 24, 1, 32)
+    assert border == 0.0 and np.abs(x0[:, 28:]).max() == 0.0
+    assert np.abs(x0[:, :28] - ref["x0"]).max() < 2e-3          # fp16 rounding of densities <= ~3
+    x2, border = tl.decode_chunk_planar(s.debug_read("x2"), n, 12, 2, 32)
+    assert border == 0.0
+    for tag, got in (("x2", x2), ("y3", tl.decode_channels_last(s.debug_read("y3"), n, 12, 64)),
+                     ("y5", tl.decode_channels_last(s.debug_read("y5"), n, 6, 128))):
+        scale = np.abs(ref[tag]).max()
+        assert np.abs(got - ref[tag]).max() < 4e-3 * scale, tag
+
+
+def test_fast_matches_fp32_validation_mode_on_many_ragged_poses():
+    """size-independent property: both precisions of the library agree pose by pose on a larger ragged batch"""
+    from gnina_b200 import CNNScorer, synth
+    rx, rt = synth.make_receptor(2000, box=50)
+    lx, lt, offs = synth.make_screen(37, seed=5, trans_box=12)
+    a = CNNScorer(["crossdock_default2018"], precision=0)
+    b = CNNScorer(["crossdock_default2018"], precision=1)
+    for s in (a, b):
+        s.set_receptor(rx, rt)
+    ra, rb = a.score_batch(lx, lt, offs), b.score_batch(lx, lt, offs)
+    assert np.abs(ra[0] - rb[0]).max() < TOL_SCORE and np.abs(ra[1] - rb[1]).max() < TOL_AFF
+    b.set_option("max_batch", 5)   # odd chunk sizes exercise the half-filled pose groups
+    rc = b.score_batch(lx, lt, offs)
+    assert np.abs(rc[0] - rb[0]).max() < 1e-6 and np.abs(rc[1] - rb[1]).max() < 1e-5
