@@ -200,49 +200,69 @@ __device__ __forceinline__ int block_ordered_slot512(bool pred, int* s_warp_coun
   return base + __popc(mask & ((1u << lane) - 1u));
 }
 
+// v2: thread = one POOLED voxel (its 8 sub-voxels share the scaled coordinate differences), CTA = 8x8x8 pooled
+// voxels (16^3 fine voxels, an 8 A cube), warp = 4x4x2 pooled voxels.  Per warp-candidate atom a warp-uniform
+// guard skips the 8-evaluation body unless some lane's pooled voxel is within reach.  Density per sub-voxel, with
+// t = (d/r)^2 clamped to 2.25:   t <= 1 : exp(-2t) = ex2(t * -2log2e)   (one MUFU)
+//                                t >  1 : u(t)^2, u = (2 sqrt(t) - 3)/e as a degree-4 polynomial (|err| < 2e-5,
+//                                         u(2.25) = 0 so the clamp also implements the cutoff at 1.5 r).
+__device__ __forceinline__ float density_t(float t) {
+  const float tc = fminf(t, 2.25f);
+  const float g = fast_ex2(tc * -2.885390081777927f);
+  float u = fmaf(tc, -0.005817742552608252f, 0.052687861025333405f);
+  u = fmaf(u, tc, -0.20902030169963837f);
+  u = fmaf(u, tc, 0.6502527594566345f);
+  u = fmaf(u, tc, -0.8559605479240417f);
+  return tc <= 1.0f ? g : u * u;
+}
+
+constexpr int kVoxChunk = 256;
+
 __global__ void __launch_bounds__(512) voxelize_pool_f16_kernel(const float4* __restrict__ list_xyzr,
                                                                 const int* __restrict__ list_ch,
                                                                 const int* __restrict__ list_n, int cap,
                                                                 const float* __restrict__ centers, float resolution,
                                                                 float dimension, uint4* __restrict__ x0, int Lp, int D,
                                                                 int P, int C8) {
-  __shared__ float4 s_atom[512];
-  __shared__ float s_inv[512];
-  __shared__ int s_ch[512];
+  __shared__ float4 s_atom[kVoxChunk];   // x, y, z, 1/r
+  __shared__ float s_thr2[kVoxChunk];    // (1.5 + half-diagonal/r)^2 : pooled-voxel centre test, in units of r
+  __shared__ float s_reach[kVoxChunk];   // 1.5 r
+  __shared__ int s_ch[kVoxChunk];
   __shared__ int s_counts[16];
-  __shared__ __align__(16) __half s_out[64 * 40];  // [pooled voxel][C8*8 <= 40 channels]
+  __shared__ __half s_out[32 * 512];     // [channel][pooled voxel]
   const int CH = C8 * 8;
   const int p = blockIdx.y;
+  const int tiles = D / 8;
   const int t = blockIdx.x;
-  const int tiles = (2 * D) / 8;
-  const int ti = t / (tiles * tiles), tj = (t / tiles) % tiles, tk = t % tiles;
+  const int tx = t / (tiles * tiles), ty = (t / tiles) % tiles, tz = t % tiles;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int k = (lane & 1) | (((lane >> 3) & 3) << 1);
-  const int j = ((lane >> 1) & 1) | ((warp & 3) << 1);
-  const int i = ((lane >> 2) & 1) | ((warp >> 2) << 1);
-  const int pv = ((warp >> 2) * 4 + (warp & 3)) * 4 + ((lane >> 3) & 3);
-  for (int e = threadIdx.x; e < 64 * CH; e += 512) s_out[e] = __float2half(0.f);
+  const int wx = warp & 1, wy = (warp >> 1) & 1, wz = warp >> 2;
+  const int px = wx * 4 + (lane & 3), py = wy * 4 + ((lane >> 2) & 3), pz = wz * 2 + (lane >> 4);
+  const int pv = (px * 8 + py) * 8 + pz;
+  for (int e = threadIdx.x; e < CH * 512 / 2; e += 512) reinterpret_cast<uint32_t*>(s_out)[e] = 0u;
   const float half = dimension * 0.5f;
   const float ox = centers[3 * p] - half, oy = centers[3 * p + 1] - half, oz = centers[3 * p + 2] - half;
-  const float gx = ox + (ti * 8 + i) * resolution, gy = oy + (tj * 8 + j) * resolution, gz = oz + (tk * 8 + k) * resolution;
-  const float lox = ox + ti * 8 * resolution, loy = oy + tj * 8 * resolution, loz = oz + tk * 8 * resolution;
-  const float span = 7.f * resolution;
-  // warp footprint: i in {2*(warp>>2), +1}, j in {2*(warp&3), +1}, k in 0..7
-  const float wlx = lox + 2 * (warp >> 2) * resolution, wly = loy + 2 * (warp & 3) * resolution, wlz = loz;
+  const float hres = 0.5f * resolution;
+  // centre of this thread's pooled voxel (between fine voxels 2X and 2X+1)
+  const float cx = ox + (2 * (tx * 8 + px) + 0.5f) * resolution;
+  const float cy = oy + (2 * (ty * 8 + py) + 0.5f) * resolution;
+  const float cz = oz + (2 * (tz * 8 + pz) + 0.5f) * resolution;
+  // CTA box and warp box (fine-voxel coordinates covered)
+  const float lox = ox + 16 * tx * resolution, loy = oy + 16 * ty * resolution, loz = oz + 16 * tz * resolution;
+  const float span = 15.f * resolution;
+  const float wlx = lox + 8 * wx * resolution, wly = loy + 8 * wy * resolution, wlz = loz + 4 * wz * resolution;
+  const float wsx = 7.f * resolution, wsz = 3.f * resolution;
   const float4* la = list_xyzr + (size_t)p * cap;
   const int* lc = list_ch + (size_t)p * cap;
   const int n = list_n[p];
   int cur = -1;
   float acc = 0.f;
-  const float kLog2e2 = -2.885390081777927f;  // -2*log2(e)
-  const float kA = 0.7357588823428847f;       // 2/e
-  const float kB = -1.1036383235143270f;      // -3/e
-  for (int base = 0; base < n; base += 512) {
-    const int ai = base + threadIdx.x;
+  for (int base = 0; base < n; base += kVoxChunk) {
     bool keep = false;
     float4 a = make_float4(0, 0, 0, 0);
     int ch = 0;
-    if (ai < n) {
+    const int ai = base + threadIdx.x;
+    if (threadIdx.x < kVoxChunk && ai < n) {
       a = la[ai];
       ch = lc[ai];
       const float reach = 1.5f * a.w + 1e-4f;
@@ -252,8 +272,11 @@ __global__ void __launch_bounds__(512) voxelize_pool_f16_kernel(const float4* __
     int tot;
     const int slot = block_ordered_slot512(keep, s_counts, tot);
     if (keep) {
-      s_atom[slot] = a;
-      s_inv[slot] = 1.0f / (a.w * a.w);
+      const float inv = 1.0f / a.w;
+      const float thr = 1.5f + 1.7320508f * hres * inv + 1e-3f;  // sub-voxel offsets are +-res/2 per axis
+      s_atom[slot] = make_float4(a.x, a.y, a.z, inv);
+      s_thr2[slot] = thr * thr;
+      s_reach[slot] = 1.5f * a.w + 1e-4f;
       s_ch[slot] = ch;
     }
     __syncthreads();
@@ -262,9 +285,9 @@ __global__ void __launch_bounds__(512) voxelize_pool_f16_kernel(const float4* __
       bool hit = false;
       if (m < tot) {
         const float4 b = s_atom[m];
-        const float reach = 1.5f * b.w + 1e-4f;
-        hit = b.x >= wlx - reach && b.x <= wlx + resolution + reach && b.y >= wly - reach &&
-              b.y <= wly + resolution + reach && b.z >= wlz - reach && b.z <= wlz + span + reach;
+        const float reach = s_reach[m];
+        hit = b.x >= wlx - reach && b.x <= wlx + wsx + reach && b.y >= wly - reach && b.y <= wly + wsx + reach &&
+              b.z >= wlz - reach && b.z <= wlz + wsz + reach;
       }
       unsigned mask = __ballot_sync(0xffffffffu, hit);
       while (mask) {
@@ -272,46 +295,40 @@ __global__ void __launch_bounds__(512) voxelize_pool_f16_kernel(const float4* __
         mask &= mask - 1;
         const int chm = s_ch[mm];
         if (chm != cur) {
-          if (cur >= 0) {
-            float v = acc;
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            if ((lane & 7) == 0) s_out[pv * CH + cur] = __float2half(v * 0.125f);
-          }
+          if (cur >= 0) s_out[cur * 512 + pv] = __float2half(acc * 0.125f);
           cur = chm;
           acc = 0.f;
         }
         const float4 b = s_atom[mm];
-        const float dx = gx - b.x, dy = gy - b.y, dz = gz - b.z;
-        const float tt = (dx * dx + dy * dy + dz * dz) * s_inv[mm];  // (d/r)^2
-        if (__any_sync(0xffffffffu, tt < 2.25f)) {
-          const float g = fast_ex2(tt * kLog2e2);                    // exp(-2 d^2/r^2)
-          const float q = tt * fast_rsqrt(tt);                       // d/r
-          const float u = fmaf(q, kA, kB);                           // (2q-3)/e  ->  u^2 = e^-2 (4q^2-12q+9)
-          float val = tt <= 1.0f ? g : u * u;
-          val = tt < 2.25f ? val : 0.f;
-          acc += val;
+        const float dx = (cx - b.x) * b.w, dy = (cy - b.y) * b.w, dz = (cz - b.z) * b.w;  // in units of r
+        const float tcen = dx * dx + dy * dy + dz * dz;
+        if (__any_sync(0xffffffffu, tcen < s_thr2[mm])) {
+          const float h = hres * b.w;
+          const float x0 = dx - h, x1 = dx + h, y0 = dy - h, y1 = dy + h, z0 = dz - h, z1 = dz + h;
+          const float sx0 = x0 * x0, sx1 = x1 * x1, sy0 = y0 * y0, sy1 = y1 * y1, sz0 = z0 * z0, sz1 = z1 * z1;
+          const float s00 = sx0 + sy0, s01 = sx0 + sy1, s10 = sx1 + sy0, s11 = sx1 + sy1;
+          acc += density_t(s00 + sz0) + density_t(s00 + sz1) + density_t(s01 + sz0) + density_t(s01 + sz1) +
+                 density_t(s10 + sz0) + density_t(s10 + sz1) + density_t(s11 + sz0) + density_t(s11 + sz1);
         }
       }
     }
     __syncthreads();
   }
-  if (cur >= 0) {
-    float v = acc;
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
-    if ((lane & 7) == 0) s_out[pv * CH + cur] = __float2half(v * 0.125f);
-  }
+  if (cur >= 0) s_out[cur * 512 + pv] = __float2half(acc * 0.125f);
   __syncthreads();
-  // write the pooled tile: 64 pooled voxels x C8 chunks of 16 B
-  for (int e = threadIdx.x; e < 64 * C8; e += 512) {
-    const int c8 = e >> 6, q = e & 63;
-    const int pi = q >> 4, pj = (q >> 2) & 3, pk = q & 3;
-    const int x = ti * 4 + pi, y = tj * 4 + pj, z = tk * 4 + pk;
-    const uint4 v = *reinterpret_cast<const uint4*>(&s_out[q * CH + c8 * 8]);
-    x0[(((size_t)p * D + x) * C8 + c8) * Lp + (size_t)(y + 1) * P + (z + 1)] = v;
+  // write the pooled tile: 512 pooled voxels x C8 chunks of 16 B, z fastest
+  for (int e = threadIdx.x; e < 512 * C8; e += 512) {
+    const int c8 = e >> 9, q = e & 511;
+    const int qx = q >> 6, qy = (q >> 3) & 7, qz = q & 7;
+    uint32_t w[4];
+#pragma unroll
+    for (int k2 = 0; k2 < 4; k2++) {
+      const uint16_t lo16 = *reinterpret_cast<const uint16_t*>(&s_out[(c8 * 8 + 2 * k2) * 512 + q]);
+      const uint16_t hi16 = *reinterpret_cast<const uint16_t*>(&s_out[(c8 * 8 + 2 * k2 + 1) * 512 + q]);
+      w[k2] = (uint32_t)lo16 | ((uint32_t)hi16 << 16);
+    }
+    const int x = tx * 8 + qx, y = ty * 8 + qy, z = tz * 8 + qz;
+    x0[(((size_t)p * D + x) * C8 + c8) * Lp + (size_t)(y + 1) * P + (z + 1)] = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -400,7 +417,14 @@ __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
     // ===== MMA issuer =====
     if (lane == 0) {
       ptx::mbar_wait(wbar, 0);
-      const uint32_t w_base = ptx::smem_u32(s_w);
+      // Descriptors are built once; per MMA only the 14-bit start-address fields change (plain integer adds).
+      const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 32) | (1ull << 46);         // SBO = 128 B, version 1
+      const uint64_t a_fixed = desc_hi | ((uint64_t)((uint32_t)SL & 0x3FFF) << 16);  // LBO = slab row (SL x 16 B)
+      const uint64_t b_fixed = desc_hi | ((uint64_t)96 << 16);                       // LBO = 96 rows x 16 B
+      const uint32_t b_addr16 = ptx::smem_u32(s_w) >> 4;
+      uint32_t aoff[9];
+#pragma unroll
+      for (int t9 = 0; t9 < 9; t9++) aoff[t9] = (uint32_t)((P + 1) + (t9 / 3 - 1) * P + (t9 % 3 - 1));
       for (int it = 0; it < D; it++) {
         const int xi = it + 1;
         const int st = it % kTcStages, ph = (it / kTcStages) & 1;
@@ -410,33 +434,41 @@ __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
           const int u = (xo - 1) / R;
           if (u > 0) ptx::mbar_wait(&acce[xo % R], (u - 1) & 1);
         }
+        // runs of output planes with consecutive TMEM slots: {tmem column, B row offset (16 B units), idesc}
+        uint32_t r_tm[2], r_boff[2], r_idesc[2];
+        int nr = 0;
+        {
+          int rs = lo;
+          for (int xo = lo; xo <= hi; xo++) {
+            if (xo == hi || ((xo + 1) % R != (xo % R) + 1)) {
+              r_tm[nr] = tmem_base + (uint32_t)(rs % R) * 32u;
+              r_boff[nr] = (uint32_t)(rs - (xi - 1)) * 32u;
+              r_idesc[nr] = ptx::idesc_f16(128, 32 * (xo - rs + 1));
+              nr++;
+              rs = xo + 1;
+            }
+          }
+        }
         ptx::mbar_wait(&full[st], ph);
         ptx::tc_fence_after();
-        // runs of output planes with consecutive TMEM slots (and, for the very first MMA of the plane, equal
-        // freshness): {first plane, #planes}
-        int run_a[2][3], run_n[2][3], nruns[2];
-        for (int first = 0; first < 2; first++) {
-          int nr = 0, rs = lo;
-          for (int xo = lo; xo <= hi; xo++) {
-            const bool last = xo == hi;
-            const bool brk = last || ((xo + 1) % R != (xo % R) + 1) || (first && ((xo + 1 >= fresh_lo) != (xo >= fresh_lo)));
-            if (brk) { run_a[first][nr] = rs; run_n[first][nr] = xo - rs + 1; nr++; rs = xo + 1; }
-          }
-          nruns[first] = nr;
+        const uint32_t a_addr16 = ptx::smem_u32(s_stage + (size_t)st * S::kStageBytes) >> 4;
+        // very first MMA of the plane: fresh output planes must be overwritten (accumulate = 0), one MMA per plane
+        {
+          const uint64_t adesc = a_fixed | (uint64_t)(a_addr16 + aoff[0]);
+          for (int xo = lo; xo <= hi; xo++)
+            ptx::mma_f16_ss(tmem_base + (uint32_t)(xo % R) * 32u, adesc,
+                            b_fixed | (uint64_t)(b_addr16 + (uint32_t)(xo - (xi - 1)) * 32u), ptx::idesc_f16(128, 32),
+                            xo >= fresh_lo ? 0u : 1u);
         }
-        const uint32_t a_stage = ptx::smem_u32(s_stage + (size_t)st * S::kStageBytes);
+#pragma unroll
         for (int t9 = 0; t9 < 9; t9++) {
-          const int off = (P + 1) + (t9 / 3 - 1) * P + (t9 % 3 - 1);
+#pragma unroll
           for (int ks = 0; ks < CIN / 16; ks++) {
-            const int first = (t9 == 0 && ks == 0) ? 1 : 0;
-            const uint64_t adesc = ptx::smem_desc(a_stage + (uint32_t)(2 * ks) * slab_row + (uint32_t)off * 16u, slab_row, 128);
-            const uint32_t b_addr = w_base + (uint32_t)((t9 * C8 + 2 * ks) * 96 * 16);
-            for (int r = 0; r < nruns[first]; r++) {
-              const int a0 = run_a[first][r], nn = run_n[first][r];
-              const uint64_t bdesc = ptx::smem_desc(b_addr + (uint32_t)(a0 - (xi - 1)) * 512u, 96 * 16, 128);
-              const uint32_t accum = (first && a0 >= fresh_lo) ? 0u : 1u;
-              ptx::mma_f16_ss(tmem_base + (uint32_t)(a0 % R) * 32u, adesc, bdesc, ptx::idesc_f16(128, 32 * nn), accum);
-            }
+            if (t9 == 0 && ks == 0) continue;
+            const uint64_t adesc = a_fixed | (uint64_t)(a_addr16 + aoff[t9] + (uint32_t)(2 * ks) * (uint32_t)SL);
+            const uint32_t bb = b_addr16 + (uint32_t)((t9 * C8 + 2 * ks) * 96);
+            ptx::mma_f16_ss(r_tm[0], adesc, b_fixed | (uint64_t)(bb + r_boff[0]), r_idesc[0], 1u);
+            if (nr == 2) ptx::mma_f16_ss(r_tm[1], adesc, b_fixed | (uint64_t)(bb + r_boff[1]), r_idesc[1], 1u);
           }
         }
         ptx::tc_commit(&empty[st]);                       // slab consumed
@@ -679,7 +711,7 @@ int tc_forward(const Model& m, const TcPoseBatch& pb, TcGridWorkspace& gw, TcWor
     }
     {
       ProfScope ps(prof, "tc_voxelize_pool", s);
-      voxelize_pool_f16_kernel<<<dim3(216, nb), 512, 0, s>>>(gw.list_xyzr, gw.list_ch, gw.list_n, cap, pb.centers,
+      voxelize_pool_f16_kernel<<<dim3(27, nb), 512, 0, s>>>(gw.list_xyzr, gw.list_ch, gw.list_n, cap, pb.centers,
                                                              pb.resolution, pb.dimension,
                                                              reinterpret_cast<uint4*>(gw.x0[0]), L1.Lp, L1.D, L1.P, L1.C8);
     }
