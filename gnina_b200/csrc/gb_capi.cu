@@ -98,11 +98,14 @@ struct gb_model {
 struct gb_cnn {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t aux = nullptr;   // voxeliser of the next chunk overlaps the network of the current one
+  cudaEvent_t ev_fork = nullptr;
   std::vector<Model*> models;
   std::vector<std::unique_ptr<GridGroup>> groups;
   std::vector<int> model_group;
   int precision = GB_PRECISION_FP32;
   int max_batch = 0;  // 0 = per-precision default
+  int overlap = 0;    // 1: voxelise chunk i+1 on the aux stream while the network of chunk i runs
   std::vector<float> rec_xyz;
   std::vector<int32_t> rec_type;
   // staged poses
@@ -119,6 +122,8 @@ struct gb_cnn {
   Profiler prof;
   ~gb_cnn() {
     if (stream) cudaStreamDestroy(stream);
+    if (aux) cudaStreamDestroy(aux);
+    if (ev_fork) cudaEventDestroy(ev_fork);
     for (Model* m : models)
       if (--m->refs == 0) delete m;
   }
@@ -258,6 +263,8 @@ int gb_cnn_create(gb_model* const* models, int n_models, int device, gb_cnn** ou
     h->models.push_back(models[i]->m);
   }
   GB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  GB_CUDA(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+  GB_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   build_groups(h.get());
   h->precision = GB_PRECISION_FP16_TC;
   for (Model* m : h->models)
@@ -276,6 +283,8 @@ int gb_cnn_clone(const gb_cnn* src, gb_cnn** out) {
   h->device = src->device;
   for (Model* m : src->models) { m->refs++; h->models.push_back(m); }
   GB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  GB_CUDA(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+  GB_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   build_groups(h.get());
   h->precision = src->precision;
   h->max_batch = src->max_batch;
@@ -306,6 +315,8 @@ int gb_cnn_set_option(gb_cnn* h, const char* key, double value) {
       for (Model* m : h->models)
         if (!tc_supported(*m)) throw Error(GB_ERR_USAGE, "model " + m->name + " has no tensor-core path yet");
     h->precision = p;
+  } else if (k == "overlap") {
+    h->overlap = value != 0;
   } else if (k == "profile") {
     h->prof.on = value != 0;
   } else if (k == "max_batch") {
@@ -322,6 +333,7 @@ double gb_cnn_get_option(const gb_cnn* h, const char* key) {
   const std::string k(key);
   if (k == "precision") return h->precision;
   if (k == "max_batch") return h->max_batch;
+  if (k == "overlap") return h->overlap;
   return NAN;
 }
 
@@ -357,7 +369,6 @@ int gb_cnn_set_receptor(gb_cnn* h, const float* xyz, const int32_t* smina_type, 
       GB_CUDA(cudaMemcpyAsync(G.rec_ch.p, ch.data(), ch.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
       GB_CUDA(cudaStreamSynchronize(h->stream));
     }
-    if (h->precision == GB_PRECISION_FP16_TC) G.tc_grid.receptor_changed();
   }
   GB_API_END
 }
@@ -475,6 +486,9 @@ int gb_cnn_run_staged(gb_cnn* h) {
   h->d_final.ensure(4 * (size_t)n);
   const int chunk = chunk_size(h);
   h->d_out3.ensure(3 * (size_t)chunk);
+  // the auxiliary stream starts after everything already queued on the main stream (staging copies, timing events)
+  GB_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+  GB_CUDA(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
   for (int p0 = 0; p0 < n; p0 += chunk) {
     const int nb = std::min(chunk, n - p0);
     for (auto& Gp : h->groups) {
@@ -492,14 +506,24 @@ int gb_cnn_run_staged(gb_cnn* h) {
         TcPoseBatch pb{G.rec_xyzr.p, G.rec_ch.p, G.n_rec, G.lig_xyzr.p, G.lig_ch.p, G.lig_off.p + p0,
                        h->d_centers.p + 3 * (size_t)p0, nb, G.max_pose_atoms, G.n_channels, G.rec.n_channels,
                        G.sig.resolution, G.sig.dimension};
-        for (int mi : G.model_idx) {
+        TcGridWorkspace& gw = G.tc_grid;
+        const int buf = (int)(gw.iter++ & 1u);
+        // aux stream: wait until the network has finished reading this buffer two chunks ago, then voxelise into it
+        cudaStream_t vs = h->overlap ? h->aux : h->stream;
+        if (gw.consumed_valid[buf]) GB_CUDA(cudaStreamWaitEvent(vs, gw.consumed[buf], 0));
+        h->launches += tc_prepare_grid(pb, gw, buf, vs, &h->prof);
+        GB_CUDA(cudaEventRecord(gw.ready[buf], vs));
+        GB_CUDA(cudaStreamWaitEvent(h->stream, gw.ready[buf], 0));
+        for (size_t k = 0; k < G.model_idx.size(); k++) {
+          const int mi = G.model_idx[k];
           const Model& Mo = *h->models[mi];
-          h->launches += tc_forward(Mo, pb, G.tc_grid, h->ws_tc, h->d_out3.p, h->stream, &h->prof);
+          h->launches += tc_forward(Mo, pb, gw.x0[buf], h->ws_tc, h->d_out3.p, h->stream, &h->prof,
+                                    k + 1 == G.model_idx.size() ? gw.consumed[buf] : nullptr);
           launch_head_post(h->d_out3.p, nb, Mo.skip_softmax, Mo.apply_logistic_loss, h->d_pose.p + (size_t)mi * n + p0,
                            h->d_aff.p + (size_t)mi * n + p0, h->d_loss.p + (size_t)mi * n + p0, h->stream);
           h->launches++;
         }
-        G.tc_grid.batch_done();
+        gw.consumed_valid[buf] = true;
       }
     }
   }

@@ -24,6 +24,7 @@
 // warps (tcgen05.ld -> bias -> ReLU -> fp16 -> global) as soon as its third input plane has been accumulated.
 // Warp roles: warp 0 = bulk-copy (TMA unit) producer, warp 1 = MMA issuer, warps 2..5 = epilogue.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cuda_fp16.h>
 #include <vector>
@@ -150,6 +151,10 @@ static std::shared_ptr<TcWeights> get_tc_weights(const Model& m) {
 TcGridWorkspace::~TcGridWorkspace() {
   for (auto p : x0)
     if (p) cudaFree(p);
+  for (auto e : ready)
+    if (e) cudaEventDestroy(e);
+  for (auto e : consumed)
+    if (e) cudaEventDestroy(e);
   if (list_xyzr) cudaFree(list_xyzr);
   if (list_ch) cudaFree(list_ch);
   if (list_n) cudaFree(list_n);
@@ -339,7 +344,7 @@ struct ConvTcParams {
   const uint4* wp;    // [NB][9][C8][96]
   const float* bias;  // [Cout]
   __half* out;        // [pose][D][D][D][Cout]
-  int D, P, G, T, NB, Lp, Cout, n_poses, relu;
+  int D, P, G, T, NB, Lp, Cout, n_poses, relu, n_groups;
 };
 
 constexpr int kTcStages = 4;
@@ -372,10 +377,12 @@ __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 2 * R + 1);
   float* s_bias = reinterpret_cast<float*>(bars + 2 * kTcStages + 2 * R + 2);  // 32 floats
 
+  // Persistent CTA: work items (pose group, tile, Cout block) are dealt round-robin; gridDim.x is a multiple of NB,
+  // so a CTA keeps one Cout block (weights stay resident).  All pipelines (slab ring, TMEM slot ring) run on
+  // counters that continue across items, so the next item's slabs stream in while the current one drains.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = blockIdx.x % p.NB;
-  const int j = (blockIdx.x / p.NB) % p.T;
-  const int g = blockIdx.x / (p.NB * p.T);
+  const int n_items = p.n_groups * p.T * p.NB;
   const int D = p.D, P = p.P;
   const int SL = 128 + 2 * (P + 1);
   const uint32_t slab_row = (uint32_t)SL * 16u;  // bytes between K chunks of the A slab
@@ -397,25 +404,36 @@ __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
   const uint32_t tmem_base = *s_tmem;
 
   if (warp == 0) {
-    // ===== producer: weights once, then one A slab per input plane =====
-    if (lane == 0) {
-      ptx::mbar_expect_tx(wbar, S::kWBytes);
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wp) + (size_t)nb * S::kWBytes;
-      for (int t9 = 0; t9 < 9; t9++)
-        ptx::bulk_g2s(s_w + t9 * (S::kWBytes / 9), wsrc + t9 * (S::kWBytes / 9), S::kWBytes / 9, wbar);
-      const uint4* xg = p.xin + (size_t)g * D * C8 * p.Lp + (size_t)128 * j;
-      for (int it = 0; it < D; it++) {
-        const int st = it % kTcStages, ph = (it / kTcStages) & 1;
-        ptx::mbar_wait(&empty[st], ph ^ 1);
-        ptx::mbar_expect_tx(&full[st], (uint32_t)C8 * slab_row);
-        uint8_t* dst = s_stage + (size_t)st * S::kStageBytes;
-        for (int c8 = 0; c8 < C8; c8++)
-          ptx::bulk_g2s(dst + (size_t)c8 * slab_row, xg + ((size_t)it * C8 + c8) * p.Lp, slab_row, &full[st]);
+    // ===== producer: weights once, then one A slab per input plane (whole warp converged, one elected lane issues) =====
+    {
+      if (ptx::elect_one()) {
+        ptx::mbar_expect_tx(wbar, S::kWBytes);
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wp) + (size_t)nb * S::kWBytes;
+        for (int t9 = 0; t9 < 9; t9++)
+          ptx::bulk_g2s(s_w + t9 * (S::kWBytes / 9), wsrc + t9 * (S::kWBytes / 9), S::kWBytes / 9, wbar);
+      }
+      __syncwarp();
+      uint32_t gp = 0;  // global plane counter of this CTA
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int j = (item / p.NB) % p.T, g = item / (p.NB * p.T);
+        const uint4* xg = p.xin + (size_t)g * D * C8 * p.Lp + (size_t)128 * j;
+        for (int it = 0; it < D; it++, gp++) {
+          const uint32_t st = gp % kTcStages, ph = (gp / kTcStages) & 1;
+          ptx::mbar_wait(&empty[st], ph ^ 1);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(&full[st], (uint32_t)C8 * slab_row);
+            uint8_t* dst = s_stage + (size_t)st * S::kStageBytes;
+#pragma unroll
+            for (int c8 = 0; c8 < C8; c8++)
+              ptx::bulk_g2s(dst + (size_t)c8 * slab_row, xg + ((size_t)it * C8 + c8) * p.Lp, slab_row, &full[st]);
+          }
+          __syncwarp();
+        }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer (whole warp converged; the tcgen05 instructions are issued by one elected lane) =====
+    {
       ptx::mbar_wait(wbar, 0);
       // Descriptors are built once; per MMA only the 14-bit start-address fields change (plain integer adds).
       const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 32) | (1ull << 46);         // SBO = 128 B, version 1
@@ -425,90 +443,101 @@ __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
       uint32_t aoff[9];
 #pragma unroll
       for (int t9 = 0; t9 < 9; t9++) aoff[t9] = (uint32_t)((P + 1) + (t9 / 3 - 1) * P + (t9 % 3 - 1));
-      for (int it = 0; it < D; it++) {
-        const int xi = it + 1;
-        const int st = it % kTcStages, ph = (it / kTcStages) & 1;
-        const int lo = xi > 1 ? xi - 1 : 1, hi = xi < D ? xi + 1 : D;
-        const int fresh_lo = xi == 1 ? 1 : xi + 1;  // output planes >= fresh_lo get their first contribution now
-        for (int xo = fresh_lo; xo <= hi; xo++) {
-          const int u = (xo - 1) / R;
-          if (u > 0) ptx::mbar_wait(&acce[xo % R], (u - 1) & 1);
-        }
-        // runs of output planes with consecutive TMEM slots: {tmem column, B row offset (16 B units), idesc}
-        uint32_t r_tm[2], r_boff[2], r_idesc[2];
-        int nr = 0;
-        {
-          int rs = lo;
-          for (int xo = lo; xo <= hi; xo++) {
-            if (xo == hi || ((xo + 1) % R != (xo % R) + 1)) {
-              r_tm[nr] = tmem_base + (uint32_t)(rs % R) * 32u;
-              r_boff[nr] = (uint32_t)(rs - (xi - 1)) * 32u;
-              r_idesc[nr] = ptx::idesc_f16(128, 32 * (xo - rs + 1));
-              nr++;
-              rs = xo + 1;
+      uint32_t gp = 0, go_base = 0;  // global input-plane / output-plane counters (output plane xo <-> go_base+xo-1)
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, go_base += D) {
+        for (int it = 0; it < D; it++, gp++) {
+          const int xi = it + 1;
+          const uint32_t st = gp % kTcStages, ph = (gp / kTcStages) & 1;
+          const int lo = xi > 1 ? xi - 1 : 1, hi = xi < D ? xi + 1 : D;
+          const int fresh_lo = xi == 1 ? 1 : xi + 1;  // output planes >= fresh_lo get their first contribution now
+          for (int xo = fresh_lo; xo <= hi; xo++) {
+            const uint32_t go = go_base + xo - 1, u = go / R;
+            if (u > 0) ptx::mbar_wait(&acce[go % R], (u - 1) & 1);
+          }
+          // runs of output planes with consecutive TMEM slots: {tmem column, B row offset (16 B units), idesc}
+          uint32_t r_tm[2], r_boff[2], r_idesc[2];
+          int nr = 0;
+          {
+            int rs = lo;
+            for (int xo = lo; xo <= hi; xo++) {
+              const uint32_t sl = (go_base + xo - 1) % R;
+              if (xo == hi || sl == R - 1) {
+                r_tm[nr] = tmem_base + ((go_base + rs - 1) % R) * 32u;
+                r_boff[nr] = (uint32_t)(rs - (xi - 1)) * 32u;
+                r_idesc[nr] = ptx::idesc_f16(128, 32 * (xo - rs + 1));
+                nr++;
+                rs = xo + 1;
+              }
             }
           }
-        }
-        ptx::mbar_wait(&full[st], ph);
-        ptx::tc_fence_after();
-        const uint32_t a_addr16 = ptx::smem_u32(s_stage + (size_t)st * S::kStageBytes) >> 4;
-        // very first MMA of the plane: fresh output planes must be overwritten (accumulate = 0), one MMA per plane
-        {
-          const uint64_t adesc = a_fixed | (uint64_t)(a_addr16 + aoff[0]);
-          for (int xo = lo; xo <= hi; xo++)
-            ptx::mma_f16_ss(tmem_base + (uint32_t)(xo % R) * 32u, adesc,
-                            b_fixed | (uint64_t)(b_addr16 + (uint32_t)(xo - (xi - 1)) * 32u), ptx::idesc_f16(128, 32),
-                            xo >= fresh_lo ? 0u : 1u);
-        }
-#pragma unroll
-        for (int t9 = 0; t9 < 9; t9++) {
-#pragma unroll
-          for (int ks = 0; ks < CIN / 16; ks++) {
-            if (t9 == 0 && ks == 0) continue;
-            const uint64_t adesc = a_fixed | (uint64_t)(a_addr16 + aoff[t9] + (uint32_t)(2 * ks) * (uint32_t)SL);
-            const uint32_t bb = b_addr16 + (uint32_t)((t9 * C8 + 2 * ks) * 96);
-            ptx::mma_f16_ss(r_tm[0], adesc, b_fixed | (uint64_t)(bb + r_boff[0]), r_idesc[0], 1u);
-            if (nr == 2) ptx::mma_f16_ss(r_tm[1], adesc, b_fixed | (uint64_t)(bb + r_boff[1]), r_idesc[1], 1u);
+          ptx::mbar_wait(&full[st], ph);
+          ptx::tc_fence_after();
+          const uint32_t a_addr16 = ptx::smem_u32(s_stage + (size_t)st * S::kStageBytes) >> 4;
+          if (ptx::elect_one()) {
+          // very first MMA of the plane: fresh output planes must be overwritten (accumulate = 0): one MMA per plane
+          {
+            const uint64_t adesc = a_fixed | (uint64_t)(a_addr16 + aoff[0]);
+            for (int xo = lo; xo <= hi; xo++)
+              ptx::mma_f16_ss(tmem_base + ((go_base + xo - 1) % R) * 32u, adesc,
+                              b_fixed | (uint64_t)(b_addr16 + (uint32_t)(xo - (xi - 1)) * 32u), ptx::idesc_f16(128, 32),
+                              xo >= fresh_lo ? 0u : 1u);
           }
+#pragma unroll
+          for (int t9 = 0; t9 < 9; t9++) {
+#pragma unroll
+            for (int ks = 0; ks < CIN / 16; ks++) {
+              if (t9 == 0 && ks == 0) continue;
+              const uint64_t adesc = a_fixed | (uint64_t)(a_addr16 + aoff[t9] + (uint32_t)(2 * ks) * (uint32_t)SL);
+              const uint32_t bb = b_addr16 + (uint32_t)((t9 * C8 + 2 * ks) * 96);
+              ptx::mma_f16_ss(r_tm[0], adesc, b_fixed | (uint64_t)(bb + r_boff[0]), r_idesc[0], 1u);
+              if (nr == 2) ptx::mma_f16_ss(r_tm[1], adesc, b_fixed | (uint64_t)(bb + r_boff[1]), r_idesc[1], 1u);
+            }
+          }
+          ptx::tc_commit(&empty[st]);                                    // slab consumed
+          if (xi >= 2) ptx::tc_commit(&accf[(go_base + xi - 2) % R]);     // output plane xi-1 is complete
+          if (xi == D) ptx::tc_commit(&accf[(go_base + D - 1) % R]);
+          }
+          __syncwarp();
         }
-        ptx::tc_commit(&empty[st]);                       // slab consumed
-        if (xi >= 2) ptx::tc_commit(&accf[(xi - 1) % R]);  // output plane xi-1 has all three input planes
-        if (xi == D) ptx::tc_commit(&accf[D % R]);
       }
     }
   } else {
     // ===== epilogue: TMEM -> registers -> bias/ReLU -> fp16 -> global =====
     const int q4 = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q4 * 32 + lane;
-    const int m = (P + 1) + 128 * j + row;
-    const int qpose = m / (P * P), rem = m % (P * P);
-    const int y = rem / P, z = rem % P;
-    const int pose = g * p.G + qpose;
-    const bool valid = qpose < p.G && pose < p.n_poses && y >= 1 && y <= D && z >= 1 && z <= D;
-    __half* obase = p.out + (((size_t)pose * D * D + (size_t)(y - 1)) * D + (z - 1)) * p.Cout + nb * 32;
-    const size_t plane_stride = (size_t)D * D * p.Cout;
-    for (int xo = 1; xo <= D; xo++) {
-      const int slot = xo % R, u = (xo - 1) / R;
-      ptx::mbar_wait(&accf[slot], u & 1);
-      ptx::tc_fence_after();
-      uint32_t v[32];
-      ptx::tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)slot * 32u, v);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&acce[slot]);
-      if (valid) {
-        uint4 o[4];
-        uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+    uint32_t go = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int j = (item / p.NB) % p.T, g = item / (p.NB * p.T);
+      const int m = (P + 1) + 128 * j + row;
+      const int qpose = m / (P * P), rem = m % (P * P);
+      const int y = rem / P, z = rem % P;
+      const int pose = g * p.G + qpose;
+      const bool valid = qpose < p.G && pose < p.n_poses && y >= 1 && y <= D && z >= 1 && z <= D;
+      __half* obase = p.out + (((size_t)pose * D * D + (size_t)(y - 1)) * D + (z - 1)) * p.Cout + nb * 32;
+      const size_t plane_stride = (size_t)D * D * p.Cout;
+      for (int xo = 1; xo <= D; xo++, go++) {
+        const uint32_t slot = go % R, u = go / R;
+        ptx::mbar_wait(&accf[slot], u & 1);
+        ptx::tc_fence_after();
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + slot * 32u, v);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&acce[slot]);
+        if (valid) {
+          uint4 o[4];
+          uint32_t* ow = reinterpret_cast<uint32_t*>(o);
 #pragma unroll
-        for (int c = 0; c < 16; c++) {
-          float f0 = __uint_as_float(v[2 * c]) + s_bias[2 * c];
-          float f1 = __uint_as_float(v[2 * c + 1]) + s_bias[2 * c + 1];
-          if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
-          const __half2 h = __floats2half2_rn(f0, f1);
-          ow[c] = *reinterpret_cast<const uint32_t*>(&h);
+          for (int c = 0; c < 16; c++) {
+            float f0 = __uint_as_float(v[2 * c]) + s_bias[2 * c];
+            float f1 = __uint_as_float(v[2 * c + 1]) + s_bias[2 * c + 1];
+            if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+            const __half2 h = __floats2half2_rn(f0, f1);
+            ow[c] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(obase + (size_t)(xo - 1) * plane_stride);
+          dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2]; dst[3] = o[3];
         }
-        uint4* dst = reinterpret_cast<uint4*>(obase + (size_t)(xo - 1) * plane_stride);
-        dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2]; dst[3] = o[3];
       }
     }
   }
@@ -650,8 +679,23 @@ static void launch_conv_tc(const ConvTc& c, const ActLayout& L, const uint4* xin
   p.xin = xin; p.wp = c.wp; p.bias = c.bias; p.out = out;
   p.D = L.D; p.P = L.P; p.G = L.G; p.T = L.T; p.NB = c.cout / 32; p.Lp = L.Lp; p.Cout = c.cout; p.n_poses = n_poses;
   p.relu = 1;
-  const int n_groups = (n_poses + L.G - 1) / L.G;
-  conv3_tc_kernel<CIN><<<n_groups * L.T * p.NB, 192, S::kTotal, s>>>(p);
+  p.n_groups = (n_poses + L.G - 1) / L.G;
+  const int n_items = p.n_groups * L.T * p.NB;
+  static int ctas_per_sm = 0, n_sm = 0;
+  if (!ctas_per_sm) {
+    int dev = 0;
+    GB_CUDA(cudaGetDevice(&dev));
+    GB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, conv3_tc_kernel<CIN>, 192, S::kTotal));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+  }
+  int grid = n_sm * ctas_per_sm;
+  static const int persist = getenv("GB_TC_PERSIST") ? atoi(getenv("GB_TC_PERSIST")) : (CIN == 64 ? 1 : 0);
+  if (persist == 0) grid = n_items;            // experiment: one item per CTA
+  else if (persist > 1) grid = n_sm * persist;  // experiment: force CTAs per SM
+  grid -= grid % p.NB;                  // a CTA keeps one Cout block
+  if (grid > n_items) grid = n_items;  // n_items is a multiple of NB
+  conv3_tc_kernel<CIN><<<grid, 192, S::kTotal, s>>>(p);
 }
 
 static size_t act_bytes(const ActLayout& L, int n_poses) {
@@ -670,55 +714,59 @@ const void* tc_debug_buffer(int i, size_t* bytes) {
   return t_debug.ptr[i];
 }
 
-int tc_forward(const Model& m, const TcPoseBatch& pb, TcGridWorkspace& gw, TcWorkspace& ws, float* out3, cudaStream_t s,
-               Profiler* prof) {
+int tc_prepare_grid(const TcPoseBatch& pb, TcGridWorkspace& gw, int buf, cudaStream_t s, Profiler* prof) {
+  const int nb = pb.n_poses;
+  const ActLayout L1 = make_layout(24, 1, 32);
+  const int cap = std::max(1, pb.n_rec + pb.max_pose_atoms);
+  const size_t need = (size_t)nb * cap;
+  if (gw.list_cap < need) {
+    GB_CUDA(cudaStreamSynchronize(s));
+    if (gw.list_xyzr) cudaFree(gw.list_xyzr);
+    if (gw.list_ch) cudaFree(gw.list_ch);
+    GB_CUDA(cudaMalloc(&gw.list_xyzr, need * sizeof(float4)));
+    GB_CUDA(cudaMalloc(&gw.list_ch, need * sizeof(int)));
+    gw.list_cap = need;
+  }
+  if (gw.listn_cap < (size_t)nb) {
+    GB_CUDA(cudaStreamSynchronize(s));
+    if (gw.list_n) cudaFree(gw.list_n);
+    GB_CUDA(cudaMalloc(&gw.list_n, (size_t)nb * sizeof(int)));
+    gw.listn_cap = nb;
+  }
+  const size_t need0 = act_bytes(L1, nb);
+  if (gw.cap[buf] < need0) {
+    GB_CUDA(cudaDeviceSynchronize());
+    if (gw.x0[buf]) cudaFree(gw.x0[buf]);
+    GB_CUDA(cudaMalloc(&gw.x0[buf], need0));
+    GB_CUDA(cudaMemset(gw.x0[buf], 0, need0));
+    gw.cap[buf] = need0;
+  }
+  for (int i = 0; i < 2; i++) {
+    if (!gw.ready[i]) GB_CUDA(cudaEventCreateWithFlags(&gw.ready[i], cudaEventDisableTiming));
+    if (!gw.consumed[i]) GB_CUDA(cudaEventCreateWithFlags(&gw.consumed[i], cudaEventDisableTiming));
+  }
+  {
+    ProfScope ps(prof, "tc_build_pose_lists", s);
+    launch_build_pose_lists(pb.rec_xyzr, pb.rec_ch, pb.n_rec, pb.lig_xyzr, pb.lig_ch, pb.lig_off, pb.centers, nb,
+                            pb.dimension / 2.f, cap, gw.list_xyzr, gw.list_ch, gw.list_n, s);
+  }
+  {
+    ProfScope ps(prof, "tc_voxelize_pool", s);
+    voxelize_pool_f16_kernel<<<dim3(27, nb), 512, 0, s>>>(gw.list_xyzr, gw.list_ch, gw.list_n, cap, pb.centers,
+                                                          pb.resolution, pb.dimension,
+                                                          reinterpret_cast<uint4*>(gw.x0[buf]), L1.Lp, L1.D, L1.P, L1.C8);
+  }
+  return 2;
+}
+
+int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspace& ws, float* out3, cudaStream_t s,
+               Profiler* prof, cudaEvent_t x0_consumed) {
   GB_CHECK(tc_supported(m), "tensor-core path supports the default2018 family only (so far)");
   auto tw = get_tc_weights(m);
   int launches = 0;
   const int nb = pb.n_poses;
   const ActLayout L1 = make_layout(24, 1, 32), L3 = make_layout(12, 2, 32), L5 = make_layout(6, 2, 64);
-  // --- pose lists + pooled grid (shared by all models of the grid group that avg-pool) ---
-  if (!gw.valid[0]) {
-    const int cap = std::max(1, pb.n_rec + pb.max_pose_atoms);
-    if (!gw.lists_valid) {
-      const size_t need = (size_t)nb * cap;
-      if (gw.list_cap < need) {
-        if (gw.list_xyzr) cudaFree(gw.list_xyzr);
-        if (gw.list_ch) cudaFree(gw.list_ch);
-        GB_CUDA(cudaMalloc(&gw.list_xyzr, need * sizeof(float4)));
-        GB_CUDA(cudaMalloc(&gw.list_ch, need * sizeof(int)));
-        gw.list_cap = need;
-      }
-      if (gw.listn_cap < (size_t)nb) {
-        if (gw.list_n) cudaFree(gw.list_n);
-        GB_CUDA(cudaMalloc(&gw.list_n, (size_t)nb * sizeof(int)));
-        gw.listn_cap = nb;
-      }
-      {
-        ProfScope ps(prof, "tc_build_pose_lists", s);
-        launch_build_pose_lists(pb.rec_xyzr, pb.rec_ch, pb.n_rec, pb.lig_xyzr, pb.lig_ch, pb.lig_off, pb.centers, nb,
-                                pb.dimension / 2.f, cap, gw.list_xyzr, gw.list_ch, gw.list_n, s);
-      }
-      launches++;
-      gw.lists_valid = true;
-    }
-    const size_t need0 = act_bytes(L1, nb);
-    if (gw.cap[0] < need0) {
-      if (gw.x0[0]) cudaFree(gw.x0[0]);
-      GB_CUDA(cudaMalloc(&gw.x0[0], need0));
-      GB_CUDA(cudaMemsetAsync(gw.x0[0], 0, need0, s));
-      gw.cap[0] = need0;
-    }
-    {
-      ProfScope ps(prof, "tc_voxelize_pool", s);
-      voxelize_pool_f16_kernel<<<dim3(27, nb), 512, 0, s>>>(gw.list_xyzr, gw.list_ch, gw.list_n, cap, pb.centers,
-                                                             pb.resolution, pb.dimension,
-                                                             reinterpret_cast<uint4*>(gw.x0[0]), L1.Lp, L1.D, L1.P, L1.C8);
-    }
-    launches++;
-    gw.valid[0] = true;
-  }
-  const uint4* x0 = reinterpret_cast<const uint4*>(gw.x0[0]);
+  const uint4* x0 = reinterpret_cast<const uint4*>(x0v);
   // --- workspaces: 0 = Y (conv outputs, reused), 1 = X2, 2 = X4 ---
   ws.ensure(0, (size_t)nb * 24 * 24 * 24 * 32 * sizeof(__half) + 1024);
   ws.ensure(1, act_bytes(L3, nb));
@@ -733,6 +781,7 @@ int tc_forward(const Model& m, const TcPoseBatch& pb, TcGridWorkspace& gw, TcWor
     ProfScope ps(prof, "tc_conv1_3x3x3_28x32_d24", s);
     launch_conv_tc<32>(tw->conv1, L1, x0, Y, nb, s);
   }
+  if (x0_consumed) GB_CUDA(cudaEventRecord(x0_consumed, s));
   {
     ProfScope ps(prof, "tc_pw2_pool", s);
     pointwise_pool_kernel<32><<<pw_blocks, 256, 0, s>>>(Y, tw->pw2.w, tw->pw2.bias, X2, 24, nb, L3.G, L3.Lp);
@@ -754,7 +803,7 @@ int tc_forward(const Model& m, const TcPoseBatch& pb, TcGridWorkspace& gw, TcWor
     fc_heads_f16_kernel<<<nb, 256, 0, s>>>(Y5, tw->fcw, tw->fcb, out3);
   }
   launches += 6;
-  t_debug.ptr[0] = gw.x0[0]; t_debug.bytes[0] = act_bytes(L1, nb);
+  t_debug.ptr[0] = x0v;      t_debug.bytes[0] = act_bytes(L1, nb);
   t_debug.ptr[1] = Y;        t_debug.bytes[1] = (size_t)nb * 1728 * 64 * sizeof(__half);  // holds Y3 after the pass
   t_debug.ptr[2] = X2;       t_debug.bytes[2] = act_bytes(L3, nb);
   t_debug.ptr[3] = X4;       t_debug.bytes[3] = act_bytes(L5, nb);

@@ -12,15 +12,17 @@ struct TcPoseBatch {
   float resolution, dimension;
 };
 
-// Pooled input grids of the current chunk, shared by the models of a grid group that pool the same way.
+// Pooled input grids, double buffered so that the (CUDA-core) voxeliser of chunk i+1 can run on an auxiliary
+// stream while the (tensor-core) network of chunk i runs on the main stream; shared by the models of a grid group.
 struct TcGridWorkspace {
-  void* x0[2] = {nullptr, nullptr};  // [0] avg-pooled, [1] max-pooled
+  void* x0[2] = {nullptr, nullptr};
   size_t cap[2] = {0, 0};
-  bool valid[2] = {false, false};
+  cudaEvent_t ready[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+  bool consumed_valid[2] = {false, false};
+  unsigned iter = 0;
   float4* list_xyzr = nullptr; int* list_ch = nullptr; int* list_n = nullptr; size_t list_cap = 0, listn_cap = 0;
-  bool lists_valid = false;
-  void receptor_changed() { valid[0] = valid[1] = false; lists_valid = false; }
-  void batch_done() { valid[0] = valid[1] = false; lists_valid = false; }
+  void receptor_changed() {}
+  void batch_done() {}
   ~TcGridWorkspace();
 };
 
@@ -32,9 +34,12 @@ struct TcWorkspace {
 };
 
 bool tc_supported(const Model& m);
-// -> out3 [n_poses][3]; returns the number of kernel launches
-int tc_forward(const Model& m, const TcPoseBatch& pb, TcGridWorkspace& gw, TcWorkspace& ws, float* out3, cudaStream_t s,
-               Profiler* prof = nullptr);
+// pose lists + fused voxelise/avg-pool of one chunk into gw.x0[buf] on stream s; returns #launches
+int tc_prepare_grid(const TcPoseBatch& pb, TcGridWorkspace& gw, int buf, cudaStream_t s, Profiler* prof = nullptr);
+// network forward on the pooled grid x0 -> out3 [n_poses][3]; records x0_consumed (if non-null) once x0 has been
+// read for the last time; returns the number of kernel launches
+int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0, TcWorkspace& ws, float* out3, cudaStream_t s,
+               Profiler* prof = nullptr, cudaEvent_t x0_consumed = nullptr);
 
 // test-only access to the buffers of the most recent tc_forward on this thread: 0 x0, 1 y(3), 2 x2, 3 x4, 4 y5
 const void* tc_debug_buffer(int i, size_t* bytes);
