@@ -360,7 +360,7 @@ struct ConvTcSmem {
   static constexpr int kTotal = kBarOff + 512;
 };
 
-template <int CIN>
+template <int CIN, int DD>
 __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
   using S = ConvTcSmem<CIN>;
   constexpr int C8 = S::C8;
@@ -383,8 +383,8 @@ __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = blockIdx.x % p.NB;
   const int n_items = p.n_groups * p.T * p.NB;
-  const int D = p.D, P = p.P;
-  const int SL = 128 + 2 * (P + 1);
+  constexpr int D = DD, P = DD + 2;
+  constexpr int SL = 128 + 2 * (P + 1);
   const uint32_t slab_row = (uint32_t)SL * 16u;  // bytes between K chunks of the A slab
 
   if (threadIdx.x == 0) {
@@ -435,14 +435,12 @@ __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
     // ===== MMA issuer (whole warp converged; the tcgen05 instructions are issued by one elected lane) =====
     {
       ptx::mbar_wait(wbar, 0);
-      // Descriptors are built once; per MMA only the 14-bit start-address fields change (plain integer adds).
-      const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 32) | (1ull << 46);         // SBO = 128 B, version 1
-      const uint64_t a_fixed = desc_hi | ((uint64_t)((uint32_t)SL & 0x3FFF) << 16);  // LBO = slab row (SL x 16 B)
-      const uint64_t b_fixed = desc_hi | ((uint64_t)96 << 16);                       // LBO = 96 rows x 16 B
-      const uint32_t b_addr16 = ptx::smem_u32(s_w) >> 4;
-      uint32_t aoff[9];
-#pragma unroll
-      for (int t9 = 0; t9 < 9; t9++) aoff[t9] = (uint32_t)((P + 1) + (t9 / 3 - 1) * P + (t9 % 3 - 1));
+      // Descriptor = (lo, hi) words; hi is constant (SBO = 128 B, version 1); lo = start address | LBO << 16.  Per
+      // MMA only the 14-bit start-address field changes, by COMPILE-TIME offsets (P and the slab pitch are template
+      // constants), so the issue loop is one 32-bit add per operand plus the UTCHMMA.
+      constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+      const uint32_t a_lo_fixed = ((uint32_t)SL & 0x3FFFu) << 16;  // LBO = slab row (SL x 16 B)
+      const uint32_t b_lo_base = (96u << 16) | (ptx::smem_u32(s_w) >> 4);  // LBO = 96 rows x 16 B
       uint32_t gp = 0, go_base = 0;  // global input-plane / output-plane counters (output plane xo <-> go_base+xo-1)
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, go_base += D) {
         for (int it = 0; it < D; it++, gp++) {
@@ -472,30 +470,44 @@ __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
           }
           ptx::mbar_wait(&full[st], ph);
           ptx::tc_fence_after();
-          const uint32_t a_addr16 = ptx::smem_u32(s_stage + (size_t)st * S::kStageBytes) >> 4;
+          const uint32_t a_lo_base = a_lo_fixed | (ptx::smem_u32(s_stage + (size_t)st * S::kStageBytes) >> 4);
           if (ptx::elect_one()) {
-          // very first MMA of the plane: fresh output planes must be overwritten (accumulate = 0): one MMA per plane
-          {
-            const uint64_t adesc = a_fixed | (uint64_t)(a_addr16 + aoff[0]);
-            for (int xo = lo; xo <= hi; xo++)
-              ptx::mma_f16_ss(tmem_base + ((go_base + xo - 1) % R) * 32u, adesc,
-                              b_fixed | (uint64_t)(b_addr16 + (uint32_t)(xo - (xi - 1)) * 32u), ptx::idesc_f16(128, 32),
-                              xo >= fresh_lo ? 0u : 1u);
-          }
-#pragma unroll
-          for (int t9 = 0; t9 < 9; t9++) {
-#pragma unroll
-            for (int ks = 0; ks < CIN / 16; ks++) {
-              if (t9 == 0 && ks == 0) continue;
-              const uint64_t adesc = a_fixed | (uint64_t)(a_addr16 + aoff[t9] + (uint32_t)(2 * ks) * (uint32_t)SL);
-              const uint32_t bb = b_addr16 + (uint32_t)((t9 * C8 + 2 * ks) * 96);
-              ptx::mma_f16_ss(r_tm[0], adesc, b_fixed | (uint64_t)(bb + r_boff[0]), r_idesc[0], 1u);
-              if (nr == 2) ptx::mma_f16_ss(r_tm[1], adesc, b_fixed | (uint64_t)(bb + r_boff[1]), r_idesc[1], 1u);
+            // very first MMA of the plane: fresh output planes are overwritten (accumulate = 0): one N=32 MMA per plane
+            for (int xo = lo; xo <= hi; xo++) {
+              const uint32_t tm = tmem_base + ((go_base + xo - 1) % R) * 32u;
+              const uint32_t bl = b_lo_base + (uint32_t)(xo - (xi - 1)) * 32u;
+              constexpr uint32_t a0 = (uint32_t)((P + 1) - P - 1);
+              if (xo >= fresh_lo) ptx::mma_f16_ss_lohi<0>(tm, a_lo_base + a0, kDescHi, bl, kDescHi, ptx::idesc_f16(128, 32));
+              else ptx::mma_f16_ss_lohi<1>(tm, a_lo_base + a0, kDescHi, bl, kDescHi, ptx::idesc_f16(128, 32));
             }
-          }
-          ptx::tc_commit(&empty[st]);                                    // slab consumed
-          if (xi >= 2) ptx::tc_commit(&accf[(go_base + xi - 2) % R]);     // output plane xi-1 is complete
-          if (xi == D) ptx::tc_commit(&accf[(go_base + D - 1) % R]);
+            if (nr == 1) {
+              const uint32_t tm0 = r_tm[0], id0 = r_idesc[0], bl0 = b_lo_base + r_boff[0];
+#pragma unroll
+              for (int t9 = 0; t9 < 9; t9++) {
+#pragma unroll
+                for (int ks = 0; ks < CIN / 16; ks++) {
+                  if (t9 == 0 && ks == 0) continue;
+                  constexpr int dummy = 0; (void)dummy;
+                  const uint32_t aoff = (uint32_t)((P + 1) + (t9 / 3 - 1) * P + (t9 % 3 - 1) + 2 * ks * SL);
+                  const uint32_t boff = (uint32_t)((t9 * C8 + 2 * ks) * 96);
+                  ptx::mma_f16_ss_lohi<1>(tm0, a_lo_base + aoff, kDescHi, bl0 + boff, kDescHi, id0);
+                }
+              }
+            } else {
+              // TMEM ring wrap inside the window (2 planes in 8): two MMAs per tap, generic loop
+              for (int t9 = 0; t9 < 9; t9++) {
+                for (int ks = 0; ks < CIN / 16; ks++) {
+                  if (t9 == 0 && ks == 0) continue;
+                  const uint32_t aoff = (uint32_t)((P + 1) + (t9 / 3 - 1) * P + (t9 % 3 - 1) + 2 * ks * SL);
+                  const uint32_t boff = (uint32_t)((t9 * C8 + 2 * ks) * 96);
+                  ptx::mma_f16_ss_lohi<1>(r_tm[0], a_lo_base + aoff, kDescHi, b_lo_base + r_boff[0] + boff, kDescHi, r_idesc[0]);
+                  ptx::mma_f16_ss_lohi<1>(r_tm[1], a_lo_base + aoff, kDescHi, b_lo_base + r_boff[1] + boff, kDescHi, r_idesc[1]);
+                }
+              }
+            }
+            ptx::tc_commit(&empty[st]);                                    // slab consumed
+            if (xi >= 2) ptx::tc_commit(&accf[(go_base + xi - 2) % R]);     // output plane xi-1 is complete
+            if (xi == D) ptx::tc_commit(&accf[(go_base + D - 1) % R]);
           }
           __syncwarp();
         }
@@ -666,15 +678,15 @@ __global__ void __launch_bounds__(256) fc_heads_f16_kernel(const __half* __restr
 }
 
 // ------------------------------------------------------------------------------------------------------------
-template <int CIN>
+template <int CIN, int DD>
 static void launch_conv_tc(const ConvTc& c, const ActLayout& L, const uint4* xin, __half* out, int n_poses, cudaStream_t s) {
   using S = ConvTcSmem<CIN>;
   static bool attr_set = false;
   if (!attr_set) {
-    GB_CUDA(cudaFuncSetAttribute(conv3_tc_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    GB_CUDA(cudaFuncSetAttribute(conv3_tc_kernel<CIN, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set = true;
   }
-  GB_CHECK(c.cin == CIN, "conv cin");
+  GB_CHECK(c.cin == CIN && L.D == DD, "conv shape");
   ConvTcParams p;
   p.xin = xin; p.wp = c.wp; p.bias = c.bias; p.out = out;
   p.D = L.D; p.P = L.P; p.G = L.G; p.T = L.T; p.NB = c.cout / 32; p.Lp = L.Lp; p.Cout = c.cout; p.n_poses = n_poses;
@@ -686,7 +698,7 @@ static void launch_conv_tc(const ConvTc& c, const ActLayout& L, const uint4* xin
     int dev = 0;
     GB_CUDA(cudaGetDevice(&dev));
     GB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, conv3_tc_kernel<CIN>, 192, S::kTotal));
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, conv3_tc_kernel<CIN, DD>, 192, S::kTotal));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
   }
   int grid = n_sm * ctas_per_sm;
@@ -695,7 +707,7 @@ static void launch_conv_tc(const ConvTc& c, const ActLayout& L, const uint4* xin
   else if (persist > 1) grid = n_sm * persist;  // experiment: force CTAs per SM
   grid -= grid % p.NB;                  // a CTA keeps one Cout block
   if (grid > n_items) grid = n_items;  // n_items is a multiple of NB
-  conv3_tc_kernel<CIN><<<grid, 192, S::kTotal, s>>>(p);
+  conv3_tc_kernel<CIN, DD><<<grid, 192, S::kTotal, s>>>(p);
 }
 
 static size_t act_bytes(const ActLayout& L, int n_poses) {
@@ -779,7 +791,7 @@ int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspa
   const int pw_blocks = 148 * 8;
   {
     ProfScope ps(prof, "tc_conv1_3x3x3_28x32_d24", s);
-    launch_conv_tc<32>(tw->conv1, L1, x0, Y, nb, s);
+    launch_conv_tc<32, 24>(tw->conv1, L1, x0, Y, nb, s);
   }
   if (x0_consumed) GB_CUDA(cudaEventRecord(x0_consumed, s));
   {
@@ -788,7 +800,7 @@ int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspa
   }
   {
     ProfScope ps(prof, "tc_conv3_3x3x3_32x64_d12", s);
-    launch_conv_tc<32>(tw->conv3, L3, X2, Y, nb, s);
+    launch_conv_tc<32, 12>(tw->conv3, L3, X2, Y, nb, s);
   }
   {
     ProfScope ps(prof, "tc_pw4_pool", s);
@@ -796,7 +808,7 @@ int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspa
   }
   {
     ProfScope ps(prof, "tc_conv5_3x3x3_64x128_d6", s);
-    launch_conv_tc<64>(tw->conv5, L5, X4, Y5, nb, s);
+    launch_conv_tc<64, 6>(tw->conv5, L5, X4, Y5, nb, s);
   }
   {
     ProfScope ps(prof, "tc_fc_heads", s);
