@@ -156,6 +156,8 @@ def main():
     ap.add_argument("--precision", type=int, default=-1, help="-1 library default, 0 fp32 validation, 1 fp16 tensor-core")
     ap.add_argument("--ref-sample", type=int, default=200, help="poses per step for --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--overlap", type=int, default=-1, help="voxeliser/network stream overlap (library option)")
+    ap.add_argument("--max-batch", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -181,6 +183,10 @@ def main():
     s = CNNScorer([MODEL], device=local)
     if args.precision >= 0:
         s.set_option("precision", args.precision)
+    if args.overlap >= 0:
+        s.set_option("overlap", args.overlap)
+    if args.max_batch:
+        s.set_option("max_batch", args.max_batch)
     precision = int(s.get_option("precision"))
     s.set_receptor(rec_xyz, rec_t)
     stream = torch.cuda.ExternalStream(s.stream_ptr(), device=dev)

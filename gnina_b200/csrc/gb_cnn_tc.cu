@@ -28,6 +28,9 @@
 #include <cstring>
 #include <cuda_fp16.h>
 #include <vector>
+#ifndef GB_TC_STAGES32
+#define GB_TC_STAGES32 3
+#endif
 #include "gb_ptx.cuh"
 #include "gb_tc.h"
 
@@ -347,7 +350,6 @@ struct ConvTcParams {
   int D, P, G, T, NB, Lp, Cout, n_poses, relu, n_groups;
 };
 
-constexpr int kTcStages = 4;
 constexpr int kTcSlots = 8;       // TMEM ring: 8 plane slots x 32 fp32 columns = 256 columns
 constexpr int kSlabMax = 128 + 2 * 27;
 
@@ -356,7 +358,10 @@ struct ConvTcSmem {
   static constexpr int C8 = CIN / 8;
   static constexpr int kWBytes = 9 * C8 * 96 * 16;
   static constexpr int kStageBytes = ((C8 * kSlabMax * 16) + 127) / 128 * 128;
-  static constexpr int kBarOff = kWBytes + kTcStages * kStageBytes;
+  // 3 stages for CIN = 32: two conv CTAs (2 x 91 KB) leave room for one voxeliser CTA (40 KB) on the same SM, so
+  // the CUDA-core voxeliser of the next chunk can overlap the tensor-core network of the current one
+  static constexpr int kStages = (CIN == 32) ? (GB_TC_STAGES32) : 4;
+  static constexpr int kBarOff = kWBytes + kStages * kStageBytes;
   static constexpr int kTotal = kBarOff + 512;
 };
 
@@ -369,13 +374,13 @@ __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
   uint8_t* s_w = smem;
   uint8_t* s_stage = smem + S::kWBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
-  uint64_t* full = bars;                        // [kTcStages]
-  uint64_t* empty = bars + kTcStages;           // [kTcStages]
-  uint64_t* accf = bars + 2 * kTcStages;        // [R]
-  uint64_t* acce = bars + 2 * kTcStages + R;    // [R]
-  uint64_t* wbar = bars + 2 * kTcStages + 2 * R;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 2 * R + 1);
-  float* s_bias = reinterpret_cast<float*>(bars + 2 * kTcStages + 2 * R + 2);  // 32 floats
+  uint64_t* full = bars;                        // [S::kStages]
+  uint64_t* empty = bars + S::kStages;           // [S::kStages]
+  uint64_t* accf = bars + 2 * S::kStages;        // [R]
+  uint64_t* acce = bars + 2 * S::kStages + R;    // [R]
+  uint64_t* wbar = bars + 2 * S::kStages + 2 * R;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * S::kStages + 2 * R + 1);
+  float* s_bias = reinterpret_cast<float*>(bars + 2 * S::kStages + 2 * R + 2);  // 32 floats
 
   // Persistent CTA: work items (pose group, tile, Cout block) are dealt round-robin; gridDim.x is a multiple of NB,
   // so a CTA keeps one Cout block (weights stay resident).  All pipelines (slab ring, TMEM slot ring) run on
@@ -388,7 +393,7 @@ __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
   const uint32_t slab_row = (uint32_t)SL * 16u;  // bytes between K chunks of the A slab
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTcStages; s++) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < S::kStages; s++) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
     for (int s = 0; s < R; s++) { ptx::mbar_init(&accf[s], 1); ptx::mbar_init(&acce[s], 128); }
     ptx::mbar_init(wbar, 1);
     ptx::fence_mbar_init();
@@ -418,7 +423,7 @@ __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
         const int j = (item / p.NB) % p.T, g = item / (p.NB * p.T);
         const uint4* xg = p.xin + (size_t)g * D * C8 * p.Lp + (size_t)128 * j;
         for (int it = 0; it < D; it++, gp++) {
-          const uint32_t st = gp % kTcStages, ph = (gp / kTcStages) & 1;
+          const uint32_t st = gp % S::kStages, ph = (gp / S::kStages) & 1;
           ptx::mbar_wait(&empty[st], ph ^ 1);
           if (ptx::elect_one()) {
             ptx::mbar_expect_tx(&full[st], (uint32_t)C8 * slab_row);
@@ -445,7 +450,7 @@ __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, go_base += D) {
         for (int it = 0; it < D; it++, gp++) {
           const int xi = it + 1;
-          const uint32_t st = gp % kTcStages, ph = (gp / kTcStages) & 1;
+          const uint32_t st = gp % S::kStages, ph = (gp / S::kStages) & 1;
           const int lo = xi > 1 ? xi - 1 : 1, hi = xi < D ? xi + 1 : D;
           const int fresh_lo = xi == 1 ? 1 : xi + 1;  // output planes >= fresh_lo get their first contribution now
           for (int xo = fresh_lo; xo <= hi; xo++) {
@@ -573,8 +578,9 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4],
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// Variant A (rows = voxels): one warp = 2 pooled voxels as the 16 rows of the MMA; faster for C = 32.
 template <int C>
-__global__ void __launch_bounds__(256) pointwise_pool_kernel(const __half* __restrict__ yin, const __half* __restrict__ w,
+__global__ void __launch_bounds__(256) pointwise_pool_rows_kernel(const __half* __restrict__ yin, const __half* __restrict__ w,
                                                              const float* __restrict__ bias, uint4* __restrict__ xout,
                                                              int D, int n_poses, int Gn, int Lpn) {
   constexpr int NT = C / 8, KS = C / 16;
@@ -640,6 +646,77 @@ __global__ void __launch_bounds__(256) pointwise_pool_kernel(const __half* __res
         const __half2 hB = __floats2half2_rn(v[2], v[3]);
         base[t] = *reinterpret_cast<const uint32_t*>(&hA);      // pooled voxel A
         base[4 + t] = *reinterpret_cast<const uint32_t*>(&hB);  // pooled voxel B = next position
+      }
+    }
+  }
+}
+
+// Variant B, faster for C = 64.
+// Transposed formulation: Y2^T[co][voxel] = W[co][ci] * Y1^T[ci][voxel]  (A = weights, resident in registers;
+// B = 8 fine voxels of ONE pooled voxel, loaded straight from the channels-last input), so the 2x2x2 average is a
+// sum over the N dimension of the accumulator fragment: c0+c1 in-thread, then two xor-shuffles over the 4 lanes of
+// a quad — instead of three shuffles on every accumulator register.
+template <int C>
+__global__ void __launch_bounds__(256) pointwise_pool_kernel(const __half* __restrict__ yin, const __half* __restrict__ w,
+                                                             const float* __restrict__ bias, __half* __restrict__ xout,
+                                                             int D, int n_poses, int Gn, int Lpn) {
+  constexpr int MT = C / 16, KS = C / 16;
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int Dn = D / 2, Pn = Dn + 2, C8n = C / 8;
+  uint32_t af[MT][KS][4];  // A fragments of W: rows = output channels
+#pragma unroll
+  for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) {
+      const __half* w0 = w + (size_t)(mt * 16 + g) * C + ks * 16 + 2 * t;
+      const __half* w1 = w0 + (size_t)8 * C;
+      af[mt][ks][0] = *reinterpret_cast<const uint32_t*>(w0);
+      af[mt][ks][1] = *reinterpret_cast<const uint32_t*>(w1);
+      af[mt][ks][2] = *reinterpret_cast<const uint32_t*>(w0 + 8);
+      af[mt][ks][3] = *reinterpret_cast<const uint32_t*>(w1 + 8);
+    }
+  float bs[MT][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; mt++) { bs[mt][0] = bias[mt * 16 + g]; bs[mt][1] = bias[mt * 16 + g + 8]; }
+
+  const int n_pv = n_poses * Dn * Dn * Dn;  // < 2^31 for any chunk size the handle allows
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int n_warps = gridDim.x * (blockDim.x >> 5);
+  // B fragment column n = g is fine voxel g of the pooled voxel: (di,dj,dk) = bits of g
+  const int di = (g >> 2) & 1, dj = (g >> 1) & 1, dk = g & 1;
+  for (int pv = warp_global; pv < n_pv; pv += n_warps) {
+    const int z0 = pv % Dn;
+    int r = pv / Dn;
+    const int y0 = r % Dn; r /= Dn;
+    const int x0 = r % Dn;
+    const int pose = r / Dn;
+    const __half* row = yin + ((((size_t)pose * D + (2 * x0 + di)) * D + (2 * y0 + dj)) * D + (2 * z0 + dk)) * C;
+    uint32_t bfr[KS][2];
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) {
+      bfr[ks][0] = *reinterpret_cast<const uint32_t*>(row + ks * 16 + 2 * t);
+      bfr[ks][1] = *reinterpret_cast<const uint32_t*>(row + ks * 16 + 8 + 2 * t);
+    }
+    const int grp = pose / Gn, q = pose % Gn;
+    const size_t pos = (size_t)q * Pn * Pn + (size_t)(y0 + 1) * Pn + (z0 + 1);
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < KS; ks++) mma_16816(acc, af[mt][ks], bfr[ks][0], bfr[ks][1]);
+      // acc[0],acc[1]: channel mt*16+g, fine voxels 2t,2t+1 ; acc[2],acc[3]: channel mt*16+g+8
+      float s0 = fmaxf(acc[0] + bs[mt][0], 0.f) + fmaxf(acc[1] + bs[mt][0], 0.f);
+      float s1 = fmaxf(acc[2] + bs[mt][1], 0.f) + fmaxf(acc[3] + bs[mt][1], 0.f);
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      if (t == 0) {
+        // chunk 2*mt holds channels mt*16 .. +7 (lane g writes channel g), chunk 2*mt+1 the next eight
+        __half* o0 = xout + ((((size_t)grp * Dn + x0) * C8n + 2 * mt) * Lpn + pos) * 8 + g;
+        o0[0] = __float2half(s0 * 0.125f);
+        o0[(size_t)Lpn * 8] = __float2half(s1 * 0.125f);
       }
     }
   }
@@ -796,7 +873,7 @@ int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspa
   if (x0_consumed) GB_CUDA(cudaEventRecord(x0_consumed, s));
   {
     ProfScope ps(prof, "tc_pw2_pool", s);
-    pointwise_pool_kernel<32><<<pw_blocks, 256, 0, s>>>(Y, tw->pw2.w, tw->pw2.bias, X2, 24, nb, L3.G, L3.Lp);
+    pointwise_pool_rows_kernel<32><<<pw_blocks, 256, 0, s>>>(Y, tw->pw2.w, tw->pw2.bias, X2, 24, nb, L3.G, L3.Lp);
   }
   {
     ProfScope ps(prof, "tc_conv3_3x3x3_32x64_d12", s);
@@ -804,7 +881,7 @@ int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspa
   }
   {
     ProfScope ps(prof, "tc_pw4_pool", s);
-    pointwise_pool_kernel<64><<<pw_blocks, 256, 0, s>>>(Y, tw->pw4.w, tw->pw4.bias, X4, 12, nb, L5.G, L5.Lp);
+    pointwise_pool_kernel<64><<<pw_blocks, 256, 0, s>>>(Y, tw->pw4.w, tw->pw4.bias, reinterpret_cast<__half*>(X4), 12, nb, L5.G, L5.Lp);
   }
   {
     ProfScope ps(prof, "tc_conv5_3x3x3_64x128_d6", s);
