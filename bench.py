@@ -88,62 +88,102 @@ def make_workload(n_poses, seed):
     return rec_xyz, rec_t, lig_xyz, np.tile(lt0, n_poses), offs
 
 
+class CpuPort:
+    """The reference's CPU algorithm restated (oracle/): C voxeliser + the same network in torch CPU fp32 ops, batch 1
+    per CNN call, the receptor re-voxelised for every pose (torch_model.cpp:153-224).  Two ways of using the host:
+      sequential    : poses one after another, torch intra-op threads = T (what `gnina --cpu T` does: one ligand
+                      worker thread for rescoring, main/main.cpp:1432-1433, torch::set_num_threads, :1374)
+      pose_parallel : W python threads each scoring whole poses with 1 torch thread (best effort for the host)
+    """
+
+    def __init__(self, n_poses):
+        import torch
+        from gnina_b200 import model_blob
+        from oracle import pipeline
+        self.torch = torch
+        self.cores = os.cpu_count() or 1
+        self.w = make_workload(n_poses, seed=1)
+        self.om = pipeline.OracleModel(model_blob.load_model(MODEL))
+        self.n = n_poses
+
+    def one(self, i):
+        rec_xyz, rec_t, lig_xyz, lig_t, offs = self.w
+        a, b = offs[i], offs[i + 1]
+        return self.om.score(rec_xyz, rec_t, lig_xyz[a:b], lig_t[a:b], np.array([0, b - a], np.int32), batch=1)
+
+    def sequential(self, idx, threads):
+        self.torch.set_num_threads(threads)
+        t0 = time.perf_counter()
+        for i in idx:
+            self.one(i)
+        return len(idx) / (time.perf_counter() - t0)
+
+    def pose_parallel(self, idx, workers):
+        from concurrent.futures import ThreadPoolExecutor
+        self.torch.set_num_threads(1)
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            list(ex.map(self.one, idx))
+        return len(idx) / (time.perf_counter() - t0)
+
+    def tune(self):
+        """pick the faster host configuration on a small pilot; -> (mode, threads, pilot rate)"""
+        self.one(0)
+        best = ("sequential", 1, 0.0)
+        for t in sorted({4, 8, 16, min(32, self.cores), self.cores}):
+            if t > self.cores:
+                continue
+            r = self.sequential(range(min(3, self.n)), t)
+            if r > best[2]:
+                best = ("sequential", t, r)
+        w = self.cores
+        r = self.pose_parallel(range(min(2 * w, self.n)), w)
+        if r > best[2]:
+            best = ("pose_parallel", w, r)
+        return best
+
+    def run(self, mode, threads, idx):
+        return self.sequential(idx, threads) if mode == "sequential" else self.pose_parallel(idx, threads)
+
+
 def run_reference(args, rank, world):
     """Reference arm: the reference's own CPU algorithm (oracle port) on the host cores, bounded sample per step."""
     if rank != 0:
         return
-    import torch
-    from gnina_b200 import model_blob
-    from oracle import pipeline
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    sample = args.ref_sample
-    rec_xyz, rec_t, lig_xyz, lig_t, offs = make_workload(sample, seed=1)
-    om = pipeline.OracleModel(model_blob.load_model(MODEL))
-
-    def step():
-        # faithful mode: batch 1 per CNN call, receptor re-voxelised for every pose (torch_model.cpp:153-224)
-        return om.score(rec_xyz, rec_t, lig_xyz, lig_t, offs, batch=1, n_threads=1)
-
-    for _ in range(args.warmup):
-        om.score(rec_xyz, rec_t, lig_xyz[:offs[2]], lig_t[:offs[2]], offs[:3], batch=1)
+    cpu = CpuPort(max(args.ref_sample, 2 * (os.cpu_count() or 1)))
+    mode, threads, pilot = cpu.tune()
+    sample = int(max(4, min(cpu.n, pilot * args.ref_step_seconds)))
+    idx = list(range(sample))
+    for _ in range(min(args.warmup, 1)):
+        cpu.run(mode, threads, idx[: max(2, sample // 8)])
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        cpu.run(mode, threads, idx)
     dt = time.perf_counter() - t0
     v = sample * args.steps / dt
+    desc = "%d poses/step, %s, %d threads, batch 1 per CNN call, receptor re-voxelised per pose" % (sample, mode, threads)
     line = {"impl": "reference", "metric": "poses/sec CNN-rescored (48^3x28ch default2018)", "value": v,
             "unit": "poses/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "CNN rescoring: 1 receptor (3000 atoms), synthetic ligand poses, 48^3x28ch "
-                                   "crossdock_default2018", "sample_poses_per_step": sample},
-            "cpu_baseline": {"value": v, "unit": "poses/s", "cores": cores, "kind": "port",
-                             "sample": "%d poses/step, batch 1 per CNN call, receptor re-voxelised per pose" % sample},
+                                   "crossdock_default2018", "sample_poses_per_step": sample, "host_mode": mode},
+            "cpu_baseline": {"value": v, "unit": "poses/s", "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def cpu_baseline(seconds_budget=20.0):
-    import torch
-    from gnina_b200 import model_blob
-    from oracle import pipeline
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    n = 24
-    rec_xyz, rec_t, lig_xyz, lig_t, offs = make_workload(n, seed=1)
-    om = pipeline.OracleModel(model_blob.load_model(MODEL))
-    om.score(rec_xyz, rec_t, lig_xyz[:offs[1]], lig_t[:offs[1]], offs[:2], batch=1)
-    t0 = time.perf_counter()
-    done = 0
-    while done < n and time.perf_counter() - t0 < seconds_budget:
-        om.score(rec_xyz, rec_t, lig_xyz[offs[done]:offs[done + 1]], lig_t[offs[done]:offs[done + 1]],
-                 np.array([0, offs[done + 1] - offs[done]], np.int32), batch=1)
-        done += 1
-    dt = time.perf_counter() - t0
-    return {"value": done / dt, "unit": "poses/s", "cores": cores, "kind": "port",
-            "sample": "%d poses, batch 1 per CNN call, receptor re-voxelised per pose (torch_model.cpp:153-224 "
-                      "restated: oracle C voxeliser + torch CPU fp32 network)" % done}
+def cpu_baseline(seconds_budget=15.0):
+    cpu = CpuPort(4 * (os.cpu_count() or 1))
+    mode, threads, pilot = cpu.tune()
+    sample = int(max(4, min(cpu.n, pilot * seconds_budget)))
+    v = cpu.run(mode, threads, list(range(sample)))
+    seq = cpu.sequential(range(3), min(8, cpu.cores))
+    return {"value": v, "unit": "poses/s", "cores": threads, "kind": "port",
+            "sample": "%d poses, %s with %d threads (best of sequential/pose-parallel pilots), batch 1 per CNN call, "
+                      "receptor re-voxelised per pose (torch_model.cpp:153-224 restated: oracle C voxeliser + torch "
+                      "CPU fp32 network)" % (sample, mode, threads),
+            "sequential_8_threads": seq}
 
 
 def main():
@@ -154,7 +194,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--poses", type=int, default=10000, help="poses per GPU per step (config 2: 10k)")
     ap.add_argument("--precision", type=int, default=-1, help="-1 library default, 0 fp32 validation, 1 fp16 tensor-core")
-    ap.add_argument("--ref-sample", type=int, default=200, help="poses per step for --impl reference")
+    ap.add_argument("--ref-sample", type=int, default=4096, help="max poses per step for --impl reference")
+    ap.add_argument("--ref-step-seconds", type=float, default=6.0, help="target CPU seconds per step (reference arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--overlap", type=int, default=-1, help="voxeliser/network stream overlap (library option)")
     ap.add_argument("--max-batch", type=int, default=0)
