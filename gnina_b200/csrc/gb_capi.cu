@@ -77,7 +77,10 @@ struct GridGroup {
   int n_rec = 0;
   // staged ligand atoms
   PinBuf<float4> h_lig_xyzr;
-  PinBuf<int> h_lig_ch, h_lig_off;
+  PinBuf<int> h_lig_ch, h_lig_off, h_lig_src;  // h_lig_src: staged atom -> index in the caller's arrays
+  DevBuf<float> lig_grad;   // [staged atoms][3], accumulated over the models of the group
+  PinBuf<float> h_lig_grad;
+  int n_staged_atoms = 0;
   DevBuf<float4> lig_xyzr;
   DevBuf<int> lig_ch, lig_off;
   int max_pose_atoms = 0;
@@ -117,6 +120,9 @@ struct gb_cnn {
   DevBuf<float> d_final;                 // [4][n_staged]
   PinBuf<float> h_final;
   Fp32Workspace ws32;
+  Fp32GradWorkspace ws_grad;
+  DevBuf<float> d_dgrid;
+  int n_input_atoms = 0;
   TcWorkspace ws_tc;
   int64_t launches = 0;
   Profiler prof;
@@ -381,6 +387,7 @@ int gb_cnn_stage_poses(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type,
   // the previous batch may still be reading the pinned staging buffers
   GB_CUDA(cudaStreamSynchronize(h->stream));
   h->n_staged = n_poses;
+  h->n_input_atoms = n_poses > 0 ? pose_offsets[n_poses] : 0;
   if (n_poses == 0) return GB_OK;
   const int total = pose_offsets[n_poses];
   GB_CHECK(pose_offsets[0] == 0 && total >= 0, "pose_offsets must start at 0");
@@ -407,6 +414,7 @@ int gb_cnn_stage_poses(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type,
     G.h_lig_xyzr.ensure((size_t)total);
     G.h_lig_ch.ensure((size_t)total);
     G.h_lig_off.ensure((size_t)n_poses + 1);
+    G.h_lig_src.ensure((size_t)total);
     const int nrc = G.rec.n_channels, nlc = G.lig.n_channels;
     int w = 0, maxp = 0;
     int cnt[64], start[64];
@@ -430,11 +438,13 @@ int gb_cnn_stage_poses(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type,
         G.h_lig_xyzr.p[dst] = make_float4(lig_xyz[3 * i], lig_xyz[3 * i + 1], lig_xyz[3 * i + 2],
                                           kSminaXsRadius[t] * G.sig.radius_scaling);
         G.h_lig_ch.p[dst] = nrc + c;
+        G.h_lig_src.p[dst] = i;
       }
       maxp = std::max(maxp, s - w);
       w = s;
     }
     G.h_lig_off.p[n_poses] = w;
+    G.n_staged_atoms = w;
     G.max_pose_atoms = maxp;
     G.lig_xyzr.ensure((size_t)total);
     G.lig_ch.ensure((size_t)total);
@@ -615,6 +625,86 @@ int gb_cnn_debug_read(gb_cnn* h, const char* name, void* out, size_t cap_bytes, 
     GB_CUDA(cudaStreamSynchronize(h->stream));
     GB_CUDA(cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
   }
+  GB_API_END
+}
+
+// TorchModel::forward(compute_gradient = true) + CNNTorchScorer::score's accumulation (cnn_torch_scorer.cpp:164-179):
+// fp32 forward keeping activations, backward of the CE loss to the grid, GridMaker::backward to the ligand atoms,
+// mean over the models of the ensemble.
+int gb_cnn_score_grad(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, const int32_t* pose_offsets, int n_poses,
+                      const float* centers, float* score, float* affinity, float* loss, float* variance,
+                      float* dlig_xyz, float* drec_xyz) {
+  int rc = gb_cnn_stage_poses(h, lig_xyz, lig_type, pose_offsets, n_poses, centers);
+  if (rc) return rc;
+  GB_API_BEGIN
+  GB_CHECK(dlig_xyz, "dlig_xyz must not be NULL");
+  if (drec_xyz) throw Error(GB_ERR_USAGE, "receptor (flexible residue) gradients are not implemented yet");
+  GB_CUDA(cudaSetDevice(h->device));
+  const int n = h->n_staged, M = (int)h->models.size();
+  const int n_in = h->n_input_atoms;
+  for (int i = 0; i < 3 * n_in; i++) dlig_xyz[i] = 0.f;
+  if (n == 0) return GB_OK;
+  for (Model* m : h->models)
+    if (m->arch != GB_ARCH_DEFAULT2018)
+      throw Error(GB_ERR_USAGE, "gradient path is implemented for the default2018 family only (model " + m->name + ")");
+  h->d_pose.ensure((size_t)M * n);
+  h->d_aff.ensure((size_t)M * n);
+  h->d_loss.ensure((size_t)M * n);
+  h->d_final.ensure(4 * (size_t)n);
+  const int chunk = h->max_batch > 0 ? std::min(h->max_batch, 8) : 8;
+  h->d_out3.ensure(3 * (size_t)std::max(chunk, chunk_size(h)));
+  for (auto& Gp : h->groups) {
+    GridGroup& G = *Gp;
+    G.lig_grad.ensure(3 * (size_t)std::max(G.n_staged_atoms, 1));
+    GB_CUDA(cudaMemsetAsync(G.lig_grad.p, 0, 3 * (size_t)std::max(G.n_staged_atoms, 1) * sizeof(float), h->stream));
+  }
+  DevBuf<float> tmp_grad;
+  for (int p0 = 0; p0 < n; p0 += chunk) {
+    const int nb = std::min(chunk, n - p0);
+    for (auto& Gp : h->groups) {
+      GridGroup& G = *Gp;
+      voxelize_chunk_f32(h, G, p0, nb);
+      const int npts = (int)std::lround(G.sig.dimension / G.sig.resolution) + 1;
+      h->d_dgrid.ensure((size_t)nb * G.n_channels * npts * npts * npts);
+      tmp_grad.ensure(3 * (size_t)std::max(G.n_staged_atoms, 1));
+      for (int mi : G.model_idx) {
+        const Model& Mo = *h->models[mi];
+        if (Mo.apply_logistic_loss || Mo.skip_softmax)
+          throw Error(GB_ERR_USAGE, "gradient of apply_logistic_loss / skip_softmax models is not implemented");
+        h->launches += forward_backward_fp32(Mo, G.grid.p, nb, h->ws_grad, h->d_out3.p, h->d_dgrid.p, h->stream, &h->prof);
+        launch_head_post(h->d_out3.p, nb, Mo.skip_softmax, Mo.apply_logistic_loss, h->d_pose.p + (size_t)mi * n + p0,
+                         h->d_aff.p + (size_t)mi * n + p0, h->d_loss.p + (size_t)mi * n + p0, h->stream);
+        // ligand atoms of this chunk: accumulate (scaled 1/M) into the group's gradient array
+        launch_grid_backward(G.lig_xyzr.p, G.lig_ch.p, G.lig_off.p + p0, G.max_pose_atoms, h->d_centers.p + 3 * (size_t)p0, nb,
+                             G.n_channels, npts, G.sig.resolution, G.sig.dimension, h->d_dgrid.p, tmp_grad.p, h->stream);
+        launch_axpy_range(tmp_grad.p, G.lig_grad.p, G.h_lig_off.p[p0] * 3, G.h_lig_off.p[p0 + nb] * 3, 1.0f / (float)M,
+                          h->stream);
+        h->launches += 3;
+      }
+    }
+  }
+  launch_ensemble(h->d_pose.p, h->d_aff.p, h->d_loss.p, M, n, n, h->d_final.p, h->d_final.p + n, h->d_final.p + 2 * (size_t)n,
+                  h->d_final.p + 3 * (size_t)n, h->stream);
+  h->launches++;
+  // typed maps may differ between grid groups: every group contributes the gradient of ITS models (already /M)
+  for (auto& Gp : h->groups) {
+    GridGroup& G = *Gp;
+    if (!G.n_staged_atoms) continue;
+    G.h_lig_grad.ensure(3 * (size_t)G.n_staged_atoms);
+    GB_CUDA(cudaMemcpyAsync(G.h_lig_grad.p, G.lig_grad.p, 3 * (size_t)G.n_staged_atoms * sizeof(float), cudaMemcpyDeviceToHost,
+                            h->stream));
+  }
+  GB_CUDA(cudaStreamSynchronize(h->stream));
+  for (auto& Gp : h->groups) {
+    GridGroup& G = *Gp;
+    for (int a = 0; a < G.n_staged_atoms; a++) {
+      const int src = G.h_lig_src.p[a];
+      for (int d = 0; d < 3; d++) dlig_xyz[3 * src + d] += G.h_lig_grad.p[3 * a + d];
+    }
+  }
+  GB_CUDA(cudaGetLastError());
+  rc = gb_cnn_fetch(h, score, affinity, loss, variance);
+  if (rc) return rc;
   GB_API_END
 }
 

@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(512) conv3d_f32_kernel(const float* __restrict
                                                          const float* __restrict__ w, const float* __restrict__ bias,
                                                          const float* __restrict__ bn_scale,
                                                          const float* __restrict__ bn_shift, float* __restrict__ out,
-                                                         int out_ctot, int out_coff, int Cout, int D, int relu) {
+                                                         int out_ctot, int out_coff, int Cout, int D, int relu,
+                                                         const float* __restrict__ mask) {
   constexpr int CIC = 4;
   constexpr int H = KS / 2;
   constexpr int TW = 8 + 2 * H;
@@ -66,8 +67,11 @@ __global__ void __launch_bounds__(512) conv3d_f32_kernel(const float* __restrict
       const int gi = ti * 8 + a - H, gj = tj * 8 + bb - H, gk = tk * 8 + cc - H;
       float v = 0.f;
       if (c0 + ci < Cin && gi >= 0 && gi < D && gj >= 0 && gj < D && gk >= 0 && gk < D) {
-        v = inb[(size_t)(c0 + ci) * vol + ((size_t)gi * D + gj) * D + gk];
+        const size_t gidx = (size_t)(c0 + ci) * vol + ((size_t)gi * D + gj) * D + gk;
+        v = inb[gidx];
         if (bn_scale) v = fmaf(v, bn_scale[c0 + ci], bn_shift[c0 + ci]);
+        // ReLU backward folded into the load: mask is the forward activation of the same shape
+        if (mask && !(mask[(size_t)b * in_ctot * vol + gidx] > 0.f)) v = 0.f;
       }
       (&s_in[0][0][0][0])[e] = v;
     }
@@ -117,16 +121,21 @@ __global__ void __launch_bounds__(512) conv3d_f32_kernel(const float* __restrict
 
 static Profiler* g_prof_tls();
 static int launch_conv(const ConvF32& c, const float* in, int in_ctot, float* out, int out_ctot, int out_coff, int D,
-                       int B, bool relu, cudaStream_t s) {
+                       int B, bool relu, cudaStream_t s, bool backward = false, const float* mask = nullptr) {
   char nm[64];
-  snprintf(nm, sizeof nm, "f32_conv%d_%dx%d_d%d", c.ks, c.cin, c.cout, D);
+  snprintf(nm, sizeof nm, backward ? "f32_dgrad%d_%dx%d_d%d" : "f32_conv%d_%dx%d_d%d", c.ks, c.cin, c.cout, D);
   ProfScope ps(g_prof_tls(), nm, s);
   const int tiles = (D + 7) / 8;
-  const int cot = (c.cout % 32 == 0) ? 32 : 16;
-  dim3 g(tiles * tiles * tiles, (c.cout + cot - 1) / cot, B);
-#define GB_LAUNCH(KS, COT)                                                                                        \
-  conv3d_f32_kernel<KS, COT><<<g, 512, 0, s>>>(in, in_ctot, c.cin, c.w, c.bias, c.bn_scale, c.bn_shift, out, out_ctot, \
-                                               out_coff, c.cout, D, relu ? 1 : 0)
+  // backward-data = the same convolution with the transposed/flipped weights: roles of cin and cout swap
+  const int kin = backward ? c.cout : c.cin, kout = backward ? c.cin : c.cout;
+  const float* kw = backward ? c.wT : c.w;
+  const float* kb = backward ? c.zero_bias : c.bias;
+  const int cot = (kout % 32 == 0) ? 32 : 16;
+  dim3 g(tiles * tiles * tiles, (kout + cot - 1) / cot, B);
+#define GB_LAUNCH(KS, COT)                                                                                     \
+  conv3d_f32_kernel<KS, COT><<<g, 512, 0, s>>>(in, in_ctot, kin, kw, kb, backward ? nullptr : c.bn_scale,      \
+                                               backward ? nullptr : c.bn_shift, out, out_ctot, out_coff, kout, D, \
+                                               relu ? 1 : 0, mask)
   if (c.ks == 3 && cot == 32) GB_LAUNCH(3, 32);
   else if (c.ks == 3) GB_LAUNCH(3, 16);
   else if (c.ks == 1 && cot == 32) GB_LAUNCH(1, 32);
@@ -341,6 +350,97 @@ int forward_fp32(const Model& m, const float* grid, int B, Fp32Workspace& ws, fl
     fc3_kernel<<<B, 256, 0, s>>>(feat, m.fc_w, m.fc_b, m.fc_features, out3);
   }
   launches++;
+  t_prof = nullptr;
+  return launches;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Backward pieces (N5 of SURVEY.md §8a): avg-pool backward (each fine voxel receives 1/8 of its pooled gradient),
+// heads backward for loss = CE(logits, label 1): dL/dz0 = softmax(z)[0], dL/dz1 = -softmax(z)[0], affinity head
+// does not enter the loss (torch_model.cpp:195).
+__global__ void unpool2_f32_kernel(const float* __restrict__ dy, float* __restrict__ dx, int C, int Dout, size_t total) {
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int Din = Dout / 2;
+  size_t r = idx;
+  const int k = r % Dout; r /= Dout;
+  const int j = r % Dout; r /= Dout;
+  const int i = r % Dout; r /= Dout;  // r = b*C + c
+  dx[idx] = 0.125f * dy[((r * Din + (i >> 1)) * Din + (j >> 1)) * Din + (k >> 1)];
+}
+
+__global__ void fc3_backward_kernel(const float* __restrict__ out3, const float* __restrict__ w, int F,
+                                    float* __restrict__ dfeat) {
+  const int b = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const float z0 = out3[3 * b], z1 = out3[3 * b + 1];
+  const float m = fmaxf(z0, z1);
+  const float e0 = expf(z0 - m), e1 = expf(z1 - m);
+  const float p0 = e0 / (e0 + e1);
+  dfeat[(size_t)b * F + f] = p0 * w[f] - p0 * w[F + f];
+}
+
+void Fp32GradWorkspace::ensure(int i, size_t n) {
+  if (cap[i] >= n) return;
+  if (a[i]) cudaFree(a[i]);
+  GB_CUDA(cudaMalloc(&a[i], n * sizeof(float)));
+  cap[i] = n;
+}
+Fp32GradWorkspace::~Fp32GradWorkspace() {
+  for (auto p : a)
+    if (p) cudaFree(p);
+}
+
+int forward_backward_fp32(const Model& m, const float* grid, int B, Fp32GradWorkspace& ws, float* out3, float* dgrid,
+                          cudaStream_t s, Profiler* prof) {
+  if (m.arch != GB_ARCH_DEFAULT2018)
+    throw Error(GB_ERR_USAGE, "gradient path is implemented for the default2018 family only (model " + m.name + ")");
+  GB_CHECK(m.npts == 48, "CNN graphs expect a 48^3 grid");
+  int launches = 0;
+  t_prof = prof;
+  const int C = m.n_channels;
+  auto conv = [&](const std::string& k) -> const ConvF32& { return m.convs.at(k); };
+  const size_t v24 = 24 * 24 * 24, v12 = 12 * 12 * 12, v6 = 6 * 6 * 6;
+  const size_t n[8] = {(size_t)B * C * v24,  (size_t)B * 32 * v24, (size_t)B * 32 * v24, (size_t)B * 32 * v12,
+                       (size_t)B * 64 * v12, (size_t)B * 64 * v12, (size_t)B * 64 * v6,  (size_t)B * 128 * v6};
+  for (int i = 0; i < 8; i++) ws.ensure(i, n[i]);
+  ws.ensure(8, (size_t)B * 32 * v24);
+  ws.ensure(9, (size_t)B * 32 * v24);
+  float *x0 = ws.a[0], *y1 = ws.a[1], *y2 = ws.a[2], *x2 = ws.a[3], *y3 = ws.a[4], *y4 = ws.a[5], *x4 = ws.a[6],
+        *y5 = ws.a[7], *ga = ws.a[8], *gb2 = ws.a[9];
+  // forward, every activation kept
+  launches += launch_pool(grid, C, x0, C, C, 48, B, false, s);
+  launches += launch_conv(conv("unit1_conv"), x0, C, y1, 32, 0, 24, B, true, s);
+  launches += launch_conv(conv("unit2_conv"), y1, 32, y2, 32, 0, 24, B, true, s);
+  launches += launch_pool(y2, 32, x2, 32, 32, 24, B, false, s);
+  launches += launch_conv(conv("unit3_conv"), x2, 32, y3, 64, 0, 12, B, true, s);
+  launches += launch_conv(conv("unit4_conv"), y3, 64, y4, 64, 0, 12, B, true, s);
+  launches += launch_pool(y4, 64, x4, 64, 64, 12, B, false, s);
+  launches += launch_conv(conv("unit5_conv"), x4, 64, y5, 128, 0, 6, B, true, s);
+  fc3_kernel<<<B, 256, 0, s>>>(y5, m.fc_w, m.fc_b, m.fc_features, out3);
+  // backward
+  const int F = m.fc_features;
+  fc3_backward_kernel<<<dim3((F + 255) / 256, B), 256, 0, s>>>(out3, m.fc_w, F, ga);              // d y5 (pre-mask)
+  launches += 2;
+  launches += launch_conv(conv("unit5_conv"), ga, 128, gb2, 64, 0, 6, B, false, s, true, y5);       // d x4
+  {
+    const size_t tot = (size_t)B * 64 * v12;
+    unpool2_f32_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(gb2, ga, 64, 12, tot);         // d y4
+  }
+  launches += launch_conv(conv("unit4_conv"), ga, 64, gb2, 64, 0, 12, B, false, s, true, y4);       // d y3
+  launches += launch_conv(conv("unit3_conv"), gb2, 64, ga, 32, 0, 12, B, false, s, true, y3);       // d x2
+  {
+    const size_t tot = (size_t)B * 32 * v24;
+    unpool2_f32_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(ga, gb2, 32, 24, tot);         // d y2
+  }
+  launches += launch_conv(conv("unit2_conv"), gb2, 32, ga, 32, 0, 24, B, false, s, true, y2);       // d y1
+  launches += launch_conv(conv("unit1_conv"), ga, 32, gb2, C, 0, 24, B, false, s, true, y1);        // d x0
+  {
+    const size_t tot = (size_t)B * C * 48 * 48 * 48;
+    unpool2_f32_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(gb2, dgrid, C, 48, tot);       // d grid
+  }
+  launches += 3;
   t_prof = nullptr;
   return launches;
 }

@@ -176,4 +176,77 @@ void launch_voxelize_f32(const float4* list_xyzr, const int* list_ch, const int*
                                         dimension, grid);
 }
 
+// GridMaker::backward (call site gninasrc/lib/torch_model.cpp:203): one warp per listed atom, lanes stride over the
+// atom's bounding box of voxels, warp-shuffle reduction of the three gradient components.
+// d rho/d x_a = rho'(d) (x_a - v)/d ; rho'(d) = -4 d/r^2 exp(-2 d^2/r^2) (d <= r), (2 A d/r + B)/r (r < d < 1.5 r).
+__global__ void __launch_bounds__(256) grid_backward_kernel(const float4* __restrict__ atoms_xyzr,
+                                                            const int* __restrict__ atoms_ch,
+                                                            const int* __restrict__ pose_off,
+                                                            const float* __restrict__ centers, int n_channels, int npts,
+                                                            float resolution, float dimension,
+                                                            const float* __restrict__ dgrid, float* __restrict__ atom_grad) {
+  const int p = blockIdx.y;
+  const int a_i = pose_off[p] + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (a_i >= pose_off[p + 1]) return;
+  const float4 a = atoms_xyzr[a_i];
+  const int ch = atoms_ch[a_i];
+  const float half = dimension / 2.f;
+  const float ox = centers[3 * p] - half, oy = centers[3 * p + 1] - half, oz = centers[3 * p + 2] - half;
+  const float ar = a.w, reach = 1.5f * ar;
+  int lo[3], hi[3];
+  const float o[3] = {ox, oy, oz}, c[3] = {a.x, a.y, a.z};
+  bool empty = false;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    lo[d] = max(0, (int)floorf((c[d] - reach - o[d]) / resolution));
+    hi[d] = min(npts - 1, (int)ceilf((c[d] + reach - o[d]) / resolution));
+    empty |= lo[d] > hi[d];
+  }
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+  if (!empty && ch >= 0 && ch < n_channels) {
+    const int ni = hi[0] - lo[0] + 1, nj = hi[1] - lo[1] + 1, nk = hi[2] - lo[2] + 1;
+    const float* g = dgrid + ((size_t)p * n_channels + ch) * npts * npts * npts;
+    const float e2 = 0.13533528323661270f, A = 4.f * e2, Bq = -12.f * e2;
+    for (int e = lane; e < ni * nj * nk; e += 32) {
+      const int k = lo[2] + e % nk, j = lo[1] + (e / nk) % nj, i = lo[0] + e / (nk * nj);
+      const float dx = (ox + i * resolution) - a.x, dy = (oy + j * resolution) - a.y, dz = (oz + k * resolution) - a.z;
+      const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+      if (dist >= reach || dist == 0.f) continue;
+      float dr;
+      if (dist <= ar) dr = -4.f * dist / (ar * ar) * expf(-2.f * dist * dist / (ar * ar));
+      else dr = (2.f * A * (dist / ar) + Bq) / ar;
+      const float sc = g[((size_t)i * npts + j) * npts + k] * dr / dist;
+      gx -= sc * dx; gy -= sc * dy; gz -= sc * dz;
+    }
+  }
+  for (int off = 16; off; off >>= 1) {
+    gx += __shfl_xor_sync(0xffffffffu, gx, off);
+    gy += __shfl_xor_sync(0xffffffffu, gy, off);
+    gz += __shfl_xor_sync(0xffffffffu, gz, off);
+  }
+  if (lane == 0) {
+    float* og = atom_grad + (size_t)a_i * 3;
+    og[0] = gx; og[1] = gy; og[2] = gz;
+  }
+}
+
+void launch_grid_backward(const float4* atoms_xyzr, const int* atoms_ch, const int* pose_off, int max_pose_atoms,
+                          const float* centers, int n_poses, int n_channels, int npts, float resolution, float dimension,
+                          const float* dgrid, float* atom_grad, cudaStream_t s) {
+  if (n_poses <= 0 || max_pose_atoms <= 0) return;
+  dim3 g((max_pose_atoms + 7) / 8, n_poses);
+  grid_backward_kernel<<<g, 256, 0, s>>>(atoms_xyzr, atoms_ch, pose_off, centers, n_channels, npts, resolution, dimension,
+                                         dgrid, atom_grad);
+}
+
+__global__ void axpy_range_kernel(const float* __restrict__ src, float* __restrict__ dst, int lo, int hi, float alpha) {
+  const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < hi) dst[i] += alpha * src[i];
+}
+void launch_axpy_range(const float* src, float* dst, int lo, int hi, float alpha, cudaStream_t s) {
+  if (hi <= lo) return;
+  axpy_range_kernel<<<(hi - lo + 255) / 256, 256, 0, s>>>(src, dst, lo, hi, alpha);
+}
+
 }  // namespace gb

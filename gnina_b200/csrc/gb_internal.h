@@ -53,6 +53,8 @@ struct ConvF32 {
   float* bias = nullptr;  // [cout]
   float* bn_scale = nullptr;  // [cin] or null : y = x*scale + shift applied to in-bounds inputs
   float* bn_shift = nullptr;
+  float* wT = nullptr;        // backward-data weights [cout][ks^3][cin]: taps flipped, channels swapped
+  float* zero_bias = nullptr; // [cin] zeros (bias of the backward-data convolution)
 };
 
 // fp16 tensor-core path weights (see gb_cnn_tc.cu)
@@ -142,6 +144,24 @@ struct Fp32Workspace {
 // grid [B][C][48^3] fp32 -> out3 [B][3] (pose logit0, logit1, affinity); returns #kernel launches
 int forward_fp32(const Model& m, const float* grid, int B, Fp32Workspace& ws, float* out3, cudaStream_t s,
                  Profiler* prof = nullptr);
+// Forward of the default2018 family keeping every activation, then backward of loss = CE(logits, label 1)
+// (torch_model.cpp:195-199) down to dLoss/dGrid [B][C][48^3].  Returns #kernel launches.
+struct Fp32GradWorkspace {
+  float* a[10] = {};   // activations: x0,y1,y2,x2,y3,y4,x4,y5 ; gradient ping-pong: a[8], a[9]
+  size_t cap[10] = {};
+  void ensure(int i, size_t nfloats);
+  ~Fp32GradWorkspace();
+};
+int forward_backward_fp32(const Model& m, const float* grid, int B, Fp32GradWorkspace& ws, float* out3, float* dgrid,
+                          cudaStream_t s, Profiler* prof = nullptr);
+// GridMaker::backward (torch_model.cpp:203): atom gradients from dLoss/dGrid [n_poses][C][N^3] for typed atoms
+// stored pose after pose (pose p owns atoms [pose_off[p], pose_off[p+1])); dgrid/centers/pose_off are those of the
+// chunk; out: atom_grad[atom][3] indexed like the atom arrays.
+void launch_grid_backward(const float4* atoms_xyzr, const int* atoms_ch, const int* pose_off, int max_pose_atoms,
+                          const float* centers, int n_poses, int n_channels, int npts, float resolution, float dimension,
+                          const float* dgrid, float* atom_grad, cudaStream_t s);
+// dst[i] += alpha * src[i] for i in [lo, hi)
+void launch_axpy_range(const float* src, float* dst, int lo, int hi, float alpha, cudaStream_t s);
 // [B][3] raw -> pose/aff/loss per torch_model.cpp:188-195
 void launch_head_post(const float* out3, int B, bool skip_softmax, bool logistic, float* pose, float* aff,
                       float* loss, cudaStream_t s);

@@ -76,6 +76,14 @@ static void add_conv(Model& m, const std::string& key, const std::string& bn_key
       for (int k = 0; k < k3; k++) r[((size_t)ci * k3 + k) * c.cout + co] = w.data[((size_t)co * c.cin + ci) * k3 + k];
   c.w = upload(m, r);
   c.bias = upload(m, std::vector<float>(b.data, b.data + b.nelem));
+  // backward-data: dX[ci] = sum_{co,tap} dY[co](pos - tap) W[co][ci][tap]  ==  conv(dY, W'), W'[ci][co][tap] = W[co][ci][flip(tap)]
+  std::vector<float> rt((size_t)c.cout * k3 * c.cin);
+  for (int co = 0; co < c.cout; co++)
+    for (int ci = 0; ci < c.cin; ci++)
+      for (int k = 0; k < k3; k++)
+        rt[((size_t)co * k3 + (k3 - 1 - k)) * c.cin + ci] = w.data[((size_t)co * c.cin + ci) * k3 + k];
+  c.wT = upload(m, rt);
+  c.zero_bias = upload(m, std::vector<float>(c.cin, 0.f));
   if (!bn_key.empty()) {
     // eval-mode BatchNorm3d, eps 1e-5 (read from the dense graphs): y = (x-mean)/sqrt(var+eps)*w + b
     const HostTensor &g = m.t(bn_key + ".weight"), &be = m.t(bn_key + ".bias"), &mu = m.t(bn_key + ".running_mean"),

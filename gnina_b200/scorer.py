@@ -143,6 +143,16 @@ class CNNScorer:
                                                         *[_fp(o) for o in out]))
         return tuple(out)
 
+    def score_grad_batch(self, lig_xyz, lig_types, pose_offsets, centers=None):
+        """score(m, compute_gradient=True) in batch form -> (score, affinity, loss, variance, dloss/dlig_xyz [n_atoms,3])"""
+        xyz, t, off, c = self._poses(lig_xyz, lig_types, pose_offsets, centers)
+        n = len(off) - 1
+        out = [np.empty(n, np.float32) for _ in range(4)]
+        grad = np.zeros((len(t), 3), np.float32)
+        capi.check(capi.lib().gb_cnn_score_grad(self._h, _fp(xyz), _ip(t), _ip(off), n, _fp(c), *[_fp(o) for o in out],
+                                                _fp(grad), None))
+        return (*out, grad)
+
     def score(self, lig_xyz, lig_types, center=None):
         """DLScorer::score(model&, false, aff, loss, var) for one pose -> (score, affinity, loss, variance)."""
         n = len(lig_types)

@@ -102,6 +102,16 @@ int gb_cnn_score_batch_models(gb_cnn* h, const float* lig_xyz, const int32_t* li
                               const int32_t* pose_offsets, int n_poses, const float* centers, float* pose,
                               float* affinity, float* loss);
 
+/* CNNTorchScorer::score(model&, compute_gradient = true, ...) in batch form: the four outputs as above plus the
+ * gradient of the (ensemble-mean) loss with respect to every ligand atom passed, dlig_xyz[n_atoms][3]
+ * (TorchModel::forward with autograd + GridMaker::backward, lib/torch_model.cpp:197-221; accumulation and 1/cnt
+ * scaling lib/cnn_torch_scorer.cpp:164-179).  The reference adds this to m.minus_forces (lib/model.cu:247-259);
+ * untyped atoms (hydrogens) get 0.  drec_xyz (flexible-residue gradients, getReceptorGradient) must be NULL for now.
+ * Runs the fp32 validation kernels (default2018 family). */
+int gb_cnn_score_grad(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, const int32_t* pose_offsets,
+                      int n_poses, const float* centers, float* score, float* affinity, float* loss, float* variance,
+                      float* dlig_xyz, float* drec_xyz);
+
 /* Split form used for device-resident measurement: stage = host->device copy of the poses (pinned staging,
  * async on the handle's stream); run = all kernels for the staged poses (no host<->device traffic);
  * fetch = device->host copy of the per-pose ensemble results and stream sync. */

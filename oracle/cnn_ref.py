@@ -82,11 +82,11 @@ def features_dense(blob, x, dtype):
 FEATURES = {"default2018": features_default2018, "default2017": features_default2017, "dense": features_dense}
 
 
-def forward_logits(blob, grid, dtype=torch.float32):
+def forward_logits(blob, grid, dtype=torch.float32, grad=False):
     """grid [B,C,N,N,N] (numpy or tensor) -> (log-softmax pose [B,2], affinity [B]) exactly as the TorchScript
-    module returns them."""
-    x = torch.as_tensor(np.asarray(grid)).to(dtype)
-    with torch.no_grad():
+    module returns them.  grad=True keeps the autograd graph (grid may then be a leaf tensor requiring grad)."""
+    x = grid.to(dtype) if torch.is_tensor(grid) else torch.as_tensor(np.asarray(grid)).to(dtype)
+    with torch.set_grad_enabled(grad):
         f = FEATURES[blob.arch](blob, x, dtype)
         pose = F.linear(f, _t(blob, "pose_output.weight", dtype), _t(blob, "pose_output.bias", dtype))
         aff = F.linear(f, _t(blob, "affinity_output.weight", dtype), _t(blob, "affinity_output.bias", dtype))
@@ -112,6 +112,16 @@ def score_grid(blob, grid, dtype=torch.float32):
     p, a = forward_logits(blob, grid, dtype)
     pose, aff, loss = head_post(blob, p, a)
     return pose.numpy(), aff.numpy(), loss.numpy()
+
+
+def loss_grid_gradient(blob, grid, dtype=torch.float64):
+    """torch_model.cpp:195-199: loss = CE(module output, label 1) (summed over the batch: poses are independent),
+    backward to the grid.  -> (pose[B], affinity[B], loss[B], dloss/dgrid [B,C,N,N,N])"""
+    g = torch.as_tensor(np.asarray(grid)).to(dtype).requires_grad_(True)
+    lp, aff = forward_logits(blob, g, dtype, grad=True)
+    pose, aff, loss = head_post(blob, lp, aff)
+    loss.sum().backward()
+    return pose.detach().numpy(), aff.detach().numpy(), loss.detach().numpy(), g.grad.numpy()
 
 
 def ensemble(scores, affinities, losses):

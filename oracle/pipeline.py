@@ -38,6 +38,36 @@ class OracleModel:
         return np.concatenate(P), np.concatenate(A), np.concatenate(L)
 
 
+def score_grad(models, rec_xyz, rec_types, lig_xyz, lig_types, pose_offsets, centers=None, dtype=torch.float64):
+    """CNNTorchScorer::score(m, compute_gradient=True): ensemble outputs + d(mean loss)/d(ligand atoms) [n_atoms,3]
+    (TorchModel::forward autograd + GridMaker::backward, torch_model.cpp:197-221; 1/cnt scaling
+    cnn_torch_scorer.cpp:176-179)."""
+    n = len(pose_offsets) - 1
+    grad = np.zeros((len(lig_types), 3), np.float64)
+    per = []
+    for m in models:
+        b = m.blob
+        P, A, L = [], [], []
+        rc, rr = gm.type_atoms(rec_types, m.rec_t2c, 0)
+        lc, lr = gm.type_atoms(lig_types, m.lig_t2c, m.n_rec)
+        for p in range(n):
+            sl = slice(pose_offsets[p], pose_offsets[p + 1])
+            c = gm.center_of(lig_xyz[sl]) if centers is None else np.asarray(centers[p], np.float32)
+            xyz = np.concatenate([rec_xyz, lig_xyz[sl]])
+            ch = np.concatenate([rc, lc[sl]])
+            rad = np.concatenate([rr, lr[sl]])
+            g = gm.grid_forward(c, xyz, ch, rad, m.n_channels, b.resolution, b.dimension, b.radius_scaling)
+            pose, aff, loss, dg = cnn_ref.loss_grid_gradient(b, g[None], dtype)
+            ag = gm.grid_backward(c, xyz, ch, rad, dg[0].astype(np.float32), b.resolution, b.dimension, b.radius_scaling)
+            grad[sl] += ag[len(rec_xyz):] / len(models)
+            P.append(pose[0]); A.append(aff[0]); L.append(loss[0])
+        per.append((P, A, L))
+    out = np.zeros((4, n))
+    for i in range(n):
+        out[:, i] = cnn_ref.ensemble([q[0][i] for q in per], [q[1][i] for q in per], [q[2][i] for q in per])
+    return out[0], out[1], out[2], out[3], grad
+
+
 def score_ensemble(models, *args, **kw):
     """-> (score[n], affinity[n], loss[n], variance[n]) with the reference's ensemble arithmetic."""
     per = [m.score(*args, **kw) for m in models]

@@ -69,6 +69,37 @@ def cnn_kat(n_poses=6):
     np.savez_compressed(os.path.join(HERE, "cnn_kat.npz"), **out)
 
 
+def grad_kat(n_poses=2):
+    """Ligand-atom gradients of the reference's own TorchScript model: autograd of CE(module output, label 1) through
+    the .pt (torch_model.cpp:195-199), then the oracle's GridMaker::backward."""
+    from oracle import gridmaker as gm
+    import torch.nn.functional as F
+    k = np.load(os.path.join(HERE, "cnn_kat.npz"))
+    name = "crossdock_default2018"
+    blob = model_blob.load_model(name)
+    om = pipeline.OracleModel(blob)
+    ts = torch.jit.load(os.path.join(REF, "gninasrc/lib/models", name + ".pt"), map_location="cpu").double()
+    offs = k["pose_offsets"][:n_poses + 1]
+    rc, rr = gm.type_atoms(k["rec_types"], om.rec_t2c, 0)
+    lc, lr = gm.type_atoms(k["lig_types"], om.lig_t2c, om.n_rec)
+    grads, losses = [], []
+    for p in range(n_poses):
+        sl = slice(offs[p], offs[p + 1])
+        c = gm.center_of(k["lig_xyz"][sl])
+        xyz = np.concatenate([k["rec_xyz"], k["lig_xyz"][sl]]); ch = np.concatenate([rc, lc[sl]]); rad = np.concatenate([rr, lr[sl]])
+        g = torch.from_numpy(gm.grid_forward(c, xyz, ch, rad, om.n_channels)[None]).double().requires_grad_(True)
+        out, _ = ts(g)
+        loss = F.cross_entropy(out, torch.ones(1, dtype=torch.long))
+        loss.backward()
+        ag = gm.grid_backward(c, xyz, ch, rad, g.grad[0].numpy().astype(np.float32))
+        grads.append(ag[len(k["rec_xyz"]):]); losses.append(float(loss))
+    np.savez_compressed(os.path.join(HERE, "grad_kat.npz"), lig_grad=np.concatenate(grads), loss=np.array(losses),
+                        n_poses=n_poses, model=np.array(name))
+    print("grad kat: |g|max", np.abs(np.concatenate(grads)).max(), "loss", losses)
+
+
 if __name__ == "__main__":
-    sparse_golden()
-    cnn_kat()
+    if "--grad-only" not in sys.argv:
+        sparse_golden()
+        cnn_kat()
+    grad_kat()
