@@ -11,7 +11,8 @@ SYMBOLS = ["gb_last_error", "gb_version", "gb_initialize_cuda", "gb_device_count
            "gb_model_get_info", "gb_model_release", "gb_model_type_atoms", "gb_cnn_create", "gb_cnn_clone",
            "gb_cnn_destroy", "gb_cnn_num_models", "gb_cnn_set_option", "gb_cnn_get_option", "gb_cnn_set_receptor",
            "gb_cnn_score_batch", "gb_cnn_score_batch_models", "gb_cnn_score_grad", "gb_cnn_stage_poses", "gb_cnn_run_staged",
-           "gb_cnn_fetch", "gb_cnn_profile_read", "gb_cnn_profile_reset", "gb_cnn_debug_read", "gb_cnn_stream", "gb_cnn_kernel_launches", "gb_cnn_voxelize"]
+           "gb_cnn_fetch", "gb_cnn_profile_read", "gb_cnn_profile_reset", "gb_cnn_debug_read", "gb_cnn_stream", "gb_cnn_kernel_launches", "gb_cnn_voxelize", "gb_vina_create", "gb_vina_destroy", "gb_vina_table_size", "gb_vina_prec_table",
+           "gb_vina_set_receptor", "gb_vina_cache_build", "gb_vina_cache_read", "gb_vina_cache_eval", "gb_vina_score_exact"]
 
 
 class GbError(RuntimeError):
@@ -68,6 +69,16 @@ def lib():
     L.gb_cnn_kernel_launches.argtypes = [vp]
     L.gb_cnn_kernel_launches.restype = C.c_int64
     L.gb_cnn_voxelize.argtypes = [vp, C.c_int, fp, ip, ip, C.c_int, fp, fp]
+    L.gb_vina_create.argtypes = [C.c_int, fp, C.c_float, C.POINTER(vp)]
+    L.gb_vina_destroy.argtypes = [vp]
+    L.gb_vina_destroy.restype = None
+    L.gb_vina_table_size.argtypes = [vp]
+    L.gb_vina_prec_table.argtypes = [vp, C.c_int, C.c_int, fp, fp, fp]
+    L.gb_vina_set_receptor.argtypes = [vp, fp, ip, C.c_int]
+    L.gb_vina_cache_build.argtypes = [vp, fp, fp, ip, ip, C.c_int]
+    L.gb_vina_cache_read.argtypes = [vp, C.c_int, fp]
+    L.gb_vina_cache_eval.argtypes = [vp, fp, ip, ip, C.c_int, C.c_float, C.c_float, fp, fp]
+    L.gb_vina_score_exact.argtypes = [vp, fp, ip, ip, C.c_int, fp, C.c_float, fp, fp]
     _lib = L
     return L
 

@@ -1,0 +1,73 @@
+"""Host-side mirror of the smina/Vina scoring entry points over the C ABI (include/gnina_b200.h, gb_vina_*):
+`precalculate_linear` tables, `cache::populate`, `cache::eval/eval_deriv`, exact final scoring ("Affinity")."""
+import ctypes as C
+import numpy as np
+from . import capi
+
+
+def _fp(a): return a.ctypes.data_as(C.POINTER(C.c_float)) if a is not None else None
+def _ip(a): return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class VinaScorer:
+    def __init__(self, device=0, weights6=None, factor=32.0):
+        L = capi.lib()
+        self._h = C.c_void_p()
+        w = None if weights6 is None else np.ascontiguousarray(weights6, np.float32)
+        capi.check(L.gb_vina_create(device, _fp(w), factor, C.byref(self._h)))
+        self.n = L.gb_vina_table_size(self._h)
+        self.dims = None
+
+    def table(self, t1, t2):
+        a, b, c = (np.empty(self.n, np.float32) for _ in range(3))
+        capi.check(capi.lib().gb_vina_prec_table(self._h, t1, t2, _fp(a), _fp(b), _fp(c)))
+        return a, b, c
+
+    def set_receptor(self, xyz, smina_types):
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        t = np.ascontiguousarray(smina_types, np.int32)
+        capi.check(capi.lib().gb_vina_set_receptor(self._h, _fp(xyz), _ip(t), len(t)))
+
+    def cache_build(self, begin, end, n, types_needed):
+        b, e = np.ascontiguousarray(begin, np.float32), np.ascontiguousarray(end, np.float32)
+        n = np.ascontiguousarray(n, np.int32)
+        tn = np.ascontiguousarray(types_needed, np.int32)
+        capi.check(capi.lib().gb_vina_cache_build(self._h, _fp(b), _fp(e), _ip(n), _ip(tn), len(tn)))
+        self.dims = (int(n[2]) + 1, int(n[1]) + 1, int(n[0]) + 1)
+
+    def cache_grid(self, t):
+        out = np.empty(self.dims, np.float32)
+        capi.check(capi.lib().gb_vina_cache_read(self._h, t, _fp(out)))
+        return out
+
+    @staticmethod
+    def _poses(lig_xyz, lig_types, pose_offsets):
+        return (np.ascontiguousarray(lig_xyz, np.float32).reshape(-1, 3), np.ascontiguousarray(lig_types, np.int32),
+                np.ascontiguousarray(pose_offsets, np.int32))
+
+    def cache_eval(self, lig_xyz, lig_types, pose_offsets, slope=1e3, v=1000.0, deriv=True):
+        x, t, o = self._poses(lig_xyz, lig_types, pose_offsets)
+        e = np.empty(len(o) - 1, np.float32)
+        d = np.zeros((len(t), 3), np.float32) if deriv else None
+        capi.check(capi.lib().gb_vina_cache_eval(self._h, _fp(x), _ip(t), _ip(o), len(o) - 1, slope, v, _fp(e), _fp(d)))
+        return e, d
+
+    def score_exact(self, lig_xyz, lig_types, pose_offsets, num_tors=None, v=1000.0):
+        """-> (intermolecular exact energy, Affinity) per pose"""
+        x, t, o = self._poses(lig_xyz, lig_types, pose_offsets)
+        n = len(o) - 1
+        nt = None if num_tors is None else np.ascontiguousarray(num_tors, np.float32)
+        e, a = np.empty(n, np.float32), np.empty(n, np.float32)
+        capi.check(capi.lib().gb_vina_score_exact(self._h, _fp(x), _ip(t), _ip(o), n, _fp(nt), v, _fp(e), _fp(a)))
+        return e, a
+
+    def close(self):
+        if self._h:
+            capi.lib().gb_vina_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

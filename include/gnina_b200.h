@@ -137,6 +137,40 @@ int gb_cnn_debug_read(gb_cnn* h, const char* name, void* out, size_t cap_bytes, 
 int gb_cnn_voxelize(gb_cnn* h, int model_index, const float* lig_xyz, const int32_t* lig_type,
                     const int32_t* pose_offsets, int n_poses, const float* centers, float* grid_out);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * smina / Vina empirical scoring (the rows of the hot path that sit next to the CNN in gnina's rescoring loop).
+ * Default term set and weights (main/main.cpp:1324-1329): gauss(o=0,w=0.5), gauss(o=3,w=2), repulsion,
+ * hydrophobic(0.5,1.5), non_dir_h_bond(-0.7,0), num_tors_div; cutoff 8 A.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct gb_vina gb_vina;
+
+/* precalculate_linear(sf, factor) ctor (lib/precalculate.h:176-208; factor = 32 for docking, main/main.cpp:904-905):
+ * tabulates every smina type pair.  weights6 = the 5 term weights + the num_tors_div weight, or NULL for the defaults. */
+int gb_vina_create(int device, const float* weights6, float factor, gb_vina** out);
+void gb_vina_destroy(gb_vina* h);
+/* samples per pair (n = sz(factor * cutoff^2) + 3 = 2051) and one pair's tables: fast[i] (eval_fast, :90-95) and the
+ * (e, dor) pairs eval_deriv interpolates (:97-133).  Host-side, for parity tests (V2). */
+int gb_vina_table_size(const gb_vina* h);
+int gb_vina_prec_table(const gb_vina* h, int t1, int t2, float* fast, float* smooth_e, float* smooth_dor);
+/* model::grid_atoms: the rigid receptor atoms; hydrogens are dropped like the reference does. */
+int gb_vina_set_receptor(gb_vina* h, const float* xyz, const int32_t* smina_type, int n);
+/* cache::populate (lib/cache.cpp:104-184) on the device: one affinity grid of (n[0]+1)x(n[1]+1)x(n[2]+1) points per
+ * needed ligand atom type over the box [begin, end] (grid_dims), x fastest like array3d. */
+int gb_vina_cache_build(gb_vina* h, const float* begin, const float* end, const int32_t* n, const int32_t* types_needed,
+                        int n_types);
+int gb_vina_cache_read(gb_vina* h, int type, float* out); /* parity access to one grid */
+/* cache::eval / cache::eval_deriv (lib/cache.cpp:50-83 -> grid::evaluate_aux, lib/grid.cpp:96-186) for a batch of
+ * poses: trilinear interpolation, curl with cap v, out-of-box penalty slope*miss.  energy[n_poses]; deriv (nullable)
+ * [n_atoms][3] = what the reference stores in m.minus_forces. */
+int gb_vina_cache_eval(gb_vina* h, const float* lig_xyz, const int32_t* lig_type, const int32_t* pose_offsets, int n_poses,
+                       float slope, float v, float* energy, float* deriv);
+/* Final scoring of rigid poses: naive_non_cache::eval with precalculate_exact (lib/naive_non_cache.cpp:29-57), i.e.
+ * the intermolecular part of model::eval_adjusted (the intramolecular terms cancel, lib/model.cu:401-406), then
+ * num_tors_div (lib/everything.h:795-809) -> the "Affinity (kcal/mol)" column.  num_tors per pose as
+ * conf_independent_inputs computes it (lib/terms.cpp:74-106); e_inter / affinity: n_poses floats (nullable). */
+int gb_vina_score_exact(gb_vina* h, const float* lig_xyz, const int32_t* lig_type, const int32_t* pose_offsets, int n_poses,
+                        const float* num_tors, float v, float* e_inter, float* affinity);
+
 #ifdef __cplusplus
 }
 #endif
