@@ -461,7 +461,7 @@ int gb_cnn_stage_poses(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type,
 
 static int chunk_size(const gb_cnn* h) {
   if (h->max_batch > 0) return h->max_batch;
-  return h->precision == GB_PRECISION_FP32 ? 16 : 1024;
+  return h->precision == GB_PRECISION_FP32 ? 16 : 2048;
 }
 
 // voxelise poses [p0, p0+nb) of group G into the fp32 reference layout
@@ -521,9 +521,14 @@ int gb_cnn_run_staged(gb_cnn* h) {
         // aux stream: wait until the network has finished reading this buffer two chunks ago, then voxelise into it
         cudaStream_t vs = h->overlap ? h->aux : h->stream;
         if (gw.consumed_valid[buf]) GB_CUDA(cudaStreamWaitEvent(vs, gw.consumed[buf], 0));
+        // overlap: the voxeliser of this chunk becomes runnable only once the network of the previous chunk has
+        // been handed to the GPU, so the (earlier-launched) conv CTAs keep their 2 slots per SM and voxeliser CTAs
+        // fill the shared memory / thread slots that are left
+        if (h->overlap && gw.started_valid) GB_CUDA(cudaStreamWaitEvent(vs, gw.started[buf ^ 1], 0));
         h->launches += tc_prepare_grid(pb, gw, buf, vs, &h->prof);
         GB_CUDA(cudaEventRecord(gw.ready[buf], vs));
         GB_CUDA(cudaStreamWaitEvent(h->stream, gw.ready[buf], 0));
+        if (h->overlap) { GB_CUDA(cudaEventRecord(gw.started[buf], h->stream)); gw.started_valid = true; }
         for (size_t k = 0; k < G.model_idx.size(); k++) {
           const int mi = G.model_idx[k];
           const Model& Mo = *h->models[mi];

@@ -158,6 +158,8 @@ TcGridWorkspace::~TcGridWorkspace() {
     if (e) cudaEventDestroy(e);
   for (auto e : consumed)
     if (e) cudaEventDestroy(e);
+  for (auto e : started)
+    if (e) cudaEventDestroy(e);
   if (list_xyzr) cudaFree(list_xyzr);
   if (list_ch) cudaFree(list_ch);
   if (list_n) cudaFree(list_n);
@@ -348,6 +350,7 @@ struct ConvTcParams {
   const float* bias;  // [Cout]
   __half* out;        // [pose][D][D][D][Cout]
   int D, P, G, T, NB, Lp, Cout, n_poses, relu, n_groups;
+  int dbg;  // experiment switches (GB_TC_DBG): 1 = no global stores, 2 = no slab loads, 4 = no MMAs
 };
 
 constexpr int kTcSlots = 8;       // TMEM ring: 8 plane slots x 32 fp32 columns = 256 columns
@@ -364,6 +367,13 @@ struct ConvTcSmem {
   static constexpr int kBarOff = kWBytes + kStages * kStageBytes;
   static constexpr int kTotal = kBarOff + 512;
 };
+
+// Per-MMA start-address offsets (16-byte units) of the A slab and the B weight block, one table per kernel
+// configuration, in constant memory: the issue loop reads them with uniform loads (ULDC) straight into the uniform
+// registers UTCHMMA consumes — no per-thread arithmetic, no uniform-register spills.
+struct MmaOff { uint32_t a, b; };
+__constant__ MmaOff c_mma_off[3][36];
+template <int CIN, int DD> struct ConvCfg { static constexpr int id = (CIN == 32 && DD == 24) ? 0 : (CIN == 32 && DD == 12) ? 1 : 2; };
 
 template <int CIN, int DD>
 __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
@@ -426,11 +436,15 @@ __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
           const uint32_t st = gp % S::kStages, ph = (gp / S::kStages) & 1;
           ptx::mbar_wait(&empty[st], ph ^ 1);
           if (ptx::elect_one()) {
-            ptx::mbar_expect_tx(&full[st], (uint32_t)C8 * slab_row);
-            uint8_t* dst = s_stage + (size_t)st * S::kStageBytes;
+            if (p.dbg & 2) {
+              ptx::mbar_arrive(&full[st]);
+            } else {
+              ptx::mbar_expect_tx(&full[st], (uint32_t)C8 * slab_row);
+              uint8_t* dst = s_stage + (size_t)st * S::kStageBytes;
 #pragma unroll
-            for (int c8 = 0; c8 < C8; c8++)
-              ptx::bulk_g2s(dst + (size_t)c8 * slab_row, xg + ((size_t)it * C8 + c8) * p.Lp, slab_row, &full[st]);
+              for (int c8 = 0; c8 < C8; c8++)
+                ptx::bulk_g2s(dst + (size_t)c8 * slab_row, xg + ((size_t)it * C8 + c8) * p.Lp, slab_row, &full[st]);
+            }
           }
           __syncwarp();
         }
@@ -477,6 +491,7 @@ __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
           ptx::tc_fence_after();
           const uint32_t a_lo_base = a_lo_fixed | (ptx::smem_u32(s_stage + (size_t)st * S::kStageBytes) >> 4);
           if (ptx::elect_one()) {
+            if (!(p.dbg & 4)) {
             // very first MMA of the plane: fresh output planes are overwritten (accumulate = 0): one N=32 MMA per plane
             for (int xo = lo; xo <= hi; xo++) {
               const uint32_t tm = tmem_base + ((go_base + xo - 1) % R) * 32u;
@@ -485,30 +500,26 @@ __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
               if (xo >= fresh_lo) ptx::mma_f16_ss_lohi<0>(tm, a_lo_base + a0, kDescHi, bl, kDescHi, ptx::idesc_f16(128, 32));
               else ptx::mma_f16_ss_lohi<1>(tm, a_lo_base + a0, kDescHi, bl, kDescHi, ptx::idesc_f16(128, 32));
             }
+            constexpr int kCfg = ConvCfg<CIN, DD>::id;
+            constexpr int kNumMma = 9 * (CIN / 16);
             if (nr == 1) {
               const uint32_t tm0 = r_tm[0], id0 = r_idesc[0], bl0 = b_lo_base + r_boff[0];
-#pragma unroll
-              for (int t9 = 0; t9 < 9; t9++) {
-#pragma unroll
-                for (int ks = 0; ks < CIN / 16; ks++) {
-                  if (t9 == 0 && ks == 0) continue;
-                  constexpr int dummy = 0; (void)dummy;
-                  const uint32_t aoff = (uint32_t)((P + 1) + (t9 / 3 - 1) * P + (t9 % 3 - 1) + 2 * ks * SL);
-                  const uint32_t boff = (uint32_t)((t9 * C8 + 2 * ks) * 96);
-                  ptx::mma_f16_ss_lohi<1>(tm0, a_lo_base + aoff, kDescHi, bl0 + boff, kDescHi, id0);
-                }
+#pragma unroll 1
+              for (int m = 1; m < kNumMma; m++) {
+                const MmaOff o = c_mma_off[kCfg][m];
+                ptx::mma_f16_ss_lohi<1>(tm0, a_lo_base + o.a, kDescHi, bl0 + o.b, kDescHi, id0);
               }
             } else {
-              // TMEM ring wrap inside the window (2 planes in 8): two MMAs per tap, generic loop
-              for (int t9 = 0; t9 < 9; t9++) {
-                for (int ks = 0; ks < CIN / 16; ks++) {
-                  if (t9 == 0 && ks == 0) continue;
-                  const uint32_t aoff = (uint32_t)((P + 1) + (t9 / 3 - 1) * P + (t9 % 3 - 1) + 2 * ks * SL);
-                  const uint32_t boff = (uint32_t)((t9 * C8 + 2 * ks) * 96);
-                  ptx::mma_f16_ss_lohi<1>(r_tm[0], a_lo_base + aoff, kDescHi, b_lo_base + r_boff[0] + boff, kDescHi, r_idesc[0]);
-                  ptx::mma_f16_ss_lohi<1>(r_tm[1], a_lo_base + aoff, kDescHi, b_lo_base + r_boff[1] + boff, kDescHi, r_idesc[1]);
-                }
+              // TMEM ring wrap inside the window (2 planes in 8): two MMAs per tap
+              const uint32_t tm0 = r_tm[0], id0 = r_idesc[0], bl0 = b_lo_base + r_boff[0];
+              const uint32_t tm1 = r_tm[1], id1 = r_idesc[1], bl1 = b_lo_base + r_boff[1];
+#pragma unroll 1
+              for (int m = 1; m < kNumMma; m++) {
+                const MmaOff o = c_mma_off[kCfg][m];
+                ptx::mma_f16_ss_lohi<1>(tm0, a_lo_base + o.a, kDescHi, bl0 + o.b, kDescHi, id0);
+                ptx::mma_f16_ss_lohi<1>(tm1, a_lo_base + o.a, kDescHi, bl1 + o.b, kDescHi, id1);
               }
+            }
             }
             ptx::tc_commit(&empty[st]);                                    // slab consumed
             if (xi >= 2) ptx::tc_commit(&accf[(go_base + xi - 2) % R]);     // output plane xi-1 is complete
@@ -541,7 +552,7 @@ __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&acce[slot]);
-        if (valid) {
+        if (valid && !(p.dbg & 1)) {
           uint4 o[4];
           uint32_t* ow = reinterpret_cast<uint32_t*>(o);
 #pragma unroll
@@ -600,18 +611,18 @@ __global__ void __launch_bounds__(256) pointwise_pool_rows_kernel(const __half* 
 #pragma unroll
   for (int nt = 0; nt < NT; nt++) { bs[nt][0] = bias[nt * 8 + 2 * t]; bs[nt][1] = bias[nt * 8 + 2 * t + 1]; }
 
-  const long long n_pairs = (long long)n_poses * Dn * Dn * Dn / 2;
-  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int n_pairs = n_poses * Dn * Dn * Dn / 2;  // < 2^31 for any chunk the handle allows
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int n_warps = gridDim.x * (blockDim.x >> 5);
   const int di = (g >> 2) & 1, dj = (g >> 1) & 1, dk = g & 1;
-  for (long long pair = warp_global; pair < n_pairs; pair += n_warps) {
+  for (int pair = warp_global; pair < n_pairs; pair += n_warps) {
     // pooled voxels 2*pair (rows 0-7) and 2*pair+1 (rows 8-15); Dn is even so both share pose, x, y
-    const long long pvA = 2 * pair;
-    const int z0 = (int)(pvA % Dn);
-    long long r = pvA / Dn;
-    const int y0 = (int)(r % Dn); r /= Dn;
-    const int x0 = (int)(r % Dn);
-    const int pose = (int)(r / Dn);
+    const int pvA = 2 * pair;
+    const int z0 = pvA % Dn;
+    int r = pvA / Dn;
+    const int y0 = r % Dn; r /= Dn;
+    const int x0 = r % Dn;
+    const int pose = r / Dn;
     const __half* rowA = yin + ((((size_t)pose * D + (2 * x0 + di)) * D + (2 * y0 + dj)) * D + (2 * z0 + dk)) * C;
     const __half* rowB = rowA + (size_t)2 * C;  // next pooled voxel in z: fine z + 2
     float acc[NT][4];
@@ -764,10 +775,25 @@ static void launch_conv_tc(const ConvTc& c, const ActLayout& L, const uint4* xin
     attr_set = true;
   }
   GB_CHECK(c.cin == CIN && L.D == DD, "conv shape");
+  static bool table_set = false;
+  if (!table_set) {
+    MmaOff h[36] = {};
+    const int P = DD + 2, SL = 128 + 2 * (P + 1), C8 = CIN / 8;
+    int m = 0;
+    for (int t9 = 0; t9 < 9; t9++)
+      for (int ks = 0; ks < CIN / 16; ks++, m++) {
+        h[m].a = (uint32_t)((P + 1) + (t9 / 3 - 1) * P + (t9 % 3 - 1) + 2 * ks * SL);
+        h[m].b = (uint32_t)((t9 * C8 + 2 * ks) * 96);
+      }
+    GB_CUDA(cudaMemcpyToSymbol(c_mma_off, h, sizeof(h), sizeof(MmaOff) * 36 * ConvCfg<CIN, DD>::id));
+    table_set = true;
+  }
   ConvTcParams p;
   p.xin = xin; p.wp = c.wp; p.bias = c.bias; p.out = out;
   p.D = L.D; p.P = L.P; p.G = L.G; p.T = L.T; p.NB = c.cout / 32; p.Lp = L.Lp; p.Cout = c.cout; p.n_poses = n_poses;
   p.relu = 1;
+  static const int dbg = getenv("GB_TC_DBG") ? atoi(getenv("GB_TC_DBG")) : 0;
+  p.dbg = dbg;
   p.n_groups = (n_poses + L.G - 1) / L.G;
   const int n_items = p.n_groups * L.T * p.NB;
   static int ctas_per_sm = 0, n_sm = 0;
@@ -833,6 +859,7 @@ int tc_prepare_grid(const TcPoseBatch& pb, TcGridWorkspace& gw, int buf, cudaStr
   for (int i = 0; i < 2; i++) {
     if (!gw.ready[i]) GB_CUDA(cudaEventCreateWithFlags(&gw.ready[i], cudaEventDisableTiming));
     if (!gw.consumed[i]) GB_CUDA(cudaEventCreateWithFlags(&gw.consumed[i], cudaEventDisableTiming));
+    if (!gw.started[i]) GB_CUDA(cudaEventCreateWithFlags(&gw.started[i], cudaEventDisableTiming));
   }
   {
     ProfScope ps(prof, "tc_build_pose_lists", s);

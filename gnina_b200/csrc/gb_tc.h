@@ -17,7 +17,8 @@ struct TcPoseBatch {
 struct TcGridWorkspace {
   void* x0[2] = {nullptr, nullptr};
   size_t cap[2] = {0, 0};
-  cudaEvent_t ready[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+  cudaEvent_t ready[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr}, started[2] = {nullptr, nullptr};
+  bool started_valid = false;
   bool consumed_valid[2] = {false, false};
   unsigned iter = 0;
   float4* list_xyzr = nullptr; int* list_ch = nullptr; int* list_n = nullptr; size_t list_cap = 0, listn_cap = 0;
