@@ -1,0 +1,202 @@
+// gnina_b200.hpp — C++ host side above the C ABI (header-only, C++17, no dependencies beyond gnina_b200.h).
+//
+// gnina's host code is C++; this header is the host-language mirror of the reference's scorer interface for the
+// accelerated path, written so that the adapter sketched in INTEGRATION.md is a few lines:
+//   gb::CNNScorer   <-> CNNTorchScorer<isCUDA>  (gninasrc/lib/cnn_torch_scorer.{h,cpp}) / DLScorer (lib/dl_scorer.h:23-66)
+//   gb::NonCacheCNN <-> non_cache_cnn::eval / eval_deriv   (gninasrc/lib/non_cache_cnn.cpp:33-54,79-169), default
+//                       options (no empirical mixing, no user grid): CNN loss + out-of-box penalties of the search box
+//                       and of the CNN box (non_cache::check_bounds(_deriv), lib/non_cache.cpp:32-50,102-123)
+//   gb::VinaScorer  <-> precalculate_linear + cache + naive_non_cache final scoring (see gnina_b200.h)
+// Errors: GB_ERR_USAGE -> gb::usage_error (reference: usage_error), everything else -> gb::internal_error.
+#pragma once
+#include <array>
+#include <cmath>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "gnina_b200.h"
+
+namespace gb {
+
+struct usage_error : std::runtime_error { using std::runtime_error::runtime_error; };
+struct internal_error : std::runtime_error { using std::runtime_error::runtime_error; };
+inline void check(int rc) {
+  if (rc == GB_OK) return;
+  if (rc == GB_ERR_USAGE) throw usage_error(gb_last_error());
+  throw internal_error(gb_last_error());
+}
+
+// cnn_torch_scorer.cpp:28-62: default ensemble, "fast", "default1.0"; "X_ensemble" needs the list of built-in names
+inline std::vector<std::string> expand_model_names(std::vector<std::string> names,
+                                                   const std::vector<std::string>& builtin = {}) {
+  for (auto& n : names)
+    if (n != "default1.0")
+      for (auto& c : n)
+        if (c == '.') c = '_';  // make_model_cpp.py:31-32
+  if (names.empty()) names = {"dense_1_3", "dense_1_3_PT_KD_3", "crossdock_default2018_KD_4"};
+  else if (names.size() == 1) {
+    if (names[0] == "fast") names = {"all_default_to_default_1_3_1"};
+    else if (names[0] == "default1.0")
+      names = {"dense", "general_default2018_3", "dense_3", "crossdock_default2018", "redock_default2018_2"};
+  }
+  std::vector<std::string> out;
+  const std::string suffix = "_ensemble";
+  for (const auto& n : names) {
+    if (n.size() > suffix.size() && n.compare(n.size() - suffix.size(), suffix.size(), suffix) == 0) {
+      const std::string prefix = n.substr(0, n.size() - suffix.size());
+      for (const auto& b : builtin)
+        if (b.compare(0, prefix.size(), prefix) == 0) out.push_back(b);
+    } else out.push_back(n);
+  }
+  return out;
+}
+
+struct Scores { std::vector<float> score, affinity, loss, variance; };
+
+class CNNScorer {
+  gb_cnn* h_ = nullptr;
+  std::vector<gb_model*> models_;
+  int device_ = 0;
+  CNNScorer() = default;
+
+ public:
+  // weights_dir holds the GNB200W1 blobs (gnina_b200/weights); names as gnina spells them
+  CNNScorer(const std::string& weights_dir, const std::vector<std::string>& names, int device = 0) : device_(device) {
+    if (gb_initialize_cuda(device) != 0) throw internal_error("no usable CUDA device (gnina_b200 has no CPU fallback)");
+    for (const auto& n : expand_model_names(names)) {
+      gb_model* m = nullptr;
+      const int rc = gb_model_load((weights_dir + "/" + n + ".gbw").c_str(), device, &m);
+      if (rc == GB_ERR_USAGE) throw usage_error("Invalid model name: " + n);  // cnn_torch_scorer.cpp:70-72
+      check(rc);
+      models_.push_back(m);
+    }
+    check(gb_cnn_create(models_.data(), (int)models_.size(), device, &h_));
+  }
+  CNNScorer(const CNNScorer&) = delete;
+  CNNScorer& operator=(const CNNScorer&) = delete;
+  ~CNNScorer() {
+    if (h_) gb_cnn_destroy(h_);
+    for (auto m : models_) gb_model_release(m);
+  }
+
+  bool initialized() const { return h_ && gb_cnn_num_models(h_) > 0; }
+  bool has_affinity() const { return true; }
+  std::unique_ptr<CNNScorer> fresh_copy() const {  // cnn_torch_scorer.h:54
+    std::unique_ptr<CNNScorer> c(new CNNScorer);
+    c->device_ = device_;
+    check(gb_cnn_clone(h_, &c->h_));
+    return c;
+  }
+  void set_option(const char* key, double v) { check(gb_cnn_set_option(h_, key, v)); }
+  gb_model_info info(int i = 0) const { gb_model_info x; check(gb_model_get_info(models_.at(i), &x)); return x; }
+  void set_receptor(const float* xyz, const int32_t* smina_type, int n) { check(gb_cnn_set_receptor(h_, xyz, smina_type, n)); }
+
+  Scores score_batch(const float* lig_xyz, const int32_t* lig_type, const int32_t* pose_offsets, int n_poses,
+                     const float* centers = nullptr) {
+    Scores s;
+    s.score.resize(n_poses); s.affinity.resize(n_poses); s.loss.resize(n_poses); s.variance.resize(n_poses);
+    check(gb_cnn_score_batch(h_, lig_xyz, lig_type, pose_offsets, n_poses, centers, s.score.data(), s.affinity.data(),
+                             s.loss.data(), s.variance.data()));
+    return s;
+  }
+  // DLScorer::score(model&, compute_gradient, affinity, loss, variance): one pose; gradient (if requested) is the
+  // derivative of the loss w.r.t. every ligand atom passed = what the reference adds to m.minus_forces
+  float score(const float* lig_xyz, const int32_t* lig_type, int n_atoms, bool compute_gradient, float& affinity,
+              float& loss, float& variance, std::vector<float>* gradient = nullptr, const float* center = nullptr) {
+    if (!initialized()) return -1.0f;  // cnn_torch_scorer.cpp:107-108
+    const int32_t offs[2] = {0, n_atoms};
+    float s = 0;
+    if (compute_gradient) {
+      std::vector<float> g(3 * (size_t)n_atoms);
+      check(gb_cnn_score_grad(h_, lig_xyz, lig_type, offs, 1, center, &s, &affinity, &loss, &variance, g.data(), nullptr));
+      if (gradient) *gradient = std::move(g);
+    } else {
+      check(gb_cnn_score_batch(h_, lig_xyz, lig_type, offs, 1, center, &s, &affinity, &loss, &variance));
+    }
+    return s;
+  }
+};
+
+// grid_dim (lib/grid_dim.h:30-43) for the two out-of-box penalties
+struct GridDim { float begin = 0, end = 0; int n = 0; };
+using GridDims = std::array<GridDim, 3>;
+
+class NonCacheCNN {
+  CNNScorer& scorer_;
+  GridDims gd_, cnn_gd_;
+  float slope_;
+
+  static bool is_hydrogen(int32_t t) { return t == 0 || t == 1; }
+  // non_cache::check_bounds_deriv, lib/non_cache.cpp:102-123
+  float check_bounds(const GridDims& dims, const float* a, float* deriv) const {
+    float pen = 0;
+    for (int j = 0; j < 3; j++) {
+      if (dims[j].n > 0) {
+        if (a[j] < dims[j].begin) { if (deriv) deriv[j] += -1 * slope_; pen += std::fabs(a[j] - dims[j].begin); }
+        else if (a[j] > dims[j].end) { if (deriv) deriv[j] += 1 * slope_; pen += std::fabs(a[j] - dims[j].end); }
+      }
+    }
+    return pen * slope_;
+  }
+
+ public:
+  // search box gd; the CNN box is centred on `cnn_center` with the model's dimension (set_bounding_box,
+  // cnn_torch_scorer.cpp:229-241)
+  NonCacheCNN(CNNScorer& s, const GridDims& gd, const float cnn_center[3], float slope) : scorer_(s), gd_(gd), slope_(slope) {
+    const gb_model_info inf = s.info(0);
+    for (int i = 0; i < 3; i++) {
+      cnn_gd_[i].begin = cnn_center[i] - inf.dimension / 2.0f;
+      cnn_gd_[i].end = cnn_center[i] + inf.dimension / 2.0f;
+      cnn_gd_[i].n = (int)(inf.dimension / inf.resolution);
+    }
+  }
+  // eval: loss + penalties ; eval_deriv additionally fills minus_forces[n_atoms][3] (zero for hydrogens)
+  float eval(const float* lig_xyz, const int32_t* lig_type, int n, std::vector<float>* minus_forces = nullptr) {
+    float e = 0, aff = 0, loss = 0, var = 0;
+    std::vector<float> grad;
+    scorer_.score(lig_xyz, lig_type, n, minus_forces != nullptr, aff, loss, var, minus_forces ? &grad : nullptr);
+    e += loss;
+    if (minus_forces) minus_forces->assign(3 * (size_t)n, 0.f);
+    for (int i = 0; i < n; i++) {
+      if (lig_type[i] < 0 || lig_type[i] >= 28 || is_hydrogen(lig_type[i])) continue;
+      float d[3] = {0, 0, 0};
+      float pen = check_bounds(gd_, lig_xyz + 3 * i, minus_forces ? d : nullptr);
+      pen += check_bounds(cnn_gd_, lig_xyz + 3 * i, minus_forces ? d : nullptr);
+      e += pen;
+      if (minus_forces)
+        for (int k = 0; k < 3; k++) (*minus_forces)[3 * i + k] = grad[3 * i + k] + d[k];
+    }
+    return e;
+  }
+};
+
+class VinaScorer {
+  gb_vina* h_ = nullptr;
+
+ public:
+  explicit VinaScorer(int device = 0, const float* weights6 = nullptr, float factor = 32.f) {
+    check(gb_vina_create(device, weights6, factor, &h_));
+  }
+  VinaScorer(const VinaScorer&) = delete;
+  ~VinaScorer() { gb_vina_destroy(h_); }
+  void set_receptor(const float* xyz, const int32_t* t, int n) { check(gb_vina_set_receptor(h_, xyz, t, n)); }
+  void cache_build(const float begin[3], const float end[3], const int32_t n[3], const std::vector<int32_t>& types) {
+    check(gb_vina_cache_build(h_, begin, end, n, types.data(), (int)types.size()));
+  }
+  std::vector<float> cache_eval(const float* xyz, const int32_t* t, const int32_t* offs, int n_poses, float slope, float v,
+                                std::vector<float>* deriv = nullptr) {
+    std::vector<float> e(n_poses);
+    if (deriv) deriv->assign(3 * (size_t)offs[n_poses], 0.f);
+    check(gb_vina_cache_eval(h_, xyz, t, offs, n_poses, slope, v, e.data(), deriv ? deriv->data() : nullptr));
+    return e;
+  }
+  std::vector<float> affinity(const float* xyz, const int32_t* t, const int32_t* offs, int n_poses, const float* num_tors,
+                              float v = 1000.f) {
+    std::vector<float> a(n_poses);
+    check(gb_vina_score_exact(h_, xyz, t, offs, n_poses, num_tors, v, nullptr, a.data()));
+    return a;
+  }
+};
+
+}  // namespace gb
