@@ -197,6 +197,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=4096, help="max poses per step for --impl reference")
     ap.add_argument("--ref-step-seconds", type=float, default=6.0, help="target CPU seconds per step (reference arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="", help="model name(s), comma separated; 'default' = gnina's default 3-model ensemble")
     ap.add_argument("--overlap", type=int, default=-1, help="voxeliser/network stream overlap (library option)")
     ap.add_argument("--max-batch", type=int, default=0)
     args = ap.parse_args()
@@ -221,7 +222,8 @@ def main():
     W = max(args.warmup, 3)
 
     rec_xyz, rec_t, lig_xyz, lig_t, offs = make_workload(args.poses, seed=1 + rank)
-    s = CNNScorer([MODEL], device=local)
+    names = [MODEL] if not args.model else ([] if args.model == "default" else args.model.split(","))
+    s = CNNScorer(names, device=local)
     if args.precision >= 0:
         s.set_option("precision", args.precision)
     if args.overlap >= 0:
@@ -300,6 +302,8 @@ def main():
     hbm, tf_burst, tf_sus, which = peaks()
     # dominant kernel: conv1 (67% of the network's FLOPs).  achieved = algorithmic FLOPs / event-measured duration
     conv1_keys = [k for k in prof if ("conv3_28x32" in k or k.startswith("tc_conv1"))]
+    if args.model:
+        conv1_keys = []
     roof = None
     if conv1_keys:
         k = conv1_keys[0]
@@ -316,7 +320,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16" if precision == 1 else "f32", "data": "synthetic",
             "config": {"workload": "CNN rescoring: 1 receptor (3000 atoms), %d synthetic ligand poses per GPU, 48^3x28ch "
-                                   "crossdock_default2018" % args.poses,
+                                   "%s" % (args.poses, ",".join(s.model_names)),
                        "precision": "fp16 tcgen05, fp32 accumulate" if precision == 1 else "fp32 CUDA-core validation path",
                        "l2": "explicit 256 MiB flush between timed steps; per-step intermediates >> L2",
                        "parallelism": "pose-sharded x%d" % world},

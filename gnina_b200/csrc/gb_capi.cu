@@ -525,14 +525,16 @@ int gb_cnn_run_staged(gb_cnn* h) {
         // been handed to the GPU, so the (earlier-launched) conv CTAs keep their 2 slots per SM and voxeliser CTAs
         // fill the shared memory / thread slots that are left
         if (h->overlap && gw.started_valid) GB_CUDA(cudaStreamWaitEvent(vs, gw.started[buf ^ 1], 0));
-        h->launches += tc_prepare_grid(pb, gw, buf, vs, &h->prof);
+        int kinds = 0;
+        for (int mi : G.model_idx) kinds |= 1 << tc_pool_kind(*h->models[mi]);
+        h->launches += tc_prepare_grid(pb, gw, buf, kinds, vs, &h->prof);
         GB_CUDA(cudaEventRecord(gw.ready[buf], vs));
         GB_CUDA(cudaStreamWaitEvent(h->stream, gw.ready[buf], 0));
         if (h->overlap) { GB_CUDA(cudaEventRecord(gw.started[buf], h->stream)); gw.started_valid = true; }
         for (size_t k = 0; k < G.model_idx.size(); k++) {
           const int mi = G.model_idx[k];
           const Model& Mo = *h->models[mi];
-          h->launches += tc_forward(Mo, pb, gw.x0[buf], h->ws_tc, h->d_out3.p, h->stream, &h->prof,
+          h->launches += tc_forward(Mo, pb, gw.x0[tc_pool_kind(Mo)][buf], h->ws_tc, h->d_out3.p, h->stream, &h->prof,
                                     k + 1 == G.model_idx.size() ? gw.consumed[buf] : nullptr);
           launch_head_post(h->d_out3.p, nb, Mo.skip_softmax, Mo.apply_logistic_loss, h->d_pose.p + (size_t)mi * n + p0,
                            h->d_aff.p + (size_t)mi * n + p0, h->d_loss.p + (size_t)mi * n + p0, h->stream);
@@ -615,9 +617,9 @@ int gb_cnn_profile_reset(gb_cnn* h) {
 int gb_cnn_debug_read(gb_cnn* h, const char* name, void* out, size_t cap_bytes, size_t* nbytes) {
   GB_API_BEGIN
   GB_CHECK(h && name && nbytes, "null argument");
-  static const char* const names[] = {"x0", "y3", "x2", "x4", "y5"};
+  static const char* const names[] = {"x0", "y3", "x2", "x4", "y5", "b0", "b1", "b2"};
   int idx = -1;
-  for (int i = 0; i < 5; i++)
+  for (int i = 0; i < 8; i++)
     if (std::string(name) == names[i]) idx = i;
   if (idx < 0) throw Error(GB_ERR_USAGE, "unknown debug buffer");
   size_t bytes = 0;

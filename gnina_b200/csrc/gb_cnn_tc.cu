@@ -37,11 +37,7 @@
 namespace gb {
 
 // ------------------------------------------------------------------------------------------------------------
-struct ActLayout {
-  int D, P, G, T, C8, Lp;
-  size_t group_u4() const { return (size_t)D * C8 * Lp; }  // uint4 per group
-};
-static ActLayout make_layout(int D, int G, int C) {
+ActLayout make_layout(int D, int G, int C) {
   ActLayout L;
   L.D = D; L.P = D + 2; L.G = G; L.C8 = C / 8;
   const int span = (G - 1) * L.P * L.P + (D - 1) * L.P + D;
@@ -51,11 +47,6 @@ static ActLayout make_layout(int D, int G, int C) {
   return L;
 }
 
-struct ConvTc {
-  int cin = 0, cout = 0;     // cin padded to a multiple of 16
-  uint4* wp = nullptr;       // [cout/32][9][cin/8][96] x 16 B
-  float* bias = nullptr;
-};
 struct PointwiseTc {
   int c = 0;
   __half* w = nullptr;       // [co][ci] row-major fp16
@@ -121,7 +112,10 @@ static PointwiseTc prep_pw(TcWeights& tw, const Model& m, const std::string& key
   return p;
 }
 
-bool tc_supported(const Model& m) { return m.arch == GB_ARCH_DEFAULT2018 && m.n_channels == 28 && m.npts == 48; }
+bool tc_supported(const Model& m) {
+  return (m.arch == GB_ARCH_DEFAULT2018 || m.arch == GB_ARCH_DENSE) && m.n_channels == 28 && m.npts == 48;
+}
+int tc_pool_kind(const Model& m) { return m.arch == GB_ARCH_DEFAULT2018 ? 0 : 1; }
 
 static std::shared_ptr<TcWeights> get_tc_weights(const Model& m) {
   Model& mm = const_cast<Model&>(m);
@@ -152,8 +146,9 @@ static std::shared_ptr<TcWeights> get_tc_weights(const Model& m) {
 }
 
 TcGridWorkspace::~TcGridWorkspace() {
-  for (auto p : x0)
-    if (p) cudaFree(p);
+  for (auto& k : x0)
+    for (auto p : k)
+      if (p) cudaFree(p);
   for (auto e : ready)
     if (e) cudaEventDestroy(e);
   for (auto e : consumed)
@@ -228,6 +223,7 @@ __device__ __forceinline__ float density_t(float t) {
 
 constexpr int kVoxChunk = 256;
 
+template <bool kMax>
 __global__ void __launch_bounds__(512) voxelize_pool_f16_kernel(const float4* __restrict__ list_xyzr,
                                                                 const int* __restrict__ list_ch,
                                                                 const int* __restrict__ list_n, int cap,
@@ -267,6 +263,19 @@ __global__ void __launch_bounds__(512) voxelize_pool_f16_kernel(const float4* __
   const int n = list_n[p];
   int cur = -1;
   float acc = 0.f;
+  float am[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // kMax: the 8 sub-voxels are kept apart until the channel is flushed
+  auto flush_value = [&]() -> float {
+    if constexpr (kMax) {
+      float v = fmaxf(fmaxf(fmaxf(am[0], am[1]), fmaxf(am[2], am[3])), fmaxf(fmaxf(am[4], am[5]), fmaxf(am[6], am[7])));
+#pragma unroll
+      for (int q = 0; q < 8; q++) am[q] = 0.f;
+      return v;
+    } else {
+      const float v = acc * 0.125f;
+      acc = 0.f;
+      return v;
+    }
+  };
   for (int base = 0; base < n; base += kVoxChunk) {
     bool keep = false;
     float4 a = make_float4(0, 0, 0, 0);
@@ -305,9 +314,8 @@ __global__ void __launch_bounds__(512) voxelize_pool_f16_kernel(const float4* __
         mask &= mask - 1;
         const int chm = s_ch[mm];
         if (chm != cur) {
-          if (cur >= 0) s_out[cur * 512 + pv] = __float2half(acc * 0.125f);
+          if (cur >= 0) s_out[cur * 512 + pv] = __float2half(flush_value());
           cur = chm;
-          acc = 0.f;
         }
         const float4 b = s_atom[mm];
         const float dx = (cx - b.x) * b.w, dy = (cy - b.y) * b.w, dz = (cz - b.z) * b.w;  // in units of r
@@ -317,14 +325,20 @@ __global__ void __launch_bounds__(512) voxelize_pool_f16_kernel(const float4* __
           const float x0 = dx - h, x1 = dx + h, y0 = dy - h, y1 = dy + h, z0 = dz - h, z1 = dz + h;
           const float sx0 = x0 * x0, sx1 = x1 * x1, sy0 = y0 * y0, sy1 = y1 * y1, sz0 = z0 * z0, sz1 = z1 * z1;
           const float s00 = sx0 + sy0, s01 = sx0 + sy1, s10 = sx1 + sy0, s11 = sx1 + sy1;
-          acc += density_t(s00 + sz0) + density_t(s00 + sz1) + density_t(s01 + sz0) + density_t(s01 + sz1) +
-                 density_t(s10 + sz0) + density_t(s10 + sz1) + density_t(s11 + sz0) + density_t(s11 + sz1);
+          if constexpr (kMax) {
+            am[0] += density_t(s00 + sz0); am[1] += density_t(s00 + sz1); am[2] += density_t(s01 + sz0);
+            am[3] += density_t(s01 + sz1); am[4] += density_t(s10 + sz0); am[5] += density_t(s10 + sz1);
+            am[6] += density_t(s11 + sz0); am[7] += density_t(s11 + sz1);
+          } else {
+            acc += density_t(s00 + sz0) + density_t(s00 + sz1) + density_t(s01 + sz0) + density_t(s01 + sz1) +
+                   density_t(s10 + sz0) + density_t(s10 + sz1) + density_t(s11 + sz0) + density_t(s11 + sz1);
+          }
         }
       }
     }
     __syncthreads();
   }
-  if (cur >= 0) s_out[cur * 512 + pv] = __float2half(acc * 0.125f);
+  if (cur >= 0) s_out[cur * 512 + pv] = __float2half(flush_value());
   __syncthreads();
   // write the pooled tile: 512 pooled voxels x C8 chunks of 16 B, z fastest
   for (int e = threadIdx.x; e < 512 * C8; e += 512) {
@@ -350,6 +364,8 @@ struct ConvTcParams {
   const float* bias;  // [Cout]
   __half* out;        // [pose][D][D][D][Cout]
   int D, P, G, T, NB, Lp, Cout, n_poses, relu, n_groups;
+  int out_mode, out_c8tot, out_c8off, out_lp;  // out_mode 1: write chunk-planar into a block buffer (dense family)
+  uint4* out_planar;
   int dbg;  // experiment switches (GB_TC_DBG): 1 = no global stores, 2 = no slab loads, 4 = no MMAs
 };
 
@@ -552,7 +568,21 @@ __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&acce[slot]);
-        if (valid && !(p.dbg & 1)) {
+        if (valid && p.out_mode == 1) {
+          uint4 o[4];
+          uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+          for (int c = 0; c < 16; c++) {
+            float f0 = fmaxf(__uint_as_float(v[2 * c]) + s_bias[2 * c], 0.f);
+            float f1 = fmaxf(__uint_as_float(v[2 * c + 1]) + s_bias[2 * c + 1], 0.f);
+            const __half2 h = __floats2half2_rn(f0, f1);
+            ow[c] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          // same D, P, G as the input: the flat position index m is also the output position
+          uint4* dst = p.out_planar + (((size_t)g * D + (xo - 1)) * p.out_c8tot + p.out_c8off + nb * 4) * p.out_lp + m;
+#pragma unroll
+          for (int c = 0; c < 4; c++) dst[(size_t)c * p.out_lp] = o[c];
+        } else if (valid && !(p.dbg & 1)) {
           uint4 o[4];
           uint32_t* ow = reinterpret_cast<uint32_t*>(o);
 #pragma unroll
@@ -767,7 +797,8 @@ __global__ void __launch_bounds__(256) fc_heads_f16_kernel(const __half* __restr
 
 // ------------------------------------------------------------------------------------------------------------
 template <int CIN, int DD>
-static void launch_conv_tc(const ConvTc& c, const ActLayout& L, const uint4* xin, __half* out, int n_poses, cudaStream_t s) {
+static void launch_conv_tc(const ConvTc& c, const ActLayout& L, const uint4* xin, __half* out, int n_poses, cudaStream_t s,
+                           uint4* out_planar = nullptr, int out_c8tot = 0, int out_c8off = 0, int out_lp = 0) {
   using S = ConvTcSmem<CIN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -792,6 +823,7 @@ static void launch_conv_tc(const ConvTc& c, const ActLayout& L, const uint4* xin
   p.xin = xin; p.wp = c.wp; p.bias = c.bias; p.out = out;
   p.D = L.D; p.P = L.P; p.G = L.G; p.T = L.T; p.NB = c.cout / 32; p.Lp = L.Lp; p.Cout = c.cout; p.n_poses = n_poses;
   p.relu = 1;
+  p.out_mode = out_planar ? 1 : 0; p.out_planar = out_planar; p.out_c8tot = out_c8tot; p.out_c8off = out_c8off; p.out_lp = out_lp;
   static const int dbg = getenv("GB_TC_DBG") ? atoi(getenv("GB_TC_DBG")) : 0;
   p.dbg = dbg;
   p.n_groups = (n_poses + L.G - 1) / L.G;
@@ -813,7 +845,7 @@ static void launch_conv_tc(const ConvTc& c, const ActLayout& L, const uint4* xin
   conv3_tc_kernel<CIN, DD><<<grid, 192, S::kTotal, s>>>(p);
 }
 
-static size_t act_bytes(const ActLayout& L, int n_poses) {
+size_t act_bytes(const ActLayout& L, int n_poses) {
   const size_t n_groups = (n_poses + L.G - 1) / L.G;
   return (n_groups * L.group_u4() + 256) * sizeof(uint4);
 }
@@ -823,13 +855,18 @@ struct TcDebug {
   size_t bytes[8];
 };
 static thread_local TcDebug t_debug;
+void tc_debug_set(int i, const void* p, size_t bytes) { t_debug.ptr[i] = p; t_debug.bytes[i] = bytes; }
+void launch_conv_tc_32_24_planar(const ConvTc& c, const uint4* xin, uint4* xout, int out_c8tot, int out_c8off, int out_lp,
+                                 int n_poses, cudaStream_t s) {
+  launch_conv_tc<32, 24>(c, make_layout(24, 1, 32), xin, nullptr, n_poses, s, xout, out_c8tot, out_c8off, out_lp);
+}
 const void* tc_debug_buffer(int i, size_t* bytes) {
   if (i < 0 || i >= 8) return nullptr;
   if (bytes) *bytes = t_debug.bytes[i];
   return t_debug.ptr[i];
 }
 
-int tc_prepare_grid(const TcPoseBatch& pb, TcGridWorkspace& gw, int buf, cudaStream_t s, Profiler* prof) {
+int tc_prepare_grid(const TcPoseBatch& pb, TcGridWorkspace& gw, int buf, int kinds_mask, cudaStream_t s, Profiler* prof) {
   const int nb = pb.n_poses;
   const ActLayout L1 = make_layout(24, 1, 32);
   const int cap = std::max(1, pb.n_rec + pb.max_pose_atoms);
@@ -849,12 +886,13 @@ int tc_prepare_grid(const TcPoseBatch& pb, TcGridWorkspace& gw, int buf, cudaStr
     gw.listn_cap = nb;
   }
   const size_t need0 = act_bytes(L1, nb);
-  if (gw.cap[buf] < need0) {
+  for (int kind = 0; kind < 2; kind++) {
+    if (!(kinds_mask & (1 << kind)) || gw.cap[kind][buf] >= need0) continue;
     GB_CUDA(cudaDeviceSynchronize());
-    if (gw.x0[buf]) cudaFree(gw.x0[buf]);
-    GB_CUDA(cudaMalloc(&gw.x0[buf], need0));
-    GB_CUDA(cudaMemset(gw.x0[buf], 0, need0));
-    gw.cap[buf] = need0;
+    if (gw.x0[kind][buf]) cudaFree(gw.x0[kind][buf]);
+    GB_CUDA(cudaMalloc(&gw.x0[kind][buf], need0));
+    GB_CUDA(cudaMemset(gw.x0[kind][buf], 0, need0));
+    gw.cap[kind][buf] = need0;
   }
   for (int i = 0; i < 2; i++) {
     if (!gw.ready[i]) GB_CUDA(cudaEventCreateWithFlags(&gw.ready[i], cudaEventDisableTiming));
@@ -866,18 +904,28 @@ int tc_prepare_grid(const TcPoseBatch& pb, TcGridWorkspace& gw, int buf, cudaStr
     launch_build_pose_lists(pb.rec_xyzr, pb.rec_ch, pb.n_rec, pb.lig_xyzr, pb.lig_ch, pb.lig_off, pb.centers, nb,
                             pb.dimension / 2.f, cap, gw.list_xyzr, gw.list_ch, gw.list_n, s);
   }
-  {
+  int launches = 1;
+  if (kinds_mask & 1) {
     ProfScope ps(prof, "tc_voxelize_pool", s);
-    voxelize_pool_f16_kernel<<<dim3(27, nb), 512, 0, s>>>(gw.list_xyzr, gw.list_ch, gw.list_n, cap, pb.centers,
-                                                          pb.resolution, pb.dimension,
-                                                          reinterpret_cast<uint4*>(gw.x0[buf]), L1.Lp, L1.D, L1.P, L1.C8);
+    voxelize_pool_f16_kernel<false><<<dim3(27, nb), 512, 0, s>>>(gw.list_xyzr, gw.list_ch, gw.list_n, cap, pb.centers,
+                                                                 pb.resolution, pb.dimension,
+                                                                 reinterpret_cast<uint4*>(gw.x0[0][buf]), L1.Lp, L1.D, L1.P, L1.C8);
+    launches++;
   }
-  return 2;
+  if (kinds_mask & 2) {
+    ProfScope ps(prof, "tc_voxelize_maxpool", s);
+    voxelize_pool_f16_kernel<true><<<dim3(27, nb), 512, 0, s>>>(gw.list_xyzr, gw.list_ch, gw.list_n, cap, pb.centers,
+                                                                pb.resolution, pb.dimension,
+                                                                reinterpret_cast<uint4*>(gw.x0[1][buf]), L1.Lp, L1.D, L1.P, L1.C8);
+    launches++;
+  }
+  return launches;
 }
 
 int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspace& ws, float* out3, cudaStream_t s,
                Profiler* prof, cudaEvent_t x0_consumed) {
-  GB_CHECK(tc_supported(m), "tensor-core path supports the default2018 family only (so far)");
+  GB_CHECK(tc_supported(m), "model has no tensor-core path");
+  if (m.arch == GB_ARCH_DENSE) return tc_forward_dense(m, pb, x0v, ws, out3, s, prof, x0_consumed);
   auto tw = get_tc_weights(m);
   int launches = 0;
   const int nb = pb.n_poses;

@@ -57,8 +57,9 @@ struct ConvF32 {
   float* zero_bias = nullptr; // [cin] zeros (bias of the backward-data convolution)
 };
 
-// fp16 tensor-core path weights (see gb_cnn_tc.cu)
+// fp16 tensor-core path weights (see gb_cnn_tc.cu, gb_cnn_tc_dense.cu)
 struct TcWeights;
+struct TcDenseWeights;
 
 struct Model {
   std::atomic<int> refs{1};
@@ -78,6 +79,7 @@ struct Model {
   float* fc_b = nullptr;  // [3]
   int fc_features = 0;
   std::shared_ptr<TcWeights> tc;  // lazily built
+  std::shared_ptr<TcDenseWeights> tc_dense;
   const HostTensor& t(const std::string& n) const;
   ~Model();
 };

@@ -15,8 +15,8 @@ struct TcPoseBatch {
 // Pooled input grids, double buffered so that the (CUDA-core) voxeliser of chunk i+1 can run on an auxiliary
 // stream while the (tensor-core) network of chunk i runs on the main stream; shared by the models of a grid group.
 struct TcGridWorkspace {
-  void* x0[2] = {nullptr, nullptr};
-  size_t cap[2] = {0, 0};
+  void* x0[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [pool kind: 0 avg, 1 max][double buffer]
+  size_t cap[2][2] = {{0, 0}, {0, 0}};
   cudaEvent_t ready[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr}, started[2] = {nullptr, nullptr};
   bool started_valid = false;
   bool consumed_valid[2] = {false, false};
@@ -28,19 +28,43 @@ struct TcGridWorkspace {
 };
 
 struct TcWorkspace {
-  void* buf[4] = {nullptr, nullptr, nullptr, nullptr};
-  size_t cap[4] = {0, 0, 0, 0};
+  void* buf[8] = {};
+  size_t cap[8] = {};
   void ensure(int i, size_t bytes);
   ~TcWorkspace();
 };
 
 bool tc_supported(const Model& m);
-// pose lists + fused voxelise/avg-pool of one chunk into gw.x0[buf] on stream s; returns #launches
-int tc_prepare_grid(const TcPoseBatch& pb, TcGridWorkspace& gw, int buf, cudaStream_t s, Profiler* prof = nullptr);
+// pose lists + fused voxelise/pool of one chunk into gw.x0[kind][buf] for every pool kind in kinds_mask (bit 0 = avg
+// for the default2018 family, bit 1 = max for the dense family) on stream s; returns #launches
+int tc_prepare_grid(const TcPoseBatch& pb, TcGridWorkspace& gw, int buf, int kinds_mask, cudaStream_t s,
+                    Profiler* prof = nullptr);
+int tc_pool_kind(const Model& m);  // 0 avg, 1 max
 // network forward on the pooled grid x0 -> out3 [n_poses][3]; records x0_consumed (if non-null) once x0 has been
 // read for the last time; returns the number of kernel launches
 int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0, TcWorkspace& ws, float* out3, cudaStream_t s,
                Profiler* prof = nullptr, cudaEvent_t x0_consumed = nullptr);
+
+// chunk-planar padded grouped activation layout (see gb_cnn_tc.cu)
+struct ActLayout {
+  int D, P, G, T, C8, Lp;
+  size_t group_u4() const { return (size_t)D * C8 * Lp; }  // uint4 per group
+};
+ActLayout make_layout(int D, int G, int C);
+size_t act_bytes(const ActLayout& L, int n_poses);
+// dense family (gb_cnn_tc_dense.cu)
+struct TcDenseWeights;
+int tc_forward_dense(const Model& m, const TcPoseBatch& pb, const void* x0max, TcWorkspace& ws, float* out3, cudaStream_t s,
+                     Profiler* prof, cudaEvent_t x0_consumed);
+// shared launcher: 3x3x3 conv 32->32 @24^3 writing chunks [c8_off, c8_off+4) of a chunk-planar block buffer
+struct ConvTc {
+  int cin = 0, cout = 0;     // cin padded to a multiple of 16
+  uint4* wp = nullptr;       // [cout/32][9][cin/8][96] x 16 B
+  float* bias = nullptr;
+};
+void launch_conv_tc_32_24_planar(const ConvTc& c, const uint4* xin, uint4* xout, int out_c8tot, int out_c8off, int out_lp,
+                                 int n_poses, cudaStream_t s);
+void tc_debug_set(int i, const void* p, size_t bytes);
 
 // test-only access to the buffers of the most recent tc_forward on this thread: 0 x0, 1 y(3), 2 x2, 3 x4, 4 y5
 const void* tc_debug_buffer(int i, size_t* bytes);

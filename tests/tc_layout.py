@@ -51,3 +51,30 @@ def oracle_intermediates(blob, grid):
         r["x4"] = F.avg_pool3d(y4, 2, 2)
         r["y5"] = F.relu(F.conv3d(r["x4"], w("unit5_conv.weight"), w("unit5_conv.bias"), padding=1))
     return {k: v.numpy() for k, v in r.items()}
+
+
+def oracle_intermediates_dense(blob, grid):
+    """dense graph (oracle/cnn_ref.py) with the block buffers kept, float64: x0 (max-pooled grid), b0 [96ch @24^3],
+    b1 [160 @12^3], b2 [224 @6^3], feat [224]"""
+    w = lambda n: torch.from_numpy(np.array(blob.tensors[n])).double()
+    x = torch.from_numpy(np.asarray(grid)).double()
+
+    def block(x, level):
+        for i in range(4):
+            bn = "dense_block_%d.data_enc_level%d_batchnorm_conv%d." % (level, level, i)
+            cv = "dense_block_%d.data_enc_level%d_conv%d." % (level, level, i)
+            y = F.batch_norm(x, w(bn + "running_mean"), w(bn + "running_var"), w(bn + "weight"), w(bn + "bias"), False, 0.1, 1e-5)
+            x = torch.cat([x, F.relu(F.conv3d(y, w(cv + "weight"), w(cv + "bias"), padding=1))], 1)
+        return x
+
+    r = {}
+    with torch.no_grad():
+        r["x0"] = F.max_pool3d(x, 2, 2)
+        y = F.relu(F.conv3d(r["x0"], w("data_enc_init_conv.weight"), w("data_enc_init_conv.bias"), padding=1))
+        r["b0"] = block(y, 0)
+        y = F.max_pool3d(F.relu(F.conv3d(r["b0"], w("data_enc_level0_bottleneck.weight"), w("data_enc_level0_bottleneck.bias"))), 2, 2)
+        r["b1"] = block(y, 1)
+        y = F.max_pool3d(F.relu(F.conv3d(r["b1"], w("data_enc_level1_bottleneck.weight"), w("data_enc_level1_bottleneck.bias"))), 2, 2)
+        r["b2"] = block(y, 2)
+        r["feat"] = F.max_pool3d(r["b2"], 6).reshape(x.shape[0], -1)
+    return {k: v.numpy() for k, v in r.items()}

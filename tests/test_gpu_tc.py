@@ -74,3 +74,45 @@ def test_fast_matches_fp32_validation_mode_on_many_ragged_poses():
     b.set_option("max_batch", 5)   # odd chunk sizes exercise the half-filled pose groups
     rc = b.score_batch(lx, lt, offs)
     assert np.abs(rc[0] - rb[0]).max() < 1e-6 and np.abs(rc[1] - rb[1]).max() < 1e-5
+
+
+@pytest.mark.parametrize("name", ["dense_1_3", "dense_1_3_PT_KD_3"])
+def test_dense_fast_scores_match_reference_pt(kat, name):
+    s = _fast([name])
+    s.set_receptor(kat["rec_xyz"], kat["rec_types"])
+    pose, aff, loss, var = s.score_batch(kat["lig_xyz"], kat["lig_types"], kat["pose_offsets"])
+    assert np.abs(pose - kat[name + "_pose_f64"]).max() < TOL_SCORE
+    assert np.abs(aff - kat[name + "_aff_f64"]).max() < TOL_AFF
+
+
+def test_dense_fast_intermediates_match_oracle(kat):
+    import tc_layout as tl
+    from gnina_b200 import model_blob
+    from oracle import pipeline
+    name, n = "dense_1_3", 3
+    offs = kat["pose_offsets"][:n + 1]
+    lx, lt = kat["lig_xyz"][:offs[-1]], kat["lig_types"][:offs[-1]]
+    blob = model_blob.load_model(name)
+    ref = tl.oracle_intermediates_dense(blob, pipeline.OracleModel(blob).grids(kat["rec_xyz"], kat["rec_types"], lx, lt, offs))
+    s = _fast([name])
+    s.set_receptor(kat["rec_xyz"], kat["rec_types"])
+    s.score_batch(lx, lt, offs)
+    x0, border = tl.decode_chunk_planar(s.debug_read("x0"), n, 24, 1, 32)
+    assert border == 0.0 and np.abs(x0[:, :28] - ref["x0"]).max() < 2e-3       # max-pooled fp16 grid
+    for tag, D, G, C in (("b0", 24, 1, 96), ("b1", 12, 2, 160), ("b2", 6, 2, 224)):
+        got, border = tl.decode_chunk_planar(s.debug_read(tag), n, D, G, C)
+        assert border == 0.0
+        assert np.abs(got - ref[tag]).max() < 4e-3 * np.abs(ref[tag]).max(), tag
+
+
+def test_default_ensemble_fast_vs_validation_mode(kat):
+    """gnina's default ensemble (2 dense + 1 default2018) entirely on the tensor-core path vs the fp32 kernels"""
+    from gnina_b200 import CNNScorer
+    a, b = CNNScorer([], precision=0), CNNScorer([], precision=1)
+    assert b.get_option("precision") == 1
+    for s in (a, b):
+        s.set_receptor(kat["rec_xyz"], kat["rec_types"])
+    ra = a.score_batch(kat["lig_xyz"], kat["lig_types"], kat["pose_offsets"])
+    rb = b.score_batch(kat["lig_xyz"], kat["lig_types"], kat["pose_offsets"])
+    assert np.abs(ra[0] - rb[0]).max() < TOL_SCORE and np.abs(ra[1] - rb[1]).max() < TOL_AFF
+    assert np.abs(ra[3] - rb[3]).max() < 2e-2      # affinity variance across the three models
