@@ -116,3 +116,30 @@ def test_default_ensemble_fast_vs_validation_mode(kat):
     rb = b.score_batch(kat["lig_xyz"], kat["lig_types"], kat["pose_offsets"])
     assert np.abs(ra[0] - rb[0]).max() < TOL_SCORE and np.abs(ra[1] - rb[1]).max() < TOL_AFF
     assert np.abs(ra[3] - rb[3]).max() < 2e-2      # affinity variance across the three models
+
+
+def test_full_size_batch_properties():
+    """BASELINE config-2 size (10k poses): size-independent properties of the fast path — batch-order invariance
+    (bit-exact), duplicate poses score identically, and a random subset agrees with the fp32 validation kernels."""
+    from gnina_b200 import CNNScorer, synth
+    rx, rt = synth.make_receptor()
+    lx0, lt0 = synth.make_ligand()
+    n, na = 10000, len(lt0)
+    lx, offs = synth.make_poses(lx0, n, seed=1)
+    lt = np.tile(lt0, n)
+    s = CNNScorer(["crossdock_default2018"], precision=1)
+    s.set_receptor(rx, rt)
+    a = s.score_batch(lx, lt, offs)
+    perm = np.random.RandomState(0).permutation(n)
+    lxp = lx.reshape(n, na, 3)[perm].reshape(-1, 3)
+    b = s.score_batch(lxp, lt, offs)
+    assert np.array_equal(a[0][perm], b[0]) and np.array_equal(a[1][perm], b[1])
+    dup = np.concatenate([lx[:na], lx[:na], lx[5 * na:6 * na]])
+    d = s.score_batch(dup, lt[:3 * na], offs[:4])
+    assert d[0][0] == d[0][1] == a[0][0] and d[0][2] == a[0][5]
+    sub = np.sort(perm[:48])
+    v = CNNScorer(["crossdock_default2018"], precision=0)
+    v.set_receptor(rx, rt)
+    ref = v.score_batch(lx.reshape(n, na, 3)[sub].reshape(-1, 3), lt[:48 * na], offs[:49])
+    assert np.abs(ref[0] - a[0][sub]).max() < TOL_SCORE and np.abs(ref[1] - a[1][sub]).max() < TOL_AFF
+    assert np.isfinite(a[0]).all() and (a[0] >= 0).all() and (a[0] <= 1).all()
