@@ -88,3 +88,74 @@ def make_screen(n_ligands, seed=3, trans_box=16.0, nmin=15, nmax=45):
         px, _ = make_poses(lx, 1, trans_box, seed=int(rs.randint(1 << 30)))
         xs.append(px); ts.append(lt); offs.append(offs[-1] + len(lt))
     return np.concatenate(xs), np.concatenate(ts), np.asarray(offs, np.int32)
+
+
+def make_flexible_ligand(n_heavy=24, n_tors=5, n_branch=3, seed=11):
+    """Synthetic ligand with a torsion tree in the reference's representation (lib/tree.h): segment 0 is the rigid
+    root, segments 1.. are torsion segments in DFS pre-order (= torsion order of `conf`).  Atoms are stored in the
+    local frame of their segment (identity orientation): coords = segment origin + local.  A linear chain with
+    `n_tors` rotatable bonds plus one side branch of `n_branch` atoms hanging off the root.
+    -> dict(local_xyz, types, seg_parent, seg_begin, seg_end, seg_rel_origin, seg_rel_axis, pair_a, pair_b,
+            conf0 [7+T] reproducing the generated coordinates, xyz0, gyration_radius)"""
+    rs = np.random.RandomState(seed)
+    xyz = [np.zeros(3)]
+    while len(xyz) < n_heavy:
+        d = rs.randn(3); d /= np.linalg.norm(d)
+        cand = xyz[-1] + 1.5 * d
+        if all(np.linalg.norm(cand - q) > 1.3 for q in xyz):
+            xyz.append(cand)
+    breaks = sorted(rs.choice(np.arange(3, n_heavy - 2, 2), size=n_tors, replace=False).tolist())
+    # side branch off atom 1 (root segment)
+    branch = []
+    cur = xyz[1]
+    while len(branch) < n_branch:
+        d = rs.randn(3); d /= np.linalg.norm(d)
+        cand = cur + 1.5 * d
+        if all(np.linalg.norm(cand - q) > 1.3 for q in xyz + branch):
+            branch.append(cand); cur = cand
+    pos = np.array(xyz + branch, np.float64)
+    n = len(pos)
+    types = rs.choice(LIG_HEAVY_TYPES, size=n).astype(np.int32)
+    seg_begin = [0] + breaks + [n_heavy]
+    seg_end = breaks + [n_heavy] + [n]
+    seg_parent = [-1] + list(range(0, n_tors)) + [0]
+    axis_root = [None] + [b - 1 for b in breaks] + [1]
+    ns = len(seg_begin)
+    origin = np.array([pos[seg_begin[s]] for s in range(ns)])
+    rel_origin = np.zeros((ns, 3)); rel_axis = np.zeros((ns, 3))
+    for s in range(1, ns):
+        rel_origin[s] = origin[s] - origin[seg_parent[s]]
+        a = origin[s] - pos[axis_root[s]]
+        rel_axis[s] = a / np.linalg.norm(a)
+    seg_of = np.zeros(n, int)
+    for s in range(ns):
+        seg_of[seg_begin[s]:seg_end[s]] = s
+    local = pos - origin[seg_of]
+    # chain neighbours for the 1-4 exclusion: consecutive chain atoms, branch hangs off atom 1
+    nbr = {i: set() for i in range(n)}
+    for i in range(n_heavy - 1):
+        nbr[i].add(i + 1); nbr[i + 1].add(i)
+    prev = 1
+    for b in range(n_heavy, n):
+        nbr[prev].add(b); nbr[b].add(prev); prev = b
+
+    def within3(i):
+        seen, front = {i}, {i}
+        for _ in range(3):
+            front = set(q for f in front for q in nbr[f]) - seen
+            seen |= front
+        return seen
+    pa, pb = [], []
+    for i in range(n):
+        w = within3(i)
+        for j2 in range(i + 1, n):
+            if seg_of[i] != seg_of[j2] and j2 not in w:
+                pa.append(i); pb.append(j2)
+    conf0 = np.zeros(7 + ns - 1, np.float32)
+    conf0[:3] = origin[0]; conf0[3] = 1.0
+    gr = float(np.sqrt(((pos - origin[0]) ** 2).sum(1).mean()))
+    return dict(local_xyz=local.astype(np.float32), types=types, seg_parent=np.array(seg_parent, np.int32),
+                seg_begin=np.array(seg_begin, np.int32), seg_end=np.array(seg_end, np.int32),
+                seg_rel_origin=rel_origin.astype(np.float32), seg_rel_axis=rel_axis.astype(np.float32),
+                pair_a=np.array(pa, np.int32), pair_b=np.array(pb, np.int32), conf0=conf0, xyz0=pos.astype(np.float32),
+                gyration_radius=gr)

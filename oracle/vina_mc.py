@@ -1,0 +1,91 @@
+"""ctypes front-end to oracle/vina_mc_ref.c (docking inner loop oracle; test infrastructure only)."""
+import ctypes as C
+import numpy as np
+from . import gridmaker as _gm
+from .vina import VinaOracle, lib as _vlib
+
+_fp, _ip, _vp = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_void_p
+
+
+class _Lig(C.Structure):
+    _fields_ = [("n_atoms", C.c_int), ("n_seg", C.c_int), ("n_pairs", C.c_int), ("local_xyz", _fp), ("type", _ip),
+                ("seg_parent", _ip), ("seg_begin", _ip), ("seg_end", _ip), ("seg_rel_origin", _fp), ("seg_rel_axis", _fp),
+                ("pair_a", _ip), ("pair_b", _ip)]
+
+
+class _Field(C.Structure):
+    _fields_ = [("grids", C.POINTER(_fp)), ("begin", _fp), ("end", _fp), ("n", _ip), ("slope", C.c_float), ("prec", _vp)]
+
+
+class _McParams(C.Structure):
+    _fields_ = [("num_steps", C.c_int), ("maxiters", C.c_int), ("num_saved_mins", C.c_int), ("temperature", C.c_float),
+                ("mutation_amplitude", C.c_float), ("min_rmsd", C.c_float), ("hunt_cap", C.c_float * 3),
+                ("gyration_radius", C.c_float)]
+
+
+def _f(a): return a.ctypes.data_as(_fp)
+def _i(a): return a.ctypes.data_as(_ip)
+
+
+class DockOracle:
+    """cache grids (dict type -> array, x fastest) + precalculate tables + ligand topology"""
+
+    def __init__(self, vina_oracle, grids, begin, end, n, lig, slope=1e3):
+        L = _vlib()
+        L.gvo_lig_set_conf.argtypes = [C.POINTER(_Lig), _fp, _fp, _fp, _fp]
+        L.gvo_lig_eval_deriv.argtypes = [C.POINTER(_Field), C.POINTER(_Lig), _fp, _fp, _fp, _fp]; L.gvo_lig_eval_deriv.restype = C.c_float
+        L.gvo_lig_eval_grid.argtypes = [C.POINTER(_Field), C.POINTER(_Lig), _fp, C.c_float, _fp]; L.gvo_lig_eval_grid.restype = C.c_float
+        L.gvo_bfgs.argtypes = [C.POINTER(_Field), C.POINTER(_Lig), _fp, _fp, C.c_int, _fp, C.POINTER(C.c_int)]; L.gvo_bfgs.restype = C.c_float
+        L.gvo_mc_run.argtypes = [C.POINTER(_Field), C.POINTER(_Lig), C.POINTER(_McParams), _fp, _fp, C.c_uint32, _fp, _fp]
+        L.gvo_random_conf.argtypes = [C.POINTER(C.c_uint32), _fp, _fp, C.c_int, _fp]
+        self.L = L
+        self.keep = []
+        k = lambda a, dt: self.keep.append(np.ascontiguousarray(a, dt)) or self.keep[-1]
+        self.lig = _Lig(len(lig["types"]), len(lig["seg_parent"]), len(lig["pair_a"]), _f(k(lig["local_xyz"], np.float32)),
+                        _i(k(lig["types"], np.int32)), _i(k(lig["seg_parent"], np.int32)), _i(k(lig["seg_begin"], np.int32)),
+                        _i(k(lig["seg_end"], np.int32)), _f(k(lig["seg_rel_origin"], np.float32)),
+                        _f(k(lig["seg_rel_axis"], np.float32)), _i(k(lig["pair_a"], np.int32)), _i(k(lig["pair_b"], np.int32)))
+        self.ptrs = (_fp * 28)()
+        for t, g in grids.items():
+            self.ptrs[t] = _f(k(g, np.float32))
+        self.field = _Field(self.ptrs, _f(k(begin, np.float32)), _f(k(end, np.float32)), _i(k(n, np.int32)), slope, vina_oracle.p)
+        self.vo = vina_oracle
+        self.T = len(lig["seg_parent"]) - 1
+        self.na = len(lig["types"])
+        self.gr = lig["gyration_radius"]
+
+    def coords(self, conf):
+        conf = np.ascontiguousarray(conf, np.float32)
+        c = np.empty((self.na, 3), np.float32); so = np.empty((self.T + 1, 3), np.float32); sa = np.empty((self.T + 1, 3), np.float32)
+        self.L.gvo_lig_set_conf(C.byref(self.lig), _f(conf), _f(c), _f(so), _f(sa))
+        return c
+
+    def eval_deriv(self, conf, v=(1000, 1000, 1000)):
+        conf = np.ascontiguousarray(conf, np.float32); v = np.ascontiguousarray(v, np.float32)
+        g = np.empty(6 + self.T, np.float32)
+        e = self.L.gvo_lig_eval_deriv(C.byref(self.field), C.byref(self.lig), _f(conf), _f(v), _f(g), None)
+        return e, g
+
+    def eval_grid(self, conf, v1=1000.0):
+        conf = np.ascontiguousarray(conf, np.float32)
+        return self.L.gvo_lig_eval_grid(C.byref(self.field), C.byref(self.lig), _f(conf), v1, None)
+
+    def bfgs(self, conf, maxiters, v=(1000, 1000, 1000)):
+        x = np.array(conf, np.float32); v = np.ascontiguousarray(v, np.float32)
+        g = np.empty(6 + self.T, np.float32); ne = C.c_int()
+        e = self.L.gvo_bfgs(C.byref(self.field), C.byref(self.lig), _f(x), _f(g), maxiters, _f(v), C.byref(ne))
+        return e, x, g, ne.value
+
+    def random_conf(self, seed, c1, c2):
+        s = C.c_uint32(seed)
+        x = np.empty(7 + self.T, np.float32)
+        self.L.gvo_random_conf(C.byref(s), _f(np.ascontiguousarray(c1, np.float32)), _f(np.ascontiguousarray(c2, np.float32)), self.T, _f(x))
+        return x, s.value
+
+    def mc(self, seed, c1, c2, num_steps, maxiters, num_saved_mins=20, temperature=1.2, amplitude=2.0, min_rmsd=0.5,
+           hunt_cap=(10, 1.5, 10)):
+        P = _McParams(num_steps, maxiters, num_saved_mins, temperature, amplitude, min_rmsd, (C.c_float * 3)(*hunt_cap), self.gr)
+        e = np.zeros(num_saved_mins, np.float32); x = np.zeros((num_saved_mins, 7 + self.T), np.float32)
+        n = self.L.gvo_mc_run(C.byref(self.field), C.byref(self.lig), C.byref(P), _f(np.ascontiguousarray(c1, np.float32)),
+                              _f(np.ascontiguousarray(c2, np.float32)), seed, _f(e), _f(x))
+        return e[:n], x[:n]
