@@ -12,7 +12,22 @@ SYMBOLS = ["gb_last_error", "gb_version", "gb_initialize_cuda", "gb_device_count
            "gb_cnn_destroy", "gb_cnn_num_models", "gb_cnn_set_option", "gb_cnn_get_option", "gb_cnn_set_receptor",
            "gb_cnn_score_batch", "gb_cnn_score_batch_models", "gb_cnn_score_grad", "gb_cnn_stage_poses", "gb_cnn_run_staged",
            "gb_cnn_fetch", "gb_cnn_profile_read", "gb_cnn_profile_reset", "gb_cnn_debug_read", "gb_cnn_stream", "gb_cnn_kernel_launches", "gb_cnn_voxelize", "gb_vina_create", "gb_vina_destroy", "gb_vina_table_size", "gb_vina_prec_table",
-           "gb_vina_set_receptor", "gb_vina_cache_build", "gb_vina_cache_read", "gb_vina_cache_eval", "gb_vina_score_exact"]
+           "gb_vina_set_receptor", "gb_vina_cache_build", "gb_vina_cache_read", "gb_vina_cache_eval", "gb_vina_score_exact", "gb_vina_set_ligand", "gb_vina_eval_deriv",
+           "gb_vina_bfgs", "gb_vina_mc"]
+
+
+class LigandTopology(C.Structure):
+    _fields_ = [("n_atoms", C.c_int32), ("n_segments", C.c_int32), ("n_pairs", C.c_int32),
+                ("local_xyz", C.POINTER(C.c_float)), ("smina_type", C.POINTER(C.c_int32)),
+                ("seg_parent", C.POINTER(C.c_int32)), ("seg_atom_begin", C.POINTER(C.c_int32)),
+                ("seg_atom_end", C.POINTER(C.c_int32)), ("seg_rel_origin", C.POINTER(C.c_float)),
+                ("seg_rel_axis", C.POINTER(C.c_float)), ("pair_a", C.POINTER(C.c_int32)), ("pair_b", C.POINTER(C.c_int32)),
+                ("gyration_radius", C.c_float)]
+
+
+class McParams(C.Structure):
+    _fields_ = [("num_steps", C.c_int32), ("maxiters", C.c_int32), ("num_saved_mins", C.c_int32), ("temperature", C.c_float),
+                ("mutation_amplitude", C.c_float), ("min_rmsd", C.c_float), ("hunt_cap", C.c_float * 3)]
 
 
 class GbError(RuntimeError):
@@ -79,6 +94,11 @@ def lib():
     L.gb_vina_cache_read.argtypes = [vp, C.c_int, fp]
     L.gb_vina_cache_eval.argtypes = [vp, fp, ip, ip, C.c_int, C.c_float, C.c_float, fp, fp]
     L.gb_vina_score_exact.argtypes = [vp, fp, ip, ip, C.c_int, fp, C.c_float, fp, fp]
+    up = C.POINTER(C.c_uint32)
+    L.gb_vina_set_ligand.argtypes = [vp, C.POINTER(LigandTopology)]
+    L.gb_vina_eval_deriv.argtypes = [vp, fp, C.c_int, fp, C.c_float, fp, fp, fp]
+    L.gb_vina_bfgs.argtypes = [vp, fp, C.c_int, C.c_int, fp, C.c_float, fp, fp, ip]
+    L.gb_vina_mc.argtypes = [vp, C.POINTER(McParams), fp, fp, up, C.c_int, C.c_float, fp, fp, ip]
     _lib = L
     return L
 

@@ -58,6 +58,18 @@ struct Vina {
   int n = 0;
   std::vector<float> h_fast, h_se, h_sd;  // [pair][n]
   float* d_fast = nullptr;
+  float2* d_smooth = nullptr;  // [pair][n] (e, dor) for eval_deriv
+  // ligand topology for the docking inner loop (gb_vina_set_ligand)
+  struct LigDev {
+    int n_atoms = 0, n_seg = 0, n_pairs = 0, max_depth = 0, n_heavy = 0;
+    float gyration_radius = 0;
+    float4* local = nullptr;   // x, y, z, smina type
+    int* atom_seg = nullptr;
+    int4* seg = nullptr;       // parent, atom begin, atom end, depth
+    float4* seg_rel_origin = nullptr;
+    float4* seg_rel_axis = nullptr;
+    int2* pairs = nullptr;
+  } lig;
   // receptor (heavy atoms, index order)
   float4* d_rec = nullptr;  // x, y, z, type
   int n_rec = 0;
@@ -72,7 +84,9 @@ struct Vina {
   ~Vina() {
     cudaSetDevice(device);
     if (stream) cudaStreamDestroy(stream);
-    cudaFree(d_fast); cudaFree(d_rec); cudaFree(d_lig); cudaFree(d_off); cudaFree(d_atom_e); cudaFree(d_deriv);
+    cudaFree(d_fast); cudaFree(d_smooth); cudaFree(d_rec);
+    cudaFree(lig.local); cudaFree(lig.atom_seg); cudaFree(lig.seg); cudaFree(lig.seg_rel_origin); cudaFree(lig.seg_rel_axis);
+    cudaFree(lig.pairs); cudaFree(d_lig); cudaFree(d_off); cudaFree(d_atom_e); cudaFree(d_deriv);
     cudaFree(d_pose_e); cudaFree(d_tors);
     for (auto g : d_grids) cudaFree(g);
   }
@@ -105,6 +119,12 @@ static void build_tables(Vina& v) {
     }
   GB_CUDA(cudaMalloc(&v.d_fast, v.h_fast.size() * sizeof(float)));
   GB_CUDA(cudaMemcpy(v.d_fast, v.h_fast.data(), v.h_fast.size() * sizeof(float), cudaMemcpyHostToDevice));
+  {
+    std::vector<float2> sm(v.h_se.size());
+    for (size_t i = 0; i < sm.size(); i++) sm[i] = make_float2(v.h_se[i], v.h_sd[i]);
+    GB_CUDA(cudaMalloc(&v.d_smooth, sm.size() * sizeof(float2)));
+    GB_CUDA(cudaMemcpy(v.d_smooth, sm.data(), sm.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  }
   GB_CUDA(cudaMemcpyToSymbol(c_props, &pr, sizeof(pr)));
   GB_CUDA(cudaMemcpyToSymbol(c_w, v.w, sizeof(v.w)));
 }
@@ -441,6 +461,625 @@ int gb_vina_score_exact(gb_vina* h, const float* lig_xyz, const int32_t* lig_typ
       affinity[p] = std::fabs(x) < eps ? 0.f : (std::fabs(y) < eps ? ((x * y > 0) ? maxfl : -maxfl) : x / y);
     }
   }
+  GBV_END
+}
+
+}  // extern "C"
+
+// =================================================================================================================
+// Docking inner loop as a batched kernel: ONE WARP PER CHAIN / CONFORMATION.
+//   V7  heterotree::set_conf (lib/tree.h:218-233,361-366): segment frames level by level (lane = segment), then atoms
+//   V5  cache::eval_deriv per atom (lane-strided), V6 eval_interacting_pairs_deriv (lib/model.cu:38-60) with the
+//       precalculate_linear (e, dor) tables, forces accumulated in shared memory
+//   V8  heterotree::derivative (lib/tree.h:300-310,374-382): per-segment force/torque (lane = segment), children
+//       folded into parents from the deepest level up
+//   V9  bfgs + fast_line_search + bfgs_update (lib/bfgs.h:52-91,358-502) with the packed upper-triangular Hessian in
+//       shared memory, conf::increment (lib/conf.h:54-59,113-118)
+//   V10 monte_carlo::operator() (lib/monte_carlo.cpp:99-148), mutate_conf (lib/mutate.cpp:35-73), metropolis_accept,
+//       add_to_output_container (lib/coords.cpp:25-56); V11: chains are independent -> one launch for all of them
+//       (the reference farms them to a boost thread pool, lib/parallel_mc.cpp:183-214)
+// Random numbers: xorshift32 exactly as oracle/vina_mc_ref.c (Boost's distributions are not reproducible here).
+// Summation order inside one evaluation differs from the sequential reference (warp reductions, shared-memory
+// atomics), so energies agree to float round-off, and long BFGS / MC trajectories are compared statistically.
+// =================================================================================================================
+namespace gb {
+
+constexpr int kDkMaxAtoms = 96, kDkMaxSeg = 32, kDkMaxN = 6 + kDkMaxSeg - 1, kDkWarps = 4;
+
+struct LigPtrs {
+  int n_atoms, n_seg, n_pairs, max_depth, n_heavy;
+  float gyration_radius;
+  const float4* local; const int* atom_seg; const int4* seg; const float4* rel_origin; const float4* rel_axis; const int2* pairs;
+};
+struct DockField { GridGeom G; GridPtrs gp; const float2* smooth; int n_samples; float factor, slope; };
+
+struct WarpWs {  // per-warp shared-memory workspace
+  float coords[kDkMaxAtoms * 3];
+  float forces[kDkMaxAtoms * 3];
+  float so[kDkMaxSeg * 3], sa[kDkMaxSeg * 3], sq[kDkMaxSeg * 4], sm[kDkMaxSeg * 9], ft[kDkMaxSeg * 6];
+  float x[kDkMaxN + 1], x_new[kDkMaxN + 1], x_orig[kDkMaxN + 1], g[kDkMaxN], g_new[kDkMaxN], g_orig[kDkMaxN], p[kDkMaxN], y[kDkMaxN],
+      mhy[kDkMaxN];
+  float h[kDkMaxN * (kDkMaxN + 1) / 2];
+  float cand[kDkMaxN + 1], tmp[kDkMaxN + 1];
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ inline void dk_normalize_angle(float& x) {
+  const float pi = 3.14159265358979323846f;
+  if (x > 3 * pi) { x -= 2 * pi * ceilf((x - pi) / (2 * pi)); }
+  else if (x < -3 * pi) { x += 2 * pi * ceilf((-x - pi) / (2 * pi)); }
+  if (x > pi) x -= 2 * pi;
+  else if (x < -pi) x += 2 * pi;
+}
+__device__ inline void dk_angle_to_q(const float* axis, float angle, float* q) {
+  dk_normalize_angle(angle);
+  const float c = cosf(angle / 2), s = sinf(angle / 2);
+  q[0] = c; q[1] = s * axis[0]; q[2] = s * axis[1]; q[3] = s * axis[2];
+}
+__device__ inline void dk_qmul(const float* l, const float* r, float* o) {
+  const float a = l[0], b = l[1], c = l[2], d = l[3];
+  o[0] = +a * r[0] - b * r[1] - c * r[2] - d * r[3];
+  o[1] = +a * r[1] + b * r[0] + c * r[3] - d * r[2];
+  o[2] = +a * r[2] - b * r[3] + c * r[0] + d * r[1];
+  o[3] = +a * r[3] + b * r[2] - c * r[1] + d * r[0];
+}
+__device__ inline void dk_qnorm_approx(float* q) {
+  const float s = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  if (fabsf(s - 1) < 1e-6f) return;
+  const float inv = 1 / sqrtf(s);
+  for (int i = 0; i < 4; i++) q[i] *= inv;
+}
+__device__ inline void dk_q_to_r3(const float* q, float* m) {
+  const float a = q[0], b = q[1], c = q[2], d = q[3];
+  const float aa = a * a, ab = a * b, ac = a * c, ad = a * d, bb = b * b, bc = b * c, bd = b * d, cc = c * c, cd = c * d, dd = d * d;
+  m[0] = (aa + bb - cc - dd); m[1] = 2 * (-ad + bc); m[2] = 2 * (ac + bd);
+  m[3] = 2 * (ad + bc); m[4] = (aa - bb + cc - dd); m[5] = 2 * (-ab + cd);
+  m[6] = 2 * (-ac + bd); m[7] = 2 * (ab + cd); m[8] = (aa - bb - cc + dd);
+}
+__device__ inline void dk_mv(const float* m, float vx, float vy, float vz, float* o) {
+  o[0] = m[0] * vx + m[1] * vy + m[2] * vz;
+  o[1] = m[3] * vx + m[4] * vy + m[5] * vz;
+  o[2] = m[6] * vx + m[7] * vy + m[8] * vz;
+}
+__device__ inline void dk_quaternion_increment(float* q, const float* rot) {
+  const float angle = sqrtf(rot[0] * rot[0] + rot[1] * rot[1] + rot[2] * rot[2]);
+  float r[4] = {1, 0, 0, 0};
+  if (angle > 1.1920929e-07f) {
+    const float axis[3] = {(1 / angle) * rot[0], (1 / angle) * rot[1], (1 / angle) * rot[2]};
+    dk_angle_to_q(axis, angle, r);
+  }
+  float o[4];
+  dk_qmul(r, q, o);
+  for (int i = 0; i < 4; i++) q[i] = o[i];
+  dk_qnorm_approx(q);
+}
+
+// V7: conf (W.x-like array xc) -> segment frames + atom coordinates in W.coords
+__device__ void dk_set_conf(const LigPtrs& L, WarpWs& W, const float* xc, int lane) {
+  for (int d = 0; d <= L.max_depth; d++) {
+    if (lane < L.n_seg) {
+      const int4 sg = L.seg[lane];
+      if (sg.w == d) {
+        float* o = W.so + 3 * lane;
+        float* q = W.sq + 4 * lane;
+        if (lane == 0) {
+          o[0] = xc[0]; o[1] = xc[1]; o[2] = xc[2];
+          q[0] = xc[3]; q[1] = xc[4]; q[2] = xc[5]; q[3] = xc[6];
+          W.sa[0] = W.sa[1] = W.sa[2] = 0.f;
+        } else {
+          const int pp = sg.x;
+          const float4 ro = L.rel_origin[lane], ra = L.rel_axis[lane];
+          float t[3];
+          dk_mv(W.sm + 9 * pp, ro.x, ro.y, ro.z, t);
+          for (int k = 0; k < 3; k++) o[k] = W.so[3 * pp + k] + t[k];
+          dk_mv(W.sm + 9 * pp, ra.x, ra.y, ra.z, W.sa + 3 * lane);
+          float aq[4];
+          dk_angle_to_q(W.sa + 3 * lane, xc[7 + lane - 1], aq);
+          dk_qmul(aq, W.sq + 4 * pp, q);
+          dk_qnorm_approx(q);
+        }
+        dk_q_to_r3(q, W.sm + 9 * lane);
+      }
+    }
+    __syncwarp();
+  }
+  for (int i = lane; i < L.n_atoms; i += 32) {
+    const int sgi = L.atom_seg[i];
+    const float4 a = L.local[i];
+    float t[3];
+    dk_mv(W.sm + 9 * sgi, a.x, a.y, a.z, t);
+    for (int k = 0; k < 3; k++) W.coords[3 * i + k] = W.so[3 * sgi + k] + t[k];
+  }
+  __syncwarp();
+}
+
+// update_energy: cache::eval (grid energy only)
+__device__ float dk_eval_grid(const LigPtrs& L, const DockField& F, WarpWs& W, const float* xc, float v1, int lane) {
+  dk_set_conf(L, W, xc, lane);
+  float e = 0.f;
+  for (int i = lane; i < L.n_atoms; i += 32) {
+    const int t = (int)L.local[i].w;
+    if (t >= 2 && t < kNumSminaTypes) e += grid_evaluate_dev(F.gp.g[t], F.G, W.coords[3 * i], W.coords[3 * i + 1], W.coords[3 * i + 2], F.slope, v1, nullptr);
+  }
+  return warp_sum(e);
+}
+
+// model::eval_deriv: returns e (all lanes), writes change[6+T] to gout
+__device__ float dk_eval_deriv(const LigPtrs& L, const DockField& F, WarpWs& W, const float* xc, const float* v, float* gout, int lane) {
+  dk_set_conf(L, W, xc, lane);
+  float e = 0.f;
+  for (int i = lane; i < L.n_atoms; i += 32) {
+    const int t = (int)L.local[i].w;
+    float d[3] = {0.f, 0.f, 0.f};
+    if (t >= 2 && t < kNumSminaTypes) e += grid_evaluate_dev(F.gp.g[t], F.G, W.coords[3 * i], W.coords[3 * i + 1], W.coords[3 * i + 2], F.slope, v[1], d);
+    W.forces[3 * i] = d[0]; W.forces[3 * i + 1] = d[1]; W.forces[3 * i + 2] = d[2];
+  }
+  __syncwarp();
+  for (int k = lane; k < L.n_pairs; k += 32) {
+    const int2 pr = L.pairs[k];
+    const float rx = W.coords[3 * pr.y] - W.coords[3 * pr.x], ry = W.coords[3 * pr.y + 1] - W.coords[3 * pr.x + 1],
+                rz = W.coords[3 * pr.y + 2] - W.coords[3 * pr.x + 2];
+    const float r2 = rx * rx + ry * ry + rz * rz;
+    if (r2 < 64.f) {
+      int t1 = (int)L.local[pr.x].w, t2 = (int)L.local[pr.y].w;
+      if (t1 > t2) { const int tt = t1; t1 = t2; t2 = tt; }
+      const float r2f = F.factor * r2;
+      const int i1 = (int)r2f;
+      const float rem = r2f - i1;
+      const float2* tb = F.smooth + (size_t)(t1 + t2 * (t2 + 1) / 2) * F.n_samples;
+      const float2 s1 = tb[i1], s2 = tb[i1 + 1];
+      float pe = s1.x + rem * (s2.x - s1.x);
+      const float dor = s1.y + rem * (s2.y - s1.y);
+      float fx = dor * rx, fy = dor * ry, fz = dor * rz;
+      if (pe > 0 && v[0] < 0.1f * 3.402823466e+38f) {
+        const float tmp = (v[0] < 1.1920929e-07f) ? 0.f : (v[0] / (v[0] + pe));
+        pe *= tmp;
+        fx *= tmp * tmp; fy *= tmp * tmp; fz *= tmp * tmp;
+      }
+      e += pe;
+      atomicAdd(&W.forces[3 * pr.x], -fx); atomicAdd(&W.forces[3 * pr.x + 1], -fy); atomicAdd(&W.forces[3 * pr.x + 2], -fz);
+      atomicAdd(&W.forces[3 * pr.y], fx); atomicAdd(&W.forces[3 * pr.y + 1], fy); atomicAdd(&W.forces[3 * pr.y + 2], fz);
+    }
+  }
+  e = warp_sum(e);
+  __syncwarp();
+  // V8: per-segment force / torque about the segment origin, then fold children into parents (deepest first)
+  if (lane < L.n_seg) {
+    const int4 sg = L.seg[lane];
+    float f[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = sg.y; i < sg.z; i++) {
+      const float rx = W.coords[3 * i] - W.so[3 * lane], ry = W.coords[3 * i + 1] - W.so[3 * lane + 1], rz = W.coords[3 * i + 2] - W.so[3 * lane + 2];
+      const float qx = W.forces[3 * i], qy = W.forces[3 * i + 1], qz = W.forces[3 * i + 2];
+      f[0] += qx; f[1] += qy; f[2] += qz;
+      f[3] += ry * qz - rz * qy; f[4] += rz * qx - rx * qz; f[5] += rx * qy - ry * qx;
+    }
+    for (int k = 0; k < 6; k++) W.ft[6 * lane + k] = f[k];
+  }
+  __syncwarp();
+  for (int d = L.max_depth; d >= 1; d--) {
+    if (lane < L.n_seg) {
+      const int4 sg = L.seg[lane];
+      if (sg.w == d) {
+        const int pp = sg.x;
+        const float* c = W.ft + 6 * lane;
+        const float rx = W.so[3 * lane] - W.so[3 * pp], ry = W.so[3 * lane + 1] - W.so[3 * pp + 1], rz = W.so[3 * lane + 2] - W.so[3 * pp + 2];
+        atomicAdd(&W.ft[6 * pp + 0], c[0]); atomicAdd(&W.ft[6 * pp + 1], c[1]); atomicAdd(&W.ft[6 * pp + 2], c[2]);
+        atomicAdd(&W.ft[6 * pp + 3], ry * c[2] - rz * c[1] + c[3]);
+        atomicAdd(&W.ft[6 * pp + 4], rz * c[0] - rx * c[2] + c[4]);
+        atomicAdd(&W.ft[6 * pp + 5], rx * c[1] - ry * c[0] + c[5]);
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) for (int k = 0; k < 6; k++) gout[k] = W.ft[k];
+  else if (lane < L.n_seg) gout[6 + lane - 1] = W.ft[6 * lane + 3] * W.sa[3 * lane] + W.ft[6 * lane + 4] * W.sa[3 * lane + 1] + W.ft[6 * lane + 5] * W.sa[3 * lane + 2];
+  __syncwarp();
+  return e;
+}
+
+__device__ inline int dk_tri(int i, int j) { return i <= j ? i + j * (j + 1) / 2 : j + i * (i + 1) / 2; }
+
+__device__ void dk_conf_increment(float* x, const float* p, float f, int T, int lane) {
+  if (lane == 0) {
+    for (int k = 0; k < 3; k++) x[k] += f * p[k];
+    const float rot[3] = {f * p[3], f * p[4], f * p[5]};
+    dk_quaternion_increment(x + 3, rot);
+  }
+  for (int t = lane; t < T; t += 32) {
+    float a = f * p[6 + t];
+    dk_normalize_angle(a);
+    float nx = x[7 + t] + a;
+    dk_normalize_angle(nx);
+    x[7 + t] = nx;
+  }
+  __syncwarp();
+}
+
+// bfgs (lib/bfgs.h:358-502), fast_line_search; W.x in/out, W.g out; returns f0 (all lanes)
+__device__ float dk_bfgs(const LigPtrs& L, const DockField& F, WarpWs& W, int maxiters, const float* v, int lane, int* n_evals) {
+  const int T = L.n_seg - 1, n = 6 + T, nx = 7 + T;
+  for (int k = lane; k < n * (n + 1) / 2; k += 32) W.h[k] = 0.f;
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) W.h[dk_tri(i, i)] = 1.f;
+  int evals = 1;
+  float f0 = dk_eval_deriv(L, F, W, W.x, v, W.g, lane);
+  const float f_orig = f0;
+  for (int i = lane; i < nx; i += 32) W.x_orig[i] = W.x[i];
+  for (int i = lane; i < n; i += 32) W.g_orig[i] = W.g[i];
+  __syncwarp();
+  bool didreset = false;
+  for (int step = 0; step < maxiters; step++) {
+    for (int i = lane; i < n; i += 32) {
+      float s = 0.f;
+      for (int j2 = 0; j2 < n; j2++) s += W.h[dk_tri(i, j2)] * W.g[j2];
+      W.p[i] = -s;
+    }
+    __syncwarp();
+    float pg = 0.f;
+    for (int i = lane; i < n; i += 32) pg += W.p[i] * W.g[i];
+    pg = warp_sum(pg);
+    float f1 = 0.f, alpha = 1.f;
+    for (int trial = 0; trial < 10; trial++) {
+      for (int i = lane; i < nx; i += 32) W.x_new[i] = W.x[i];
+      __syncwarp();
+      dk_conf_increment(W.x_new, W.p, alpha, T, lane);
+      f1 = dk_eval_deriv(L, F, W, W.x_new, v, W.g_new, lane);
+      evals++;
+      if (f1 - f0 < 0.0001f * alpha * pg) break;
+      alpha *= 0.5f;
+    }
+    if (alpha == 0.f) break;
+    for (int i = lane; i < n; i += 32) W.y[i] = W.g_new[i] - W.g[i];
+    f0 = f1;
+    for (int i = lane; i < nx; i += 32) W.x[i] = W.x_new[i];
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) W.g[i] = W.g_new[i];
+    __syncwarp();
+    float gn = 0.f, yy = 0.f, yp = 0.f;
+    for (int i = lane; i < n; i += 32) { gn += W.g[i] * W.g[i]; yy += W.y[i] * W.y[i]; yp += W.y[i] * W.p[i]; }
+    gn = warp_sum(gn); yy = warp_sum(yy); yp = warp_sum(yp);
+    if (!(gn >= 1e-4f)) break;
+    if (step == 0 || didreset) {
+      didreset = false;
+      if (fabsf(yy) > 1.1920929e-07f)
+        for (int i = lane; i < n; i += 32) W.h[dk_tri(i, i)] = alpha * yp / yy;
+      __syncwarp();
+    }
+    if (!(alpha * yp < 1.1920929e-07f)) {  // bfgs_update
+      for (int i = lane; i < n; i += 32) {
+        float s = 0.f;
+        for (int j2 = 0; j2 < n; j2++) s += W.h[dk_tri(i, j2)] * W.y[j2];
+        W.mhy[i] = -s;
+      }
+      __syncwarp();
+      float yhy = 0.f;
+      for (int i = lane; i < n; i += 32) yhy += W.y[i] * W.mhy[i];
+      yhy = -warp_sum(yhy);
+      const float r = 1 / (alpha * yp);
+      for (int k = lane; k < n * (n + 1) / 2; k += 32) {
+        // invert k = i + j(j+1)/2, i <= j
+        int j2 = (int)((sqrtf(8.f * k + 1.f) - 1.f) * 0.5f);
+        while (j2 * (j2 + 1) / 2 > k) j2--;
+        while ((j2 + 1) * (j2 + 2) / 2 <= k) j2++;
+        const int i = k - j2 * (j2 + 1) / 2;
+        W.h[k] += alpha * r * (W.mhy[i] * W.p[j2] + W.mhy[j2] * W.p[i]) + alpha * alpha * (r * r * yhy + r) * W.p[i] * W.p[j2];
+      }
+      __syncwarp();
+    }
+  }
+  if (!(f0 <= f_orig)) {
+    f0 = f_orig;
+    for (int i = lane; i < nx; i += 32) W.x[i] = W.x_orig[i];
+    for (int i = lane; i < n; i += 32) W.g[i] = W.g_orig[i];
+    __syncwarp();
+  }
+  if (n_evals) *n_evals = evals;
+  return f0;
+}
+
+// xorshift32 as in oracle/vina_mc_ref.c; the state lives in lane 0's register and results are broadcast
+__device__ inline uint32_t dk_rng_next(uint32_t& s) { uint32_t x = s; x ^= x << 13; x ^= x >> 17; x ^= x << 5; s = x; return x; }
+__device__ inline float dk_rng_fl(uint32_t& s, float a, float b) { return a + (b - a) * ((float)(dk_rng_next(s) >> 8) * (1.0f / 16777216.0f)); }
+__device__ inline void dk_rng_sphere(uint32_t& s, float* o) {
+  for (;;) {
+    o[0] = dk_rng_fl(s, -1, 1); o[1] = dk_rng_fl(s, -1, 1); o[2] = dk_rng_fl(s, -1, 1);
+    if (o[0] * o[0] + o[1] * o[1] + o[2] * o[2] < 1) return;
+  }
+}
+
+__global__ void __launch_bounds__(32 * kDkWarps) dock_eval_kernel(LigPtrs L, DockField F, const float* __restrict__ confs, int n,
+                                                                  float v0, float v1, float v2, float* __restrict__ e_out,
+                                                                  float* __restrict__ change_out, float* __restrict__ coords_out,
+                                                                  int mode, int maxiters, float* __restrict__ confs_out,
+                                                                  int* __restrict__ evals_out) {
+  __shared__ WarpWs ws[kDkWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * kDkWarps + warp;
+  if (c >= n) return;
+  WarpWs& W = ws[warp];
+  const int T = L.n_seg - 1, nx = 7 + T, ng = 6 + T;
+  const float v[3] = {v0, v1, v2};
+  for (int i = lane; i < nx; i += 32) W.x[i] = confs[(size_t)c * nx + i];
+  __syncwarp();
+  if (mode == 0) {
+    const float e = dk_eval_deriv(L, F, W, W.x, v, W.g, lane);
+    if (lane == 0) e_out[c] = e;
+    for (int i = lane; i < ng; i += 32) change_out[(size_t)c * ng + i] = W.g[i];
+    if (coords_out)
+      for (int i = lane; i < 3 * L.n_atoms; i += 32) coords_out[(size_t)c * 3 * L.n_atoms + i] = W.coords[i];
+  } else {
+    int ne = 0;
+    const float e = dk_bfgs(L, F, W, maxiters, v, lane, &ne);
+    if (lane == 0) { e_out[c] = e; if (evals_out) evals_out[c] = ne; }
+    for (int i = lane; i < nx; i += 32) confs_out[(size_t)c * nx + i] = W.x[i];
+    if (change_out)
+      for (int i = lane; i < ng; i += 32) change_out[(size_t)c * ng + i] = W.g[i];
+  }
+}
+
+struct McDev { int num_steps, maxiters, num_saved_mins; float temperature, mutation_amplitude, min_rmsd; float hunt_cap[3]; };
+
+__global__ void __launch_bounds__(32 * kDkWarps) dock_mc_kernel(LigPtrs L, DockField F, McDev P, float c1x, float c1y, float c1z, float c2x,
+                                                                float c2y, float c2z, const uint32_t* __restrict__ seeds, int n_chains,
+                                                                float* __restrict__ out_e, float* __restrict__ out_conf,
+                                                                float* __restrict__ out_heavy, int* __restrict__ n_out_arr) {
+  __shared__ WarpWs ws[kDkWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * kDkWarps + warp;
+  if (c >= n_chains) return;
+  WarpWs& W = ws[warp];
+  const int T = L.n_seg - 1, nx = 7 + T, nh = L.n_heavy, S = P.num_saved_mins;
+  float* oe = out_e + (size_t)c * S;
+  float* oc = out_conf + (size_t)c * S * nx;
+  float* oh = out_heavy + (size_t)c * S * 3 * nh;
+  uint32_t rs = seeds[c] ? seeds[c] : 1u;  // only lane 0's copy advances; draws are broadcast
+  const float av[3] = {1000.f, 1000.f, 1000.f};
+  const float pi = 3.14159265358979323846f;
+  // conf::randomize
+  if (lane == 0) {
+    const float c1[3] = {c1x, c1y, c1z}, c2[3] = {c2x, c2y, c2z};
+    for (int k = 0; k < 3; k++) W.tmp[k] = dk_rng_fl(rs, c1[k], c2[k]);
+    for (;;) {
+      float q[4], s = 0;
+      for (int k = 0; k < 4; k++) { q[k] = dk_rng_fl(rs, -1, 1); s += q[k] * q[k]; }
+      if (s < 1 && s > 1e-3f) { const float inv = 1 / sqrtf(s); for (int k = 0; k < 4; k++) W.tmp[3 + k] = q[k] * inv; break; }
+    }
+    for (int t = 0; t < T; t++) W.tmp[7 + t] = dk_rng_fl(rs, -pi, pi);
+  }
+  __syncwarp();
+  float tmp_e = 0.f, best_e = 3.402823466e+38f;
+  int n_out = 0;
+  for (int step = 0; step < P.num_steps; step++) {
+    for (int i = lane; i < nx; i += 32) W.cand[i] = W.tmp[i];
+    __syncwarp();
+    if (lane == 0) {  // mutate_conf
+      const int which = (int)(dk_rng_next(rs) % (uint32_t)(2 + T));
+      float r[3];
+      if (which == 0) { dk_rng_sphere(rs, r); for (int k = 0; k < 3; k++) W.cand[k] += P.mutation_amplitude * r[k]; }
+      else if (which == 1) {
+        if (L.gyration_radius > 1.1920929e-07f) {
+          dk_rng_sphere(rs, r);
+          const float rot[3] = {P.mutation_amplitude / L.gyration_radius * r[0], P.mutation_amplitude / L.gyration_radius * r[1],
+                                P.mutation_amplitude / L.gyration_radius * r[2]};
+          dk_quaternion_increment(W.cand + 3, rot);
+        }
+      } else W.cand[7 + which - 2] = dk_rng_fl(rs, -pi, pi);
+    }
+    __syncwarp();
+    for (int i = lane; i < nx; i += 32) W.x[i] = W.cand[i];
+    __syncwarp();
+    dk_bfgs(L, F, W, P.maxiters, P.hunt_cap, lane, nullptr);
+    for (int i = lane; i < nx; i += 32) W.cand[i] = W.x[i];
+    __syncwarp();
+    const float cand_e = dk_eval_grid(L, F, W, W.cand, av[1], lane);
+    int accept = (step == 0 || cand_e < tmp_e) ? 1 : 0;
+    if (!accept) {
+      float u = 0.f;
+      if (lane == 0) u = dk_rng_fl(rs, 0, 1);
+      u = __shfl_sync(0xffffffffu, u, 0);
+      accept = u < expf((tmp_e - cand_e) / P.temperature);
+    }
+    if (accept) {
+      for (int i = lane; i < nx; i += 32) W.tmp[i] = W.cand[i];
+      __syncwarp();
+      tmp_e = cand_e;
+      if (tmp_e < best_e || n_out < S) {
+        for (int i = lane; i < nx; i += 32) W.x[i] = W.tmp[i];
+        __syncwarp();
+        dk_bfgs(L, F, W, P.maxiters, av, lane, nullptr);
+        for (int i = lane; i < nx; i += 32) W.tmp[i] = W.x[i];
+        __syncwarp();
+        tmp_e = dk_eval_grid(L, F, W, W.tmp, av[1], lane);  // leaves the coordinates in W.coords
+        // add_to_output_container: rmsd of the heavy atoms to every kept pose
+        int ci = n_out;
+        float cr = 3.402823466e+38f;
+        for (int o = 0; o < n_out; o++) {
+          float acc = 0.f;
+          int hk = 0;
+          for (int i = 0; i < L.n_atoms; i++) {  // heavy index = running count (uniform across lanes)
+            if ((int)L.local[i].w >= 2) {
+              if ((hk & 31) == lane) {
+                const float* q = oh + ((size_t)o * nh + hk) * 3;
+                const float dx = W.coords[3 * i] - q[0], dy = W.coords[3 * i + 1] - q[1], dz = W.coords[3 * i + 2] - q[2];
+                acc += dx * dx + dy * dy + dz * dz;
+              }
+              hk++;
+            }
+          }
+          acc = warp_sum(acc);
+          const float r = nh > 0 ? sqrtf(acc / nh) : 0.f;
+          if (o == 0 || r < cr) { ci = o; cr = r; }
+        }
+        int slot = -1;
+        if (ci < n_out && cr < P.min_rmsd) { if (tmp_e < oe[ci]) slot = ci; }
+        else if (n_out < S) slot = n_out++;
+        else if (n_out > 0 && tmp_e < oe[n_out - 1]) slot = n_out - 1;
+        if (slot >= 0) {
+          __syncwarp();
+          if (lane == 0) oe[slot] = tmp_e;
+          for (int i = lane; i < nx; i += 32) oc[(size_t)slot * nx + i] = W.tmp[i];
+          int hk = 0;
+          for (int i = 0; i < L.n_atoms; i++)
+            if ((int)L.local[i].w >= 2) {
+              if ((hk & 31) == lane) for (int k = 0; k < 3; k++) oh[((size_t)slot * nh + hk) * 3 + k] = W.coords[3 * i + k];
+              hk++;
+            }
+          __syncwarp();
+          // out.sort(): bubble the changed entry to its place (entries are otherwise sorted)
+          for (int a = 1; a < n_out; a++)
+            for (int b = a; b > 0; b--) {
+              const float eb = oe[b], ea = oe[b - 1];
+              if (!(eb < ea)) break;
+              __syncwarp();
+              if (lane == 0) { oe[b] = ea; oe[b - 1] = eb; }
+              for (int i = lane; i < nx; i += 32) { const float t2 = oc[(size_t)b * nx + i]; oc[(size_t)b * nx + i] = oc[(size_t)(b - 1) * nx + i]; oc[(size_t)(b - 1) * nx + i] = t2; }
+              for (int i = lane; i < 3 * nh; i += 32) { const float t2 = oh[(size_t)b * 3 * nh + i]; oh[(size_t)b * 3 * nh + i] = oh[(size_t)(b - 1) * 3 * nh + i]; oh[(size_t)(b - 1) * 3 * nh + i] = t2; }
+              __syncwarp();
+            }
+        }
+        if (tmp_e < best_e) best_e = tmp_e;
+      }
+    }
+  }
+  if (lane == 0) n_out_arr[c] = n_out;
+}
+
+}  // namespace gb
+
+static void make_field(const Vina& v, float slope, DockField& F) {
+  for (int i = 0; i < 3; i++) {
+    F.G.dims[i] = v.gn[i] + 1;
+    F.G.dm1[i] = (float)(F.G.dims[i] - 1.0);
+    F.G.begin[i] = v.begin[i];
+    F.G.factor[i] = F.G.dm1[i] / (v.end[i] - v.begin[i]);
+    F.G.finv[i] = 1 / F.G.factor[i];
+  }
+  for (int t = 0; t < kNumSminaTypes; t++) F.gp.g[t] = v.d_grids[t];
+  F.smooth = v.d_smooth; F.n_samples = v.n; F.factor = v.factor; F.slope = slope;
+}
+static LigPtrs lig_ptrs(const Vina& v) {
+  const auto& l = v.lig;
+  return LigPtrs{l.n_atoms, l.n_seg, l.n_pairs, l.max_depth, l.n_heavy, l.gyration_radius, l.local, l.atom_seg, l.seg, l.seg_rel_origin,
+                 l.seg_rel_axis, l.pairs};
+}
+static void check_dock_ready(const Vina& v) {
+  GB_CHECK(v.lig.n_atoms > 0, "gb_vina_set_ligand has not been called");
+  GB_CHECK(v.gn[0] > 0, "gb_vina_cache_build has not been called");
+  for (int t = 2; t < kNumSminaTypes; t++) (void)t;
+}
+
+extern "C" {
+
+int gb_vina_set_ligand(gb_vina* h, const gb_ligand_topology* t) {
+  GBV_BEGIN
+  GB_CHECK(h && t, "null argument");
+  GB_CHECK(t->n_atoms > 0 && t->n_atoms <= kDkMaxAtoms, "ligand atom count out of range (max 96)");
+  GB_CHECK(t->n_segments >= 1 && t->n_segments <= kDkMaxSeg, "segment count out of range (max 32)");
+  Vina& v = h->v;
+  GB_CUDA(cudaSetDevice(v.device));
+  auto& l = v.lig;
+  cudaFree(l.local); cudaFree(l.atom_seg); cudaFree(l.seg); cudaFree(l.seg_rel_origin); cudaFree(l.seg_rel_axis); cudaFree(l.pairs);
+  l = Vina::LigDev();
+  const int na = t->n_atoms, ns = t->n_segments;
+  std::vector<float4> local(na), ro(ns), ra(ns);
+  std::vector<int> aseg(na, -1);
+  std::vector<int4> seg(ns);
+  int max_depth = 0, nh = 0;
+  for (int s = 0; s < ns; s++) {
+    const int par = t->seg_parent[s];
+    GB_CHECK((s == 0 && par < 0) || (s > 0 && par >= 0 && par < s), "segments must be in DFS pre-order with parent < child");
+    const int depth = s == 0 ? 0 : seg[par].w + 1;
+    max_depth = std::max(max_depth, depth);
+    seg[s] = make_int4(par, t->seg_atom_begin[s], t->seg_atom_end[s], depth);
+    for (int i = t->seg_atom_begin[s]; i < t->seg_atom_end[s]; i++) { GB_CHECK(i >= 0 && i < na, "segment atom range"); aseg[i] = s; }
+    ro[s] = make_float4(t->seg_rel_origin[3 * s], t->seg_rel_origin[3 * s + 1], t->seg_rel_origin[3 * s + 2], 0.f);
+    ra[s] = make_float4(t->seg_rel_axis[3 * s], t->seg_rel_axis[3 * s + 1], t->seg_rel_axis[3 * s + 2], 0.f);
+  }
+  for (int i = 0; i < na; i++) {
+    GB_CHECK(aseg[i] >= 0, "every atom must belong to a segment");
+    local[i] = make_float4(t->local_xyz[3 * i], t->local_xyz[3 * i + 1], t->local_xyz[3 * i + 2], (float)t->smina_type[i]);
+    nh += t->smina_type[i] >= 2;
+  }
+  std::vector<int2> pairs(std::max(t->n_pairs, 1));
+  for (int k = 0; k < t->n_pairs; k++) pairs[k] = make_int2(t->pair_a[k], t->pair_b[k]);
+  auto up = [&](auto** d, const auto& hv) {
+    GB_CUDA(cudaMalloc(d, hv.size() * sizeof(hv[0])));
+    GB_CUDA(cudaMemcpy(*d, hv.data(), hv.size() * sizeof(hv[0]), cudaMemcpyHostToDevice));
+  };
+  up(&l.local, local); up(&l.atom_seg, aseg); up(&l.seg, seg); up(&l.seg_rel_origin, ro); up(&l.seg_rel_axis, ra); up(&l.pairs, pairs);
+  l.n_atoms = na; l.n_seg = ns; l.n_pairs = t->n_pairs; l.max_depth = max_depth; l.n_heavy = nh; l.gyration_radius = t->gyration_radius;
+  GBV_END
+}
+
+static int dock_eval_common(gb_vina* h, const float* confs, int n, const float* vcap, float slope, int mode, int maxiters, float* e,
+                            float* change, float* coords, float* confs_out, int32_t* evals) {
+  GBV_BEGIN
+  GB_CHECK(h && confs && vcap && e && n >= 0, "bad arguments");
+  Vina& v = h->v;
+  GB_CUDA(cudaSetDevice(v.device));
+  check_dock_ready(v);
+  if (n == 0) return GB_OK;
+  const int T = v.lig.n_seg - 1, nx = 7 + T, ng = 6 + T, na = v.lig.n_atoms;
+  float *d_conf, *d_e, *d_g, *d_c = nullptr, *d_xo = nullptr;
+  int* d_ev = nullptr;
+  GB_CUDA(cudaMalloc(&d_conf, (size_t)n * nx * 4)); GB_CUDA(cudaMalloc(&d_e, (size_t)n * 4)); GB_CUDA(cudaMalloc(&d_g, (size_t)n * ng * 4));
+  if (coords) GB_CUDA(cudaMalloc(&d_c, (size_t)n * 3 * na * 4));
+  if (mode == 1) { GB_CUDA(cudaMalloc(&d_xo, (size_t)n * nx * 4)); GB_CUDA(cudaMalloc(&d_ev, (size_t)n * 4)); }
+  GB_CUDA(cudaMemcpyAsync(d_conf, confs, (size_t)n * nx * 4, cudaMemcpyHostToDevice, v.stream));
+  DockField F;
+  make_field(v, slope, F);
+  dock_eval_kernel<<<(n + kDkWarps - 1) / kDkWarps, 32 * kDkWarps, 0, v.stream>>>(lig_ptrs(v), F, d_conf, n, vcap[0], vcap[1], vcap[2], d_e, d_g,
+                                                                                  d_c, mode, maxiters, d_xo, d_ev);
+  GB_CUDA(cudaGetLastError());
+  GB_CUDA(cudaMemcpyAsync(e, d_e, (size_t)n * 4, cudaMemcpyDeviceToHost, v.stream));
+  if (change) GB_CUDA(cudaMemcpyAsync(change, d_g, (size_t)n * ng * 4, cudaMemcpyDeviceToHost, v.stream));
+  if (coords) GB_CUDA(cudaMemcpyAsync(coords, d_c, (size_t)n * 3 * na * 4, cudaMemcpyDeviceToHost, v.stream));
+  if (mode == 1 && confs_out) GB_CUDA(cudaMemcpyAsync(confs_out, d_xo, (size_t)n * nx * 4, cudaMemcpyDeviceToHost, v.stream));
+  if (mode == 1 && evals) GB_CUDA(cudaMemcpyAsync(evals, d_ev, (size_t)n * 4, cudaMemcpyDeviceToHost, v.stream));
+  GB_CUDA(cudaStreamSynchronize(v.stream));
+  cudaFree(d_conf); cudaFree(d_e); cudaFree(d_g); cudaFree(d_c); cudaFree(d_xo); cudaFree(d_ev);
+  GBV_END
+}
+
+int gb_vina_eval_deriv(gb_vina* h, const float* confs, int n, const float* v3, float slope, float* e, float* change, float* coords) {
+  return dock_eval_common(h, confs, n, v3, slope, 0, 0, e, change, coords, nullptr, nullptr);
+}
+int gb_vina_bfgs(gb_vina* h, float* confs, int n, int maxiters, const float* v3, float slope, float* e, float* change, int32_t* n_evals) {
+  return dock_eval_common(h, confs, n, v3, slope, 1, maxiters, e, change, nullptr, confs, n_evals);
+}
+
+int gb_vina_mc(gb_vina* h, const gb_mc_params* P, const float* corner1, const float* corner2, const uint32_t* seeds, int n_chains,
+               float slope, float* out_e, float* out_conf, int32_t* n_out) {
+  GBV_BEGIN
+  GB_CHECK(h && P && corner1 && corner2 && seeds && out_e && out_conf && n_out && n_chains >= 0, "bad arguments");
+  GB_CHECK(P->num_saved_mins >= 1 && P->num_saved_mins <= 64, "num_saved_mins out of range (1..64)");
+  Vina& v = h->v;
+  GB_CUDA(cudaSetDevice(v.device));
+  check_dock_ready(v);
+  if (n_chains == 0) return GB_OK;
+  const int T = v.lig.n_seg - 1, nx = 7 + T, S = P->num_saved_mins, nh = std::max(v.lig.n_heavy, 1);
+  uint32_t* d_seeds; float *d_e, *d_c, *d_h; int* d_n;
+  GB_CUDA(cudaMalloc(&d_seeds, (size_t)n_chains * 4)); GB_CUDA(cudaMalloc(&d_e, (size_t)n_chains * S * 4));
+  GB_CUDA(cudaMalloc(&d_c, (size_t)n_chains * S * nx * 4)); GB_CUDA(cudaMalloc(&d_h, (size_t)n_chains * S * 3 * nh * 4));
+  GB_CUDA(cudaMalloc(&d_n, (size_t)n_chains * 4));
+  GB_CUDA(cudaMemcpyAsync(d_seeds, seeds, (size_t)n_chains * 4, cudaMemcpyHostToDevice, v.stream));
+  GB_CUDA(cudaMemsetAsync(d_e, 0, (size_t)n_chains * S * 4, v.stream));
+  GB_CUDA(cudaMemsetAsync(d_c, 0, (size_t)n_chains * S * nx * 4, v.stream));
+  DockField F;
+  make_field(v, slope, F);
+  McDev M{P->num_steps, P->maxiters, S, P->temperature, P->mutation_amplitude, P->min_rmsd, {P->hunt_cap[0], P->hunt_cap[1], P->hunt_cap[2]}};
+  dock_mc_kernel<<<(n_chains + kDkWarps - 1) / kDkWarps, 32 * kDkWarps, 0, v.stream>>>(lig_ptrs(v), F, M, corner1[0], corner1[1], corner1[2],
+                                                                                     corner2[0], corner2[1], corner2[2], d_seeds, n_chains, d_e,
+                                                                                     d_c, d_h, d_n);
+  GB_CUDA(cudaGetLastError());
+  GB_CUDA(cudaMemcpyAsync(out_e, d_e, (size_t)n_chains * S * 4, cudaMemcpyDeviceToHost, v.stream));
+  GB_CUDA(cudaMemcpyAsync(out_conf, d_c, (size_t)n_chains * S * nx * 4, cudaMemcpyDeviceToHost, v.stream));
+  GB_CUDA(cudaMemcpyAsync(n_out, d_n, (size_t)n_chains * 4, cudaMemcpyDeviceToHost, v.stream));
+  GB_CUDA(cudaStreamSynchronize(v.stream));
+  cudaFree(d_seeds); cudaFree(d_e); cudaFree(d_c); cudaFree(d_h); cudaFree(d_n);
   GBV_END
 }
 

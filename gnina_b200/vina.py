@@ -61,6 +61,48 @@ class VinaScorer:
         capi.check(capi.lib().gb_vina_score_exact(self._h, _fp(x), _ip(t), _ip(o), n, _fp(nt), v, _fp(e), _fp(a)))
         return e, a
 
+    # ---- docking inner loop -------------------------------------------------------------------------------------
+    def set_ligand(self, lig):
+        """lig: dict as gnina_b200.synth.make_flexible_ligand returns it (the fields of gb_ligand_topology)"""
+        k = lambda a, dt: np.ascontiguousarray(a, dt)
+        self._lig_keep = [k(lig["local_xyz"], np.float32), k(lig["types"], np.int32), k(lig["seg_parent"], np.int32),
+                          k(lig["seg_begin"], np.int32), k(lig["seg_end"], np.int32), k(lig["seg_rel_origin"], np.float32),
+                          k(lig["seg_rel_axis"], np.float32), k(lig["pair_a"], np.int32), k(lig["pair_b"], np.int32)]
+        a = self._lig_keep
+        t = capi.LigandTopology(len(a[1]), len(a[2]), len(a[7]), _fp(a[0]), _ip(a[1]), _ip(a[2]), _ip(a[3]), _ip(a[4]), _fp(a[5]),
+                                _fp(a[6]), _ip(a[7]), _ip(a[8]), float(lig["gyration_radius"]))
+        capi.check(capi.lib().gb_vina_set_ligand(self._h, C.byref(t)))
+        self.T, self.na = len(a[2]) - 1, len(a[1])
+
+    def eval_deriv(self, confs, v=(1000, 1000, 1000), slope=1e3, coords=False):
+        x = np.ascontiguousarray(confs, np.float32).reshape(-1, 7 + self.T)
+        n = len(x)
+        v = np.ascontiguousarray(v, np.float32)
+        e = np.empty(n, np.float32); g = np.empty((n, 6 + self.T), np.float32)
+        c = np.empty((n, self.na, 3), np.float32) if coords else None
+        capi.check(capi.lib().gb_vina_eval_deriv(self._h, _fp(x), n, _fp(v), slope, _fp(e), _fp(g), _fp(c)))
+        return (e, g, c) if coords else (e, g)
+
+    def bfgs(self, confs, maxiters, v=(1000, 1000, 1000), slope=1e3):
+        x = np.array(confs, np.float32).reshape(-1, 7 + self.T)
+        n = len(x)
+        v = np.ascontiguousarray(v, np.float32)
+        e = np.empty(n, np.float32); g = np.empty((n, 6 + self.T), np.float32); ne = np.empty(n, np.int32)
+        capi.check(capi.lib().gb_vina_bfgs(self._h, _fp(x), n, maxiters, _fp(v), slope, _fp(e), _fp(g), _ip(ne)))
+        return e, x, g, ne
+
+    def mc(self, seeds, corner1, corner2, num_steps, maxiters, num_saved_mins=20, temperature=1.2, amplitude=2.0, min_rmsd=0.5,
+           hunt_cap=(10, 1.5, 10), slope=1e3):
+        seeds = np.ascontiguousarray(seeds, np.uint32)
+        n = len(seeds)
+        P = capi.McParams(num_steps, maxiters, num_saved_mins, temperature, amplitude, min_rmsd, (C.c_float * 3)(*hunt_cap))
+        e = np.zeros((n, num_saved_mins), np.float32); x = np.zeros((n, num_saved_mins, 7 + self.T), np.float32)
+        no = np.zeros(n, np.int32)
+        c1, c2 = np.ascontiguousarray(corner1, np.float32), np.ascontiguousarray(corner2, np.float32)
+        capi.check(capi.lib().gb_vina_mc(self._h, C.byref(P), _fp(c1), _fp(c2), seeds.ctypes.data_as(C.POINTER(C.c_uint32)), n, slope,
+                                         _fp(e), _fp(x), _ip(no)))
+        return e, x, no
+
     def close(self):
         if self._h:
             capi.lib().gb_vina_destroy(self._h)

@@ -171,6 +171,49 @@ int gb_vina_cache_eval(gb_vina* h, const float* lig_xyz, const int32_t* lig_type
 int gb_vina_score_exact(gb_vina* h, const float* lig_xyz, const int32_t* lig_type, const int32_t* pose_offsets, int n_poses,
                         const float* num_tors, float v, float* e_inter, float* affinity);
 
+/* ---- docking inner loop: conformation -> energy/gradient, BFGS, Monte-Carlo chains (one warp per chain) --------
+ * The ligand as gnina's model holds it (lib/tree.h, lib/model.h): atoms in the local frame of their torsion-tree
+ * segment; segment 0 = rigid root (rigid_body), segments 1.. = torsion segments in DFS pre-order, which is also the
+ * order of conf.torsions (heterotree::set_conf, lib/tree.h:361-366); relative origin/axis as segment's ctor stores
+ * them (lib/tree.h:208-216); intramolecular interacting pairs (lib/interacting_pairs.h:7-19) and gyration radius
+ * (lib/model.cpp:1002-1014).  conf = position[3], orientation quaternion[4] (a,b,c,d), torsions[n_segments-1];
+ * change = force[3], torque[3], torsion derivatives. */
+typedef struct {
+  int32_t n_atoms, n_segments, n_pairs;
+  const float* local_xyz;        /* [n_atoms][3] */
+  const int32_t* smina_type;     /* [n_atoms]    */
+  const int32_t* seg_parent;     /* [n_segments], -1 for the root */
+  const int32_t* seg_atom_begin; /* [n_segments] */
+  const int32_t* seg_atom_end;
+  const float* seg_rel_origin;   /* [n_segments][3] */
+  const float* seg_rel_axis;     /* [n_segments][3] */
+  const int32_t* pair_a;         /* [n_pairs] */
+  const int32_t* pair_b;
+  float gyration_radius;
+} gb_ligand_topology;
+/* monte_carlo members (lib/monte_carlo.h:29-41): defaults temperature 1.2, hunt_cap (10, 1.5, 10), min_rmsd 0.5,
+ * num_saved_mins 50, mutation_amplitude 2; num_steps and maxiters as main/main.cpp:442-457 derives them. */
+typedef struct {
+  int32_t num_steps, maxiters, num_saved_mins;
+  float temperature, mutation_amplitude, min_rmsd;
+  float hunt_cap[3];
+} gb_mc_params;
+
+int gb_vina_set_ligand(gb_vina* h, const gb_ligand_topology* lig); /* <= 96 atoms, <= 32 segments */
+/* model::eval_deriv with ig = cache (lib/model.cu:202-225): e[n], change[n][6+T], coords[n][n_atoms][3] (nullable).
+ * v3 = the curl caps (ligand pairs, grid, other pairs), slope = out-of-box penalty slope of the cache. */
+int gb_vina_eval_deriv(gb_vina* h, const float* confs, int n, const float* v3, float slope, float* e, float* change,
+                       float* coords);
+/* quasi_newton::operator() -> bfgs with fast_line_search (lib/quasi_newton.cpp:49-83, lib/bfgs.h:358-502), n
+ * independent minimisations; confs are updated in place. */
+int gb_vina_bfgs(gb_vina* h, float* confs, int n, int maxiters, const float* v3, float slope, float* e, float* change,
+                 int32_t* n_evals);
+/* parallel_mc::operator() / monte_carlo::operator() (lib/parallel_mc.cpp:183-214, lib/monte_carlo.cpp:99-148): n_chains
+ * independent Monte-Carlo chains (seeds as parallel_mc draws them, :197-199), each returning up to num_saved_mins
+ * RMSD-distinct minima sorted by energy: out_e[n_chains][S], out_conf[n_chains][S][7+T], n_out[n_chains]. */
+int gb_vina_mc(gb_vina* h, const gb_mc_params* params, const float* corner1, const float* corner2, const uint32_t* seeds,
+               int n_chains, float slope, float* out_e, float* out_conf, int32_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif
