@@ -92,6 +92,41 @@ def main():
     cpu = kk / (time.perf_counter() - t0)
     out.append({"row": "vina_exact_affinity (V12)", "value": nv / dt, "unit": "poses/s", "cpu_oracle": cpu,
                 "cpu_sample": "%d poses, scalar C" % kk, "note": "includes H2D of the poses and D2H of the energies"})
+    # --- docking inner loop (V6-V11): one warp per conformation / chain ---
+    from oracle.vina_mc import DockOracle
+    lig = synth.make_flexible_ligand()
+    needed2 = sorted(set(int(t) for t in lig["types"] if t > 1))
+    v.cache_build(begin, end, ng, needed2)
+    v.set_ligand(lig)
+    d = DockOracle(o, {t: v.cache_grid(t) for t in needed2}, begin, end, ng, lig)
+    X = np.stack([d.random_conf(1 + i, [-6, -6, -6], [6, 6, 6])[0] for i in range(512)])
+    Xb = np.tile(X, (64, 1))                                     # 32768 conformations
+    dt = timed(lambda: v.eval_deriv(Xb), reps=3)
+    t0 = time.perf_counter()
+    for x in X[:200]:
+        d.eval_deriv(x)
+    cpu = 200 / (time.perf_counter() - t0)
+    out.append({"row": "dock_eval_deriv (V5+V6+V7+V8)", "value": len(Xb) / dt, "unit": "eval_deriv/s", "cpu_oracle": cpu,
+                "cpu_sample": "200 conformations, scalar C", "ligand": "27 heavy atoms, 6 torsions, %d pairs" % len(lig["pair_a"])})
+    res = {}
+    def run_bfgs():
+        res["ne"] = v.bfgs(Xb[:8192], 12)[3]
+    dt = timed(run_bfgs, reps=2)
+    t0 = time.perf_counter()
+    ner = sum(d.bfgs(x, 12)[3] for x in X[:40])
+    cdt = time.perf_counter() - t0
+    out.append({"row": "dock_bfgs 12 iterations (V9)", "value": 8192 / dt, "unit": "minimisations/s",
+                "device_eval_deriv_per_s": float(res["ne"].sum()) / dt, "cpu_oracle": 40 / cdt, "cpu_eval_deriv_per_s": ner / cdt})
+    n_chains, steps = 4096, 40
+    seeds = (np.arange(1, n_chains + 1, dtype=np.uint32) * 2654435761) & 0xFFFFFFFF
+    dt = timed(lambda: v.mc(seeds, [-6, -6, -6], [6, 6, 6], steps, 12, 8), reps=1)
+    t0 = time.perf_counter()
+    for c in range(3):
+        d.mc(int(seeds[c]), [-6, -6, -6], [6, 6, 6], steps, 12, 8)
+    cpu = 3 * steps / (time.perf_counter() - t0)
+    out.append({"row": "dock_monte_carlo chains (V10+V11)", "value": n_chains * steps / dt, "unit": "MC steps/s",
+                "chains": n_chains, "steps_per_chain": steps, "ligands_per_s_at_exhaustiveness_64": n_chains / 64 / dt,
+                "cpu_oracle": cpu, "cpu_sample": "3 chains, scalar C, 1 thread"})
     for r in out:
         print(json.dumps(r))
 
