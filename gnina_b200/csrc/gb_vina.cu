@@ -59,6 +59,13 @@ struct Vina {
   std::vector<float> h_fast, h_se, h_sd;  // [pair][n]
   float* d_fast = nullptr;
   float2* d_smooth = nullptr;  // [pair][n] (e, dor) for eval_deriv
+  // precalculate_splines (V3): n_sp intervals per pair, coefficients (a,b,c,d); valid = some knot is non-zero
+  int n_sp = 0;
+  float sp_fraction = 0.f;
+  std::vector<float4> h_sp;
+  std::vector<unsigned char> h_sp_valid;
+  float4* d_sp = nullptr;
+  int use_splines = 0;
   // ligand topology for the docking inner loop (gb_vina_set_ligand)
   struct LigDev {
     int n_atoms = 0, n_seg = 0, n_pairs = 0, max_depth = 0, n_heavy = 0;
@@ -84,7 +91,7 @@ struct Vina {
   ~Vina() {
     cudaSetDevice(device);
     if (stream) cudaStreamDestroy(stream);
-    cudaFree(d_fast); cudaFree(d_smooth); cudaFree(d_rec);
+    cudaFree(d_fast); cudaFree(d_smooth); cudaFree(d_sp); cudaFree(d_rec);
     cudaFree(lig.local); cudaFree(lig.atom_seg); cudaFree(lig.seg); cudaFree(lig.seg_rel_origin); cudaFree(lig.seg_rel_axis);
     cudaFree(lig.pairs); cudaFree(d_lig); cudaFree(d_off); cudaFree(d_atom_e); cudaFree(d_deriv);
     cudaFree(d_pose_e); cudaFree(d_tors);
@@ -124,6 +131,48 @@ static void build_tables(Vina& v) {
     for (size_t i = 0; i < sm.size(); i++) sm[i] = make_float2(v.h_se[i], v.h_sd[i]);
     GB_CUDA(cudaMalloc(&v.d_smooth, sm.size() * sizeof(float2)));
     GB_CUDA(cudaMemcpy(v.d_smooth, sm.data(), sm.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  }
+  {  // V3: Spline::initialize (lib/splines.h:38-97) for every pair: knots i*fraction (i < n) + (cutoff, 0), zero end
+     // slopes; the tridiagonal system is solved with the Thomas algorithm in double (the reference inverts it densely
+     // in float with Eigen), coefficients stored as float like SplineData
+    const float cutoff = 8.f, spf = 10.f;  // --minimize uses factor 10 (main/main.cpp:1162-1165)
+    const int nsp = (int)(unsigned)(spf * cutoff);
+    v.n_sp = nsp; v.sp_fraction = cutoff / (float)nsp;
+    v.h_sp.assign((size_t)npairs * nsp, make_float4(0, 0, 0, 0));
+    v.h_sp_valid.assign(npairs, 0);
+    std::vector<double> y(nsp + 1), C(nsp + 1), dg(nsp + 1), up(nsp + 1), lo(nsp + 1), dd(nsp + 1);
+    std::vector<float> xs(nsp + 1);
+    for (int t2 = 0; t2 < kNumSminaTypes; t2++)
+      for (int t1 = 0; t1 <= t2; t1++) {
+        bool nonzero = false;
+        for (int i = 0; i < nsp; i++) {
+          xs[i] = i * v.sp_fraction;
+          const float val = eval_terms(pr, v.w, t1, t2, xs[i]);
+          y[i] = val;
+          nonzero |= val != 0;
+        }
+        xs[nsp] = cutoff; y[nsp] = 0;
+        const int pi = tri_index(t1, t2), e = nsp;
+        v.h_sp_valid[pi] = nonzero;
+        if (!nonzero) continue;
+        const double fr = (double)(float)(xs[1] - xs[0]), hlast = (double)(float)(xs[e] - xs[e - 1]);
+        for (int j2 = 0; j2 <= e; j2++) {
+          const double hj = (j2 == e - 1) ? hlast : fr;
+          if (j2 == 0) { lo[j2] = 0; dg[j2] = 2 * fr; up[j2] = fr; C[j2] = 6 * ((y[1] - y[0]) / fr); }
+          else if (j2 == e) { lo[j2] = hlast; dg[j2] = 2 * hlast; up[j2] = 0; C[j2] = 6 * (-(y[e] - y[e - 1]) / hlast); }
+          else { lo[j2] = hj; dg[j2] = 2 * (fr + hj); up[j2] = hj; C[j2] = 6 * ((y[j2 + 1] - y[j2]) / hj - (y[j2] - y[j2 - 1]) / fr); }
+        }
+        for (int j2 = 1; j2 <= e; j2++) { const double mm = lo[j2] / dg[j2 - 1]; dg[j2] -= mm * up[j2 - 1]; C[j2] -= mm * C[j2 - 1]; }
+        dd[e] = C[e] / dg[e];
+        for (int j2 = e - 1; j2 >= 0; j2--) dd[j2] = (C[j2] - up[j2] * dd[j2 + 1]) / dg[j2];
+        for (int i = 0; i < e; i++) {
+          const double hi = (i == e - 1) ? hlast : fr;
+          v.h_sp[(size_t)pi * nsp + i] = make_float4((float)((dd[i + 1] - dd[i]) / (6 * hi)), (float)(dd[i] / 2),
+                                                     (float)((y[i + 1] - y[i]) / hi - dd[i + 1] * hi / 6 - dd[i] * hi / 3), (float)y[i]);
+        }
+      }
+    GB_CUDA(cudaMalloc(&v.d_sp, v.h_sp.size() * sizeof(float4)));
+    GB_CUDA(cudaMemcpy(v.d_sp, v.h_sp.data(), v.h_sp.size() * sizeof(float4), cudaMemcpyHostToDevice));
   }
   GB_CUDA(cudaMemcpyToSymbol(c_props, &pr, sizeof(pr)));
   GB_CUDA(cudaMemcpyToSymbol(c_w, v.w, sizeof(v.w)));
@@ -491,7 +540,7 @@ struct LigPtrs {
   float gyration_radius;
   const float4* local; const int* atom_seg; const int4* seg; const float4* rel_origin; const float4* rel_axis; const int2* pairs;
 };
-struct DockField { GridGeom G; GridPtrs gp; const float2* smooth; int n_samples; float factor, slope; };
+struct DockField { GridGeom G; GridPtrs gp; const float2* smooth; int n_samples; float factor, slope; const float4* sp; int n_sp; float sp_fraction; };
 
 struct WarpWs {  // per-warp shared-memory workspace
   float coords[kDkMaxAtoms * 3];
@@ -626,13 +675,24 @@ __device__ float dk_eval_deriv(const LigPtrs& L, const DockField& F, WarpWs& W, 
     if (r2 < 64.f) {
       int t1 = (int)L.local[pr.x].w, t2 = (int)L.local[pr.y].w;
       if (t1 > t2) { const int tt = t1; t1 = t2; t2 = tt; }
-      const float r2f = F.factor * r2;
-      const int i1 = (int)r2f;
-      const float rem = r2f - i1;
-      const float2* tb = F.smooth + (size_t)(t1 + t2 * (t2 + 1) / 2) * F.n_samples;
-      const float2 s1 = tb[i1], s2 = tb[i1 + 1];
-      float pe = s1.x + rem * (s2.x - s1.x);
-      const float dor = s1.y + rem * (s2.y - s1.y);
+      float pe, dor;
+      if (F.sp) {  // precalculate_splines::eval_deriv (a pair whose knots are all zero has all-zero coefficients)
+        const float r = sqrtf(r2);
+        int idx = (int)(r / F.sp_fraction);
+        if (idx >= F.n_sp) idx = F.n_sp - 1;
+        const float4 c = F.sp[(size_t)(t1 + t2 * (t2 + 1) / 2) * F.n_sp + idx];
+        const float lx = r - idx * F.sp_fraction;
+        pe = ((c.x * lx + c.y) * lx + c.z) * lx + c.w;
+        dor = ((3 * c.x * lx + 2 * c.y) * lx + c.z) / r;
+      } else {
+        const float r2f = F.factor * r2;
+        const int i1 = (int)r2f;
+        const float rem = r2f - i1;
+        const float2* tb = F.smooth + (size_t)(t1 + t2 * (t2 + 1) / 2) * F.n_samples;
+        const float2 s1 = tb[i1], s2 = tb[i1 + 1];
+        pe = s1.x + rem * (s2.x - s1.x);
+        dor = s1.y + rem * (s2.y - s1.y);
+      }
       float fx = dor * rx, fy = dor * ry, fz = dor * rz;
       if (pe > 0 && v[0] < 0.1f * 3.402823466e+38f) {
         const float tmp = (v[0] < 1.1920929e-07f) ? 0.f : (v[0] / (v[0] + pe));
@@ -959,6 +1019,7 @@ static void make_field(const Vina& v, float slope, DockField& F) {
   }
   for (int t = 0; t < kNumSminaTypes; t++) F.gp.g[t] = v.d_grids[t];
   F.smooth = v.d_smooth; F.n_samples = v.n; F.factor = v.factor; F.slope = slope;
+  F.sp = v.use_splines ? v.d_sp : nullptr; F.n_sp = v.n_sp; F.sp_fraction = v.sp_fraction;
 }
 static LigPtrs lig_ptrs(const Vina& v) {
   const auto& l = v.lig;
@@ -972,6 +1033,21 @@ static void check_dock_ready(const Vina& v) {
 }
 
 extern "C" {
+
+int gb_vina_set_precalc(gb_vina* h, int use_splines) {
+  GBV_BEGIN
+  GB_CHECK(h, "null argument");
+  h->v.use_splines = use_splines ? 1 : 0;
+  GBV_END
+}
+int gb_vina_spline_size(const gb_vina* h) { return h ? h->v.n_sp : 0; }
+int gb_vina_spline_table(const gb_vina* h, int t1, int t2, float* abcd) {
+  GBV_BEGIN
+  GB_CHECK(h && abcd && t1 >= 0 && t2 >= 0 && t1 < kNumSminaTypes && t2 < kNumSminaTypes, "bad type");
+  if (t1 > t2) std::swap(t1, t2);
+  memcpy(abcd, &h->v.h_sp[(size_t)tri_index(t1, t2) * h->v.n_sp], sizeof(float4) * h->v.n_sp);
+  GBV_END
+}
 
 int gb_vina_set_ligand(gb_vina* h, const gb_ligand_topology* t) {
   GBV_BEGIN

@@ -61,6 +61,15 @@ class VinaScorer:
         capi.check(capi.lib().gb_vina_score_exact(self._h, _fp(x), _ip(t), _ip(o), n, _fp(nt), v, _fp(e), _fp(a)))
         return e, a
 
+    def spline_table(self, t1, t2):
+        n = capi.lib().gb_vina_spline_size(self._h)
+        out = np.empty((n, 4), np.float32)
+        capi.check(capi.lib().gb_vina_spline_table(self._h, t1, t2, _fp(out)))
+        return out
+
+    def set_precalc(self, use_splines):
+        capi.check(capi.lib().gb_vina_set_precalc(self._h, int(bool(use_splines))))
+
     # ---- docking inner loop -------------------------------------------------------------------------------------
     def set_ligand(self, lig):
         """lig: dict as gnina_b200.synth.make_flexible_ligand returns it (the fields of gb_ligand_topology)"""

@@ -200,6 +200,13 @@ typedef struct {
 } gb_mc_params;
 
 int gb_vina_set_ligand(gb_vina* h, const gb_ligand_topology* lig); /* <= 96 atoms, <= 32 segments */
+/* precalculate_splines (lib/precalculate.h:380-449, lib/splines.h:22-138; factor 10 -> 80 intervals per type pair, what
+ * --minimize uses, main/main.cpp:1162-1165).  gb_vina_spline_table: the (a,b,c,d) coefficients of one pair
+ * [gb_vina_spline_size()][4]; gb_vina_set_precalc(h, 1) makes the intramolecular pair terms of eval_deriv / bfgs / mc use
+ * the splines instead of the linear tables. */
+int gb_vina_spline_size(const gb_vina* h);
+int gb_vina_spline_table(const gb_vina* h, int t1, int t2, float* abcd);
+int gb_vina_set_precalc(gb_vina* h, int use_splines);
 /* model::eval_deriv with ig = cache (lib/model.cu:202-225): e[n], change[n][6+T], coords[n][n_atoms][3] (nullable).
  * v3 = the curl caps (ligand pairs, grid, other pairs), slope = out-of-box penalty slope of the cache. */
 int gb_vina_eval_deriv(gb_vina* h, const float* confs, int n, const float* v3, float slope, float* e, float* change,

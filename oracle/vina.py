@@ -45,6 +45,27 @@ class VinaOracle:
         except Exception:
             pass
 
+    def splines(self, factor=10.0):
+        L = lib()
+        L.gvo_splines_create.argtypes = [_vp, C.c_float]; L.gvo_splines_create.restype = _vp
+        L.gvo_splines_n.argtypes = [_vp]
+        L.gvo_splines_table.argtypes = [_vp, C.c_int, C.c_int, _fp]
+        L.gvo_splines_eval_deriv.argtypes = [_vp, C.c_int, C.c_int, C.c_float, _fp, _fp]
+        if not hasattr(self, "_sp"):
+            self._sp = L.gvo_splines_create(self.p, factor)
+        return self._sp
+
+    def spline_table(self, t1, t2):
+        sp = self.splines()
+        out = np.empty((lib().gvo_splines_n(sp), 4), np.float32)
+        lib().gvo_splines_table(sp, t1, t2, _f(out))
+        return out
+
+    def spline_eval_deriv(self, t1, t2, r2):
+        e, d = C.c_float(), C.c_float()
+        lib().gvo_splines_eval_deriv(self.splines(), t1, t2, r2, C.byref(e), C.byref(d))
+        return e.value, d.value
+
     def table(self, t1, t2):
         a, b, c = (np.empty(self.n, np.float32) for _ in range(3))
         lib().gvo_prec_table(self.p, t1, t2, _f(a), _f(b), _f(c))

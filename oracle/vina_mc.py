@@ -14,7 +14,7 @@ class _Lig(C.Structure):
 
 
 class _Field(C.Structure):
-    _fields_ = [("grids", C.POINTER(_fp)), ("begin", _fp), ("end", _fp), ("n", _ip), ("slope", C.c_float), ("prec", _vp)]
+    _fields_ = [("grids", C.POINTER(_fp)), ("begin", _fp), ("end", _fp), ("n", _ip), ("slope", C.c_float), ("prec", _vp), ("splines", _vp)]
 
 
 class _McParams(C.Structure):
@@ -48,11 +48,15 @@ class DockOracle:
         self.ptrs = (_fp * 28)()
         for t, g in grids.items():
             self.ptrs[t] = _f(k(g, np.float32))
-        self.field = _Field(self.ptrs, _f(k(begin, np.float32)), _f(k(end, np.float32)), _i(k(n, np.int32)), slope, vina_oracle.p)
+        self.field = _Field(self.ptrs, _f(k(begin, np.float32)), _f(k(end, np.float32)), _i(k(n, np.int32)), slope, vina_oracle.p, None)
         self.vo = vina_oracle
         self.T = len(lig["seg_parent"]) - 1
         self.na = len(lig["types"])
         self.gr = lig["gyration_radius"]
+
+    def use_splines(self, on=True):
+        """precalculate_splines (factor 10) for the intramolecular pair terms instead of precalculate_linear"""
+        self.field.splines = self.vo.splines() if on else None
 
     def coords(self, conf):
         conf = np.ascontiguousarray(conf, np.float32)

@@ -22,6 +22,8 @@
 
 typedef struct gvo_prec gvo_prec; /* vina_ref.c */
 void gvo_prec_eval_deriv(const gvo_prec *p, int t1, int t2, float r2, float *e, float *dor);
+typedef struct gvo_splines gvo_splines;
+void gvo_splines_eval_deriv(const gvo_splines *s, int t1, int t2, float r2, float *e, float *dor);
 float gvo_grid_evaluate(const float *data, const float *begin, const float *end, const int32_t *n, const float *loc,
                         float slope, float v, float *deriv);
 
@@ -41,6 +43,7 @@ typedef struct {
   const int32_t *n;
   float slope;
   const gvo_prec *prec;
+  const gvo_splines *splines; /* NULL: precalculate_linear ; else precalculate_splines for the pair terms */
 } gvo_field;
 
 #define PI_F 3.14159265358979323846f
@@ -169,7 +172,8 @@ float gvo_lig_eval_deriv(const gvo_field *F, const gvo_lig *L, const float *conf
     float r2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
     if (r2 < 64.f) {
       float pe, dor, f[3];
-      gvo_prec_eval_deriv(F->prec, L->type[a], L->type[b], r2, &pe, &dor);
+      if (F->splines) gvo_splines_eval_deriv(F->splines, L->type[a], L->type[b], r2, &pe, &dor);
+      else gvo_prec_eval_deriv(F->prec, L->type[a], L->type[b], r2, &pe, &dor);
       for (int q = 0; q < 3; q++) f[q] = dor * r[q];
       if (pe > 0 && v[0] < 0.1f * kMax) { float tmp = (v[0] < kEps) ? 0 : (v[0] / (v[0] + pe)); pe *= tmp; for (int q = 0; q < 3; q++) f[q] *= tmp * tmp; }
       ie += pe;

@@ -252,3 +252,83 @@ float gvo_num_tors_div(const gvo_prec *p, float e, float num_tors) { /* everythi
   if (fabsf(y) < kEps) return (e * y > 0) ? kMaxFl : -kMaxFl;
   return e / y;
 }
+
+/* ---- V3: precalculate_splines (lib/precalculate.h:380-449) + Spline (lib/splines.h:22-138) ---------------------
+ * n = factor*cutoff intervals (factor 10 for --minimize, main/main.cpp:1162-1165): points (i*fraction, E(i*fraction))
+ * for i < n plus (cutoff, 0); natural-to-clamped cubic spline with zero first derivative at both ends.  The reference
+ * inverts the (tridiagonal, symmetric for even spacing) system densely with Eigen in float; here it is solved with
+ * the Thomas algorithm in double and the coefficients are rounded to float (difference: float round-off of the
+ * reference's inverse).  eval_deriv returns (value, d/dr divided by r). */
+typedef struct gvo_splines { int n; float cutoff, fraction; float *abcd; /* [pair][n][4] */ unsigned char *valid; } gvo_splines;
+
+gvo_splines *gvo_splines_create(const gvo_prec *p, float factor) {
+  gvo_splines *s = (gvo_splines *)calloc(1, sizeof(gvo_splines));
+  s->cutoff = 8.f;
+  s->n = (int)(unsigned)(factor * s->cutoff);
+  s->fraction = s->cutoff / (float)s->n;
+  const int n = s->n, npairs = NT * (NT + 1) / 2, np = n + 1;
+  s->abcd = (float *)calloc((size_t)npairs * n * 4, sizeof(float));
+  s->valid = (unsigned char *)calloc(npairs, 1);
+  double *y = (double *)malloc(sizeof(double) * np), *C = (double *)malloc(sizeof(double) * np), *dg = (double *)malloc(sizeof(double) * np),
+         *up = (double *)malloc(sizeof(double) * np), *lo = (double *)malloc(sizeof(double) * np), *dd = (double *)malloc(sizeof(double) * np);
+  float *xs = (float *)malloc(sizeof(float) * np);
+  for (int t2 = 0; t2 < NT; t2++)
+    for (int t1 = 0; t1 <= t2; t1++) {
+      int nonzero = 0;
+      for (int i = 0; i < n; i++) {
+        xs[i] = i * s->fraction;
+        float v = gvo_eval_terms(p->w, t1, t2, xs[i]);
+        y[i] = v;
+        if (v != 0) nonzero = 1;
+      }
+      xs[n] = s->cutoff; y[n] = 0;
+      const int pi = tri_index(t1, t2);
+      s->valid[pi] = (unsigned char)nonzero;
+      if (!nonzero) continue;
+      const int e = n;
+      const double fr = (double)(float)(xs[1] - xs[0]), hlast = (double)(float)(xs[e] - xs[e - 1]);
+      /* row vector ddy * A = C with A(i-1,i) = hi, A(i,i) = 2(fr+hi), A(i+1,i) = hi  (columns i = 1..e-1),
+       * A(0,0) = 2 fr, A(1,0) = fr, A(e,e) = 2 hlast, A(e-1,e) = hlast.  Equation of column j:
+       *   ddy(j-1) A(j-1,j) + ddy(j) A(j,j) + ddy(j+1) A(j+1,j) = C(j) */
+      for (int j = 0; j <= e; j++) {
+        double hj = (j == e - 1) ? hlast : fr;
+        if (j == 0) { lo[j] = 0; dg[j] = 2 * fr; up[j] = fr; C[j] = 6 * ((y[1] - y[0]) / fr); }
+        else if (j == e) { lo[j] = hlast; dg[j] = 2 * hlast; up[j] = 0; C[j] = 6 * (-(y[e] - y[e - 1]) / hlast); }
+        else { lo[j] = hj; dg[j] = 2 * (fr + hj); up[j] = hj; C[j] = 6 * ((y[j + 1] - y[j]) / hj - (y[j] - y[j - 1]) / fr); }
+      }
+      /* Thomas */
+      for (int j = 1; j <= e; j++) { double m = lo[j] / dg[j - 1]; dg[j] -= m * up[j - 1]; C[j] -= m * C[j - 1]; }
+      dd[e] = C[e] / dg[e];
+      for (int j = e - 1; j >= 0; j--) dd[j] = (C[j] - up[j] * dd[j + 1]) / dg[j];
+      for (int i = 0; i < e; i++) {
+        double hi = (i == e - 1) ? hlast : fr;
+        float *o = s->abcd + ((size_t)pi * n + i) * 4;
+        o[0] = (float)((dd[i + 1] - dd[i]) / (6 * hi));
+        o[1] = (float)(dd[i] / 2);
+        o[2] = (float)((y[i + 1] - y[i]) / hi - dd[i + 1] * hi / 6 - dd[i] * hi / 3);
+        o[3] = (float)y[i];
+      }
+    }
+  free(y); free(C); free(dg); free(up); free(lo); free(dd); free(xs);
+  return s;
+}
+void gvo_splines_free(gvo_splines *s) { if (s) { free(s->abcd); free(s->valid); free(s); } }
+int gvo_splines_n(const gvo_splines *s) { return s->n; }
+void gvo_splines_table(const gvo_splines *s, int t1, int t2, float *abcd) {
+  if (t1 > t2) { int t = t1; t1 = t2; t2 = t; }
+  memcpy(abcd, s->abcd + (size_t)tri_index(t1, t2) * s->n * 4, sizeof(float) * 4 * s->n);
+}
+/* precalculate_splines::eval_deriv: (value, derivative / r) at r = sqrt(r2) */
+void gvo_splines_eval_deriv(const gvo_splines *s, int t1, int t2, float r2, float *e, float *dor) {
+  if (t1 > t2) { int t = t1; t1 = t2; t2 = t; }
+  const int pi = tri_index(t1, t2);
+  const float r = sqrtf(r2);
+  *e = 0; *dor = 0;
+  if (!s->valid[pi] || r >= s->cutoff) return;
+  unsigned index = (unsigned)(r / s->fraction);
+  if ((int)index >= s->n) index = s->n - 1;
+  const float *c = s->abcd + ((size_t)pi * s->n + index) * 4;
+  const float lx = r - index * s->fraction; /* SplineData.x = points[i].first = i*fraction */
+  *e = ((c[0] * lx + c[1]) * lx + c[2]) * lx + c[3];
+  *dor = ((3 * c[0] * lx + 2 * c[1]) * lx + c[2]) / r;
+}

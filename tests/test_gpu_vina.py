@@ -78,3 +78,29 @@ def test_exact_final_score_matches_oracle(system):
     assert v.score_exact(np.zeros((0, 3), np.float32), np.zeros(0, np.int32), [0])[0].shape == (0,)
     eh, _ = v.score_exact(lx[:2], np.array([1, 0], np.int32), [0, 2])
     assert eh[0] == 0.0
+
+
+def test_spline_tables_and_spline_pair_terms_match_oracle():
+    """V3: precalculate_splines coefficients equal the oracle's; eval_deriv with the spline pair terms matches too"""
+    from gnina_b200 import synth
+    from gnina_b200.vina import VinaScorer
+    from oracle.vina import VinaOracle
+    from oracle.vina_mc import DockOracle
+    v, o = VinaScorer(), VinaOracle()
+    for t1, t2 in ((2, 2), (2, 13), (7, 13), (12, 12), (4, 17)):
+        a, b = v.spline_table(t1, t2), o.spline_table(t1, t2)
+        assert a.shape == b.shape == (80, 4) and np.abs(a - b).max() <= 1e-6 * max(1.0, np.abs(b).max())
+    rx, rt = synth.make_receptor(700, box=32)
+    lig = synth.make_flexible_ligand()
+    begin, end, n = [-9.0] * 3, [9.0] * 3, [48, 48, 48]
+    needed = sorted(set(int(t) for t in lig["types"] if t > 1))
+    v.set_receptor(rx, rt); v.cache_build(begin, end, n, needed); v.set_ligand(lig)
+    d = DockOracle(o, {t: v.cache_grid(t) for t in needed}, begin, end, n, lig)
+    X = np.stack([d.random_conf(50 + i, [-3, -3, -3], [3, 3, 3])[0] for i in range(16)])
+    e_lin, _ = v.eval_deriv(X)
+    v.set_precalc(True); d.use_splines(True)
+    e, g = v.eval_deriv(X)
+    assert np.abs(e - e_lin).max() > 0           # the spline tables are really in use
+    for i, x in enumerate(X):
+        er, gr = d.eval_deriv(x)
+        assert abs(e[i] - er) <= 2e-5 * max(1.0, abs(er)) and np.abs(g[i] - gr).max() <= 2e-4 * max(1.0, np.abs(gr).max())

@@ -99,3 +99,20 @@ def test_final_scoring_pieces():
     w = 0.1 * (W[5] + 1)
     assert abs(o.num_tors_div(-7.5, 4.0) - (-7.5 / (1 + w * 4.0 / 5.0))) < 1e-6
     assert o.num_tors_div(0.0, 3.0) == 0.0
+
+
+def test_splines_interpolate_the_terms_with_zero_end_slopes():
+    o = VinaOracle()
+    tab = o.spline_table(2, 13)
+    assert tab.shape == (80, 4)
+    for i in (0, 17, 33, 38, 60):           # knots are reproduced, derivative tracks the exact terms
+        r = i * 0.1
+        e, dor = o.spline_eval_deriv(2, 13, r * r if i else 1e-12)
+        assert abs(e - o.exact(2, 13, r * r)) < 2e-6 * max(1.0, abs(e))
+    assert abs(tab[0, 2]) < 1e-5             # zero first derivative at r = 0 (c coefficient of the first interval)
+    r = 4.41
+    e, dor = o.spline_eval_deriv(13, 2, r * r)
+    h = 1e-3
+    num = (o.exact(2, 13, (r + h) ** 2) - o.exact(2, 13, (r - h) ** 2)) / (2 * h) / r
+    assert abs(e - o.exact(2, 13, r * r)) < 1e-5 and abs(dor - num) < 1e-4
+    assert o.spline_eval_deriv(2, 13, 64.0) == (0.0, 0.0)
