@@ -30,6 +30,9 @@ sys.path.insert(0, ROOT)
 MODEL = "crossdock_default2018"
 FLOP_PER_EVAL = {"default2018": 0.998148096e9, "dense": 4.541571072e9, "default2017": 1.122729984e9}
 CONV1_FLOP = 668_860_416.0  # conv3^3 28->32 @24^3
+# dram__bytes_read.sum + dram__bytes_write.sum of the conv1 launch, ncu --set full, 1024 poses per launch
+# (profiles/r1e_ncu_conv1_tcgen05.csv: 1.095620 GB + 0.863929 GB) -> per pose
+CONV1_NCU_DRAM_BYTES_PER_POSE = (1.095620e9 + 0.863929e9) / 1024
 
 
 def peaks():
@@ -311,7 +314,10 @@ def main():
         flops = CONV1_FLOP * args.poses * args.steps
         ach = flops / (tot_ms * 1e-3) / 1e12
         roof = {"kernel": k, "bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s",
-                "frac": ach / tf_sus, "traffic": None, "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json)" % which,
+                "frac": ach / tf_sus,
+                "traffic": (CONV1_NCU_DRAM_BYTES_PER_POSE * args.poses * args.steps / max(cnt, 1)) if k.startswith("tc_conv1") else None,
+                "traffic_unit": "DRAM bytes per launch (ncu capture profiles/r1e_ncu_conv1_tcgen05.csv, scaled by poses per launch)",
+                "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json)" % which,
                 "launches": cnt, "avg_launch_ms": tot_ms / max(cnt, 1)}
     total_ms = sum(v[0] for v in prof.values())
     shares = {k: round(v[0] / total_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])} if total_ms else {}
