@@ -658,7 +658,9 @@ int gb_cnn_score_grad(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, 
   h->d_aff.ensure((size_t)M * n);
   h->d_loss.ensure((size_t)M * n);
   h->d_final.ensure(4 * (size_t)n);
-  const int chunk = h->max_batch > 0 ? std::min(h->max_batch, 8) : 8;
+  // precision "fp16": forward AND backward on the tensor-core path (gb_cnn_tc_grad.cu); "fp32": validation kernels
+  const bool fast = h->precision != GB_PRECISION_FP32;
+  const int chunk = fast ? (h->max_batch > 0 ? h->max_batch : 1024) : (h->max_batch > 0 ? std::min(h->max_batch, 8) : 8);
   h->d_out3.ensure(3 * (size_t)std::max(chunk, chunk_size(h)));
   for (auto& Gp : h->groups) {
     GridGroup& G = *Gp;
@@ -670,23 +672,41 @@ int gb_cnn_score_grad(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, 
     const int nb = std::min(chunk, n - p0);
     for (auto& Gp : h->groups) {
       GridGroup& G = *Gp;
-      voxelize_chunk_f32(h, G, p0, nb);
-      const int npts = (int)std::lround(G.sig.dimension / G.sig.resolution) + 1;
-      h->d_dgrid.ensure((size_t)nb * G.n_channels * npts * npts * npts);
       tmp_grad.ensure(3 * (size_t)std::max(G.n_staged_atoms, 1));
+      const int npts = (int)std::lround(G.sig.dimension / G.sig.resolution) + 1;
+      TcPoseBatch pb{G.rec_xyzr.p, G.rec_ch.p, G.n_rec, G.lig_xyzr.p, G.lig_ch.p, G.lig_off.p + p0,
+                     h->d_centers.p + 3 * (size_t)p0, nb, G.max_pose_atoms, G.n_channels, G.rec.n_channels,
+                     G.sig.resolution, G.sig.dimension};
+      if (fast) {
+        TcGridWorkspace& gw = G.tc_grid;
+        h->launches += tc_prepare_grid(pb, gw, 0, 1 << 0, h->stream, &h->prof);
+        gw.consumed_valid[0] = gw.consumed_valid[1] = false;  // everything here is ordered on the main stream
+      } else {
+        voxelize_chunk_f32(h, G, p0, nb);
+        h->d_dgrid.ensure((size_t)nb * G.n_channels * npts * npts * npts);
+      }
       for (int mi : G.model_idx) {
         const Model& Mo = *h->models[mi];
         if (Mo.apply_logistic_loss || Mo.skip_softmax)
           throw Error(GB_ERR_USAGE, "gradient of apply_logistic_loss / skip_softmax models is not implemented");
-        h->launches += forward_backward_fp32(Mo, G.grid.p, nb, h->ws_grad, h->d_out3.p, h->d_dgrid.p, h->stream, &h->prof);
+        if (fast) {
+          h->launches += tc_forward(Mo, pb, G.tc_grid.x0[0][0], h->ws_tc, h->d_out3.p, h->stream, &h->prof, nullptr, true);
+        } else {
+          h->launches += forward_backward_fp32(Mo, G.grid.p, nb, h->ws_grad, h->d_out3.p, h->d_dgrid.p, h->stream, &h->prof);
+        }
         launch_head_post(h->d_out3.p, nb, Mo.skip_softmax, Mo.apply_logistic_loss, h->d_pose.p + (size_t)mi * n + p0,
                          h->d_aff.p + (size_t)mi * n + p0, h->d_loss.p + (size_t)mi * n + p0, h->stream);
         // ligand atoms of this chunk: accumulate (scaled 1/M) into the group's gradient array
-        launch_grid_backward(G.lig_xyzr.p, G.lig_ch.p, G.lig_off.p + p0, G.max_pose_atoms, h->d_centers.p + 3 * (size_t)p0, nb,
-                             G.n_channels, npts, G.sig.resolution, G.sig.dimension, h->d_dgrid.p, tmp_grad.p, h->stream);
+        if (fast) {
+          h->launches += tc_backward(Mo, pb, h->ws_tc, h->d_out3.p, tmp_grad.p, h->stream, &h->prof);
+        } else {
+          launch_grid_backward(G.lig_xyzr.p, G.lig_ch.p, G.lig_off.p + p0, G.max_pose_atoms, h->d_centers.p + 3 * (size_t)p0, nb,
+                               G.n_channels, npts, G.sig.resolution, G.sig.dimension, h->d_dgrid.p, tmp_grad.p, h->stream);
+          h->launches++;
+        }
         launch_axpy_range(tmp_grad.p, G.lig_grad.p, G.h_lig_off.p[p0] * 3, G.h_lig_off.p[p0 + nb] * 3, 1.0f / (float)M,
                           h->stream);
-        h->launches += 3;
+        h->launches += 2;
       }
     }
   }

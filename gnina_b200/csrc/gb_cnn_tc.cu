@@ -47,35 +47,24 @@ ActLayout make_layout(int D, int G, int C) {
   return L;
 }
 
-struct PointwiseTc {
-  int c = 0;
-  __half* w = nullptr;       // [co][ci] row-major fp16
-  float* bias = nullptr;
-};
-struct TcWeights {
-  ConvTc conv1, conv3, conv5;
-  PointwiseTc pw2, pw4;
-  float* fcw = nullptr;      // [3][216*128] channels-last order
-  float* fcb = nullptr;
-  std::vector<void*> allocs;
-  ~TcWeights() { for (void* p : allocs) cudaFree(p); }
-};
+TcWeights::~TcWeights() { for (void* p : allocs) cudaFree(p); }
 
 template <typename T>
-static T* tc_upload(TcWeights& w, const std::vector<T>& h) {
+static T* tc_upload(std::vector<void*>& allocs, const std::vector<T>& h) {
   T* d = nullptr;
   GB_CUDA(cudaMalloc(&d, h.size() * sizeof(T)));
-  w.allocs.push_back(d);
+  allocs.push_back(d);
   GB_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
   return d;
 }
+template <typename T>
+static T* tc_upload(TcWeights& w, const std::vector<T>& h) { return tc_upload(w.allocs, h); }
 
-static ConvTc prep_conv(TcWeights& tw, const Model& m, const std::string& key) {
-  const HostTensor& w = m.t(key + ".weight");
-  const HostTensor& b = m.t(key + ".bias");
+// Pack a 3x3x3 kernel wfn(co, ci, kx, ky, kz) into the stacked-dx B operand layout [cout/32][9][cin/8][96] x 16 B.
+ConvTc make_conv_tc(std::vector<void*>& allocs, int cout, int cin, const std::function<float(int, int, int, int, int)>& wfn,
+                    const float* bias) {
   ConvTc c;
-  const int cout = w.shape[0], cin = w.shape[1];
-  GB_CHECK(w.shape[2] == 3 && cout % 32 == 0, "tc conv shape");
+  GB_CHECK(cout % 32 == 0, "tc conv shape");
   c.cout = cout;
   c.cin = (cin + 15) / 16 * 16;
   const int C8 = c.cin / 8, NB = cout / 32;
@@ -90,13 +79,25 @@ static ConvTc prep_conv(TcWeights& tw, const Model& m, const std::string& key) {
               for (int e = 0; e < 8; e++) {
                 const int ci = c8 * 8 + e;
                 if (ci >= cin) continue;
-                const float v = w.data[((((size_t)(nb * 32 + co) * cin + ci) * 3 + kx) * 3 + ky) * 3 + kz];
-                h[((((size_t)nb * 9 + ky * 3 + kz) * C8 + c8) * 96 + blk * 32 + co) * 8 + e] = __float2half(v);
+                h[((((size_t)nb * 9 + ky * 3 + kz) * C8 + c8) * 96 + blk * 32 + co) * 8 + e] =
+                    __float2half(wfn(nb * 32 + co, ci, kx, ky, kz));
               }
           }
-  c.wp = reinterpret_cast<uint4*>(tc_upload(tw, h));
-  c.bias = tc_upload(tw, std::vector<float>(b.data, b.data + b.nelem));
+  c.wp = reinterpret_cast<uint4*>(tc_upload(allocs, h));
+  std::vector<float> b(cout, 0.f);
+  if (bias) b.assign(bias, bias + cout);
+  c.bias = tc_upload(allocs, b);
   return c;
+}
+
+static ConvTc prep_conv(TcWeights& tw, const Model& m, const std::string& key) {
+  const HostTensor& w = m.t(key + ".weight");
+  const HostTensor& b = m.t(key + ".bias");
+  const int cout = w.shape[0], cin = w.shape[1];
+  GB_CHECK(w.shape[2] == 3, "tc conv shape");
+  return make_conv_tc(tw.allocs, cout, cin, [&](int co, int ci, int kx, int ky, int kz) {
+    return w.data[((((size_t)co * cin + ci) * 3 + kx) * 3 + ky) * 3 + kz];
+  }, b.data);
 }
 
 static PointwiseTc prep_pw(TcWeights& tw, const Model& m, const std::string& key) {
@@ -117,7 +118,7 @@ bool tc_supported(const Model& m) {
 }
 int tc_pool_kind(const Model& m) { return m.arch == GB_ARCH_DEFAULT2018 ? 0 : 1; }
 
-static std::shared_ptr<TcWeights> get_tc_weights(const Model& m) {
+std::shared_ptr<TcWeights> get_tc_weights(const Model& m) {
   Model& mm = const_cast<Model&>(m);
   if (mm.tc) return mm.tc;
   auto tw = std::make_shared<TcWeights>();
@@ -388,8 +389,10 @@ struct ConvTcSmem {
 // configuration, in constant memory: the issue loop reads them with uniform loads (ULDC) straight into the uniform
 // registers UTCHMMA consumes — no per-thread arithmetic, no uniform-register spills.
 struct MmaOff { uint32_t a, b; };
-__constant__ MmaOff c_mma_off[3][36];
-template <int CIN, int DD> struct ConvCfg { static constexpr int id = (CIN == 32 && DD == 24) ? 0 : (CIN == 32 && DD == 12) ? 1 : 2; };
+__constant__ MmaOff c_mma_off[4][36];
+template <int CIN, int DD> struct ConvCfg {
+  static constexpr int id = (CIN == 32 && DD == 24) ? 0 : (CIN == 32 && DD == 12) ? 1 : (CIN == 64 && DD == 6) ? 2 : 3;
+};
 
 template <int CIN, int DD>
 __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
@@ -573,8 +576,9 @@ __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
           uint32_t* ow = reinterpret_cast<uint32_t*>(o);
 #pragma unroll
           for (int c = 0; c < 16; c++) {
-            float f0 = fmaxf(__uint_as_float(v[2 * c]) + s_bias[2 * c], 0.f);
-            float f1 = fmaxf(__uint_as_float(v[2 * c + 1]) + s_bias[2 * c + 1], 0.f);
+            float f0 = __uint_as_float(v[2 * c]) + s_bias[2 * c];
+            float f1 = __uint_as_float(v[2 * c + 1]) + s_bias[2 * c + 1];
+            if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
             const __half2 h = __floats2half2_rn(f0, f1);
             ow[c] = *reinterpret_cast<const uint32_t*>(&h);
           }
@@ -798,7 +802,7 @@ __global__ void __launch_bounds__(256) fc_heads_f16_kernel(const __half* __restr
 // ------------------------------------------------------------------------------------------------------------
 template <int CIN, int DD>
 static void launch_conv_tc(const ConvTc& c, const ActLayout& L, const uint4* xin, __half* out, int n_poses, cudaStream_t s,
-                           uint4* out_planar = nullptr, int out_c8tot = 0, int out_c8off = 0, int out_lp = 0) {
+                           uint4* out_planar = nullptr, int out_c8tot = 0, int out_c8off = 0, int out_lp = 0, int relu = 1) {
   using S = ConvTcSmem<CIN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -822,7 +826,7 @@ static void launch_conv_tc(const ConvTc& c, const ActLayout& L, const uint4* xin
   ConvTcParams p;
   p.xin = xin; p.wp = c.wp; p.bias = c.bias; p.out = out;
   p.D = L.D; p.P = L.P; p.G = L.G; p.T = L.T; p.NB = c.cout / 32; p.Lp = L.Lp; p.Cout = c.cout; p.n_poses = n_poses;
-  p.relu = 1;
+  p.relu = relu;
   p.out_mode = out_planar ? 1 : 0; p.out_planar = out_planar; p.out_c8tot = out_c8tot; p.out_c8off = out_c8off; p.out_lp = out_lp;
   static const int dbg = getenv("GB_TC_DBG") ? atoi(getenv("GB_TC_DBG")) : 0;
   p.dbg = dbg;
@@ -859,6 +863,14 @@ void tc_debug_set(int i, const void* p, size_t bytes) { t_debug.ptr[i] = p; t_de
 void launch_conv_tc_32_24_planar(const ConvTc& c, const uint4* xin, uint4* xout, int out_c8tot, int out_c8off, int out_lp,
                                  int n_poses, cudaStream_t s) {
   launch_conv_tc<32, 24>(c, make_layout(24, 1, 32), xin, nullptr, n_poses, s, xout, out_c8tot, out_c8off, out_lp);
+}
+void launch_conv_tc_any(int cin, int D, const ConvTc& c, const ActLayout& L, const uint4* xin, __half* out, int n_poses,
+                        cudaStream_t s, uint4* out_planar, int out_c8tot, int out_c8off, int out_lp, int relu) {
+  if (cin == 32 && D == 24) launch_conv_tc<32, 24>(c, L, xin, out, n_poses, s, out_planar, out_c8tot, out_c8off, out_lp, relu);
+  else if (cin == 32 && D == 12) launch_conv_tc<32, 12>(c, L, xin, out, n_poses, s, out_planar, out_c8tot, out_c8off, out_lp, relu);
+  else if (cin == 64 && D == 6) launch_conv_tc<64, 6>(c, L, xin, out, n_poses, s, out_planar, out_c8tot, out_c8off, out_lp, relu);
+  else if (cin == 64 && D == 12) launch_conv_tc<64, 12>(c, L, xin, out, n_poses, s, out_planar, out_c8tot, out_c8off, out_lp, relu);
+  else throw Error(GB_ERR_INTERNAL, "no tensor-core conv instantiation for this shape");
 }
 const void* tc_debug_buffer(int i, size_t* bytes) {
   if (i < 0 || i >= 8) return nullptr;
@@ -923,7 +935,7 @@ int tc_prepare_grid(const TcPoseBatch& pb, TcGridWorkspace& gw, int buf, int kin
 }
 
 int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspace& ws, float* out3, cudaStream_t s,
-               Profiler* prof, cudaEvent_t x0_consumed) {
+               Profiler* prof, cudaEvent_t x0_consumed, bool keep_activations) {
   GB_CHECK(tc_supported(m), "model has no tensor-core path");
   if (m.arch == GB_ARCH_DENSE) return tc_forward_dense(m, pb, x0v, ws, out3, s, prof, x0_consumed);
   auto tw = get_tc_weights(m);
@@ -940,6 +952,12 @@ int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspa
   uint4* X2 = reinterpret_cast<uint4*>(ws.buf[1]);
   uint4* X4 = reinterpret_cast<uint4*>(ws.buf[2]);
   __half* Y5 = reinterpret_cast<__half*>(ws.buf[3]);
+  __half* Y3 = Y;  // conv3's output reuses conv1's buffer unless the backward pass needs both
+  if (keep_activations) {
+    GB_CHECK(m.arch == GB_ARCH_DEFAULT2018, "activations are kept for the default2018 family only");
+    ws.ensure(7, (size_t)nb * 12 * 12 * 12 * 64 * sizeof(__half) + 1024);
+    Y3 = reinterpret_cast<__half*>(ws.buf[7]);
+  }
   const int pw_blocks = 148 * 8;
   {
     ProfScope ps(prof, "tc_conv1_3x3x3_28x32_d24", s);
@@ -952,11 +970,11 @@ int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspa
   }
   {
     ProfScope ps(prof, "tc_conv3_3x3x3_32x64_d12", s);
-    launch_conv_tc<32, 12>(tw->conv3, L3, X2, Y, nb, s);
+    launch_conv_tc<32, 12>(tw->conv3, L3, X2, Y3, nb, s);
   }
   {
     ProfScope ps(prof, "tc_pw4_pool", s);
-    pointwise_pool_kernel<64><<<pw_blocks, 256, 0, s>>>(Y, tw->pw4.w, tw->pw4.bias, reinterpret_cast<__half*>(X4), 12, nb, L5.G, L5.Lp);
+    pointwise_pool_kernel<64><<<pw_blocks, 256, 0, s>>>(Y3, tw->pw4.w, tw->pw4.bias, reinterpret_cast<__half*>(X4), 12, nb, L5.G, L5.Lp);
   }
   {
     ProfScope ps(prof, "tc_conv5_3x3x3_64x128_d6", s);
@@ -968,7 +986,7 @@ int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspa
   }
   launches += 6;
   t_debug.ptr[0] = x0v;      t_debug.bytes[0] = act_bytes(L1, nb);
-  t_debug.ptr[1] = Y;        t_debug.bytes[1] = (size_t)nb * 1728 * 64 * sizeof(__half);  // holds Y3 after the pass
+  t_debug.ptr[1] = Y3;       t_debug.bytes[1] = (size_t)nb * 1728 * 64 * sizeof(__half);  // holds Y3 after the pass
   t_debug.ptr[2] = X2;       t_debug.bytes[2] = act_bytes(L3, nb);
   t_debug.ptr[3] = X4;       t_debug.bytes[3] = act_bytes(L5, nb);
   t_debug.ptr[4] = Y5;       t_debug.bytes[4] = (size_t)nb * 216 * 128 * sizeof(__half);

@@ -60,6 +60,7 @@ struct ConvF32 {
 // fp16 tensor-core path weights (see gb_cnn_tc.cu, gb_cnn_tc_dense.cu)
 struct TcWeights;
 struct TcDenseWeights;
+struct TcGradWeights;
 
 struct Model {
   std::atomic<int> refs{1};
@@ -80,6 +81,7 @@ struct Model {
   int fc_features = 0;
   std::shared_ptr<TcWeights> tc;  // lazily built
   std::shared_ptr<TcDenseWeights> tc_dense;
+  std::shared_ptr<TcGradWeights> tc_grad;  // backward-data weights of the fast gradient path
   const HostTensor& t(const std::string& n) const;
   ~Model();
 };

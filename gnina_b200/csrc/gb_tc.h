@@ -1,6 +1,8 @@
 // Fast path: fused voxelise+pool (fp16, channel-chunk-planar) and tcgen05 fp16 convolutions.  See gb_cnn_tc.cu.
 #pragma once
 #include "gb_internal.h"
+#include <cuda_fp16.h>
+#include <functional>
 
 namespace gb {
 
@@ -28,8 +30,8 @@ struct TcGridWorkspace {
 };
 
 struct TcWorkspace {
-  void* buf[8] = {};
-  size_t cap[8] = {};
+  void* buf[16] = {};
+  size_t cap[16] = {};
   void ensure(int i, size_t bytes);
   ~TcWorkspace();
 };
@@ -43,7 +45,12 @@ int tc_pool_kind(const Model& m);  // 0 avg, 1 max
 // network forward on the pooled grid x0 -> out3 [n_poses][3]; records x0_consumed (if non-null) once x0 has been
 // read for the last time; returns the number of kernel launches
 int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0, TcWorkspace& ws, float* out3, cudaStream_t s,
-               Profiler* prof = nullptr, cudaEvent_t x0_consumed = nullptr);
+               Profiler* prof = nullptr, cudaEvent_t x0_consumed = nullptr, bool keep_activations = false);
+// default2018 family, after tc_forward(..., keep_activations = true) on the same workspace: backward of the CE loss
+// through the network and the fused voxelise/pool to the ligand atoms of the chunk; atom_grad [chunk atoms][3] (see
+// gb_cnn_tc_grad.cu); returns #launches
+int tc_backward(const Model& m, const TcPoseBatch& pb, TcWorkspace& ws, const float* out3, float* atom_grad, cudaStream_t s,
+                Profiler* prof = nullptr);
 
 // chunk-planar padded grouped activation layout (see gb_cnn_tc.cu)
 struct ActLayout {
@@ -62,6 +69,25 @@ struct ConvTc {
   uint4* wp = nullptr;       // [cout/32][9][cin/8][96] x 16 B
   float* bias = nullptr;
 };
+struct PointwiseTc {
+  int c = 0;
+  __half* w = nullptr;       // [co][ci] row-major fp16
+  float* bias = nullptr;
+};
+struct TcWeights {
+  ConvTc conv1, conv3, conv5;
+  PointwiseTc pw2, pw4;
+  float* fcw = nullptr;      // [3][216*128] channels-last order
+  float* fcb = nullptr;
+  std::vector<void*> allocs;
+  ~TcWeights();
+};
+std::shared_ptr<TcWeights> get_tc_weights(const Model& m);
+ConvTc make_conv_tc(std::vector<void*>& allocs, int cout, int cin, const std::function<float(int, int, int, int, int)>& wfn,
+                    const float* bias);
+// any instantiated (cin, D): out_planar == nullptr -> channels-last `out`, else chunk-planar (same D, P, G as the input)
+void launch_conv_tc_any(int cin, int D, const ConvTc& c, const ActLayout& L, const uint4* xin, __half* out, int n_poses,
+                        cudaStream_t s, uint4* out_planar, int out_c8tot, int out_c8off, int out_lp, int relu);
 void launch_conv_tc_32_24_planar(const ConvTc& c, const uint4* xin, uint4* xout, int out_c8tot, int out_c8off, int out_lp,
                                  int n_poses, cudaStream_t s);
 void tc_debug_set(int i, const void* p, size_t bytes);

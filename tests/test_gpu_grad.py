@@ -17,7 +17,7 @@ def test_ligand_gradient_matches_reference_autograd(kat, golden_dir):
     g = np.load(os.path.join(golden_dir, "grad_kat.npz"))
     n = int(g["n_poses"])
     offs = kat["pose_offsets"][:n + 1]
-    s = CNNScorer([str(g["model"])])
+    s = CNNScorer([str(g["model"])], precision=0)
     s.set_receptor(kat["rec_xyz"], kat["rec_types"])
     sc, aff, loss, var, grad = s.score_grad_batch(kat["lig_xyz"][:offs[-1]], kat["lig_types"][:offs[-1]], offs)
     assert np.abs(loss - g["loss"]).max() < 1e-4
@@ -58,10 +58,10 @@ def test_ensemble_gradient_is_mean_of_model_gradients(kat):
     x, t = kat["lig_xyz"][:offs[-1]], kat["lig_types"][:offs[-1]]
     gs = []
     for nm in names:
-        s = CNNScorer([nm])
+        s = CNNScorer([nm], precision=0)
         s.set_receptor(kat["rec_xyz"], kat["rec_types"])
         gs.append(s.score_grad_batch(x, t, offs)[4])
-    e = CNNScorer(names)
+    e = CNNScorer(names, precision=0)
     e.set_receptor(kat["rec_xyz"], kat["rec_types"])
     out = e.score_grad_batch(x, t, offs)
     assert np.abs(out[4] - 0.5 * (gs[0] + gs[1])).max() < 1e-5 * max(1.0, np.abs(out[4]).max())
@@ -74,3 +74,48 @@ def test_gradient_rejects_unsupported_models():
     s.set_receptor(np.zeros((1, 3), np.float32), np.array([2], np.int32))
     with pytest.raises(capi.GbError, match="default2018"):
         s.score_grad_batch(np.zeros((1, 3), np.float32), np.array([2], np.int32), [0, 1])
+
+
+# ---- fast mode: tcgen05 backward-data convolutions, fp16 gradients with loss scaling (gb_cnn_tc_grad.cu) ----------
+FAST_GRAD_TOL = 2e-2     # of max |gradient| of the batch; fp16 operands end to end
+FAST_LOSS_TOL = 5e-3
+
+
+def test_fast_gradient_matches_reference_autograd(kat, golden_dir):
+    from gnina_b200 import CNNScorer
+    g = np.load(os.path.join(golden_dir, "grad_kat.npz"))
+    n = int(g["n_poses"])
+    offs = kat["pose_offsets"][:n + 1]
+    s = CNNScorer([str(g["model"])], precision=1)
+    s.set_receptor(kat["rec_xyz"], kat["rec_types"])
+    x, t = kat["lig_xyz"][:offs[-1]], kat["lig_types"][:offs[-1]]
+    sc, aff, loss, var, grad = s.score_grad_batch(x, t, offs)
+    assert np.abs(loss - g["loss"]).max() < FAST_LOSS_TOL
+    scale = np.abs(g["lig_grad"]).max()
+    assert np.abs(grad - g["lig_grad"]).max() < FAST_GRAD_TOL * scale
+    assert np.abs(grad[t <= 1]).max() == 0.0
+    # the forward outputs of the gradient call are the fast scoring path's
+    plain = s.score_batch(x, t, offs)
+    assert np.abs(plain[0] - sc).max() < 1e-6 and np.abs(plain[1] - aff).max() < 1e-5
+
+
+def test_fast_gradient_matches_validation_path_on_a_ragged_multi_chunk_batch(kat):
+    from gnina_b200 import CNNScorer, synth
+    xyz, types, offs = synth.make_screen(301, seed=5, trans_box=6.0)   # odd pose count: half-filled pose group
+    names = ["crossdock_default2018", "crossdock_default2018_KD_4"]
+    ref = CNNScorer(names, precision=0)
+    fast = CNNScorer(names, precision=1, max_batch=128)              # 3 chunks, the last one ragged
+    for s in (ref, fast):
+        s.set_receptor(kat["rec_xyz"], kat["rec_types"])
+    a = ref.score_grad_batch(xyz, types, offs)
+    b = fast.score_grad_batch(xyz, types, offs)
+    assert np.abs(a[2] - b[2]).max() < FAST_LOSS_TOL
+    ga, gb = a[4], b[4]
+    scale = np.abs(ga).max()
+    assert np.abs(ga - gb).max() < FAST_GRAD_TOL * scale
+    cos = float((ga * gb).sum() / (np.linalg.norm(ga) * np.linalg.norm(gb)))
+    assert cos > 0.9995
+    # a second call on the same handle (buffers reused, smaller batch) is unaffected by stale workspace contents
+    k = 7
+    b2 = fast.score_grad_batch(xyz[:offs[k]], types[:offs[k]], offs[:k + 1])
+    assert np.abs(b2[4] - gb[:offs[k]]).max() < 1e-6 * max(scale, 1.0)
