@@ -40,16 +40,26 @@ def main():
     n = 1000
     lx, offs = synth.make_poses(lx0, n, seed=5)
     lt = np.tile(lt0, n)
-    s = CNNScorer(["crossdock_default2018"])
-    s.set_receptor(rec_xyz, rec_t)
-    dt = timed(lambda: s.score_grad_batch(lx, lt, offs), reps=2)
     om = pipeline.OracleModel(model_blob.load_model("crossdock_default2018"))
     k = 2
     t0 = time.perf_counter()
     pipeline.score_grad([om], rec_xyz, rec_t, lx[:offs[k]], lt[:offs[k]], offs[:k + 1], dtype=torch.float32)
     cpu = k / (time.perf_counter() - t0)
-    out.append({"row": "cnn_gradient (G2+N5+S1)", "value": n / dt, "unit": "poses/s", "mode": "fp32 validation kernels",
-                "cpu_oracle": cpu, "cpu_sample": "%d poses, torch autograd + C gridmaker backward" % k})
+    for prec, mode, nn in ((1, "fp16 tcgen05 forward + backward", n), (0, "fp32 validation kernels", 256)):
+        s = CNNScorer(["crossdock_default2018"], precision=prec)
+        s.set_receptor(rec_xyz, rec_t)
+        dt = timed(lambda: s.score_grad_batch(lx[:offs[nn]], lt[:offs[nn]], offs[:nn + 1]), reps=3)
+        out.append({"row": "cnn_gradient (G2+N5+S1), %d poses" % nn, "value": nn / dt, "unit": "poses/s", "mode": mode,
+                    "cpu_oracle": cpu, "cpu_sample": "%d poses, torch autograd + C gridmaker backward" % k})
+    # larger batch: the config-5 workload batched over many ligands
+    n_big = 8192
+    lxb, offb = synth.make_poses(lx0, n_big, seed=6)
+    ltb = np.tile(lt0, n_big)
+    s = CNNScorer(["crossdock_default2018"], precision=1)
+    s.set_receptor(rec_xyz, rec_t)
+    dt = timed(lambda: s.score_grad_batch(lxb, ltb, offb), reps=3)
+    out.append({"row": "cnn_gradient (G2+N5+S1), %d poses" % n_big, "value": n_big / dt, "unit": "poses/s",
+                "mode": "fp16 tcgen05 forward + backward"})
 
     # --- fp32 validation forward and the default 3-model ensemble ---
     n2 = 512

@@ -51,9 +51,9 @@ def test_cpp_host_scores_match_oracle(golden_dir, tmp_path):
         _, idx, sc, aff, loss = lines[1 + p].split()
         assert abs(float(sc) - kat[name + "_pose_f64"][p]) < 2e-3 and abs(float(aff) - kat[name + "_aff_f64"][p]) < 1e-2
     single = lines[1 + n].split()
-    assert abs(float(single[1]) - kat[name + "_pose_f64"][0]) < 2e-5      # gradient call runs the fp32 kernels
+    assert abs(float(single[1]) - kat[name + "_pose_f64"][0]) < 2e-3      # gradient call: fast fp16 forward + backward
     grad = np.load(os.path.join(golden_dir, "grad_kat.npz"))["lig_grad"][:offs[1]]
-    assert abs(float(single[5]) - np.abs(grad).sum()) < 1e-3 * np.abs(grad).sum()
+    assert abs(float(single[5]) - np.abs(grad).sum()) < 1e-2 * np.abs(grad).sum()
     # non_cache_cnn: loss + slope * (distance outside [-1,1]^3 box) over heavy atoms; the CNN box (23.5 A around the
     # origin) adds its own penalty for atoms beyond +-11.75
     om = pipeline.OracleModel(model_blob.load_model(name))
