@@ -61,6 +61,16 @@ def main():
     out.append({"row": "cnn_gradient (G2+N5+S1), %d poses" % n_big, "value": n_big / dt, "unit": "poses/s",
                 "mode": "fp16 tcgen05 forward + backward"})
 
+    # --- config 4 shape: virtual screen, ragged ligands, --cnn dense_ensemble (20 models) ---
+    n4 = 4096
+    sx, st, so = synth.make_screen(n4, seed=3)
+    e20 = CNNScorer(["dense_ensemble"], precision=1)
+    e20.set_receptor(rec_xyz, rec_t)
+    dt = timed(lambda: e20.score_batch(sx, st, so), reps=2)
+    out.append({"row": "virtual screen, dense_ensemble (config 4 shape), %d ligands" % n4, "value": n4 / dt, "unit": "ligands/s",
+                "mode": "fp16 tcgen05", "models": len(e20.model_names), "model_evals_per_s": n4 * len(e20.model_names) / dt})
+    del e20
+
     # --- fp32 validation forward and the default 3-model ensemble ---
     n2 = 512
     for names, tag in ((["crossdock_default2018"], "cnn_validation_fp32 (N1)"), ([], "default_ensemble 3 models (N1+N2, S1)")):

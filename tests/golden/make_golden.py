@@ -98,7 +98,33 @@ def grad_kat(n_poses=2):
     print("grad kat: |g|max", np.abs(np.concatenate(grads)).max(), "loss", losses)
 
 
+def ensemble_kat(n_poses=3):
+    """BASELINE.json config 4's `--cnn dense_ensemble`: every embedded model whose name starts with "dense"
+    (cnn_torch_scorer.cpp:49-60) = 15 dense-architecture + 5 default2018-architecture models.  Per-model fp64 outputs
+    of the reference's own .pt files on the first poses of cnn_kat.npz, and CNNTorchScorer::score's ensemble
+    statistics (mean score / affinity, population variance of the affinity, cnn_torch_scorer.cpp:117-192)."""
+    k = np.load(os.path.join(HERE, "cnn_kat.npz"))
+    offs = k["pose_offsets"][:n_poses + 1]
+    names = sorted(f[:-3] for f in os.listdir(os.path.join(REF, "gninasrc/lib/models")) if f.startswith("dense") and f.endswith(".pt"))
+    om = pipeline.OracleModel(model_blob.load_model("dense_1.3"))          # all 20 share the default 14+14 maps
+    grids = torch.from_numpy(om.grids(k["rec_xyz"], k["rec_types"], k["lig_xyz"][:offs[-1]], k["lig_types"][:offs[-1]], offs)).double()
+    pose, aff = [], []
+    for name in names:
+        ts = torch.jit.load(os.path.join(REF, "gninasrc/lib/models", name + ".pt"), map_location="cpu").double()
+        with torch.no_grad():
+            gp, ga = ts(grids)
+        pose.append(torch.softmax(gp, 1)[:, 1].numpy()); aff.append(ga.numpy().reshape(-1))
+        print(name, pose[-1], aff[-1])
+    pose, aff = np.array(pose), np.array(aff)
+    np.savez_compressed(os.path.join(HERE, "ensemble_kat.npz"), models=np.array([n.replace(".", "_") for n in names]),
+                        n_poses=n_poses, pose_f64=pose, aff_f64=aff, score=pose.mean(0), affinity=aff.mean(0),
+                        variance=aff.var(0))
+
+
 if __name__ == "__main__":
+    if "--ensemble-only" in sys.argv:
+        ensemble_kat()
+        sys.exit(0)
     if "--grad-only" not in sys.argv:
         sparse_golden()
         cnn_kat()

@@ -143,3 +143,25 @@ def test_full_size_batch_properties():
     ref = v.score_batch(lx.reshape(n, na, 3)[sub].reshape(-1, 3), lt[:48 * na], offs[:49])
     assert np.abs(ref[0] - a[0][sub]).max() < TOL_SCORE and np.abs(ref[1] - a[1][sub]).max() < TOL_AFF
     assert np.isfinite(a[0]).all() and (a[0] >= 0).all() and (a[0] <= 1).all()
+
+
+def test_dense_ensemble_matches_reference_pt(golden_dir):
+    """BASELINE config 4: `--cnn dense_ensemble` = 20 models (15 dense + 5 default2018 architecture), ensemble
+    statistics of CNNTorchScorer::score against the reference's own .pt files (tests/golden/ensemble_kat.npz)."""
+    from gnina_b200 import CNNScorer
+    kat = np.load(os.path.join(golden_dir, "cnn_kat.npz"))
+    e = np.load(os.path.join(golden_dir, "ensemble_kat.npz"))
+    n = int(e["n_poses"])
+    offs = kat["pose_offsets"][:n + 1]
+    x, t = kat["lig_xyz"][:offs[-1]], kat["lig_types"][:offs[-1]]
+    for prec, tol_s, tol_a, tol_v in ((1, 2e-3, 1e-2, 2e-2), (0, 2e-5, 1e-4, 5e-4)):
+        s = CNNScorer(["dense_ensemble"], precision=prec)
+        assert len(s.model_names) == 20
+        s.set_receptor(kat["rec_xyz"], kat["rec_types"])
+        sc, aff, loss, var = s.score_batch(x, t, offs)
+        assert np.abs(sc - e["score"]).max() < tol_s
+        assert np.abs(aff - e["affinity"]).max() < tol_a
+        assert np.abs(var - e["variance"]).max() < tol_v
+        per_model = s.score_batch_models(x, t, offs)
+        order = [list(e["models"]).index(m) for m in s.model_names]
+        assert np.abs(per_model[0] - e["pose_f64"][order]).max() < tol_s

@@ -56,7 +56,7 @@ GenericMetal Boron Manganese Magnesium Zinc Calcium Iron
 
 def classify(sd):
     keys = list(sd.keys())
-    if any(k.startswith("dense_block_0") for k in keys):
+    if any("dense_block_0" in k for k in keys):
         return "dense"
     if any(k.endswith("unit5_conv.weight") for k in keys):
         return "default2018"
@@ -105,7 +105,7 @@ def convert(src, dst_dir):
         for pre in ("features.", "pose.", "affinity."):
             if k.startswith(pre):
                 k = k[len(pre):]
-        return k
+        return k.replace(".blocks.", ".")   # the pre-1.3 dense exports nest the block layers one level deeper
     tensors = [(canon(k), v.detach().numpy()) for k, v in sd.items() if v.dtype == torch.float32]
     # gnina model names replace '.' by '_' (gninasrc/make_model_cpp.py:31-32)
     name = os.path.basename(src)[:-3].replace(".", "_")
