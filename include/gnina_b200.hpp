@@ -7,10 +7,16 @@
 //                       options (no empirical mixing, no user grid): CNN loss + out-of-box penalties of the search box
 //                       and of the CNN box (non_cache::check_bounds(_deriv), lib/non_cache.cpp:32-50,102-123)
 //   gb::VinaScorer  <-> precalculate_linear + cache + naive_non_cache final scoring (see gnina_b200.h)
+//   gb::PoseBatcher <-> the pose queue SURVEY.md 8(f)-1 asks for: gnina's ligand loop (main/main.cpp:749-771, 233-269,
+//                       324-346) scores one pose per call; the batcher collects poses and hands them to the batch
+//                       entry point, delivering results in submission order
+//   gb::read_gninatypes / write_gninatypes <-> gninatyper's typed-atom records (gninatyper/gninatyper.cpp:30-36,72-77)
 // Errors: GB_ERR_USAGE -> gb::usage_error (reference: usage_error), everything else -> gb::internal_error.
 #pragma once
 #include <array>
 #include <cmath>
+#include <cstdio>
+#include <functional>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -116,6 +122,101 @@ class CNNScorer {
     }
     return s;
   }
+};
+
+// ---- typed-atom records: `.gninatypes` = a flat array of {float x, y, z; int32 smina_type} (gninatyper.cpp:30-36,
+// written one molecule per file at :72-77).  The smina type is exactly the int32 the ABI takes, so a virtual screen
+// can feed pre-typed ligands without OpenBabel.
+struct TypedAtoms {
+  std::vector<float> xyz;      // [n][3]
+  std::vector<int32_t> type;   // [n]
+  size_t size() const { return type.size(); }
+};
+inline TypedAtoms read_gninatypes(const std::string& path) {
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) throw usage_error("Could not open " + path);
+  TypedAtoms a;
+  struct Rec { float x, y, z; int32_t t; } r;
+  static_assert(sizeof(Rec) == 16, "gninatypes record");
+  size_t got;
+  while ((got = std::fread(&r, 1, sizeof r, f)) == sizeof r) {
+    a.xyz.push_back(r.x); a.xyz.push_back(r.y); a.xyz.push_back(r.z);
+    a.type.push_back(r.t);
+  }
+  std::fclose(f);
+  if (got != 0) throw usage_error("Truncated gninatypes file " + path);
+  return a;
+}
+inline void write_gninatypes(const std::string& path, const float* xyz, const int32_t* type, size_t n) {
+  FILE* f = std::fopen(path.c_str(), "wb");
+  if (!f) throw usage_error("Could not open " + path + " for writing");
+  for (size_t i = 0; i < n; i++) {
+    const float c[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+    if (std::fwrite(c, 4, 3, f) != 3 || std::fwrite(&type[i], 4, 1, f) != 1) { std::fclose(f); throw internal_error("short write " + path); }
+  }
+  std::fclose(f);
+}
+
+// ---- pose queue in front of the batch entry point -------------------------------------------------------------
+// add() copies one pose and returns its ticket (0, 1, 2, ... in submission order); when `capacity` poses are queued,
+// or on flush() / destruction, ONE batch call scores them and `deliver` is invoked once per pose in ticket order.
+// All poses of a batcher use either their own ligand centre (cnn_center unset, the reference default) or one fixed
+// centre (cnnopts.cnn_center, cnn_torch_scorer.cpp:118-121).
+class PoseBatcher {
+ public:
+  using Runner = std::function<Scores(const float* xyz, const int32_t* type, const int32_t* offsets, int n_poses,
+                                      const float* centers)>;
+  using Deliver = std::function<void(size_t ticket, float score, float affinity, float loss, float variance)>;
+
+  PoseBatcher(Runner run, size_t capacity, Deliver deliver, const float* fixed_center = nullptr)
+      : run_(std::move(run)), deliver_(std::move(deliver)), capacity_(capacity ? capacity : 1) {
+    if (fixed_center) { has_center_ = true; center_ = {fixed_center[0], fixed_center[1], fixed_center[2]}; }
+    offs_.push_back(0);
+  }
+  PoseBatcher(CNNScorer& s, size_t capacity, Deliver deliver, const float* fixed_center = nullptr)
+      : PoseBatcher([&s](const float* x, const int32_t* t, const int32_t* o, int n, const float* c) {
+                      return s.score_batch(x, t, o, n, c);
+                    }, capacity, std::move(deliver), fixed_center) {}
+  PoseBatcher(const PoseBatcher&) = delete;
+  PoseBatcher& operator=(const PoseBatcher&) = delete;
+  ~PoseBatcher() {
+    try { flush(); } catch (...) {}  // destructors must not throw; call flush() yourself to see errors
+  }
+
+  size_t add(const float* xyz, const int32_t* type, int n_atoms) {
+    xyz_.insert(xyz_.end(), xyz, xyz + 3 * (size_t)n_atoms);
+    type_.insert(type_.end(), type, type + n_atoms);
+    offs_.push_back((int32_t)type_.size());
+    const size_t ticket = next_ticket_++;
+    if (queued() >= capacity_) flush();
+    return ticket;
+  }
+  size_t queued() const { return offs_.size() - 1; }
+  size_t batches_run() const { return batches_; }
+  void flush() {
+    const size_t n = queued();
+    if (n == 0) return;
+    std::vector<float> centers;
+    if (has_center_)
+      for (size_t i = 0; i < n; i++) centers.insert(centers.end(), center_.begin(), center_.end());
+    // take the queue first: a throwing runner must not leave half-delivered poses queued for a second delivery
+    std::vector<float> xyz; std::vector<int32_t> type, offs;
+    xyz.swap(xyz_); type.swap(type_); offs.swap(offs_);
+    offs_.push_back(0);
+    const size_t first = next_ticket_ - n;
+    const Scores r = run_(xyz.data(), type.data(), offs.data(), (int)n, has_center_ ? centers.data() : nullptr);
+    batches_++;
+    for (size_t i = 0; i < n; i++) deliver_(first + i, r.score[i], r.affinity[i], r.loss[i], r.variance[i]);
+  }
+
+ private:
+  Runner run_;
+  Deliver deliver_;
+  size_t capacity_, next_ticket_ = 0, batches_ = 0;
+  bool has_center_ = false;
+  std::array<float, 3> center_{};
+  std::vector<float> xyz_;
+  std::vector<int32_t> type_, offs_;
 };
 
 // grid_dim (lib/grid_dim.h:30-43) for the two out-of-box penalties

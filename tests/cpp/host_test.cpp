@@ -1,9 +1,12 @@
 // C++ host-side check: builds against include/gnina_b200.hpp + libgnina_b200.so.
 //   host_test --names                      : model-name expansion only (no device needed)
+//   host_test --host <tmp.gninatypes>      : PoseBatcher with a stub runner + gninatypes round trip (no device needed)
 //   host_test <weights_dir> <case.bin>     : score the poses in case.bin through gb::CNNScorer / gb::NonCacheCNN and
 //                                            print the results as text (compared with the oracle by the pytest)
 // case.bin (little endian): int32 n_rec, n_lig_atoms, n_poses; float rec_xyz[3 n_rec]; int32 rec_type[n_rec];
 //                           float lig_xyz[3 n_lig]; int32 lig_type[n_lig]; int32 offsets[n_poses + 1]
+#include <algorithm>
+#include <array>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -23,6 +26,45 @@ int main(int argc, char** argv) {
     auto e = gb::expand_model_names({"crossdock_default2018_ensemble"}, {"crossdock_default2018", "crossdock_default2018_1", "dense"});
     printf("%s %s %s | %s | %zu\n", d[0].c_str(), d[1].c_str(), d[2].c_str(), f[0].c_str(), e.size());
     return 0;
+  }
+  if (argc >= 3 && !strcmp(argv[1], "--host")) {
+    // typed-atom records: write, read back, and reject a truncated file
+    const float xyz[6] = {1.5f, -2.25f, 3.0f, 0.f, 1e-3f, -7.f};
+    const int32_t ty[2] = {2, 13};
+    gb::write_gninatypes(argv[2], xyz, ty, 2);
+    auto a = gb::read_gninatypes(argv[2]);
+    bool ok = a.size() == 2 && a.xyz[1] == -2.25f && a.xyz[5] == -7.f && a.type[1] == 13;
+    { FILE* f = fopen(argv[2], "ab"); fputc(0, f); fclose(f); }
+    try { gb::read_gninatypes(argv[2]); ok = false; } catch (const gb::usage_error&) {}
+    try { gb::read_gninatypes(std::string(argv[2]) + ".missing"); ok = false; } catch (const gb::usage_error&) {}
+    printf("gninatypes %s\n", ok ? "ok" : "FAILED");
+    // pose queue: stub runner scores a pose as (n_atoms, first x, centre x or -1, batch size)
+    std::vector<std::array<float, 5>> got;
+    auto runner = [](const float* x, const int32_t*, const int32_t* o, int n, const float* c) {
+      gb::Scores r;
+      for (int i = 0; i < n; i++) {
+        r.score.push_back((float)(o[i + 1] - o[i])); r.affinity.push_back(x[3 * o[i]]);
+        r.loss.push_back(c ? c[3 * i] : -1.f); r.variance.push_back((float)n);
+      }
+      return r;
+    };
+    auto deliver = [&](size_t t, float s, float af, float l, float v) { got.push_back({(float)t, s, af, l, v}); };
+    {
+      gb::PoseBatcher q(runner, 3, deliver);
+      for (int p = 0; p < 7; p++) {
+        std::vector<float> px(3 * (size_t)(p + 1), (float)(10 + p));
+        std::vector<int32_t> pt(p + 1, 2);
+        const size_t t = q.add(px.data(), pt.data(), p + 1);
+        if (t != (size_t)p) ok = false;
+      }
+      printf("queued %zu batches %zu delivered %zu\n", q.queued(), q.batches_run(), got.size());
+    }  // destructor flushes the ragged tail
+    for (auto& g : got) printf("ticket %.0f n %.0f x %.0f c %.0f batch %.0f\n", g[0], g[1], g[2], g[3], g[4]);
+    const float ctr[3] = {4.f, 5.f, 6.f};
+    got.clear();
+    { gb::PoseBatcher q(runner, 8, deliver, ctr); const float x1[3] = {1, 2, 3}; const int32_t t1[1] = {2}; q.add(x1, t1, 1); q.flush(); q.flush(); }
+    printf("fixed centre %.0f deliveries %zu\n", got.empty() ? -1.f : got[0][3], got.size());
+    return ok ? 0 : 1;
   }
   if (argc < 3) return 2;
   try {
@@ -49,6 +91,15 @@ int main(int argc, char** argv) {
     std::vector<float> grad;
     const float sc = c->score(lig_xyz.data(), lig_t.data(), offs[1], true, aff, loss, var, &grad);
     printf("single %.7f %.6f %.6f gradsum %.6f\n", sc, aff, loss, [&] { double t = 0; for (float g : grad) t += std::fabs(g); return t; }());
+    {  // the pose queue in front of the real scorer reproduces the direct batch call, in order
+      double worst = 0; size_t n_del = 0;
+      gb::PoseBatcher q(s, 2, [&](size_t t, float sc2, float af2, float, float) {
+        worst = std::max(worst, (double)std::fabs(sc2 - r.score[t]) + std::fabs(af2 - r.affinity[t])); n_del++;
+      });
+      for (int p = 0; p < hdr[2]; p++) q.add(lig_xyz.data() + 3 * (size_t)offs[p], lig_t.data() + offs[p], offs[p + 1] - offs[p]);
+      q.flush();
+      printf("batcher delivered %zu batches %zu maxdiff %.3g\n", n_del, q.batches_run(), worst);
+    }
     // non_cache_cnn::eval_deriv with a search box that cuts through the ligand: penalties + derivative signs
     gb::GridDims gd;
     for (int i = 0; i < 3; i++) { gd[i].begin = -1.0f; gd[i].end = 1.0f; gd[i].n = 8; }

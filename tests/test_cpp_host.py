@@ -50,7 +50,10 @@ def test_cpp_host_scores_match_oracle(golden_dir, tmp_path):
     for p in range(n):
         _, idx, sc, aff, loss = lines[1 + p].split()
         assert abs(float(sc) - kat[name + "_pose_f64"][p]) < 2e-3 and abs(float(aff) - kat[name + "_aff_f64"][p]) < 1e-2
-    single = lines[1 + n].split()
+    by_tag = {l.split()[0]: l.split() for l in lines}
+    assert by_tag["batcher"][1:] == ["delivered", str(n), "batches", "2", "maxdiff"] + by_tag["batcher"][6:] and \
+        float(by_tag["batcher"][6]) < 1e-6                                # gb::PoseBatcher == the direct batch call
+    single = by_tag["single"]
     assert abs(float(single[1]) - kat[name + "_pose_f64"][0]) < 2e-3      # gradient call: fast fp16 forward + backward
     grad = np.load(os.path.join(golden_dir, "grad_kat.npz"))["lig_grad"][:offs[1]]
     assert abs(float(single[5]) - np.abs(grad).sum()) < 1e-2 * np.abs(grad).sum()
@@ -60,5 +63,5 @@ def test_cpp_host_scores_match_oracle(golden_dir, tmp_path):
     loss0 = om.score(kat["rec_xyz"], kat["rec_types"], lx[:offs[1]], lt[:offs[1]], offs[:2], dtype=torch.float64)[2][0]
     heavy = lx[:offs[1]][lt[:offs[1]] > 1]
     pen = 10.0 * (np.clip(np.abs(heavy) - 1.0, 0, None).sum() + np.clip(np.abs(heavy) - 11.75, 0, None).sum())
-    e, e0 = float(lines[2 + n].split()[1]), float(lines[2 + n].split()[2])
+    e, e0 = float(by_tag["noncache"][1]), float(by_tag["noncache"][2])
     assert abs(e - (loss0 + pen)) < 1e-3 * max(1.0, abs(loss0 + pen)) and abs(e0 - (loss0 + pen)) < 3e-3 * max(1.0, abs(e0))
