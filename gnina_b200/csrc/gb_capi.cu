@@ -651,15 +651,19 @@ int gb_cnn_score_grad(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, 
   const int n_in = h->n_input_atoms;
   for (int i = 0; i < 3 * n_in; i++) dlig_xyz[i] = 0.f;
   if (n == 0) return GB_OK;
-  for (Model* m : h->models)
-    if (m->arch != GB_ARCH_DEFAULT2018)
-      throw Error(GB_ERR_USAGE, "gradient path is implemented for the default2018 family only (model " + m->name + ")");
+  bool all_default2018 = true;
+  for (Model* m : h->models) {
+    if (m->arch != GB_ARCH_DEFAULT2018 && m->arch != GB_ARCH_DENSE)
+      throw Error(GB_ERR_USAGE, "gradient path is implemented for the default2018 and dense families only (model " + m->name + ")");
+    all_default2018 &= m->arch == GB_ARCH_DEFAULT2018;
+  }
   h->d_pose.ensure((size_t)M * n);
   h->d_aff.ensure((size_t)M * n);
   h->d_loss.ensure((size_t)M * n);
   h->d_final.ensure(4 * (size_t)n);
   // precision "fp16": forward AND backward on the tensor-core path (gb_cnn_tc_grad.cu); "fp32": validation kernels
-  const bool fast = h->precision != GB_PRECISION_FP32;
+  // the tensor-core backward covers the default2018 family; an ensemble with a dense member runs the fp32 kernels
+  const bool fast = h->precision != GB_PRECISION_FP32 && all_default2018;
   const int chunk = fast ? (h->max_batch > 0 ? h->max_batch : 1024) : (h->max_batch > 0 ? std::min(h->max_batch, 8) : 8);
   h->d_out3.ensure(3 * (size_t)std::max(chunk, chunk_size(h)));
   for (auto& Gp : h->groups) {

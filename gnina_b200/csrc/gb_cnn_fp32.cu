@@ -38,7 +38,9 @@ __global__ void __launch_bounds__(512) conv3d_f32_kernel(const float* __restrict
                                                          const float* __restrict__ bn_scale,
                                                          const float* __restrict__ bn_shift, float* __restrict__ out,
                                                          int out_ctot, int out_coff, int Cout, int D, int relu,
-                                                         const float* __restrict__ mask) {
+                                                         const float* __restrict__ mask,
+                                                         const float* __restrict__ out_scale = nullptr,
+                                                         int accumulate = 0) {
   constexpr int CIC = 4;
   constexpr int H = KS / 2;
   constexpr int TW = 8 + 2 * H;
@@ -113,6 +115,9 @@ __global__ void __launch_bounds__(512) conv3d_f32_kernel(const float* __restrict
       if (co0 + c < Cout) {
         float v = acc[c] + bias[co0 + c];
         if (relu) v = fmaxf(v, 0.f);
+        // dense-block backward: chain rule through the folded BatchNorm (x scale) and sum into the concat gradient
+        if (out_scale) v *= out_scale[co0 + c];
+        if (accumulate) v += ob[(size_t)c * vol];
         ob[(size_t)c * vol] = v;
       }
     }
@@ -121,7 +126,8 @@ __global__ void __launch_bounds__(512) conv3d_f32_kernel(const float* __restrict
 
 static Profiler* g_prof_tls();
 static int launch_conv(const ConvF32& c, const float* in, int in_ctot, float* out, int out_ctot, int out_coff, int D,
-                       int B, bool relu, cudaStream_t s, bool backward = false, const float* mask = nullptr) {
+                       int B, bool relu, cudaStream_t s, bool backward = false, const float* mask = nullptr,
+                       bool bn_accumulate = false) {
   char nm[64];
   snprintf(nm, sizeof nm, backward ? "f32_dgrad%d_%dx%d_d%d" : "f32_conv%d_%dx%d_d%d", c.ks, c.cin, c.cout, D);
   ProfScope ps(g_prof_tls(), nm, s);
@@ -135,7 +141,8 @@ static int launch_conv(const ConvF32& c, const float* in, int in_ctot, float* ou
 #define GB_LAUNCH(KS, COT)                                                                                     \
   conv3d_f32_kernel<KS, COT><<<g, 512, 0, s>>>(in, in_ctot, kin, kw, kb, backward ? nullptr : c.bn_scale,      \
                                                backward ? nullptr : c.bn_shift, out, out_ctot, out_coff, kout, D, \
-                                               relu ? 1 : 0, mask)
+                                               relu ? 1 : 0, mask, bn_accumulate ? c.bn_scale : nullptr,     \
+                                               bn_accumulate ? 1 : 0)
   if (c.ks == 3 && cot == 32) GB_LAUNCH(3, 32);
   else if (c.ks == 3) GB_LAUNCH(3, 16);
   else if (c.ks == 1 && cot == 32) GB_LAUNCH(1, 32);
@@ -369,6 +376,59 @@ __global__ void unpool2_f32_kernel(const float* __restrict__ dy, float* __restri
   dx[idx] = 0.125f * dy[((r * Din + (i >> 1)) * Din + (j >> 1)) * Din + (k >> 1)];
 }
 
+// max-pool backward: the gradient of a pooled voxel goes to the FIRST maximum of its 2x2x2 window in (x, y, z) scan
+// order (ATen max_pool3d keeps the first index whose value is strictly greater); channel-strided like pool2.
+__global__ void unpool2_max_f32_kernel(const float* __restrict__ dy, int dy_ctot, const float* __restrict__ xin, int x_ctot,
+                                       float* __restrict__ dx, int dx_ctot, int C, int Din, size_t total) {
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int Do = Din / 2;
+  size_t r = idx;
+  const int k = r % Do; r /= Do;
+  const int j = r % Do; r /= Do;
+  const int i = r % Do; r /= Do;
+  const int c = r % C;
+  const int b = r / C;
+  const size_t off = (size_t)(2 * i) * Din * Din + (size_t)(2 * j) * Din + 2 * k;
+  const float* p = xin + ((size_t)b * x_ctot + c) * Din * Din * Din + off;
+  float* q = dx + ((size_t)b * dx_ctot + c) * Din * Din * Din + off;
+  float best = -INFINITY;
+  int arg = 0;
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    const float x = p[(size_t)(e >> 2) * Din * Din + ((e >> 1) & 1) * Din + (e & 1)];
+    if (x > best) { best = x; arg = e; }
+  }
+  const float g = dy[(((size_t)b * dy_ctot + c) * Do + i) * Do * Do + (size_t)j * Do + k];
+#pragma unroll
+  for (int e = 0; e < 8; e++) q[(size_t)(e >> 2) * Din * Din + ((e >> 1) & 1) * Din + (e & 1)] = e == arg ? g : 0.f;
+}
+
+// global max backward + FC backward for the dense family: d feat[c] = p0 (w0[c] - w1[c]) lands on the first maximum
+// of channel c's volume, zero elsewhere.  One warp per (pose, channel).
+__global__ void dense_head_backward_kernel(const float* __restrict__ out3, const float* __restrict__ w, int F,
+                                           const float* __restrict__ fin, float* __restrict__ dfin, int vol) {
+  const int b = blockIdx.x / F, c = blockIdx.x % F;
+  const float* p = fin + (size_t)blockIdx.x * vol;
+  float best = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int e = threadIdx.x; e < vol; e += 32) {
+    const float x = p[e];
+    if (x > best) { best = x; arg = e; }
+  }
+  for (int o = 16; o; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+  }
+  const float z0 = out3[3 * b], z1 = out3[3 * b + 1];
+  const float m = fmaxf(z0, z1);
+  const float e0 = expf(z0 - m), e1 = expf(z1 - m);
+  const float g = e0 / (e0 + e1) * (w[c] - w[F + c]);
+  float* q = dfin + (size_t)blockIdx.x * vol;
+  for (int e = threadIdx.x; e < vol; e += 32) q[e] = e == arg ? g : 0.f;
+}
+
 __global__ void fc3_backward_kernel(const float* __restrict__ out3, const float* __restrict__ w, int F,
                                     float* __restrict__ dfeat) {
   const int b = blockIdx.y;
@@ -392,13 +452,21 @@ Fp32GradWorkspace::~Fp32GradWorkspace() {
     if (p) cudaFree(p);
 }
 
+static int forward_backward_dense_fp32(const Model& m, const float* grid, int B, Fp32GradWorkspace& ws, float* out3,
+                                       float* dgrid, cudaStream_t s);
+
 int forward_backward_fp32(const Model& m, const float* grid, int B, Fp32GradWorkspace& ws, float* out3, float* dgrid,
                           cudaStream_t s, Profiler* prof) {
-  if (m.arch != GB_ARCH_DEFAULT2018)
-    throw Error(GB_ERR_USAGE, "gradient path is implemented for the default2018 family only (model " + m.name + ")");
+  if (m.arch != GB_ARCH_DEFAULT2018 && m.arch != GB_ARCH_DENSE)
+    throw Error(GB_ERR_USAGE, "gradient path is implemented for the default2018 and dense families only (model " + m.name + ")");
   GB_CHECK(m.npts == 48, "CNN graphs expect a 48^3 grid");
   int launches = 0;
   t_prof = prof;
+  if (m.arch == GB_ARCH_DENSE) {
+    launches = forward_backward_dense_fp32(m, grid, B, ws, out3, dgrid, s);
+    t_prof = nullptr;
+    return launches;
+  }
   const int C = m.n_channels;
   auto conv = [&](const std::string& k) -> const ConvF32& { return m.convs.at(k); };
   const size_t v24 = 24 * 24 * 24, v12 = 12 * 12 * 12, v6 = 6 * 6 * 6;
@@ -442,6 +510,91 @@ int forward_backward_fp32(const Model& m, const float* grid, int B, Fp32GradWork
   }
   launches += 3;
   t_prof = nullptr;
+  return launches;
+}
+
+// Dense family (N2) forward keeping every activation, then the backward pass (N5):
+//   head -> global max -> block 2 -> max-pool -> bottleneck 1 -> block 1 -> max-pool -> bottleneck 0 -> block 0 ->
+//   init conv -> max-pool -> grid.
+// A dense-block layer j reads channels [0, cj) of the running concatenation F through BatchNorm (folded to
+// scale/shift on the load) and appends 16 channels.  Backward, layers in reverse order:
+//   g_j = dF[cj : cj+16] * [F[cj : cj+16] > 0];   dF[0 : cj] += bn_scale_j * conv^T(g_j)
+// (the convolution kernel's epilogue applies bn_scale and accumulates in place).
+static int forward_backward_dense_fp32(const Model& m, const float* grid, int B, Fp32GradWorkspace& ws, float* out3,
+                                       float* dgrid, cudaStream_t s) {
+  int launches = 0;
+  const int C = m.n_channels;
+  auto conv = [&](const std::string& k) -> const ConvF32& { return m.convs.at(k); };
+  const size_t v24 = 24 * 24 * 24, v12 = 12 * 12 * 12, v6 = 6 * 6 * 6;
+  // activations: 0 P0 [C@24], 1 F0 [96@24], 2 N0 [96@24], 3 F1 [160@12], 4 N1 [160@12], 5 F2 [224@6], 6 feat [224]
+  // gradients : 7 dF0 / dP0 share nothing: 7 dF2 [224@6], 8 dN1 then dF1 ping-pong, 9 dN0/dF0 ping-pong
+  ws.ensure(0, (size_t)B * C * v24);
+  ws.ensure(1, (size_t)B * 96 * v24);
+  ws.ensure(2, (size_t)B * 96 * v24);
+  ws.ensure(3, (size_t)B * 160 * v12);
+  ws.ensure(4, (size_t)B * 160 * v12);
+  ws.ensure(5, (size_t)B * 224 * v6);
+  ws.ensure(6, (size_t)B * 224);
+  ws.ensure(7, (size_t)B * 224 * v6);
+  ws.ensure(8, (size_t)B * 96 * v24);   // also holds [160@12] (smaller)
+  ws.ensure(9, (size_t)B * 96 * v24);
+  float *P0 = ws.a[0], *F0 = ws.a[1], *N0 = ws.a[2], *F1 = ws.a[3], *N1 = ws.a[4], *F2 = ws.a[5], *feat = ws.a[6];
+  float *dF2 = ws.a[7], *ga = ws.a[8], *gb2 = ws.a[9];
+  auto layer = [&](int L, int i) -> const ConvF32& {
+    return conv("dense_block_" + std::to_string(L) + ".data_enc_level" + std::to_string(L) + "_conv" + std::to_string(i));
+  };
+  // ---- forward ----
+  launches += launch_pool(grid, C, P0, C, C, 48, B, true, s);
+  launches += launch_conv(conv("data_enc_init_conv"), P0, C, F0, 96, 0, 24, B, true, s);
+  auto block = [&](int L, float* buf, int c0, int D) {
+    for (int i = 0; i < 4; i++) launches += launch_conv(layer(L, i), buf, c0 + 64, buf, c0 + 64, c0 + 16 * i, D, B, true, s);
+  };
+  block(0, F0, 32, 24);
+  launches += launch_conv(conv("data_enc_level0_bottleneck"), F0, 96, N0, 96, 0, 24, B, true, s);
+  launches += launch_pool(N0, 96, F1, 160, 96, 24, B, true, s);
+  block(1, F1, 96, 12);
+  launches += launch_conv(conv("data_enc_level1_bottleneck"), F1, 160, N1, 160, 0, 12, B, true, s);
+  launches += launch_pool(N1, 160, F2, 224, 160, 12, B, true, s);
+  block(2, F2, 160, 6);
+  global_max_kernel<<<B * 224, 32, 0, s>>>(F2, feat, (int)v6);
+  fc3_kernel<<<B, 256, 0, s>>>(feat, m.fc_w, m.fc_b, m.fc_features, out3);
+  launches += 2;
+  // ---- backward ----
+  GB_CHECK(m.fc_features == 224, "dense head features");
+  dense_head_backward_kernel<<<B * 224, 32, 0, s>>>(out3, m.fc_w, 224, F2, dF2, (int)v6);
+  launches++;
+  // block backward on a [ctot = c0 + 64] buffer pair (F activations, dF gradients); vol = D^3
+  auto block_backward = [&](int L, const float* F, float* dF, int c0, int D) {
+    const size_t vol = (size_t)D * D * D;
+    const int ctot = c0 + 64;
+    for (int i = 3; i >= 0; i--) {
+      const int cj = c0 + 16 * i;
+      // input = dF channels [cj, cj+16), masked by F's same channels; output accumulates into dF channels [0, cj)
+      launches += launch_conv(layer(L, i), dF + (size_t)cj * vol, ctot, dF, ctot, 0, D, B, false, s, true,
+                              F + (size_t)cj * vol, true);
+    }
+  };
+  block_backward(2, F2, dF2, 160, 6);
+  // max-pool 12 -> 6 fed channels [0,160) of F2 from N1
+  {
+    const size_t tot = (size_t)B * 160 * v6;
+    unpool2_max_f32_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(dF2, 224, N1, 160, ga, 160, 160, 12, tot);  // dN1
+  }
+  launches += launch_conv(conv("data_enc_level1_bottleneck"), ga, 160, gb2, 160, 0, 12, B, false, s, true, N1);       // dF1
+  block_backward(1, F1, gb2, 96, 12);
+  {
+    const size_t tot = (size_t)B * 96 * v12;
+    unpool2_max_f32_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(gb2, 160, N0, 96, ga, 96, 96, 24, tot);      // dN0
+  }
+  launches += launch_conv(conv("data_enc_level0_bottleneck"), ga, 96, gb2, 96, 0, 24, B, false, s, true, N0);         // dF0
+  block_backward(0, F0, gb2, 32, 24);
+  // init conv: gradient of its 32 output channels (first channels of F0), masked by its ReLU
+  launches += launch_conv(conv("data_enc_init_conv"), gb2, 96, ga, C, 0, 24, B, false, s, true, F0);                  // dP0
+  {
+    const size_t tot = (size_t)B * C * v24;
+    unpool2_max_f32_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(ga, C, grid, C, dgrid, C, C, 48, tot);
+  }
+  launches += 3;
   return launches;
 }
 

@@ -107,7 +107,8 @@ int gb_cnn_score_batch_models(gb_cnn* h, const float* lig_xyz, const int32_t* li
  * (TorchModel::forward with autograd + GridMaker::backward, lib/torch_model.cpp:197-221; accumulation and 1/cnt
  * scaling lib/cnn_torch_scorer.cpp:164-179).  The reference adds this to m.minus_forces (lib/model.cu:247-259);
  * untyped atoms (hydrogens) get 0.  drec_xyz (flexible-residue gradients, getReceptorGradient) must be NULL for now.
- * default2018 family.  Option "precision" selects the kernels: GB_PRECISION_FP16_TC (default) runs forward AND
+ * default2018 and dense families.  Option "precision" selects the kernels: GB_PRECISION_FP16_TC (default; ensembles
+ * of default2018-architecture models only -- an ensemble with a dense member uses the fp32 kernels) runs forward AND
  * backward on the tensor cores (fp16 gradients with loss scaling, gb_cnn_tc_grad.cu; max |error| 5e-3 of the largest
  * gradient component on the reference's vectors), GB_PRECISION_FP32 the fp32 validation kernels (4e-7). */
 int gb_cnn_score_grad(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, const int32_t* pose_offsets,

@@ -69,13 +69,12 @@ def cnn_kat(n_poses=6):
     np.savez_compressed(os.path.join(HERE, "cnn_kat.npz"), **out)
 
 
-def grad_kat(n_poses=2):
+def grad_kat(n_poses=2, name="crossdock_default2018", out_name="grad_kat.npz"):
     """Ligand-atom gradients of the reference's own TorchScript model: autograd of CE(module output, label 1) through
     the .pt (torch_model.cpp:195-199), then the oracle's GridMaker::backward."""
     from oracle import gridmaker as gm
     import torch.nn.functional as F
     k = np.load(os.path.join(HERE, "cnn_kat.npz"))
-    name = "crossdock_default2018"
     blob = model_blob.load_model(name)
     om = pipeline.OracleModel(blob)
     ts = torch.jit.load(os.path.join(REF, "gninasrc/lib/models", name + ".pt"), map_location="cpu").double()
@@ -93,8 +92,8 @@ def grad_kat(n_poses=2):
         loss.backward()
         ag = gm.grid_backward(c, xyz, ch, rad, g.grad[0].numpy().astype(np.float32))
         grads.append(ag[len(k["rec_xyz"]):]); losses.append(float(loss))
-    np.savez_compressed(os.path.join(HERE, "grad_kat.npz"), lig_grad=np.concatenate(grads), loss=np.array(losses),
-                        n_poses=n_poses, model=np.array(name))
+    np.savez_compressed(os.path.join(HERE, out_name), lig_grad=np.concatenate(grads), loss=np.array(losses),
+                        n_poses=n_poses, model=np.array(name.replace(".", "_")))
     print("grad kat: |g|max", np.abs(np.concatenate(grads)).max(), "loss", losses)
 
 
@@ -125,7 +124,11 @@ if __name__ == "__main__":
     if "--ensemble-only" in sys.argv:
         ensemble_kat()
         sys.exit(0)
+    if "--dense-grad-only" in sys.argv:
+        grad_kat(2, "dense_1.3", "grad_kat_dense.npz")   # max-pool / BatchNorm / concat backward (dense family)
+        sys.exit(0)
     if "--grad-only" not in sys.argv:
         sparse_golden()
         cnn_kat()
     grad_kat()
+    grad_kat(2, "dense_1.3", "grad_kat_dense.npz")

@@ -70,10 +70,44 @@ def test_ensemble_gradient_is_mean_of_model_gradients(kat):
 
 def test_gradient_rejects_unsupported_models():
     from gnina_b200 import CNNScorer, capi
-    s = CNNScorer(["dense_1_3"])
+    s = CNNScorer(["default2017"])
     s.set_receptor(np.zeros((1, 3), np.float32), np.array([2], np.int32))
-    with pytest.raises(capi.GbError, match="default2018"):
+    with pytest.raises(capi.GbError, match="default2018 and dense"):
         s.score_grad_batch(np.zeros((1, 3), np.float32), np.array([2], np.int32), [0, 1])
+
+
+def test_dense_gradient_matches_reference_autograd(kat, golden_dir):
+    """dense family (N2) backward: max-pool argmax routing, folded BatchNorm, concat accumulation, global max"""
+    from gnina_b200 import CNNScorer
+    g = np.load(os.path.join(golden_dir, "grad_kat_dense.npz"))
+    n = int(g["n_poses"])
+    offs = kat["pose_offsets"][:n + 1]
+    x, t = kat["lig_xyz"][:offs[-1]], kat["lig_types"][:offs[-1]]
+    s = CNNScorer([str(g["model"])])           # default precision: a dense member selects the fp32 kernels
+    s.set_receptor(kat["rec_xyz"], kat["rec_types"])
+    sc, aff, loss, var, grad = s.score_grad_batch(x, t, offs)
+    assert np.abs(loss - g["loss"]).max() < 1e-4
+    scale = np.abs(g["lig_grad"]).max()
+    assert np.abs(grad - g["lig_grad"]).max() < 5e-4 * scale
+    assert np.abs(grad[t <= 1]).max() == 0.0
+
+
+def test_default_ensemble_gradient_matches_oracle(kat):
+    """`--cnn_scoring refinement` with gnina's default ensemble (2 dense + 1 default2018): mean gradient (S1)"""
+    import torch
+    from gnina_b200 import CNNScorer, model_blob
+    from oracle import pipeline
+    n = 1
+    offs = kat["pose_offsets"][:n + 1]
+    x, t = kat["lig_xyz"][:offs[-1]], kat["lig_types"][:offs[-1]]
+    s = CNNScorer([])
+    s.set_receptor(kat["rec_xyz"], kat["rec_types"])
+    out = s.score_grad_batch(x, t, offs)
+    oms = [pipeline.OracleModel(model_blob.load_model(nm)) for nm in s.model_names]
+    ref = pipeline.score_grad(oms, kat["rec_xyz"], kat["rec_types"], x, t, offs, dtype=torch.float32)
+    assert abs(out[0][0] - ref[0][0]) < 2e-5 and abs(out[1][0] - ref[1][0]) < 1e-4 and abs(out[3][0] - ref[3][0]) < 1e-3
+    scale = np.abs(ref[4]).max()
+    assert np.abs(out[4] - ref[4]).max() < 5e-4 * scale
 
 
 # ---- fast mode: tcgen05 backward-data convolutions, fp16 gradients with loss scaling (gb_cnn_tc_grad.cu) ----------
