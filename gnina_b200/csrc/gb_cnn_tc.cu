@@ -767,6 +767,133 @@ __global__ void __launch_bounds__(256) pointwise_pool_kernel(const __half* __res
   }
 }
 
+// Variant C (current): transposed formulation with 16-byte loads and the 2x2x2 average done by a second MMA.
+//   * B operand = 16 fine voxels (two z-adjacent pooled voxels) straight from the channels-last input with ONE
+//     16-byte load per lane and 32 channels: lane (g, t) reads channels [8t, 8t+8) of voxel g.  The reduction index
+//     K may be permuted freely as long as A uses the same permutation: MMA k-slots (2t, 2t+1, 2t+8, 2t+9) of k-step
+//     s carry channels 8t + 4s + (0, 1, 2, 3) (+32 for the second 16-byte load when C = 64); the weight fragments
+//     are gathered with that permutation once, into registers.
+//   * bias + ReLU on the accumulator fragments, which re-packed to fp16 ARE the A fragments (channels x 16 voxels) of
+//     a second MMA against the constant pooling matrix S[voxel][pooled] = 1/8: no shuffles.
+//   * D is a template parameter, so the index arithmetic is constant division.
+template <int C, int D>
+__global__ void __launch_bounds__(256) pointwise_pool_mma_kernel(const __half* __restrict__ yin, const __half* __restrict__ w,
+                                                                 const float* __restrict__ bias, __half* __restrict__ xout,
+                                                                 int n_poses, int Gn, int Lpn) {
+  constexpr int MT = C / 16, KS = C / 16, LD = C / 32;  // LD: 16-byte loads per lane and voxel
+  constexpr int Dn = D / 2, Pn = Dn + 2, C8n = C / 8;
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t af[MT][KS][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) {
+      const int ch = 32 * (ks >> 1) + 8 * t + 4 * (ks & 1);
+      const __half* w0 = w + (size_t)(mt * 16 + g) * C + ch;
+      const __half* w1 = w0 + (size_t)8 * C;
+      af[mt][ks][0] = *reinterpret_cast<const uint32_t*>(w0);
+      af[mt][ks][1] = *reinterpret_cast<const uint32_t*>(w1);
+      af[mt][ks][2] = *reinterpret_cast<const uint32_t*>(w0 + 2);
+      af[mt][ks][3] = *reinterpret_cast<const uint32_t*>(w1 + 2);
+    }
+  float bs[MT][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; mt++) { bs[mt][0] = bias[mt * 16 + g]; bs[mt][1] = bias[mt * 16 + g + 8]; }
+  // pooling matrix fragment: column n = g of S; rows k < 8 -> pooled voxel 0 (A), k >= 8 -> pooled voxel 1 (B)
+  const uint32_t eighth2 = 0x30003000u;  // half2(0.125, 0.125)
+  const uint32_t sb0 = g == 0 ? eighth2 : 0u, sb1 = g == 1 ? eighth2 : 0u;
+
+  const int n_pairs = n_poses * (Dn * Dn * Dn / 2);
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int n_warps = gridDim.x * (blockDim.x >> 5);
+  const int di = (g >> 2) & 1, dj = (g >> 1) & 1, dk = g & 1;
+  const int voff = ((di * D + dj) * D + dk) * C + 8 * t;  // this lane's fine voxel inside the 2x2x2 window, channel chunk
+  // software pipeline: the 16-byte loads of the NEXT pair are issued before the MMAs of the current one
+  auto pair_base = [&](int pair) -> const __half* {
+    const int pvA = 2 * pair;
+    const int z0 = pvA % Dn;
+    int r = pvA / Dn;
+    const int y0 = r % Dn; r /= Dn;
+    const int x0 = r % Dn;
+    const int pose = r / Dn;
+    return yin + ((((size_t)pose * D + 2 * x0) * D + 2 * y0) * D + 2 * z0) * C + voff;
+  };
+  constexpr bool kPrefetch = false;  // measured: prefetching the next pair costs occupancy and is slower (r1i)
+  uint4 va[LD], vb[LD];
+  if (kPrefetch && warp_global < n_pairs) {
+    const __half* base = pair_base(warp_global);
+#pragma unroll
+    for (int l = 0; l < LD; l++) {
+      va[l] = *reinterpret_cast<const uint4*>(base + 32 * l);           // pooled voxel A
+      vb[l] = *reinterpret_cast<const uint4*>(base + 2 * C + 32 * l);   // pooled voxel B = fine z + 2
+    }
+  }
+  for (int pair = warp_global; pair < n_pairs; pair += n_warps) {
+    const int pvA = 2 * pair;
+    const int z0 = pvA % Dn;
+    int r = pvA / Dn;
+    const int y0 = r % Dn; r /= Dn;
+    const int x0 = r % Dn;
+    const int pose = r / Dn;
+    if (!kPrefetch) {
+      const __half* base = pair_base(pair);
+#pragma unroll
+      for (int l = 0; l < LD; l++) {
+        va[l] = *reinterpret_cast<const uint4*>(base + 32 * l);
+        vb[l] = *reinterpret_cast<const uint4*>(base + 2 * C + 32 * l);
+      }
+    }
+    uint4 na[LD], nb2[LD];
+    const bool more = kPrefetch && pair + n_warps < n_pairs;
+    if (more) {
+      const __half* base = pair_base(pair + n_warps);
+#pragma unroll
+      for (int l = 0; l < LD; l++) {
+        na[l] = *reinterpret_cast<const uint4*>(base + 32 * l);
+        nb2[l] = *reinterpret_cast<const uint4*>(base + 2 * C + 32 * l);
+      }
+    }
+    const int grp = pose / Gn, q = pose % Gn;
+    const size_t pos = (size_t)q * Pn * Pn + (size_t)(y0 + 1) * Pn + (z0 + 1);
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+      float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < KS; ks++) {
+        const uint32_t* pa = reinterpret_cast<const uint32_t*>(&va[ks >> 1]);
+        const uint32_t* pb = reinterpret_cast<const uint32_t*>(&vb[ks >> 1]);
+        mma_16816(ca, af[mt][ks], pa[2 * (ks & 1)], pa[2 * (ks & 1) + 1]);
+        mma_16816(cb, af[mt][ks], pb[2 * (ks & 1)], pb[2 * (ks & 1) + 1]);
+      }
+      // ca: channels (mt*16 + g | + 8) x fine voxels (2t, 2t+1) of A; cb: same for B
+      uint32_t a2[4];
+      {
+        const __half2 h0 = __floats2half2_rn(fmaxf(ca[0] + bs[mt][0], 0.f), fmaxf(ca[1] + bs[mt][0], 0.f));
+        const __half2 h1 = __floats2half2_rn(fmaxf(ca[2] + bs[mt][1], 0.f), fmaxf(ca[3] + bs[mt][1], 0.f));
+        const __half2 h2 = __floats2half2_rn(fmaxf(cb[0] + bs[mt][0], 0.f), fmaxf(cb[1] + bs[mt][0], 0.f));
+        const __half2 h3 = __floats2half2_rn(fmaxf(cb[2] + bs[mt][1], 0.f), fmaxf(cb[3] + bs[mt][1], 0.f));
+        a2[0] = *reinterpret_cast<const uint32_t*>(&h0); a2[1] = *reinterpret_cast<const uint32_t*>(&h1);
+        a2[2] = *reinterpret_cast<const uint32_t*>(&h2); a2[3] = *reinterpret_cast<const uint32_t*>(&h3);
+      }
+      float pz[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_16816(pz, a2, sb0, sb1);
+      // lanes t == 0: pz[0], pz[1] = channel mt*16+g of pooled A, B; pz[2], pz[3] = channel mt*16+8+g
+      if (t == 0) {
+        __half* o0 = xout + ((((size_t)grp * Dn + x0) * C8n + 2 * mt) * Lpn + pos) * 8 + g;
+        o0[0] = __float2half(pz[0]);
+        o0[8] = __float2half(pz[1]);
+        o0[(size_t)Lpn * 8] = __float2half(pz[2]);
+        o0[(size_t)Lpn * 8 + 8] = __float2half(pz[3]);
+      }
+    }
+    if (more) {
+#pragma unroll
+      for (int l = 0; l < LD; l++) { va[l] = na[l]; vb[l] = nb2[l]; }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Kernel D: FC heads on conv5's channels-last fp16 output [pose][216][128].
 __global__ void __launch_bounds__(256) fc_heads_f16_kernel(const __half* __restrict__ y5, const float* __restrict__ w,
@@ -966,7 +1093,12 @@ int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspa
   if (x0_consumed) GB_CUDA(cudaEventRecord(x0_consumed, s));
   {
     ProfScope ps(prof, "tc_pw2_pool", s);
-    pointwise_pool_rows_kernel<32><<<pw_blocks, 256, 0, s>>>(Y, tw->pw2.w, tw->pw2.bias, X2, 24, nb, L3.G, L3.Lp);
+    static const int pw_variant = getenv("GB_TC_PW") ? atoi(getenv("GB_TC_PW")) : 2;
+    if (pw_variant == 2)
+      pointwise_pool_mma_kernel<32, 24><<<pw_blocks, 256, 0, s>>>(Y, tw->pw2.w, tw->pw2.bias, reinterpret_cast<__half*>(X2), nb,
+                                                                  L3.G, L3.Lp);
+    else
+      pointwise_pool_rows_kernel<32><<<pw_blocks, 256, 0, s>>>(Y, tw->pw2.w, tw->pw2.bias, X2, 24, nb, L3.G, L3.Lp);
   }
   {
     ProfScope ps(prof, "tc_conv3_3x3x3_32x64_d12", s);
@@ -974,7 +1106,12 @@ int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspa
   }
   {
     ProfScope ps(prof, "tc_pw4_pool", s);
-    pointwise_pool_kernel<64><<<pw_blocks, 256, 0, s>>>(Y3, tw->pw4.w, tw->pw4.bias, reinterpret_cast<__half*>(X4), 12, nb, L5.G, L5.Lp);
+    static const int pw_variant = getenv("GB_TC_PW") ? atoi(getenv("GB_TC_PW")) : 2;
+    if (pw_variant == 2)
+      pointwise_pool_mma_kernel<64, 12><<<pw_blocks, 256, 0, s>>>(Y3, tw->pw4.w, tw->pw4.bias, reinterpret_cast<__half*>(X4), nb,
+                                                                  L5.G, L5.Lp);
+    else
+      pointwise_pool_kernel<64><<<pw_blocks, 256, 0, s>>>(Y3, tw->pw4.w, tw->pw4.bias, reinterpret_cast<__half*>(X4), 12, nb, L5.G, L5.Lp);
   }
   {
     ProfScope ps(prof, "tc_conv5_3x3x3_64x128_d6", s);

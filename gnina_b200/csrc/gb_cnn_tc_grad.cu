@@ -110,94 +110,165 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 }
 __device__ __forceinline__ float2 unpack_h2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
 
-template <int C>
+// Data movement (same ideas as pointwise_pool_mma_kernel, gb_cnn_tc.cu):
+//   * y rows are read with ONE 16-byte load per lane and 32 channels -- lane (g, t) holds channels [8t, 8t+8) of voxel
+//     rows g and g+8 -- and used as A fragments under a permutation of the reduction index (k-slots 2t, 2t+1, 2t+8,
+//     2t+9 of k-step s carry channels 8t + 4s + 0..3, +32 for the second load when C = 64);
+//   * the output channels of the second GEMM are permuted the other way round (column pair (2t, 2t+1) of n-tile j is
+//     channel pair 8t + 2j, +1), so that a lane's four accumulator pairs are exactly the 16-byte element (chunk t,
+//     this voxel) of the chunk-planar output -- one 16-byte store -- and the y > 0 mask comes from the registers the
+//     lane already loaded;
+//   * both weight matrices live in shared memory in FRAGMENT order (one conflict-free 8-byte load per MMA).
+template <int C, int D>
 __global__ void __launch_bounds__(256) pw_backward_kernel(const __half* __restrict__ yin, const __half* __restrict__ w,
                                                           const float* __restrict__ bias, const uint32_t* __restrict__ gxa,
-                                                          const uint32_t* __restrict__ gxb, uint32_t* __restrict__ out, int D,
+                                                          const uint32_t* __restrict__ gxb, uint4* __restrict__ out,
                                                           int n_poses, int Gn, int Lpn, int Gf, int Lpf) {
-  constexpr int NT = C / 8, KS = C / 16, WP = C + 8;  // row pitch C + 8 halves: conflict-free fragment loads
-  __shared__ __align__(16) __half s_w[C * WP];   // W  [co][ci]
-  __shared__ __align__(16) __half s_wt[C * WP];  // W^T [ci][co]
+  constexpr int NT = C / 8, KS = C / 16, LD = C / 32;
+  constexpr int Dn = D / 2, Pn = Dn + 2, Pf = D + 2;
+  __shared__ uint2 s_wf[NT * KS * 32];   // first GEMM  u = y W^T : B fragments, k permuted
+  __shared__ uint2 s_wtf[NT * KS * 32];  // second GEMM dy = d W  : B fragments, n permuted
   __shared__ float s_b[C];
-  for (int e = threadIdx.x; e < C * C; e += 256) {
-    const int r = e / C, c = e % C;
-    const __half v = w[e];
-    s_w[r * WP + c] = v;
-    s_wt[c * WP + r] = v;
+  for (int e = threadIdx.x; e < NT * KS * 32; e += 256) {
+    const int ln = e & 31, ks = (e >> 5) % KS, nt = e / (32 * KS);
+    const int gg = ln >> 2, tt = ln & 3;
+    {
+      const int co = nt * 8 + gg, ch = 32 * (ks >> 1) + 8 * tt + 4 * (ks & 1);
+      const uint32_t* p = reinterpret_cast<const uint32_t*>(w + (size_t)co * C + ch);
+      s_wf[e] = make_uint2(p[0], p[1]);
+    }
+    {
+      // n-tile nt, column gg <-> input channel ci; rows k = output channels 16 ks + (2tt, 2tt+1 | +8)
+      const int ci = 32 * (nt >> 2) + 8 * (gg >> 1) + 2 * (nt & 3) + (gg & 1);
+      const int co = 16 * ks + 2 * tt;
+      const __half2 lo = __halves2half2(w[(size_t)co * C + ci], w[(size_t)(co + 1) * C + ci]);
+      const __half2 hi = __halves2half2(w[(size_t)(co + 8) * C + ci], w[(size_t)(co + 9) * C + ci]);
+      s_wtf[e] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    }
   }
   if (threadIdx.x < C) s_b[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int Dn = D / 2, Pn = Dn + 2, Pf = D + 2;
-  const int n_pairs = n_poses * Dn * Dn * Dn / 2;
+  // Work item = 16 fine voxels (the 16 MMA rows; lane (g, t) owns rows g and g+8).  The backward pass has no pooling
+  // reduction -- every fine voxel just reads its pooled parent -- so any 16 voxels do.  D = 24: row g = (x, y, zb+g),
+  // row g+8 = (x, y+1, zb+g) with zb a multiple of 8, so that the 8 lanes of a quad-column write 128 contiguous bytes
+  // of each chunk plane (the 2x2x2-window mapping writes isolated 16-byte pieces: half-filled 32-byte sectors); both
+  // rows share their pooled parent.  D = 12 (8 does not divide 12): rows = the 2x2x2 windows of two z-adjacent pooled
+  // voxels.
+  constexpr bool kRowZ = D % 8 == 0;
+  constexpr int kItemsPerPose = D * D * D / 16;
+  const int n_items = n_poses * kItemsPerPose;
   const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int n_warps = gridDim.x * (blockDim.x >> 5);
-  const int di = (g >> 2) & 1, dj = (g >> 1) & 1, dk = g & 1;
-  for (int pair = warp_global; pair < n_pairs; pair += n_warps) {
-    const int pvA = 2 * pair;
-    const int z0 = pvA % Dn;
-    int r = pvA / Dn;
-    const int y0 = r % Dn; r /= Dn;
-    const int x0 = r % Dn;
-    const int pose = r / Dn;
-    const int xf = 2 * x0 + di, yf = 2 * y0 + dj, zf = 2 * z0 + dk;
-    const __half* rowA = yin + ((((size_t)pose * D + xf) * D + yf) * D + zf) * C;
-    const __half* rowB = rowA + (size_t)2 * C;
-    uint32_t a[KS][4];
+  for (int item = warp_global; item < n_items; item += n_warps) {
+    int pose, xa, ya_, za, x0, y0a, z0a, z0b;  // fine voxel of row g; pooled parents of rows g / g+8 (x0, y0a shared)
+    int rowb_off, posb_off;                    // row g+8 relative to row g: input halves, output positions
+    if constexpr (kRowZ) {
+      const int zb = (item % (D / 8)) * 8;
+      int r = item / (D / 8);
+      const int yp = r % Dn; r /= Dn;
+      xa = r % D;
+      pose = r / D;
+      ya_ = 2 * yp; za = zb + g;
+      x0 = xa >> 1; y0a = yp; z0a = za >> 1; z0b = z0a;
+      rowb_off = D * C; posb_off = Pf;
+    } else {
+      const int pvA = 2 * item;
+      const int z0 = pvA % Dn;
+      int r = pvA / Dn;
+      y0a = r % Dn; r /= Dn;
+      x0 = r % Dn;
+      pose = r / Dn;
+      xa = 2 * x0 + ((g >> 2) & 1); ya_ = 2 * y0a + ((g >> 1) & 1); za = 2 * z0 + (g & 1);
+      z0a = z0; z0b = z0 + 1;
+      rowb_off = 2 * C; posb_off = 2;
+    }
+    const __half* rowA = yin + ((((size_t)pose * D + xa) * D + ya_) * D + za) * C + 8 * t;
+    uint4 ya[LD], yb[LD];
 #pragma unroll
-    for (int ks = 0; ks < KS; ks++) {
-      a[ks][0] = *reinterpret_cast<const uint32_t*>(rowA + ks * 16 + 2 * t);
-      a[ks][1] = *reinterpret_cast<const uint32_t*>(rowB + ks * 16 + 2 * t);
-      a[ks][2] = *reinterpret_cast<const uint32_t*>(rowA + ks * 16 + 8 + 2 * t);
-      a[ks][3] = *reinterpret_cast<const uint32_t*>(rowB + ks * 16 + 8 + 2 * t);
+    for (int l = 0; l < LD; l++) {
+      ya[l] = *reinterpret_cast<const uint4*>(rowA + 32 * l);
+      yb[l] = *reinterpret_cast<const uint4*>(rowA + rowb_off + 32 * l);
+    }
+    // gradient gathers issued before the first GEMM so their latency hides behind it
+    const int grpn = pose / Gn, qn = pose % Gn;
+    const size_t posn = (size_t)qn * Pn * Pn + (size_t)(y0a + 1) * Pn + (z0a + 1);
+    const int gb_off = (z0b - z0a) * 4;  // uint32 units; 0 when both rows share the parent
+    uint32_t gra[NT], grb[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+      const size_t gi = ((((size_t)grpn * Dn + x0) * NT + nt) * Lpn + posn) * 4 + t;
+      gra[nt] = gxa[gi];
+      grb[nt] = kRowZ ? gra[nt] : gxa[gi + gb_off];
+    }
+    uint32_t gra2[NT], grb2[NT];
+    if (gxb) {
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) {
+        const size_t gi = ((((size_t)grpn * Dn + x0) * NT + nt) * Lpn + posn) * 4 + t;
+        gra2[nt] = gxb[gi];
+        grb2[nt] = kRowZ ? gra2[nt] : gxb[gi + gb_off];
+      }
     }
     // u = W y (+ b): pre-activation of the pointwise conv, for its ReLU mask
     float acc[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; nt++) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
 #pragma unroll
-    for (int ks = 0; ks < KS; ks++)
+    for (int ks = 0; ks < KS; ks++) {
+      const uint32_t* pa = reinterpret_cast<const uint32_t*>(&ya[ks >> 1]);
+      const uint32_t* pb = reinterpret_cast<const uint32_t*>(&yb[ks >> 1]);
+      const uint32_t a[4] = {pa[2 * (ks & 1)], pb[2 * (ks & 1)], pa[2 * (ks & 1) + 1], pb[2 * (ks & 1) + 1]};
 #pragma unroll
       for (int nt = 0; nt < NT; nt++) {
-        const __half* wr = s_w + (nt * 8 + g) * WP + ks * 16 + 2 * t;
-        mma_16816_g(acc[nt], a[ks], *reinterpret_cast<const uint32_t*>(wr), *reinterpret_cast<const uint32_t*>(wr + 8));
+        const uint2 b = s_wf[(nt * KS + ks) * 32 + lane];
+        mma_16816_g(acc[nt], a, b.x, b.y);
       }
-    // d = unpool(gx) * [u > 0], re-packed from accumulator fragments into A fragments
-    const int grpn = pose / Gn, qn = pose % Gn;
-    const size_t posn = (size_t)qn * Pn * Pn + (size_t)(y0 + 1) * Pn + (z0 + 1);
+    }
+    // d = unpool(gx) * [u > 0], re-packed from accumulator fragments into A fragments (natural channel order)
     uint32_t a2[KS][4];
 #pragma unroll
     for (int nt = 0; nt < NT; nt++) {
-      const size_t gi = ((((size_t)grpn * Dn + x0) * NT + nt) * Lpn + posn) * 4 + t;
-      float2 fa = unpack_h2(gxa[gi]), fb = unpack_h2(gxa[gi + 4]);
+      float2 fa = unpack_h2(gra[nt]), fb = unpack_h2(grb[nt]);
       if (gxb) {
-        const float2 fa2 = unpack_h2(gxb[gi]), fb2 = unpack_h2(gxb[gi + 4]);
+        const float2 fa2 = unpack_h2(gra2[nt]), fb2 = unpack_h2(grb2[nt]);
         fa.x += fa2.x; fa.y += fa2.y; fb.x += fb2.x; fb.y += fb2.y;
       }
       const float b0 = s_b[nt * 8 + 2 * t], b1 = s_b[nt * 8 + 2 * t + 1];
       a2[nt >> 1][(nt & 1) * 2 + 0] = pack_h2(acc[nt][0] + b0 > 0.f ? fa.x : 0.f, acc[nt][1] + b1 > 0.f ? fa.y : 0.f);
       a2[nt >> 1][(nt & 1) * 2 + 1] = pack_h2(acc[nt][2] + b0 > 0.f ? fb.x : 0.f, acc[nt][3] + b1 > 0.f ? fb.y : 0.f);
     }
-    // d_in = d W  (rows voxels, K = co, N = ci)
+    // d_in = d W  (rows voxels, K = co natural, N = ci permuted: column pair (2t, 2t+1) of n-tile j = channels 8t+2j, +1)
 #pragma unroll
     for (int nt = 0; nt < NT; nt++) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
 #pragma unroll
     for (int ks = 0; ks < KS; ks++)
 #pragma unroll
       for (int nt = 0; nt < NT; nt++) {
-        const __half* wr = s_wt + (nt * 8 + g) * WP + ks * 16 + 2 * t;
-        mma_16816_g(acc[nt], a2[ks], *reinterpret_cast<const uint32_t*>(wr), *reinterpret_cast<const uint32_t*>(wr + 8));
+        const uint2 b = s_wtf[(nt * KS + ks) * 32 + lane];
+        mma_16816_g(acc[nt], a2[ks], b.x, b.y);
       }
-    // mask with y > 0 (ReLU of the 3x3x3 conv) and store: row g -> fine voxel of A, row g + 8 -> of B (z + 2)
+    // mask with y > 0 (ReLU of the 3x3x3 conv) and store one 16-byte element per row and channel chunk
     const int grpf = pose / Gf, qf = pose % Gf;
-    const size_t posf = (size_t)qf * Pf * Pf + (size_t)(yf + 1) * Pf + (zf + 1);
+    const size_t posf = (size_t)qf * Pf * Pf + (size_t)(ya_ + 1) * Pf + (za + 1);
 #pragma unroll
-    for (int nt = 0; nt < NT; nt++) {
-      const float2 ya = unpack_h2(a[nt >> 1][(nt & 1) * 2 + 0]), yb = unpack_h2(a[nt >> 1][(nt & 1) * 2 + 1]);
-      const size_t oi = ((((size_t)grpf * D + xf) * NT + nt) * Lpf + posf) * 4 + t;
-      out[oi] = pack_h2(ya.x > 0.f ? acc[nt][0] : 0.f, ya.y > 0.f ? acc[nt][1] : 0.f);
-      out[oi + 8] = pack_h2(yb.x > 0.f ? acc[nt][2] : 0.f, yb.y > 0.f ? acc[nt][3] : 0.f);
+    for (int l = 0; l < LD; l++) {
+      uint4 oa, ob;
+      uint32_t* wa = reinterpret_cast<uint32_t*>(&oa);
+      uint32_t* wb = reinterpret_cast<uint32_t*>(&ob);
+      const uint32_t* pa = reinterpret_cast<const uint32_t*>(&ya[l]);
+      const uint32_t* pb = reinterpret_cast<const uint32_t*>(&yb[l]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const float2 va = unpack_h2(pa[j]), vb = unpack_h2(pb[j]);
+        const float* c = acc[4 * l + j];
+        wa[j] = pack_h2(va.x > 0.f ? c[0] : 0.f, va.y > 0.f ? c[1] : 0.f);
+        wb[j] = pack_h2(vb.x > 0.f ? c[2] : 0.f, vb.y > 0.f ? c[3] : 0.f);
+      }
+      uint4* dst = out + (((size_t)grpf * D + xa) * NT + 4 * l + t) * Lpf + posf;
+      dst[0] = oa;
+      dst[posb_off] = ob;
     }
   }
 }
@@ -301,9 +372,9 @@ int tc_backward(const Model& m, const TcPoseBatch& pb, TcWorkspace& ws, const fl
   }
   {
     ProfScope ps(prof, "tcg_unpool_dpw4", s);
-    pw_backward_kernel<64><<<pw_blocks, 256, 0, s>>>(Y3, tw->pw4.w, tw->pw4.bias, reinterpret_cast<const uint32_t*>(GX4a),
-                                                     reinterpret_cast<const uint32_t*>(GX4b), reinterpret_cast<uint32_t*>(GY3),
-                                                     12, nb, L5.G, L5.Lp, L3.G, L3.Lp);
+    pw_backward_kernel<64, 12><<<pw_blocks, 256, 0, s>>>(Y3, tw->pw4.w, tw->pw4.bias, reinterpret_cast<const uint32_t*>(GX4a),
+                                                         reinterpret_cast<const uint32_t*>(GX4b), GY3, nb, L5.G, L5.Lp, L3.G,
+                                                         L3.Lp);
   }
   {
     ProfScope ps(prof, "tcg_dconv3_3x3x3_64x32_d12", s);
@@ -311,8 +382,8 @@ int tc_backward(const Model& m, const TcPoseBatch& pb, TcWorkspace& ws, const fl
   }
   {
     ProfScope ps(prof, "tcg_unpool_dpw2", s);
-    pw_backward_kernel<32><<<pw_blocks, 256, 0, s>>>(Y1, tw->pw2.w, tw->pw2.bias, reinterpret_cast<const uint32_t*>(GX2), nullptr,
-                                                     reinterpret_cast<uint32_t*>(GY1), 24, nb, L3.G, L3.Lp, L1.G, L1.Lp);
+    pw_backward_kernel<32, 24><<<pw_blocks, 256, 0, s>>>(Y1, tw->pw2.w, tw->pw2.bias, reinterpret_cast<const uint32_t*>(GX2),
+                                                         nullptr, GY1, nb, L3.G, L3.Lp, L1.G, L1.Lp);
   }
   {
     ProfScope ps(prof, "tcg_dconv1_3x3x3_32x28_d24", s);
