@@ -309,31 +309,40 @@ __global__ void __launch_bounds__(512) voxelize_pool_f16_kernel(const float4* __
         hit = b.x >= wlx - reach && b.x <= wlx + wsx + reach && b.y >= wly - reach && b.y <= wly + wsx + reach &&
               b.z >= wlz - reach && b.z <= wlz + wsz + reach;
       }
-      unsigned mask = __ballot_sync(0xffffffffu, hit);
-      while (mask) {
-        const int mm = wb + __ffs(mask) - 1;
-        mask &= mask - 1;
+      // Two-level test.  (1) warp level: candidates whose reach touches the warp's 4x4x2 box (ballot above).
+      // (2) lane level: the subset each lane's own pooled voxel can see.  A reach sphere (r ~ 3.3 A) fills only ~20 %
+      // of the boxes it touches, so evaluating a candidate on all 32 lanes wastes most of the work; instead every
+      // lane walks ITS bit mask (divergent loop, trip count = the busiest lane's), in list order, so the sums and
+      // the channel flushes are exactly those of the all-lanes loop minus terms that are identically zero.
+      const unsigned wmask = __ballot_sync(0xffffffffu, hit);
+      unsigned lmask = 0u;
+      for (unsigned mk = wmask; mk; mk &= mk - 1) {
+        const int bit = __ffs(mk) - 1;
+        const float4 b = s_atom[wb + bit];
+        const float dx = (cx - b.x) * b.w, dy = (cy - b.y) * b.w, dz = (cz - b.z) * b.w;  // in units of r
+        if (dx * dx + dy * dy + dz * dz < s_thr2[wb + bit]) lmask |= 1u << bit;
+      }
+      while (lmask) {
+        const int mm = wb + __ffs(lmask) - 1;
+        lmask &= lmask - 1;
         const int chm = s_ch[mm];
         if (chm != cur) {
           if (cur >= 0) s_out[cur * 512 + pv] = __float2half(flush_value());
           cur = chm;
         }
         const float4 b = s_atom[mm];
-        const float dx = (cx - b.x) * b.w, dy = (cy - b.y) * b.w, dz = (cz - b.z) * b.w;  // in units of r
-        const float tcen = dx * dx + dy * dy + dz * dz;
-        if (__any_sync(0xffffffffu, tcen < s_thr2[mm])) {
-          const float h = hres * b.w;
-          const float x0 = dx - h, x1 = dx + h, y0 = dy - h, y1 = dy + h, z0 = dz - h, z1 = dz + h;
-          const float sx0 = x0 * x0, sx1 = x1 * x1, sy0 = y0 * y0, sy1 = y1 * y1, sz0 = z0 * z0, sz1 = z1 * z1;
-          const float s00 = sx0 + sy0, s01 = sx0 + sy1, s10 = sx1 + sy0, s11 = sx1 + sy1;
-          if constexpr (kMax) {
-            am[0] += density_t(s00 + sz0); am[1] += density_t(s00 + sz1); am[2] += density_t(s01 + sz0);
-            am[3] += density_t(s01 + sz1); am[4] += density_t(s10 + sz0); am[5] += density_t(s10 + sz1);
-            am[6] += density_t(s11 + sz0); am[7] += density_t(s11 + sz1);
-          } else {
-            acc += density_t(s00 + sz0) + density_t(s00 + sz1) + density_t(s01 + sz0) + density_t(s01 + sz1) +
-                   density_t(s10 + sz0) + density_t(s10 + sz1) + density_t(s11 + sz0) + density_t(s11 + sz1);
-          }
+        const float dx = (cx - b.x) * b.w, dy = (cy - b.y) * b.w, dz = (cz - b.z) * b.w;
+        const float h = hres * b.w;
+        const float x0 = dx - h, x1 = dx + h, y0 = dy - h, y1 = dy + h, z0 = dz - h, z1 = dz + h;
+        const float sx0 = x0 * x0, sx1 = x1 * x1, sy0 = y0 * y0, sy1 = y1 * y1, sz0 = z0 * z0, sz1 = z1 * z1;
+        const float s00 = sx0 + sy0, s01 = sx0 + sy1, s10 = sx1 + sy0, s11 = sx1 + sy1;
+        if constexpr (kMax) {
+          am[0] += density_t(s00 + sz0); am[1] += density_t(s00 + sz1); am[2] += density_t(s01 + sz0);
+          am[3] += density_t(s01 + sz1); am[4] += density_t(s10 + sz0); am[5] += density_t(s10 + sz1);
+          am[6] += density_t(s11 + sz0); am[7] += density_t(s11 + sz1);
+        } else {
+          acc += density_t(s00 + sz0) + density_t(s00 + sz1) + density_t(s01 + sz0) + density_t(s01 + sz1) +
+                 density_t(s10 + sz0) + density_t(s10 + sz1) + density_t(s11 + sz0) + density_t(s11 + sz1);
         }
       }
     }
