@@ -147,6 +147,20 @@ def main():
     out.append({"row": "dock_monte_carlo chains (V10+V11)", "value": n_chains * steps / dt, "unit": "MC steps/s",
                 "chains": n_chains, "steps_per_chain": steps, "ligands_per_s_at_exhaustiveness_64": n_chains / 64 / dt,
                 "cpu_oracle": cpu, "cpu_sample": "3 chains, scalar C, 1 thread"})
+    # --- config 3 glue: cache build -> 64 chains -> merge -> CNN rescoring -> exact affinity -> ranked modes ---
+    from gnina_b200 import docking
+    cs = CNNScorer(["crossdock_default2018"], precision=1)
+    cs.set_receptor(rec_xyz, rec_t)
+    ref_steps = docking.reference_num_steps(len(lig["types"]), 6 + v.T)
+    st = 200
+    docking.dock_ligand(v, cs, lig, [-6, -6, -6], [6, 6, 6], exhaustiveness=64, seed=1, num_steps=st)
+    t0 = time.perf_counter()
+    poses = docking.dock_ligand(v, cs, lig, [-6, -6, -6], [6, 6, 6], exhaustiveness=64, seed=2, num_steps=st)
+    dt = time.perf_counter() - t0
+    out.append({"row": "dock + rescore pipeline, one ligand at a time (config 3 glue)", "value": 1.0 / dt, "unit": "ligands/s",
+                "exhaustiveness": 64, "mc_steps_per_chain": st, "reference_formula_steps": ref_steps, "modes_out": len(poses),
+                "note": "64 chains = 64 warps: one ligand cannot fill the GPU; throughput needs ligands in flight concurrently "
+                        "(the MC row above runs 4096 chains per launch)"})
     for r in out:
         print(json.dumps(r))
 

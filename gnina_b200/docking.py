@@ -1,0 +1,106 @@
+"""BASELINE config 3 glued together: the docking branch of gnina's `main_procedure` (main/main.cpp:312-400) over the
+device kernels — everything between "ligand topology in" and "ranked poses out":
+
+  cache::populate (V4)  ->  parallel_mc = all chains in one launch (V10/V11)  ->  merge_output_containers
+  (lib/parallel_mc.cpp:165-181, min_rmsd forced to 2)  ->  CNN rescoring of every kept pose (get_cnn_info,
+  main.cpp:195-207, one batch call)  ->  final Vina energy (V12)  ->  sort by CNNscore (main.cpp:349-360)
+  ->  remove_redundant (main.cpp:182-192)  ->  first num_modes.
+
+Not here (DESIGN.md "next"): refine_structure's non-cache BFGS between the search and the rescoring.
+Host logic (containers, sorting) is numpy; nothing in this module imports the CPU oracle."""
+import numpy as np
+
+
+def rmsd_upper_bound(a, b):
+    """lib/coords.cpp:24-30"""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.sqrt(((a - b) ** 2).sum() / len(a))) if len(a) else 0.0
+
+
+class OutputContainer:
+    """output_container + add_to_output_container (lib/coords.cpp:32-57): RMSD-deduplicated, energy-sorted, capped."""
+
+    def __init__(self, min_rmsd, max_size):
+        self.min_rmsd, self.max_size = float(min_rmsd), int(max_size)
+        self.items = []          # dicts: e, coords, conf (+ whatever the caller attaches later)
+
+    def add(self, e, coords, conf):
+        t = {"e": float(e), "coords": np.asarray(coords, np.float32), "conf": np.asarray(conf, np.float32)}
+        best, best_r = len(self.items), np.inf
+        for i, o in enumerate(self.items):                       # find_closest
+            r = rmsd_upper_bound(t["coords"], o["coords"])
+            if i == 0 or r < best_r:
+                best, best_r = i, r
+        if best < len(self.items) and best_r < self.min_rmsd:    # a very similar one: keep the better
+            if t["e"] < self.items[best]["e"]:
+                self.items[best] = t
+        elif len(self.items) < self.max_size:
+            self.items.append(t)
+        elif self.items and t["e"] < self.items[-1]["e"]:        # full: replace the worst
+            self.items[-1] = t
+        self.items.sort(key=lambda o: o["e"])                    # stable, like ptr_vector::sort on e
+
+
+def merge_chains(e, confs, coords, n_out, num_saved_mins):
+    """merge_output_containers over the chains' containers, in chain order; min_rmsd = 2 (parallel_mc.cpp:175)."""
+    out = OutputContainer(2.0, num_saved_mins)
+    for c in range(len(n_out)):
+        for k in range(int(n_out[c])):
+            out.add(e[c, k], coords[c, k], confs[c, k])
+    return out
+
+
+def remove_redundant(items, min_rmsd):
+    """main/main.cpp:182-192 (note: keeps a pose whose closest kept pose is EXACTLY min_rmsd away or further: '>')."""
+    kept = []
+    for it in items:
+        best = min((rmsd_upper_bound(it["coords"], k["coords"]) for k in kept), default=None)
+        if best is None or best > min_rmsd:
+            kept.append(it)
+    return kept
+
+
+def reference_num_steps(n_movable_atoms, n_dof):
+    """main/main.cpp:442-443"""
+    return int(70 * 3 * (50 + n_movable_atoms + 10 * n_dof) // 2)
+
+
+def dock_ligand(vina, cnn, lig, corner1, corner2, exhaustiveness=8, seed=1, num_steps=None, maxiters=None,
+                num_saved_mins=50, num_modes=9, out_min_rmsd=1.0, sort_order="cnnscore", grid_spacing=0.375,
+                grid_margin=4.0):
+    """vina: VinaScorer with the receptor set; cnn: CNNScorer with the same receptor set; lig: ligand topology dict.
+    -> list of dicts (conf, coords, e = final Vina affinity, search_e, cnnscore, cnnaffinity, cnnvariance), ranked."""
+    types = np.asarray(lig["types"], np.int32)
+    corner1 = np.asarray(corner1, np.float32); corner2 = np.asarray(corner2, np.float32)
+    vina.set_ligand(lig)
+    T = vina.T
+    # grid over the search box plus a margin, granularity 0.375 A (main.cpp:622)
+    begin = corner1 - grid_margin
+    n = np.ceil((corner2 + grid_margin - begin) / grid_spacing).astype(np.int32)
+    end = begin + n * grid_spacing
+    vina.cache_build(begin.tolist(), end.tolist(), n.tolist(), sorted(set(int(t) for t in types if t > 1)))
+    if num_steps is None:
+        num_steps = reference_num_steps(len(types), 6 + T)
+    if maxiters is None:
+        maxiters = int((25 + len(types)) // 3)                     # ssd_par.evals, main.cpp:454
+    rs = np.random.RandomState(seed)
+    seeds = rs.randint(1, 1000000, size=exhaustiveness).astype(np.uint32)   # random_int(0, 1000000, generator)
+    e, X, n_out = vina.mc(seeds, corner1, corner2, num_steps=num_steps, maxiters=maxiters, num_saved_mins=num_saved_mins)
+    flat = X.reshape(-1, 7 + T)
+    _, _, coords = vina.eval_deriv(flat, coords=True)
+    coords = coords.reshape(len(seeds), num_saved_mins, len(types), 3)
+    merged = merge_chains(e, X, coords, n_out, num_saved_mins).items
+    if not merged:
+        return []
+    # one CNN batch call and one exact-scoring call over all kept poses
+    xyz = np.concatenate([m["coords"] for m in merged]).astype(np.float32)
+    offs = (np.arange(len(merged) + 1) * len(types)).astype(np.int32)
+    tt = np.tile(types, len(merged))
+    sc, aff, _, var = cnn.score_batch(xyz, tt, offs)
+    _, affin = vina.score_exact(xyz, tt, offs, num_tors=np.full(len(merged), T, np.float32))
+    for i, m in enumerate(merged):
+        m["search_e"] = m["e"]
+        m["e"] = float(affin[i]); m["cnnscore"] = float(sc[i]); m["cnnaffinity"] = float(aff[i]); m["cnnvariance"] = float(var[i])
+    key = {"cnnscore": lambda o: -o["cnnscore"], "cnnaffinity": lambda o: -o["cnnaffinity"], "energy": lambda o: o["e"]}[sort_order]
+    merged.sort(key=key)
+    return remove_redundant(merged, out_min_rmsd)[:num_modes]

@@ -1,0 +1,77 @@
+"""Config 3 glue (gnina_b200/docking.py): host-side containers against hand-worked cases of lib/coords.cpp:32-57,
+lib/parallel_mc.cpp:165-181 and main/main.cpp:182-192 (CPU); the whole dock -> rescore pipeline on the device (GPU)."""
+import numpy as np
+import pytest
+from gnina_b200 import docking
+
+
+def _pose(shift, n=4):
+    base = np.arange(3 * n, dtype=np.float32).reshape(n, 3)
+    return base + np.float32(shift)
+
+
+def test_rmsd_upper_bound():
+    a, b = _pose(0), _pose(0)
+    b[0, 0] += 2.0
+    assert abs(docking.rmsd_upper_bound(a, b) - 1.0) < 1e-7          # sqrt(4 / 4 atoms)
+    assert docking.rmsd_upper_bound(np.zeros((0, 3)), np.zeros((0, 3))) == 0.0
+
+
+def test_add_to_output_container_rules():
+    c = docking.OutputContainer(min_rmsd=1.0, max_size=3)
+    c.add(-1.0, _pose(0), [0])
+    c.add(-2.0, _pose(0.1), [1])        # rmsd 0.17 < 1: similar and better -> replaces
+    assert [o["e"] for o in c.items] == [-2.0] and c.items[0]["conf"][0] == 1
+    c.add(-1.5, _pose(0.2), [2])        # similar and worse -> dropped
+    assert [o["e"] for o in c.items] == [-2.0]
+    c.add(-0.5, _pose(5), [3]); c.add(-3.0, _pose(10), [4])
+    assert [o["e"] for o in c.items] == [-3.0, -2.0, -0.5]           # sorted
+    c.add(0.0, _pose(20), [5])          # full, worse than the worst -> dropped
+    assert [o["e"] for o in c.items] == [-3.0, -2.0, -0.5]
+    c.add(-1.0, _pose(30), [6])         # full, better than the worst -> replaces the worst, re-sorted
+    assert [o["e"] for o in c.items] == [-3.0, -2.0, -1.0] and c.items[2]["conf"][0] == 6
+
+
+def test_merge_chains_uses_rmsd_2_and_remove_redundant_is_strict():
+    # two chains found the same minimum (0.6 A apart in RMSD): with the search's min_rmsd 0.5 both survive in their own
+    # containers, the merge (min_rmsd forced to 2) keeps the better one only
+    e = np.array([[-5.0, -1.0], [-6.0, 0.0]], np.float32)
+    coords = np.stack([np.stack([_pose(0), _pose(9)]), np.stack([_pose(0.6 / np.sqrt(3)), _pose(0)])])
+    confs = np.zeros((2, 2, 7), np.float32)
+    confs[1, 0, 0] = 42
+    m = docking.merge_chains(e, confs, coords, np.array([2, 1]), num_saved_mins=50).items
+    assert [o["e"] for o in m] == [-6.0, -1.0] and m[0]["conf"][0] == 42
+    items = [{"coords": _pose(0)}, {"coords": _pose(1.0 / np.sqrt(3))}, {"coords": _pose(2.0)}]
+    d01 = docking.rmsd_upper_bound(items[0]["coords"], items[1]["coords"])
+    kept = docking.remove_redundant(items, min_rmsd=d01)              # distance == min_rmsd -> NOT kept ('>' in main.cpp:187)
+    assert len(kept) == 2 and kept[1] is items[2]
+    assert len(docking.remove_redundant(items, min_rmsd=d01 * 0.99)) == 3
+
+
+def test_reference_num_steps():
+    assert docking.reference_num_steps(27, 12) == 70 * 3 * (50 + 27 + 120) // 2
+
+
+@pytest.mark.gpu
+def test_dock_and_rescore_pipeline():
+    from gnina_b200 import CNNScorer, synth
+    from gnina_b200.vina import VinaScorer
+    rec_xyz, rec_t = synth.make_receptor()
+    lig = synth.make_flexible_ligand()
+    v = VinaScorer(); v.set_receptor(rec_xyz, rec_t)
+    c = CNNScorer(["crossdock_default2018"]); c.set_receptor(rec_xyz, rec_t)
+    poses = docking.dock_ligand(v, c, lig, [-6, -6, -6], [6, 6, 6], exhaustiveness=8, seed=3, num_steps=60, num_saved_mins=20)
+    assert 1 <= len(poses) <= 9
+    sc = [p["cnnscore"] for p in poses]
+    assert sc == sorted(sc, reverse=True) and all(0.0 <= s <= 1.0 for s in sc)       # ranked by CNNscore
+    for i, p in enumerate(poses):
+        assert p["coords"].shape == (len(lig["types"]), 3) and np.isfinite(p["e"]) and np.isfinite(p["cnnaffinity"])
+        for q in poses[:i]:
+            assert docking.rmsd_upper_bound(p["coords"], q["coords"]) > 1.0              # out_min_rmsd
+        # the scores attached to a pose are those of its coordinates
+        one = c.score_batch(p["coords"], lig["types"], [0, len(lig["types"])])
+        assert abs(one[0][0] - p["cnnscore"]) < 1e-6
+        e_aff = v.score_exact(p["coords"], lig["types"], [0, len(lig["types"])], num_tors=np.array([v.T], np.float32))[1][0]
+        assert abs(e_aff - p["e"]) < 1e-5 * max(1.0, abs(p["e"]))
+    again = docking.dock_ligand(v, c, lig, [-6, -6, -6], [6, 6, 6], exhaustiveness=8, seed=3, num_steps=60, num_saved_mins=20)
+    assert [p["cnnscore"] for p in again] == sc                                            # same seed, same result
