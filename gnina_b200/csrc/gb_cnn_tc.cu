@@ -118,7 +118,13 @@ bool tc_supported(const Model& m) {
 }
 int tc_pool_kind(const Model& m) { return m.arch == GB_ARCH_DEFAULT2018 ? 0 : 1; }
 
+std::mutex& tc_init_mutex() {
+  static std::mutex mu;
+  return mu;
+}
+
 std::shared_ptr<TcWeights> get_tc_weights(const Model& m) {
+  std::lock_guard<std::mutex> lk(tc_init_mutex());
   Model& mm = const_cast<Model&>(m);
   if (mm.tc) return mm.tc;
   auto tw = std::make_shared<TcWeights>();
@@ -940,6 +946,7 @@ template <int CIN, int DD>
 static void launch_conv_tc(const ConvTc& c, const ActLayout& L, const uint4* xin, __half* out, int n_poses, cudaStream_t s,
                            uint4* out_planar = nullptr, int out_c8tot = 0, int out_c8off = 0, int out_lp = 0, int relu = 1) {
   using S = ConvTcSmem<CIN>;
+  std::unique_lock<std::mutex> init_lock(tc_init_mutex());
   static bool attr_set = false;
   if (!attr_set) {
     GB_CUDA(cudaFuncSetAttribute(conv3_tc_kernel<CIN, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
@@ -977,6 +984,7 @@ static void launch_conv_tc(const ConvTc& c, const ActLayout& L, const uint4* xin
     if (ctas_per_sm < 1) ctas_per_sm = 1;
   }
   int grid = n_sm * ctas_per_sm;
+  init_lock.unlock();
   static const int persist = getenv("GB_TC_PERSIST") ? atoi(getenv("GB_TC_PERSIST")) : (CIN == 64 ? 1 : 0);
   if (persist == 0) grid = n_items;            // experiment: one item per CTA
   else if (persist > 1) grid = n_sm * persist;  // experiment: force CTAs per SM

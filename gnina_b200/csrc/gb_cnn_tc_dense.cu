@@ -122,6 +122,7 @@ static DenseLayerTc prep_dense_layer(TcDenseWeights& tw, const Model& m, int L, 
 }
 
 static std::shared_ptr<TcDenseWeights> get_dense_weights(const Model& m) {
+  std::lock_guard<std::mutex> lk(tc_init_mutex());
   Model& mm = const_cast<Model&>(m);
   if (mm.tc_dense) return mm.tc_dense;
   auto tw = std::make_shared<TcDenseWeights>();
@@ -338,6 +339,7 @@ static void launch_dense_conv(const DenseLayerTc& L, const ActLayout& A, uint4* 
   constexpr int P = DD + 2, SL = 128 + 2 * (P + 1);
   constexpr int kStageBytes = ((2 * SL * 16) + 127) / 128 * 128;
   constexpr int kSmem = 2 * kDnWBytes + kDnStages * kStageBytes + 16 * 8 + 16 + (16 + 27 * 16) * 4 + 64;
+  std::unique_lock<std::mutex> init_lock(tc_init_mutex());
   static bool init = false;
   if (!init) {
     GB_CUDA(cudaFuncSetAttribute(dense_conv_tc_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
@@ -346,6 +348,7 @@ static void launch_dense_conv(const DenseLayerTc& L, const ActLayout& A, uint4* 
     GB_CUDA(cudaMemcpyToSymbol(c_dense_aoff, h, sizeof(h), sizeof(uint32_t) * 9 * DenseCfg<DD>::id));
     init = true;
   }
+  init_lock.unlock();
   DenseConvParams p;
   p.xin = buf; p.xout = buf; p.wp = L.wp; p.bias = L.bias; p.corr = L.corr;
   p.KS = L.cin / 16; p.C8tot = C8tot; p.c8_off = c8_off; p.G = A.G; p.T = A.T; p.Lp = A.Lp; p.n_poses = n_poses;
@@ -468,10 +471,13 @@ template <int C>
 static void launch_bottleneck(const PointwiseGen& pw, const uint4* xin, const ActLayout& Ain, uint4* xout, const ActLayout& Aout,
                               int n_poses, cudaStream_t s) {
   const int smem = C * (C + 8) * (int)sizeof(__half) + C * (int)sizeof(float);
-  static bool init = false;
-  if (!init) {
-    GB_CUDA(cudaFuncSetAttribute(bottleneck_maxpool_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    init = true;
+  {
+    std::lock_guard<std::mutex> lk(tc_init_mutex());
+    static bool init = false;
+    if (!init) {
+      GB_CUDA(cudaFuncSetAttribute(bottleneck_maxpool_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      init = true;
+    }
   }
   GB_CHECK(pw.c == C, "bottleneck channels");
   bottleneck_maxpool_kernel<C><<<148 * 3, 256, smem, s>>>(xin, Ain.D, Ain.G, Ain.Lp, Ain.C8, pw.w, pw.bias,

@@ -33,6 +33,7 @@ struct TcGradWeights {
 };
 
 static std::shared_ptr<TcGradWeights> get_grad_weights(const Model& m) {
+  std::lock_guard<std::mutex> lk(tc_init_mutex());
   Model& mm = const_cast<Model&>(m);
   if (mm.tc_grad) return mm.tc_grad;
   auto gw = std::make_shared<TcGradWeights>();

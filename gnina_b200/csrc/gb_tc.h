@@ -3,6 +3,7 @@
 #include "gb_internal.h"
 #include <cuda_fp16.h>
 #include <functional>
+#include <mutex>
 
 namespace gb {
 
@@ -36,6 +37,9 @@ struct TcWorkspace {
   ~TcWorkspace();
 };
 
+// one-time initialisations (lazily packed weights, function attributes, constant tables) happen under this lock:
+// clones of a scorer run on different host threads and share the models
+std::mutex& tc_init_mutex();
 bool tc_supported(const Model& m);
 // pose lists + fused voxelise/pool of one chunk into gw.x0[kind][buf] for every pool kind in kinds_mask (bit 0 = avg
 // for the default2018 family, bit 1 = max for the dense family) on stream s; returns #launches

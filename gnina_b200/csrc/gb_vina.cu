@@ -53,6 +53,21 @@ __host__ __device__ inline float eval_terms(const P& pr, const float* w, int t1,
 struct Vina {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // grow-only device workspace of the docking entry points (no cudaMalloc/cudaFree -- and their implicit device
+  // synchronisation -- per call, so handles on different host threads overlap their kernels)
+  void* dws[8] = {};
+  size_t dws_cap[8] = {};
+  template <typename T>
+  T* ws(int i, size_t n) {
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    if (dws_cap[i] < bytes) {
+      if (dws[i]) cudaFree(dws[i]);
+      dws[i] = nullptr; dws_cap[i] = 0;
+      GB_CUDA(cudaMalloc(&dws[i], bytes));
+      dws_cap[i] = bytes;
+    }
+    return reinterpret_cast<T*>(dws[i]);
+  }
   float w[6];
   float factor = 32.f, cutoff_sqr = 64.f;
   int n = 0;
@@ -83,7 +98,9 @@ struct Vina {
   // cache
   float begin[3], end[3];
   int gn[3] = {0, 0, 0};
-  float* d_grids[kNumSminaTypes] = {};
+  float* d_grids[kNumSminaTypes] = {};       // grids of the CURRENT cache (null = type not built)
+  float* grid_pool[kNumSminaTypes] = {};     // grow-only backing store, reused from ligand to ligand
+  size_t grid_pool_cap[kNumSminaTypes] = {};
   // pose staging
   float4* d_lig = nullptr; int* d_off = nullptr; float* d_atom_e = nullptr; float* d_deriv = nullptr; float* d_pose_e = nullptr;
   float* d_tors = nullptr;
@@ -91,11 +108,12 @@ struct Vina {
   ~Vina() {
     cudaSetDevice(device);
     if (stream) cudaStreamDestroy(stream);
+    for (auto q : dws) cudaFree(q);
     cudaFree(d_fast); cudaFree(d_smooth); cudaFree(d_sp); cudaFree(d_rec);
     cudaFree(lig.local); cudaFree(lig.atom_seg); cudaFree(lig.seg); cudaFree(lig.seg_rel_origin); cudaFree(lig.seg_rel_axis);
     cudaFree(lig.pairs); cudaFree(d_lig); cudaFree(d_off); cudaFree(d_atom_e); cudaFree(d_deriv);
     cudaFree(d_pose_e); cudaFree(d_tors);
-    for (auto g : d_grids) cudaFree(g);
+    for (auto g : grid_pool) cudaFree(g);
   }
 };
 
@@ -415,7 +433,7 @@ int gb_vina_cache_build(gb_vina* h, const float* begin, const float* end, const 
   GB_CHECK(h && begin && end && n && types_needed && n_types > 0 && n_types <= kMaxNeeded, "bad cache arguments");
   Vina& v = h->v;
   GB_CUDA(cudaSetDevice(v.device));
-  for (auto& g : v.d_grids) { cudaFree(g); g = nullptr; }
+  for (auto& g : v.d_grids) g = nullptr;
   NeededTypes nt;
   nt.n = n_types;
   const size_t vol = (size_t)(n[0] + 1) * (n[1] + 1) * (n[2] + 1);
@@ -429,7 +447,13 @@ int gb_vina_cache_build(gb_vina* h, const float* begin, const float* end, const 
   for (int j = 0; j < n_types; j++) {
     const int t = types_needed[j];
     GB_CHECK(t >= 2 && t < kNumSminaTypes, "needed type must be a heavy smina type");
-    GB_CUDA(cudaMalloc(&v.d_grids[t], vol * sizeof(float)));
+    if (v.grid_pool_cap[t] < vol) {
+      cudaFree(v.grid_pool[t]);
+      v.grid_pool[t] = nullptr; v.grid_pool_cap[t] = 0;
+      GB_CUDA(cudaMalloc(&v.grid_pool[t], vol * sizeof(float)));
+      v.grid_pool_cap[t] = vol;
+    }
+    v.d_grids[t] = v.grid_pool[t];
     nt.t[j] = t;
     nt.grid[j] = v.d_grids[t];
   }
@@ -1057,9 +1081,9 @@ int gb_vina_set_ligand(gb_vina* h, const gb_ligand_topology* t) {
   Vina& v = h->v;
   GB_CUDA(cudaSetDevice(v.device));
   auto& l = v.lig;
-  cudaFree(l.local); cudaFree(l.atom_seg); cudaFree(l.seg); cudaFree(l.seg_rel_origin); cudaFree(l.seg_rel_axis); cudaFree(l.pairs);
-  l = Vina::LigDev();
+  l.n_atoms = 0;  // not ready until the upload below succeeds
   const int na = t->n_atoms, ns = t->n_segments;
+  GB_CHECK(t->n_pairs >= 0 && t->n_pairs <= kDkMaxAtoms * (kDkMaxAtoms - 1) / 2, "pair count out of range");
   std::vector<float4> local(na), ro(ns), ra(ns);
   std::vector<int> aseg(na, -1);
   std::vector<int4> seg(ns);
@@ -1081,11 +1105,16 @@ int gb_vina_set_ligand(gb_vina* h, const gb_ligand_topology* t) {
   }
   std::vector<int2> pairs(std::max(t->n_pairs, 1));
   for (int k = 0; k < t->n_pairs; k++) pairs[k] = make_int2(t->pair_a[k], t->pair_b[k]);
-  auto up = [&](auto** d, const auto& hv) {
-    GB_CUDA(cudaMalloc(d, hv.size() * sizeof(hv[0])));
-    GB_CUDA(cudaMemcpy(*d, hv.data(), hv.size() * sizeof(hv[0]), cudaMemcpyHostToDevice));
+  // device arrays are allocated once at their maximum size (96 atoms, 32 segments, 4560 pairs: < 60 KB) and reused
+  // from ligand to ligand: no cudaFree (device-wide synchronisation) between the ligands of a screen
+  auto up = [&](auto** d, const auto& hv, size_t max_elems) {
+    if (!*d) GB_CUDA(cudaMalloc(d, max_elems * sizeof(hv[0])));
+    GB_CUDA(cudaMemcpyAsync(*d, hv.data(), hv.size() * sizeof(hv[0]), cudaMemcpyHostToDevice, v.stream));
   };
-  up(&l.local, local); up(&l.atom_seg, aseg); up(&l.seg, seg); up(&l.seg_rel_origin, ro); up(&l.seg_rel_axis, ra); up(&l.pairs, pairs);
+  const size_t max_pairs = (size_t)kDkMaxAtoms * (kDkMaxAtoms - 1) / 2;
+  up(&l.local, local, kDkMaxAtoms); up(&l.atom_seg, aseg, kDkMaxAtoms); up(&l.seg, seg, kDkMaxSeg);
+  up(&l.seg_rel_origin, ro, kDkMaxSeg); up(&l.seg_rel_axis, ra, kDkMaxSeg); up(&l.pairs, pairs, max_pairs);
+  GB_CUDA(cudaStreamSynchronize(v.stream));  // the host vectors above go out of scope
   l.n_atoms = na; l.n_seg = ns; l.n_pairs = t->n_pairs; l.max_depth = max_depth; l.n_heavy = nh; l.gyration_radius = t->gyration_radius;
   GBV_END
 }
@@ -1099,11 +1128,12 @@ static int dock_eval_common(gb_vina* h, const float* confs, int n, const float* 
   check_dock_ready(v);
   if (n == 0) return GB_OK;
   const int T = v.lig.n_seg - 1, nx = 7 + T, ng = 6 + T, na = v.lig.n_atoms;
-  float *d_conf, *d_e, *d_g, *d_c = nullptr, *d_xo = nullptr;
-  int* d_ev = nullptr;
-  GB_CUDA(cudaMalloc(&d_conf, (size_t)n * nx * 4)); GB_CUDA(cudaMalloc(&d_e, (size_t)n * 4)); GB_CUDA(cudaMalloc(&d_g, (size_t)n * ng * 4));
-  if (coords) GB_CUDA(cudaMalloc(&d_c, (size_t)n * 3 * na * 4));
-  if (mode == 1) { GB_CUDA(cudaMalloc(&d_xo, (size_t)n * nx * 4)); GB_CUDA(cudaMalloc(&d_ev, (size_t)n * 4)); }
+  float* d_conf = v.ws<float>(0, (size_t)n * nx);
+  float* d_e = v.ws<float>(1, n);
+  float* d_g = v.ws<float>(2, (size_t)n * ng);
+  float* d_c = coords ? v.ws<float>(3, (size_t)n * 3 * na) : nullptr;
+  float* d_xo = mode == 1 ? v.ws<float>(4, (size_t)n * nx) : nullptr;
+  int* d_ev = mode == 1 ? v.ws<int>(5, n) : nullptr;
   GB_CUDA(cudaMemcpyAsync(d_conf, confs, (size_t)n * nx * 4, cudaMemcpyHostToDevice, v.stream));
   DockField F;
   make_field(v, slope, F);
@@ -1116,7 +1146,6 @@ static int dock_eval_common(gb_vina* h, const float* confs, int n, const float* 
   if (mode == 1 && confs_out) GB_CUDA(cudaMemcpyAsync(confs_out, d_xo, (size_t)n * nx * 4, cudaMemcpyDeviceToHost, v.stream));
   if (mode == 1 && evals) GB_CUDA(cudaMemcpyAsync(evals, d_ev, (size_t)n * 4, cudaMemcpyDeviceToHost, v.stream));
   GB_CUDA(cudaStreamSynchronize(v.stream));
-  cudaFree(d_conf); cudaFree(d_e); cudaFree(d_g); cudaFree(d_c); cudaFree(d_xo); cudaFree(d_ev);
   GBV_END
 }
 
@@ -1137,10 +1166,11 @@ int gb_vina_mc(gb_vina* h, const gb_mc_params* P, const float* corner1, const fl
   check_dock_ready(v);
   if (n_chains == 0) return GB_OK;
   const int T = v.lig.n_seg - 1, nx = 7 + T, S = P->num_saved_mins, nh = std::max(v.lig.n_heavy, 1);
-  uint32_t* d_seeds; float *d_e, *d_c, *d_h; int* d_n;
-  GB_CUDA(cudaMalloc(&d_seeds, (size_t)n_chains * 4)); GB_CUDA(cudaMalloc(&d_e, (size_t)n_chains * S * 4));
-  GB_CUDA(cudaMalloc(&d_c, (size_t)n_chains * S * nx * 4)); GB_CUDA(cudaMalloc(&d_h, (size_t)n_chains * S * 3 * nh * 4));
-  GB_CUDA(cudaMalloc(&d_n, (size_t)n_chains * 4));
+  uint32_t* d_seeds = v.ws<uint32_t>(0, n_chains);
+  float* d_e = v.ws<float>(1, (size_t)n_chains * S);
+  float* d_c = v.ws<float>(2, (size_t)n_chains * S * nx);
+  float* d_h = v.ws<float>(3, (size_t)n_chains * S * 3 * nh);
+  int* d_n = v.ws<int>(4, n_chains);
   GB_CUDA(cudaMemcpyAsync(d_seeds, seeds, (size_t)n_chains * 4, cudaMemcpyHostToDevice, v.stream));
   GB_CUDA(cudaMemsetAsync(d_e, 0, (size_t)n_chains * S * 4, v.stream));
   GB_CUDA(cudaMemsetAsync(d_c, 0, (size_t)n_chains * S * nx * 4, v.stream));
@@ -1155,7 +1185,6 @@ int gb_vina_mc(gb_vina* h, const gb_mc_params* P, const float* corner1, const fl
   GB_CUDA(cudaMemcpyAsync(out_conf, d_c, (size_t)n_chains * S * nx * 4, cudaMemcpyDeviceToHost, v.stream));
   GB_CUDA(cudaMemcpyAsync(n_out, d_n, (size_t)n_chains * 4, cudaMemcpyDeviceToHost, v.stream));
   GB_CUDA(cudaStreamSynchronize(v.stream));
-  cudaFree(d_seeds); cudaFree(d_e); cudaFree(d_c); cudaFree(d_h); cudaFree(d_n);
   GBV_END
 }
 

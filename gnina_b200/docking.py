@@ -104,3 +104,35 @@ def dock_ligand(vina, cnn, lig, corner1, corner2, exhaustiveness=8, seed=1, num_
     key = {"cnnscore": lambda o: -o["cnnscore"], "cnnaffinity": lambda o: -o["cnnaffinity"], "energy": lambda o: o["e"]}[sort_order]
     merged.sort(key=key)
     return remove_redundant(merged, out_min_rmsd)[:num_modes]
+
+
+def dock_many(ligands, rec_xyz, rec_types, cnn_model_names, corner1, corner2, n_workers=8, device=0, seeds=None, **kw):
+    """Config 3's "1 receptor x many ligands": one ligand's 64 chains are 64 warps and cannot fill a B200, so ligands
+    are kept in flight concurrently — `n_workers` host threads, each with its own VinaScorer handle (own stream, own
+    affinity-grid pool) and its own CNNScorer clone (`fresh_copy`, shared weights), exactly the per-thread model copies
+    of the reference's `parallel_mc` (lib/parallel_mc.cpp:145-163) one level up.  ctypes releases the GIL during the
+    library calls, so the workers' kernels overlap on the device.  Results are returned in input order and are
+    identical to sequential `dock_ligand` calls with the same seeds."""
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+    from .scorer import CNNScorer
+    from .vina import VinaScorer
+    master = CNNScorer(cnn_model_names, device=device)
+    master.set_receptor(rec_xyz, rec_types)
+    tls = threading.local()
+    lock = threading.Lock()
+
+    def worker_state():
+        if not hasattr(tls, "v"):
+            tls.v = VinaScorer(device=device)
+            tls.v.set_receptor(rec_xyz, rec_types)
+            with lock:
+                tls.c = master.fresh_copy()
+        return tls.v, tls.c
+
+    def run(i):
+        v, c = worker_state()
+        return dock_ligand(v, c, ligands[i], corner1, corner2, seed=(i + 1 if seeds is None else int(seeds[i])), **kw)
+
+    with ThreadPoolExecutor(max_workers=max(1, int(n_workers))) as ex:
+        return list(ex.map(run, range(len(ligands))))

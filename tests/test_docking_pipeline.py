@@ -75,3 +75,22 @@ def test_dock_and_rescore_pipeline():
         assert abs(e_aff - p["e"]) < 1e-5 * max(1.0, abs(p["e"]))
     again = docking.dock_ligand(v, c, lig, [-6, -6, -6], [6, 6, 6], exhaustiveness=8, seed=3, num_steps=60, num_saved_mins=20)
     assert [p["cnnscore"] for p in again] == sc                                            # same seed, same result
+
+
+@pytest.mark.gpu
+def test_concurrent_ligands_equal_sequential_docking():
+    """dock_many keeps several ligands in flight on worker threads (own Vina handle + CNN clone each); the result of
+    every ligand is bit-identical to docking it alone: no shared mutable state between handles."""
+    from gnina_b200 import CNNScorer, synth
+    from gnina_b200.vina import VinaScorer
+    rec_xyz, rec_t = synth.make_receptor()
+    ligs = [synth.make_flexible_ligand(n_heavy=18 + 2 * i, n_tors=3 + i % 3, seed=20 + i) for i in range(6)]
+    kw = dict(exhaustiveness=4, num_steps=30, num_saved_mins=10)
+    many = docking.dock_many(ligs, rec_xyz, rec_t, ["crossdock_default2018"], [-6, -6, -6], [6, 6, 6], n_workers=3, **kw)
+    v = VinaScorer(); v.set_receptor(rec_xyz, rec_t)
+    c = CNNScorer(["crossdock_default2018"]); c.set_receptor(rec_xyz, rec_t)
+    for i, lig in enumerate(ligs):
+        one = docking.dock_ligand(v, c, lig, [-6, -6, -6], [6, 6, 6], seed=i + 1, **kw)
+        assert len(one) == len(many[i]) >= 1
+        for a, b in zip(one, many[i]):
+            assert a["cnnscore"] == b["cnnscore"] and a["e"] == b["e"] and np.array_equal(a["coords"], b["coords"])
