@@ -7,6 +7,7 @@
 //         and num_tors_div (lib/everything.h:795-809): the printed "Affinity (kcal/mol)" of a rigid pose
 // Summation orders follow the reference (per-atom partial, curl, then atoms in index order), so results differ from
 // the CPU restatement only by the device's expf/sqrtf rounding.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -1185,6 +1186,44 @@ int gb_vina_mc(gb_vina* h, const gb_mc_params* P, const float* corner1, const fl
   GB_CUDA(cudaMemcpyAsync(out_conf, d_c, (size_t)n_chains * S * nx * 4, cudaMemcpyDeviceToHost, v.stream));
   GB_CUDA(cudaMemcpyAsync(n_out, d_n, (size_t)n_chains * 4, cudaMemcpyDeviceToHost, v.stream));
   GB_CUDA(cudaStreamSynchronize(v.stream));
+  GBV_END
+}
+
+int gb_vina_merge_outputs(const float* e, const float* coords, const int32_t* n_out, int n_chains, int S, int n_atoms,
+                          float min_rmsd, int max_size, int32_t* kept, int32_t* n_kept) {
+  GBV_BEGIN
+  GB_CHECK(e && coords && n_out && kept && n_kept && n_chains >= 0 && S >= 1 && n_atoms >= 0 && max_size >= 0, "bad arguments");
+  std::vector<int> out;  // flat indices, kept sorted by energy
+  const size_t stride = (size_t)n_atoms * 3;
+  auto rmsd = [&](int a, int b) -> double {  // rmsd_upper_bound
+    if (n_atoms == 0) return 0.0;
+    const float *pa = coords + (size_t)a * stride, *pb = coords + (size_t)b * stride;
+    double acc = 0;
+    for (size_t i = 0; i < stride; i++) { const double d = (double)pa[i] - (double)pb[i]; acc += d * d; }
+    return std::sqrt(acc / n_atoms);
+  };
+  for (int c = 0; c < n_chains; c++) {
+    GB_CHECK(n_out[c] >= 0 && n_out[c] <= S, "n_out out of range");
+    for (int k = 0; k < n_out[c]; k++) {
+      const int t = c * S + k;
+      size_t best = out.size();
+      double best_r = 0;
+      for (size_t i = 0; i < out.size(); i++) {  // find_closest
+        const double r = rmsd(t, out[i]);
+        if (i == 0 || r < best_r) { best = i; best_r = r; }
+      }
+      if (best < out.size() && best_r < min_rmsd) {
+        if (e[t] < e[out[best]]) out[best] = t;
+      } else if ((int)out.size() < max_size) {
+        out.push_back(t);
+      } else if (!out.empty() && e[t] < e[out.back()]) {
+        out.back() = t;
+      }
+      std::stable_sort(out.begin(), out.end(), [&](int a, int b) { return e[a] < e[b]; });
+    }
+  }
+  for (size_t i = 0; i < out.size(); i++) kept[i] = out[i];
+  *n_kept = (int32_t)out.size();
   GBV_END
 }
 

@@ -42,12 +42,35 @@ class OutputContainer:
 
 
 def merge_chains(e, confs, coords, n_out, num_saved_mins):
-    """merge_output_containers over the chains' containers, in chain order; min_rmsd = 2 (parallel_mc.cpp:175)."""
+    """merge_output_containers over the chains' containers, in chain order; min_rmsd = 2 (parallel_mc.cpp:175).
+    Pure-Python statement of the rule (tests); `merge_chains_native` is the library's host-side C++ version."""
     out = OutputContainer(2.0, num_saved_mins)
     for c in range(len(n_out)):
         for k in range(int(n_out[c])):
             out.add(e[c, k], coords[c, k], confs[c, k])
     return out
+
+
+def merge_chains_native(e, confs, coords, n_out, num_saved_mins, min_rmsd=2.0):
+    """gb_vina_merge_outputs: the same merge in the library (C++, host only; thousands of RMSDs per ligand would hold
+    the GIL for most of a docking run otherwise) -> list of dicts like OutputContainer.items."""
+    import ctypes as C
+    from . import capi
+    e = np.ascontiguousarray(e, np.float32); coords = np.ascontiguousarray(coords, np.float32)
+    n_out = np.ascontiguousarray(n_out, np.int32)
+    n_chains, S = e.shape
+    na = coords.shape[2]
+    kept = np.zeros(max(num_saved_mins, 1), np.int32)
+    nk = C.c_int32(0)
+    fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    capi.check(capi.lib().gb_vina_merge_outputs(e.ctypes.data_as(fp), coords.ctypes.data_as(fp), n_out.ctypes.data_as(ip),
+                                                n_chains, S, na, float(min_rmsd), int(num_saved_mins), kept.ctypes.data_as(ip),
+                                                C.byref(nk)))
+    items = []
+    for f in kept[:nk.value]:
+        c, k = divmod(int(f), S)
+        items.append({"e": float(e[c, k]), "coords": coords[c, k].copy(), "conf": np.asarray(confs[c, k], np.float32).copy()})
+    return items
 
 
 def remove_redundant(items, min_rmsd):
@@ -89,7 +112,7 @@ def dock_ligand(vina, cnn, lig, corner1, corner2, exhaustiveness=8, seed=1, num_
     flat = X.reshape(-1, 7 + T)
     _, _, coords = vina.eval_deriv(flat, coords=True)
     coords = coords.reshape(len(seeds), num_saved_mins, len(types), 3)
-    merged = merge_chains(e, X, coords, n_out, num_saved_mins).items
+    merged = merge_chains_native(e, X, coords, n_out, num_saved_mins)
     if not merged:
         return []
     # one CNN batch call and one exact-scoring call over all kept poses

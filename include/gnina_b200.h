@@ -223,6 +223,14 @@ int gb_vina_bfgs(gb_vina* h, float* confs, int n, int maxiters, const float* v3,
  * RMSD-distinct minima sorted by energy: out_e[n_chains][S], out_conf[n_chains][S][7+T], n_out[n_chains]. */
 int gb_vina_mc(gb_vina* h, const gb_mc_params* params, const float* corner1, const float* corner2, const uint32_t* seeds,
                int n_chains, float slope, float* out_e, float* out_conf, int32_t* n_out);
+/* merge_output_containers over the chains' containers (lib/parallel_mc.cpp:165-181 -> add_to_output_container,
+ * lib/coords.cpp:43-56, find_closest / rmsd_upper_bound :24-41): chains in order, each chain's minima in order;
+ * a pose closer than min_rmsd (RMSD over the n_atoms coordinates given) to a kept one replaces it if better,
+ * otherwise it is appended while there is room or replaces the worst; the container is re-sorted by energy after
+ * every insertion.  Host-only (no device work).  e[n_chains][S], coords[n_chains][S][n_atoms][3], n_out[n_chains];
+ * kept[max_size] receives flat indices chain * S + k in final (energy) order, *n_kept their number. */
+int gb_vina_merge_outputs(const float* e, const float* coords, const int32_t* n_out, int n_chains, int S, int n_atoms,
+                          float min_rmsd, int max_size, int32_t* kept, int32_t* n_kept);
 
 #ifdef __cplusplus
 }

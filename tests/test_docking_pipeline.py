@@ -94,3 +94,26 @@ def test_concurrent_ligands_equal_sequential_docking():
         assert len(one) == len(many[i]) >= 1
         for a, b in zip(one, many[i]):
             assert a["cnnscore"] == b["cnnscore"] and a["e"] == b["e"] and np.array_equal(a["coords"], b["coords"])
+
+
+def test_native_merge_equals_the_python_statement():
+    """gb_vina_merge_outputs (host-only C++ in the library; no device needed) against OutputContainer on random chains
+    with many near-duplicates"""
+    rs = np.random.RandomState(4)
+    n_chains, S, na = 12, 8, 5
+    centres = rs.randn(6, na, 3) * 4
+    coords = np.zeros((n_chains, S, na, 3), np.float32)
+    e = np.zeros((n_chains, S), np.float32)
+    n_out = rs.randint(0, S + 1, n_chains).astype(np.int32)
+    for c in range(n_chains):
+        for k in range(S):
+            coords[c, k] = centres[rs.randint(6)] + rs.randn(na, 3) * 0.4
+            e[c, k] = rs.randn()
+        e[c, :n_out[c]] = np.sort(e[c, :n_out[c]])
+    confs = rs.randn(n_chains, S, 9).astype(np.float32)
+    for max_size in (3, 50):
+        py = docking.merge_chains(e, confs, coords, n_out, max_size).items
+        nat = docking.merge_chains_native(e, confs, coords, n_out, max_size)
+        assert [o["e"] for o in py] == [o["e"] for o in nat] and len(py) >= 1
+        for a, b in zip(py, nat):
+            assert np.array_equal(a["coords"], b["coords"]) and np.array_equal(a["conf"], b["conf"])
