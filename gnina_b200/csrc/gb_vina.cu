@@ -69,6 +69,22 @@ struct Vina {
     }
     return reinterpret_cast<T*>(dws[i]);
   }
+  // pinned staging for results: a device->host copy into PAGEABLE memory waits for the stream's kernel inside the
+  // driver call, holding driver locks that stall the launches of other host threads (measured: 8 handles on 8 threads
+  // ran their Monte-Carlo kernels back to back); copies into pinned memory are truly asynchronous
+  void* pws[8] = {};
+  size_t pws_cap[8] = {};
+  template <typename T>
+  T* pin(int i, size_t n) {
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    if (pws_cap[i] < bytes) {
+      if (pws[i]) cudaFreeHost(pws[i]);
+      pws[i] = nullptr; pws_cap[i] = 0;
+      GB_CUDA(cudaMallocHost(&pws[i], bytes));
+      pws_cap[i] = bytes;
+    }
+    return reinterpret_cast<T*>(pws[i]);
+  }
   float w[6];
   float factor = 32.f, cutoff_sqr = 64.f;
   int n = 0;
@@ -110,6 +126,7 @@ struct Vina {
     cudaSetDevice(device);
     if (stream) cudaStreamDestroy(stream);
     for (auto q : dws) cudaFree(q);
+    for (auto q : pws) cudaFreeHost(q);
     cudaFree(d_fast); cudaFree(d_smooth); cudaFree(d_sp); cudaFree(d_rec);
     cudaFree(lig.local); cudaFree(lig.atom_seg); cudaFree(lig.seg); cudaFree(lig.seg_rel_origin); cudaFree(lig.seg_rel_axis);
     cudaFree(lig.pairs); cudaFree(d_lig); cudaFree(d_off); cudaFree(d_atom_e); cudaFree(d_deriv);
@@ -1135,18 +1152,30 @@ static int dock_eval_common(gb_vina* h, const float* confs, int n, const float* 
   float* d_c = coords ? v.ws<float>(3, (size_t)n * 3 * na) : nullptr;
   float* d_xo = mode == 1 ? v.ws<float>(4, (size_t)n * nx) : nullptr;
   int* d_ev = mode == 1 ? v.ws<int>(5, n) : nullptr;
-  GB_CUDA(cudaMemcpyAsync(d_conf, confs, (size_t)n * nx * 4, cudaMemcpyHostToDevice, v.stream));
+  float* p_conf = v.pin<float>(0, (size_t)n * nx);
+  memcpy(p_conf, confs, (size_t)n * nx * 4);
+  GB_CUDA(cudaMemcpyAsync(d_conf, p_conf, (size_t)n * nx * 4, cudaMemcpyHostToDevice, v.stream));
   DockField F;
   make_field(v, slope, F);
   dock_eval_kernel<<<(n + kDkWarps - 1) / kDkWarps, 32 * kDkWarps, 0, v.stream>>>(lig_ptrs(v), F, d_conf, n, vcap[0], vcap[1], vcap[2], d_e, d_g,
                                                                                   d_c, mode, maxiters, d_xo, d_ev);
   GB_CUDA(cudaGetLastError());
-  GB_CUDA(cudaMemcpyAsync(e, d_e, (size_t)n * 4, cudaMemcpyDeviceToHost, v.stream));
-  if (change) GB_CUDA(cudaMemcpyAsync(change, d_g, (size_t)n * ng * 4, cudaMemcpyDeviceToHost, v.stream));
-  if (coords) GB_CUDA(cudaMemcpyAsync(coords, d_c, (size_t)n * 3 * na * 4, cudaMemcpyDeviceToHost, v.stream));
-  if (mode == 1 && confs_out) GB_CUDA(cudaMemcpyAsync(confs_out, d_xo, (size_t)n * nx * 4, cudaMemcpyDeviceToHost, v.stream));
-  if (mode == 1 && evals) GB_CUDA(cudaMemcpyAsync(evals, d_ev, (size_t)n * 4, cudaMemcpyDeviceToHost, v.stream));
+  float* p_e = v.pin<float>(1, n);
+  float* p_g = change ? v.pin<float>(2, (size_t)n * ng) : nullptr;
+  float* p_c = coords ? v.pin<float>(3, (size_t)n * 3 * na) : nullptr;
+  float* p_xo = (mode == 1 && confs_out) ? v.pin<float>(4, (size_t)n * nx) : nullptr;
+  int* p_ev = (mode == 1 && evals) ? v.pin<int>(5, n) : nullptr;
+  GB_CUDA(cudaMemcpyAsync(p_e, d_e, (size_t)n * 4, cudaMemcpyDeviceToHost, v.stream));
+  if (p_g) GB_CUDA(cudaMemcpyAsync(p_g, d_g, (size_t)n * ng * 4, cudaMemcpyDeviceToHost, v.stream));
+  if (p_c) GB_CUDA(cudaMemcpyAsync(p_c, d_c, (size_t)n * 3 * na * 4, cudaMemcpyDeviceToHost, v.stream));
+  if (p_xo) GB_CUDA(cudaMemcpyAsync(p_xo, d_xo, (size_t)n * nx * 4, cudaMemcpyDeviceToHost, v.stream));
+  if (p_ev) GB_CUDA(cudaMemcpyAsync(p_ev, d_ev, (size_t)n * 4, cudaMemcpyDeviceToHost, v.stream));
   GB_CUDA(cudaStreamSynchronize(v.stream));
+  memcpy(e, p_e, (size_t)n * 4);
+  if (p_g) memcpy(change, p_g, (size_t)n * ng * 4);
+  if (p_c) memcpy(coords, p_c, (size_t)n * 3 * na * 4);
+  if (p_xo) memcpy(confs_out, p_xo, (size_t)n * nx * 4);
+  if (p_ev) memcpy(evals, p_ev, (size_t)n * 4);
   GBV_END
 }
 
@@ -1172,7 +1201,9 @@ int gb_vina_mc(gb_vina* h, const gb_mc_params* P, const float* corner1, const fl
   float* d_c = v.ws<float>(2, (size_t)n_chains * S * nx);
   float* d_h = v.ws<float>(3, (size_t)n_chains * S * 3 * nh);
   int* d_n = v.ws<int>(4, n_chains);
-  GB_CUDA(cudaMemcpyAsync(d_seeds, seeds, (size_t)n_chains * 4, cudaMemcpyHostToDevice, v.stream));
+  uint32_t* p_seeds = v.pin<uint32_t>(0, n_chains);
+  memcpy(p_seeds, seeds, (size_t)n_chains * 4);
+  GB_CUDA(cudaMemcpyAsync(d_seeds, p_seeds, (size_t)n_chains * 4, cudaMemcpyHostToDevice, v.stream));
   GB_CUDA(cudaMemsetAsync(d_e, 0, (size_t)n_chains * S * 4, v.stream));
   GB_CUDA(cudaMemsetAsync(d_c, 0, (size_t)n_chains * S * nx * 4, v.stream));
   DockField F;
@@ -1182,10 +1213,16 @@ int gb_vina_mc(gb_vina* h, const gb_mc_params* P, const float* corner1, const fl
                                                                                      corner2[0], corner2[1], corner2[2], d_seeds, n_chains, d_e,
                                                                                      d_c, d_h, d_n);
   GB_CUDA(cudaGetLastError());
-  GB_CUDA(cudaMemcpyAsync(out_e, d_e, (size_t)n_chains * S * 4, cudaMemcpyDeviceToHost, v.stream));
-  GB_CUDA(cudaMemcpyAsync(out_conf, d_c, (size_t)n_chains * S * nx * 4, cudaMemcpyDeviceToHost, v.stream));
-  GB_CUDA(cudaMemcpyAsync(n_out, d_n, (size_t)n_chains * 4, cudaMemcpyDeviceToHost, v.stream));
+  float* p_e = v.pin<float>(1, (size_t)n_chains * S);
+  float* p_c = v.pin<float>(2, (size_t)n_chains * S * nx);
+  int* p_n = v.pin<int>(3, n_chains);
+  GB_CUDA(cudaMemcpyAsync(p_e, d_e, (size_t)n_chains * S * 4, cudaMemcpyDeviceToHost, v.stream));
+  GB_CUDA(cudaMemcpyAsync(p_c, d_c, (size_t)n_chains * S * nx * 4, cudaMemcpyDeviceToHost, v.stream));
+  GB_CUDA(cudaMemcpyAsync(p_n, d_n, (size_t)n_chains * 4, cudaMemcpyDeviceToHost, v.stream));
   GB_CUDA(cudaStreamSynchronize(v.stream));
+  memcpy(out_e, p_e, (size_t)n_chains * S * 4);
+  memcpy(out_conf, p_c, (size_t)n_chains * S * nx * 4);
+  memcpy(n_out, p_n, (size_t)n_chains * 4);
   GBV_END
 }
 
