@@ -298,6 +298,55 @@ class VinaScorer {
     check(gb_vina_score_exact(h_, xyz, t, offs, n_poses, num_tors, v, nullptr, a.data()));
     return a;
   }
+
+  // ---- docking inner loop (model::set / eval_deriv, quasi_newton, parallel_mc) --------------------------------------
+  void set_ligand(const gb_ligand_topology& t) {
+    check(gb_vina_set_ligand(h_, &t));
+    n_tors_ = t.n_segments - 1; n_atoms_ = t.n_atoms;
+  }
+  int conf_size() const { return 7 + n_tors_; }  // position 3, orientation quaternion 4, torsions
+  // energy (+ change[6+T] per conformation, + coordinates) of n conformations
+  std::vector<float> eval_deriv(const float* confs, int n, const float v3[3], float slope, std::vector<float>* change = nullptr,
+                                std::vector<float>* coords = nullptr) {
+    std::vector<float> e(n);
+    if (change) change->assign((size_t)n * (6 + n_tors_), 0.f);
+    if (coords) coords->assign((size_t)n * 3 * n_atoms_, 0.f);
+    check(gb_vina_eval_deriv(h_, confs, n, v3, slope, e.data(), change ? change->data() : nullptr, coords ? coords->data() : nullptr));
+    return e;
+  }
+  std::vector<float> bfgs(float* confs_inout, int n, int maxiters, const float v3[3], float slope) {
+    std::vector<float> e(n);
+    check(gb_vina_bfgs(h_, confs_inout, n, maxiters, v3, slope, e.data(), nullptr, nullptr));
+    return e;
+  }
+  struct ChainOutputs {       // the chains' output_containers, flattened
+    int n_chains = 0, S = 0;  // S = num_saved_mins
+    std::vector<float> e, conf;
+    std::vector<int32_t> n_out;
+  };
+  // parallel_mc::operator(): every chain of a ligand in one launch
+  ChainOutputs parallel_mc(const gb_mc_params& P, const float corner1[3], const float corner2[3], const std::vector<uint32_t>& seeds,
+                           float slope = 1e3f) {
+    ChainOutputs o;
+    o.n_chains = (int)seeds.size(); o.S = P.num_saved_mins;
+    o.e.assign((size_t)o.n_chains * o.S, 0.f);
+    o.conf.assign((size_t)o.n_chains * o.S * conf_size(), 0.f);
+    o.n_out.assign(o.n_chains, 0);
+    check(gb_vina_mc(h_, &P, corner1, corner2, seeds.data(), o.n_chains, slope, o.e.data(), o.conf.data(), o.n_out.data()));
+    return o;
+  }
+  // merge_output_containers (host only): flat indices chain * S + k of the kept poses, best first
+  static std::vector<int32_t> merge_outputs(const float* e, const float* coords, const int32_t* n_out, int n_chains, int S, int n_atoms,
+                                            int max_size, float min_rmsd = 2.f) {
+    std::vector<int32_t> kept(max_size > 0 ? max_size : 1);
+    int32_t n = 0;
+    check(gb_vina_merge_outputs(e, coords, n_out, n_chains, S, n_atoms, min_rmsd, max_size, kept.data(), &n));
+    kept.resize(n);
+    return kept;
+  }
+
+ private:
+  int n_tors_ = 0, n_atoms_ = 0;
 };
 
 }  // namespace gb

@@ -64,6 +64,15 @@ int main(int argc, char** argv) {
     got.clear();
     { gb::PoseBatcher q(runner, 8, deliver, ctr); const float x1[3] = {1, 2, 3}; const int32_t t1[1] = {2}; q.add(x1, t1, 1); q.flush(); q.flush(); }
     printf("fixed centre %.0f deliveries %zu\n", got.empty() ? -1.f : got[0][3], got.size());
+    {  // merge_output_containers through the C++ wrapper: two chains found the same pose (rmsd 0.5), one found another
+      const float me[4] = {-5.f, -1.f, -6.f, 0.f};                        // [chain 2][S 2]
+      const float mc[4 * 3] = {0, 0, 0, 9, 9, 9, 0.5f, 0, 0, 0, 0, 0};    // one atom per pose
+      const int32_t mn[2] = {2, 1};
+      auto kept = gb::VinaScorer::merge_outputs(me, mc, mn, 2, 2, 1, 50);
+      printf("merge");
+      for (auto k : kept) printf(" %d", k);
+      printf("\n");
+    }
     return ok ? 0 : 1;
   }
   if (argc < 3) return 2;

@@ -91,6 +91,7 @@ def test_cpp_pose_batcher_and_gninatypes(tmp_path):
     for p in range(7):
         assert out[2 + p] == "ticket %d n %d x %d c -1 batch %d" % (p, p + 1, 10 + p, 3 if p < 6 else 1)
     assert out[9] == "fixed centre 4 deliveries 1"
+    assert out[10] == "merge 2 1"       # chain 1's better copy (flat index 2) replaces chain 0's; the distinct pose stays
 
 
 @pytest.mark.gpu
