@@ -129,33 +129,55 @@ def dock_ligand(vina, cnn, lig, corner1, corner2, exhaustiveness=8, seed=1, num_
     return remove_redundant(merged, out_min_rmsd)[:num_modes]
 
 
-def dock_many(ligands, rec_xyz, rec_types, cnn_model_names, corner1, corner2, n_workers=8, device=0, seeds=None, **kw):
+class DockingPool:
     """Config 3's "1 receptor x many ligands": one ligand's 64 chains are 64 warps and cannot fill a B200, so ligands
     are kept in flight concurrently — `n_workers` host threads, each with its own VinaScorer handle (own stream, own
     affinity-grid pool) and its own CNNScorer clone (`fresh_copy`, shared weights), exactly the per-thread model copies
     of the reference's `parallel_mc` (lib/parallel_mc.cpp:145-163) one level up.  ctypes releases the GIL during the
-    library calls, so the workers' kernels overlap on the device.  Results are returned in input order and are
-    identical to sequential `dock_ligand` calls with the same seeds."""
-    import threading
-    from concurrent.futures import ThreadPoolExecutor
-    from .scorer import CNNScorer
-    from .vina import VinaScorer
-    master = CNNScorer(cnn_model_names, device=device)
-    master.set_receptor(rec_xyz, rec_types)
-    tls = threading.local()
-    lock = threading.Lock()
+    library calls, so the workers' kernels overlap on the device.  Worker state (tables, receptor, workspaces) lives
+    as long as the pool, so a screen pays for it once.  Results come back in input order and are identical to
+    sequential `dock_ligand` calls with the same seeds."""
 
-    def worker_state():
-        if not hasattr(tls, "v"):
-            tls.v = VinaScorer(device=device)
-            tls.v.set_receptor(rec_xyz, rec_types)
-            with lock:
-                tls.c = master.fresh_copy()
-        return tls.v, tls.c
+    def __init__(self, rec_xyz, rec_types, cnn_model_names, n_workers=8, device=0):
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
+        from .scorer import CNNScorer
+        self._rec = (rec_xyz, rec_types)
+        self._device = device
+        self._master = CNNScorer(cnn_model_names, device=device)
+        self._master.set_receptor(rec_xyz, rec_types)
+        self._tls = threading.local()
+        self._lock = threading.Lock()
+        self._ex = ThreadPoolExecutor(max_workers=max(1, int(n_workers)))
 
-    def run(i):
-        v, c = worker_state()
-        return dock_ligand(v, c, ligands[i], corner1, corner2, seed=(i + 1 if seeds is None else int(seeds[i])), **kw)
+    def _state(self):
+        from .vina import VinaScorer
+        t = self._tls
+        if not hasattr(t, "v"):
+            t.v = VinaScorer(device=self._device)
+            t.v.set_receptor(*self._rec)
+            with self._lock:
+                t.c = self._master.fresh_copy()
+        return t.v, t.c
 
-    with ThreadPoolExecutor(max_workers=max(1, int(n_workers))) as ex:
-        return list(ex.map(run, range(len(ligands))))
+    def dock(self, ligands, corner1, corner2, seeds=None, **kw):
+        def run(i):
+            v, c = self._state()
+            return dock_ligand(v, c, ligands[i], corner1, corner2, seed=(i + 1 if seeds is None else int(seeds[i])), **kw)
+        return list(self._ex.map(run, range(len(ligands))))
+
+    def close(self):
+        self._ex.shutdown(wait=True)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+        return False
+
+
+def dock_many(ligands, rec_xyz, rec_types, cnn_model_names, corner1, corner2, n_workers=8, device=0, seeds=None, **kw):
+    """One-shot convenience around DockingPool."""
+    with DockingPool(rec_xyz, rec_types, cnn_model_names, n_workers, device) as pool:
+        return pool.dock(ligands, corner1, corner2, seeds=seeds, **kw)
