@@ -44,9 +44,10 @@ struct DevBuf {
   size_t cap = 0;
   void ensure(size_t n) {
     if (cap >= n) return;
+    n = std::max<size_t>(std::max<size_t>(n, 4096), cap + cap / 2);  // floor + geometric growth: few device-wide syncs
     if (p) cudaFree(p);
     p = nullptr;
-    GB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    GB_CUDA(cudaMalloc(&p, n * sizeof(T)));
     cap = n;
   }
   ~DevBuf() { if (p) cudaFree(p); }
@@ -57,9 +58,10 @@ struct PinBuf {
   size_t cap = 0;
   void ensure(size_t n) {
     if (cap >= n) return;
+    n = std::max<size_t>(std::max<size_t>(n, 4096), cap + cap / 2);
     if (p) cudaFreeHost(p);
     p = nullptr;
-    GB_CUDA(cudaHostAlloc(&p, std::max<size_t>(n, 1) * sizeof(T), cudaHostAllocDefault));
+    GB_CUDA(cudaHostAlloc(&p, n * sizeof(T), cudaHostAllocDefault));
     cap = n;
   }
   ~PinBuf() { if (p) cudaFreeHost(p); }

@@ -1026,7 +1026,11 @@ int tc_prepare_grid(const TcPoseBatch& pb, TcGridWorkspace& gw, int buf, int kin
   const int nb = pb.n_poses;
   const ActLayout L1 = make_layout(24, 1, 32);
   const int cap = std::max(1, pb.n_rec + pb.max_pose_atoms);
-  const size_t need = (size_t)nb * cap;
+  // allocation sizes have a floor (64 poses, 128 ligand atoms) so that small batches of varying size -- the kept
+  // poses of one docked ligand -- never re-allocate: cudaFree / cudaMemset synchronise the whole device and would
+  // stall the kernels of other handles (DockingPool keeps one handle per host thread)
+  const int nb_alloc = std::max(nb, 64);
+  const size_t need = (size_t)nb_alloc * std::max(cap, pb.n_rec + 128);
   if (gw.list_cap < need) {
     GB_CUDA(cudaStreamSynchronize(s));
     if (gw.list_xyzr) cudaFree(gw.list_xyzr);
@@ -1035,13 +1039,13 @@ int tc_prepare_grid(const TcPoseBatch& pb, TcGridWorkspace& gw, int buf, int kin
     GB_CUDA(cudaMalloc(&gw.list_ch, need * sizeof(int)));
     gw.list_cap = need;
   }
-  if (gw.listn_cap < (size_t)nb) {
+  if (gw.listn_cap < (size_t)nb_alloc) {
     GB_CUDA(cudaStreamSynchronize(s));
     if (gw.list_n) cudaFree(gw.list_n);
-    GB_CUDA(cudaMalloc(&gw.list_n, (size_t)nb * sizeof(int)));
-    gw.listn_cap = nb;
+    GB_CUDA(cudaMalloc(&gw.list_n, (size_t)nb_alloc * sizeof(int)));
+    gw.listn_cap = nb_alloc;
   }
-  const size_t need0 = act_bytes(L1, nb);
+  const size_t need0 = act_bytes(L1, nb_alloc);
   for (int kind = 0; kind < 2; kind++) {
     if (!(kinds_mask & (1 << kind)) || gw.cap[kind][buf] >= need0) continue;
     GB_CUDA(cudaDeviceSynchronize());
@@ -1085,13 +1089,14 @@ int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspa
   auto tw = get_tc_weights(m);
   int launches = 0;
   const int nb = pb.n_poses;
+  const int nb_alloc = std::max(nb, 64);  // see tc_prepare_grid
   const ActLayout L1 = make_layout(24, 1, 32), L3 = make_layout(12, 2, 32), L5 = make_layout(6, 2, 64);
   const uint4* x0 = reinterpret_cast<const uint4*>(x0v);
   // --- workspaces: 0 = Y (conv outputs, reused), 1 = X2, 2 = X4 ---
-  ws.ensure(0, (size_t)nb * 24 * 24 * 24 * 32 * sizeof(__half) + 1024);
-  ws.ensure(1, act_bytes(L3, nb));
-  ws.ensure(2, act_bytes(L5, nb));
-  ws.ensure(3, (size_t)nb * 216 * 128 * sizeof(__half) + 1024);
+  ws.ensure(0, (size_t)nb_alloc * 24 * 24 * 24 * 32 * sizeof(__half) + 1024);
+  ws.ensure(1, act_bytes(L3, nb_alloc));
+  ws.ensure(2, act_bytes(L5, nb_alloc));
+  ws.ensure(3, (size_t)nb_alloc * 216 * 128 * sizeof(__half) + 1024);
   __half* Y = reinterpret_cast<__half*>(ws.buf[0]);
   uint4* X2 = reinterpret_cast<uint4*>(ws.buf[1]);
   uint4* X4 = reinterpret_cast<uint4*>(ws.buf[2]);
@@ -1099,7 +1104,7 @@ int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspa
   __half* Y3 = Y;  // conv3's output reuses conv1's buffer unless the backward pass needs both
   if (keep_activations) {
     GB_CHECK(m.arch == GB_ARCH_DEFAULT2018, "activations are kept for the default2018 family only");
-    ws.ensure(7, (size_t)nb * 12 * 12 * 12 * 64 * sizeof(__half) + 1024);
+    ws.ensure(7, (size_t)nb_alloc * 12 * 12 * 12 * 64 * sizeof(__half) + 1024);
     Y3 = reinterpret_cast<__half*>(ws.buf[7]);
   }
   const int pw_blocks = 148 * 8;

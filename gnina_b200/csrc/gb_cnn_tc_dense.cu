@@ -488,10 +488,11 @@ int tc_forward_dense(const Model& m, const TcPoseBatch& pb, const void* x0max, T
                      Profiler* prof, cudaEvent_t x0_consumed) {
   auto tw = get_dense_weights(m);
   const int nb = pb.n_poses;
+  const int nb_alloc = std::max(nb, 64);  // allocation floor, see tc_prepare_grid
   const ActLayout A0 = make_layout(24, 1, 96), A1 = make_layout(12, 2, 160), A2 = make_layout(6, 2, 224);
-  ws.ensure(4, act_bytes(A0, nb));
-  ws.ensure(5, act_bytes(A1, nb));
-  ws.ensure(6, act_bytes(A2, nb));
+  ws.ensure(4, act_bytes(A0, nb_alloc));
+  ws.ensure(5, act_bytes(A1, nb_alloc));
+  ws.ensure(6, act_bytes(A2, nb_alloc));
   uint4* B0 = reinterpret_cast<uint4*>(ws.buf[4]);
   uint4* B1 = reinterpret_cast<uint4*>(ws.buf[5]);
   uint4* B2 = reinterpret_cast<uint4*>(ws.buf[6]);

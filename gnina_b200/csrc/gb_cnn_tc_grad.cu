@@ -341,20 +341,21 @@ int tc_backward(const Model& m, const TcPoseBatch& pb, TcWorkspace& ws, const fl
   auto tw = get_tc_weights(m);
   auto gw = get_grad_weights(m);
   const int nb = pb.n_poses;
+  const int nb_alloc = std::max(nb, 64);  // allocation floor, see tc_prepare_grid
   const ActLayout L1 = make_layout(24, 1, 32), L3 = make_layout(12, 2, 64), L5 = make_layout(6, 2, 64);
   // forward activations kept by tc_forward(keep_activations = true)
   const __half* Y1 = reinterpret_cast<const __half*>(ws.buf[0]);
   const __half* Y3 = reinterpret_cast<const __half*>(ws.buf[7]);
   const __half* Y5 = reinterpret_cast<const __half*>(ws.buf[3]);
   GB_CHECK(Y1 && Y3 && Y5, "tc_backward needs the activations of tc_forward(keep_activations = true)");
-  ws.ensure(8, act_bytes(L5, nb));
-  ws.ensure(9, act_bytes(L5, nb));
-  ws.ensure(10, act_bytes(L5, nb));
-  ws.ensure(11, act_bytes(L5, nb));
-  ws.ensure(12, act_bytes(L3, nb));
-  ws.ensure(13, act_bytes(make_layout(12, 2, 32), nb));
-  ws.ensure(14, act_bytes(L1, nb));
-  ws.ensure(15, (size_t)nb * 24 * 24 * 24 * 32 * sizeof(__half) + 1024);
+  ws.ensure(8, act_bytes(L5, nb_alloc));
+  ws.ensure(9, act_bytes(L5, nb_alloc));
+  ws.ensure(10, act_bytes(L5, nb_alloc));
+  ws.ensure(11, act_bytes(L5, nb_alloc));
+  ws.ensure(12, act_bytes(L3, nb_alloc));
+  ws.ensure(13, act_bytes(make_layout(12, 2, 32), nb_alloc));
+  ws.ensure(14, act_bytes(L1, nb_alloc));
+  ws.ensure(15, (size_t)nb_alloc * 24 * 24 * 24 * 32 * sizeof(__half) + 1024);
   uint4 *G5a = reinterpret_cast<uint4*>(ws.buf[8]), *G5b = reinterpret_cast<uint4*>(ws.buf[9]);
   uint4 *GX4a = reinterpret_cast<uint4*>(ws.buf[10]), *GX4b = reinterpret_cast<uint4*>(ws.buf[11]);
   uint4* GY3 = reinterpret_cast<uint4*>(ws.buf[12]);

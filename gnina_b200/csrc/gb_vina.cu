@@ -108,6 +108,8 @@ struct Vina {
     float4* seg_rel_origin = nullptr;
     float4* seg_rel_axis = nullptr;
     int2* pairs = nullptr;
+    int* adj_off = nullptr;    // [n_atoms + 1] CSR over the pair list, both directions
+    int* adj = nullptr;        // [2 n_pairs] partner atom
   } lig;
   // receptor (heavy atoms, index order)
   float4* d_rec = nullptr;  // x, y, z, type
@@ -129,7 +131,7 @@ struct Vina {
     for (auto q : pws) cudaFreeHost(q);
     cudaFree(d_fast); cudaFree(d_smooth); cudaFree(d_sp); cudaFree(d_rec);
     cudaFree(lig.local); cudaFree(lig.atom_seg); cudaFree(lig.seg); cudaFree(lig.seg_rel_origin); cudaFree(lig.seg_rel_axis);
-    cudaFree(lig.pairs); cudaFree(d_lig); cudaFree(d_off); cudaFree(d_atom_e); cudaFree(d_deriv);
+    cudaFree(lig.pairs); cudaFree(lig.adj_off); cudaFree(lig.adj); cudaFree(d_lig); cudaFree(d_off); cudaFree(d_atom_e); cudaFree(d_deriv);
     cudaFree(d_pose_e); cudaFree(d_tors);
     for (auto g : grid_pool) cudaFree(g);
   }
@@ -581,6 +583,7 @@ struct LigPtrs {
   int n_atoms, n_seg, n_pairs, max_depth, n_heavy;
   float gyration_radius;
   const float4* local; const int* atom_seg; const int4* seg; const float4* rel_origin; const float4* rel_axis; const int2* pairs;
+  const int* adj_off; const int* adj;
 };
 struct DockField { GridGeom G; GridPtrs gp; const float2* smooth; int n_samples; float factor, slope; const float4* sp; int n_sp; float sp_fraction; };
 
@@ -728,42 +731,53 @@ __device__ float dk_eval_deriv(const LigPtrs& L, const DockField& F, WarpWs& W, 
     W.forces[3 * i] = d[0]; W.forces[3 * i + 1] = d[1]; W.forces[3 * i + 2] = d[2];
   }
   __syncwarp();
-  for (int k = lane; k < L.n_pairs; k += 32) {
-    const int2 pr = L.pairs[k];
-    const float rx = W.coords[3 * pr.y] - W.coords[3 * pr.x], ry = W.coords[3 * pr.y + 1] - W.coords[3 * pr.x + 1],
-                rz = W.coords[3 * pr.y + 2] - W.coords[3 * pr.x + 2];
-    const float r2 = rx * rx + ry * ry + rz * rz;
-    if (r2 < 64.f) {
-      int t1 = (int)L.local[pr.x].w, t2 = (int)L.local[pr.y].w;
-      if (t1 > t2) { const int tt = t1; t1 = t2; t2 = tt; }
-      float pe, dor;
-      if (F.sp) {  // precalculate_splines::eval_deriv (a pair whose knots are all zero has all-zero coefficients)
-        const float r = sqrtf(r2);
-        int idx = (int)(r / F.sp_fraction);
-        if (idx >= F.n_sp) idx = F.n_sp - 1;
-        const float4 c = F.sp[(size_t)(t1 + t2 * (t2 + 1) / 2) * F.n_sp + idx];
-        const float lx = r - idx * F.sp_fraction;
-        pe = ((c.x * lx + c.y) * lx + c.z) * lx + c.w;
-        dor = ((3 * c.x * lx + 2 * c.y) * lx + c.z) / r;
-      } else {
-        const float r2f = F.factor * r2;
-        const int i1 = (int)r2f;
-        const float rem = r2f - i1;
-        const float2* tb = F.smooth + (size_t)(t1 + t2 * (t2 + 1) / 2) * F.n_samples;
-        const float2 s1 = tb[i1], s2 = tb[i1 + 1];
-        pe = s1.x + rem * (s2.x - s1.x);
-        dor = s1.y + rem * (s2.y - s1.y);
+  // V6 intramolecular pairs, atom by atom: lane i walks atom i's partners (CSR, both directions) and sums the forces
+  // on ITS atom in registers -- every pair is evaluated from both ends (the energy counts half each time), which costs
+  // 2x the table lookups and removes the shared-memory float atomics that the pair-parallel version spent 70 % of
+  // its stall samples on (ncu r1l: consecutive pairs share their first atom, a 32-way serialised CAS loop).  The sums
+  // are now in a fixed order: evaluations are reproducible.
+  for (int i = lane; i < L.n_atoms; i += 32) {
+    const float xi = W.coords[3 * i], yi = W.coords[3 * i + 1], zi = W.coords[3 * i + 2];
+    const int ti = (int)L.local[i].w;
+    float fxs = 0.f, fys = 0.f, fzs = 0.f, es = 0.f;
+    const int q1 = L.adj_off[i + 1];
+    for (int q = L.adj_off[i]; q < q1; q++) {
+      const int j = L.adj[q];
+      const float rx = W.coords[3 * j] - xi, ry = W.coords[3 * j + 1] - yi, rz = W.coords[3 * j + 2] - zi;
+      const float r2 = rx * rx + ry * ry + rz * rz;
+      if (r2 < 64.f) {
+        int t1 = ti, t2 = (int)L.local[j].w;
+        if (t1 > t2) { const int tt = t1; t1 = t2; t2 = tt; }
+        float pe, dor;
+        if (F.sp) {  // precalculate_splines::eval_deriv (a pair whose knots are all zero has all-zero coefficients)
+          const float r = sqrtf(r2);
+          int idx = (int)(r / F.sp_fraction);
+          if (idx >= F.n_sp) idx = F.n_sp - 1;
+          const float4 c = F.sp[(size_t)(t1 + t2 * (t2 + 1) / 2) * F.n_sp + idx];
+          const float lx = r - idx * F.sp_fraction;
+          pe = ((c.x * lx + c.y) * lx + c.z) * lx + c.w;
+          dor = ((3 * c.x * lx + 2 * c.y) * lx + c.z) / r;
+        } else {
+          const float r2f = F.factor * r2;
+          const int i1 = (int)r2f;
+          const float rem = r2f - i1;
+          const float2* tb = F.smooth + (size_t)(t1 + t2 * (t2 + 1) / 2) * F.n_samples;
+          const float2 s1 = tb[i1], s2 = tb[i1 + 1];
+          pe = s1.x + rem * (s2.x - s1.x);
+          dor = s1.y + rem * (s2.y - s1.y);
+        }
+        float fx = dor * rx, fy = dor * ry, fz = dor * rz;
+        if (pe > 0 && v[0] < 0.1f * 3.402823466e+38f) {
+          const float tmp = (v[0] < 1.1920929e-07f) ? 0.f : (v[0] / (v[0] + pe));
+          pe *= tmp;
+          fx *= tmp * tmp; fy *= tmp * tmp; fz *= tmp * tmp;
+        }
+        es += pe;
+        fxs -= fx; fys -= fy; fzs -= fz;  // force on atom i of the pair (i, j): -dor (x_j - x_i)
       }
-      float fx = dor * rx, fy = dor * ry, fz = dor * rz;
-      if (pe > 0 && v[0] < 0.1f * 3.402823466e+38f) {
-        const float tmp = (v[0] < 1.1920929e-07f) ? 0.f : (v[0] / (v[0] + pe));
-        pe *= tmp;
-        fx *= tmp * tmp; fy *= tmp * tmp; fz *= tmp * tmp;
-      }
-      e += pe;
-      atomicAdd(&W.forces[3 * pr.x], -fx); atomicAdd(&W.forces[3 * pr.x + 1], -fy); atomicAdd(&W.forces[3 * pr.x + 2], -fz);
-      atomicAdd(&W.forces[3 * pr.y], fx); atomicAdd(&W.forces[3 * pr.y + 1], fy); atomicAdd(&W.forces[3 * pr.y + 2], fz);
     }
+    e += 0.5f * es;
+    W.forces[3 * i] += fxs; W.forces[3 * i + 1] += fys; W.forces[3 * i + 2] += fzs;
   }
   e = warp_sum(e);
   __syncwarp();
@@ -1088,7 +1102,7 @@ static void make_field(const Vina& v, float slope, DockField& F) {
 static LigPtrs lig_ptrs(const Vina& v) {
   const auto& l = v.lig;
   return LigPtrs{l.n_atoms, l.n_seg, l.n_pairs, l.max_depth, l.n_heavy, l.gyration_radius, l.local, l.atom_seg, l.seg, l.seg_rel_origin,
-                 l.seg_rel_axis, l.pairs};
+                 l.seg_rel_axis, l.pairs, l.adj_off, l.adj};
 }
 static void check_dock_ready(const Vina& v) {
   GB_CHECK(v.lig.n_atoms > 0, "gb_vina_set_ligand has not been called");
@@ -1154,6 +1168,21 @@ int gb_vina_set_ligand(gb_vina* h, const gb_ligand_topology* t) {
   const size_t max_pairs = (size_t)kDkMaxAtoms * (kDkMaxAtoms - 1) / 2;
   up(&l.local, local, kDkMaxAtoms); up(&l.atom_seg, aseg, kDkMaxAtoms); up(&l.seg, seg, kDkMaxSeg);
   up(&l.seg_rel_origin, ro, kDkMaxSeg); up(&l.seg_rel_axis, ra, kDkMaxSeg); up(&l.pairs, pairs, max_pairs);
+  // CSR adjacency of the pair list in both directions: the device sums the pair forces atom by atom (no atomics)
+  std::vector<int> adj_off(na + 1, 0), adj(std::max(2 * t->n_pairs, 1), 0);
+  for (int k = 0; k < t->n_pairs; k++) {
+    GB_CHECK(t->pair_a[k] >= 0 && t->pair_a[k] < na && t->pair_b[k] >= 0 && t->pair_b[k] < na && t->pair_a[k] != t->pair_b[k], "pair atom index");
+    adj_off[t->pair_a[k] + 1]++; adj_off[t->pair_b[k] + 1]++;
+  }
+  for (int i = 0; i < na; i++) adj_off[i + 1] += adj_off[i];
+  {
+    std::vector<int> fill(adj_off.begin(), adj_off.end() - 1);
+    for (int k = 0; k < t->n_pairs; k++) {  // pair order is kept inside every atom's list
+      adj[fill[t->pair_a[k]]++] = t->pair_b[k];
+      adj[fill[t->pair_b[k]]++] = t->pair_a[k];
+    }
+  }
+  up(&l.adj_off, adj_off, kDkMaxAtoms + 1); up(&l.adj, adj, 2 * max_pairs);
   GB_CUDA(cudaStreamSynchronize(v.stream));  // the host vectors above go out of scope
   l.n_atoms = na; l.n_seg = ns; l.n_pairs = t->n_pairs; l.max_depth = max_depth; l.n_heavy = nh; l.gyration_radius = t->gyration_radius;
   GBV_END
