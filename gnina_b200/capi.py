@@ -43,6 +43,11 @@ class ModelInfo(C.Structure):
                 ("name", C.c_char * 64)]
 
 
+# 32 hardware work queues instead of 8 (see prefer_many_hw_queues, gb_internal.h): must be in the environment before
+# the process initialises CUDA, whoever does it first (this library or torch)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+
 def lib():
     global _lib
     if _lib is not None:

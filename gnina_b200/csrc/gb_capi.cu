@@ -10,6 +10,10 @@
 namespace gb {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& m) { g_last_error = m; }
+void prefer_many_hw_queues() {
+  static const int once = (setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0), 0);
+  (void)once;
+}
 
 void Profiler::begin(const char* name, cudaStream_t s) {
   int id = -1;
@@ -151,6 +155,7 @@ struct gb_cnn {
   return GB_OK;
 
 static void require_device() {
+  prefer_many_hw_queues();
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
     cudaGetLastError();
@@ -170,6 +175,7 @@ int gb_device_count(void) {
 }
 
 int gb_initialize_cuda(int device) {
+  prefer_many_hw_queues();
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
   cudaDeviceProp prop;

@@ -17,6 +17,11 @@ struct Error : std::runtime_error {
   Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
 };
 void set_last_error(const std::string& m);
+// Before the first CUDA call of the process: ask for 32 hardware work queues instead of the default 8, unless the
+// user set CUDA_DEVICE_MAX_CONNECTIONS.  Every handle owns a stream; with 8 queues, streams of different host threads
+// share a queue and a copy queued behind another handle's pending D2H waits for THAT handle's long kernel (measured:
+// set_ligand 0.1 ms -> 200 ms with 16 docking workers).  No effect if CUDA is already initialised.
+void prefer_many_hw_queues();
 
 #define GB_CUDA(expr)                                                                                  \
   do {                                                                                                 \

@@ -396,6 +396,7 @@ extern "C" {
 int gb_vina_create(int device, const float* weights6, float factor, gb_vina** out) {
   GBV_BEGIN
   GB_CHECK(out, "null argument");
+  prefer_many_hw_queues();
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
