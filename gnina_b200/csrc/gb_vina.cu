@@ -60,8 +60,9 @@ struct Vina {
   size_t dws_cap[8] = {};
   template <typename T>
   T* ws(int i, size_t n) {
-    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
     if (dws_cap[i] < bytes) {
+      bytes = std::max(bytes, dws_cap[i] + dws_cap[i] / 2);
       if (dws[i]) cudaFree(dws[i]);
       dws[i] = nullptr; dws_cap[i] = 0;
       GB_CUDA(cudaMalloc(&dws[i], bytes));
@@ -76,8 +77,9 @@ struct Vina {
   size_t pws_cap[8] = {};
   template <typename T>
   T* pin(int i, size_t n) {
-    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
     if (pws_cap[i] < bytes) {
+      bytes = std::max(bytes, pws_cap[i] + pws_cap[i] / 2);
       if (pws[i]) cudaFreeHost(pws[i]);
       pws[i] = nullptr; pws_cap[i] = 0;
       GB_CUDA(cudaMallocHost(&pws[i], bytes));
@@ -372,14 +374,14 @@ static void stage_poses(Vina& v, const float* lig_xyz, const int32_t* lig_type, 
   const int n_atoms = off[n_poses];
   if ((size_t)n_atoms > v.cap_atoms) {
     cudaFree(v.d_lig); cudaFree(v.d_atom_e); cudaFree(v.d_deriv);
-    v.cap_atoms = (size_t)n_atoms + 1024;
+    v.cap_atoms = std::max<size_t>({(size_t)n_atoms + 1024, 16384, v.cap_atoms * 2});  // floor + doubling: rare device-wide syncs
     GB_CUDA(cudaMalloc(&v.d_lig, v.cap_atoms * sizeof(float4)));
     GB_CUDA(cudaMalloc(&v.d_atom_e, v.cap_atoms * sizeof(float)));
     GB_CUDA(cudaMalloc(&v.d_deriv, v.cap_atoms * 3 * sizeof(float)));
   }
   if ((size_t)n_poses + 1 > v.cap_poses) {
     cudaFree(v.d_off); cudaFree(v.d_pose_e); cudaFree(v.d_tors);
-    v.cap_poses = (size_t)n_poses + 1024;
+    v.cap_poses = std::max<size_t>({(size_t)n_poses + 1024, 4096, v.cap_poses * 2});
     GB_CUDA(cudaMalloc(&v.d_off, v.cap_poses * sizeof(int)));
     GB_CUDA(cudaMalloc(&v.d_pose_e, v.cap_poses * sizeof(float)));
     GB_CUDA(cudaMalloc(&v.d_tors, v.cap_poses * sizeof(float)));
@@ -1198,13 +1200,16 @@ static int dock_eval_common(gb_vina* h, const float* confs, int n, const float* 
   check_dock_ready(v);
   if (n == 0) return GB_OK;
   const int T = v.lig.n_seg - 1, nx = 7 + T, ng = 6 + T, na = v.lig.n_atoms;
-  float* d_conf = v.ws<float>(0, (size_t)n * nx);
+  // workspaces are sized by the MAXIMUM ligand dimensions: in a screen every ligand has another size, and a growing
+  // buffer means cudaFree / cudaFreeHost = a device-wide synchronisation that stalls every other handle's kernels
+  constexpr size_t NXA = 7 + kDkMaxSeg - 1, NGA = 6 + kDkMaxSeg - 1, NAA = kDkMaxAtoms;
+  float* d_conf = v.ws<float>(0, (size_t)n * NXA);
   float* d_e = v.ws<float>(1, n);
-  float* d_g = v.ws<float>(2, (size_t)n * ng);
-  float* d_c = coords ? v.ws<float>(3, (size_t)n * 3 * na) : nullptr;
-  float* d_xo = mode == 1 ? v.ws<float>(4, (size_t)n * nx) : nullptr;
+  float* d_g = v.ws<float>(2, (size_t)n * NGA);
+  float* d_c = coords ? v.ws<float>(3, (size_t)n * 3 * NAA) : nullptr;
+  float* d_xo = mode == 1 ? v.ws<float>(4, (size_t)n * NXA) : nullptr;
   int* d_ev = mode == 1 ? v.ws<int>(5, n) : nullptr;
-  float* p_conf = v.pin<float>(0, (size_t)n * nx);
+  float* p_conf = v.pin<float>(0, (size_t)n * NXA);
   memcpy(p_conf, confs, (size_t)n * nx * 4);
   GB_CUDA(cudaMemcpyAsync(d_conf, p_conf, (size_t)n * nx * 4, cudaMemcpyHostToDevice, v.stream));
   DockField F;
@@ -1214,9 +1219,9 @@ static int dock_eval_common(gb_vina* h, const float* confs, int n, const float* 
                                                                                   d_c, mode, maxiters, d_xo, d_ev);
   GB_CUDA(cudaGetLastError());
   float* p_e = v.pin<float>(1, n);
-  float* p_g = change ? v.pin<float>(2, (size_t)n * ng) : nullptr;
-  float* p_c = coords ? v.pin<float>(3, (size_t)n * 3 * na) : nullptr;
-  float* p_xo = (mode == 1 && confs_out) ? v.pin<float>(4, (size_t)n * nx) : nullptr;
+  float* p_g = change ? v.pin<float>(2, (size_t)n * NGA) : nullptr;
+  float* p_c = coords ? v.pin<float>(3, (size_t)n * 3 * NAA) : nullptr;
+  float* p_xo = (mode == 1 && confs_out) ? v.pin<float>(4, (size_t)n * NXA) : nullptr;
   int* p_ev = (mode == 1 && evals) ? v.pin<int>(5, n) : nullptr;
   GB_CUDA(cudaMemcpyAsync(p_e, d_e, (size_t)n * 4, cudaMemcpyDeviceToHost, v.stream));
   if (p_g) GB_CUDA(cudaMemcpyAsync(p_g, d_g, (size_t)n * ng * 4, cudaMemcpyDeviceToHost, v.stream));
@@ -1251,8 +1256,9 @@ int gb_vina_mc(gb_vina* h, const gb_mc_params* P, const float* corner1, const fl
   const int T = v.lig.n_seg - 1, nx = 7 + T, S = P->num_saved_mins, nh = std::max(v.lig.n_heavy, 1);
   uint32_t* d_seeds = v.ws<uint32_t>(0, n_chains);
   float* d_e = v.ws<float>(1, (size_t)n_chains * S);
-  float* d_c = v.ws<float>(2, (size_t)n_chains * S * nx);
-  float* d_h = v.ws<float>(3, (size_t)n_chains * S * 3 * nh);
+  constexpr size_t NXA = 7 + kDkMaxSeg - 1;  // allocation by maximum ligand dimensions, see dock_eval_common
+  float* d_c = v.ws<float>(2, (size_t)n_chains * S * NXA);
+  float* d_h = v.ws<float>(3, (size_t)n_chains * S * 3 * kDkMaxAtoms);
   int* d_n = v.ws<int>(4, n_chains);
   uint32_t* p_seeds = v.pin<uint32_t>(0, n_chains);
   memcpy(p_seeds, seeds, (size_t)n_chains * 4);
@@ -1268,7 +1274,7 @@ int gb_vina_mc(gb_vina* h, const gb_mc_params* P, const float* corner1, const fl
                                                                                      d_c, d_h, d_n);
   GB_CUDA(cudaGetLastError());
   float* p_e = v.pin<float>(1, (size_t)n_chains * S);
-  float* p_c = v.pin<float>(2, (size_t)n_chains * S * nx);
+  float* p_c = v.pin<float>(2, (size_t)n_chains * S * NXA);
   int* p_n = v.pin<int>(3, n_chains);
   GB_CUDA(cudaMemcpyAsync(p_e, d_e, (size_t)n_chains * S * 4, cudaMemcpyDeviceToHost, v.stream));
   GB_CUDA(cudaMemcpyAsync(p_c, d_c, (size_t)n_chains * S * nx * 4, cudaMemcpyDeviceToHost, v.stream));
