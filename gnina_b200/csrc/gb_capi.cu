@@ -394,11 +394,12 @@ int gb_cnn_stage_poses(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type,
   GB_CUDA(cudaSetDevice(h->device));
   // the previous batch may still be reading the pinned staging buffers
   GB_CUDA(cudaStreamSynchronize(h->stream));
-  h->n_staged = n_poses;
-  h->n_input_atoms = n_poses > 0 ? pose_offsets[n_poses] : 0;
+  h->n_staged = 0;  // nothing is staged until every check below has passed
+  h->n_input_atoms = 0;
   if (n_poses == 0) return GB_OK;
   const int total = pose_offsets[n_poses];
   GB_CHECK(pose_offsets[0] == 0 && total >= 0, "pose_offsets must start at 0");
+  for (int p = 0; p < n_poses; p++) GB_CHECK(pose_offsets[p + 1] >= pose_offsets[p], "pose_offsets must be non-decreasing");
   h->h_centers.ensure(3 * (size_t)n_poses);
   h->d_centers.ensure(3 * (size_t)n_poses);
   for (int p = 0; p < n_poses; p++) {
@@ -464,6 +465,8 @@ int gb_cnn_stage_poses(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type,
     GB_CUDA(cudaMemcpyAsync(G.lig_off.p, G.h_lig_off.p, ((size_t)n_poses + 1) * sizeof(int), cudaMemcpyHostToDevice,
                             h->stream));
   }
+  h->n_staged = n_poses;
+  h->n_input_atoms = total;
   GB_API_END
 }
 
