@@ -81,6 +81,10 @@ struct GridGroup {
   DevBuf<float4> rec_xyzr;
   DevBuf<int> rec_ch;
   int n_rec = 0;
+  std::vector<int> h_rec_src;   // typed receptor atom -> index in the caller's receptor arrays
+  DevBuf<int> rec_off;          // {0, n_rec}: the receptor as one "pose" for the atom-gradient kernels
+  DevBuf<float> rec_grad;       // [n_rec][3], accumulated over the models of the group
+  PinBuf<float> h_rec_grad;
   // staged ligand atoms
   PinBuf<float4> h_lig_xyzr;
   PinBuf<int> h_lig_ch, h_lig_off, h_lig_src;  // h_lig_src: staged atom -> index in the caller's arrays
@@ -369,13 +373,21 @@ int gb_cnn_set_receptor(gb_cnn* h, const float* xyz, const int32_t* smina_type, 
     }
     std::vector<float4> a;
     std::vector<int> ch;
+    G.h_rec_src.clear();
     for (int c = 0; c < G.rec.n_channels; c++)
       for (int i : by_ch[c]) {
         a.push_back(make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2],
                                 kSminaXsRadius[smina_type[i]] * G.sig.radius_scaling));
         ch.push_back(c);
+        G.h_rec_src.push_back(i);
       }
     G.n_rec = (int)a.size();
+    {
+      const int off[2] = {0, G.n_rec};
+      G.rec_off.ensure(2);
+      GB_CUDA(cudaMemcpyAsync(G.rec_off.p, off, sizeof(off), cudaMemcpyHostToDevice, h->stream));
+      GB_CUDA(cudaStreamSynchronize(h->stream));
+    }
     G.rec_xyzr.ensure(a.size());
     G.rec_ch.ensure(ch.size());
     if (G.n_rec) {
@@ -656,7 +668,14 @@ int gb_cnn_score_grad(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, 
   if (rc) return rc;
   GB_API_BEGIN
   GB_CHECK(dlig_xyz, "dlig_xyz must not be NULL");
-  if (drec_xyz) throw Error(GB_ERR_USAGE, "receptor (flexible residue) gradients are not implemented yet");
+  // getReceptorGradient (torch_model.cpp:226-232): the reference scores ONE pose per call and reads the gradient of its
+  // (flexible) receptor atoms afterwards; the batch form keeps that contract -- with a shared receptor a per-pose
+  // receptor gradient only exists for a single pose
+  if (drec_xyz && h->n_staged != 1)
+    throw Error(GB_ERR_USAGE, "receptor gradients (drec_xyz) are defined for a single pose per call");
+  const int n_rec_in = (int)h->rec_type.size();
+  if (drec_xyz)
+    for (int i = 0; i < 3 * n_rec_in; i++) drec_xyz[i] = 0.f;
   GB_CUDA(cudaSetDevice(h->device));
   const int n = h->n_staged, M = (int)h->models.size();
   const int n_in = h->n_input_atoms;
@@ -682,7 +701,13 @@ int gb_cnn_score_grad(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, 
     G.lig_grad.ensure(3 * (size_t)std::max(G.n_staged_atoms, 1));
     GB_CUDA(cudaMemsetAsync(G.lig_grad.p, 0, 3 * (size_t)std::max(G.n_staged_atoms, 1) * sizeof(float), h->stream));
   }
-  DevBuf<float> tmp_grad;
+  DevBuf<float> tmp_grad, tmp_rec;
+  if (drec_xyz)
+    for (auto& Gp : h->groups) {
+      GridGroup& G = *Gp;
+      G.rec_grad.ensure(3 * (size_t)std::max(G.n_rec, 1));
+      GB_CUDA(cudaMemsetAsync(G.rec_grad.p, 0, 3 * (size_t)std::max(G.n_rec, 1) * sizeof(float), h->stream));
+    }
   for (int p0 = 0; p0 < n; p0 += chunk) {
     const int nb = std::min(chunk, n - p0);
     for (auto& Gp : h->groups) {
@@ -712,11 +737,23 @@ int gb_cnn_score_grad(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, 
         launch_head_post(h->d_out3.p, nb, Mo.skip_softmax, Mo.apply_logistic_loss, h->d_pose.p + (size_t)mi * n + p0,
                          h->d_aff.p + (size_t)mi * n + p0, h->d_loss.p + (size_t)mi * n + p0, h->stream);
         // ligand atoms of this chunk: accumulate (scaled 1/M) into the group's gradient array
+        const bool want_rec = drec_xyz && G.n_rec > 0;
+        if (want_rec) tmp_rec.ensure(3 * (size_t)G.n_rec);
         if (fast) {
-          h->launches += tc_backward(Mo, pb, h->ws_tc, h->d_out3.p, tmp_grad.p, h->stream, &h->prof);
+          h->launches += tc_backward(Mo, pb, h->ws_tc, h->d_out3.p, tmp_grad.p, h->stream, &h->prof,
+                                     want_rec ? G.rec_off.p : nullptr, want_rec ? tmp_rec.p : nullptr);
         } else {
           launch_grid_backward(G.lig_xyzr.p, G.lig_ch.p, G.lig_off.p + p0, G.max_pose_atoms, h->d_centers.p + 3 * (size_t)p0, nb,
                                G.n_channels, npts, G.sig.resolution, G.sig.dimension, h->d_dgrid.p, tmp_grad.p, h->stream);
+          h->launches++;
+          if (want_rec) {  // the receptor as the single pose's second atom set
+            launch_grid_backward(G.rec_xyzr.p, G.rec_ch.p, G.rec_off.p, G.n_rec, h->d_centers.p, 1, G.n_channels, npts,
+                                 G.sig.resolution, G.sig.dimension, h->d_dgrid.p, tmp_rec.p, h->stream);
+            h->launches++;
+          }
+        }
+        if (want_rec) {
+          launch_axpy_range(tmp_rec.p, G.rec_grad.p, 0, 3 * G.n_rec, 1.0f / (float)M, h->stream);
           h->launches++;
         }
         launch_axpy_range(tmp_grad.p, G.lig_grad.p, G.h_lig_off.p[p0] * 3, G.h_lig_off.p[p0 + nb] * 3, 1.0f / (float)M,
@@ -736,7 +773,20 @@ int gb_cnn_score_grad(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, 
     GB_CUDA(cudaMemcpyAsync(G.h_lig_grad.p, G.lig_grad.p, 3 * (size_t)G.n_staged_atoms * sizeof(float), cudaMemcpyDeviceToHost,
                             h->stream));
   }
+  if (drec_xyz)
+    for (auto& Gp : h->groups) {
+      GridGroup& G = *Gp;
+      if (!G.n_rec) continue;
+      G.h_rec_grad.ensure(3 * (size_t)G.n_rec);
+      GB_CUDA(cudaMemcpyAsync(G.h_rec_grad.p, G.rec_grad.p, 3 * (size_t)G.n_rec * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    }
   GB_CUDA(cudaStreamSynchronize(h->stream));
+  if (drec_xyz)
+    for (auto& Gp : h->groups) {
+      GridGroup& G = *Gp;
+      for (int a = 0; a < G.n_rec; a++)
+        for (int d = 0; d < 3; d++) drec_xyz[3 * G.h_rec_src[a] + d] += G.h_rec_grad.p[3 * a + d];
+    }
   for (auto& Gp : h->groups) {
     GridGroup& G = *Gp;
     for (int a = 0; a < G.n_staged_atoms; a++) {

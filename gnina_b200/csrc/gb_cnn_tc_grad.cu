@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(256) grid_backward_pooled_kernel(const float4*
 
 // ------------------------------------------------------------------------------------------------------------
 int tc_backward(const Model& m, const TcPoseBatch& pb, TcWorkspace& ws, const float* out3, float* atom_grad, cudaStream_t s,
-                Profiler* prof) {
+                Profiler* prof, const int* rec_off, float* rec_grad) {
   GB_CHECK(m.arch == GB_ARCH_DEFAULT2018 && tc_supported(m), "fast backward: default2018 family only");
   auto tw = get_tc_weights(m);
   auto gw = get_grad_weights(m);
@@ -398,6 +398,13 @@ int tc_backward(const Model& m, const TcPoseBatch& pb, TcWorkspace& ws, const fl
       grid_backward_pooled_kernel<<<g, 256, 0, s>>>(pb.lig_xyzr, pb.lig_ch, pb.lig_off, pb.centers, pb.n_channels, pb.resolution,
                                                     pb.dimension, GX0, 1.f / (512.f * kLossScale), atom_grad);
     }
+  }
+  if (rec_grad && pb.n_rec > 0) {  // getReceptorGradient: the receptor atoms of the (single) pose
+    GB_CHECK(nb == 1 && rec_off, "receptor gradients need a single-pose chunk");
+    ProfScope ps(prof, "tcg_grid_backward_receptor", s);
+    dim3 g((pb.n_rec + 7) / 8, 1);
+    grid_backward_pooled_kernel<<<g, 256, 0, s>>>(pb.rec_xyzr, pb.rec_ch, rec_off, pb.centers, pb.n_channels, pb.resolution,
+                                                  pb.dimension, GX0, 1.f / (512.f * kLossScale), rec_grad);
   }
   tc_debug_set(5, GX0, (size_t)nb * 24 * 24 * 24 * 32 * sizeof(__half));
   tc_debug_set(6, GY1, act_bytes(L1, nb));

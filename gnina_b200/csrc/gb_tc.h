@@ -53,8 +53,9 @@ int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0, TcWorkspac
 // default2018 family, after tc_forward(..., keep_activations = true) on the same workspace: backward of the CE loss
 // through the network and the fused voxelise/pool to the ligand atoms of the chunk; atom_grad [chunk atoms][3] (see
 // gb_cnn_tc_grad.cu); returns #launches
+// rec_off / rec_grad (optional, single-pose chunks): the typed receptor atoms {0, n_rec} as a second atom set of pose 0
 int tc_backward(const Model& m, const TcPoseBatch& pb, TcWorkspace& ws, const float* out3, float* atom_grad, cudaStream_t s,
-                Profiler* prof = nullptr);
+                Profiler* prof = nullptr, const int* rec_off = nullptr, float* rec_grad = nullptr);
 
 // chunk-planar padded grouped activation layout (see gb_cnn_tc.cu)
 struct ActLayout {

@@ -60,9 +60,11 @@ class CNNScorer:
         self.device = device
         self._h = C.c_void_p()
         self._models = []
+        self._n_rec = 0
         if _clone_of is not None:
             capi.check(L.gb_cnn_clone(_clone_of._h, C.byref(self._h)))
             self.model_names = list(_clone_of.model_names)
+            self._n_rec = _clone_of._n_rec          # the clone carries the receptor
             return
         rc = L.gb_initialize_cuda(device)
         if rc != 0:
@@ -116,6 +118,7 @@ class CNNScorer:
         t = np.ascontiguousarray(smina_types, np.int32)
         assert len(xyz) == len(t)
         capi.check(capi.lib().gb_cnn_set_receptor(self._h, _fp(xyz), _ip(t), len(t)))
+        self._n_rec = len(t)
 
     @staticmethod
     def _poses(lig_xyz, lig_types, pose_offsets, centers):
@@ -143,15 +146,17 @@ class CNNScorer:
                                                         *[_fp(o) for o in out]))
         return tuple(out)
 
-    def score_grad_batch(self, lig_xyz, lig_types, pose_offsets, centers=None):
-        """score(m, compute_gradient=True) in batch form -> (score, affinity, loss, variance, dloss/dlig_xyz [n_atoms,3])"""
+    def score_grad_batch(self, lig_xyz, lig_types, pose_offsets, centers=None, receptor=False):
+        """score(m, compute_gradient=True) in batch form -> (score, affinity, loss, variance, dloss/dlig_xyz [n_atoms,3]);
+        receptor=True (single pose only) appends getReceptorGradient: dloss/drec_xyz [n_receptor_atoms, 3]."""
         xyz, t, off, c = self._poses(lig_xyz, lig_types, pose_offsets, centers)
         n = len(off) - 1
         out = [np.empty(n, np.float32) for _ in range(4)]
         grad = np.zeros((len(t), 3), np.float32)
+        rgrad = np.zeros((self._n_rec, 3), np.float32) if receptor else None
         capi.check(capi.lib().gb_cnn_score_grad(self._h, _fp(xyz), _ip(t), _ip(off), n, _fp(c), *[_fp(o) for o in out],
-                                                _fp(grad), None))
-        return (*out, grad)
+                                                _fp(grad), _fp(rgrad)))
+        return (*out, grad, rgrad) if receptor else (*out, grad)
 
     def score(self, lig_xyz, lig_types, center=None):
         """DLScorer::score(model&, false, aff, loss, var) for one pose -> (score, affinity, loss, variance)."""

@@ -106,7 +106,9 @@ int gb_cnn_score_batch_models(gb_cnn* h, const float* lig_xyz, const int32_t* li
  * gradient of the (ensemble-mean) loss with respect to every ligand atom passed, dlig_xyz[n_atoms][3]
  * (TorchModel::forward with autograd + GridMaker::backward, lib/torch_model.cpp:197-221; accumulation and 1/cnt
  * scaling lib/cnn_torch_scorer.cpp:164-179).  The reference adds this to m.minus_forces (lib/model.cu:247-259);
- * untyped atoms (hydrogens) get 0.  drec_xyz (flexible-residue gradients, getReceptorGradient) must be NULL for now.
+ * untyped atoms (hydrogens) get 0.  drec_xyz (NULL, or [n receptor atoms][3] in gb_cnn_set_receptor's order):
+ * getReceptorGradient (lib/torch_model.cpp:226-232), what the reference adds to the flexible residues' atoms; the
+ * reference scores one pose per call, and with a shared receptor the quantity only exists per pose: n_poses must be 1.
  * default2018 and dense families.  Option "precision" selects the kernels: GB_PRECISION_FP16_TC (default; ensembles
  * of default2018-architecture models only -- an ensemble with a dense member uses the fp32 kernels) runs forward AND
  * backward on the tensor cores (fp16 gradients with loss scaling, gb_cnn_tc_grad.cu; max |error| 5e-3 of the largest

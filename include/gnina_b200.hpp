@@ -64,6 +64,7 @@ class CNNScorer {
   gb_cnn* h_ = nullptr;
   std::vector<gb_model*> models_;
   int device_ = 0;
+  int n_rec_ = 0;
   CNNScorer() = default;
 
  public:
@@ -91,12 +92,16 @@ class CNNScorer {
   std::unique_ptr<CNNScorer> fresh_copy() const {  // cnn_torch_scorer.h:54
     std::unique_ptr<CNNScorer> c(new CNNScorer);
     c->device_ = device_;
+    c->n_rec_ = n_rec_;
     check(gb_cnn_clone(h_, &c->h_));
     return c;
   }
   void set_option(const char* key, double v) { check(gb_cnn_set_option(h_, key, v)); }
   gb_model_info info(int i = 0) const { gb_model_info x; check(gb_model_get_info(models_.at(i), &x)); return x; }
-  void set_receptor(const float* xyz, const int32_t* smina_type, int n) { check(gb_cnn_set_receptor(h_, xyz, smina_type, n)); }
+  void set_receptor(const float* xyz, const int32_t* smina_type, int n) {
+    check(gb_cnn_set_receptor(h_, xyz, smina_type, n));
+    n_rec_ = n;
+  }
 
   Scores score_batch(const float* lig_xyz, const int32_t* lig_type, const int32_t* pose_offsets, int n_poses,
                      const float* centers = nullptr) {
@@ -108,14 +113,19 @@ class CNNScorer {
   }
   // DLScorer::score(model&, compute_gradient, affinity, loss, variance): one pose; gradient (if requested) is the
   // derivative of the loss w.r.t. every ligand atom passed = what the reference adds to m.minus_forces
+  // receptor_gradient (optional, sized 3 x receptor atoms by the caller's set_receptor): getReceptorGradient, what the
+  // reference adds to the flexible-residue atoms' minus_forces
   float score(const float* lig_xyz, const int32_t* lig_type, int n_atoms, bool compute_gradient, float& affinity,
-              float& loss, float& variance, std::vector<float>* gradient = nullptr, const float* center = nullptr) {
+              float& loss, float& variance, std::vector<float>* gradient = nullptr, const float* center = nullptr,
+              std::vector<float>* receptor_gradient = nullptr) {
     if (!initialized()) return -1.0f;  // cnn_torch_scorer.cpp:107-108
     const int32_t offs[2] = {0, n_atoms};
     float s = 0;
     if (compute_gradient) {
       std::vector<float> g(3 * (size_t)n_atoms);
-      check(gb_cnn_score_grad(h_, lig_xyz, lig_type, offs, 1, center, &s, &affinity, &loss, &variance, g.data(), nullptr));
+      if (receptor_gradient) receptor_gradient->assign(3 * (size_t)n_rec_, 0.f);
+      check(gb_cnn_score_grad(h_, lig_xyz, lig_type, offs, 1, center, &s, &affinity, &loss, &variance, g.data(),
+                              receptor_gradient ? receptor_gradient->data() : nullptr));
       if (gradient) *gradient = std::move(g);
     } else {
       check(gb_cnn_score_batch(h_, lig_xyz, lig_type, offs, 1, center, &s, &affinity, &loss, &variance));

@@ -38,12 +38,14 @@ class OracleModel:
         return np.concatenate(P), np.concatenate(A), np.concatenate(L)
 
 
-def score_grad(models, rec_xyz, rec_types, lig_xyz, lig_types, pose_offsets, centers=None, dtype=torch.float64):
+def score_grad(models, rec_xyz, rec_types, lig_xyz, lig_types, pose_offsets, centers=None, dtype=torch.float64,
+               receptor=False):
     """CNNTorchScorer::score(m, compute_gradient=True): ensemble outputs + d(mean loss)/d(ligand atoms) [n_atoms,3]
     (TorchModel::forward autograd + GridMaker::backward, torch_model.cpp:197-221; 1/cnt scaling
     cnn_torch_scorer.cpp:176-179)."""
     n = len(pose_offsets) - 1
     grad = np.zeros((len(lig_types), 3), np.float64)
+    rgrad = np.zeros((len(rec_types), 3), np.float64)   # getReceptorGradient (torch_model.cpp:226-232), summed over poses
     per = []
     for m in models:
         b = m.blob
@@ -60,11 +62,14 @@ def score_grad(models, rec_xyz, rec_types, lig_xyz, lig_types, pose_offsets, cen
             pose, aff, loss, dg = cnn_ref.loss_grid_gradient(b, g[None], dtype)
             ag = gm.grid_backward(c, xyz, ch, rad, dg[0].astype(np.float32), b.resolution, b.dimension, b.radius_scaling)
             grad[sl] += ag[len(rec_xyz):] / len(models)
+            rgrad += ag[:len(rec_xyz)] / len(models)
             P.append(pose[0]); A.append(aff[0]); L.append(loss[0])
         per.append((P, A, L))
     out = np.zeros((4, n))
     for i in range(n):
         out[:, i] = cnn_ref.ensemble([q[0][i] for q in per], [q[1][i] for q in per], [q[2][i] for q in per])
+    if receptor:
+        return out[0], out[1], out[2], out[3], grad, rgrad
     return out[0], out[1], out[2], out[3], grad
 
 

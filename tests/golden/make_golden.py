@@ -81,7 +81,7 @@ def grad_kat(n_poses=2, name="crossdock_default2018", out_name="grad_kat.npz"):
     offs = k["pose_offsets"][:n_poses + 1]
     rc, rr = gm.type_atoms(k["rec_types"], om.rec_t2c, 0)
     lc, lr = gm.type_atoms(k["lig_types"], om.lig_t2c, om.n_rec)
-    grads, losses = [], []
+    grads, losses, rgrads = [], [], []
     for p in range(n_poses):
         sl = slice(offs[p], offs[p + 1])
         c = gm.center_of(k["lig_xyz"][sl])
@@ -91,8 +91,9 @@ def grad_kat(n_poses=2, name="crossdock_default2018", out_name="grad_kat.npz"):
         loss = F.cross_entropy(out, torch.ones(1, dtype=torch.long))
         loss.backward()
         ag = gm.grid_backward(c, xyz, ch, rad, g.grad[0].numpy().astype(np.float32))
-        grads.append(ag[len(k["rec_xyz"]):]); losses.append(float(loss))
+        grads.append(ag[len(k["rec_xyz"]):]); losses.append(float(loss)); rgrads.append(ag[:len(k["rec_xyz"])])
     np.savez_compressed(os.path.join(HERE, out_name), lig_grad=np.concatenate(grads), loss=np.array(losses),
+                        rec_grad=np.stack(rgrads).astype(np.float32),   # [pose][receptor atom][3]: getReceptorGradient
                         n_poses=n_poses, model=np.array(name.replace(".", "_")))
     print("grad kat: |g|max", np.abs(np.concatenate(grads)).max(), "loss", losses)
 

@@ -160,3 +160,29 @@ def test_fast_gradient_matches_validation_path_on_a_ragged_multi_chunk_batch(kat
     k = 7
     b2 = fast.score_grad_batch(xyz[:offs[k]], types[:offs[k]], offs[:k + 1])
     assert np.abs(b2[4] - gb[:offs[k]]).max() < 1e-6 * max(scale, 1.0)
+
+
+def test_receptor_gradient_matches_reference_autograd(kat, golden_dir):
+    """getReceptorGradient (flexible-residue atoms): d loss / d receptor atoms of a single pose, validation and fast
+    kernels, against autograd through the reference .pt + the oracle's GridMaker::backward"""
+    from gnina_b200 import CNNScorer, capi
+    g = np.load(os.path.join(golden_dir, "grad_kat.npz"))
+    offs = kat["pose_offsets"]
+    for prec, tol in ((0, 2e-4), (1, FAST_GRAD_TOL)):
+        s = CNNScorer([str(g["model"])], precision=prec)
+        s.set_receptor(kat["rec_xyz"], kat["rec_types"])
+        for p in range(int(g["n_poses"])):
+            x, t = kat["lig_xyz"][offs[p]:offs[p + 1]], kat["lig_types"][offs[p]:offs[p + 1]]
+            out = s.score_grad_batch(x, t, [0, len(t)], receptor=True)
+            want = g["rec_grad"][p]
+            scale = np.abs(want).max()
+            assert out[5].shape == want.shape
+            assert np.abs(out[5] - want).max() < tol * scale, (prec, p)
+            assert np.abs(out[5][kat["rec_types"] <= 1]).max() == 0.0 if (kat["rec_types"] <= 1).any() else True
+            assert np.abs(out[4] - g["lig_grad"][offs[p]:offs[p + 1]]).max() < tol * np.abs(g["lig_grad"]).max()
+        with pytest.raises(capi.GbError, match="single pose"):
+            s.score_grad_batch(kat["lig_xyz"][:offs[2]], kat["lig_types"][:offs[2]], offs[:3], receptor=True)
+    # a clone carries the receptor and answers the same
+    c = s.fresh_copy()
+    x, t = kat["lig_xyz"][:offs[1]], kat["lig_types"][:offs[1]]
+    assert np.array_equal(c.score_grad_batch(x, t, [0, len(t)], receptor=True)[5], s.score_grad_batch(x, t, [0, len(t)], receptor=True)[5])
