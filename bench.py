@@ -337,7 +337,7 @@ def main():
             "kernel_time_share": shares,
             "model_tflops": value * FLOP_PER_EVAL["default2018"] / 1e12,
             "checksum": float(np.sum(res[0], dtype=np.float64))}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # the CPU port is timed beside the N = 1 run only
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line))
     if world > 1:
