@@ -119,6 +119,10 @@ struct gb_cnn {
   int precision = GB_PRECISION_FP32;
   int max_batch = 0;  // 0 = per-precision default
   int overlap = 0;    // 1: voxelise chunk i+1 on the aux stream while the network of chunk i runs
+  int cnn_rotation = 0;            // --cnn_rotation: evaluations per model; 0/1 = the unrotated pose only
+  uint32_t rotation_seed = 0;      // --seed
+  PinBuf<float> h_rot;             // [R][n_staged][9]
+  DevBuf<float> d_rot;
   std::vector<float> rec_xyz;
   std::vector<int32_t> rec_type;
   // staged poses
@@ -306,6 +310,8 @@ int gb_cnn_clone(const gb_cnn* src, gb_cnn** out) {
   build_groups(h.get());
   h->precision = src->precision;
   h->max_batch = src->max_batch;
+  h->cnn_rotation = src->cnn_rotation;
+  h->rotation_seed = src->rotation_seed;
   gb_cnn* raw = h.release();
   *out = raw;
   if (!src->rec_type.empty())
@@ -337,6 +343,11 @@ int gb_cnn_set_option(gb_cnn* h, const char* key, double value) {
     h->overlap = value != 0;
   } else if (k == "profile") {
     h->prof.on = value != 0;
+  } else if (k == "cnn_rotation") {
+    GB_CHECK(value >= 0 && value <= 24, "cnn_rotation out of range (0..24, as gnina's option)");
+    h->cnn_rotation = (int)value;
+  } else if (k == "rotation_seed") {
+    h->rotation_seed = (uint32_t)value;
   } else if (k == "max_batch") {
     GB_CHECK(value >= 0 && value <= 65536, "max_batch out of range");
     h->max_batch = (int)value;
@@ -352,6 +363,8 @@ double gb_cnn_get_option(const gb_cnn* h, const char* key) {
   if (k == "precision") return h->precision;
   if (k == "max_batch") return h->max_batch;
   if (k == "overlap") return h->overlap;
+  if (k == "cnn_rotation") return h->cnn_rotation;
+  if (k == "rotation_seed") return h->rotation_seed;
   return NAN;
 }
 
@@ -488,7 +501,7 @@ static int chunk_size(const gb_cnn* h) {
 }
 
 // voxelise poses [p0, p0+nb) of group G into the fp32 reference layout
-static void voxelize_chunk_f32(gb_cnn* h, GridGroup& G, int p0, int nb) {
+static void voxelize_chunk_f32(gb_cnn* h, GridGroup& G, int p0, int nb, const float* rot = nullptr) {
   const int cap = G.n_rec + G.max_pose_atoms;
   G.list_xyzr.ensure((size_t)nb * std::max(cap, 1));
   G.list_ch.ensure((size_t)nb * std::max(cap, 1));
@@ -499,7 +512,7 @@ static void voxelize_chunk_f32(gb_cnn* h, GridGroup& G, int p0, int nb) {
   ProfScope ps(&h->prof, "f32_build_pose_lists", h->stream);
   launch_build_pose_lists(G.rec_xyzr.p, G.rec_ch.p, G.n_rec, G.lig_xyzr.p, G.lig_ch.p, G.lig_off.p + p0,
                           h->d_centers.p + 3 * (size_t)p0, nb, G.sig.dimension / 2.f, std::max(cap, 1), G.list_xyzr.p,
-                          G.list_ch.p, G.list_n.p, h->stream);
+                          G.list_ch.p, G.list_n.p, h->stream, rot);
   }
   ProfScope ps2(&h->prof, "f32_voxelize", h->stream);
   launch_voxelize_f32(G.list_xyzr.p, G.list_ch.p, G.list_n.p, std::max(cap, 1), h->d_centers.p + 3 * (size_t)p0, nb,
@@ -507,12 +520,51 @@ static void voxelize_chunk_f32(gb_cnn* h, GridGroup& G, int p0, int nb) {
   h->launches += 2;
 }
 
+// G3: rotation r >= 1 of staged pose p -- a uniformly random rotation (Shoemake's quaternion construction) from a
+// counter-based generator keyed by (seed, r, p).  The reference draws from libmolgrid's generator (seeded per model,
+// cnn_torch_scorer.cpp:131-132), which cannot be reproduced here: the MECHANISM is pinned (tests rotate the inputs
+// on the host with the matrix returned by gb_cnn_get_rotation), the random stream is not.
+static uint32_t rot_hash(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  uint32_t x = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u ^ (c + 0x165667B1u) * 0xC2B2AE3Du ^ (d + 1u) * 0x27D4EB2Fu;
+  x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12; x *= 0x297A2D39u; x ^= x >> 15;
+  return x;
+}
+static void rotation_matrix(uint32_t seed, int r, int p, float* R) {
+  if (r <= 0) { const float I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}; for (int k = 0; k < 9; k++) R[k] = I[k]; return; }
+  auto u = [&](uint32_t k) { return (rot_hash(seed, (uint32_t)r, (uint32_t)p, k) >> 8) * (1.0 / 16777216.0); };
+  const double u1 = u(0), u2 = u(1), u3 = u(2), pi2 = 6.283185307179586;
+  const double a = std::sqrt(1 - u1), b = std::sqrt(u1);
+  const double qx = a * std::sin(pi2 * u2), qy = a * std::cos(pi2 * u2), qz = b * std::sin(pi2 * u3), qw = b * std::cos(pi2 * u3);
+  const double m[9] = {1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw),     2 * (qx * qz + qy * qw),
+                       2 * (qx * qy + qz * qw),     1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw),
+                       2 * (qx * qz - qy * qw),     2 * (qy * qz + qx * qw),     1 - 2 * (qx * qx + qy * qy)};
+  for (int k = 0; k < 9; k++) R[k] = (float)m[k];
+}
+static int n_rotations(const gb_cnn* h) { return std::max(1, h->cnn_rotation); }
+
+int gb_cnn_get_rotation(const gb_cnn* h, int rotation, int pose, float* matrix9) {
+  GB_API_BEGIN
+  GB_CHECK(h && matrix9 && rotation >= 0 && rotation < n_rotations(h) && pose >= 0, "bad rotation query");
+  rotation_matrix(h->rotation_seed, rotation, pose, matrix9);
+  GB_API_END
+}
+
 int gb_cnn_run_staged(gb_cnn* h) {
   GB_API_BEGIN
   GB_CHECK(h, "null handle");
   GB_CUDA(cudaSetDevice(h->device));
-  const int n = h->n_staged, M = (int)h->models.size();
+  const int n = h->n_staged, M0 = (int)h->models.size();
   if (n == 0) return GB_OK;
+  // every model is evaluated on R rotations of every pose (cnn_torch_scorer.cpp:127-163); the (model, rotation)
+  // evaluations are the ensemble's members: slot mi * R + r
+  const int R = n_rotations(h), M = M0 * R;
+  if (R > 1) {
+    h->h_rot.ensure((size_t)R * n * 9);
+    h->d_rot.ensure((size_t)R * n * 9);
+    for (int r = 0; r < R; r++)
+      for (int p = 0; p < n; p++) rotation_matrix(h->rotation_seed, r, p, h->h_rot.p + ((size_t)r * n + p) * 9);
+    GB_CUDA(cudaMemcpyAsync(h->d_rot.p, h->h_rot.p, (size_t)R * n * 9 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  }
   h->d_pose.ensure((size_t)M * n);
   h->d_aff.ensure((size_t)M * n);
   h->d_loss.ensure((size_t)M * n);
@@ -522,23 +574,26 @@ int gb_cnn_run_staged(gb_cnn* h) {
   // the auxiliary stream starts after everything already queued on the main stream (staging copies, timing events)
   GB_CUDA(cudaEventRecord(h->ev_fork, h->stream));
   GB_CUDA(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
-  for (int p0 = 0; p0 < n; p0 += chunk) {
+  for (int p0 = 0; p0 < n; p0 += chunk)
+  for (int r = 0; r < R; r++) {
     const int nb = std::min(chunk, n - p0);
+    const float* rot = r > 0 ? h->d_rot.p + ((size_t)r * n + p0) * 9 : nullptr;
     for (auto& Gp : h->groups) {
       GridGroup& G = *Gp;
       if (h->precision == GB_PRECISION_FP32) {
-        voxelize_chunk_f32(h, G, p0, nb);
+        voxelize_chunk_f32(h, G, p0, nb, rot);
         for (int mi : G.model_idx) {
           const Model& Mo = *h->models[mi];
+          const size_t slot = (size_t)mi * R + r;
           h->launches += forward_fp32(Mo, G.grid.p, nb, h->ws32, h->d_out3.p, h->stream, &h->prof);
-          launch_head_post(h->d_out3.p, nb, Mo.skip_softmax, Mo.apply_logistic_loss, h->d_pose.p + (size_t)mi * n + p0,
-                           h->d_aff.p + (size_t)mi * n + p0, h->d_loss.p + (size_t)mi * n + p0, h->stream);
+          launch_head_post(h->d_out3.p, nb, Mo.skip_softmax, Mo.apply_logistic_loss, h->d_pose.p + slot * n + p0,
+                           h->d_aff.p + slot * n + p0, h->d_loss.p + slot * n + p0, h->stream);
           h->launches++;
         }
       } else {
         TcPoseBatch pb{G.rec_xyzr.p, G.rec_ch.p, G.n_rec, G.lig_xyzr.p, G.lig_ch.p, G.lig_off.p + p0,
                        h->d_centers.p + 3 * (size_t)p0, nb, G.max_pose_atoms, G.n_channels, G.rec.n_channels,
-                       G.sig.resolution, G.sig.dimension};
+                       G.sig.resolution, G.sig.dimension, rot};
         TcGridWorkspace& gw = G.tc_grid;
         const int buf = (int)(gw.iter++ & 1u);
         // aux stream: wait until the network has finished reading this buffer two chunks ago, then voxelise into it
@@ -557,10 +612,11 @@ int gb_cnn_run_staged(gb_cnn* h) {
         for (size_t k = 0; k < G.model_idx.size(); k++) {
           const int mi = G.model_idx[k];
           const Model& Mo = *h->models[mi];
+          const size_t slot = (size_t)mi * R + r;
           h->launches += tc_forward(Mo, pb, gw.x0[tc_pool_kind(Mo)][buf], h->ws_tc, h->d_out3.p, h->stream, &h->prof,
                                     k + 1 == G.model_idx.size() ? gw.consumed[buf] : nullptr);
-          launch_head_post(h->d_out3.p, nb, Mo.skip_softmax, Mo.apply_logistic_loss, h->d_pose.p + (size_t)mi * n + p0,
-                           h->d_aff.p + (size_t)mi * n + p0, h->d_loss.p + (size_t)mi * n + p0, h->stream);
+          launch_head_post(h->d_out3.p, nb, Mo.skip_softmax, Mo.apply_logistic_loss, h->d_pose.p + slot * n + p0,
+                           h->d_aff.p + slot * n + p0, h->d_loss.p + slot * n + p0, h->stream);
           h->launches++;
         }
         gw.consumed_valid[buf] = true;
@@ -606,7 +662,7 @@ int gb_cnn_score_batch_models(gb_cnn* h, const float* lig_xyz, const int32_t* li
   rc = gb_cnn_run_staged(h);
   if (rc) return rc;
   GB_API_BEGIN
-  const size_t cnt = (size_t)h->models.size() * n_poses;
+  const size_t cnt = (size_t)h->models.size() * n_rotations(h) * n_poses;  // slots model * R + rotation
   if (cnt) {
     if (pose) GB_CUDA(cudaMemcpyAsync(pose, h->d_pose.p, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     if (affinity) GB_CUDA(cudaMemcpyAsync(affinity, h->d_aff.p, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
@@ -668,6 +724,7 @@ int gb_cnn_score_grad(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, 
   if (rc) return rc;
   GB_API_BEGIN
   GB_CHECK(dlig_xyz, "dlig_xyz must not be NULL");
+  if (n_rotations(h) > 1) throw Error(GB_ERR_USAGE, "gradients with cnn_rotation > 1 are not implemented");
   // getReceptorGradient (torch_model.cpp:226-232): the reference scores ONE pose per call and reads the gradient of its
   // (flexible) receptor atoms afterwards; the batch form keeps that contract -- with a shared receptor a per-pose
   // receptor gradient only exists for a single pose

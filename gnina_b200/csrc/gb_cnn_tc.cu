@@ -1062,7 +1062,7 @@ int tc_prepare_grid(const TcPoseBatch& pb, TcGridWorkspace& gw, int buf, int kin
   {
     ProfScope ps(prof, "tc_build_pose_lists", s);
     launch_build_pose_lists(pb.rec_xyzr, pb.rec_ch, pb.n_rec, pb.lig_xyzr, pb.lig_ch, pb.lig_off, pb.centers, nb,
-                            pb.dimension / 2.f, cap, gw.list_xyzr, gw.list_ch, gw.list_n, s);
+                            pb.dimension / 2.f, cap, gw.list_xyzr, gw.list_ch, gw.list_n, s, pb.rot);
   }
   int launches = 1;
   if (kinds_mask & 1) {

@@ -38,10 +38,16 @@ __global__ void __launch_bounds__(256) build_pose_lists_kernel(const float4* __r
                                                                const int* __restrict__ lig_off,
                                                                const float* __restrict__ centers, float half_dim,
                                                                int cap, float4* __restrict__ list_xyzr,
-                                                               int* __restrict__ list_ch, int* __restrict__ list_n) {
+                                                               int* __restrict__ list_ch, int* __restrict__ list_n,
+                                                               const float* __restrict__ rot) {
   __shared__ int s_counts[8];
   const int p = blockIdx.x;
   const float cx = centers[3 * p], cy = centers[3 * p + 1], cz = centers[3 * p + 2];
+  // G3: Transform(center, 0, rotate) (torch_model.cpp:170-173) -- every atom of the pose (receptor and ligand) is
+  // rotated about the grid centre before gridding; rot = row-major 3x3 per pose, NULL = identity
+  float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+  if (rot)
+    for (int k = 0; k < 9; k++) R[k] = rot[9 * p + k];
   float4* out_a = list_xyzr + (size_t)p * cap;
   int* out_c = list_ch + (size_t)p * cap;
   int n_out = 0;
@@ -57,6 +63,12 @@ __global__ void __launch_bounds__(256) build_pose_lists_kernel(const float4* __r
       if (i < e) {
         a = src[i];
         ch = srcc[i];
+        if (rot) {
+          const float dx = a.x - cx, dy = a.y - cy, dz = a.z - cz;
+          a.x = cx + (R[0] * dx + R[1] * dy + R[2] * dz);
+          a.y = cy + (R[3] * dx + R[4] * dy + R[5] * dz);
+          a.z = cz + (R[6] * dx + R[7] * dy + R[8] * dz);
+        }
         const float reach = half_dim + 1.5f * a.w;
         keep = fabsf(a.x - cx) <= reach && fabsf(a.y - cy) <= reach && fabsf(a.z - cz) <= reach;
       }
@@ -74,10 +86,10 @@ __global__ void __launch_bounds__(256) build_pose_lists_kernel(const float4* __r
 
 void launch_build_pose_lists(const float4* rec_xyzr, const int* rec_ch, int n_rec, const float4* lig_xyzr,
                              const int* lig_ch, const int* lig_off, const float* centers, int n_poses, float half_dim,
-                             int cap, float4* list_xyzr, int* list_ch, int* list_n, cudaStream_t s) {
+                             int cap, float4* list_xyzr, int* list_ch, int* list_n, cudaStream_t s, const float* rot) {
   if (n_poses <= 0) return;
   build_pose_lists_kernel<<<n_poses, 256, 0, s>>>(rec_xyzr, rec_ch, n_rec, lig_xyzr, lig_ch, lig_off, centers, half_dim,
-                                                  cap, list_xyzr, list_ch, list_n);
+                                                  cap, list_xyzr, list_ch, list_n, rot);
 }
 
 __device__ __forceinline__ float density_exact(float dx, float dy, float dz, float ar) {

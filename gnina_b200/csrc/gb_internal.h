@@ -136,7 +136,7 @@ struct ProfScope {
 // kernels: gb_grid.cu
 void launch_build_pose_lists(const float4* rec_xyzr, const int* rec_ch, int n_rec, const float4* lig_xyzr,
                              const int* lig_ch, const int* lig_off, const float* centers, int n_poses, float half_dim,
-                             int cap, float4* list_xyzr, int* list_ch, int* list_n, cudaStream_t s);
+                             int cap, float4* list_xyzr, int* list_ch, int* list_n, cudaStream_t s, const float* rot = nullptr);
 void launch_voxelize_f32(const float4* list_xyzr, const int* list_ch, const int* list_n, int cap, const float* centers,
                          int n_poses, int n_channels, int npts, float resolution, float dimension, float* grid,
                          cudaStream_t s);

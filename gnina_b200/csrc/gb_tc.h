@@ -13,6 +13,7 @@ struct TcPoseBatch {
   const float* centers;                                            // idem
   int n_poses, max_pose_atoms, n_channels, n_rec_channels;
   float resolution, dimension;
+  const float* rot = nullptr;  // [n_poses][9] rotation about the grid centre (G3), or null; offset to the chunk like centers
 };
 
 // Pooled input grids, double buffered so that the (CUDA-core) voxeliser of chunk i+1 can run on an auxiliary

@@ -138,13 +138,20 @@ class CNNScorer:
         return tuple(out)
 
     def score_batch_models(self, lig_xyz, lig_types, pose_offsets, centers=None):
-        """-> (pose, affinity, loss), each [n_models, n_poses] (TorchModel::forward outputs)."""
+        """-> (pose, affinity, loss), each [n_models * R, n_poses] (TorchModel::forward outputs; R = max(1, cnn_rotation),
+        row = model * R + rotation)."""
         xyz, t, off, c = self._poses(lig_xyz, lig_types, pose_offsets, centers)
-        n, m = len(off) - 1, len(self.model_names)
+        n, m = len(off) - 1, len(self.model_names) * max(1, int(self.get_option("cnn_rotation")))
         out = [np.empty((m, n), np.float32) for _ in range(3)]
         capi.check(capi.lib().gb_cnn_score_batch_models(self._h, _fp(xyz), _ip(t), _ip(off), n, _fp(c),
                                                         *[_fp(o) for o in out]))
         return tuple(out)
+
+    def rotation(self, r, pose):
+        """row-major 3x3 matrix of rotation index r (0 = identity) for batch pose index `pose` (gb_cnn_get_rotation)"""
+        m = np.zeros(9, np.float32)
+        capi.check(capi.lib().gb_cnn_get_rotation(self._h, int(r), int(pose), _fp(m)))
+        return m.reshape(3, 3)
 
     def score_grad_batch(self, lig_xyz, lig_types, pose_offsets, centers=None, receptor=False):
         """score(m, compute_gradient=True) in batch form -> (score, affinity, loss, variance, dloss/dlig_xyz [n_atoms,3]);

@@ -75,7 +75,12 @@ int gb_cnn_clone(const gb_cnn* h, gb_cnn** out);
 void gb_cnn_destroy(gb_cnn* h);
 int gb_cnn_num_models(const gb_cnn* h);
 
-/* Options: "precision" (GB_PRECISION_*), "max_batch" (poses per device pass), "profile" (0/1). */
+/* Options: "precision" (GB_PRECISION_*), "max_batch" (poses per device pass), "profile" (0/1),
+ * "cnn_rotation" (0..24, gnina's --cnn_rotation: every model is evaluated on the unrotated pose and on
+ * cnn_rotation - 1 random rotations of receptor + ligand about the grid centre, cnn_torch_scorer.cpp:127-163 ->
+ * TorchModel::forward(rotate) lib/torch_model.cpp:170-173; all model x rotation evaluations are ensemble members),
+ * "rotation_seed" (gnina's --seed).  The random stream is this library's (libmolgrid's is not reproducible here):
+ * gb_cnn_get_rotation returns the matrix used, so callers can reproduce any evaluation exactly. */
 int gb_cnn_set_option(gb_cnn* h, const char* key, double value);
 double gb_cnn_get_option(const gb_cnn* h, const char* key);
 
@@ -98,9 +103,14 @@ int gb_cnn_score_batch(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type,
                        float* variance);
 
 /* Same, but un-averaged: outputs are [n_models][n_poses] (TorchModel::forward's {pose, affinity, loss}). */
+/* with cnn_rotation R > 1 the rows are the model x rotation evaluations: row = model * R + rotation */
 int gb_cnn_score_batch_models(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type,
                               const int32_t* pose_offsets, int n_poses, const float* centers, float* pose,
                               float* affinity, float* loss);
+
+/* Row-major 3x3 rotation applied about the grid centre for rotation index `rotation` (0 = identity) of the staged
+ * pose `pose` (index within the batch). */
+int gb_cnn_get_rotation(const gb_cnn* h, int rotation, int pose, float* matrix9);
 
 /* CNNTorchScorer::score(model&, compute_gradient = true, ...) in batch form: the four outputs as above plus the
  * gradient of the (ensemble-mean) loss with respect to every ligand atom passed, dlig_xyz[n_atoms][3]

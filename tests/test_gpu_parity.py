@@ -147,3 +147,58 @@ def test_errors_are_reported_not_fatal():
     from gnina_b200 import CNNScorer, usage_error
     with pytest.raises(usage_error, match="Invalid model name"):
         CNNScorer(["no_such_model"])
+
+
+def test_cnn_rotation_mechanism(kat):
+    """G3 (--cnn_rotation): every (model, rotation) evaluation equals scoring inputs rotated on the host about the grid
+    centre with the matrix the library reports; the ensemble statistics run over all model x rotation evaluations.
+    (The random STREAM is the library's own -- libmolgrid's generator is not reproducible -- the mechanism is pinned.)"""
+    from gnina_b200 import CNNScorer, capi
+    names = ["crossdock_default2018", "crossdock_default2018_KD_4"]
+    offs = kat["pose_offsets"][:3]
+    x, t = kat["lig_xyz"][:offs[-1]], kat["lig_types"][:offs[-1]]
+    rec, rt = kat["rec_xyz"], kat["rec_types"]
+    R = 3
+    s = CNNScorer(names, precision=0)
+    s.set_option("cnn_rotation", R); s.set_option("rotation_seed", 7)
+    s.set_receptor(rec, rt)
+    per = s.score_batch_models(x, t, offs)
+    assert per[0].shape == (len(names) * R, 2)
+    ens = s.score_batch(x, t, offs)
+    assert np.abs(ens[0] - per[0].mean(0)).max() < 1e-6 and np.abs(ens[1] - per[1].mean(0)).max() < 1e-5
+    assert np.abs(ens[3] - per[1].var(0)).max() < 1e-4 and np.abs(ens[2] - per[2].mean(0)).max() < 1e-5
+    plain = CNNScorer(names, precision=0)
+    plain.set_receptor(rec, rt)
+    base = plain.score_batch_models(x, t, offs)
+    for m in range(len(names)):
+        assert np.array_equal(per[0][m * R], base[0][m])                      # rotation 0 = the unrotated evaluation
+    seen = []
+    for r in (1, 2):
+        for p in (0, 1):
+            M = s.rotation(r, p)
+            assert np.abs(M @ M.T - np.eye(3)).max() < 1e-6 and abs(np.linalg.det(M) - 1) < 1e-6
+            assert np.abs(M - np.eye(3)).max() > 1e-2
+            seen.append(M)
+            lp = x[offs[p]:offs[p + 1]].astype(np.float64)
+            c = x[offs[p]:offs[p + 1]].mean(0, dtype=np.float32).astype(np.float64)
+            q = CNNScorer(names, precision=0)
+            q.set_receptor((c + (rec.astype(np.float64) - c) @ M.T.astype(np.float64)).astype(np.float32), rt)
+            out = q.score_batch_models((c + (lp - c) @ M.T.astype(np.float64)).astype(np.float32), t[offs[p]:offs[p + 1]],
+                                       [0, offs[p + 1] - offs[p]], [c.astype(np.float32)])
+            for m in range(len(names)):
+                assert abs(out[0][m, 0] - per[0][m * R + r, p]) < 5e-5, (r, p, m)
+                assert abs(out[1][m, 0] - per[1][m * R + r, p]) < 2e-4, (r, p, m)
+    assert np.abs(seen[0] - seen[1]).max() > 1e-2 and np.abs(seen[0] - seen[2]).max() > 1e-2   # per pose, per rotation
+    assert np.array_equal(s.rotation(0, 1), np.eye(3, dtype=np.float32))
+    # fast mode runs the same rotations
+    f = CNNScorer(names, precision=1)
+    f.set_option("cnn_rotation", R); f.set_option("rotation_seed", 7)
+    f.set_receptor(rec, rt)
+    pf = f.score_batch_models(x, t, offs)
+    assert np.abs(pf[0] - per[0]).max() < 2e-3 and np.abs(pf[1] - per[1]).max() < 1e-2
+    c2 = f.fresh_copy()
+    assert np.array_equal(c2.score_batch(x, t, offs)[0], f.score_batch(x, t, offs)[0])          # clones keep the option
+    with pytest.raises(capi.GbError, match="cnn_rotation"):
+        f.score_grad_batch(x, t, offs)
+    with pytest.raises(capi.GbError, match="out of range"):
+        f.set_option("cnn_rotation", 25)
