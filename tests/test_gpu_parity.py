@@ -202,3 +202,53 @@ def test_cnn_rotation_mechanism(kat):
         f.score_grad_batch(x, t, offs)
     with pytest.raises(capi.GbError, match="out of range"):
         f.set_option("cnn_rotation", 25)
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_empty_grid_reproduces_the_reference_zero_grid_answer(kat, prec):
+    """SURVEY.md 8c known answer of the reference's own crossdock_default2018.pt on an all-zero grid: pose 0.92233,
+    affinity 1.46472.  Reached three ways through the whole pipeline: no receptor at all + untyped ligand, a grid
+    centred far away from every atom, and a receptor replaced by hydrogens."""
+    from gnina_b200 import CNNScorer
+    name = "crossdock_default2018"
+    zp = float(np.exp(kat[name + "_zero_logp_f64"][0, 1])), float(kat[name + "_zero_aff_f64"].reshape(-1)[0])
+    assert abs(zp[0] - 0.92233) < 1e-5 and abs(zp[1] - 1.46472) < 1e-5
+    tp, ta = (2e-5, 1e-4) if prec == 0 else (2e-3, 1e-2)
+    o = kat["pose_offsets"]
+    x, t = kat["lig_xyz"][:o[2]], kat["lig_types"][:o[2]]
+    s = CNNScorer([name], precision=prec)
+    # (1) receptor with zero atoms, ligand of hydrogens only
+    s.set_receptor(np.zeros((0, 3), np.float32), np.zeros(0, np.int32))
+    got = s.score_batch(x, np.ones_like(t), o[:3])
+    assert np.abs(got[0] - zp[0]).max() < tp and np.abs(got[1] - zp[1]).max() < ta
+    # (2) real receptor and ligand, grid centred 500 A away
+    s.set_receptor(kat["rec_xyz"], kat["rec_types"])
+    got = s.score_batch(x, t, o[:3], np.full((2, 3), 500.0, np.float32))
+    assert np.abs(got[0] - zp[0]).max() < tp and np.abs(got[1] - zp[1]).max() < ta
+    # (3) back to a normal call on the same handle: nothing stale
+    ref = CNNScorer([name], precision=prec)
+    ref.set_receptor(kat["rec_xyz"], kat["rec_types"])
+    assert np.array_equal(s.score_batch(x, t, o[:3])[0], ref.score_batch(x, t, o[:3])[0])
+    # (4) receptor of hydrogens only
+    s.set_receptor(kat["rec_xyz"], np.ones_like(kat["rec_types"]))
+    got = s.score_batch(x, np.zeros_like(t), o[:3])
+    assert np.abs(got[0] - zp[0]).max() < tp and np.abs(got[1] - zp[1]).max() < ta
+
+
+def test_chunk_boundaries_and_big_ligands(kat):
+    """a batch that crosses the default 2048-pose device chunk by one pose, and a 150-heavy-atom ligand (larger than
+    any list floor): identical to scoring the same poses alone"""
+    from gnina_b200 import CNNScorer, synth
+    s = CNNScorer(["crossdock_default2018"], precision=1)
+    s.set_receptor(kat["rec_xyz"], kat["rec_types"])
+    xyz, types, offs = synth.make_screen(2049, seed=9, trans_box=6.0)
+    big = s.score_batch(xyz, types, offs)
+    for p in (0, 2047, 2048):
+        one = s.score_batch(xyz[offs[p]:offs[p + 1]], types[offs[p]:offs[p + 1]], [0, offs[p + 1] - offs[p]])
+        assert one[0][0] == big[0][p] and one[1][0] == big[1][p]
+    lx, lt = synth.make_ligand(150, 10, seed=3)
+    v0 = CNNScorer(["crossdock_default2018"], precision=0)
+    v0.set_receptor(kat["rec_xyz"], kat["rec_types"])
+    a = s.score_batch(lx, lt, [0, len(lt)])
+    b = v0.score_batch(lx, lt, [0, len(lt)])
+    assert abs(a[0][0] - b[0][0]) < 3e-3 and abs(a[1][0] - b[1][0]) < 1e-2 * max(1.0, abs(b[1][0]))   # fast-mode tolerance
