@@ -542,6 +542,17 @@ static void rotation_matrix(uint32_t seed, int r, int p, float* R) {
 }
 static int n_rotations(const gb_cnn* h) { return std::max(1, h->cnn_rotation); }
 
+// matrices of every (rotation, staged pose) -> h->d_rot [R][n][9]
+static void upload_rotations(gb_cnn* h) {
+  const int R = n_rotations(h), n = h->n_staged;
+  if (R <= 1 || n == 0) return;
+  h->h_rot.ensure((size_t)R * n * 9);
+  h->d_rot.ensure((size_t)R * n * 9);
+  for (int r = 0; r < R; r++)
+    for (int p = 0; p < n; p++) rotation_matrix(h->rotation_seed, r, p, h->h_rot.p + ((size_t)r * n + p) * 9);
+  GB_CUDA(cudaMemcpyAsync(h->d_rot.p, h->h_rot.p, (size_t)R * n * 9 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+}
+
 int gb_cnn_get_rotation(const gb_cnn* h, int rotation, int pose, float* matrix9) {
   GB_API_BEGIN
   GB_CHECK(h && matrix9 && rotation >= 0 && rotation < n_rotations(h) && pose >= 0, "bad rotation query");
@@ -558,13 +569,7 @@ int gb_cnn_run_staged(gb_cnn* h) {
   // every model is evaluated on R rotations of every pose (cnn_torch_scorer.cpp:127-163); the (model, rotation)
   // evaluations are the ensemble's members: slot mi * R + r
   const int R = n_rotations(h), M = M0 * R;
-  if (R > 1) {
-    h->h_rot.ensure((size_t)R * n * 9);
-    h->d_rot.ensure((size_t)R * n * 9);
-    for (int r = 0; r < R; r++)
-      for (int p = 0; p < n; p++) rotation_matrix(h->rotation_seed, r, p, h->h_rot.p + ((size_t)r * n + p) * 9);
-    GB_CUDA(cudaMemcpyAsync(h->d_rot.p, h->h_rot.p, (size_t)R * n * 9 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  }
+  upload_rotations(h);
   h->d_pose.ensure((size_t)M * n);
   h->d_aff.ensure((size_t)M * n);
   h->d_loss.ensure((size_t)M * n);
@@ -724,7 +729,6 @@ int gb_cnn_score_grad(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, 
   if (rc) return rc;
   GB_API_BEGIN
   GB_CHECK(dlig_xyz, "dlig_xyz must not be NULL");
-  if (n_rotations(h) > 1) throw Error(GB_ERR_USAGE, "gradients with cnn_rotation > 1 are not implemented");
   // getReceptorGradient (torch_model.cpp:226-232): the reference scores ONE pose per call and reads the gradient of its
   // (flexible) receptor atoms afterwards; the batch form keeps that contract -- with a shared receptor a per-pose
   // receptor gradient only exists for a single pose
@@ -734,10 +738,13 @@ int gb_cnn_score_grad(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, 
   if (drec_xyz)
     for (int i = 0; i < 3 * n_rec_in; i++) drec_xyz[i] = 0.f;
   GB_CUDA(cudaSetDevice(h->device));
-  const int n = h->n_staged, M = (int)h->models.size();
+  // M = ensemble members = models x rotations (cnn_torch_scorer.cpp:127-179: outputs and gradients are accumulated
+  // over both loops and divided by cnt); a rotated evaluation's gradient is rotated back by the atom-gradient kernels
+  const int n = h->n_staged, R = n_rotations(h), M = (int)h->models.size() * R;
   const int n_in = h->n_input_atoms;
   for (int i = 0; i < 3 * n_in; i++) dlig_xyz[i] = 0.f;
   if (n == 0) return GB_OK;
+  upload_rotations(h);
   bool all_default2018 = true;
   for (Model* m : h->models) {
     if (m->arch != GB_ARCH_DEFAULT2018 && m->arch != GB_ARCH_DENSE)
@@ -765,21 +772,23 @@ int gb_cnn_score_grad(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, 
       G.rec_grad.ensure(3 * (size_t)std::max(G.n_rec, 1));
       GB_CUDA(cudaMemsetAsync(G.rec_grad.p, 0, 3 * (size_t)std::max(G.n_rec, 1) * sizeof(float), h->stream));
     }
-  for (int p0 = 0; p0 < n; p0 += chunk) {
+  for (int p0 = 0; p0 < n; p0 += chunk)
+  for (int r = 0; r < R; r++) {
     const int nb = std::min(chunk, n - p0);
+    const float* rot = r > 0 ? h->d_rot.p + ((size_t)r * n + p0) * 9 : nullptr;
     for (auto& Gp : h->groups) {
       GridGroup& G = *Gp;
       tmp_grad.ensure(3 * (size_t)std::max(G.n_staged_atoms, 1));
       const int npts = (int)std::lround(G.sig.dimension / G.sig.resolution) + 1;
       TcPoseBatch pb{G.rec_xyzr.p, G.rec_ch.p, G.n_rec, G.lig_xyzr.p, G.lig_ch.p, G.lig_off.p + p0,
                      h->d_centers.p + 3 * (size_t)p0, nb, G.max_pose_atoms, G.n_channels, G.rec.n_channels,
-                     G.sig.resolution, G.sig.dimension};
+                     G.sig.resolution, G.sig.dimension, rot};
       if (fast) {
         TcGridWorkspace& gw = G.tc_grid;
         h->launches += tc_prepare_grid(pb, gw, 0, 1 << 0, h->stream, &h->prof);
         gw.consumed_valid[0] = gw.consumed_valid[1] = false;  // everything here is ordered on the main stream
       } else {
-        voxelize_chunk_f32(h, G, p0, nb);
+        voxelize_chunk_f32(h, G, p0, nb, rot);
         h->d_dgrid.ensure((size_t)nb * G.n_channels * npts * npts * npts);
       }
       for (int mi : G.model_idx) {
@@ -791,8 +800,9 @@ int gb_cnn_score_grad(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, 
         } else {
           h->launches += forward_backward_fp32(Mo, G.grid.p, nb, h->ws_grad, h->d_out3.p, h->d_dgrid.p, h->stream, &h->prof);
         }
-        launch_head_post(h->d_out3.p, nb, Mo.skip_softmax, Mo.apply_logistic_loss, h->d_pose.p + (size_t)mi * n + p0,
-                         h->d_aff.p + (size_t)mi * n + p0, h->d_loss.p + (size_t)mi * n + p0, h->stream);
+        const size_t slot = (size_t)mi * R + r;
+        launch_head_post(h->d_out3.p, nb, Mo.skip_softmax, Mo.apply_logistic_loss, h->d_pose.p + slot * n + p0,
+                         h->d_aff.p + slot * n + p0, h->d_loss.p + slot * n + p0, h->stream);
         // ligand atoms of this chunk: accumulate (scaled 1/M) into the group's gradient array
         const bool want_rec = drec_xyz && G.n_rec > 0;
         if (want_rec) tmp_rec.ensure(3 * (size_t)G.n_rec);
@@ -801,11 +811,11 @@ int gb_cnn_score_grad(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, 
                                      want_rec ? G.rec_off.p : nullptr, want_rec ? tmp_rec.p : nullptr);
         } else {
           launch_grid_backward(G.lig_xyzr.p, G.lig_ch.p, G.lig_off.p + p0, G.max_pose_atoms, h->d_centers.p + 3 * (size_t)p0, nb,
-                               G.n_channels, npts, G.sig.resolution, G.sig.dimension, h->d_dgrid.p, tmp_grad.p, h->stream);
+                               G.n_channels, npts, G.sig.resolution, G.sig.dimension, h->d_dgrid.p, tmp_grad.p, h->stream, rot);
           h->launches++;
           if (want_rec) {  // the receptor as the single pose's second atom set
             launch_grid_backward(G.rec_xyzr.p, G.rec_ch.p, G.rec_off.p, G.n_rec, h->d_centers.p, 1, G.n_channels, npts,
-                                 G.sig.resolution, G.sig.dimension, h->d_dgrid.p, tmp_rec.p, h->stream);
+                                 G.sig.resolution, G.sig.dimension, h->d_dgrid.p, tmp_rec.p, h->stream, rot);
             h->launches++;
           }
         }

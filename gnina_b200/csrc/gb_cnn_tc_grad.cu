@@ -283,13 +283,22 @@ __global__ void __launch_bounds__(256) grid_backward_pooled_kernel(const float4*
                                                                    const float* __restrict__ centers, int n_channels,
                                                                    float resolution, float dimension,
                                                                    const __half* __restrict__ gx0, float scale,
-                                                                   float* __restrict__ atom_grad) {
+                                                                   float* __restrict__ atom_grad, const float* __restrict__ rot) {
   constexpr int npts = 48, Dp = 24;
   const int p = blockIdx.y;
   const int a_i = pose_off[p] + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (a_i >= pose_off[p + 1]) return;
-  const float4 a = atoms_xyzr[a_i];
+  float4 a = atoms_xyzr[a_i];
+  float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};  // G3, as grid_backward_kernel (gb_grid.cu)
+  if (rot) {
+    for (int k = 0; k < 9; k++) R[k] = rot[9 * p + k];
+    const float cx = centers[3 * p], cy = centers[3 * p + 1], cz = centers[3 * p + 2];
+    const float dx = a.x - cx, dy = a.y - cy, dz = a.z - cz;
+    a.x = cx + (R[0] * dx + R[1] * dy + R[2] * dz);
+    a.y = cy + (R[3] * dx + R[4] * dy + R[5] * dz);
+    a.z = cz + (R[6] * dx + R[7] * dy + R[8] * dz);
+  }
   const int ch = atoms_ch[a_i];
   const float half = dimension / 2.f;
   const float ox = centers[3 * p] - half, oy = centers[3 * p + 1] - half, oz = centers[3 * p + 2] - half;
@@ -330,7 +339,10 @@ __global__ void __launch_bounds__(256) grid_backward_pooled_kernel(const float4*
   }
   if (lane == 0) {
     float* og = atom_grad + (size_t)a_i * 3;
-    og[0] = gx * scale; og[1] = gy * scale; og[2] = gz * scale;
+    gx *= scale; gy *= scale; gz *= scale;
+    og[0] = R[0] * gx + R[3] * gy + R[6] * gz;
+    og[1] = R[1] * gx + R[4] * gy + R[7] * gz;
+    og[2] = R[2] * gx + R[5] * gy + R[8] * gz;
   }
 }
 
@@ -396,7 +408,7 @@ int tc_backward(const Model& m, const TcPoseBatch& pb, TcWorkspace& ws, const fl
     if (pb.max_pose_atoms > 0) {
       dim3 g((pb.max_pose_atoms + 7) / 8, nb);
       grid_backward_pooled_kernel<<<g, 256, 0, s>>>(pb.lig_xyzr, pb.lig_ch, pb.lig_off, pb.centers, pb.n_channels, pb.resolution,
-                                                    pb.dimension, GX0, 1.f / (512.f * kLossScale), atom_grad);
+                                                    pb.dimension, GX0, 1.f / (512.f * kLossScale), atom_grad, pb.rot);
     }
   }
   if (rec_grad && pb.n_rec > 0) {  // getReceptorGradient: the receptor atoms of the (single) pose
@@ -404,7 +416,7 @@ int tc_backward(const Model& m, const TcPoseBatch& pb, TcWorkspace& ws, const fl
     ProfScope ps(prof, "tcg_grid_backward_receptor", s);
     dim3 g((pb.n_rec + 7) / 8, 1);
     grid_backward_pooled_kernel<<<g, 256, 0, s>>>(pb.rec_xyzr, pb.rec_ch, rec_off, pb.centers, pb.n_channels, pb.resolution,
-                                                  pb.dimension, GX0, 1.f / (512.f * kLossScale), rec_grad);
+                                                  pb.dimension, GX0, 1.f / (512.f * kLossScale), rec_grad, pb.rot);
   }
   tc_debug_set(5, GX0, (size_t)nb * 24 * 24 * 24 * 32 * sizeof(__half));
   tc_debug_set(6, GY1, act_bytes(L1, nb));

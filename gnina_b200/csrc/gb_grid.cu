@@ -196,12 +196,24 @@ __global__ void __launch_bounds__(256) grid_backward_kernel(const float4* __rest
                                                             const int* __restrict__ pose_off,
                                                             const float* __restrict__ centers, int n_channels, int npts,
                                                             float resolution, float dimension,
-                                                            const float* __restrict__ dgrid, float* __restrict__ atom_grad) {
+                                                            const float* __restrict__ dgrid, float* __restrict__ atom_grad,
+                                                            const float* __restrict__ rot) {
   const int p = blockIdx.y;
   const int a_i = pose_off[p] + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (a_i >= pose_off[p + 1]) return;
-  const float4 a = atoms_xyzr[a_i];
+  float4 a = atoms_xyzr[a_i];
+  // G3: the grid was built from atoms rotated about the centre (x' = c + R (x - c)); the gradient is taken at x' and
+  // rotated back, d/dx = R^T d/dx' (Transform::backward, torch_model.cpp:204-206)
+  float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+  if (rot) {
+    for (int k = 0; k < 9; k++) R[k] = rot[9 * p + k];
+    const float cx = centers[3 * p], cy = centers[3 * p + 1], cz = centers[3 * p + 2];
+    const float dx = a.x - cx, dy = a.y - cy, dz = a.z - cz;
+    a.x = cx + (R[0] * dx + R[1] * dy + R[2] * dz);
+    a.y = cy + (R[3] * dx + R[4] * dy + R[5] * dz);
+    a.z = cz + (R[6] * dx + R[7] * dy + R[8] * dz);
+  }
   const int ch = atoms_ch[a_i];
   const float half = dimension / 2.f;
   const float ox = centers[3 * p] - half, oy = centers[3 * p + 1] - half, oz = centers[3 * p + 2] - half;
@@ -239,17 +251,19 @@ __global__ void __launch_bounds__(256) grid_backward_kernel(const float4* __rest
   }
   if (lane == 0) {
     float* og = atom_grad + (size_t)a_i * 3;
-    og[0] = gx; og[1] = gy; og[2] = gz;
+    og[0] = R[0] * gx + R[3] * gy + R[6] * gz;   // R^T g (identity without rotation)
+    og[1] = R[1] * gx + R[4] * gy + R[7] * gz;
+    og[2] = R[2] * gx + R[5] * gy + R[8] * gz;
   }
 }
 
 void launch_grid_backward(const float4* atoms_xyzr, const int* atoms_ch, const int* pose_off, int max_pose_atoms,
                           const float* centers, int n_poses, int n_channels, int npts, float resolution, float dimension,
-                          const float* dgrid, float* atom_grad, cudaStream_t s) {
+                          const float* dgrid, float* atom_grad, cudaStream_t s, const float* rot) {
   if (n_poses <= 0 || max_pose_atoms <= 0) return;
   dim3 g((max_pose_atoms + 7) / 8, n_poses);
   grid_backward_kernel<<<g, 256, 0, s>>>(atoms_xyzr, atoms_ch, pose_off, centers, n_channels, npts, resolution, dimension,
-                                         dgrid, atom_grad);
+                                         dgrid, atom_grad, rot);
 }
 
 __global__ void axpy_range_kernel(const float* __restrict__ src, float* __restrict__ dst, int lo, int hi, float alpha) {

@@ -168,7 +168,7 @@ int forward_backward_fp32(const Model& m, const float* grid, int B, Fp32GradWork
 // chunk; out: atom_grad[atom][3] indexed like the atom arrays.
 void launch_grid_backward(const float4* atoms_xyzr, const int* atoms_ch, const int* pose_off, int max_pose_atoms,
                           const float* centers, int n_poses, int n_channels, int npts, float resolution, float dimension,
-                          const float* dgrid, float* atom_grad, cudaStream_t s);
+                          const float* dgrid, float* atom_grad, cudaStream_t s, const float* rot = nullptr);
 // dst[i] += alpha * src[i] for i in [lo, hi)
 void launch_axpy_range(const float* src, float* dst, int lo, int hi, float alpha, cudaStream_t s);
 // [B][3] raw -> pose/aff/loss per torch_model.cpp:188-195

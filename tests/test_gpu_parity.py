@@ -198,10 +198,29 @@ def test_cnn_rotation_mechanism(kat):
     assert np.abs(pf[0] - per[0]).max() < 2e-3 and np.abs(pf[1] - per[1]).max() < 1e-2
     c2 = f.fresh_copy()
     assert np.array_equal(c2.score_batch(x, t, offs)[0], f.score_batch(x, t, offs)[0])          # clones keep the option
-    with pytest.raises(capi.GbError, match="cnn_rotation"):
-        f.score_grad_batch(x, t, offs)
     with pytest.raises(capi.GbError, match="out of range"):
         f.set_option("cnn_rotation", 25)
+    # gradients: the rotated evaluation's gradient is taken in the rotated frame and rotated back (Transform::backward,
+    # torch_model.cpp:204-206); the result is the mean over model x rotation evaluations (cnn_torch_scorer.cpp:164-179)
+    one = [names[0]]
+    g2 = CNNScorer(one, precision=0)
+    g2.set_option("cnn_rotation", 2); g2.set_option("rotation_seed", 11)
+    g2.set_receptor(rec, rt)
+    xp, tp = x[:offs[1]], t[:offs[1]]
+    c = xp.mean(0, dtype=np.float32).astype(np.float64)
+    M = g2.rotation(1, 0).astype(np.float64)
+    got = g2.score_grad_batch(xp, tp, [0, len(tp)], [c.astype(np.float32)], receptor=True)
+    g0 = CNNScorer(one, precision=0)
+    g0.set_receptor(rec, rt)
+    a0 = g0.score_grad_batch(xp, tp, [0, len(tp)], [c.astype(np.float32)], receptor=True)
+    g1 = CNNScorer(one, precision=0)
+    g1.set_receptor((c + (rec.astype(np.float64) - c) @ M.T).astype(np.float32), rt)
+    a1 = g1.score_grad_batch((c + (xp.astype(np.float64) - c) @ M.T).astype(np.float32), tp, [0, len(tp)], [c.astype(np.float32)],
+                             receptor=True)
+    for k in (4, 5):                                   # ligand and receptor gradients
+        want = 0.5 * (a0[k] + a1[k].astype(np.float64) @ M)          # row vectors: R^T g' = g' R
+        assert np.abs(got[k] - want).max() < 2e-4 * max(1e-3, np.abs(want).max()), k
+    assert abs(got[2][0] - 0.5 * (a0[2][0] + a1[2][0])) < 1e-5
 
 
 @pytest.mark.parametrize("prec", [0, 1])
