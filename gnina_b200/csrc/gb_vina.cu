@@ -807,25 +807,17 @@ __device__ float dk_eval_deriv(const LigPtrs& L, const DockField& F, WarpWs& W, 
     for (int k = 0; k < 6; k++) W.ft[6 * lane + k] = f[k];
   }
   __syncwarp();
-  // branches_derivative (tree.h:300-310), deepest level first.  Parent-centric: the lane of a segment at depth d
-  // gathers its children (segments are in DFS pre-order, so children have larger indices and were finished one level
-  // earlier) -- plain adds in child order instead of shared-memory float atomics from the children's lanes.
-  for (int d = L.max_depth - 1; d >= 0; d--) {
+  for (int d = L.max_depth; d >= 1; d--) {
     if (lane < L.n_seg) {
       const int4 sg = L.seg[lane];
       if (sg.w == d) {
-        float acc[6];
-        for (int k = 0; k < 6; k++) acc[k] = W.ft[6 * lane + k];
-        for (int ch = lane + 1; ch < L.n_seg; ch++) {
-          if (L.seg[ch].x != lane) continue;
-          const float* c = W.ft + 6 * ch;
-          const float rx = W.so[3 * ch] - W.so[3 * lane], ry = W.so[3 * ch + 1] - W.so[3 * lane + 1], rz = W.so[3 * ch + 2] - W.so[3 * lane + 2];
-          acc[0] += c[0]; acc[1] += c[1]; acc[2] += c[2];
-          acc[3] += ry * c[2] - rz * c[1] + c[3];
-          acc[4] += rz * c[0] - rx * c[2] + c[4];
-          acc[5] += rx * c[1] - ry * c[0] + c[5];
-        }
-        for (int k = 0; k < 6; k++) W.ft[6 * lane + k] = acc[k];
+        const int pp = sg.x;
+        const float* c = W.ft + 6 * lane;
+        const float rx = W.so[3 * lane] - W.so[3 * pp], ry = W.so[3 * lane + 1] - W.so[3 * pp + 1], rz = W.so[3 * lane + 2] - W.so[3 * pp + 2];
+        atomicAdd(&W.ft[6 * pp + 0], c[0]); atomicAdd(&W.ft[6 * pp + 1], c[1]); atomicAdd(&W.ft[6 * pp + 2], c[2]);
+        atomicAdd(&W.ft[6 * pp + 3], ry * c[2] - rz * c[1] + c[3]);
+        atomicAdd(&W.ft[6 * pp + 4], rz * c[0] - rx * c[2] + c[4]);
+        atomicAdd(&W.ft[6 * pp + 5], rx * c[1] - ry * c[0] + c[5]);
       }
     }
     __syncwarp();
