@@ -228,7 +228,7 @@ __device__ __forceinline__ float density_t(float t) {
   return tc <= 1.0f ? g : u * u;
 }
 
-constexpr int kVoxChunk = 256;
+constexpr int kVoxChunk = 512;  // one ordered compaction per 512 list atoms: every thread of the CTA stages one
 
 template <bool kMax>
 __global__ void __launch_bounds__(512) voxelize_pool_f16_kernel(const float4* __restrict__ list_xyzr,
