@@ -14,7 +14,8 @@ class _Lig(C.Structure):
 
 
 class _Field(C.Structure):
-    _fields_ = [("grids", C.POINTER(_fp)), ("begin", _fp), ("end", _fp), ("n", _ip), ("slope", C.c_float), ("prec", _vp), ("splines", _vp)]
+    _fields_ = [("grids", C.POINTER(_fp)), ("begin", _fp), ("end", _fp), ("n", _ip), ("slope", C.c_float), ("prec", _vp), ("splines", _vp),
+                ("rec_xyz", _fp), ("rec_type", _ip), ("n_rec", C.c_int)]
 
 
 class _McParams(C.Structure):
@@ -48,11 +49,42 @@ class DockOracle:
         self.ptrs = (_fp * 28)()
         for t, g in grids.items():
             self.ptrs[t] = _f(k(g, np.float32))
-        self.field = _Field(self.ptrs, _f(k(begin, np.float32)), _f(k(end, np.float32)), _i(k(n, np.int32)), slope, vina_oracle.p, None)
+        self.field = _Field(self.ptrs, _f(k(begin, np.float32)), _f(k(end, np.float32)), _i(k(n, np.int32)), slope, vina_oracle.p, None,
+                            None, None, 0)
+        L.gvo_noncache_atom.argtypes = [C.POINTER(_Field), C.c_int, _fp, C.c_float, _fp]; L.gvo_noncache_atom.restype = C.c_float
+        L.gvo_within.argtypes = [C.POINTER(_Field), C.POINTER(_Lig), _fp, C.c_float]
+        L.gvo_refine_structure.argtypes = [C.POINTER(_Field), C.POINTER(_Lig), _fp, _fp, C.c_int, _fp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.gvo_refine_structure.restype = C.c_float
         self.vo = vina_oracle
         self.T = len(lig["seg_parent"]) - 1
         self.na = len(lig["types"])
         self.gr = lig["gyration_radius"]
+
+    def use_noncache(self, rec_xyz=None, rec_types=None):
+        """non_cache (lib/non_cache.cpp): sum the intermolecular term over the receptor atoms directly instead of the
+        cache grids; begin/end become the search box of check_bounds.  None switches back to the cache."""
+        if rec_xyz is None:
+            self.field.rec_xyz, self.field.rec_type, self.field.n_rec = None, None, 0
+            return
+        x = np.ascontiguousarray(rec_xyz, np.float32); t = np.ascontiguousarray(rec_types, np.int32)
+        self.keep += [x, t]
+        self.field.rec_xyz, self.field.rec_type, self.field.n_rec = _f(x), _i(t), len(t)
+
+    def noncache_atom(self, t, xyz, v=1000.0):
+        """non_cache::eval_deriv for one atom of smina type t -> (energy incl. out-of-box penalty, minus-force)"""
+        a = np.ascontiguousarray(xyz, np.float32); d = np.zeros(3, np.float32)
+        return self.L.gvo_noncache_atom(C.byref(self.field), int(t), _f(a), v, _f(d)), d
+
+    def within(self, conf, margin=1e-4):
+        conf = np.ascontiguousarray(conf, np.float32)
+        return bool(self.L.gvo_within(C.byref(self.field), C.byref(self.lig), _f(conf), margin))
+
+    def refine_structure(self, conf, maxiters, v=(1000, 1000, 1000)):
+        """main/main.cpp:131-171 -> (energy, refined conf, n_evals, within)"""
+        x = np.array(conf, np.float32); v = np.ascontiguousarray(v, np.float32)
+        g = np.empty(6 + self.T, np.float32); ne, ok = C.c_int(), C.c_int()
+        e = self.L.gvo_refine_structure(C.byref(self.field), C.byref(self.lig), _f(x), _f(g), maxiters, _f(v), C.byref(ne), C.byref(ok))
+        return e, x, ne.value, bool(ok.value)
 
     def use_splines(self, on=True):
         """precalculate_splines (factor 10) for the intramolecular pair terms instead of precalculate_linear"""

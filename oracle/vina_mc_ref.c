@@ -44,6 +44,12 @@ typedef struct {
   float slope;
   const gvo_prec *prec;
   const gvo_splines *splines; /* NULL: precalculate_linear ; else precalculate_splines for the pair terms */
+  /* non_cache (lib/non_cache.cpp): when rec_xyz != NULL the intermolecular term is summed over the receptor atoms
+   * directly (begin/end are then the search box gd of check_bounds_deriv) instead of read from the cache grids --
+   * what refine_structure (main/main.cpp:131-171) minimises after the search */
+  const float *rec_xyz;
+  const int32_t *rec_type;
+  int n_rec;
 } gvo_field;
 
 #define PI_F 3.14159265358979323846f
@@ -154,6 +160,53 @@ static void node_derivative(const gvo_lig *L, int s, const float *coords, const 
 }
 
 /* model::eval_deriv with ig = cache: returns e, fills change[6+T] (and coords if non-NULL) */
+/* non_cache::eval_deriv for one movable atom (lib/non_cache.cpp:126-174): clamp to the box (check_bounds_deriv
+ * :102-123, penalty slope * L1 distance), sum e and dor * r over receptor atoms with r^2 < cutoff^2 (the szv_grid only
+ * pre-selects candidates), curl(e, deriv, v), add the out-of-box derivative.  deriv may be NULL (non_cache::eval). */
+float gvo_noncache_atom(const gvo_field *F, int t1, const float *a, float v, float *deriv) {
+  float adj[3], oob[3] = {0, 0, 0}, pen = 0;
+  for (int j = 0; j < 3; j++) {
+    adj[j] = a[j];
+    if (a[j] < F->begin[j]) { adj[j] = F->begin[j]; oob[j] = -1; pen += fabsf(a[j] - F->begin[j]); }
+    else if (a[j] > F->end[j]) { adj[j] = F->end[j]; oob[j] = 1; pen += fabsf(a[j] - F->end[j]); }
+  }
+  pen *= F->slope;
+  float e = 0, d[3] = {0, 0, 0};
+  for (int b = 0; b < F->n_rec; b++) {
+    const int t2 = F->rec_type[b];
+    if (t2 < 0 || t2 >= 28 || is_h(t2)) continue; /* grid_atoms: heavy receptor atoms */
+    const float r[3] = {adj[0] - F->rec_xyz[3 * b], adj[1] - F->rec_xyz[3 * b + 1], adj[2] - F->rec_xyz[3 * b + 2]};
+    const float r2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    if (r2 < 64.f) {
+      float pe, dor;
+      gvo_prec_eval_deriv(F->prec, t1, t2, r2, &pe, &dor);
+      e += pe;
+      for (int q = 0; q < 3; q++) d[q] += dor * r[q];
+    }
+  }
+  if (e > 0 && v < 0.1f * kMax) { /* curl, lib/curl.h:30-42 */
+    const float tmp = (v < kEps) ? 0 : (v / (v + e));
+    e *= tmp;
+    for (int q = 0; q < 3; q++) d[q] *= tmp * tmp;
+  }
+  if (deriv) for (int q = 0; q < 3; q++) deriv[q] = d[q] + F->slope * oob[q];
+  return e + pen;
+}
+
+/* non_cache::within (lib/non_cache.cpp:84-100): every heavy movable atom inside the box (margin 0.0001 as refine uses) */
+int gvo_within(const gvo_field *F, const gvo_lig *L, const float *conf, float margin) {
+  float *coords = (float *)malloc(12 * L->n_atoms), *so = (float *)malloc(12 * L->n_seg), *sa = (float *)malloc(12 * L->n_seg);
+  gvo_lig_set_conf(L, conf, coords, so, sa);
+  int ok = 1;
+  for (int i = 0; i < L->n_atoms && ok; i++) {
+    if (is_h(L->type[i])) continue;
+    for (int j = 0; j < 3; j++)
+      if (coords[3 * i + j] < F->begin[j] - margin || coords[3 * i + j] > F->end[j] + margin) ok = 0;
+  }
+  free(coords); free(so); free(sa);
+  return ok;
+}
+
 float gvo_lig_eval_deriv(const gvo_field *F, const gvo_lig *L, const float *conf, const float *v, float *change, float *coords_out) {
   const int n = L->n_atoms;
   float *coords = (float *)malloc(12 * n), *forces = (float *)calloc(3 * n, 4), *so = (float *)malloc(12 * L->n_seg),
@@ -163,7 +216,8 @@ float gvo_lig_eval_deriv(const gvo_field *F, const gvo_lig *L, const float *conf
   for (int i = 0; i < n; i++) { /* cache::eval_deriv */
     const int t = L->type[i];
     if (t < 0 || t >= 28 || is_h(t)) continue;
-    e += gvo_grid_evaluate(F->grids[t], F->begin, F->end, F->n, coords + 3 * i, F->slope, v[1], forces + 3 * i);
+    if (F->rec_xyz) e += gvo_noncache_atom(F, t, coords + 3 * i, v[1], forces + 3 * i);
+    else e += gvo_grid_evaluate(F->grids[t], F->begin, F->end, F->n, coords + 3 * i, F->slope, v[1], forces + 3 * i);
   }
   float ie = 0;
   for (int k = 0; k < L->n_pairs; k++) { /* eval_interacting_pairs_deriv with v[0] */
@@ -197,7 +251,8 @@ float gvo_lig_eval_grid(const gvo_field *F, const gvo_lig *L, const float *conf,
   for (int i = 0; i < n; i++) {
     const int t = L->type[i];
     if (t < 0 || t >= 28 || is_h(t)) continue;
-    e += gvo_grid_evaluate(F->grids[t], F->begin, F->end, F->n, coords + 3 * i, F->slope, v1, 0);
+    if (F->rec_xyz) e += gvo_noncache_atom(F, t, coords + 3 * i, v1, 0);
+    else e += gvo_grid_evaluate(F->grids[t], F->begin, F->end, F->n, coords + 3 * i, F->slope, v1, 0);
   }
   if (coords_out) memcpy(coords_out, coords, 12 * n);
   free(coords); free(so); free(sa);
@@ -277,6 +332,29 @@ float gvo_bfgs(const gvo_field *F, const gvo_lig *L, float *x, float *g, int max
 }
 
 /* ---- random numbers: xorshift32, shared bit for bit with the device code ------------------------------ */
+/* refine_structure (main/main.cpp:131-171) on a non_cache field: up to 5 BFGS runs (quasi_newton::operator(),
+ * lib/quasi_newton.cpp:49-83) with the out-of-box slope 10, 100, ... until every heavy atom is within the box
+ * (non_cache::within, margin 1e-4); returns the last run's energy, x is refined in place, *within_out tells whether the
+ * final pose is inside (the reference sets out.e = max_fl otherwise). */
+float gvo_refine_structure(const gvo_field *F0, const gvo_lig *L, float *x, float *g, int maxiters, const float *v, int *n_evals,
+                           int *within_out) {
+  gvo_field F = *F0;
+  float slope = 10.f, e = 0;
+  int evals = 0, ok = 0;
+  for (int p = 0; p < 5; p++) {
+    int ne = 0;
+    F.slope = slope;
+    e = gvo_bfgs(&F, L, x, g, maxiters, v, &ne);
+    evals += ne;
+    ok = gvo_within(&F, L, x, 0.0001f);
+    if (ok) break;
+    slope *= 10.f;
+  }
+  if (n_evals) *n_evals = evals;
+  if (within_out) *within_out = ok;
+  return e;
+}
+
 static uint32_t rng_next(uint32_t *s) { uint32_t x = *s; x ^= x << 13; x ^= x >> 17; x ^= x << 5; *s = x; return x; }
 static float rng_fl(uint32_t *s, float a, float b) { return a + (b - a) * ((float)(rng_next(s) >> 8) * (1.0f / 16777216.0f)); }
 static int rng_int(uint32_t *s, int a, int b) { return a + (int)(rng_next(s) % (uint32_t)(b - a + 1)); }
