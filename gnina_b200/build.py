@@ -6,9 +6,14 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgnina_b200.so")
-SOURCES = ["gb_model.cu", "gb_grid.cu", "gb_cnn_fp32.cu", "gb_cnn_tc.cu", "gb_cnn_tc_dense.cu", "gb_cnn_tc_grad.cu", "gb_capi.cu", "gb_vina.cu"]
+SOURCES = ["gb_model.cu", "gb_grid.cu", "gb_cnn_fp32.cu", "gb_cnn_tc.cu", "gb_vox_tc.cu", "gb_cnn_tc_dense.cu", "gb_cnn_tc_grad.cu", "gb_capi.cu", "gb_vina.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+
+
+# gb_vina.cu restates float code whose sums and products must round like the reference's sequential C++ (compiled
+# without FMA contraction): no fused multiply-add anywhere in that file
+PER_FILE_FLAGS = {"gb_vina.cu": ["-fmad=false"]}
 
 
 def needs_build():
@@ -29,7 +34,7 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(HERE, "build", src + ".o")
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + PER_FILE_FLAGS.get(src, []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:

@@ -152,20 +152,6 @@ std::shared_ptr<TcWeights> get_tc_weights(const Model& m) {
   return tw;
 }
 
-TcGridWorkspace::~TcGridWorkspace() {
-  for (auto& k : x0)
-    for (auto p : k)
-      if (p) cudaFree(p);
-  for (auto e : ready)
-    if (e) cudaEventDestroy(e);
-  for (auto e : consumed)
-    if (e) cudaEventDestroy(e);
-  for (auto e : started)
-    if (e) cudaEventDestroy(e);
-  if (list_xyzr) cudaFree(list_xyzr);
-  if (list_ch) cudaFree(list_ch);
-  if (list_n) cudaFree(list_n);
-}
 void TcWorkspace::ensure(int i, size_t bytes) {
   if (cap[i] >= bytes) return;
   if (buf[i]) cudaFree(buf[i]);
@@ -177,199 +163,6 @@ void TcWorkspace::ensure(int i, size_t bytes) {
 TcWorkspace::~TcWorkspace() {
   for (auto p : buf)
     if (p) cudaFree(p);
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// Kernel A: voxelise + 2x2x2 average pool, fp16 output in the conv1 input layout.
-// CTA = 8x8x8 fine voxels (4x4x4 pooled) of one pose; thread = one fine voxel; the 8 fine voxels of a pooled
-// voxel are 8 lanes of one warp (xor-shuffle reduction).  Atoms: pose list (channel sorted) -> tile list (ordered
-// compaction in smem) -> per-warp cull (ballot) -> per-lane density.  Density: libmolgrid's piecewise function
-// with MUFU ex2 / rsqrt.
-__device__ __forceinline__ float fast_ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float fast_rsqrt(float x) {
-  float y;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ int block_ordered_slot512(bool pred, int* s_warp_counts, int& total) {
-  const unsigned mask = __ballot_sync(0xffffffffu, pred);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) s_warp_counts[warp] = __popc(mask);
-  __syncthreads();
-  int base = 0, tot = 0;
-#pragma unroll
-  for (int w = 0; w < 16; w++) {
-    const int c = s_warp_counts[w];
-    if (w < warp) base += c;
-    tot += c;
-  }
-  __syncthreads();
-  total = tot;
-  return base + __popc(mask & ((1u << lane) - 1u));
-}
-
-// v2: thread = one POOLED voxel (its 8 sub-voxels share the scaled coordinate differences), CTA = 8x8x8 pooled
-// voxels (16^3 fine voxels, an 8 A cube), warp = 4x4x2 pooled voxels.  Per warp-candidate atom a warp-uniform
-// guard skips the 8-evaluation body unless some lane's pooled voxel is within reach.  Density per sub-voxel, with
-// t = (d/r)^2 clamped to 2.25:   t <= 1 : exp(-2t) = ex2(t * -2log2e)   (one MUFU)
-//                                t >  1 : u(t)^2, u = (2 sqrt(t) - 3)/e as a degree-4 polynomial (|err| < 2e-5,
-//                                         u(2.25) = 0 so the clamp also implements the cutoff at 1.5 r).
-__device__ __forceinline__ float density_t(float t) {
-  const float tc = fminf(t, 2.25f);
-  const float g = fast_ex2(tc * -2.885390081777927f);
-  float u = fmaf(tc, -0.005817742552608252f, 0.052687861025333405f);
-  u = fmaf(u, tc, -0.20902030169963837f);
-  u = fmaf(u, tc, 0.6502527594566345f);
-  u = fmaf(u, tc, -0.8559605479240417f);
-  return tc <= 1.0f ? g : u * u;
-}
-
-constexpr int kVoxChunk = 512;  // one ordered compaction per 512 list atoms: every thread of the CTA stages one
-
-template <bool kMax>
-__global__ void __launch_bounds__(512) voxelize_pool_f16_kernel(const float4* __restrict__ list_xyzr,
-                                                                const int* __restrict__ list_ch,
-                                                                const int* __restrict__ list_n, int cap,
-                                                                const float* __restrict__ centers, float resolution,
-                                                                float dimension, uint4* __restrict__ x0, int Lp, int D,
-                                                                int P, int C8) {
-  __shared__ float4 s_atom[kVoxChunk];   // x, y, z, 1/r
-  __shared__ float s_thr2[kVoxChunk];    // (1.5 + half-diagonal/r)^2 : pooled-voxel centre test, in units of r
-  __shared__ float s_reach[kVoxChunk];   // 1.5 r
-  __shared__ int s_ch[kVoxChunk];
-  __shared__ int s_counts[16];
-  __shared__ __half s_out[32 * 512];     // [channel][pooled voxel]
-  const int CH = C8 * 8;
-  const int p = blockIdx.y;
-  const int tiles = D / 8;
-  const int t = blockIdx.x;
-  const int tx = t / (tiles * tiles), ty = (t / tiles) % tiles, tz = t % tiles;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wx = warp & 1, wy = (warp >> 1) & 1, wz = warp >> 2;
-  const int px = wx * 4 + (lane & 3), py = wy * 4 + ((lane >> 2) & 3), pz = wz * 2 + (lane >> 4);
-  const int pv = (px * 8 + py) * 8 + pz;
-  for (int e = threadIdx.x; e < CH * 512 / 2; e += 512) reinterpret_cast<uint32_t*>(s_out)[e] = 0u;
-  const float half = dimension * 0.5f;
-  const float ox = centers[3 * p] - half, oy = centers[3 * p + 1] - half, oz = centers[3 * p + 2] - half;
-  const float hres = 0.5f * resolution;
-  // centre of this thread's pooled voxel (between fine voxels 2X and 2X+1)
-  const float cx = ox + (2 * (tx * 8 + px) + 0.5f) * resolution;
-  const float cy = oy + (2 * (ty * 8 + py) + 0.5f) * resolution;
-  const float cz = oz + (2 * (tz * 8 + pz) + 0.5f) * resolution;
-  // CTA box and warp box (fine-voxel coordinates covered)
-  const float lox = ox + 16 * tx * resolution, loy = oy + 16 * ty * resolution, loz = oz + 16 * tz * resolution;
-  const float span = 15.f * resolution;
-  const float wlx = lox + 8 * wx * resolution, wly = loy + 8 * wy * resolution, wlz = loz + 4 * wz * resolution;
-  const float wsx = 7.f * resolution, wsz = 3.f * resolution;
-  const float4* la = list_xyzr + (size_t)p * cap;
-  const int* lc = list_ch + (size_t)p * cap;
-  const int n = list_n[p];
-  int cur = -1;
-  float acc = 0.f;
-  float am[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // kMax: the 8 sub-voxels are kept apart until the channel is flushed
-  auto flush_value = [&]() -> float {
-    if constexpr (kMax) {
-      float v = fmaxf(fmaxf(fmaxf(am[0], am[1]), fmaxf(am[2], am[3])), fmaxf(fmaxf(am[4], am[5]), fmaxf(am[6], am[7])));
-#pragma unroll
-      for (int q = 0; q < 8; q++) am[q] = 0.f;
-      return v;
-    } else {
-      const float v = acc * 0.125f;
-      acc = 0.f;
-      return v;
-    }
-  };
-  for (int base = 0; base < n; base += kVoxChunk) {
-    bool keep = false;
-    float4 a = make_float4(0, 0, 0, 0);
-    int ch = 0;
-    const int ai = base + threadIdx.x;
-    if (threadIdx.x < kVoxChunk && ai < n) {
-      a = la[ai];
-      ch = lc[ai];
-      const float reach = 1.5f * a.w + 1e-4f;
-      keep = a.x >= lox - reach && a.x <= lox + span + reach && a.y >= loy - reach && a.y <= loy + span + reach &&
-             a.z >= loz - reach && a.z <= loz + span + reach;
-    }
-    int tot;
-    const int slot = block_ordered_slot512(keep, s_counts, tot);
-    if (keep) {
-      const float inv = 1.0f / a.w;
-      const float thr = 1.5f + 1.7320508f * hres * inv + 1e-3f;  // sub-voxel offsets are +-res/2 per axis
-      s_atom[slot] = make_float4(a.x, a.y, a.z, inv);
-      s_thr2[slot] = thr * thr;
-      s_reach[slot] = 1.5f * a.w + 1e-4f;
-      s_ch[slot] = ch;
-    }
-    __syncthreads();
-    for (int wb = 0; wb < tot; wb += 32) {
-      const int m = wb + lane;
-      bool hit = false;
-      if (m < tot) {
-        const float4 b = s_atom[m];
-        const float reach = s_reach[m];
-        hit = b.x >= wlx - reach && b.x <= wlx + wsx + reach && b.y >= wly - reach && b.y <= wly + wsx + reach &&
-              b.z >= wlz - reach && b.z <= wlz + wsz + reach;
-      }
-      // Two-level test.  (1) warp level: candidates whose reach touches the warp's 4x4x2 box (ballot above).
-      // (2) lane level: the subset each lane's own pooled voxel can see.  A reach sphere (r ~ 3.3 A) fills only ~20 %
-      // of the boxes it touches, so evaluating a candidate on all 32 lanes wastes most of the work; instead every
-      // lane walks ITS bit mask (divergent loop, trip count = the busiest lane's), in list order, so the sums and
-      // the channel flushes are exactly those of the all-lanes loop minus terms that are identically zero.
-      const unsigned wmask = __ballot_sync(0xffffffffu, hit);
-      unsigned lmask = 0u;
-      for (unsigned mk = wmask; mk; mk &= mk - 1) {
-        const int bit = __ffs(mk) - 1;
-        const float4 b = s_atom[wb + bit];
-        const float dx = (cx - b.x) * b.w, dy = (cy - b.y) * b.w, dz = (cz - b.z) * b.w;  // in units of r
-        if (dx * dx + dy * dy + dz * dz < s_thr2[wb + bit]) lmask |= 1u << bit;
-      }
-      while (lmask) {
-        const int mm = wb + __ffs(lmask) - 1;
-        lmask &= lmask - 1;
-        const int chm = s_ch[mm];
-        if (chm != cur) {
-          if (cur >= 0) s_out[cur * 512 + pv] = __float2half(flush_value());
-          cur = chm;
-        }
-        const float4 b = s_atom[mm];
-        const float dx = (cx - b.x) * b.w, dy = (cy - b.y) * b.w, dz = (cz - b.z) * b.w;
-        const float h = hres * b.w;
-        const float x0 = dx - h, x1 = dx + h, y0 = dy - h, y1 = dy + h, z0 = dz - h, z1 = dz + h;
-        const float sx0 = x0 * x0, sx1 = x1 * x1, sy0 = y0 * y0, sy1 = y1 * y1, sz0 = z0 * z0, sz1 = z1 * z1;
-        const float s00 = sx0 + sy0, s01 = sx0 + sy1, s10 = sx1 + sy0, s11 = sx1 + sy1;
-        if constexpr (kMax) {
-          am[0] += density_t(s00 + sz0); am[1] += density_t(s00 + sz1); am[2] += density_t(s01 + sz0);
-          am[3] += density_t(s01 + sz1); am[4] += density_t(s10 + sz0); am[5] += density_t(s10 + sz1);
-          am[6] += density_t(s11 + sz0); am[7] += density_t(s11 + sz1);
-        } else {
-          acc += density_t(s00 + sz0) + density_t(s00 + sz1) + density_t(s01 + sz0) + density_t(s01 + sz1) +
-                 density_t(s10 + sz0) + density_t(s10 + sz1) + density_t(s11 + sz0) + density_t(s11 + sz1);
-        }
-      }
-    }
-    __syncthreads();
-  }
-  if (cur >= 0) s_out[cur * 512 + pv] = __float2half(flush_value());
-  __syncthreads();
-  // write the pooled tile: 512 pooled voxels x C8 chunks of 16 B, z fastest
-  for (int e = threadIdx.x; e < 512 * C8; e += 512) {
-    const int c8 = e >> 9, q = e & 511;
-    const int qx = q >> 6, qy = (q >> 3) & 7, qz = q & 7;
-    uint32_t w[4];
-#pragma unroll
-    for (int k2 = 0; k2 < 4; k2++) {
-      const uint16_t lo16 = *reinterpret_cast<const uint16_t*>(&s_out[(c8 * 8 + 2 * k2) * 512 + q]);
-      const uint16_t hi16 = *reinterpret_cast<const uint16_t*>(&s_out[(c8 * 8 + 2 * k2 + 1) * 512 + q]);
-      w[k2] = (uint32_t)lo16 | ((uint32_t)hi16 << 16);
-    }
-    const int x = tx * 8 + qx, y = ty * 8 + qy, z = tz * 8 + qz;
-    x0[(((size_t)p * D + x) * C8 + c8) * Lp + (size_t)(y + 1) * P + (z + 1)] = make_uint4(w[0], w[1], w[2], w[3]);
-  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1020,66 +813,6 @@ const void* tc_debug_buffer(int i, size_t* bytes) {
   if (i < 0 || i >= 8) return nullptr;
   if (bytes) *bytes = t_debug.bytes[i];
   return t_debug.ptr[i];
-}
-
-int tc_prepare_grid(const TcPoseBatch& pb, TcGridWorkspace& gw, int buf, int kinds_mask, cudaStream_t s, Profiler* prof) {
-  const int nb = pb.n_poses;
-  const ActLayout L1 = make_layout(24, 1, 32);
-  const int cap = std::max(1, pb.n_rec + pb.max_pose_atoms);
-  // allocation sizes have a floor (64 poses, 128 ligand atoms) so that small batches of varying size -- the kept
-  // poses of one docked ligand -- never re-allocate: cudaFree / cudaMemset synchronise the whole device and would
-  // stall the kernels of other handles (DockingPool keeps one handle per host thread)
-  const int nb_alloc = std::max(nb, 64);
-  const size_t need = (size_t)nb_alloc * std::max(cap, pb.n_rec + 128);
-  if (gw.list_cap < need) {
-    GB_CUDA(cudaStreamSynchronize(s));
-    if (gw.list_xyzr) cudaFree(gw.list_xyzr);
-    if (gw.list_ch) cudaFree(gw.list_ch);
-    GB_CUDA(cudaMalloc(&gw.list_xyzr, need * sizeof(float4)));
-    GB_CUDA(cudaMalloc(&gw.list_ch, need * sizeof(int)));
-    gw.list_cap = need;
-  }
-  if (gw.listn_cap < (size_t)nb_alloc) {
-    GB_CUDA(cudaStreamSynchronize(s));
-    if (gw.list_n) cudaFree(gw.list_n);
-    GB_CUDA(cudaMalloc(&gw.list_n, (size_t)nb_alloc * sizeof(int)));
-    gw.listn_cap = nb_alloc;
-  }
-  const size_t need0 = act_bytes(L1, nb_alloc);
-  for (int kind = 0; kind < 2; kind++) {
-    if (!(kinds_mask & (1 << kind)) || gw.cap[kind][buf] >= need0) continue;
-    GB_CUDA(cudaDeviceSynchronize());
-    if (gw.x0[kind][buf]) cudaFree(gw.x0[kind][buf]);
-    GB_CUDA(cudaMalloc(&gw.x0[kind][buf], need0));
-    GB_CUDA(cudaMemset(gw.x0[kind][buf], 0, need0));
-    gw.cap[kind][buf] = need0;
-  }
-  for (int i = 0; i < 2; i++) {
-    if (!gw.ready[i]) GB_CUDA(cudaEventCreateWithFlags(&gw.ready[i], cudaEventDisableTiming));
-    if (!gw.consumed[i]) GB_CUDA(cudaEventCreateWithFlags(&gw.consumed[i], cudaEventDisableTiming));
-    if (!gw.started[i]) GB_CUDA(cudaEventCreateWithFlags(&gw.started[i], cudaEventDisableTiming));
-  }
-  {
-    ProfScope ps(prof, "tc_build_pose_lists", s);
-    launch_build_pose_lists(pb.rec_xyzr, pb.rec_ch, pb.n_rec, pb.lig_xyzr, pb.lig_ch, pb.lig_off, pb.centers, nb,
-                            pb.dimension / 2.f, cap, gw.list_xyzr, gw.list_ch, gw.list_n, s, pb.rot);
-  }
-  int launches = 1;
-  if (kinds_mask & 1) {
-    ProfScope ps(prof, "tc_voxelize_pool", s);
-    voxelize_pool_f16_kernel<false><<<dim3(27, nb), 512, 0, s>>>(gw.list_xyzr, gw.list_ch, gw.list_n, cap, pb.centers,
-                                                                 pb.resolution, pb.dimension,
-                                                                 reinterpret_cast<uint4*>(gw.x0[0][buf]), L1.Lp, L1.D, L1.P, L1.C8);
-    launches++;
-  }
-  if (kinds_mask & 2) {
-    ProfScope ps(prof, "tc_voxelize_maxpool", s);
-    voxelize_pool_f16_kernel<true><<<dim3(27, nb), 512, 0, s>>>(gw.list_xyzr, gw.list_ch, gw.list_n, cap, pb.centers,
-                                                                pb.resolution, pb.dimension,
-                                                                reinterpret_cast<uint4*>(gw.x0[1][buf]), L1.Lp, L1.D, L1.P, L1.C8);
-    launches++;
-  }
-  return launches;
 }
 
 int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspace& ws, float* out3, cudaStream_t s,

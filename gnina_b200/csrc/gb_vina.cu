@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <vector>
 #include "gb_internal.h"
 
@@ -111,7 +112,10 @@ struct Vina {
     float4* seg_rel_axis = nullptr;
     int2* pairs = nullptr;
     int* adj_off = nullptr;    // [n_atoms + 1] CSR over the pair list, both directions
-    int* adj = nullptr;        // [2 n_pairs] partner atom
+    int* adj = nullptr;        // [2 n_pairs] partner atom | pair index << 8 | (this atom is the pair's first) << 30
+    int* child_off = nullptr;  // [n_seg + 1] CSR of the torsion tree: children of every segment, ascending
+    int* child = nullptr;      // [n_seg - 1]
+    unsigned heavy_types = 0;  // bit t set: a movable heavy atom of smina type t (checked against the built grids)
   } lig;
   // receptor (heavy atoms, index order)
   float4* d_rec = nullptr;  // x, y, z, type
@@ -133,7 +137,7 @@ struct Vina {
     for (auto q : pws) cudaFreeHost(q);
     cudaFree(d_fast); cudaFree(d_smooth); cudaFree(d_sp); cudaFree(d_rec);
     cudaFree(lig.local); cudaFree(lig.atom_seg); cudaFree(lig.seg); cudaFree(lig.seg_rel_origin); cudaFree(lig.seg_rel_axis);
-    cudaFree(lig.pairs); cudaFree(lig.adj_off); cudaFree(lig.adj); cudaFree(d_lig); cudaFree(d_off); cudaFree(d_atom_e); cudaFree(d_deriv);
+    cudaFree(lig.pairs); cudaFree(lig.adj_off); cudaFree(lig.adj); cudaFree(lig.child_off); cudaFree(lig.child); cudaFree(d_lig); cudaFree(d_off); cudaFree(d_atom_e); cudaFree(d_deriv);
     cudaFree(d_pose_e); cudaFree(d_tors);
     for (auto g : grid_pool) cudaFree(g);
   }
@@ -586,9 +590,15 @@ struct LigPtrs {
   int n_atoms, n_seg, n_pairs, max_depth, n_heavy;
   float gyration_radius;
   const float4* local; const int* atom_seg; const int4* seg; const float4* rel_origin; const float4* rel_axis; const int2* pairs;
-  const int* adj_off; const int* adj;
+  const int* adj_off; const int* adj;      // adj: partner | pair index << 8 | first-of-pair << 30
+  const int* child_off; const int* child;  // children of every segment (CSR, ascending)
 };
-struct DockField { GridGeom G; GridPtrs gp; const float2* smooth; int n_samples; float factor, slope; const float4* sp; int n_sp; float sp_fraction; };
+// rec != nullptr selects non_cache (lib/non_cache.cpp): direct sums over the receptor's heavy atoms instead of the
+// affinity grids, with the box [nc_begin, nc_end] for the out-of-box clamp and penalty
+struct DockField {
+  GridGeom G; GridPtrs gp; const float2* smooth; int n_samples; float factor, slope; const float4* sp; int n_sp; float sp_fraction;
+  const float4* rec; int n_rec; float nc_begin[3], nc_end[3];
+};
 
 // Per-warp shared-memory workspace, carved out of dynamic shared memory and sized by the ACTUAL ligand (atoms,
 // segments) instead of the maxima: a typical ligand (27 atoms, 7 segments) needs 2.3 KB per warp instead of 10 KB, so
@@ -601,13 +611,14 @@ struct WarpWs {
   float *g, *g_new, *g_orig, *p, *y, *mhy;  // [n]  (6 + T)
   float *h;                            // [n (n + 1) / 2]
   float *cand, *tmp;                   // [n + 2]
+  float *ea, *pe;                      // [na] per-atom grid energies, [np] per-pair energies (summed in index order)
 };
-__host__ __device__ inline int dk_ws_floats(int na, int ns) {
+__host__ __device__ inline int dk_ws_floats(int na, int ns, int np) {
   const int n = 6 + ns - 1;
-  int f = 6 * na + 25 * ns + 3 * (n + 2) + 6 * n + n * (n + 1) / 2 + 2 * (n + 2);
+  int f = 6 * na + 25 * ns + 3 * (n + 2) + 6 * n + n * (n + 1) / 2 + 2 * (n + 2) + na + np;
   return (f + 3) & ~3;  // 16-byte multiple
 }
-__device__ inline void dk_ws_carve(WarpWs& W, float* base, int na, int ns) {
+__device__ inline void dk_ws_carve(WarpWs& W, float* base, int na, int ns, int np) {
   const int n = 6 + ns - 1;
   float* p = base;
   auto take = [&](int k) { float* r = p; p += k; return r; };
@@ -617,6 +628,27 @@ __device__ inline void dk_ws_carve(WarpWs& W, float* base, int na, int ns) {
   W.g = take(n); W.g_new = take(n); W.g_orig = take(n); W.p = take(n); W.y = take(n); W.mhy = take(n);
   W.h = take(n * (n + 1) / 2);
   W.cand = take(n + 2); W.tmp = take(n + 2);
+  W.ea = take(na); W.pe = take(np);
+}
+// sin / cos of a float argument, correctly rounded (evaluated in double): what glibc's sinf / cosf return in all but
+// ~1e-4 of the cases, so that the torsion-tree kinematics reproduce the CPU restatement bit for bit.  B200 has a full-rate
+// FP64 pipe; two calls per torsion and evaluation are noise next to the pair-table lookups.
+__device__ inline void dk_sincos(float a, float* s, float* c) {
+  double sd, cd;
+  sincos((double)a, &sd, &cd);
+  *s = (float)sd; *c = (float)cd;
+}
+// sum_{k<n} a[k] (or a[k] b[k]) in index order, every lane computing the same chain: the reference's sequential
+// float association (lib/model.cu:38-60, lib/bfgs.h), not a butterfly -- a different order changes line-search decisions
+__device__ inline float dk_sum_seq(const float* a, int n) {
+  float s = 0.f;
+  for (int k = 0; k < n; k++) s += a[k];
+  return s;
+}
+__device__ inline float dk_dot_seq(const float* a, const float* b, int n) {
+  float s = 0.f;
+  for (int k = 0; k < n; k++) s += a[k] * b[k];
+  return s;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -632,7 +664,8 @@ __device__ inline void dk_normalize_angle(float& x) {
 }
 __device__ inline void dk_angle_to_q(const float* axis, float angle, float* q) {
   dk_normalize_angle(angle);
-  const float c = cosf(angle / 2), s = sinf(angle / 2);
+  float c, s;
+  dk_sincos(angle / 2, &s, &c);
   q[0] = c; q[1] = s * axis[0]; q[2] = s * axis[1]; q[3] = s * axis[2];
 }
 __device__ inline void dk_qmul(const float* l, const float* r, float* o) {
@@ -682,8 +715,7 @@ __device__ void dk_set_conf(const LigPtrs& L, WarpWs& W, const float* xc, int la
   if (lane >= 1 && lane < L.n_seg) {
     float ang = xc[7 + lane - 1];
     dk_normalize_angle(ang);
-    tors_c = cosf(ang / 2);
-    tors_s = sinf(ang / 2);
+    dk_sincos(ang / 2, &tors_s, &tors_c);
   }
   for (int d = 0; d <= L.max_depth; d++) {
     if (lane < L.n_seg) {
@@ -722,79 +754,128 @@ __device__ void dk_set_conf(const LigPtrs& L, WarpWs& W, const float* xc, int la
   __syncwarp();
 }
 
-// update_energy: cache::eval (grid energy only)
-__device__ float dk_eval_grid(const LigPtrs& L, const DockField& F, WarpWs& W, const float* xc, float v1, int lane) {
-  dk_set_conf(L, W, xc, lane);
-  float e = 0.f;
-  for (int i = lane; i < L.n_atoms; i += 32) {
-    const int t = (int)L.local[i].w;
-    if (t >= 2 && t < kNumSminaTypes) e += grid_evaluate_dev(F.gp.g[t], F.G, W.coords[3 * i], W.coords[3 * i + 1], W.coords[3 * i + 2], F.slope, v1, nullptr);
+// precalculate::eval_deriv of one type pair at squared distance r2 -> (e, dE/dr / r): the linear tables
+// (lib/precalculate.h:97-133) or, when selected, the splines (:380-449)
+__device__ __forceinline__ void dk_pair_terms(const DockField& F, int t1, int t2, float r2, float& pe, float& dor) {
+  if (t1 > t2) { const int tt = t1; t1 = t2; t2 = tt; }
+  if (F.sp) {  // precalculate_splines::eval_deriv (a pair whose knots are all zero has all-zero coefficients)
+    const float r = sqrtf(r2);
+    int idx = (int)(r / F.sp_fraction);
+    if (idx >= F.n_sp) idx = F.n_sp - 1;
+    const float4 c = F.sp[(size_t)(t1 + t2 * (t2 + 1) / 2) * F.n_sp + idx];
+    const float lx = r - idx * F.sp_fraction;
+    pe = ((c.x * lx + c.y) * lx + c.z) * lx + c.w;
+    dor = ((3 * c.x * lx + 2 * c.y) * lx + c.z) / r;
+  } else {
+    const float r2f = F.factor * r2;
+    const int i1 = (int)r2f;
+    const float rem = r2f - i1;
+    const float2* tb = F.smooth + (size_t)(t1 + t2 * (t2 + 1) / 2) * F.n_samples;
+    const float2 s1 = tb[i1], s2 = tb[i1 + 1];
+    pe = s1.x + rem * (s2.x - s1.x);
+    dor = s1.y + rem * (s2.y - s1.y);
   }
-  return warp_sum(e);
 }
 
-// model::eval_deriv: returns e (all lanes), writes change[6+T] to gout
+// non_cache::eval / eval_deriv for one movable heavy atom (lib/non_cache.cpp:52-81,126-174): clamp to the box
+// (check_bounds_deriv :102-123, penalty = slope x L1 distance), sum e and dor r over the receptor atoms with r^2 < 64 in
+// index order (the reference's szv_grid only pre-selects candidates, in ascending order), curl, out-of-box derivative
+__device__ float dk_noncache_atom(const DockField& F, int t1, float ax, float ay, float az, float v, float* deriv) {
+  const float a[3] = {ax, ay, az};
+  float adj[3], oob[3] = {0.f, 0.f, 0.f}, pen = 0.f;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    adj[j] = a[j];
+    if (a[j] < F.nc_begin[j]) { adj[j] = F.nc_begin[j]; oob[j] = -1.f; pen += fabsf(a[j] - F.nc_begin[j]); }
+    else if (a[j] > F.nc_end[j]) { adj[j] = F.nc_end[j]; oob[j] = 1.f; pen += fabsf(a[j] - F.nc_end[j]); }
+  }
+  pen *= F.slope;
+  float e = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
+  for (int b = 0; b < F.n_rec; b++) {
+    const float4 rb = F.rec[b];
+    const float r0 = adj[0] - rb.x, r1 = adj[1] - rb.y, r2c = adj[2] - rb.z;
+    const float r2 = r0 * r0 + r1 * r1 + r2c * r2c;
+    if (r2 < 64.f) {
+      float pe, dor;
+      dk_pair_terms(F, t1, (int)rb.w, r2, pe, dor);
+      e += pe;
+      d0 += dor * r0; d1 += dor * r1; d2 += dor * r2c;
+    }
+  }
+  if (e > 0 && v < 0.1f * 3.402823466e+38f) {  // curl (lib/curl.h:30-42)
+    const float tmp = (v < 1.1920929e-07f) ? 0.f : (v / (v + e));
+    e *= tmp;
+    d0 *= tmp * tmp; d1 *= tmp * tmp; d2 *= tmp * tmp;
+  }
+  if (deriv) { deriv[0] = d0 + F.slope * oob[0]; deriv[1] = d1 + F.slope * oob[1]; deriv[2] = d2 + F.slope * oob[2]; }
+  return e + pen;
+}
+
+// ig->eval / ig->eval_deriv for atom i (cache or non_cache); 0 and zero forces for hydrogens
+__device__ __forceinline__ float dk_atom_field(const LigPtrs& L, const DockField& F, const WarpWs& W, int i, float v1, float* d) {
+  const int t = (int)L.local[i].w;
+  if (!(t >= 2 && t < kNumSminaTypes)) return 0.f;
+  if (F.rec) return dk_noncache_atom(F, t, W.coords[3 * i], W.coords[3 * i + 1], W.coords[3 * i + 2], v1, d);
+  return grid_evaluate_dev(F.gp.g[t], F.G, W.coords[3 * i], W.coords[3 * i + 1], W.coords[3 * i + 2], F.slope, v1, d);
+}
+
+// update_energy: cache::eval (intermolecular energy only), atoms summed in index order
+__device__ float dk_eval_grid(const LigPtrs& L, const DockField& F, WarpWs& W, const float* xc, float v1, int lane) {
+  dk_set_conf(L, W, xc, lane);
+  for (int i = lane; i < L.n_atoms; i += 32) W.ea[i] = dk_atom_field(L, F, W, i, v1, nullptr);
+  __syncwarp();
+  const float e = dk_sum_seq(W.ea, L.n_atoms);
+  __syncwarp();
+  return e;
+}
+
+// model::eval_deriv (lib/model.cu:202-225): returns e (all lanes), writes change[6+T] to gout.  Every sum follows the
+// reference's association -- atom energies in atom order, pair energies in pair order, the forces on an atom in the
+// order its pairs appear in the pair list, children folded into their parent in ascending order -- so that the result
+// agrees with the sequential CPU code to round-off of the transcendental functions only (north_star: 1e-6).
 __device__ float dk_eval_deriv(const LigPtrs& L, const DockField& F, WarpWs& W, const float* xc, const float* v, float* gout, int lane) {
   dk_set_conf(L, W, xc, lane);
-  float e = 0.f;
   for (int i = lane; i < L.n_atoms; i += 32) {
-    const int t = (int)L.local[i].w;
     float d[3] = {0.f, 0.f, 0.f};
-    if (t >= 2 && t < kNumSminaTypes) e += grid_evaluate_dev(F.gp.g[t], F.G, W.coords[3 * i], W.coords[3 * i + 1], W.coords[3 * i + 2], F.slope, v[1], d);
+    W.ea[i] = dk_atom_field(L, F, W, i, v[1], d);
     W.forces[3 * i] = d[0]; W.forces[3 * i + 1] = d[1]; W.forces[3 * i + 2] = d[2];
   }
   __syncwarp();
-  // V6 intramolecular pairs, atom by atom: lane i walks atom i's partners (CSR, both directions) and sums the forces
-  // on ITS atom in registers -- every pair is evaluated from both ends (the energy counts half each time), which costs
-  // 2x the table lookups and removes the shared-memory float atomics that the pair-parallel version spent 70 % of
-  // its stall samples on (ncu r1l: consecutive pairs share their first atom, a 32-way serialised CAS loop).  The sums
-  // are now in a fixed order: evaluations are reproducible.
+  // V6 intramolecular pairs, atom by atom: lane i walks atom i's partners (CSR over the pair list, both directions, in
+  // pair order) and continues the force sum of ITS atom in registers, starting from the grid force -- exactly the
+  // sequence of additions the reference performs on minus_forces[i].  Every pair is evaluated from both ends (2x the
+  // table lookups, no shared-memory atomics: ncu r1l); the end that is the pair's first atom records the pair energy.
   for (int i = lane; i < L.n_atoms; i += 32) {
     const float xi = W.coords[3 * i], yi = W.coords[3 * i + 1], zi = W.coords[3 * i + 2];
     const int ti = (int)L.local[i].w;
-    float fxs = 0.f, fys = 0.f, fzs = 0.f, es = 0.f;
+    float fxs = W.forces[3 * i], fys = W.forces[3 * i + 1], fzs = W.forces[3 * i + 2];
     const int q1 = L.adj_off[i + 1];
     for (int q = L.adj_off[i]; q < q1; q++) {
-      const int j = L.adj[q];
+      const int code = L.adj[q];
+      const int j = code & 0xff, k = (code >> 8) & 0x3fffff;
+      const bool first = (code >> 30) & 1;
       const float rx = W.coords[3 * j] - xi, ry = W.coords[3 * j + 1] - yi, rz = W.coords[3 * j + 2] - zi;
       const float r2 = rx * rx + ry * ry + rz * rz;
+      float pe = 0.f;
       if (r2 < 64.f) {
-        int t1 = ti, t2 = (int)L.local[j].w;
-        if (t1 > t2) { const int tt = t1; t1 = t2; t2 = tt; }
-        float pe, dor;
-        if (F.sp) {  // precalculate_splines::eval_deriv (a pair whose knots are all zero has all-zero coefficients)
-          const float r = sqrtf(r2);
-          int idx = (int)(r / F.sp_fraction);
-          if (idx >= F.n_sp) idx = F.n_sp - 1;
-          const float4 c = F.sp[(size_t)(t1 + t2 * (t2 + 1) / 2) * F.n_sp + idx];
-          const float lx = r - idx * F.sp_fraction;
-          pe = ((c.x * lx + c.y) * lx + c.z) * lx + c.w;
-          dor = ((3 * c.x * lx + 2 * c.y) * lx + c.z) / r;
-        } else {
-          const float r2f = F.factor * r2;
-          const int i1 = (int)r2f;
-          const float rem = r2f - i1;
-          const float2* tb = F.smooth + (size_t)(t1 + t2 * (t2 + 1) / 2) * F.n_samples;
-          const float2 s1 = tb[i1], s2 = tb[i1 + 1];
-          pe = s1.x + rem * (s2.x - s1.x);
-          dor = s1.y + rem * (s2.y - s1.y);
-        }
+        float dor;
+        dk_pair_terms(F, ti, (int)L.local[j].w, r2, pe, dor);
         float fx = dor * rx, fy = dor * ry, fz = dor * rz;
         if (pe > 0 && v[0] < 0.1f * 3.402823466e+38f) {
           const float tmp = (v[0] < 1.1920929e-07f) ? 0.f : (v[0] / (v[0] + pe));
           pe *= tmp;
           fx *= tmp * tmp; fy *= tmp * tmp; fz *= tmp * tmp;
         }
-        es += pe;
-        fxs -= fx; fys -= fy; fzs -= fz;  // force on atom i of the pair (i, j): -dor (x_j - x_i)
+        fxs -= fx; fys -= fy; fzs -= fz;  // pair (a, b), r = x_b - x_a: forces[a] -= dor r ; seen from b, r changes sign
       }
+      if (first) W.pe[k] = pe;            // a pair beyond the cut-off adds nothing to the reference's running sum
     }
-    e += 0.5f * es;
-    W.forces[3 * i] += fxs; W.forces[3 * i + 1] += fys; W.forces[3 * i + 2] += fzs;
+    W.forces[3 * i] = fxs; W.forces[3 * i + 1] = fys; W.forces[3 * i + 2] = fzs;
   }
-  e = warp_sum(e);
   __syncwarp();
-  // V8: per-segment force / torque about the segment origin, then fold children into parents (deepest first)
+  float e = dk_sum_seq(W.ea, L.n_atoms);
+  e += dk_sum_seq(W.pe, L.n_pairs);
+  // V8: per-segment force / torque about the segment origin (sum_force_and_torque, lib/tree.h:133-140) ...
   if (lane < L.n_seg) {
     const int4 sg = L.seg[lane];
     float f[6] = {0, 0, 0, 0, 0, 0};
@@ -807,17 +888,20 @@ __device__ float dk_eval_deriv(const LigPtrs& L, const DockField& F, WarpWs& W, 
     for (int k = 0; k < 6; k++) W.ft[6 * lane + k] = f[k];
   }
   __syncwarp();
-  for (int d = L.max_depth; d >= 1; d--) {
-    if (lane < L.n_seg) {
-      const int4 sg = L.seg[lane];
-      if (sg.w == d) {
-        const int pp = sg.x;
-        const float* c = W.ft + 6 * lane;
-        const float rx = W.so[3 * lane] - W.so[3 * pp], ry = W.so[3 * lane + 1] - W.so[3 * pp + 1], rz = W.so[3 * lane + 2] - W.so[3 * pp + 2];
-        atomicAdd(&W.ft[6 * pp + 0], c[0]); atomicAdd(&W.ft[6 * pp + 1], c[1]); atomicAdd(&W.ft[6 * pp + 2], c[2]);
-        atomicAdd(&W.ft[6 * pp + 3], ry * c[2] - rz * c[1] + c[3]);
-        atomicAdd(&W.ft[6 * pp + 4], rz * c[0] - rx * c[2] + c[4]);
-        atomicAdd(&W.ft[6 * pp + 5], rx * c[1] - ry * c[0] + c[5]);
+  // ... then every parent gathers its children in ascending order, deepest parents first (branches_derivative,
+  // lib/tree.h:300-310): no atomics, the reference's order
+  for (int d = L.max_depth - 1; d >= 0; d--) {
+    if (lane < L.n_seg && L.seg[lane].w == d) {
+      float* ft = W.ft + 6 * lane;
+      const int c1 = L.child_off[lane + 1];
+      for (int q = L.child_off[lane]; q < c1; q++) {
+        const int ch = L.child[q];
+        const float* c = W.ft + 6 * ch;
+        const float rx = W.so[3 * ch] - W.so[3 * lane], ry = W.so[3 * ch + 1] - W.so[3 * lane + 1], rz = W.so[3 * ch + 2] - W.so[3 * lane + 2];
+        ft[0] += c[0]; ft[1] += c[1]; ft[2] += c[2];
+        ft[3] += (ry * c[2] - rz * c[1]) + c[3];
+        ft[4] += (rz * c[0] - rx * c[2]) + c[4];
+        ft[5] += (rx * c[1] - ry * c[0]) + c[5];
       }
     }
     __syncwarp();
@@ -866,9 +950,7 @@ __device__ float dk_bfgs(const LigPtrs& L, const DockField& F, WarpWs& W, int ma
       W.p[i] = -s;
     }
     __syncwarp();
-    float pg = 0.f;
-    for (int i = lane; i < n; i += 32) pg += W.p[i] * W.g[i];
-    pg = warp_sum(pg);
+    const float pg = dk_dot_seq(W.p, W.g, n);
     float f1 = 0.f, alpha = 1.f;
     for (int trial = 0; trial < 10; trial++) {
       for (int i = lane; i < nx; i += 32) W.x_new[i] = W.x[i];
@@ -886,9 +968,7 @@ __device__ float dk_bfgs(const LigPtrs& L, const DockField& F, WarpWs& W, int ma
     __syncwarp();
     for (int i = lane; i < n; i += 32) W.g[i] = W.g_new[i];
     __syncwarp();
-    float gn = 0.f, yy = 0.f, yp = 0.f;
-    for (int i = lane; i < n; i += 32) { gn += W.g[i] * W.g[i]; yy += W.y[i] * W.y[i]; yp += W.y[i] * W.p[i]; }
-    gn = warp_sum(gn); yy = warp_sum(yy); yp = warp_sum(yp);
+    const float gn = dk_dot_seq(W.g, W.g, n), yy = dk_dot_seq(W.y, W.y, n), yp = dk_dot_seq(W.y, W.p, n);
     if (!(gn >= 1e-4f)) break;
     if (step == 0 || didreset) {
       didreset = false;
@@ -903,9 +983,7 @@ __device__ float dk_bfgs(const LigPtrs& L, const DockField& F, WarpWs& W, int ma
         W.mhy[i] = -s;
       }
       __syncwarp();
-      float yhy = 0.f;
-      for (int i = lane; i < n; i += 32) yhy += W.y[i] * W.mhy[i];
-      yhy = -warp_sum(yhy);
+      const float yhy = -dk_dot_seq(W.y, W.mhy, n);
       const float r = 1 / (alpha * yp);
       for (int k = lane; k < n * (n + 1) / 2; k += 32) {
         // invert k = i + j(j+1)/2, i <= j
@@ -948,7 +1026,7 @@ __global__ void __launch_bounds__(32 * kDkWarps) dock_eval_kernel(LigPtrs L, Doc
   const int c = blockIdx.x * kDkWarps + warp;
   if (c >= n) return;
   WarpWs W;
-  dk_ws_carve(W, dk_smem + (size_t)warp * dk_ws_floats(L.n_atoms, L.n_seg), L.n_atoms, L.n_seg);
+  dk_ws_carve(W, dk_smem + (size_t)warp * dk_ws_floats(L.n_atoms, L.n_seg, L.n_pairs), L.n_atoms, L.n_seg, L.n_pairs);
   const int T = L.n_seg - 1, nx = 7 + T, ng = 6 + T;
   const float v[3] = {v0, v1, v2};
   for (int i = lane; i < nx; i += 32) W.x[i] = confs[(size_t)c * nx + i];
@@ -969,19 +1047,58 @@ __global__ void __launch_bounds__(32 * kDkWarps) dock_eval_kernel(LigPtrs L, Doc
   }
 }
 
+// refine_structure (main/main.cpp:131-171): up to 5 quasi-Newton runs on the non_cache field with the out-of-box slope
+// 10, 100, ... until every heavy atom is inside the box (non_cache::within, margin 1e-4); e = max_fl if it never is
+__global__ void __launch_bounds__(32 * kDkWarps) dock_refine_kernel(LigPtrs L, DockField F0, float* __restrict__ confs, int n, float v0,
+                                                                    float v1, float v2, int maxiters, float* __restrict__ e_out,
+                                                                    int* __restrict__ within_out, int* __restrict__ evals_out) {
+  extern __shared__ __align__(16) float dk_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * kDkWarps + warp;
+  if (c >= n) return;
+  WarpWs W;
+  dk_ws_carve(W, dk_smem + (size_t)warp * dk_ws_floats(L.n_atoms, L.n_seg, L.n_pairs), L.n_atoms, L.n_seg, L.n_pairs);
+  const int T = L.n_seg - 1, nx = 7 + T;
+  const float v[3] = {v0, v1, v2};
+  for (int i = lane; i < nx; i += 32) W.x[i] = confs[(size_t)c * nx + i];
+  __syncwarp();
+  DockField F = F0;
+  float slope = 10.f, e = 0.f;
+  int evals = 0, ok = 0;
+  for (int p = 0; p < 5; p++) {
+    F.slope = slope;
+    int ne = 0;
+    e = dk_bfgs(L, F, W, maxiters, v, lane, &ne);
+    evals += ne;
+    dk_set_conf(L, W, W.x, lane);  // m.set(out.c)
+    int inside = 1;
+    for (int i = lane; i < L.n_atoms; i += 32) {
+      if ((int)L.local[i].w < 2) continue;
+      for (int j = 0; j < 3; j++)
+        if (W.coords[3 * i + j] < F.nc_begin[j] - 0.0001f || W.coords[3 * i + j] > F.nc_end[j] + 0.0001f) inside = 0;
+    }
+    ok = __all_sync(0xffffffffu, inside);
+    if (ok) break;
+    slope *= 10.f;
+  }
+  if (lane == 0) { e_out[c] = ok ? e : 3.402823466e+38f; within_out[c] = ok; evals_out[c] = evals; }
+  for (int i = lane; i < nx; i += 32) confs[(size_t)c * nx + i] = W.x[i];
+}
+
 struct McDev { int num_steps, maxiters, num_saved_mins; float temperature, mutation_amplitude, min_rmsd; float hunt_cap[3]; };
 
 // no min-blocks hint: capping the chain kernel at 64 registers measured 17 % slower (621 k vs 750 k MC steps/s)
 __global__ void __launch_bounds__(32 * kDkWarps) dock_mc_kernel(LigPtrs L, DockField F, McDev P, float c1x, float c1y, float c1z, float c2x,
                                                                 float c2y, float c2z, const uint32_t* __restrict__ seeds, int n_chains,
                                                                 float* __restrict__ out_e, float* __restrict__ out_conf,
-                                                                float* __restrict__ out_heavy, int* __restrict__ n_out_arr) {
+                                                                float* __restrict__ out_heavy, int* __restrict__ n_out_arr,
+                                                                float* __restrict__ trace) {
   extern __shared__ __align__(16) float dk_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * kDkWarps + warp;
   if (c >= n_chains) return;
   WarpWs W;
-  dk_ws_carve(W, dk_smem + (size_t)warp * dk_ws_floats(L.n_atoms, L.n_seg), L.n_atoms, L.n_seg);
+  dk_ws_carve(W, dk_smem + (size_t)warp * dk_ws_floats(L.n_atoms, L.n_seg, L.n_pairs), L.n_atoms, L.n_seg, L.n_pairs);
   const int T = L.n_seg - 1, nx = 7 + T, nh = L.n_heavy, S = P.num_saved_mins;
   float* oe = out_e + (size_t)c * S;
   float* oc = out_conf + (size_t)c * S * nx;
@@ -1031,7 +1148,7 @@ __global__ void __launch_bounds__(32 * kDkWarps) dock_mc_kernel(LigPtrs L, DockF
       float u = 0.f;
       if (lane == 0) u = dk_rng_fl(rs, 0, 1);
       u = __shfl_sync(0xffffffffu, u, 0);
-      accept = u < expf((tmp_e - cand_e) / P.temperature);
+      accept = u < (float)exp((double)((tmp_e - cand_e) / P.temperature));  // correctly rounded, like glibc's expf
     }
     if (accept) {
       for (int i = lane; i < nx; i += 32) W.tmp[i] = W.cand[i];
@@ -1048,19 +1165,21 @@ __global__ void __launch_bounds__(32 * kDkWarps) dock_mc_kernel(LigPtrs L, DockF
         int ci = n_out;
         float cr = 3.402823466e+38f;
         for (int o = 0; o < n_out; o++) {
-          float acc = 0.f;
+          // squared coordinate differences lane-parallel into W.forces (free here), then summed in index order
           int hk = 0;
           for (int i = 0; i < L.n_atoms; i++) {  // heavy index = running count (uniform across lanes)
             if ((int)L.local[i].w >= 2) {
               if ((hk & 31) == lane) {
                 const float* q = oh + ((size_t)o * nh + hk) * 3;
                 const float dx = W.coords[3 * i] - q[0], dy = W.coords[3 * i + 1] - q[1], dz = W.coords[3 * i + 2] - q[2];
-                acc += dx * dx + dy * dy + dz * dz;
+                W.forces[3 * hk] = dx * dx; W.forces[3 * hk + 1] = dy * dy; W.forces[3 * hk + 2] = dz * dz;
               }
               hk++;
             }
           }
-          acc = warp_sum(acc);
+          __syncwarp();
+          const float acc = dk_sum_seq(W.forces, 3 * nh);
+          __syncwarp();
           const float r = nh > 0 ? sqrtf(acc / nh) : 0.f;
           if (o == 0 || r < cr) { ci = o; cr = r; }
         }
@@ -1094,6 +1213,7 @@ __global__ void __launch_bounds__(32 * kDkWarps) dock_mc_kernel(LigPtrs L, DockF
         if (tmp_e < best_e) best_e = tmp_e;
       }
     }
+    if (trace && lane == 0) trace[(size_t)c * P.num_steps + step] = tmp_e;  // the chain's current energy after this step
   }
   if (lane == 0) n_out_arr[c] = n_out;
 }
@@ -1111,16 +1231,23 @@ static void make_field(const Vina& v, float slope, DockField& F) {
   for (int t = 0; t < kNumSminaTypes; t++) F.gp.g[t] = v.d_grids[t];
   F.smooth = v.d_smooth; F.n_samples = v.n; F.factor = v.factor; F.slope = slope;
   F.sp = v.use_splines ? v.d_sp : nullptr; F.n_sp = v.n_sp; F.sp_fraction = v.sp_fraction;
+  F.rec = nullptr; F.n_rec = 0;
+  for (int i = 0; i < 3; i++) { F.nc_begin[i] = v.begin[i]; F.nc_end[i] = v.end[i]; }
 }
 static LigPtrs lig_ptrs(const Vina& v) {
   const auto& l = v.lig;
   return LigPtrs{l.n_atoms, l.n_seg, l.n_pairs, l.max_depth, l.n_heavy, l.gyration_radius, l.local, l.atom_seg, l.seg, l.seg_rel_origin,
-                 l.seg_rel_axis, l.pairs, l.adj_off, l.adj};
+                 l.seg_rel_axis, l.pairs, l.adj_off, l.adj, l.child_off, l.child};
 }
-static void check_dock_ready(const Vina& v) {
+// every entry point that evaluates the affinity grids: a ligand atom type without a built grid would dereference a
+// null device pointer, and the resulting illegal-address error is sticky for the whole process
+static void check_dock_ready(const Vina& v, bool needs_grids = true) {
   GB_CHECK(v.lig.n_atoms > 0, "gb_vina_set_ligand has not been called");
+  if (!needs_grids) return;
   GB_CHECK(v.gn[0] > 0, "gb_vina_cache_build has not been called");
-  for (int t = 2; t < kNumSminaTypes; t++) (void)t;
+  for (int t = 2; t < kNumSminaTypes; t++)
+    if (((v.lig.heavy_types >> t) & 1u) && !v.d_grids[t])
+      throw Error(GB_ERR_USAGE, std::string("ligand atom type ") + kSminaNames[t] + " has no affinity grid: pass it to gb_vina_cache_build");
 }
 
 extern "C" {
@@ -1191,23 +1318,62 @@ int gb_vina_set_ligand(gb_vina* h, const gb_ligand_topology* t) {
   {
     std::vector<int> fill(adj_off.begin(), adj_off.end() - 1);
     for (int k = 0; k < t->n_pairs; k++) {  // pair order is kept inside every atom's list
-      adj[fill[t->pair_a[k]]++] = t->pair_b[k];
-      adj[fill[t->pair_b[k]]++] = t->pair_a[k];
+      adj[fill[t->pair_a[k]]++] = t->pair_b[k] | (k << 8) | (1 << 30);
+      adj[fill[t->pair_b[k]]++] = t->pair_a[k] | (k << 8);
     }
   }
   up(&l.adj_off, adj_off, kDkMaxAtoms + 1); up(&l.adj, adj, 2 * max_pairs);
+  std::vector<int> child_off(ns + 1, 0), child(std::max(ns - 1, 1), 0);
+  for (int s2 = 1; s2 < ns; s2++) child_off[t->seg_parent[s2] + 1]++;
+  for (int s2 = 0; s2 < ns; s2++) child_off[s2 + 1] += child_off[s2];
+  {
+    std::vector<int> fill(child_off.begin(), child_off.end() - 1);
+    for (int s2 = 1; s2 < ns; s2++) child[fill[t->seg_parent[s2]]++] = s2;  // ascending within every parent
+  }
+  up(&l.child_off, child_off, kDkMaxSeg + 1); up(&l.child, child, kDkMaxSeg);
+  unsigned heavy = 0;
+  for (int i = 0; i < na; i++)
+    if (t->smina_type[i] >= 2 && t->smina_type[i] < kNumSminaTypes) heavy |= 1u << t->smina_type[i];
+  l.heavy_types = heavy;
   GB_CUDA(cudaStreamSynchronize(v.stream));  // the host vectors above go out of scope
   l.n_atoms = na; l.n_seg = ns; l.n_pairs = t->n_pairs; l.max_depth = max_depth; l.n_heavy = nh; l.gyration_radius = t->gyration_radius;
   GBV_END
 }
 
+// dynamic shared memory of the docking kernels: kDkWarps per-warp workspaces sized by the actual ligand.  A large
+// ligand (96 atoms, 4560 pairs) needs more than the 48 KB a kernel gets by default: opt in once per device.
+static size_t dock_smem_bytes(const Vina& v) {
+  const size_t bytes = (size_t)kDkWarps * dk_ws_floats(v.lig.n_atoms, v.lig.n_seg, v.lig.n_pairs) * sizeof(float);
+  constexpr int kMaxDyn = 160 * 1024;
+  GB_CHECK(bytes <= (size_t)kMaxDyn, "ligand too large for the per-warp docking workspace");
+  static std::mutex mu;
+  static bool done[64] = {};
+  std::lock_guard<std::mutex> lk(mu);
+  if (v.device < 64 && !done[v.device]) {
+    GB_CUDA(cudaFuncSetAttribute(dock_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
+    GB_CUDA(cudaFuncSetAttribute(dock_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
+    GB_CUDA(cudaFuncSetAttribute(dock_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
+    done[v.device] = true;
+  }
+  return bytes;
+}
+// non_cache field: direct receptor sums, box = [bb, be] (grid_dims of the search box, main/main.cpp:474-497)
+static void make_noncache_field(const Vina& v, float slope, const float* bb, const float* be, DockField& F) {
+  GB_CHECK(v.d_rec && v.n_rec > 0, "gb_vina_set_receptor has not been called");
+  GB_CHECK(bb && be, "non_cache needs the box");
+  make_field(v, slope, F);
+  F.rec = v.d_rec; F.n_rec = v.n_rec;
+  for (int i = 0; i < 3; i++) { F.nc_begin[i] = bb[i]; F.nc_end[i] = be[i]; }
+}
+
 static int dock_eval_common(gb_vina* h, const float* confs, int n, const float* vcap, float slope, int mode, int maxiters, float* e,
-                            float* change, float* coords, float* confs_out, int32_t* evals) {
+                            float* change, float* coords, float* confs_out, int32_t* evals, const float* nc_begin = nullptr,
+                            const float* nc_end = nullptr) {
   GBV_BEGIN
   GB_CHECK(h && confs && vcap && e && n >= 0, "bad arguments");
   Vina& v = h->v;
   GB_CUDA(cudaSetDevice(v.device));
-  check_dock_ready(v);
+  check_dock_ready(v, nc_begin == nullptr);
   if (n == 0) return GB_OK;
   const int T = v.lig.n_seg - 1, nx = 7 + T, ng = 6 + T, na = v.lig.n_atoms;
   // workspaces are sized by the MAXIMUM ligand dimensions: in a screen every ligand has another size, and a growing
@@ -1223,8 +1389,9 @@ static int dock_eval_common(gb_vina* h, const float* confs, int n, const float* 
   memcpy(p_conf, confs, (size_t)n * nx * 4);
   GB_CUDA(cudaMemcpyAsync(d_conf, p_conf, (size_t)n * nx * 4, cudaMemcpyHostToDevice, v.stream));
   DockField F;
-  make_field(v, slope, F);
-  const size_t dk_smem_bytes = (size_t)kDkWarps * dk_ws_floats(v.lig.n_atoms, v.lig.n_seg) * sizeof(float);  // <= 40 KB
+  if (nc_begin) make_noncache_field(v, slope, nc_begin, nc_end, F);
+  else make_field(v, slope, F);
+  const size_t dk_smem_bytes = dock_smem_bytes(v);
   dock_eval_kernel<<<(n + kDkWarps - 1) / kDkWarps, 32 * kDkWarps, dk_smem_bytes, v.stream>>>(lig_ptrs(v), F, d_conf, n, vcap[0], vcap[1], vcap[2], d_e, d_g,
                                                                                   d_c, mode, maxiters, d_xo, d_ev);
   GB_CUDA(cudaGetLastError());
@@ -1254,8 +1421,57 @@ int gb_vina_bfgs(gb_vina* h, float* confs, int n, int maxiters, const float* v3,
   return dock_eval_common(h, confs, n, v3, slope, 1, maxiters, e, change, nullptr, confs, n_evals);
 }
 
+int gb_vina_eval_deriv_noncache(gb_vina* h, const float* confs, int n, const float* v3, float slope, const float* box_begin,
+                                const float* box_end, float* e, float* change) {
+  if (!box_begin || !box_end) { gb::set_last_error("gb_vina_eval_deriv_noncache: null box"); return GB_ERR_USAGE; }
+  return dock_eval_common(h, confs, n, v3, slope, 0, 0, e, change, nullptr, nullptr, nullptr, box_begin, box_end);
+}
+
+int gb_vina_refine(gb_vina* h, float* confs, int n, int maxiters, const float* v3, const float* box_begin, const float* box_end,
+                   float* e, int32_t* within, int32_t* n_evals) {
+  GBV_BEGIN
+  GB_CHECK(h && confs && v3 && box_begin && box_end && e && n >= 0, "bad arguments");
+  Vina& v = h->v;
+  GB_CUDA(cudaSetDevice(v.device));
+  check_dock_ready(v, false);
+  if (n == 0) return GB_OK;
+  const int T = v.lig.n_seg - 1, nx = 7 + T;
+  constexpr size_t NXA = 7 + kDkMaxSeg - 1;
+  float* d_conf = v.ws<float>(0, (size_t)n * NXA);
+  float* d_e = v.ws<float>(1, n);
+  int* d_in = v.ws<int>(5, n);
+  int* d_ev = v.ws<int>(6, n);
+  float* p_conf = v.pin<float>(0, (size_t)n * NXA);
+  memcpy(p_conf, confs, (size_t)n * nx * 4);
+  GB_CUDA(cudaMemcpyAsync(d_conf, p_conf, (size_t)n * nx * 4, cudaMemcpyHostToDevice, v.stream));
+  DockField F;
+  make_noncache_field(v, 10.f, box_begin, box_end, F);
+  const size_t smem = dock_smem_bytes(v);
+  dock_refine_kernel<<<(n + kDkWarps - 1) / kDkWarps, 32 * kDkWarps, smem, v.stream>>>(lig_ptrs(v), F, d_conf, n, v3[0], v3[1], v3[2], maxiters,
+                                                                                    d_e, d_in, d_ev);
+  GB_CUDA(cudaGetLastError());
+  float* p_e = v.pin<float>(1, n);
+  int* p_in = v.pin<int>(5, n);
+  int* p_ev = v.pin<int>(6, n);
+  GB_CUDA(cudaMemcpyAsync(p_conf, d_conf, (size_t)n * nx * 4, cudaMemcpyDeviceToHost, v.stream));
+  GB_CUDA(cudaMemcpyAsync(p_e, d_e, (size_t)n * 4, cudaMemcpyDeviceToHost, v.stream));
+  GB_CUDA(cudaMemcpyAsync(p_in, d_in, (size_t)n * 4, cudaMemcpyDeviceToHost, v.stream));
+  GB_CUDA(cudaMemcpyAsync(p_ev, d_ev, (size_t)n * 4, cudaMemcpyDeviceToHost, v.stream));
+  GB_CUDA(cudaStreamSynchronize(v.stream));
+  memcpy(confs, p_conf, (size_t)n * nx * 4);
+  memcpy(e, p_e, (size_t)n * 4);
+  if (within) memcpy(within, p_in, (size_t)n * 4);
+  if (n_evals) memcpy(n_evals, p_ev, (size_t)n * 4);
+  GBV_END
+}
+
 int gb_vina_mc(gb_vina* h, const gb_mc_params* P, const float* corner1, const float* corner2, const uint32_t* seeds, int n_chains,
                float slope, float* out_e, float* out_conf, int32_t* n_out) {
+  return gb_vina_mc_traced(h, P, corner1, corner2, seeds, n_chains, slope, out_e, out_conf, n_out, nullptr);
+}
+
+int gb_vina_mc_traced(gb_vina* h, const gb_mc_params* P, const float* corner1, const float* corner2, const uint32_t* seeds, int n_chains,
+                      float slope, float* out_e, float* out_conf, int32_t* n_out, float* trace) {
   GBV_BEGIN
   GB_CHECK(h && P && corner1 && corner2 && seeds && out_e && out_conf && n_out && n_chains >= 0, "bad arguments");
   GB_CHECK(P->num_saved_mins >= 1 && P->num_saved_mins <= 64, "num_saved_mins out of range (1..64)");
@@ -1278,10 +1494,11 @@ int gb_vina_mc(gb_vina* h, const gb_mc_params* P, const float* corner1, const fl
   DockField F;
   make_field(v, slope, F);
   McDev M{P->num_steps, P->maxiters, S, P->temperature, P->mutation_amplitude, P->min_rmsd, {P->hunt_cap[0], P->hunt_cap[1], P->hunt_cap[2]}};
-  const size_t dk_smem_bytes = (size_t)kDkWarps * dk_ws_floats(v.lig.n_atoms, v.lig.n_seg) * sizeof(float);  // <= 40 KB
+  const size_t dk_smem_bytes = dock_smem_bytes(v);
+  float* d_trace = trace ? v.ws<float>(7, (size_t)n_chains * std::max(P->num_steps, 1)) : nullptr;
   dock_mc_kernel<<<(n_chains + kDkWarps - 1) / kDkWarps, 32 * kDkWarps, dk_smem_bytes, v.stream>>>(lig_ptrs(v), F, M, corner1[0], corner1[1], corner1[2],
                                                                                      corner2[0], corner2[1], corner2[2], d_seeds, n_chains, d_e,
-                                                                                     d_c, d_h, d_n);
+                                                                                     d_c, d_h, d_n, d_trace);
   GB_CUDA(cudaGetLastError());
   float* p_e = v.pin<float>(1, (size_t)n_chains * S);
   float* p_c = v.pin<float>(2, (size_t)n_chains * S * NXA);
@@ -1289,7 +1506,10 @@ int gb_vina_mc(gb_vina* h, const gb_mc_params* P, const float* corner1, const fl
   GB_CUDA(cudaMemcpyAsync(p_e, d_e, (size_t)n_chains * S * 4, cudaMemcpyDeviceToHost, v.stream));
   GB_CUDA(cudaMemcpyAsync(p_c, d_c, (size_t)n_chains * S * nx * 4, cudaMemcpyDeviceToHost, v.stream));
   GB_CUDA(cudaMemcpyAsync(p_n, d_n, (size_t)n_chains * 4, cudaMemcpyDeviceToHost, v.stream));
+  float* p_tr = trace ? v.pin<float>(7, (size_t)n_chains * std::max(P->num_steps, 1)) : nullptr;
+  if (p_tr) GB_CUDA(cudaMemcpyAsync(p_tr, d_trace, (size_t)n_chains * P->num_steps * 4, cudaMemcpyDeviceToHost, v.stream));
   GB_CUDA(cudaStreamSynchronize(v.stream));
+  if (p_tr) memcpy(trace, p_tr, (size_t)n_chains * P->num_steps * 4);
   memcpy(out_e, p_e, (size_t)n_chains * S * 4);
   memcpy(out_conf, p_c, (size_t)n_chains * S * nx * 4);
   memcpy(n_out, p_n, (size_t)n_chains * 4);

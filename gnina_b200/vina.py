@@ -100,17 +100,38 @@ class VinaScorer:
         capi.check(capi.lib().gb_vina_bfgs(self._h, _fp(x), n, maxiters, _fp(v), slope, _fp(e), _fp(g), _ip(ne)))
         return e, x, g, ne
 
+    def eval_deriv_noncache(self, confs, box_begin, box_end, v=(1000, 1000, 1000), slope=1e3):
+        """model::eval_deriv with ig = non_cache (direct receptor sums, lib/non_cache.cpp:126-174) -> (e, change)"""
+        x = np.ascontiguousarray(confs, np.float32).reshape(-1, 7 + self.T)
+        n = len(x)
+        v = np.ascontiguousarray(v, np.float32)
+        b, en = np.ascontiguousarray(box_begin, np.float32), np.ascontiguousarray(box_end, np.float32)
+        e = np.empty(n, np.float32); g = np.empty((n, 6 + self.T), np.float32)
+        capi.check(capi.lib().gb_vina_eval_deriv_noncache(self._h, _fp(x), n, _fp(v), slope, _fp(b), _fp(en), _fp(e), _fp(g)))
+        return e, g
+
+    def refine(self, confs, maxiters, box_begin, box_end, v=(1000, 1000, 1000)):
+        """refine_structure (main/main.cpp:131-171) -> (e, refined confs, within, n_evals)"""
+        x = np.array(confs, np.float32).reshape(-1, 7 + self.T)
+        n = len(x)
+        v = np.ascontiguousarray(v, np.float32)
+        b, en = np.ascontiguousarray(box_begin, np.float32), np.ascontiguousarray(box_end, np.float32)
+        e = np.empty(n, np.float32); ok = np.empty(n, np.int32); ne = np.empty(n, np.int32)
+        capi.check(capi.lib().gb_vina_refine(self._h, _fp(x), n, maxiters, _fp(v), _fp(b), _fp(en), _fp(e), _ip(ok), _ip(ne)))
+        return e, x, ok.astype(bool), ne
+
     def mc(self, seeds, corner1, corner2, num_steps, maxiters, num_saved_mins=20, temperature=1.2, amplitude=2.0, min_rmsd=0.5,
-           hunt_cap=(10, 1.5, 10), slope=1e3):
+           hunt_cap=(10, 1.5, 10), slope=1e3, trace=False):
         seeds = np.ascontiguousarray(seeds, np.uint32)
         n = len(seeds)
         P = capi.McParams(num_steps, maxiters, num_saved_mins, temperature, amplitude, min_rmsd, (C.c_float * 3)(*hunt_cap))
         e = np.zeros((n, num_saved_mins), np.float32); x = np.zeros((n, num_saved_mins, 7 + self.T), np.float32)
         no = np.zeros(n, np.int32)
         c1, c2 = np.ascontiguousarray(corner1, np.float32), np.ascontiguousarray(corner2, np.float32)
-        capi.check(capi.lib().gb_vina_mc(self._h, C.byref(P), _fp(c1), _fp(c2), seeds.ctypes.data_as(C.POINTER(C.c_uint32)), n, slope,
-                                         _fp(e), _fp(x), _ip(no)))
-        return e, x, no
+        tr = np.zeros((n, num_steps), np.float32) if trace else None
+        capi.check(capi.lib().gb_vina_mc_traced(self._h, C.byref(P), _fp(c1), _fp(c2), seeds.ctypes.data_as(C.POINTER(C.c_uint32)), n,
+                                                slope, _fp(e), _fp(x), _ip(no), _fp(tr)))
+        return (e, x, no, tr) if trace else (e, x, no)
 
     def close(self):
         if self._h:

@@ -235,6 +235,23 @@ int gb_vina_bfgs(gb_vina* h, float* confs, int n, int maxiters, const float* v3,
  * RMSD-distinct minima sorted by energy: out_e[n_chains][S], out_conf[n_chains][S][7+T], n_out[n_chains]. */
 int gb_vina_mc(gb_vina* h, const gb_mc_params* params, const float* corner1, const float* corner2, const uint32_t* seeds,
                int n_chains, float slope, float* out_e, float* out_conf, int32_t* n_out);
+/* Same, additionally recording every chain's current energy after each Monte-Carlo step (monte_carlo.cpp:99-148's
+ * `tmp.e`): trace[n_chains][num_steps], nullable.  Test/diagnostic access: chains driven by the same generator must
+ * accept the same moves as the CPU restatement. */
+int gb_vina_mc_traced(gb_vina* h, const gb_mc_params* params, const float* corner1, const float* corner2, const uint32_t* seeds,
+                      int n_chains, float slope, float* out_e, float* out_conf, int32_t* n_out, float* trace);
+/* model::eval_deriv with ig = non_cache (lib/non_cache.cpp:126-174): direct sums over the receptor's heavy atoms (the
+ * reference pre-selects them with an szv_grid, same order) instead of the affinity grids; [box_begin, box_end] is
+ * the grid_dims box whose faces clamp the atom and charge slope x distance outside (check_bounds_deriv, :102-123). */
+int gb_vina_eval_deriv_noncache(gb_vina* h, const float* confs, int n, const float* v3, float slope, const float* box_begin,
+                                const float* box_end, float* e, float* change);
+/* refine_structure (main/main.cpp:131-171) for n conformations at once: up to five quasi-Newton runs
+ * (lib/quasi_newton.cpp:49-83, bfgs with fast_line_search) against non_cache with the out-of-box slope 10, 100, ... until
+ * every heavy atom is inside the box (non_cache::within, margin 1e-4).  confs are refined in place; e[n] = the last
+ * run's energy, or max float when the pose never entered the box (the reference sets out.e = max_fl); within[n],
+ * n_evals[n] nullable.  Needs gb_vina_set_receptor + gb_vina_set_ligand, no cache. */
+int gb_vina_refine(gb_vina* h, float* confs, int n, int maxiters, const float* v3, const float* box_begin, const float* box_end,
+                   float* e, int32_t* within, int32_t* n_evals);
 /* merge_output_containers over the chains' containers (lib/parallel_mc.cpp:165-181 -> add_to_output_container,
  * lib/coords.cpp:43-56, find_closest / rmsd_upper_bound :24-41): chains in order, each chain's minima in order;
  * a pose closer than min_rmsd (RMSD over the n_atoms coordinates given) to a kept one replaces it if better,

@@ -25,7 +25,12 @@ import torch.nn.functional as F
 
 
 def _t(blob, name, dtype):
-    return torch.from_numpy(np.array(blob.tensors[name])).to(dtype)
+    # converted once per (blob, tensor, dtype): a CPU baseline must not re-convert 1.5 MB of weights per call
+    cache = blob.__dict__.setdefault("_torch_cache", {})
+    key = (name, dtype)
+    if key not in cache:
+        cache[key] = torch.from_numpy(np.array(blob.tensors[name])).to(dtype)
+    return cache[key]
 
 
 def features_default2018(blob, x, dtype):

@@ -38,6 +38,7 @@ class DockOracle:
         L.gvo_lig_eval_grid.argtypes = [C.POINTER(_Field), C.POINTER(_Lig), _fp, C.c_float, _fp]; L.gvo_lig_eval_grid.restype = C.c_float
         L.gvo_bfgs.argtypes = [C.POINTER(_Field), C.POINTER(_Lig), _fp, _fp, C.c_int, _fp, C.POINTER(C.c_int)]; L.gvo_bfgs.restype = C.c_float
         L.gvo_mc_run.argtypes = [C.POINTER(_Field), C.POINTER(_Lig), C.POINTER(_McParams), _fp, _fp, C.c_uint32, _fp, _fp]
+        L.gvo_mc_run_traced.argtypes = [C.POINTER(_Field), C.POINTER(_Lig), C.POINTER(_McParams), _fp, _fp, C.c_uint32, _fp, _fp, _fp]
         L.gvo_random_conf.argtypes = [C.POINTER(C.c_uint32), _fp, _fp, C.c_int, _fp]
         self.L = L
         self.keep = []
@@ -119,9 +120,10 @@ class DockOracle:
         return x, s.value
 
     def mc(self, seed, c1, c2, num_steps, maxiters, num_saved_mins=20, temperature=1.2, amplitude=2.0, min_rmsd=0.5,
-           hunt_cap=(10, 1.5, 10)):
+           hunt_cap=(10, 1.5, 10), trace=False):
         P = _McParams(num_steps, maxiters, num_saved_mins, temperature, amplitude, min_rmsd, (C.c_float * 3)(*hunt_cap), self.gr)
         e = np.zeros(num_saved_mins, np.float32); x = np.zeros((num_saved_mins, 7 + self.T), np.float32)
-        n = self.L.gvo_mc_run(C.byref(self.field), C.byref(self.lig), C.byref(P), _f(np.ascontiguousarray(c1, np.float32)),
-                              _f(np.ascontiguousarray(c2, np.float32)), seed, _f(e), _f(x))
-        return e[:n], x[:n]
+        tr = np.zeros(num_steps, np.float32)
+        n = self.L.gvo_mc_run_traced(C.byref(self.field), C.byref(self.lig), C.byref(P), _f(np.ascontiguousarray(c1, np.float32)),
+                                     _f(np.ascontiguousarray(c2, np.float32)), seed, _f(e), _f(x), _f(tr))
+        return (e[:n], x[:n], tr) if trace else (e[:n], x[:n])

@@ -395,8 +395,8 @@ static void mutate_conf(float *x, int T, float amplitude, float gr, uint32_t *s)
 }
 
 /* output container entry: e, conf[7+T], heavy coords.  Returns the number of entries kept (sorted by e). */
-int gvo_mc_run(const gvo_field *F, const gvo_lig *L, const gvo_mc_params *P, const float *corner1, const float *corner2,
-               uint32_t seed, float *out_e, float *out_conf /* [num_saved_mins][7+T] */) {
+int gvo_mc_run_traced(const gvo_field *F, const gvo_lig *L, const gvo_mc_params *P, const float *corner1, const float *corner2,
+                      uint32_t seed, float *out_e, float *out_conf /* [num_saved_mins][7+T] */, float *trace /* [num_steps] or NULL */) {
   const int T = L->n_seg - 1, nx = 7 + T, n = 6 + T, na = L->n_atoms;
   int nh = 0;
   for (int i = 0; i < na; i++) nh += !is_h(L->type[i]);
@@ -449,7 +449,12 @@ int gvo_mc_run(const gvo_field *F, const gvo_lig *L, const gvo_mc_params *P, con
         if (tmp_e < best_e) best_e = tmp_e;
       }
     }
+    if (trace) trace[step] = tmp_e; /* the chain's current energy (monte_carlo.cpp's tmp.e) after this step */
   }
   free(tmp); free(cand); free(g); free(coords); free(oc); free(hv);
   return n_out;
+}
+int gvo_mc_run(const gvo_field *F, const gvo_lig *L, const gvo_mc_params *P, const float *corner1, const float *corner2,
+               uint32_t seed, float *out_e, float *out_conf) {
+  return gvo_mc_run_traced(F, L, P, corner1, corner2, seed, out_e, out_conf, 0);
 }

@@ -29,57 +29,149 @@ def _confs(d, k, seed0=1):
 
 
 def test_eval_deriv_matches_oracle(setup):
+    """north_star: Vina arithmetic within 1e-6.  The device sums follow the reference's association (atom energies in
+    atom order, pair energies in pair order, forces per atom in pair-list order, children folded in ascending order, no
+    FMA contraction, correctly rounded sin/cos), so the only differences left are last-bit differences of sqrtf-free
+    arithmetic: measured 0 .. 2 ulp."""
     v, d, lig = setup
     X = np.concatenate([lig["conf0"][None], _confs(d, 40)])
     for caps in ((1000, 1000, 1000), (10, 1.5, 10)):
         e, g, c = v.eval_deriv(X, caps, coords=True)
         for i, x in enumerate(X):
             er, gr = d.eval_deriv(x, caps)
-            assert abs(e[i] - er) <= 2e-5 * max(1.0, abs(er)), (i, e[i], er)
-            assert np.abs(g[i] - gr).max() <= 2e-4 * max(1.0, np.abs(gr).max())
-            assert np.abs(c[i] - d.coords(x)).max() < 2e-5
+            assert abs(e[i] - er) <= 1e-6 * max(1.0, abs(er)), (i, e[i], er)
+            assert np.abs(g[i] - gr).max() <= 1e-6 * max(1.0, np.abs(gr).max()), (i, np.abs(g[i] - gr).max())
+            assert np.abs(c[i] - d.coords(x)).max() <= 2e-6
+
+
+def test_eval_deriv_is_reproducible(setup):
+    v, d, lig = setup
+    X = _confs(d, 64, seed0=500)
+    e1, g1 = v.eval_deriv(X)
+    e2, g2 = v.eval_deriv(X[::-1].copy())
+    assert np.array_equal(e1, e2[::-1]) and np.array_equal(g1, g2[::-1])
+
+
+def test_noncache_eval_deriv_matches_oracle(setup):
+    """model::eval_deriv with ig = non_cache (lib/non_cache.cpp:126-174): direct receptor sums, box clamp + slope."""
+    v, d, lig = setup
+    from gnina_b200 import synth
+    rx, rt = synth.make_receptor(900, box=34)
+    begin, end = [-5.0] * 3, [5.0] * 3                               # small box: some atoms are clamped
+    X = np.concatenate([lig["conf0"][None], _confs(d, 24, seed0=300)])
+    d.use_noncache(rx, rt)
+    old = (d.field.begin, d.field.end, d.field.slope)
+    try:
+        import ctypes as C
+        b = np.asarray(begin, np.float32); en = np.asarray(end, np.float32)
+        d.field.begin = b.ctypes.data_as(C.POINTER(C.c_float)); d.field.end = en.ctypes.data_as(C.POINTER(C.c_float))
+        for slope in (10.0, 1000.0):
+            d.field.slope = slope
+            e, g = v.eval_deriv_noncache(X, begin, end, slope=slope)
+            for i, x in enumerate(X):
+                er, gr = d.eval_deriv(x)
+                assert abs(e[i] - er) <= 1e-6 * max(1.0, abs(er)), (i, e[i], er)
+                assert np.abs(g[i] - gr).max() <= 1e-6 * max(1.0, np.abs(gr).max())
+    finally:
+        d.field.begin, d.field.end, d.field.slope = old
+        d.use_noncache(None)
+
+
+def test_refine_structure_matches_oracle(setup):
+    """refine_structure (main/main.cpp:131-171): slope escalation 10, 100, ... until the pose is inside the box; the
+    device refines all poses of a ligand in one launch."""
+    v, d, lig = setup
+    from gnina_b200 import synth
+    import ctypes as C
+    rx, rt = synth.make_receptor(900, box=34)
+    begin, end = [-6.0] * 3, [6.0] * 3
+    X = _confs(d, 16, seed0=700)
+    X[:4, :3] += 5.0                                                  # start some poses partly outside the box
+    d.use_noncache(rx, rt)
+    old = (d.field.begin, d.field.end, d.field.slope)
+    try:
+        b = np.asarray(begin, np.float32); en = np.asarray(end, np.float32)
+        d.field.begin = b.ctypes.data_as(C.POINTER(C.c_float)); d.field.end = en.ctypes.data_as(C.POINTER(C.c_float))
+        e, Xo, ok, ne = v.refine(X, 20, begin, end)
+        same = 0
+        for i in range(len(X)):
+            er, xr, ner, okr = d.refine_structure(X[i], 20)
+            assert bool(ok[i]) == okr
+            if not okr:
+                assert e[i] > 1e37                                    # out.e = max_fl
+                continue
+            # identical trajectories: same evaluation count, same final conformation and energy
+            if ne[i] == ner and abs(e[i] - er) <= 1e-5 * max(1.0, abs(er)) and np.abs(Xo[i] - xr).max() < 1e-4:
+                same += 1
+            assert e[i] <= er + 0.05 * abs(er) + 0.5                  # never a worse minimum than the oracle's
+            assert d.within(Xo[i])
+        assert same >= 0.9 * ok.sum()
+    finally:
+        d.field.begin, d.field.end, d.field.slope = old
+        d.use_noncache(None)
 
 
 def test_bfgs_from_identical_starts(setup):
-    """One BFGS iteration (gradient, search direction, line search with up to 10 evaluations, Hessian update) must
-    coincide with the oracle; over many iterations float-order differences inside an evaluation get amplified by the
-    line-search decisions (measured: 100 % identical after 1 iteration, 96 % after 3, 50 % after 12), so long runs are
-    compared on what matters: both are descents of the same quality."""
+    """Same evaluations, same sequential reductions inside BFGS (lib/bfgs.h): the device follows the oracle's trajectory
+    -- same number of line-search evaluations, same accepted steps -- for at least 95 % of the starts over 3 iterations
+    (what is left are last-bit differences in a transcendental function flipping a line-search comparison)."""
     v, d, lig = setup
-    X = _confs(d, 24, seed0=100)
+    X = _confs(d, 48, seed0=100)
     e0, _ = v.eval_deriv(X)
-    for iters, frac in ((1, 0.9), (2, 0.8)):
+    for iters, frac in ((1, 0.98), (3, 0.95), (12, 0.85)):
         e, Xo, g, ne = v.bfgs(X, iters)
         same = 0
         for i in range(len(X)):
             er, xr, gr, ner = d.bfgs(X[i], iters)
-            if iters == 1:   # same number of line-search evaluations, same accepted step, same energy
-                ok = abs(e[i] - er) <= 1e-4 * max(1.0, abs(er)) and ne[i] == ner and np.abs(Xo[i] - xr).max() < 1e-2
-            else:
-                ok = abs(e[i] - er) <= 1e-2 * max(1.0, abs(er))
-            same += ok
-        assert same >= frac * len(X)
+            same += bool(abs(e[i] - er) <= 1e-5 * max(1.0, abs(er)) and ne[i] == ner and np.abs(Xo[i] - xr).max() < 1e-4)
+        assert same >= frac * len(X), (iters, same)
     e, Xo, g, ne = v.bfgs(X, 12)
-    ref = np.array([d.bfgs(x, 12)[0] for x in X])
     for i in range(len(X)):
         assert e[i] <= e0[i] + 1e-4 * max(1.0, abs(e0[i]))                       # never worse than the start
-        assert abs(d.eval_deriv(Xo[i])[0] - e[i]) <= 1e-4 * max(1.0, abs(e[i]))  # returned conf has the returned energy
-    assert np.median(e) <= np.median(ref) + 0.05 * abs(np.median(ref)) + 0.5
+        assert abs(d.eval_deriv(Xo[i])[0] - e[i]) <= 1e-5 * max(1.0, abs(e[i]))  # returned conf has the returned energy
     assert (ne >= 2).all()
 
 
 def test_monte_carlo_chains(setup):
+    """Chain by chain: same xorshift stream, same evaluations -> the device chain must accept the same moves as the oracle
+    chain.  The per-step trace of the chain's current energy is compared; a chain counts as identical when every one of its
+    first K steps agrees (a wrong acceptance rule, mutation or container update shows up within a few steps)."""
     v, d, lig = setup
+    K, steps = 12, 25
     seeds = np.arange(1, 33, dtype=np.uint32) * 7919
-    e, X, n_out = v.mc(seeds, [-4, -4, -4], [4, 4, 4], num_steps=25, maxiters=8, num_saved_mins=6)
+    e, X, n_out, tr = v.mc(seeds, [-4, -4, -4], [4, 4, 4], num_steps=steps, maxiters=8, num_saved_mins=6, trace=True)
     assert (n_out >= 1).all() and (n_out <= 6).all()
-    best_ref = []
+    identical_k, identical_all = 0, 0
+    n_ref = 16
     for c in range(len(seeds)):
         k = n_out[c]
         assert np.all(np.diff(e[c, :k]) >= 0)                                     # sorted container
-        assert abs(d.eval_grid(X[c, 0]) - e[c, 0]) <= 1e-3 * max(1.0, abs(e[c, 0]))  # energies belong to the poses
-        if c < 8:
-            best_ref.append(d.mc(int(seeds[c]), [-4, -4, -4], [4, 4, 4], 25, 8, 6)[0][0])
-    # same generator, same algorithm: chains coincide until float noise flips a decision; compare the search quality
-    # (the synthetic receptor has no pocket, so energies are positive; only the relative quality is meaningful)
-    assert np.median(e[:8, 0]) <= np.median(best_ref) + 0.1 * abs(np.median(best_ref)) + 0.5
+        assert abs(d.eval_grid(X[c, 0]) - e[c, 0]) <= 1e-5 * max(1.0, abs(e[c, 0]))  # energies belong to the poses
+        if c < n_ref:
+            er, xr, trr = d.mc(int(seeds[c]), [-4, -4, -4], [4, 4, 4], steps, 8, 6, trace=True)
+            tol = 1e-5 * np.maximum(1.0, np.abs(trr))
+            agree = np.abs(tr[c] - trr) <= tol
+            identical_k += bool(agree[:K].all())
+            if agree.all():
+                identical_all += 1
+                assert len(er) == k and np.abs(er - e[c, :k]).max() <= 1e-5 * max(1.0, np.abs(er).max())
+    assert identical_k >= 0.9 * n_ref, (identical_k, identical_all)
+    assert identical_all >= 0.6 * n_ref, (identical_k, identical_all)
+
+
+def test_unbuilt_grid_type_is_rejected(setup):
+    """a ligand atom type without an affinity grid must raise instead of dereferencing a null device pointer"""
+    v, d, lig = setup
+    from gnina_b200 import capi
+    lig2 = dict(lig)
+    t = np.array(lig["types"], np.int32).copy()
+    t[0] = 15 if 15 not in set(t.tolist()) else 16                   # Phosphorus / Fluorine: not in the built cache
+    lig2["types"] = t
+    v.set_ligand(lig2)
+    try:
+        with pytest.raises(Exception):
+            v.eval_deriv(lig["conf0"][None])
+    finally:
+        v.set_ligand(lig)
+    e, _ = v.eval_deriv(lig["conf0"][None])                            # the handle is still usable
+    assert np.isfinite(e).all()
