@@ -120,6 +120,34 @@ def _cpu_worker_run(span):
     return float(np.sum(r[0]))
 
 
+def usable_cores():
+    """host cores this process may actually use: the scheduler affinity mask and the cgroup CPU quota both cap it
+    (os.cpu_count() reports the machine, not the container) -> (usable, os.cpu_count(), how)"""
+    total = os.cpu_count() or 1
+    n, how = total, "os.cpu_count"
+    try:
+        a = len(os.sched_getaffinity(0))
+        if a < n:
+            n, how = a, "sched_getaffinity"
+    except (AttributeError, OSError):
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                quota, period = txt[0], float(txt[1])
+            else:
+                quota, period = txt[0], float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota not in ("max", "-1"):
+                q = max(1, int(float(quota) / period))
+                if q < n:
+                    n, how = q, "cgroup cpu quota"
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return n, total, how
+
+
 class CpuPort:
     """The reference's CPU algorithm restated (oracle/): C voxeliser + the same network in torch CPU fp32 ops, the
     receptor re-voxelised for every pose (torch_model.cpp:153-224).  Host usage: W worker processes (spawned, 1 torch
@@ -131,7 +159,7 @@ class CpuPort:
 
     def __init__(self, n_poses, workers=None):
         import tempfile
-        self.cores = os.cpu_count() or 1
+        self.cores, self.machine_cores, self.cores_how = usable_cores()
         self.workers = workers or self.cores
         self.n = n_poses
         rec_xyz, rec_t, lig_xyz, lig_t, offs = make_workload(n_poses, seed=1)
@@ -187,7 +215,7 @@ def run_reference(args, rank, world):
     """Reference arm: the reference's own CPU algorithm (oracle port) on the host cores, bounded sample per step."""
     if rank != 0:
         return
-    cpu = CpuPort(max(args.ref_sample, 64 * (os.cpu_count() or 1)))
+    cpu = CpuPort(max(args.ref_sample, 64 * usable_cores()[0]))
     try:
         batch, pilot = cpu.tune()
         sample = int(max(cpu.workers * batch, min(cpu.n, pilot * args.ref_step_seconds)))
@@ -209,21 +237,28 @@ def run_reference(args, rank, world):
             "config": {"workload": "CNN rescoring: 1 receptor (3000 atoms), synthetic ligand poses, 48^3x28ch "
                                    "crossdock_default2018", "sample_poses_per_step": sample, "batch_per_cnn_call": batch},
             "cpu_baseline": {"value": v, "unit": "poses/s", "cores": cpu.workers, "kind": "port", "sample": desc,
-                             "poses_per_s_per_core": v / cpu.workers},
+                             "poses_per_s_per_core": v / cpu.workers, "machine_cores": cpu.machine_cores,
+                             "cores_from": cpu.cores_how},
             "e2e": {"value": v, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 def cpu_baseline(seconds_budget=12.0):
-    cpu = CpuPort(64 * (os.cpu_count() or 1))
+    cpu = CpuPort(64 * usable_cores()[0])
     try:
         batch, pilot = cpu.tune()
         sample = int(max(cpu.workers * batch, min(cpu.n, pilot * seconds_budget)))
         v = cpu.run(batch, sample)
         other = 32 if batch == 1 else 1
         alt = cpu.run(other, min(sample, cpu.workers * max(4, other)))
+        # one worker alone: what a core does when nothing else competes for memory bandwidth and caches
+        spans = [(0, 4)]
+        t0 = time.perf_counter()
+        cpu.pool(1).map(_cpu_worker_run, spans)
+        single = 4 / (time.perf_counter() - t0)
         return {"value": v, "unit": "poses/s", "cores": cpu.workers, "kind": "port", "sample": cpu.describe(batch, min(sample, cpu.n)),
-                "poses_per_s_per_core": v / cpu.workers, "batch_%d_poses_per_s" % other: alt}
+                "poses_per_s_per_core": v / cpu.workers, "batch_%d_poses_per_s" % other: alt,
+                "single_process_poses_per_s": single, "machine_cores": cpu.machine_cores, "cores_from": cpu.cores_how}
     finally:
         cpu.close()
 

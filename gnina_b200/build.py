@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgnina_b200.so")
-SOURCES = ["gb_model.cu", "gb_grid.cu", "gb_cnn_fp32.cu", "gb_cnn_tc.cu", "gb_vox_tc.cu", "gb_cnn_tc_dense.cu", "gb_cnn_tc_grad.cu", "gb_capi.cu", "gb_vina.cu"]
+SOURCES = ["gb_model.cu", "gb_grid.cu", "gb_cnn_fp32.cu", "gb_cnn_tc.cu", "gb_cnn_tc_fused.cu", "gb_vox_tc.cu", "gb_cnn_tc_dense.cu", "gb_cnn_tc_grad.cu", "gb_capi.cu", "gb_vina.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

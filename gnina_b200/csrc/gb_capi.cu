@@ -136,6 +136,7 @@ struct gb_cnn {
   Fp32Workspace ws32;
   Fp32GradWorkspace ws_grad;
   DevBuf<float> d_dgrid;
+  DevBuf<float> tmp_grad, tmp_rec;   // per-chunk atom gradients of gb_cnn_score_grad
   int n_input_atoms = 0;
   TcWorkspace ws_tc;
   int64_t launches = 0;
@@ -312,10 +313,14 @@ int gb_cnn_clone(const gb_cnn* src, gb_cnn** out) {
   h->max_batch = src->max_batch;
   h->cnn_rotation = src->cnn_rotation;
   h->rotation_seed = src->rotation_seed;
-  gb_cnn* raw = h.release();
-  *out = raw;
-  if (!src->rec_type.empty())
-    return gb_cnn_set_receptor(raw, src->rec_xyz.data(), src->rec_type.data(), (int)src->rec_type.size());
+  h->overlap = src->overlap;
+  h->prof.on = src->prof.on;
+  *out = nullptr;
+  if (!src->rec_type.empty()) {
+    const int rc = gb_cnn_set_receptor(h.get(), src->rec_xyz.data(), src->rec_type.data(), (int)src->rec_type.size());
+    if (rc != GB_OK) return rc;   // the half-built clone is destroyed with h; *out stays null
+  }
+  *out = h.release();
   GB_API_END
 }
 
@@ -609,7 +614,7 @@ int gb_cnn_run_staged(gb_cnn* h) {
         // fill the shared memory / thread slots that are left
         if (h->overlap && gw.started_valid) GB_CUDA(cudaStreamWaitEvent(vs, gw.started[buf ^ 1], 0));
         int kinds = 0;
-        for (int mi : G.model_idx) kinds |= 1 << tc_pool_kind(*h->models[mi]);
+        for (int mi : G.model_idx) kinds |= 1 << tc_grid_kind(*h->models[mi], false);
         h->launches += tc_prepare_grid(pb, gw, buf, kinds, vs, &h->prof);
         GB_CUDA(cudaEventRecord(gw.ready[buf], vs));
         GB_CUDA(cudaStreamWaitEvent(h->stream, gw.ready[buf], 0));
@@ -618,7 +623,7 @@ int gb_cnn_run_staged(gb_cnn* h) {
           const int mi = G.model_idx[k];
           const Model& Mo = *h->models[mi];
           const size_t slot = (size_t)mi * R + r;
-          h->launches += tc_forward(Mo, pb, gw.x0[tc_pool_kind(Mo)][buf], h->ws_tc, h->d_out3.p, h->stream, &h->prof,
+          h->launches += tc_forward(Mo, pb, gw.x0[tc_grid_kind(Mo, false)][buf], h->ws_tc, h->d_out3.p, h->stream, &h->prof,
                                     k + 1 == G.model_idx.size() ? gw.consumed[buf] : nullptr);
           launch_head_post(h->d_out3.p, nb, Mo.skip_softmax, Mo.apply_logistic_loss, h->d_pose.p + slot * n + p0,
                            h->d_aff.p + slot * n + p0, h->d_loss.p + slot * n + p0, h->stream);
@@ -747,7 +752,7 @@ int gb_cnn_score_grad(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, 
   upload_rotations(h);
   bool all_default2018 = true;
   for (Model* m : h->models) {
-    if (m->arch != GB_ARCH_DEFAULT2018 && m->arch != GB_ARCH_DENSE)
+    if (m->arch != GB_ARCH_DEFAULT2018 && m->arch != GB_ARCH_DENSE && m->arch != GB_ARCH_OVERLAP)
       throw Error(GB_ERR_USAGE, "gradient path is implemented for the default2018 and dense families only (model " + m->name + ")");
     all_default2018 &= m->arch == GB_ARCH_DEFAULT2018;
   }
@@ -765,7 +770,10 @@ int gb_cnn_score_grad(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, 
     G.lig_grad.ensure(3 * (size_t)std::max(G.n_staged_atoms, 1));
     GB_CUDA(cudaMemsetAsync(G.lig_grad.p, 0, 3 * (size_t)std::max(G.n_staged_atoms, 1) * sizeof(float), h->stream));
   }
-  DevBuf<float> tmp_grad, tmp_rec;
+  // grow-only members, not locals: this is the per-BFGS-step call of CNN refinement, and a cudaFree per call is a
+  // device-wide synchronisation that stalls every other handle's stream
+  DevBuf<float>& tmp_grad = h->tmp_grad;
+  DevBuf<float>& tmp_rec = h->tmp_rec;
   if (drec_xyz)
     for (auto& Gp : h->groups) {
       GridGroup& G = *Gp;
@@ -793,7 +801,8 @@ int gb_cnn_score_grad(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, 
       }
       for (int mi : G.model_idx) {
         const Model& Mo = *h->models[mi];
-        if (Mo.apply_logistic_loss || Mo.skip_softmax)
+        // the overlay test model IS a logistic-loss model (loss = -log out[1], no softmax): its backward kernel handles that
+        if ((Mo.apply_logistic_loss || Mo.skip_softmax) && Mo.arch != GB_ARCH_OVERLAP)
           throw Error(GB_ERR_USAGE, "gradient of apply_logistic_loss / skip_softmax models is not implemented");
         if (fast) {
           h->launches += tc_forward(Mo, pb, G.tc_grid.x0[0][0], h->ws_tc, h->d_out3.p, h->stream, &h->prof, nullptr, true);

@@ -289,11 +289,54 @@ static thread_local Profiler* t_prof = nullptr;
 static Profiler* g_prof_tls() { return t_prof; }
 
 // ---------------------------------------------------------------------------------------------------------
+// GB_ARCH_OVERLAP: the graph of test/gnina/data/overlap.pt (read with torch.jit.load(...).code):
+//   prot = x[:, 0] * x[:, 1];  ave = avg_pool3d(prot, 48).flatten(1);  ave = where(ave > 0, ave, 1e-20)
+//   return (hstack([zeros, ave]), zeros)        -> metadata: skip_softmax, apply_logistic_loss: score = ave, loss = -log ave
+// One block per pose; the backward kernel writes d loss / d grid = -(1 / ave) * d ave / d grid (zero where the
+// `where` took the constant branch).
+__global__ void __launch_bounds__(256) overlap_forward_kernel(const float* __restrict__ grid, int vol, float* __restrict__ out3) {
+  __shared__ double red[8];
+  const float* rec = grid + (size_t)blockIdx.x * 2 * vol;
+  const float* lig = rec + vol;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < vol; i += 256) acc += (double)(rec[i] * lig[i]);
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; w++) t += red[w];
+    const float ave = (float)(t / vol);
+    out3[3 * blockIdx.x] = 0.f;
+    out3[3 * blockIdx.x + 1] = ave > 0.f ? ave : 1e-20f;
+    out3[3 * blockIdx.x + 2] = 0.f;
+  }
+}
+__global__ void overlap_backward_kernel(const float* __restrict__ grid, int vol, const float* __restrict__ out3,
+                                        float* __restrict__ dgrid) {
+  const int p = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= vol) return;
+  const float ave = out3[3 * p + 1];
+  const float coef = ave > 1e-20f ? -1.f / (ave * (float)vol) : 0.f;   // d(-log ave)/d ave * d ave / d prot
+  const float* rec = grid + (size_t)p * 2 * vol;
+  float* d = dgrid + (size_t)p * 2 * vol;
+  d[i] = coef * rec[vol + i];
+  d[vol + i] = coef * rec[i];
+}
+static int overlap_forward(const Model& m, const float* grid, int B, float* out3, cudaStream_t s) {
+  GB_CHECK(m.n_channels == 2, "overlap model: 2 channels");
+  const int vol = m.npts * m.npts * m.npts;
+  overlap_forward_kernel<<<B, 256, 0, s>>>(grid, vol, out3);
+  return 1;
+}
+
 int forward_fp32(const Model& m, const float* grid, int B, Fp32Workspace& ws, float* out3, cudaStream_t s,
                  Profiler* prof) {
   int launches = 0;
   const int C = m.n_channels;
   t_prof = prof;
+  if (m.arch == GB_ARCH_OVERLAP) return overlap_forward(m, grid, B, out3, s);
   GB_CHECK(m.npts == 48, "CNN graphs expect a 48^3 grid");
   auto conv = [&](const std::string& k) -> const ConvF32& {
     auto it = m.convs.find(k);
@@ -457,6 +500,12 @@ static int forward_backward_dense_fp32(const Model& m, const float* grid, int B,
 
 int forward_backward_fp32(const Model& m, const float* grid, int B, Fp32GradWorkspace& ws, float* out3, float* dgrid,
                           cudaStream_t s, Profiler* prof) {
+  if (m.arch == GB_ARCH_OVERLAP) {
+    const int vol = m.npts * m.npts * m.npts;
+    overlap_forward(m, grid, B, out3, s);
+    overlap_backward_kernel<<<dim3((vol + 255) / 256, B), 256, 0, s>>>(grid, vol, out3, dgrid);
+    return 2;
+  }
   if (m.arch != GB_ARCH_DEFAULT2018 && m.arch != GB_ARCH_DENSE)
     throw Error(GB_ERR_USAGE, "gradient path is implemented for the default2018 and dense families only (model " + m.name + ")");
   GB_CHECK(m.npts == 48, "CNN graphs expect a 48^3 grid");

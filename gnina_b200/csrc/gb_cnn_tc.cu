@@ -117,6 +117,14 @@ bool tc_supported(const Model& m) {
   return (m.arch == GB_ARCH_DEFAULT2018 || m.arch == GB_ARCH_DENSE) && m.n_channels == 28 && m.npts == 48;
 }
 int tc_pool_kind(const Model& m) { return m.arch == GB_ARCH_DEFAULT2018 ? 0 : 1; }
+bool tc_fused_enabled() {
+  static const bool on = !(getenv("GB_TC_FUSED") && atoi(getenv("GB_TC_FUSED")) == 0);
+  return on;
+}
+int tc_grid_kind(const Model& m, bool keep_activations) {
+  if (m.arch == GB_ARCH_DEFAULT2018 && !keep_activations && tc_fused_enabled()) return 2;
+  return tc_pool_kind(m);
+}
 
 std::mutex& tc_init_mutex() {
   static std::mutex mu;
@@ -157,7 +165,12 @@ void TcWorkspace::ensure(int i, size_t bytes) {
   if (buf[i]) cudaFree(buf[i]);
   buf[i] = nullptr;
   GB_CUDA(cudaMalloc(&buf[i], bytes));
-  GB_CUDA(cudaMemset(buf[i], 0, bytes));  // zero borders of the padded layouts; interiors are rewritten per chunk
+  // zero borders of the padded layouts; interiors are rewritten per chunk.  The memset runs on the legacy default stream,
+  // the kernels on the handle's NON-BLOCKING stream, which does not wait for it: without the synchronise below the memset
+  // could land after the first kernels had written the buffer (seen as a rare wrong score on a handle's first call
+  // when the allocator returned recycled memory, r2d).  Growth is rare; cudaMalloc / cudaFree synchronise anyway.
+  GB_CUDA(cudaMemset(buf[i], 0, bytes));
+  GB_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
   cap[i] = bytes;
 }
 TcWorkspace::~TcWorkspace() {
@@ -841,12 +854,17 @@ int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspa
     Y3 = reinterpret_cast<__half*>(ws.buf[7]);
   }
   const int pw_blocks = 148 * 8;
-  {
+  const bool fused = tc_grid_kind(m, keep_activations) == 2;
+  if (fused) {
+    // unit1_conv + ReLU + unit2_conv + ReLU + avg-pool in one kernel (x0 is in the row-group layout): straight to X2
+    ProfScope ps(prof, "tc_conv1_pw2_pool_fused", s);
+    launch_conv1_pw2_pool(tw->conv1, tw->pw2.w, tw->pw2.bias, x0, make_fused_x0_layout(), X2, L3, nb, s);
+  } else {
     ProfScope ps(prof, "tc_conv1_3x3x3_28x32_d24", s);
     launch_conv_tc<32, 24>(tw->conv1, L1, x0, Y, nb, s);
   }
   if (x0_consumed) GB_CUDA(cudaEventRecord(x0_consumed, s));
-  {
+  if (!fused) {
     ProfScope ps(prof, "tc_pw2_pool", s);
     static const int pw_variant = getenv("GB_TC_PW") ? atoi(getenv("GB_TC_PW")) : 2;
     if (pw_variant == 2)
@@ -876,8 +894,8 @@ int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspa
     ProfScope ps(prof, "tc_fc_heads", s);
     fc_heads_f16_kernel<<<nb, 256, 0, s>>>(Y5, tw->fcw, tw->fcb, out3);
   }
-  launches += 6;
-  t_debug.ptr[0] = x0v;      t_debug.bytes[0] = act_bytes(L1, nb);
+  launches += fused ? 5 : 6;
+  t_debug.ptr[0] = x0v;      t_debug.bytes[0] = act_bytes(fused ? make_fused_x0_layout() : L1, nb);
   t_debug.ptr[1] = Y3;       t_debug.bytes[1] = (size_t)nb * 1728 * 64 * sizeof(__half);  // holds Y3 after the pass
   t_debug.ptr[2] = X2;       t_debug.bytes[2] = act_bytes(L3, nb);
   t_debug.ptr[3] = X4;       t_debug.bytes[3] = act_bytes(L5, nb);

@@ -1,0 +1,388 @@
+// Scoring path of the default2018 family: unit1_conv (3x3x3, 28(32) -> 32 @ 24^3) + ReLU + unit2_conv (1x1x1, 32 -> 32)
+// + ReLU + 2x2x2 average pool in ONE tcgen05 kernel (N1 of SURVEY.md §8a; the TorchScript graph executed at
+// lib/torch_model.cpp:185).  The 3x3x3 convolution is the implicit GEMM of gb_cnn_tc.cu (three dx taps stacked into
+// N = 96, plane-marching TMEM ring); what is new is the tile shape and everything after the accumulator:
+//
+//   M tile = 16 rows (y) x 8 (z) of one x plane, instead of 128 consecutive flat positions.  The rows of a group of
+//   8 poses are stacked (row R = q * 26 + yp, 26 = 24 + 2 zero rows per pose) and tiles start at ODD rows, so the two
+//   rows and the two columns of every 2x2 pooling window always lie in the same tile -- in fact in the same warp of
+//   the epilogue (partners are lanes ^1 and ^8).  In shared memory the A slab is a dense [chunk][18 rows][10 z][8 ch]
+//   box: MMA row group g (8 consecutive z) sits at g * 160 B, so the UMMA descriptor simply uses SBO = 160 B and a tap
+//   (dy, dz) is again a constant start-address offset, (1+dy) * 10 + (1+dz) elements.  The box is fetched by ONE
+//   tensor-map TMA instruction per input plane (cp.async.bulk.tensor.5d, zero fill outside the tensor): this is the
+//   "TMA im2col" of the north star -- the halo is part of the box, nothing is materialised.  Valid rows: 24 of every 26
+//   (92 %; the flat tiling had 576 / 640 = 90 %).
+//
+//   Epilogue, per output plane: TMEM -> registers, + bias, ReLU, fp16 -> this warp's 32 rows of a shared-memory tile
+//   (channels-last, 16-byte chunks XOR-swizzled so that both the row-wise stores and the fragment loads are conflict
+//   free).  After the second plane of a pair (x odd, x even) the warp holds 2 x 4 x 8 fine voxels = 8 complete pooling
+//   windows and runs unit2_conv on them with mma.sync straight from shared memory (the formulation of
+//   pointwise_pool_mma_kernel: weights resident as A fragments, 16 voxels as the B operand with the reduction index
+//   permuted so that a lane's 16-byte load IS its fragment, bias + ReLU on the accumulators, the 2x2x2 average as a second
+//   MMA against a constant 1/8 matrix) and writes the 12^3 input of unit3_conv.  No warp outside the epilogue is involved
+//   (a first version issued the pointwise GEMM as a second tcgen05.mma from the MMA warp: it queued behind up to three
+//   planes of convolution MMAs and the epilogue ran at the queue's latency -- 62 ms instead of 8 per 10 k poses, r2c).
+//   Y1 (0.88 MB per pose) never exists in HBM and the pointwise kernel is gone (round 1: 11 % of the step).
+//
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue.
+#include <cstdlib>
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <mutex>
+#include "gb_ptx.cuh"
+#include "gb_tc.h"
+
+namespace gb {
+
+namespace {
+
+constexpr int kG = kFusedGroup;       // poses per row group
+constexpr int kD = 24, kP = 26;
+constexpr int kRows = kG * kP;        // 208 stacked rows per group
+constexpr int kRowTiles = (kRows + 15) / 16;   // 13
+constexpr int kZBlocks = 3;
+constexpr int kSlabRows = 18, kSlabZ = 10;
+constexpr int kChunkBytes = kSlabRows * kSlabZ * 16;   // 2880: one 8-channel chunk of the slab = LBO
+constexpr int kStageBytes = 4 * kChunkBytes;           // 11520
+constexpr int kStages = 3;
+constexpr int kWBytes = 9 * 4 * 96 * 16;               // 55296
+constexpr int kYBytes = 2 * 128 * 64;                  // 16384  [plane parity][row][32 ch fp16], chunks swizzled
+constexpr int kR = 8;                                  // TMEM ring: 8 plane slots x 32 columns
+constexpr int kOffStage = kWBytes;
+constexpr int kOffY = kOffStage + kStages * kStageBytes;
+constexpr int kOffBar = kOffY + kYBytes;
+constexpr int kSmemTotal = kOffBar + 512;
+
+struct FusedParams {
+  const uint4* wp;     // conv1: [9][4][96] x 16 B (make_conv_tc)
+  const float* bias1;  // [32]
+  const __half* w2;    // pointwise: [co][ci] row-major fp16
+  const float* bias2;  // [32]
+  __half* xout;        // X2: chunk-planar D = 12 (make_layout(12, Gn, 32))
+  int out_lp, out_G, n_poses, n_groups;
+};
+
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__constant__ uint32_t c_fused_off[18][2];  // per (tap, k step): A start offset, B row offset (16-byte units)
+
+__global__ void __launch_bounds__(192) conv1_pw2_pool_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_w = smem;
+  uint8_t* s_stage = smem + kOffStage;
+  uint8_t* s_y = smem + kOffY;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* full = bars;                  // [kStages]
+  uint64_t* empty = bars + kStages;       // [kStages]
+  uint64_t* accf = bars + 2 * kStages;    // [kR]  conv plane complete
+  uint64_t* acce = accf + kR;             // [kR]  conv plane drained (128 arrivals)
+  uint64_t* wbar = acce + kR;             // weights landed
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(wbar + 1);
+  float* s_bias = reinterpret_cast<float*>(s_tmem + 2);   // bias1[32]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = p.n_groups * kRowTiles * kZBlocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; s++) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kR; s++) { ptx::mbar_init(&accf[s], 1); ptx::mbar_init(&acce[s], 128); }
+    ptx::mbar_init(wbar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (threadIdx.x < 32) s_bias[threadIdx.x] = p.bias1[threadIdx.x];
+  if (warp == 1) {
+    ptx::tmem_alloc(s_tmem, kR * 32);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===== producer: weights once (bulk copies), then one tensor-map TMA box per input plane =====
+    if (ptx::elect_one()) {
+      ptx::prefetch_tmap(&tmap);
+      ptx::mbar_expect_tx(wbar, kWBytes);
+      for (int t9 = 0; t9 < 9; t9++)
+        ptx::bulk_g2s(s_w + t9 * (kWBytes / 9), reinterpret_cast<const uint8_t*>(p.wp) + t9 * (kWBytes / 9), kWBytes / 9, wbar);
+    }
+    __syncwarp();
+    uint32_t gp = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int zb = item % kZBlocks, k = (item / kZBlocks) % kRowTiles, g = item / (kZBlocks * kRowTiles);
+      for (int it = 0; it < kD; it++, gp++) {
+        const uint32_t st = gp % kStages, ph = (gp / kStages) & 1;
+        ptx::mbar_wait(&empty[st], ph ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(&full[st], kStageBytes);
+          // box = {10 z x 8 ch, 18 rows, 4 chunks, 1 plane} at (z0 - 1, R0 - 1) = (8 zb, 16 k); rows past the group are zero-filled
+          ptx::tma_load_4d(s_stage + (size_t)st * kStageBytes, &tmap, 64 * zb, 16 * k, 0, g * kD + it, &full[st]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t kDescHiA = (uint32_t)(kSlabZ * 16 >> 4) | (1u << 14);   // SBO = 160 B between 8-row groups
+    constexpr uint32_t kDescHiB = (128u >> 4) | (1u << 14);
+    const uint32_t a_lo_fixed = ((uint32_t)(kChunkBytes >> 4)) << 16;         // LBO = 2880 B between K chunks
+    const uint32_t b_lo_base = (96u << 16) | (ptx::smem_u32(s_w) >> 4);
+    auto wait_service = [&](uint64_t* bar, uint32_t parity) { ptx::mbar_wait(bar, parity); };
+    wait_service(wbar, 0);
+    uint32_t gp = 0, go_base = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, go_base += kD) {
+      for (int it = 0; it < kD; it++, gp++) {
+        const int xi = it + 1;
+        const uint32_t st = gp % kStages, ph = (gp / kStages) & 1;
+        const int lo = xi > 1 ? xi - 1 : 1, hi = xi < kD ? xi + 1 : kD;
+        const int fresh_lo = xi == 1 ? 1 : xi + 1;  // output planes >= fresh_lo get their first contribution now
+        for (int xo = fresh_lo; xo <= hi; xo++) {
+          const uint32_t go = go_base + xo - 1, u = go / kR;
+          if (u > 0) wait_service(&acce[go % kR], (u - 1) & 1);
+        }
+        uint32_t r_tm[2], r_boff[2], r_idesc[2];
+        int nr = 0;
+        {
+          int rs = lo;
+          for (int xo = lo; xo <= hi; xo++) {
+            const uint32_t sl = (go_base + xo - 1) % kR;
+            if (xo == hi || sl == kR - 1) {
+              r_tm[nr] = tmem_base + ((go_base + rs - 1) % kR) * 32u;
+              r_boff[nr] = (uint32_t)(rs - (xi - 1)) * 32u;
+              r_idesc[nr] = ptx::idesc_f16(128, 32 * (xo - rs + 1));
+              nr++;
+              rs = xo + 1;
+            }
+          }
+        }
+        wait_service(&full[st], ph);
+        ptx::tc_fence_after();
+        const uint32_t a_lo_base = a_lo_fixed | (ptx::smem_u32(s_stage + (size_t)st * kStageBytes) >> 4);
+        if (ptx::elect_one()) {
+          // first MMA of the plane (tap 0, k step 0): fresh output planes are overwritten (accumulate = 0), one N = 32 MMA each
+          for (int xo = lo; xo <= hi; xo++) {
+            const uint32_t tm = tmem_base + ((go_base + xo - 1) % kR) * 32u;
+            const uint32_t bl = b_lo_base + (uint32_t)(xo - (xi - 1)) * 32u;
+            if (xo >= fresh_lo) ptx::mma_f16_ss_lohi<0>(tm, a_lo_base, kDescHiA, bl, kDescHiB, ptx::idesc_f16(128, 32));
+            else ptx::mma_f16_ss_lohi<1>(tm, a_lo_base, kDescHiA, bl, kDescHiB, ptx::idesc_f16(128, 32));
+          }
+          // the issue loop stays inside ONE elected region (ptxas then keeps UTCHMMA on the uniform datapath without
+          // re-electing per instruction; r2d: electing per MMA cost ~1 ms per 10 k poses)
+          if (nr == 1) {
+            const uint32_t tm0 = r_tm[0], id0 = r_idesc[0], bl0 = b_lo_base + r_boff[0];
+#pragma unroll 1
+            for (int m = 1; m < 18; m++) ptx::mma_f16_ss_lohi<1>(tm0, a_lo_base + c_fused_off[m][0], kDescHiA, bl0 + c_fused_off[m][1], kDescHiB, id0);
+          } else {
+            const uint32_t tm0 = r_tm[0], id0 = r_idesc[0], bl0 = b_lo_base + r_boff[0];
+            const uint32_t tm1 = r_tm[1], id1 = r_idesc[1], bl1 = b_lo_base + r_boff[1];
+#pragma unroll 1
+            for (int m = 1; m < 18; m++) {
+              const uint32_t oa = c_fused_off[m][0], ob = c_fused_off[m][1];
+              ptx::mma_f16_ss_lohi<1>(tm0, a_lo_base + oa, kDescHiA, bl0 + ob, kDescHiB, id0);
+              ptx::mma_f16_ss_lohi<1>(tm1, a_lo_base + oa, kDescHiA, bl1 + ob, kDescHiB, id1);
+            }
+          }
+          ptx::tc_commit(&empty[st]);                                     // slab consumed
+          if (xi >= 2) ptx::tc_commit(&accf[(go_base + xi - 2) % kR]);      // output plane xi - 1 is complete
+          if (xi == kD) ptx::tc_commit(&accf[(go_base + kD - 1) % kR]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== epilogue =====
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    const uint32_t tm_lane = (uint32_t)(q4 * 32) << 16;
+    constexpr int Dn = 12, Pn = 14;
+    // --- pointwise weights as mma.sync A fragments (rows = output channels), reduction index permuted: k-slots
+    // (2t, 2t+1, 2t+8, 2t+9) of k step s carry input channels 8t + 4s + (0..3); see pointwise_pool_mma_kernel ---
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t af[2][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+      for (int ks = 0; ks < 2; ks++) {
+        const __half* w0 = p.w2 + (size_t)(mt * 16 + g) * 32 + 8 * t + 4 * ks;
+        const __half* w1 = w0 + (size_t)8 * 32;
+        af[mt][ks][0] = *reinterpret_cast<const uint32_t*>(w0);
+        af[mt][ks][1] = *reinterpret_cast<const uint32_t*>(w1);
+        af[mt][ks][2] = *reinterpret_cast<const uint32_t*>(w0 + 2);
+        af[mt][ks][3] = *reinterpret_cast<const uint32_t*>(w1 + 2);
+      }
+    float bs[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++) { bs[mt][0] = p.bias2[mt * 16 + g]; bs[mt][1] = p.bias2[mt * 16 + g + 8]; }
+    const uint32_t eighth2 = 0x30003000u;  // half2(0.125, 0.125): pooling matrix, column n = g
+    const uint32_t sb0 = g == 0 ? eighth2 : 0u, sb1 = g == 1 ? eighth2 : 0u;
+    // fine voxel of this lane inside a 2x2x2 window: (di, dj, dk) = bits of g (plane, tile row, z)
+    const int di = (g >> 2) & 1, dj = (g >> 1) & 1, dk = g & 1;
+    uint32_t go = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int zb = item % kZBlocks, k = (item / kZBlocks) % kRowTiles, grp = item / (kZBlocks * kRowTiles);
+      for (int xo = 1; xo <= kD; xo++, go++) {
+        const uint32_t slot = go % kR, u = go / kR;
+        // ---- conv accumulator -> bias, ReLU, fp16 -> this thread's row of the shared tile of plane parity (xo - 1) & 1 ----
+        ptx::mbar_wait(&accf[slot], u & 1);
+        ptx::tc_fence_after();
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_base + tm_lane + slot * 32u, v);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&acce[slot]);
+        uint8_t* yrow_ptr = s_y + ((xo - 1) & 1) * 8192 + row * 64;
+        const int sw = (row >> 1) & 3;
+#pragma unroll
+        for (int c8 = 0; c8 < 4; c8++) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const int c = c8 * 8 + 2 * e;
+            const float f0 = fmaxf(__uint_as_float(v[c]) + s_bias[c], 0.f);
+            const float f1 = fmaxf(__uint_as_float(v[c + 1]) + s_bias[c + 1], 0.f);
+            const __half2 h = __floats2half2_rn(f0, f1);
+            w[e] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(yrow_ptr + ((c8 ^ sw) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        if (xo & 1) continue;
+        __syncwarp();
+        // ---- both planes of the pair are staged: unit2_conv + ReLU + 2x2x2 average on this warp's 8 pooling windows ----
+        const int xq = (xo >> 1) - 1;
+#pragma unroll
+        for (int jy = 0; jy < 2; jy++) {
+          // tile rows of the window pair (jy): R, R + 1 with R = 16 k + 1 + 4 q4 + 2 jy (odd)
+          const int R = 16 * k + 1 + 4 * q4 + 2 * jy;
+          const int q = R / kP, yp = R - q * kP;
+          const int pose = grp * kG + q;
+          const bool ok = q < kG && pose < p.n_poses && yp >= 1 && yp <= kD;   // uniform across the warp
+          const int yo = (yp - 1) >> 1;
+#pragma unroll
+          for (int jz = 0; jz < 2; jz++) {
+            // pooled voxels A = (jy, 2 jz), B = (jy, 2 jz + 1); this lane's fine voxel of A: tile row 2 jy + dj, z 4 jz + dk
+            const int ra = q4 * 32 + (2 * jy + dj) * 8 + 4 * jz + dk;
+            const uint8_t* pa_ = s_y + di * 8192 + ra * 64;
+            const uint4 va = *reinterpret_cast<const uint4*>(pa_ + ((t ^ ((ra >> 1) & 3)) * 16));
+            const int rb = ra + 2;
+            const uint4 vb = *reinterpret_cast<const uint4*>(pa_ + 128 + ((t ^ ((rb >> 1) & 3)) * 16));
+            const uint32_t* pa = reinterpret_cast<const uint32_t*>(&va);
+            const uint32_t* pb = reinterpret_cast<const uint32_t*>(&vb);
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) {
+              float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int ks = 0; ks < 2; ks++) {
+                mma_16816(ca, af[mt][ks], pa[2 * ks], pa[2 * ks + 1]);
+                mma_16816(cb, af[mt][ks], pb[2 * ks], pb[2 * ks + 1]);
+              }
+              uint32_t a2[4];
+              {
+                const __half2 h0 = __floats2half2_rn(fmaxf(ca[0] + bs[mt][0], 0.f), fmaxf(ca[1] + bs[mt][0], 0.f));
+                const __half2 h1 = __floats2half2_rn(fmaxf(ca[2] + bs[mt][1], 0.f), fmaxf(ca[3] + bs[mt][1], 0.f));
+                const __half2 h2 = __floats2half2_rn(fmaxf(cb[0] + bs[mt][0], 0.f), fmaxf(cb[1] + bs[mt][0], 0.f));
+                const __half2 h3 = __floats2half2_rn(fmaxf(cb[2] + bs[mt][1], 0.f), fmaxf(cb[3] + bs[mt][1], 0.f));
+                a2[0] = *reinterpret_cast<const uint32_t*>(&h0); a2[1] = *reinterpret_cast<const uint32_t*>(&h1);
+                a2[2] = *reinterpret_cast<const uint32_t*>(&h2); a2[3] = *reinterpret_cast<const uint32_t*>(&h3);
+              }
+              float pz[4] = {0.f, 0.f, 0.f, 0.f};
+              mma_16816(pz, a2, sb0, sb1);
+              // lanes t == 0: pz[0], pz[1] = channel mt*16+g of pooled A, B; pz[2], pz[3] = channel mt*16+8+g
+              if (t == 0 && ok) {
+                const int zo = 4 * zb + 2 * jz;
+                const size_t pos = (size_t)(pose % p.out_G) * Pn * Pn + (size_t)(yo + 1) * Pn + (zo + 1);
+                __half* o0 = p.xout + ((((size_t)(pose / p.out_G) * Dn + xq) * 4 + 2 * mt) * p.out_lp + pos) * 8 + g;
+                o0[0] = __float2half(pz[0]);
+                o0[8] = __float2half(pz[1]);
+                o0[(size_t)p.out_lp * 8] = __float2half(pz[2]);
+                o0[(size_t)p.out_lp * 8 + 8] = __float2half(pz[3]);
+              }
+            }
+          }
+        }
+        __syncwarp();   // the next odd plane overwrites this warp's rows of parity 0
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kR * 32);
+  }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no direct libcuda symbol dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+}  // namespace
+
+ActLayout make_fused_x0_layout() { return make_layout(kD, kG, 32); }
+
+void launch_conv1_pw2_pool(const ConvTc& conv1, const __half* w2, const float* bias2, const uint4* x0, const ActLayout& L0, uint4* x2,
+                           const ActLayout& L2, int n_poses, cudaStream_t s) {
+  GB_CHECK(conv1.cin == 32 && conv1.cout == 32 && L0.D == kD && L0.G == kG && L2.D == 12, "fused conv1 shape");
+  EncodeTiledFn enc = encode_tiled_fn();
+  GB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available in this driver");
+  const int n_groups = (n_poses + kG - 1) / kG;
+  int dev = 0;
+  GB_CUDA(cudaGetDevice(&dev));
+  static std::mutex mu;
+  static bool attr_set[64] = {};
+  static int n_sm[64] = {};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    GB_CHECK(dev < 64, "device index");
+    if (!attr_set[dev]) {
+      GB_CUDA(cudaFuncSetAttribute(conv1_pw2_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+      uint32_t h[18][2];
+      for (int t9 = 0; t9 < 9; t9++)
+        for (int ks = 0; ks < 2; ks++) {
+          h[t9 * 2 + ks][0] = (uint32_t)((t9 / 3) * kSlabZ + (t9 % 3) + 2 * ks * (kChunkBytes >> 4));
+          h[t9 * 2 + ks][1] = (uint32_t)((t9 * 4 + 2 * ks) * 96);
+        }
+      GB_CUDA(cudaMemcpyToSymbol(c_fused_off, h, sizeof(h)));
+      GB_CUDA(cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev));
+      attr_set[dev] = true;
+    }
+  }
+  // x0 as a 4-D tensor {26 z x 8 channels (contiguous: one 416-byte row), 208 rows, 4 chunks, planes x groups}; a box row is
+  // 10 z x 8 channels = 160 contiguous bytes (a 5-D map with the 16-byte channel group as its own dimension made the TMA
+  // unit fetch 720 16-byte pieces per plane)
+  CUtensorMap tmap;
+  const cuuint64_t gdim[4] = {(cuuint64_t)kP * 8, (cuuint64_t)kRows, 4, (cuuint64_t)kD * n_groups};
+  const cuuint64_t gstr[3] = {(cuuint64_t)kP * 16, (cuuint64_t)L0.Lp * 16, (cuuint64_t)4 * L0.Lp * 16};
+  const cuuint32_t box[4] = {kSlabZ * 8, kSlabRows, 4, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<uint4*>(x0), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
+  FusedParams p;
+  p.wp = conv1.wp; p.bias1 = conv1.bias; p.w2 = w2; p.bias2 = bias2; p.xout = reinterpret_cast<__half*>(x2); p.out_lp = L2.Lp; p.out_G = L2.G;
+  p.n_poses = n_poses; p.n_groups = n_groups;
+  const int n_items = n_groups * kRowTiles * kZBlocks;
+  static const int persist = getenv("GB_TC_FUSED_PERSIST") ? atoi(getenv("GB_TC_FUSED_PERSIST")) : 0;
+  int grid = persist > 0 ? std::min(n_items, n_sm[dev] * persist) : n_items;
+  conv1_pw2_pool_kernel<<<grid, 192, kSmemTotal, s>>>(tmap, p);
+}
+
+}  // namespace gb

@@ -120,7 +120,7 @@ Model* load_model_from_memory(const void* data, size_t n, int device, const std:
   off += (8 - off % 8) % 8;
   m->arch = (int)arch;
   m->apply_logistic_loss = flags & 1; m->skip_softmax = flags & 2;
-  if (arch < 1 || arch > 3) throw Error(GB_ERR_USAGE, bad);
+  if (arch < 1 || arch > 4) throw Error(GB_ERR_USAGE, bad);
   const size_t entry = 96 + 4 + 24 + 4 + 8 + 8;
   if (off + entry * nt > n) throw Error(GB_ERR_USAGE, bad);
   for (uint32_t i = 0; i < nt; i++) {
@@ -128,7 +128,15 @@ Model* load_model_from_memory(const void* data, size_t n, int device, const std:
     std::string tn(e, strnlen(e, 96));
     uint32_t ndim, dims[6]; uint64_t toff, nelem;
     memcpy(&ndim, e + 96, 4); memcpy(dims, e + 100, 24); memcpy(&toff, e + 128, 8); memcpy(&nelem, e + 136, 8);
-    if (ndim > 6 || toff + nelem * 4 > n) throw Error(GB_ERR_USAGE, bad);
+    // a user-supplied blob (--cnn_models) is untrusted input: the tensor must lie inside the file (overflow-safe), be
+    // float-aligned, and its dimensions must multiply to its element count
+    if (ndim > 6 || toff > n || toff % 4 != 0 || nelem > (n - toff) / 4) throw Error(GB_ERR_USAGE, bad);
+    uint64_t prod = 1;
+    for (uint32_t d = 0; d < ndim; d++) {
+      if (dims[d] == 0 || dims[d] > (1u << 28) || prod > (1ull << 40)) throw Error(GB_ERR_USAGE, bad);
+      prod *= dims[d];
+    }
+    if (prod != nelem) throw Error(GB_ERR_USAGE, bad);
     HostTensor t;
     for (uint32_t d = 0; d < ndim; d++) t.shape.push_back((int)dims[d]);
     t.data = (const float*)(p + toff); t.nelem = nelem;
@@ -140,6 +148,10 @@ Model* load_model_from_memory(const void* data, size_t n, int device, const std:
   m->npts = (int)std::lround(m->dimension / m->resolution) + 1;
 
   GB_CUDA(cudaSetDevice(device));
+  if (m->arch == GB_ARCH_OVERLAP) {  // no parameters: channel 0 = receptor, channel 1 = ligand
+    if (m->n_channels != 2) throw Error(GB_ERR_USAGE, bad);
+    return m.release();
+  }
   if (m->arch == GB_ARCH_DEFAULT2018) {
     for (const char* k : {"unit1_conv", "unit2_conv", "unit3_conv", "unit4_conv", "unit5_conv"}) add_conv(*m, k);
   } else if (m->arch == GB_ARCH_DEFAULT2017) {

@@ -15,12 +15,16 @@ struct TcPoseBatch {
   float resolution, dimension;
   const float* rot = nullptr;  // [n_poses][9] rotation about the grid centre (G3), or null; offset to the chunk like centers
 };
+constexpr int kFusedGroup = 8;  // poses per row group of the fused conv1 kernel's input layout (gb_cnn_tc_fused.cu)
 
 // Pooled input grids, double buffered so that the (CUDA-core) voxeliser of chunk i+1 can run on an auxiliary
 // stream while the (tensor-core) network of chunk i runs on the main stream; shared by the models of a grid group.
 struct TcGridWorkspace {
-  void* x0[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [pool kind: 0 avg, 1 max][double buffer]
-  size_t cap[2][2] = {{0, 0}, {0, 0}};
+  // [kind][double buffer]; kind 0 = average pool, one pose per group (gradient path, gb_cnn_tc_grad.cu), 1 = max pool
+  // (dense family), 2 = average pool in row groups of kFusedGroup poses (scoring path, gb_cnn_tc_fused.cu).  The layouts
+  // differ in where their zero borders are, so every kind owns its buffers.
+  void* x0[3][2] = {};
+  size_t cap[3][2] = {};
   cudaEvent_t ready[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr}, started[2] = {nullptr, nullptr};
   bool started_valid = false;
   bool consumed_valid[2] = {false, false};
@@ -47,6 +51,9 @@ bool tc_supported(const Model& m);
 int tc_prepare_grid(const TcPoseBatch& pb, TcGridWorkspace& gw, int buf, int kinds_mask, cudaStream_t s,
                     Profiler* prof = nullptr);
 int tc_pool_kind(const Model& m);  // 0 avg, 1 max
+// buffer kind tc_forward expects for model m: tc_pool_kind, or 2 when the fused scoring kernel will run
+int tc_grid_kind(const Model& m, bool keep_activations);
+bool tc_fused_enabled();
 // network forward on the pooled grid x0 -> out3 [n_poses][3]; records x0_consumed (if non-null) once x0 has been
 // read for the last time; returns the number of kernel launches
 int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0, TcWorkspace& ws, float* out3, cudaStream_t s,
@@ -97,6 +104,10 @@ void launch_conv_tc_any(int cin, int D, const ConvTc& c, const ActLayout& L, con
 void launch_conv_tc_32_24_planar(const ConvTc& c, const uint4* xin, uint4* xout, int out_c8tot, int out_c8off, int out_lp,
                                  int n_poses, cudaStream_t s);
 void tc_debug_set(int i, const void* p, size_t bytes);
+// fused scoring kernel (gb_cnn_tc_fused.cu): x0 in the row-group layout -> X2 (input of unit3_conv)
+ActLayout make_fused_x0_layout();
+void launch_conv1_pw2_pool(const ConvTc& conv1, const __half* w2, const float* bias2, const uint4* x0, const ActLayout& L0, uint4* x2,
+                           const ActLayout& L2, int n_poses, cudaStream_t s);
 
 // test-only access to the buffers of the most recent tc_forward on this thread: 0 x0, 1 y(3), 2 x2, 3 x4, 4 y5
 const void* tc_debug_buffer(int i, size_t* bytes);

@@ -24,6 +24,7 @@
 //           channel chunks of its voxel with four 32-bit shared loads each.
 #include <cstdlib>
 #include <cuda_fp16.h>
+#include "gb_ptx.cuh"
 #include "gb_tc.h"
 
 namespace gb {
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(512, kMinBlocks) voxelize_pool_f16_kernel(cons
                                                                 const int* __restrict__ list_ch,
                                                                 const int* __restrict__ list_n, int cap,
                                                                 const float* __restrict__ centers, float resolution,
-                                                                float dimension, uint4* __restrict__ x0, int Lp) {
+                                                                float dimension, uint4* __restrict__ x0, int Lp, int G) {
   // the pooled grid of every supported model is 24^3 x 32 channels (48^3 fine voxels, 28 channels padded): compile-time
   // dimensions keep the index arithmetic free of integer divisions (ncu r2a: the prologue was 11 % of the instructions)
   constexpr int D = 24, P = D + 2, C8 = 4, tiles = D / 8;
@@ -260,14 +261,22 @@ __global__ void __launch_bounds__(512, kMinBlocks) voxelize_pool_f16_kernel(cons
     if (base + kVoxChunk < n) __syncthreads();  // the next chunk overwrites the staged atoms
   }
   if (cur >= 0) flush();
-  // every thread emits ITS OWN voxel (it is the only writer of words [.][pv] of S.out): no block-wide barrier, a warp
-  // that is done leaves (ncu r2a: 18 % of the stall samples sat on the barrier in front of a staged, transposed output)
+  // Output.  Global rows are z-contiguous (8 voxels = 128 B per chunk), but a warp owns only 2 z: the four warps that share
+  // (wx, wy) -- a 4 x 4 x 8 sub-block, 16 full z rows -- synchronise among themselves (named barrier, 128 threads) and
+  // each thread emits one voxel of the sub-block, z fastest.  (r2a: the block-wide barrier in front of a tile-wide
+  // transposed output held 18 % of the stall samples; r2b: per-thread own-voxel stores without any barrier were slower
+  // still -- 32-byte runs.)
+  ptx::named_bar_sync(1 + (warp & 3), 128);
   {
-    const int x = tx * 8 + px, y = ty * 8 + py, z = tz * 8 + pz;
-    uint4* dst = x0 + (((size_t)p * D + x) * C8) * Lp + (size_t)(y + 1) * P + (z + 1);
+    const int gt = (warp >> 2) * 32 + lane;
+    const int qz = gt & 7, qy = wy * 4 + ((gt >> 3) & 3), qx = wx * 4 + (gt >> 5);
+    const int qv = (qx * 8 + qy) * 8 + qz;
+    const int x = tx * 8 + qx, y = ty * 8 + qy, z = tz * 8 + qz;
+    // group of G poses: [group][x][chunk][q P^2 + (y+1) P + (z+1)]
+    uint4* dst = x0 + (((size_t)(p / G) * D + x) * C8) * Lp + (size_t)(p % G) * P * P + (size_t)(y + 1) * P + (z + 1);
 #pragma unroll
     for (int c8 = 0; c8 < C8; c8++) {
-      const uint32_t* w = S.out + (c8 * 4) * 512 + pv;
+      const uint32_t* w = S.out + (c8 * 4) * 512 + qv;
       dst[(size_t)c8 * Lp] = make_uint4(w[0], w[512], w[1024], w[1536]);
     }
   }
@@ -292,7 +301,7 @@ TcGridWorkspace::~TcGridWorkspace() {
 
 int tc_prepare_grid(const TcPoseBatch& pb, TcGridWorkspace& gw, int buf, int kinds_mask, cudaStream_t s, Profiler* prof) {
   const int nb = pb.n_poses;
-  const ActLayout L1 = make_layout(24, 1, 32);
+  const ActLayout L1 = make_layout(24, 1, 32), LF = make_fused_x0_layout();
   const int cap = std::max(1, pb.n_rec + pb.max_pose_atoms);
   // allocation sizes have a floor (64 poses, 128 ligand atoms) so that small batches of varying size -- the kept
   // poses of one docked ligand -- never re-allocate: cudaFree / cudaMemset synchronise the whole device and would
@@ -315,8 +324,8 @@ int tc_prepare_grid(const TcPoseBatch& pb, TcGridWorkspace& gw, int buf, int kin
     GB_CUDA(cudaMalloc(&gw.list_n, (size_t)nb_alloc * sizeof(int)));
     gw.listn_cap = nb_alloc;
   }
-  const size_t need0 = act_bytes(L1, nb_alloc);
-  for (int kind = 0; kind < 2; kind++) {
+  for (int kind = 0; kind < 3; kind++) {
+    const size_t need0 = act_bytes(kind == 2 ? LF : L1, nb_alloc);
     if (!(kinds_mask & (1 << kind)) || gw.cap[kind][buf] >= need0) continue;
     // growing the pooled-grid buffer: only kernels of THIS handle (its two streams) can still be using the old one
     GB_CUDA(cudaStreamSynchronize(s));
@@ -359,13 +368,19 @@ int tc_prepare_grid(const TcPoseBatch& pb, TcGridWorkspace& gw, int buf, int kin
   if (kinds_mask & 1) {
     ProfScope ps(prof, "tc_voxelize_pool", s);
     kern(false)<<<dim3(27, nb), 512, sizeof(VoxSmem), s>>>(gw.list_xyzr, gw.list_ch, gw.list_n, cap, pb.centers, pb.resolution,
-                                                          pb.dimension, reinterpret_cast<uint4*>(gw.x0[0][buf]), L1.Lp);
+                                                          pb.dimension, reinterpret_cast<uint4*>(gw.x0[0][buf]), L1.Lp, 1);
+    launches++;
+  }
+  if (kinds_mask & 4) {
+    ProfScope ps(prof, "tc_voxelize_pool", s);
+    kern(false)<<<dim3(27, nb), 512, sizeof(VoxSmem), s>>>(gw.list_xyzr, gw.list_ch, gw.list_n, cap, pb.centers, pb.resolution,
+                                                          pb.dimension, reinterpret_cast<uint4*>(gw.x0[2][buf]), LF.Lp, LF.G);
     launches++;
   }
   if (kinds_mask & 2) {
     ProfScope ps(prof, "tc_voxelize_maxpool", s);
     kern(true)<<<dim3(27, nb), 512, sizeof(VoxSmem), s>>>(gw.list_xyzr, gw.list_ch, gw.list_n, cap, pb.centers, pb.resolution,
-                                                         pb.dimension, reinterpret_cast<uint4*>(gw.x0[1][buf]), L1.Lp);
+                                                         pb.dimension, reinterpret_cast<uint4*>(gw.x0[1][buf]), L1.Lp, 1);
     launches++;
   }
   return launches;

@@ -2,11 +2,14 @@
 device kernels — everything between "ligand topology in" and "ranked poses out":
 
   cache::populate (V4)  ->  parallel_mc = all chains in one launch (V10/V11)  ->  merge_output_containers
-  (lib/parallel_mc.cpp:165-181, min_rmsd forced to 2)  ->  CNN rescoring of every kept pose (get_cnn_info,
-  main.cpp:195-207, one batch call)  ->  final Vina energy (V12)  ->  sort by CNNscore (main.cpp:349-360)
-  ->  remove_redundant (main.cpp:182-192)  ->  first num_modes.
+  (lib/parallel_mc.cpp:165-181, min_rmsd forced to 2)  ->  refine_structure of every kept pose (main.cpp:131-171:
+  quasi-Newton on non_cache with slope escalation, all poses in one launch)  ->  CNN rescoring of the refined poses
+  (get_cnn_info, main.cpp:195-207, one batch call)  ->  final Vina energy (V12)  ->  sort by CNNscore
+  (main.cpp:349-360)  ->  remove_redundant (main.cpp:182-192)  ->  first num_modes.
 
-Not here (DESIGN.md "next"): refine_structure's non-cache BFGS between the search and the rescoring.
+RMSDs are taken over the heavy atoms (get_heavy_atom_movable_coords), the search uses the docking branch's Monte-Carlo
+settings (min_rmsd 1, hunt_cap (10,10,10), main.cpp:458-460), and the torsion penalty uses conf_independent_inputs'
+num_tors (lib/terms.cpp:74-106) when the ligand dict carries it.
 Host logic (containers, sorting) is numpy; nothing in this module imports the CPU oracle."""
 import numpy as np
 
@@ -88,9 +91,12 @@ def reference_num_steps(n_movable_atoms, n_dof):
     return int(70 * 3 * (50 + n_movable_atoms + 10 * n_dof) // 2)
 
 
+MAX_FL = 3.4028234663852886e+38
+
+
 def dock_ligand(vina, cnn, lig, corner1, corner2, exhaustiveness=8, seed=1, num_steps=None, maxiters=None,
                 num_saved_mins=50, num_modes=9, out_min_rmsd=1.0, sort_order="cnnscore", grid_spacing=0.375,
-                grid_margin=4.0):
+                grid_margin=4.0, refine=True):
     """vina: VinaScorer with the receptor set; cnn: CNNScorer with the same receptor set; lig: ligand topology dict.
     -> list of dicts (conf, coords, e = final Vina affinity, search_e, cnnscore, cnnaffinity, cnnvariance), ranked."""
     types = np.asarray(lig["types"], np.int32)
@@ -108,22 +114,36 @@ def dock_ligand(vina, cnn, lig, corner1, corner2, exhaustiveness=8, seed=1, num_
         maxiters = int((25 + len(types)) // 3)                     # ssd_par.evals, main.cpp:454
     rs = np.random.RandomState(seed)
     seeds = rs.randint(1, 1000000, size=exhaustiveness).astype(np.uint32)   # random_int(0, 1000000, generator)
-    e, X, n_out = vina.mc(seeds, corner1, corner2, num_steps=num_steps, maxiters=maxiters, num_saved_mins=num_saved_mins)
+    # the docking branch's Monte-Carlo settings (main/main.cpp:458,460), not the monte_carlo ctor defaults
+    e, X, n_out = vina.mc(seeds, corner1, corner2, num_steps=num_steps, maxiters=maxiters, num_saved_mins=num_saved_mins,
+                          min_rmsd=1.0, hunt_cap=(10, 10, 10))
     flat = X.reshape(-1, 7 + T)
     _, _, coords = vina.eval_deriv(flat, coords=True)
+    heavy = np.flatnonzero(types > 1)                               # get_heavy_atom_movable_coords
     coords = coords.reshape(len(seeds), num_saved_mins, len(types), 3)
-    merged = merge_chains_native(e, X, coords, n_out, num_saved_mins)
+    merged = merge_chains_native(e, X, coords[:, :, heavy], n_out, num_saved_mins)
     if not merged:
         return []
+    confs = np.stack([m["conf"] for m in merged])
+    if refine:  # refine_structure on every kept pose, cap = authentic_v, minparm.maxiters = ssd_par.evals
+        e_ref, confs, ok, _ = vina.refine(confs, maxiters, corner1, corner2)
+    else:
+        e_ref, ok = np.array([m["e"] for m in merged], np.float32), np.ones(len(merged), bool)
+    _, _, all_coords = vina.eval_deriv(confs, coords=True)
     # one CNN batch call and one exact-scoring call over all kept poses
-    xyz = np.concatenate([m["coords"] for m in merged]).astype(np.float32)
+    xyz = all_coords.reshape(-1, 3).astype(np.float32)
     offs = (np.arange(len(merged) + 1) * len(types)).astype(np.int32)
     tt = np.tile(types, len(merged))
     sc, aff, _, var = cnn.score_batch(xyz, tt, offs)
-    _, affin = vina.score_exact(xyz, tt, offs, num_tors=np.full(len(merged), T, np.float32))
+    num_tors = float(lig.get("num_tors", T))                        # conf_independent_inputs (lib/terms.cpp:74-106)
+    _, affin = vina.score_exact(xyz, tt, offs, num_tors=np.full(len(merged), num_tors, np.float32))
     for i, m in enumerate(merged):
         m["search_e"] = m["e"]
-        m["e"] = float(affin[i]); m["cnnscore"] = float(sc[i]); m["cnnaffinity"] = float(aff[i]); m["cnnvariance"] = float(var[i])
+        m["conf"] = confs[i]; m["all_coords"] = all_coords[i]; m["coords"] = all_coords[i][heavy]
+        m["refined_e"] = float(e_ref[i]); m["within"] = bool(ok[i])
+        # a pose that never entered the box keeps e = max_fl (main.cpp:163-164, :335)
+        m["e"] = float(affin[i]) if ok[i] else MAX_FL
+        m["cnnscore"] = float(sc[i]); m["cnnaffinity"] = float(aff[i]); m["cnnvariance"] = float(var[i])
     key = {"cnnscore": lambda o: -o["cnnscore"], "cnnaffinity": lambda o: -o["cnnaffinity"], "energy": lambda o: o["e"]}[sort_order]
     merged.sort(key=key)
     return remove_redundant(merged, out_min_rmsd)[:num_modes]

@@ -8,7 +8,7 @@ import os
 import struct
 import numpy as np
 
-ARCH_NAMES = {1: "default2018", 2: "dense", 3: "default2017"}
+ARCH_NAMES = {1: "default2018", 2: "dense", 3: "default2017", 4: "overlap"}
 WEIGHTS_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "weights")
 
 

@@ -20,13 +20,33 @@ class usage_error(ValueError):
     """reference: usage_error (gninasrc/lib/common.h) — bad model name / file"""
 
 
+# the reference's built-in model table (gninasrc/lib/torch_models.h = gninasrc/lib/models/*.pt), '.' -> '_'
+REFERENCE_MODELS = tuple(sorted(n.replace(".", "_") for n in """
+all_default_to_default_1.3_1 all_default_to_default_1.3_2 all_default_to_default_1.3_3 crossdock_default2018
+crossdock_default2018_1.3 crossdock_default2018_1.3_1 crossdock_default2018_1.3_2 crossdock_default2018_1.3_3
+crossdock_default2018_1.3_4 crossdock_default2018_1 crossdock_default2018_2 crossdock_default2018_3 crossdock_default2018_4
+crossdock_default2018_KD_1 crossdock_default2018_KD_2 crossdock_default2018_KD_3 crossdock_default2018_KD_4
+crossdock_default2018_KD_5 default2017 dense dense_1.3 dense_1.3_1 dense_1.3_2 dense_1.3_3 dense_1.3_4 dense_1.3_PT_KD
+dense_1.3_PT_KD_1 dense_1.3_PT_KD_2 dense_1.3_PT_KD_3 dense_1.3_PT_KD_4 dense_1.3_PT_KD_def2018 dense_1.3_PT_KD_def2018_1
+dense_1.3_PT_KD_def2018_2 dense_1.3_PT_KD_def2018_3 dense_1.3_PT_KD_def2018_4 dense_1 dense_2 dense_3 dense_4
+general_default2018 general_default2018_1 general_default2018_2 general_default2018_3 general_default2018_4
+general_default2018_KD_1 general_default2018_KD_2 general_default2018_KD_3 general_default2018_KD_4 general_default2018_KD_5
+redock_default2018 redock_default2018_1.3 redock_default2018_1.3_1 redock_default2018_1.3_2 redock_default2018_1.3_3
+redock_default2018_1.3_4 redock_default2018_1 redock_default2018_2 redock_default2018_3 redock_default2018_4
+redock_default2018_KD_1 redock_default2018_KD_2 redock_default2018_KD_3 redock_default2018_KD_4 redock_default2018_KD_5
+""".split()))
+
+
 def builtin_models():
-    """names of the built-in models, like builtin_torch_models() (gninasrc/lib/torch_models.h)"""
+    """names of the packaged built-in models (a subset of REFERENCE_MODELS until every blob is extracted with
+    tools/extract_models.py), like builtin_torch_models() (gninasrc/lib/torch_models.h)"""
     return sorted(f[:-4] for f in os.listdir(WEIGHTS_DIR) if f.endswith(".gbw"))
 
 
-def expand_model_names(names):
-    """cnn_torch_scorer.cpp:28-62: default ensemble, 'fast', 'default1.0', '<prefix>_ensemble'."""
+def expand_model_names(names, check=True):
+    """cnn_torch_scorer.cpp:28-62: default ensemble, 'fast', 'default1.0', '<prefix>_ensemble'.  An ensemble expands over
+    the REFERENCE's model table, never over "whatever is packaged": a missing member is an error, not a smaller
+    ensemble with different scores."""
     names = [n.replace(".", "_") if n not in ("default1.0",) else n for n in names]
     if len(names) == 0:
         names = ["dense_1_3", "dense_1_3_PT_KD_3", "crossdock_default2018_KD_4"]
@@ -36,13 +56,19 @@ def expand_model_names(names):
         elif names[0] == "default1.0":
             names = ["dense", "general_default2018_3", "dense_3", "crossdock_default2018", "redock_default2018_2"]
     out = []
-    avail = builtin_models()
     for n in names:
         if n.endswith("_ensemble"):
             prefix = n[: -len("_ensemble")]
-            out += [a for a in avail if a.startswith(prefix)]
+            out += [a for a in REFERENCE_MODELS if a.startswith(prefix)]   # std::map order = sorted
         else:
             out.append(n)
+    if not check:
+        return out
+    avail = set(builtin_models())
+    missing = [n for n in out if n in REFERENCE_MODELS and n not in avail]
+    if missing:
+        raise usage_error("built-in model(s) not packaged in gnina_b200/weights: %s (run tools/extract_models.py on the "
+                         "reference's gninasrc/lib/models)" % ", ".join(missing))
     return out
 
 

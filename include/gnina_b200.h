@@ -30,7 +30,9 @@ typedef enum {
 typedef struct gb_model gb_model; /* one CNN: weights + typing + grid metadata  (TorchModel<isCUDA>, lib/torch_model.h:22-47) */
 typedef struct gb_cnn gb_cnn;     /* an ensemble scorer                          (CNNTorchScorer<isCUDA>, lib/cnn_torch_scorer.h:25-57) */
 
-enum { GB_ARCH_DEFAULT2018 = 1, GB_ARCH_DENSE = 2, GB_ARCH_DEFAULT2017 = 3 };
+/* GB_ARCH_OVERLAP: the parameter-free "overlay" graph of the reference's own minimisation test
+ * (test/gnina/data/overlap.pt, test/gnina/test_min.py): out = (0, mean(rec * lig)), loss = -log out[1]. */
+enum { GB_ARCH_DEFAULT2018 = 1, GB_ARCH_DENSE = 2, GB_ARCH_DEFAULT2017 = 3, GB_ARCH_OVERLAP = 4 };
 enum { GB_PRECISION_FP32 = 0, /* validation mode: fp32 CUDA-core kernels, reference-layout fp32 grid      */
        GB_PRECISION_FP16_TC = 1 /* fast mode: fused pooled fp16 grid + tcgen05 fp16 convs, fp32 accumulate */ };
 

@@ -91,6 +91,13 @@ def forward_logits(blob, grid, dtype=torch.float32, grad=False):
     """grid [B,C,N,N,N] (numpy or tensor) -> (log-softmax pose [B,2], affinity [B]) exactly as the TorchScript
     module returns them.  grad=True keeps the autograd graph (grid may then be a leaf tensor requiring grad)."""
     x = grid.to(dtype) if torch.is_tensor(grid) else torch.as_tensor(np.asarray(grid)).to(dtype)
+    if blob.arch == "overlap":
+        # test/gnina/data/overlap.pt (the model of test_min.py), restated from its TorchScript code: out[0] is NOT a
+        # log-softmax here -- the metadata sets skip_softmax and apply_logistic_loss
+        with torch.set_grad_enabled(grad):
+            ave = F.avg_pool3d(x[:, 0] * x[:, 1], x.shape[-1]).flatten(1)
+            ave = torch.where(ave > 0, ave, torch.full_like(ave, 1e-20))
+            return torch.hstack([torch.zeros_like(ave), ave]), torch.zeros(x.shape[0], dtype=dtype)
     with torch.set_grad_enabled(grad):
         f = FEATURES[blob.arch](blob, x, dtype)
         pose = F.linear(f, _t(blob, "pose_output.weight", dtype), _t(blob, "pose_output.bias", dtype))

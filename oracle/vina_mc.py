@@ -61,6 +61,21 @@ class DockOracle:
         self.na = len(lig["types"])
         self.gr = lig["gyration_radius"]
 
+    def set_box(self, begin=None, end=None, slope=None):
+        """replace the box [begin, end] (check_bounds / grid origin) and the out-of-box slope; None restores the
+        construction-time values.  (Never save `self.field.begin` and assign it back: a ctypes pointer FIELD accessed
+        through the structure aliases the structure's memory, so the 'saved' value changes with the field.)"""
+        if not hasattr(self, "_box0"):
+            self._box0 = (C.cast(self.field.begin, C.c_void_p).value, C.cast(self.field.end, C.c_void_p).value, self.field.slope)
+        if begin is None:
+            self.field.begin = C.cast(self._box0[0], _fp); self.field.end = C.cast(self._box0[1], _fp); self.field.slope = self._box0[2]
+            return
+        b = np.ascontiguousarray(begin, np.float32); e = np.ascontiguousarray(end, np.float32)
+        self.keep += [b, e]
+        self.field.begin, self.field.end = _f(b), _f(e)
+        if slope is not None:
+            self.field.slope = slope
+
     def use_noncache(self, rec_xyz=None, rec_types=None):
         """non_cache (lib/non_cache.cpp): sum the intermolecular term over the receptor atoms directly instead of the
         cache grids; begin/end become the search box of check_bounds.  None switches back to the cache."""

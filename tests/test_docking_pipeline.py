@@ -64,15 +64,21 @@ def test_dock_and_rescore_pipeline():
     assert 1 <= len(poses) <= 9
     sc = [p["cnnscore"] for p in poses]
     assert sc == sorted(sc, reverse=True) and all(0.0 <= s <= 1.0 for s in sc)       # ranked by CNNscore
+    n_heavy = int((np.asarray(lig["types"]) > 1).sum())
     for i, p in enumerate(poses):
-        assert p["coords"].shape == (len(lig["types"]), 3) and np.isfinite(p["e"]) and np.isfinite(p["cnnaffinity"])
+        assert p["all_coords"].shape == (len(lig["types"]), 3) and p["coords"].shape == (n_heavy, 3)   # RMSDs: heavy atoms
+        assert np.isfinite(p["cnnaffinity"]) and (np.isfinite(p["e"]) or not p["within"])
         for q in poses[:i]:
             assert docking.rmsd_upper_bound(p["coords"], q["coords"]) > 1.0              # out_min_rmsd
-        # the scores attached to a pose are those of its coordinates
-        one = c.score_batch(p["coords"], lig["types"], [0, len(lig["types"])])
+        # the scores attached to a pose are those of its (refined) coordinates
+        one = c.score_batch(p["all_coords"], lig["types"], [0, len(lig["types"])])
         assert abs(one[0][0] - p["cnnscore"]) < 1e-6
-        e_aff = v.score_exact(p["coords"], lig["types"], [0, len(lig["types"])], num_tors=np.array([v.T], np.float32))[1][0]
-        assert abs(e_aff - p["e"]) < 1e-5 * max(1.0, abs(p["e"]))
+        if p["within"]:
+            e_aff = v.score_exact(p["all_coords"], lig["types"], [0, len(lig["types"])], num_tors=np.array([v.T], np.float32))[1][0]
+            assert abs(e_aff - p["e"]) < 1e-5 * max(1.0, abs(p["e"]))
+            # refine_structure left every heavy atom inside the search box (non_cache::within)
+            hv = p["coords"]
+            assert (hv >= -6 - 1e-3).all() and (hv <= 6 + 1e-3).all()
     again = docking.dock_ligand(v, c, lig, [-6, -6, -6], [6, 6, 6], exhaustiveness=8, seed=3, num_steps=60, num_saved_mins=20)
     assert [p["cnnscore"] for p in again] == sc                                            # same seed, same result
 

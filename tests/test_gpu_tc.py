@@ -49,7 +49,8 @@ def test_fast_intermediates_match_oracle(kat):
     s = _fast([name])
     s.set_receptor(kat["rec_xyz"], kat["rec_types"])
     s.score_batch(lx, lt, offs)
-    x0, border = tl.decode_chunk_planar(s.debug_read("x0"), n, 24, 1, 32)
+    # scoring path: the pooled grid is laid out in row groups of 8 poses for the fused unit1_conv kernel
+    x0, border = tl.decode_chunk_planar(s.debug_read("x0"), n, 24, 8, 32)
     assert border == 0.0 and np.abs(x0[:, 28:]).max() == 0.0
     assert np.abs(x0[:, :28] - ref["x0"]).max() < 2e-3          # fp16 rounding of densities <= ~3
     x2, border = tl.decode_chunk_planar(s.debug_read("x2"), n, 12, 2, 32)
@@ -143,6 +144,36 @@ def test_full_size_batch_properties():
     ref = v.score_batch(lx.reshape(n, na, 3)[sub].reshape(-1, 3), lt[:48 * na], offs[:49])
     assert np.abs(ref[0] - a[0][sub]).max() < TOL_SCORE and np.abs(ref[1] - a[1][sub]).max() < TOL_AFF
     assert np.isfinite(a[0]).all() and (a[0] >= 0).all() and (a[0] <= 1).all()
+    # ... and with the CPU oracle (fp64 run of the same graph on the oracle's grids) on poses spread over the batch,
+    # including the last row group (10000 = 1250 groups of 8) and the last chunk
+    import torch
+    from gnina_b200 import model_blob
+    from oracle import pipeline
+    pick = np.array([0, 7, 8, 2047, 2048, 4999, 9991, 9999])
+    om = pipeline.OracleModel(model_blob.load_model("crossdock_default2018"))
+    want = om.score(rx, rt, lx.reshape(n, na, 3)[pick].reshape(-1, 3), lt[:len(pick) * na], offs[:len(pick) + 1], dtype=torch.float64)
+    assert np.abs(want[0] - a[0][pick]).max() < TOL_SCORE and np.abs(want[1] - a[1][pick]).max() < TOL_AFF
+
+
+@pytest.mark.parametrize("n", [1, 7, 9, 17, 100])
+def test_fused_conv1_kernel_equals_unfused_path(kat, n):
+    """The fused unit1_conv + unit2_conv + pool kernel (row-group tiles, tensor-map TMA, second MMA in the epilogue) and
+    the separate kernels (GB_TC_FUSED=0 semantics, reached here through the gradient call that keeps activations)
+    compute the same network: scores agree to fp16 round-off for ragged group counts (partial last group of 8)."""
+    from gnina_b200 import CNNScorer, synth
+    rx, rt = synth.make_receptor(1500, box=44)
+    lx0, lt0 = synth.make_ligand(22, 3, seed=4)
+    lx, offs = synth.make_poses(lx0, n, trans_box=10, seed=n)
+    lt = np.tile(lt0, n)
+    s = _fast(["crossdock_default2018"])
+    s.set_receptor(rx, rt)
+    fused = s.score_batch(lx, lt, offs)
+    unfused = s.score_grad_batch(lx, lt, offs)          # forward with kept activations: conv1, pointwise, pool as 3 kernels
+    assert np.abs(fused[0] - unfused[0]).max() < 5e-4 and np.abs(fused[1] - unfused[1]).max() < 2e-3
+    v = CNNScorer(["crossdock_default2018"], precision=0)
+    v.set_receptor(rx, rt)
+    ref = v.score_batch(lx, lt, offs)
+    assert np.abs(fused[0] - ref[0]).max() < TOL_SCORE and np.abs(fused[1] - ref[1]).max() < TOL_AFF
 
 
 def test_dense_ensemble_matches_reference_pt(golden_dir):

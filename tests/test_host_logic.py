@@ -13,10 +13,20 @@ def test_expand_model_names_like_reference():
     # cnn_torch_scorer.cpp:28-62
     assert scorer.expand_model_names([]) == ["dense_1_3", "dense_1_3_PT_KD_3", "crossdock_default2018_KD_4"]
     assert scorer.expand_model_names(["fast"]) == ["all_default_to_default_1_3_1"]
-    assert scorer.expand_model_names(["default1.0"])[0] == "dense"
+    assert scorer.expand_model_names(["default1.0"], check=False) == ["dense", "general_default2018_3", "dense_3",
+                                                                      "crossdock_default2018", "redock_default2018_2"]
     assert scorer.expand_model_names(["dense_1.3"]) == ["dense_1_3"]
-    ens = scorer.expand_model_names(["crossdock_default2018_ensemble"])
-    assert "crossdock_default2018" in ens and all(e.startswith("crossdock_default2018") for e in ens)
+    # an ensemble expands over the REFERENCE's table (64 models), not over whatever happens to be packaged
+    assert len(scorer.REFERENCE_MODELS) == 64
+    ens = scorer.expand_model_names(["crossdock_default2018_ensemble"], check=False)
+    assert len(ens) == 15 and "crossdock_default2018" in ens and all(e.startswith("crossdock_default2018") for e in ens)
+    assert len(scorer.expand_model_names(["dense_ensemble"], check=False)) == 20
+    assert len(scorer.expand_model_names(["redock_default2018_ensemble"], check=False)) == 15
+    # a member that is not packaged is an error, never a silently smaller ensemble
+    missing = [m for m in ens if m not in scorer.builtin_models()]
+    if missing:
+        with pytest.raises(scorer.usage_error, match="not packaged"):
+            scorer.expand_model_names(["crossdock_default2018_ensemble"])
 
 
 def test_blob_reader_roundtrip():

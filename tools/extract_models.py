@@ -9,7 +9,7 @@ what travels with the repo.  No libtorch is needed at run time on the product pa
 
 File layout (little endian):
   char  magic[8]  = "GNB200W1"
-  u32   arch (1 default2018, 2 dense, 3 default2017), u32 n_tensors
+  u32   arch (1 default2018, 2 dense, 3 default2017, 4 overlap), u32 n_tensors
   f32   resolution, dimension, radius_scaling ; u32 flags (bit0 apply_logistic_loss, bit1 skip_softmax)
   u32   name_len, recmap_len, ligmap_len, reserved
   bytes name, recmap, ligmap ; zero pad to 8
@@ -20,7 +20,7 @@ import argparse, json, os, struct, sys
 import numpy as np
 import torch
 
-ARCH = {"default2018": 1, "dense": 2, "default2017": 3}
+ARCH = {"default2018": 1, "dense": 2, "default2017": 3, "overlap": 4}
 
 DEFAULT_RECMAP = """AliphaticCarbonXSHydrophobe 
 AliphaticCarbonXSNonHydrophobe 
@@ -62,6 +62,8 @@ def classify(sd):
         return "default2018"
     if any(k.endswith("unit3_conv1.weight") for k in keys):
         return "default2017"
+    if not keys:
+        return "overlap"   # the parameter-free overlay graph of test/gnina/data/overlap*.pt (test_min.py)
     raise ValueError("unknown architecture: %s" % keys[:5])
 
 
