@@ -597,7 +597,7 @@ int gb_cnn_run_staged(gb_cnn* h) {
           const size_t slot = (size_t)mi * R + r;
           h->launches += forward_fp32(Mo, G.grid.p, nb, h->ws32, h->d_out3.p, h->stream, &h->prof);
           launch_head_post(h->d_out3.p, nb, Mo.skip_softmax, Mo.apply_logistic_loss, h->d_pose.p + slot * n + p0,
-                           h->d_aff.p + slot * n + p0, h->d_loss.p + slot * n + p0, h->stream);
+                           h->d_aff.p + slot * n + p0, h->d_loss.p + slot * n + p0, h->stream, Mo.arch == GB_ARCH_OVERLAP);
           h->launches++;
         }
       } else {
@@ -626,7 +626,7 @@ int gb_cnn_run_staged(gb_cnn* h) {
           h->launches += tc_forward(Mo, pb, gw.x0[tc_grid_kind(Mo, false)][buf], h->ws_tc, h->d_out3.p, h->stream, &h->prof,
                                     k + 1 == G.model_idx.size() ? gw.consumed[buf] : nullptr);
           launch_head_post(h->d_out3.p, nb, Mo.skip_softmax, Mo.apply_logistic_loss, h->d_pose.p + slot * n + p0,
-                           h->d_aff.p + slot * n + p0, h->d_loss.p + slot * n + p0, h->stream);
+                           h->d_aff.p + slot * n + p0, h->d_loss.p + slot * n + p0, h->stream, Mo.arch == GB_ARCH_OVERLAP);
           h->launches++;
         }
         gw.consumed_valid[buf] = true;
@@ -811,7 +811,7 @@ int gb_cnn_score_grad(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, 
         }
         const size_t slot = (size_t)mi * R + r;
         launch_head_post(h->d_out3.p, nb, Mo.skip_softmax, Mo.apply_logistic_loss, h->d_pose.p + slot * n + p0,
-                         h->d_aff.p + slot * n + p0, h->d_loss.p + slot * n + p0, h->stream);
+                         h->d_aff.p + slot * n + p0, h->d_loss.p + slot * n + p0, h->stream, Mo.arch == GB_ARCH_OVERLAP);
         // ligand atoms of this chunk: accumulate (scaled 1/M) into the group's gradient array
         const bool want_rec = drec_xyz && G.n_rec > 0;
         if (want_rec) tmp_rec.ensure(3 * (size_t)G.n_rec);

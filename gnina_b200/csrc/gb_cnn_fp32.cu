@@ -229,23 +229,24 @@ __global__ void __launch_bounds__(256) fc3_kernel(const float* __restrict__ feat
 // softmax(z), so pose = softmax(z)[1]; with skip_softmax the reference reads the module output [0,1] itself,
 // i.e. log_softmax(z)[1].  loss = CE(module output, label 1) = -log_softmax(z)[1]; with apply_logistic_loss
 // the reference takes -log(module output[0,1]) = -log(log_softmax(z)[1]).
-__global__ void head_post_kernel(const float* __restrict__ out3, int B, int skip_softmax, int logistic,
+// raw_output: out3 already holds the module's output (the overlay test model returns (0, score), not a log-softmax)
+__global__ void head_post_kernel(const float* __restrict__ out3, int B, int skip_softmax, int logistic, int raw_output,
                                  float* __restrict__ pose, float* __restrict__ aff, float* __restrict__ loss) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const float z0 = out3[3 * b], z1 = out3[3 * b + 1];
   const float m = fmaxf(z0, z1);
   const float lse = m + logf(expf(z0 - m) + expf(z1 - m));
-  const float lp1 = z1 - lse;
+  const float lp1 = raw_output ? z1 : z1 - lse;
   pose[b] = skip_softmax ? lp1 : expf(lp1);
   aff[b] = out3[3 * b + 2];
   loss[b] = logistic ? -logf(lp1) : -lp1;
 }
 
 void launch_head_post(const float* out3, int B, bool skip_softmax, bool logistic, float* pose, float* aff, float* loss,
-                      cudaStream_t s) {
+                      cudaStream_t s, bool raw_output) {
   if (B <= 0) return;
-  head_post_kernel<<<(B + 127) / 128, 128, 0, s>>>(out3, B, skip_softmax, logistic, pose, aff, loss);
+  head_post_kernel<<<(B + 127) / 128, 128, 0, s>>>(out3, B, skip_softmax, logistic, raw_output, pose, aff, loss);
 }
 
 // CNNTorchScorer::score accumulation, cnn_torch_scorer.cpp:117-192: score accumulates in double, affinity/loss in

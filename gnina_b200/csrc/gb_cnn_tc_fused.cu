@@ -46,17 +46,28 @@ constexpr int kChunkBytes = kSlabRows * kSlabZ * 16;   // 2880: one 8-channel ch
 constexpr int kStageBytes = 4 * kChunkBytes;           // 11520
 constexpr int kStages = 3;
 constexpr int kWBytes = 9 * 4 * 96 * 16;               // 55296
-constexpr int kYBytes = 2 * 128 * 64;                  // 16384  [plane parity][row][32 ch fp16], chunks swizzled
-constexpr int kR = 8;                                  // TMEM ring: 8 plane slots x 32 columns
+constexpr int kYBytes = 2 * 128 * 64;                  // 16384: variant A [plane parity][row][32 ch fp16] (chunks swizzled),
+                                                       //        variant B 2 x [chunk][row][8 ch] = double-buffered A operand
+constexpr int kW2Bytes = 4 * 32 * 16;                  // 2048  [chunk][co][8 ci] (variant B)
 constexpr int kOffStage = kWBytes;
 constexpr int kOffY = kOffStage + kStages * kStageBytes;
-constexpr int kOffBar = kOffY + kYBytes;
+constexpr int kOffW2 = kOffY + kYBytes;
+constexpr int kOffBar = kOffW2 + kW2Bytes;
 constexpr int kSmemTotal = kOffBar + 512;
+// The 1x1x1 convolution after the accumulator comes in two variants (template parameter kTcPw):
+//   A (false): mma.sync from shared memory inside the epilogue warps; TMEM ring of 8 plane slots
+//   B (true) : a second tcgen05.mma (D2 = relu(conv) x W2^T, 32 more TMEM columns, double buffered) issued by the MMA warp on
+//              a FIXED schedule -- the pointwise MMA of output plane j goes into the queue right before the convolution
+//              MMAs of the input plane two commits later, when plane j's accumulator has long been complete and staged --
+//              and an epilogue that runs one plane behind itself (stage plane j, then finish plane j - 1), so neither side
+//              ever waits for the other's latency.  TMEM ring of 6 plane slots + 2 x 32 columns.
+template <bool kTcPw> struct Var { static constexpr int kR = kTcPw ? 6 : 8; };
 
 struct FusedParams {
   const uint4* wp;     // conv1: [9][4][96] x 16 B (make_conv_tc)
   const float* bias1;  // [32]
-  const __half* w2;    // pointwise: [co][ci] row-major fp16
+  const __half* w2;    // pointwise: [co][ci] row-major fp16 (variant A)
+  const uint4* w2p;    // pointwise: [ci / 8][co][ci % 8] fp16 = K-major B operand (variant B)
   const float* bias2;  // [32]
   __half* xout;        // X2: chunk-planar D = 12 (make_layout(12, Gn, 32))
   int out_lp, out_G, n_poses, n_groups;
@@ -71,7 +82,9 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4],
 
 __constant__ uint32_t c_fused_off[18][2];  // per (tap, k step): A start offset, B row offset (16-byte units)
 
+template <bool kTcPw>
 __global__ void __launch_bounds__(192) conv1_pw2_pool_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
+  constexpr int kR = Var<kTcPw>::kR;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_w = smem;
   uint8_t* s_stage = smem + kOffStage;
@@ -82,8 +95,11 @@ __global__ void __launch_bounds__(192) conv1_pw2_pool_kernel(const __grid_consta
   uint64_t* accf = bars + 2 * kStages;    // [kR]  conv plane complete
   uint64_t* acce = accf + kR;             // [kR]  conv plane drained (128 arrivals)
   uint64_t* wbar = acce + kR;             // weights landed
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(wbar + 1);
-  float* s_bias = reinterpret_cast<float*>(s_tmem + 2);   // bias1[32]
+  uint64_t* a2_full = wbar + 1;           // [2] variant B: a plane is staged for the pointwise MMA (128 arrivals)
+  uint64_t* d2_full = a2_full + 2;        // [2] variant B: pointwise accumulator complete
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(d2_full + 2);
+  float* s_bias = reinterpret_cast<float*>(s_tmem + 2);   // bias1[32], bias2[32]
+  uint8_t* s_w2 = smem + kOffW2;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = p.n_groups * kRowTiles * kZBlocks;
@@ -92,11 +108,13 @@ __global__ void __launch_bounds__(192) conv1_pw2_pool_kernel(const __grid_consta
     for (int s = 0; s < kStages; s++) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
     for (int s = 0; s < kR; s++) { ptx::mbar_init(&accf[s], 1); ptx::mbar_init(&acce[s], 128); }
     ptx::mbar_init(wbar, 1);
+    for (int b = 0; b < 2; b++) { ptx::mbar_init(&a2_full[b], 128); ptx::mbar_init(&d2_full[b], 1); }
     ptx::fence_mbar_init();
   }
   if (threadIdx.x < 32) s_bias[threadIdx.x] = p.bias1[threadIdx.x];
+  else if (threadIdx.x < 64) s_bias[threadIdx.x] = p.bias2[threadIdx.x - 32];
   if (warp == 1) {
-    ptx::tmem_alloc(s_tmem, kR * 32);
+    ptx::tmem_alloc(s_tmem, 256);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -108,9 +126,10 @@ __global__ void __launch_bounds__(192) conv1_pw2_pool_kernel(const __grid_consta
     // ===== producer: weights once (bulk copies), then one tensor-map TMA box per input plane =====
     if (ptx::elect_one()) {
       ptx::prefetch_tmap(&tmap);
-      ptx::mbar_expect_tx(wbar, kWBytes);
+      ptx::mbar_expect_tx(wbar, kWBytes + (kTcPw ? kW2Bytes : 0));
       for (int t9 = 0; t9 < 9; t9++)
         ptx::bulk_g2s(s_w + t9 * (kWBytes / 9), reinterpret_cast<const uint8_t*>(p.wp) + t9 * (kWBytes / 9), kWBytes / 9, wbar);
+      if (kTcPw) ptx::bulk_g2s(s_w2, p.w2p, kW2Bytes, wbar);
     }
     __syncwarp();
     uint32_t gp = 0;
@@ -135,9 +154,30 @@ __global__ void __launch_bounds__(192) conv1_pw2_pool_kernel(const __grid_consta
     const uint32_t b_lo_base = (96u << 16) | (ptx::smem_u32(s_w) >> 4);
     auto wait_service = [&](uint64_t* bar, uint32_t parity) { ptx::mbar_wait(bar, parity); };
     wait_service(wbar, 0);
+    // variant B: pointwise MMA of output plane j: D2[j & 1] = A2[j & 1] (128 x 32) x W2^T, two K = 16 steps
+    const uint32_t w2_lo = ((uint32_t)(512 >> 4) << 16) | (ptx::smem_u32(s_w2) >> 4);   // LBO = 32 rows x 16 B
+    uint32_t pw_issued = 0, committed = 0;
+    auto issue_pw_until = [&](uint32_t upto) {
+      for (; pw_issued < upto; pw_issued++) {
+        const uint32_t b = pw_issued & 1;
+        ptx::mbar_wait(&a2_full[b], (pw_issued >> 1) & 1);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t a2_lo = ((uint32_t)(2048 >> 4) << 16) | (ptx::smem_u32(s_y + b * 8192) >> 4);   // LBO = 128 rows x 16 B
+          const uint32_t tm_d2 = tmem_base + kR * 32 + b * 32;
+          ptx::mma_f16_ss_lohi<0>(tm_d2, a2_lo, kDescHiB, w2_lo, kDescHiB, ptx::idesc_f16(128, 32));
+          ptx::mma_f16_ss_lohi<1>(tm_d2, a2_lo + 2 * (2048 >> 4), kDescHiB, w2_lo + 2 * (512 >> 4), kDescHiB, ptx::idesc_f16(128, 32));
+          ptx::tc_commit(&d2_full[b]);
+        }
+        __syncwarp();
+      }
+    };
     uint32_t gp = 0, go_base = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, go_base += kD) {
       for (int it = 0; it < kD; it++, gp++) {
+        // planes committed at least one input plane ago are complete (or about to be) and staged: their pointwise MMAs go
+        // into the queue now, ahead of this input plane's convolution MMAs; the most recent commit is left for next time
+        if (kTcPw && committed > 0) issue_pw_until(committed - 1);
         const int xi = it + 1;
         const uint32_t st = gp % kStages, ph = (gp / kStages) & 1;
         const int lo = xi > 1 ? xi - 1 : 1, hi = xi < kD ? xi + 1 : kD;
@@ -193,6 +233,88 @@ __global__ void __launch_bounds__(192) conv1_pw2_pool_kernel(const __grid_consta
           if (xi == kD) ptx::tc_commit(&accf[(go_base + kD - 1) % kR]);
         }
         __syncwarp();
+        committed += (xi >= 2) + (xi == kD);
+      }
+    }
+    if (kTcPw) issue_pw_until(committed);   // the last planes
+  } else if constexpr (kTcPw) {
+    // ===== epilogue, variant B: stage plane j for the pointwise tcgen05.mma, then finish plane j - 1 =====
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    const int yrow = row >> 3, zz = row & 7;
+    const uint32_t tm_lane = (uint32_t)(q4 * 32) << 16;
+    constexpr int Dn = 12, Pn = 14;
+    int n_my = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) n_my++;
+    const uint32_t n_planes = (uint32_t)n_my * kD;
+    float keep[32];
+    uint4* xo4 = reinterpret_cast<uint4*>(p.xout);
+    for (uint32_t j = 0; j <= n_planes; j++) {
+      if (j < n_planes) {
+        // ---- step 1 (plane j): conv accumulator -> bias, ReLU, fp16 -> A operand buffer j & 1 ----
+        const uint32_t slot = j % kR, u = j / kR, b = j & 1;
+        ptx::mbar_wait(&accf[slot], u & 1);
+        ptx::tc_fence_after();
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_base + tm_lane + slot * 32u, v);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&acce[slot]);
+#pragma unroll
+        for (int c8 = 0; c8 < 4; c8++) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const int c = c8 * 8 + 2 * e;
+            const float f0 = fmaxf(__uint_as_float(v[c]) + s_bias[c], 0.f);
+            const float f1 = fmaxf(__uint_as_float(v[c + 1]) + s_bias[c + 1], 0.f);
+            const __half2 h = __floats2half2_rn(f0, f1);
+            w[e] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(s_y + b * 8192 + c8 * 2048 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        ptx::fence_proxy_async();   // generic-proxy stores -> visible to the tensor core
+        ptx::mbar_arrive(&a2_full[b]);
+      }
+      if (j == 0) continue;
+      // ---- step 2 (plane j - 1): pointwise accumulator -> bias, ReLU, 2x2x2 average ----
+      const uint32_t jj = j - 1, b = jj & 1;
+      ptx::mbar_wait(&d2_full[b], (jj >> 1) & 1);
+      ptx::tc_fence_after();
+      uint32_t v[32];
+      ptx::tmem_ld32(tmem_base + tm_lane + (uint32_t)(kR * 32) + b * 32u, v);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      const int xo = (int)(jj % kD) + 1;
+      if (xo & 1) {
+#pragma unroll
+        for (int c = 0; c < 32; c++) keep[c] = fmaxf(__uint_as_float(v[c]) + s_bias[32 + c], 0.f);
+      } else {
+        uint32_t o[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float s0 = keep[c] + fmaxf(__uint_as_float(v[c]) + s_bias[32 + c], 0.f);
+          float s1 = keep[c + 1] + fmaxf(__uint_as_float(v[c + 1]) + s_bias[32 + c + 1], 0.f);
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 8);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+          const __half2 h = __floats2half2_rn(s0 * 0.125f, s1 * 0.125f);
+          o[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        const int item = blockIdx.x + (int)(jj / kD) * gridDim.x;
+        const int zb = item % kZBlocks, k = (item / kZBlocks) % kRowTiles, grp = item / (kZBlocks * kRowTiles);
+        const int R = 16 * k + 1 + yrow;
+        const int q = R / kP, yp = R - q * kP;
+        const int pose = grp * kG + q;
+        // the lane that stores a pooled voxel: even tile row (= odd yp) and even z; its window is rows R, R+1, columns zz, zz+1
+        if (((lane & 9) == 0) && q < kG && pose < p.n_poses && yp >= 1 && yp <= kD) {
+          const int yo = (yp - 1) >> 1, zo = 4 * zb + (zz >> 1);
+          uint4* dst = xo4 + (((size_t)(pose / p.out_G) * Dn + ((xo >> 1) - 1)) * 4) * p.out_lp + (size_t)(pose % p.out_G) * Pn * Pn +
+                       (size_t)(yo + 1) * Pn + (zo + 1);
+#pragma unroll
+          for (int c8 = 0; c8 < 4; c8++) dst[(size_t)c8 * p.out_lp] = make_uint4(o[4 * c8], o[4 * c8 + 1], o[4 * c8 + 2], o[4 * c8 + 3]);
+        }
       }
     }
   } else {
@@ -313,7 +435,7 @@ __global__ void __launch_bounds__(192) conv1_pw2_pool_kernel(const __grid_consta
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kR * 32);
+    ptx::tmem_dealloc(tmem_base, 256);
   }
 }
 
@@ -337,8 +459,20 @@ EncodeTiledFn encode_tiled_fn() {
 
 ActLayout make_fused_x0_layout() { return make_layout(kD, kG, 32); }
 
-void launch_conv1_pw2_pool(const ConvTc& conv1, const __half* w2, const float* bias2, const uint4* x0, const ActLayout& L0, uint4* x2,
-                           const ActLayout& L2, int n_poses, cudaStream_t s) {
+// unit2_conv weight [co][ci] fp32 -> [ci / 8][co][ci % 8] fp16: the K-major B operand (LBO = 32 rows x 16 B)
+uint4* pack_pointwise_tc(std::vector<void*>& allocs, const float* w, int c) {
+  std::vector<__half> h((size_t)c * c);
+  for (int co = 0; co < c; co++)
+    for (int ci = 0; ci < c; ci++) h[((size_t)(ci / 8) * c + co) * 8 + (ci % 8)] = __float2half(w[(size_t)co * c + ci]);
+  __half* d = nullptr;
+  GB_CUDA(cudaMalloc(&d, h.size() * sizeof(__half)));
+  allocs.push_back(d);
+  GB_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  return reinterpret_cast<uint4*>(d);
+}
+
+void launch_conv1_pw2_pool(const ConvTc& conv1, const __half* w2, const uint4* w2p, const float* bias2, const uint4* x0, const ActLayout& L0,
+                           uint4* x2, const ActLayout& L2, int n_poses, cudaStream_t s) {
   GB_CHECK(conv1.cin == 32 && conv1.cout == 32 && L0.D == kD && L0.G == kG && L2.D == 12, "fused conv1 shape");
   EncodeTiledFn enc = encode_tiled_fn();
   GB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available in this driver");
@@ -352,7 +486,8 @@ void launch_conv1_pw2_pool(const ConvTc& conv1, const __half* w2, const float* b
     std::lock_guard<std::mutex> lk(mu);
     GB_CHECK(dev < 64, "device index");
     if (!attr_set[dev]) {
-      GB_CUDA(cudaFuncSetAttribute(conv1_pw2_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+      GB_CUDA(cudaFuncSetAttribute(conv1_pw2_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+      GB_CUDA(cudaFuncSetAttribute(conv1_pw2_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
       uint32_t h[18][2];
       for (int t9 = 0; t9 < 9; t9++)
         for (int ks = 0; ks < 2; ks++) {
@@ -377,12 +512,15 @@ void launch_conv1_pw2_pool(const ConvTc& conv1, const __half* w2, const float* b
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
   FusedParams p;
-  p.wp = conv1.wp; p.bias1 = conv1.bias; p.w2 = w2; p.bias2 = bias2; p.xout = reinterpret_cast<__half*>(x2); p.out_lp = L2.Lp; p.out_G = L2.G;
+  p.wp = conv1.wp; p.bias1 = conv1.bias; p.w2 = w2; p.w2p = w2p; p.bias2 = bias2; p.xout = reinterpret_cast<__half*>(x2); p.out_lp = L2.Lp; p.out_G = L2.G;
   p.n_poses = n_poses; p.n_groups = n_groups;
   const int n_items = n_groups * kRowTiles * kZBlocks;
-  static const int persist = getenv("GB_TC_FUSED_PERSIST") ? atoi(getenv("GB_TC_FUSED_PERSIST")) : 0;
+  static const int persist = getenv("GB_TC_FUSED_PERSIST") ? atoi(getenv("GB_TC_FUSED_PERSIST")) : 2;
+  static const int tc_pw = getenv("GB_TC_FUSED_PW") ? atoi(getenv("GB_TC_FUSED_PW")) : 1;   // 1 (default): pointwise conv as a second tcgen05.mma;
+                                                                                                  // 0: mma.sync in the epilogue (r2g: 9.9 vs 7.6 ms)
   int grid = persist > 0 ? std::min(n_items, n_sm[dev] * persist) : n_items;
-  conv1_pw2_pool_kernel<<<grid, 192, kSmemTotal, s>>>(tmap, p);
+  if (tc_pw) conv1_pw2_pool_kernel<true><<<grid, 192, kSmemTotal, s>>>(tmap, p);
+  else conv1_pw2_pool_kernel<false><<<grid, 192, kSmemTotal, s>>>(tmap, p);
 }
 
 }  // namespace gb

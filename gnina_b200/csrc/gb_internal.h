@@ -173,7 +173,7 @@ void launch_grid_backward(const float4* atoms_xyzr, const int* atoms_ch, const i
 void launch_axpy_range(const float* src, float* dst, int lo, int hi, float alpha, cudaStream_t s);
 // [B][3] raw -> pose/aff/loss per torch_model.cpp:188-195
 void launch_head_post(const float* out3, int B, bool skip_softmax, bool logistic, float* pose, float* aff,
-                      float* loss, cudaStream_t s);
+                      float* loss, cudaStream_t s, bool raw_output = false);
 // ensemble mean/variance (cnn_torch_scorer.cpp:117-192): per-model arrays [M][B] -> 4 x [B]
 void launch_ensemble(const float* pose, const float* aff, const float* loss, int M, int B, int stride, float* o_score,
                      float* o_aff, float* o_loss, float* o_var, cudaStream_t s);

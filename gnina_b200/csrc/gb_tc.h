@@ -90,6 +90,7 @@ struct PointwiseTc {
 struct TcWeights {
   ConvTc conv1, conv3, conv5;
   PointwiseTc pw2, pw4;
+  uint4* pw2_packed = nullptr;  // unit2_conv as the K-major B operand of the fused kernel's second tcgen05.mma
   float* fcw = nullptr;      // [3][216*128] channels-last order
   float* fcb = nullptr;
   std::vector<void*> allocs;
@@ -106,7 +107,8 @@ void launch_conv_tc_32_24_planar(const ConvTc& c, const uint4* xin, uint4* xout,
 void tc_debug_set(int i, const void* p, size_t bytes);
 // fused scoring kernel (gb_cnn_tc_fused.cu): x0 in the row-group layout -> X2 (input of unit3_conv)
 ActLayout make_fused_x0_layout();
-void launch_conv1_pw2_pool(const ConvTc& conv1, const __half* w2, const float* bias2, const uint4* x0, const ActLayout& L0, uint4* x2,
+uint4* pack_pointwise_tc(std::vector<void*>& allocs, const float* w, int c);
+void launch_conv1_pw2_pool(const ConvTc& conv1, const __half* w2, const uint4* w2p, const float* bias2, const uint4* x0, const ActLayout& L0, uint4* x2,
                            const ActLayout& L2, int n_poses, cudaStream_t s);
 
 // test-only access to the buffers of the most recent tc_forward on this thread: 0 x0, 1 y(3), 2 x2, 3 x4, 4 y5

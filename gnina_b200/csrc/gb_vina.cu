@@ -457,12 +457,10 @@ int gb_vina_set_receptor(gb_vina* h, const float* xyz, const int32_t* smina_type
 int gb_vina_cache_build(gb_vina* h, const float* begin, const float* end, const int32_t* n, const int32_t* types_needed,
                         int n_types) {
   GBV_BEGIN
-  GB_CHECK(h && begin && end && n && types_needed && n_types > 0 && n_types <= kMaxNeeded, "bad cache arguments");
+  GB_CHECK(h && begin && end && n && types_needed && n_types > 0 && n_types <= kNumSminaTypes, "bad cache arguments");
   Vina& v = h->v;
   GB_CUDA(cudaSetDevice(v.device));
   for (auto& g : v.d_grids) g = nullptr;
-  NeededTypes nt;
-  nt.n = n_types;
   const size_t vol = (size_t)(n[0] + 1) * (n[1] + 1) * (n[2] + 1);
   float finv[3];
   for (int i = 0; i < 3; i++) {
@@ -471,23 +469,29 @@ int gb_vina_cache_build(gb_vina* h, const float* begin, const float* end, const 
     const float factor = (float)((n[i] + 1) - 1.0) / (end[i] - begin[i]);
     finv[i] = 1 / factor;
   }
-  for (int j = 0; j < n_types; j++) {
-    const int t = types_needed[j];
-    GB_CHECK(t >= 2 && t < kNumSminaTypes, "needed type must be a heavy smina type");
-    if (v.grid_pool_cap[t] < vol) {
-      cudaFree(v.grid_pool[t]);
-      v.grid_pool[t] = nullptr; v.grid_pool_cap[t] = 0;
-      GB_CUDA(cudaMalloc(&v.grid_pool[t], vol * sizeof(float)));
-      v.grid_pool_cap[t] = vol;
+  // the kernel keeps up to kMaxNeeded running sums per grid point: a ligand with more heavy types (the reference's own
+  // random-molecule tests draw all 26) takes another pass over the receptor
+  for (int j0 = 0; j0 < n_types; j0 += kMaxNeeded) {
+    NeededTypes nt;
+    nt.n = std::min(kMaxNeeded, n_types - j0);
+    for (int j = 0; j < nt.n; j++) {
+      const int t = types_needed[j0 + j];
+      GB_CHECK(t >= 2 && t < kNumSminaTypes, "needed type must be a heavy smina type");
+      if (v.grid_pool_cap[t] < vol) {
+        cudaFree(v.grid_pool[t]);
+        v.grid_pool[t] = nullptr; v.grid_pool_cap[t] = 0;
+        GB_CUDA(cudaMalloc(&v.grid_pool[t], vol * sizeof(float)));
+        v.grid_pool_cap[t] = vol;
+      }
+      v.d_grids[t] = v.grid_pool[t];
+      nt.t[j] = t;
+      nt.grid[j] = v.d_grids[t];
     }
-    v.d_grids[t] = v.grid_pool[t];
-    nt.t[j] = t;
-    nt.grid[j] = v.d_grids[t];
+    cache_populate_kernel<<<(unsigned)((vol + 127) / 128), 128, 0, v.stream>>>(v.d_rec, v.n_rec, v.d_fast, v.n, v.factor,
+                                                                                v.cutoff_sqr, begin[0], begin[1], begin[2], finv[0],
+                                                                                finv[1], finv[2], n[0] + 1, n[1] + 1, n[2] + 1, nt);
+    GB_CUDA(cudaGetLastError());
   }
-  cache_populate_kernel<<<(unsigned)((vol + 127) / 128), 128, 0, v.stream>>>(v.d_rec, v.n_rec, v.d_fast, v.n, v.factor,
-                                                                              v.cutoff_sqr, begin[0], begin[1], begin[2], finv[0],
-                                                                              finv[1], finv[2], n[0] + 1, n[1] + 1, n[2] + 1, nt);
-  GB_CUDA(cudaGetLastError());
   GB_CUDA(cudaStreamSynchronize(v.stream));
   GBV_END
 }
@@ -1085,6 +1089,19 @@ __global__ void __launch_bounds__(32 * kDkWarps) dock_refine_kernel(LigPtrs L, D
   for (int i = lane; i < nx; i += 32) confs[(size_t)c * nx + i] = W.x[i];
 }
 
+// the empirical term of non_cache_cnn::eval_deriv (lib/non_cache_cnn.cpp:113-140) for free atoms: one thread per atom
+__global__ void noncache_atoms_kernel(const float4* __restrict__ atoms, int n, DockField F, float v, float* __restrict__ e_out,
+                                      float* __restrict__ d_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 a = atoms[i];
+  const int t = (int)a.w;
+  float d[3] = {0.f, 0.f, 0.f}, e = 0.f;
+  if (t >= 2 && t < kNumSminaTypes) e = dk_noncache_atom(F, t, a.x, a.y, a.z, v, d);
+  e_out[i] = e;
+  d_out[3 * i] = d[0]; d_out[3 * i + 1] = d[1]; d_out[3 * i + 2] = d[2];
+}
+
 struct McDev { int num_steps, maxiters, num_saved_mins; float temperature, mutation_amplitude, min_rmsd; float hunt_cap[3]; };
 
 // no min-blocks hint: capping the chain kernel at 64 registers measured 17 % slower (621 k vs 750 k MC steps/s)
@@ -1425,6 +1442,25 @@ int gb_vina_eval_deriv_noncache(gb_vina* h, const float* confs, int n, const flo
                                 const float* box_end, float* e, float* change) {
   if (!box_begin || !box_end) { gb::set_last_error("gb_vina_eval_deriv_noncache: null box"); return GB_ERR_USAGE; }
   return dock_eval_common(h, confs, n, v3, slope, 0, 0, e, change, nullptr, nullptr, nullptr, box_begin, box_end);
+}
+
+int gb_vina_noncache_atoms(gb_vina* h, const float* xyz, const int32_t* smina_type, int n_atoms, const float* box_begin,
+                           const float* box_end, float v, float* e, float* deriv) {
+  GBV_BEGIN
+  GB_CHECK(h && xyz && smina_type && box_begin && box_end && e && deriv && n_atoms >= 0, "bad arguments");
+  Vina& vv = h->v;
+  GB_CUDA(cudaSetDevice(vv.device));
+  if (n_atoms == 0) return GB_OK;
+  const int32_t off[2] = {0, n_atoms};
+  stage_poses(vv, xyz, smina_type, off, 1);
+  DockField F;
+  make_noncache_field(vv, 0.f, box_begin, box_end, F);   // slope 0: the caller adds its own out-of-box terms
+  noncache_atoms_kernel<<<(n_atoms + 127) / 128, 128, 0, vv.stream>>>(vv.d_lig, n_atoms, F, v, vv.d_atom_e, vv.d_deriv);
+  GB_CUDA(cudaGetLastError());
+  GB_CUDA(cudaMemcpyAsync(e, vv.d_atom_e, (size_t)n_atoms * sizeof(float), cudaMemcpyDeviceToHost, vv.stream));
+  GB_CUDA(cudaMemcpyAsync(deriv, vv.d_deriv, (size_t)n_atoms * 3 * sizeof(float), cudaMemcpyDeviceToHost, vv.stream));
+  GB_CUDA(cudaStreamSynchronize(vv.stream));
+  GBV_END
 }
 
 int gb_vina_refine(gb_vina* h, float* confs, int n, int maxiters, const float* v3, const float* box_begin, const float* box_end,

@@ -159,3 +159,17 @@ def make_flexible_ligand(n_heavy=24, n_tors=5, n_branch=3, seed=11):
                 seg_rel_origin=rel_origin.astype(np.float32), seg_rel_axis=rel_axis.astype(np.float32),
                 pair_a=np.array(pa, np.int32), pair_b=np.array(pb, np.int32), conf0=conf0, xyz0=pos.astype(np.float32),
                 gyration_radius=gr)
+
+
+def make_gninacheck_mol(rs, natoms=0, min_atoms=200, max_atoms=500, max_x=25.0, max_y=25.0, max_z=25.0):
+    """The random-molecule generator of the reference's own `gninacheck` tests (test/gnina/test_utils.cpp:13-44,
+    defaults test_utils.h:21-24): atom count uniform in [min_atoms, max_atoms + 1] unless given, coordinates uniform in
+    [-max, max] per axis, smina type uniform over ALL 28 types (hydrogens and metals included), nothing prevents overlaps.
+    `rs` is a numpy RandomState (MT19937 like the reference's std::mt19937; the draw algorithms of libstdc++'s
+    distributions are not reproduced, so molecules match in distribution, not draw by draw).
+    -> (xyz float32 [n,3], smina types int32 [n])"""
+    if not natoms:
+        natoms = int(rs.randint(min_atoms, max_atoms + 2))
+    xyz = np.stack([rs.uniform(-m, m, size=natoms) for m in (max_x, max_y, max_z)], axis=1).astype(np.float32)
+    types = rs.randint(0, 28, size=natoms).astype(np.int32)
+    return xyz, types

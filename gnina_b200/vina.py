@@ -110,6 +110,14 @@ class VinaScorer:
         capi.check(capi.lib().gb_vina_eval_deriv_noncache(self._h, _fp(x), n, _fp(v), slope, _fp(b), _fp(en), _fp(e), _fp(g)))
         return e, g
 
+    def noncache_atoms(self, xyz, smina_types, box_begin, box_end, v=1000.0):
+        """per-atom empirical term of non_cache_cnn::eval_deriv (lib/non_cache_cnn.cpp:113-140) -> (e[n], deriv[n,3])"""
+        x = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3); t = np.ascontiguousarray(smina_types, np.int32)
+        b, en = np.ascontiguousarray(box_begin, np.float32), np.ascontiguousarray(box_end, np.float32)
+        e = np.empty(len(t), np.float32); d = np.empty((len(t), 3), np.float32)
+        capi.check(capi.lib().gb_vina_noncache_atoms(self._h, _fp(x), _ip(t), len(t), _fp(b), _fp(en), v, _fp(e), _fp(d)))
+        return e, d
+
     def refine(self, confs, maxiters, box_begin, box_end, v=(1000, 1000, 1000)):
         """refine_structure (main/main.cpp:131-171) -> (e, refined confs, within, n_evals)"""
         x = np.array(confs, np.float32).reshape(-1, 7 + self.T)

@@ -247,6 +247,12 @@ int gb_vina_mc_traced(gb_vina* h, const gb_mc_params* params, const float* corne
  * the grid_dims box whose faces clamp the atom and charge slope x distance outside (check_bounds_deriv, :102-123). */
 int gb_vina_eval_deriv_noncache(gb_vina* h, const float* confs, int n, const float* v3, float slope, const float* box_begin,
                                 const float* box_end, float* e, float* change);
+/* The empirical term non_cache_cnn::eval_deriv mixes into the CNN forces (lib/non_cache_cnn.cpp:113-140, options
+ * mix_emp_force / mix_emp_energy / empirical_weight): for every heavy atom the precalculate::eval_deriv sum over the
+ * receptor atoms within the cut-off, taken at the atom's position clamped to [box_begin, box_end], then curl(e, deriv, v).
+ * e[n_atoms], deriv[n_atoms][3]; hydrogens give zeros; the caller adds its out-of-box penalties. */
+int gb_vina_noncache_atoms(gb_vina* h, const float* xyz, const int32_t* smina_type, int n_atoms, const float* box_begin,
+                           const float* box_end, float v, float* e, float* deriv);
 /* refine_structure (main/main.cpp:131-171) for n conformations at once: up to five quasi-Newton runs
  * (lib/quasi_newton.cpp:49-83, bfgs with fast_line_search) against non_cache with the out-of-box slope 10, 100, ... until
  * every heavy atom is inside the box (non_cache::within, margin 1e-4).  confs are refined in place; e[n] = the last

@@ -233,10 +233,19 @@ class PoseBatcher {
 struct GridDim { float begin = 0, end = 0; int n = 0; };
 using GridDims = std::array<GridDim, 3>;
 
+class VinaScorer;
+// per-atom empirical term used by NonCacheCNN's mixing (defined after VinaScorer)
+inline void vina_noncache_atoms(VinaScorer& v, const float* xyz, const int32_t* type, int n, const float begin[3], const float end[3],
+                                float cap, std::vector<float>& e, std::vector<float>& deriv);
+
 class NonCacheCNN {
   CNNScorer& scorer_;
   GridDims gd_, cnn_gd_;
   float slope_;
+  // cnn_options::mix_emp_force / mix_emp_energy / empirical_weight (lib/non_cache_cnn.cpp:113-166)
+  VinaScorer* vina_ = nullptr;
+  float emp_weight_ = 1.f;
+  bool mix_force_ = false, mix_energy_ = false;
 
   static bool is_hydrogen(int32_t t) { return t == 0 || t == 1; }
   // non_cache::check_bounds_deriv, lib/non_cache.cpp:102-123
@@ -262,22 +271,43 @@ class NonCacheCNN {
       cnn_gd_[i].n = (int)(inf.dimension / inf.resolution);
     }
   }
-  // eval: loss + penalties ; eval_deriv additionally fills minus_forces[n_atoms][3] (zero for hydrogens)
-  float eval(const float* lig_xyz, const int32_t* lig_type, int n, std::vector<float>* minus_forces = nullptr) {
+  // --cnn_mix_emp_force / --cnn_mix_emp_energy / --cnn_empirical_weight: the empirical (smina) term evaluated directly over
+  // the receptor (vina must have the receptor set) is blended into the forces / the energy of eval_deriv
+  void set_empirical(VinaScorer* vina, float weight, bool mix_force, bool mix_energy) {
+    vina_ = vina; emp_weight_ = weight; mix_force_ = mix_force && vina; mix_energy_ = mix_energy && vina;
+  }
+  // eval (minus_forces == nullptr, lib/non_cache_cnn.cpp:33-54): loss + penalties.
+  // eval_deriv (:79-169): additionally fills minus_forces[n_atoms][3] (zero for hydrogens); v = curl cap of the empirical
+  // term.  With mix_emp_force the forces are (cnn + oob + w (emp + oob_search_box)) / (1 + w); with mix_emp_energy the
+  // energy is (loss + penalties + w emp) / (1 + w) -- the identity test/gnina/test_min.py:45-61 checks to 1e-3.
+  float eval(const float* lig_xyz, const int32_t* lig_type, int n, std::vector<float>* minus_forces = nullptr, float v = 1000.f) {
     float e = 0, aff = 0, loss = 0, var = 0;
     std::vector<float> grad;
     scorer_.score(lig_xyz, lig_type, n, minus_forces != nullptr, aff, loss, var, minus_forces ? &grad : nullptr);
     e += loss;
+    std::vector<float> emp_e, emp_d;
+    const bool mixing = minus_forces && mix_force_;
+    if (mixing) {
+      const float b[3] = {gd_[0].begin, gd_[1].begin, gd_[2].begin}, en[3] = {gd_[0].end, gd_[1].end, gd_[2].end};
+      vina_noncache_atoms(*vina_, lig_xyz, lig_type, n, b, en, v, emp_e, emp_d);
+    }
     if (minus_forces) minus_forces->assign(3 * (size_t)n, 0.f);
     for (int i = 0; i < n; i++) {
       if (lig_type[i] < 0 || lig_type[i] >= 28 || is_hydrogen(lig_type[i])) continue;
-      float d[3] = {0, 0, 0};
-      float pen = check_bounds(gd_, lig_xyz + 3 * i, minus_forces ? d : nullptr);
-      pen += check_bounds(cnn_gd_, lig_xyz + 3 * i, minus_forces ? d : nullptr);
+      float d_emp_box[3] = {0, 0, 0}, d_cnn_box[3] = {0, 0, 0};
+      float pen = check_bounds(gd_, lig_xyz + 3 * i, minus_forces ? d_emp_box : nullptr);
+      pen += check_bounds(cnn_gd_, lig_xyz + 3 * i, minus_forces ? d_cnn_box : nullptr);
       e += pen;
-      if (minus_forces)
-        for (int k = 0; k < 3; k++) (*minus_forces)[3 * i + k] = grad[3 * i + k] + d[k];
+      if (minus_forces) {
+        for (int k = 0; k < 3; k++) {
+          float f = grad[3 * i + k] + d_emp_box[k] + d_cnn_box[k];
+          if (mixing) f = (f + emp_weight_ * (emp_d[3 * i + k] + d_emp_box[k])) / (1.0f + emp_weight_);
+          (*minus_forces)[3 * i + k] = f;
+        }
+        if (mixing && mix_energy_) e += emp_weight_ * emp_e[i];
+      }
     }
+    if (minus_forces && mix_energy_) e /= (1.0f + emp_weight_);
     return e;
   }
 };
@@ -329,6 +359,29 @@ class VinaScorer {
     check(gb_vina_bfgs(h_, confs_inout, n, maxiters, v3, slope, e.data(), nullptr, nullptr));
     return e;
   }
+  // model::eval_deriv with ig = non_cache (lib/non_cache.cpp:126-174): direct receptor sums, box = [begin, end]
+  std::vector<float> eval_deriv_noncache(const float* confs, int n, const float v3[3], float slope, const float begin[3],
+                                         const float end[3], std::vector<float>* change = nullptr) {
+    std::vector<float> e(n), g((size_t)n * (6 + n_tors_));
+    check(gb_vina_eval_deriv_noncache(h_, confs, n, v3, slope, begin, end, e.data(), g.data()));
+    if (change) *change = std::move(g);
+    return e;
+  }
+  // refine_structure (main/main.cpp:131-171) on n poses at once; e = max float for a pose that never entered the box
+  std::vector<float> refine(float* confs_inout, int n, int maxiters, const float v3[3], const float begin[3], const float end[3],
+                            std::vector<int32_t>* within = nullptr) {
+    std::vector<float> e(n);
+    std::vector<int32_t> ok(n);
+    check(gb_vina_refine(h_, confs_inout, n, maxiters, v3, begin, end, e.data(), ok.data(), nullptr));
+    if (within) *within = std::move(ok);
+    return e;
+  }
+  // per-atom empirical term of non_cache_cnn::eval_deriv (lib/non_cache_cnn.cpp:113-140)
+  void noncache_atoms(const float* xyz, const int32_t* type, int n, const float begin[3], const float end[3], float cap,
+                      std::vector<float>& e, std::vector<float>& deriv) {
+    e.assign(n, 0.f); deriv.assign(3 * (size_t)n, 0.f);
+    check(gb_vina_noncache_atoms(h_, xyz, type, n, begin, end, cap, e.data(), deriv.data()));
+  }
   struct ChainOutputs {       // the chains' output_containers, flattened
     int n_chains = 0, S = 0;  // S = num_saved_mins
     std::vector<float> e, conf;
@@ -358,5 +411,10 @@ class VinaScorer {
  private:
   int n_tors_ = 0, n_atoms_ = 0;
 };
+
+inline void vina_noncache_atoms(VinaScorer& v, const float* xyz, const int32_t* type, int n, const float begin[3], const float end[3],
+                                float cap, std::vector<float>& e, std::vector<float>& deriv) {
+  v.noncache_atoms(xyz, type, n, begin, end, cap, e, deriv);
+}
 
 }  // namespace gb

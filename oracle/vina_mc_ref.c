@@ -62,9 +62,18 @@ static void normalize_angle(float *x) { /* quaternion.h:261-281 */
   else if (*x > PI_F) *x -= 2 * PI_F;
   else if (*x < -PI_F) *x += 2 * PI_F;
 }
+/* sin / cos / exp of a float argument, CORRECTLY ROUNDED (evaluated in double, rounded once).  The reference calls
+ * std::sin / std::cos / std::exp on `fl` = float, i.e. whatever sinf / cosf / expf its libm provides; those are not
+ * specified bit for bit (glibc's differ from the correctly rounded value for 1.3 % of the arguments, by one ulp;
+ * measured) and a GPU has no glibc.  The correctly rounded value is what every libm approximates and what both this
+ * restatement and the device code can compute identically, so that BFGS and Monte-Carlo trajectories can be compared
+ * step by step instead of statistically. */
+static float sin_cr(float x) { return (float)sin((double)x); }
+static float cos_cr(float x) { return (float)cos((double)x); }
+static float exp_cr(float x) { return (float)exp((double)x); }
 static void angle_to_q(const float *axis, float angle, float *q) {
   normalize_angle(&angle);
-  float c = cosf(angle / 2), s = sinf(angle / 2);
+  float c = cos_cr(angle / 2), s = sin_cr(angle / 2);
   q[0] = c; q[1] = s * axis[0]; q[2] = s * axis[1]; q[3] = s * axis[2];
 }
 static void qmul(const float *l, const float *r, float *o) {
@@ -414,7 +423,7 @@ int gvo_mc_run_traced(const gvo_field *F, const gvo_lig *L, const gvo_mc_params 
     float cand_e = gvo_lig_eval_grid(F, L, cand, av[1], 0);
     int accept = step == 0 || cand_e < tmp_e;
     if (!accept) { /* metropolis_accept :38-42 */
-      const float pr = expf((tmp_e - cand_e) / P->temperature);
+      const float pr = exp_cr((tmp_e - cand_e) / P->temperature);
       accept = rng_fl(&s, 0, 1) < pr;
     }
     if (accept) {

@@ -118,6 +118,25 @@ int main(int argc, char** argv) {
     const float e = nc.eval(lig_xyz.data(), lig_t.data(), offs[1], &mf);
     const float e0 = nc.eval(lig_xyz.data(), lig_t.data(), offs[1]);
     printf("noncache %.5f %.5f forces %zu\n", e, e0, mf.size());
+    {  // --cnn_mix_emp_force / --cnn_mix_emp_energy (lib/non_cache_cnn.cpp:113-166): with a box that contains the ligand
+       // the blended energy is (CNN loss + w * empirical) / (1 + w), the identity test/gnina/test_min.py:45-61 checks
+      gb::GridDims wide;
+      for (int i = 0; i < 3; i++) { wide[i].begin = -40.0f; wide[i].end = 40.0f; wide[i].n = 8; }
+      gb::VinaScorer vs;
+      vs.set_receptor(rec_xyz.data(), rec_t.data(), hdr[0]);
+      gb::NonCacheCNN plain(s, wide, ctr, 10.0f), mixed(s, wide, ctr, 10.0f);
+      const float w = 0.5f;
+      mixed.set_empirical(&vs, w, true, true);
+      std::vector<float> f0, f1, ee, ed;
+      const float e_plain = plain.eval(lig_xyz.data(), lig_t.data(), offs[1], &f0);
+      const float e_mixed = mixed.eval(lig_xyz.data(), lig_t.data(), offs[1], &f1);
+      const float b3[3] = {-40.f, -40.f, -40.f}, e3[3] = {40.f, 40.f, 40.f};
+      vs.noncache_atoms(lig_xyz.data(), lig_t.data(), offs[1], b3, e3, 1000.f, ee, ed);
+      double emp = 0, worst = 0;
+      for (float x : ee) emp += x;
+      for (size_t i = 0; i < f0.size(); i++) worst = std::max(worst, (double)std::fabs(f1[i] - (f0[i] + w * ed[i]) / (1 + w)));
+      printf("mixing %.6f %.6f %.6f %.3g\n", e_plain, e_mixed, emp, worst);
+    }
   } catch (const std::exception& e) {
     printf("ERROR %s\n", e.what());
     return 1;

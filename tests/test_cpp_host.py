@@ -63,5 +63,18 @@ def test_cpp_host_scores_match_oracle(golden_dir, tmp_path):
     loss0 = om.score(kat["rec_xyz"], kat["rec_types"], lx[:offs[1]], lt[:offs[1]], offs[:2], dtype=torch.float64)[2][0]
     heavy = lx[:offs[1]][lt[:offs[1]] > 1]
     pen = 10.0 * (np.clip(np.abs(heavy) - 1.0, 0, None).sum() + np.clip(np.abs(heavy) - 11.75, 0, None).sum())
+    # empirical mixing: total = (CNN loss + w * empirical) / (1 + w), forces blended the same way (test_min.py:45-61, 1e-3)
+    e_plain, e_mixed, emp, worst = (float(x) for x in by_tag["mixing"][1:5])
+    assert abs(e_mixed - (e_plain + 0.5 * emp) / 1.5) < 1e-3 * max(1.0, abs(e_mixed)) and worst < 1e-5
+    from oracle.vina import VinaOracle
+    from oracle.vina_mc import DockOracle
+    vo = VinaOracle()
+    dk = DockOracle(vo, {}, [-40.0] * 3, [40.0] * 3, [8, 8, 8], dict(local_xyz=np.zeros((1, 3), np.float32), types=np.array([2], np.int32),
+                    seg_parent=np.array([-1], np.int32), seg_begin=np.array([0], np.int32), seg_end=np.array([1], np.int32),
+                    seg_rel_origin=np.zeros((1, 3), np.float32), seg_rel_axis=np.zeros((1, 3), np.float32),
+                    pair_a=np.zeros(0, np.int32), pair_b=np.zeros(0, np.int32), gyration_radius=1.0), slope=0.0)
+    dk.use_noncache(kat["rec_xyz"], kat["rec_types"])
+    emp_ref = sum(dk.noncache_atom(int(t), x)[0] for x, t in zip(lx[:offs[1]], lt[:offs[1]]) if t > 1)
+    assert abs(emp - emp_ref) < 1e-5 * max(1.0, abs(emp_ref))
     e, e0 = float(by_tag["noncache"][1]), float(by_tag["noncache"][2])
     assert abs(e - (loss0 + pen)) < 1e-3 * max(1.0, abs(loss0 + pen)) and abs(e0 - (loss0 + pen)) < 3e-3 * max(1.0, abs(e0))

@@ -38,9 +38,9 @@ def test_overlay_model_matches_reference_pt(golden_dir, name):
         assert np.abs(out[4] - g).max() <= 2e-4 * max(1.0, np.abs(g).max())
 
 
-def _minimise(s, x0, pack, unpack):
+def _minimise(s, n_atoms, pack, unpack):
     from scipy.optimize import minimize
-    types = np.full(len(x0), C_TYPE, np.int32)
+    types = np.full(n_atoms, C_TYPE, np.int32)
 
     def f(p):
         xyz = unpack(p).astype(np.float32)
@@ -55,7 +55,7 @@ def test_single_atom_is_pulled_onto_the_receptor_atom(golden_dir):
     s = _scorer(golden_dir, "overlap")
     s.set_receptor(np.zeros((1, 3), np.float32), np.array([C_TYPE], np.int32))
     start = np.array([[1.0, 1.0, 1.0]])
-    xyz, r = _minimise(s, start, lambda p, g: start.ravel().copy() if p is None else g.ravel(), lambda p: p.reshape(1, 3))
+    xyz, r = _minimise(s, 1, lambda p, g: start.ravel().copy() if p is None else g.ravel(), lambda p: p.reshape(1, 3))
     assert np.linalg.norm(xyz[0]) < 0.1, (xyz, r.message)
 
 
@@ -80,6 +80,6 @@ def test_two_atoms_are_pulled_onto_the_receptor_pair(golden_dir):
         du_dph = np.array([-np.sin(th) * np.sin(ph), np.sin(th) * np.cos(ph), 0.0])
         d = h * (g[1] - g[0])
         return np.concatenate([g[0] + g[1], [d @ du_dth, d @ du_dph]])
-    xyz, r = _minimise(s, None, pack, unpack)
+    xyz, r = _minimise(s, 2, pack, unpack)
     d = np.linalg.norm(xyz[:, None, :] - rec[None], axis=2)
     assert (d.min(axis=1) < 0.1).all() and len(set(d.argmin(axis=1))) == 2, (xyz, r.message)

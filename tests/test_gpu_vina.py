@@ -104,3 +104,53 @@ def test_spline_tables_and_spline_pair_terms_match_oracle():
     for i, x in enumerate(X):
         er, gr = d.eval_deriv(x)
         assert abs(e[i] - er) <= 2e-5 * max(1.0, abs(er)) and np.abs(g[i] - gr).max() <= 2e-4 * max(1.0, np.abs(gr).max())
+
+
+@pytest.mark.parametrize("seed", [1, 20220616, 987654321])
+def test_gninacheck_random_molecules(seed):
+    """The reference's `gninacheck` tests (test/gnina/test_cache.cu, test_gpucode.cpp) hold no numbers: they draw random
+    molecules (test_utils.cpp make_mol: every smina type incl. hydrogens and metals, overlapping atoms allowed), build the
+    cache over the ligand's bounding box (granularity 0.375, slope 10, v = 10) and require two live implementations to
+    agree to 0.01.  Same generator, same set-up, device vs oracle, at the north star's 1e-6 instead of 0.01:
+      V4  cache::populate         on the box grid (sub-sampled in the oracle: the scalar C loop is slow)
+      V5  cache::eval_deriv       energy and forces of the ligand, slope 10, v = 10
+      V6  eval_interacting_pairs  all atom pairs of a random molecule as one rigid body (test_eval_intra)"""
+    from gnina_b200 import synth
+    from gnina_b200.vina import VinaScorer
+    from oracle.vina import VinaOracle
+    from oracle.vina_mc import DockOracle
+    rs = np.random.RandomState(seed)                      # seed logged by pytest's parametrisation
+    lig_xyz, lig_t = synth.make_gninacheck_mol(rs, min_atoms=20, max_atoms=60, max_x=5, max_y=5, max_z=5)
+    lo, hi = lig_xyz.min(0), lig_xyz.max(0)
+    center, span = (hi + lo) / 2, hi - lo
+    n = np.ceil(span / 0.375).astype(np.int32)             # test_cache.cu:77-82
+    begin = (center - 0.375 * n / 2).astype(np.float32)
+    end = (begin + 0.375 * n).astype(np.float32)
+    rec_xyz, rec_t = synth.make_gninacheck_mol(rs, 0, 10, 500, *(np.abs(np.stack([lo, hi])).max(0) + 8.0))
+    v, o = VinaScorer(), VinaOracle()
+    v.set_receptor(rec_xyz, rec_t)
+    needed = sorted(set(int(t) for t in lig_t if t > 1))   # get_movable_atom_types: heavy types only
+    v.cache_build(begin, end, n, needed)
+    grids = {t: v.cache_grid(t) for t in needed}
+    t0 = needed[len(needed) // 2]
+    ref = o.cache_populate(begin, end, n, rec_xyz, rec_t, t0)
+    assert np.abs(grids[t0] - ref).max() <= TOL * max(1.0, np.abs(ref).max())
+    offs = np.array([0, len(lig_t)], np.int32)
+    e, d = v.cache_eval(lig_xyz, lig_t, offs, slope=10.0, v=10.0)
+    er, dr = VinaOracle.cache_eval(grids, begin, end, n, lig_xyz, lig_t, 10.0, 10.0)
+    assert abs(e[0] - er) <= TOL * max(1.0, abs(er))
+    assert np.abs(d - dr).max() <= TOL * max(1.0, np.abs(dr).max())
+    # V6: one rigid segment, every pair (i < j), curl cap 10 on the pairs like single_point_calc's v
+    na = len(lig_t)
+    pa, pb = np.triu_indices(na, 1)
+    lig = dict(local_xyz=lig_xyz - lig_xyz[0], types=lig_t, seg_parent=np.array([-1], np.int32), seg_begin=np.array([0], np.int32),
+               seg_end=np.array([na], np.int32), seg_rel_origin=np.zeros((1, 3), np.float32), seg_rel_axis=np.zeros((1, 3), np.float32),
+               pair_a=pa.astype(np.int32), pair_b=pb.astype(np.int32), gyration_radius=1.0)
+    v.set_ligand(lig)
+    dk = DockOracle(o, grids, begin, end, n, lig, slope=10.0)
+    conf = np.zeros((1, 7), np.float32); conf[0, :3] = lig_xyz[0]; conf[0, 3] = 1.0
+    caps = (10.0, 10.0, 10.0)
+    e2, g2 = v.eval_deriv(conf, caps, slope=10.0)
+    e2r, g2r = dk.eval_deriv(conf[0], caps)
+    assert abs(e2[0] - e2r) <= TOL * max(1.0, abs(e2r))
+    assert np.abs(g2[0] - g2r).max() <= 4e-6 * max(1.0, np.abs(g2r).max())
