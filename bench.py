@@ -31,10 +31,24 @@ sys.path.insert(0, ROOT)
 
 MODEL = "crossdock_default2018"
 FLOP_PER_EVAL = {"default2018": 0.998148096e9, "dense": 4.541571072e9, "default2017": 1.122729984e9}
-CONV1_FLOP = 668_860_416.0  # conv3^3 28->32 @24^3
-# dram__bytes_read.sum + dram__bytes_write.sum of the conv1 launch, ncu --set full, 1024 poses per launch
-# (profiles/r1e_ncu_conv1_tcgen05.csv: 1.095620 GB + 0.863929 GB) -> per pose
-CONV1_NCU_DRAM_BYTES_PER_POSE = (1.095620e9 + 0.863929e9) / 1024
+CONV1_FLOP = 668_860_416.0  # unit1_conv: conv3^3 28->32 @24^3
+CONV2_FLOP = 28_311_552.0   # unit2_conv: conv1^3 32->32 @24^3, computed by the same (fused) kernel
+
+
+def ncu_traffic(kernel_key):
+    """DRAM bytes per pose of the dominant kernel from the latest committed `ncu --set full` capture of THIS build
+    (profiles/traffic.json, written by tools/ncu_traffic.py from the .ncu-rep: dram__bytes_read.sum + dram__bytes_write.sum
+    divided by the poses of the captured launch) -> (bytes per pose, source) or (None, None).  DRAM counters cannot be read
+    inside a timed run; a capture that does not name this kernel yields null rather than a stale constant."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        d = json.load(open(path))
+        e = d.get(kernel_key)
+        if e:
+            return float(e["dram_bytes_per_pose"]), e.get("source", "profiles/traffic.json")
+    except (OSError, ValueError, KeyError):
+        pass
+    return None, None
 
 
 def peaks():
@@ -359,6 +373,10 @@ def main():
     ap.add_argument("--model", default="", help="model name(s), comma separated; 'default' = gnina's default 3-model ensemble")
     ap.add_argument("--overlap", type=int, default=-1, help="voxeliser/network stream overlap (library option)")
     ap.add_argument("--max-batch", type=int, default=0)
+    ap.add_argument("--workload", default="rescoring", choices=["rescoring", "screen", "minimize"],
+                    help="rescoring = BASELINE config 2 (the headline); screen = config 4 (100k ragged ligands x dense_ensemble, "
+                         "sharded over the GPUs); minimize = config 5 (1k poses with atom gradients, sharded)")
+    ap.add_argument("--ligands", type=int, default=100000, help="total ligands of --workload screen (all GPUs together)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -380,6 +398,9 @@ def main():
     from gnina_b200 import CNNScorer
     W = max(args.warmup, 3)
 
+    if args.workload != "rescoring":
+        run_other_workload(args, rank, world, local, dev, dist)
+        return
     rec_xyz, rec_t, lig_xyz, lig_t, offs = make_workload(args.poses, seed=1 + rank)
     names = [MODEL] if not args.model else ([] if args.model == "default" else args.model.split(","))
     s = CNNScorer(names, device=local)
@@ -400,7 +421,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    gathered = [torch.empty(4 * args.poses, device=dev) for _ in range(world)] if world > 1 else None
+    gathered = torch.empty(world * 4 * args.poses, device=dev) if world > 1 else None
+    mine = torch.empty(4 * args.poses, device=dev)
 
     # ---------------- device-resident: value ----------------
     s.stage(lig_xyz, lig_t, offs)
@@ -442,8 +464,9 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.steps):
         out_host = s.score_batch(lig_xyz, lig_t, offs)           # H2D poses, kernels, D2H 4 x n floats
-        if world > 1:                                             # final score gather (NCCL), SURVEY.md §8e
-            dist.all_gather(gathered, torch.from_numpy(np.concatenate(out_host)).to(dev))
+        if world > 1:                                             # final score gather (NCCL), SURVEY.md §8e:
+            s.fetch_device(mine.data_ptr())                       # straight from the handle's device results, no host bounce
+            dist.all_gather_into_tensor(gathered, mine)
     barrier()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], device=dev, dtype=torch.float64)
@@ -454,6 +477,29 @@ def main():
     h2d = n_atoms * (16 + 4) + (args.poses + 1) * 4 + args.poses * 12
     d2h = 4 * 4 * args.poses
 
+    # ---------------- strong scaling: config 2's FIXED 10k poses split over the ranks ----------------
+    strong = None
+    if world > 1:
+        per = args.poses // world
+        lo = rank * per
+        s.stage(lig_xyz[offs[lo]:offs[lo + per]], lig_t[offs[lo]:offs[lo + per]], offs[lo:lo + per + 1] - offs[lo])
+        for _ in range(W):
+            s.run_staged()
+        barrier()
+        evs2 = []
+        for _ in range(args.steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            s.run_staged()
+            b.record(stream)
+            evs2.append((a, b))
+        barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs2)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        strong = {"value": per * world * args.steps / (float(t.item()) * 1e-3), "unit": "poses/s", "total_poses": per * world,
+                  "poses_per_gpu": per, "scaling": "strong", "note": "BASELINE config 2's fixed 10k poses split over the ranks, device-resident"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -467,12 +513,16 @@ def main():
     if conv1_keys:
         k = conv1_keys[0]
         tot_ms, cnt = prof[k]
-        flops = CONV1_FLOP * args.poses * args.steps
+        fused = "pw2" in k   # the fused kernel also computes unit2_conv
+        flops = (CONV1_FLOP + (CONV2_FLOP if fused else 0.0)) * args.poses * args.steps
         ach = flops / (tot_ms * 1e-3) / 1e12
+        per_pose, src = ncu_traffic(k)
         roof = {"kernel": k, "bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s",
-                "frac": ach / tf_sus,
-                "traffic": (CONV1_NCU_DRAM_BYTES_PER_POSE * args.poses * args.steps / max(cnt, 1)) if k.startswith("tc_conv1") else None,
-                "traffic_unit": "DRAM bytes per launch (ncu capture profiles/r1e_ncu_conv1_tcgen05.csv, scaled by poses per launch)",
+                "frac": ach / tf_sus, "frac_of_burst_peak": ach / tf_burst,
+                "algorithmic_flop_per_pose": CONV1_FLOP + (CONV2_FLOP if fused else 0.0),
+                "traffic": (per_pose * args.poses * args.steps / max(cnt, 1)) if per_pose else None,
+                "traffic_unit": "DRAM bytes per launch = ncu dram__bytes_read.sum + dram__bytes_write.sum per pose (%s) x poses per launch" % src
+                                if per_pose else None,
                 "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json)" % which,
                 "launches": cnt, "avg_launch_ms": tot_ms / max(cnt, 1)}
     total_ms = sum(v[0] for v in prof.values())
@@ -491,6 +541,8 @@ def main():
             "kernel_time_share": shares,
             "model_tflops": value * FLOP_PER_EVAL["default2018"] / 1e12,
             "checksum": float(np.sum(res[0], dtype=np.float64))}
+    if strong:
+        line["strong_scaling"] = strong
     if not args.no_gpu_reference and world == 1 and not args.model:
         del flush
         torch.cuda.empty_cache()
@@ -503,6 +555,82 @@ def main():
     if not args.no_cpu_baseline and world == 1:   # the CPU port is timed beside the N = 1 run only
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_other_workload(args, rank, world, local, dev, dist):
+    """BASELINE configs 4 and 5 as sharded, SCALE-able bench lines (same JSON contract, their own metric):
+      screen   : config 4 -- args.ligands ragged ligands (N_heavy ~ U[15,45]) x 1 pose x `--cnn dense_ensemble` (20 models),
+                 ligands split over the ranks (strong scaling: the total is fixed), results gathered with NCCL from device
+                 buffers; metric ligands/s through the public call (host buffers in, four floats per ligand out)
+      minimize : config 5 -- 1000 poses with atom gradients (G2 + N5), default2018, split over the ranks"""
+    import torch
+    from gnina_b200 import CNNScorer, synth
+    rec_xyz, rec_t = synth.make_receptor()
+    W = max(args.warmup, 1)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    if args.workload == "screen":
+        total = args.ligands
+        per = total // world
+        # every rank generates only its own shard (deterministic per ligand index range)
+        sx, st, so = synth.make_screen(min(per, 4096), seed=3 + rank)
+        reps = -(-per // (len(so) - 1))                     # the shard = the 4096 generated ligands repeated (timing only)
+        s = CNNScorer(["dense_ensemble"], device=local, precision=1)
+        s.set_receptor(rec_xyz, rec_t)
+        nl = len(so) - 1
+        mine = torch.empty(4 * nl, device=dev)
+        gathered = torch.empty(world * 4 * nl, device=dev) if world > 1 else None
+
+        def step():
+            done = 0
+            for r in range(reps):
+                k = min(nl, per - done)
+                s.score_batch(sx[:so[k]], st[:so[k]], so[:k + 1])
+                if world > 1:
+                    s.fetch_device(mine.data_ptr())
+                    dist.all_gather_into_tensor(gathered, mine)
+                done += k
+        metric, unit, n_units = "ligands/sec virtual screen (dense_ensemble, 20 models, 48^3x28ch)", "ligands/s", per * world
+        cfg = {"workload": "config 4: %d ragged ligands x dense_ensemble (20 models), %d per GPU in batches of %d" % (per * world, per, nl),
+               "parallelism": "ligand-sharded x%d, NCCL all_gather of the device results per batch" % world}
+    else:
+        total = 1000
+        per = total // world
+        lx0, lt0 = synth.make_ligand()
+        lx, offs = synth.make_poses(lx0, per, seed=5 + rank)
+        lt = np.tile(lt0, per)
+        s = CNNScorer([MODEL], device=local, precision=1)
+        s.set_receptor(rec_xyz, rec_t)
+
+        def step():
+            s.score_grad_batch(lx, lt, offs)
+        metric, unit, n_units = "poses/sec with atom gradients (CNN minimisation step, default2018)", "poses/s", per * world
+        cfg = {"workload": "config 5: %d poses with ligand-atom gradients (forward + backward), %d per GPU" % (per * world, per),
+               "parallelism": "pose-sharded x%d" % world}
+    for _ in range(W):
+        step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        v = n_units * args.steps / float(t.item())
+        print(json.dumps({"metric": metric, "value": v, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": W,
+                          "ms_per_step": 1e3 * float(t.item()) / args.steps, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": cfg,
+                          "e2e": {"value": v, "unit": unit, "note": "timed through the public call with host buffers (the value IS end to end)"},
+                          "gpu_launches": int(s.kernel_launches())}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -655,6 +655,17 @@ int gb_cnn_fetch(gb_cnn* h, float* score, float* affinity, float* loss, float* v
   GB_API_END
 }
 
+int gb_cnn_fetch_device(gb_cnn* h, float* device_dst) {
+  GB_API_BEGIN
+  GB_CHECK(h && device_dst, "null argument");
+  GB_CUDA(cudaSetDevice(h->device));
+  const int n = h->n_staged;
+  if (n == 0) return GB_OK;
+  GB_CUDA(cudaMemcpyAsync(device_dst, h->d_final.p, 4 * (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  GB_CUDA(cudaStreamSynchronize(h->stream));
+  GB_API_END
+}
+
 int gb_cnn_score_batch(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type, const int32_t* pose_offsets,
                        int n_poses, const float* centers, float* score, float* affinity, float* loss,
                        float* variance) {

@@ -208,8 +208,7 @@ struct ConvTcSmem {
 };
 
 // Per-MMA start-address offsets (16-byte units) of the A slab and the B weight block, one table per kernel
-// configuration, in constant memory: the issue loop reads them with uniform loads (ULDC) straight into the uniform
-// registers UTCHMMA consumes — no per-thread arithmetic, no uniform-register spills.
+// configuration, in constant memory (uniform loads straight into the uniform registers UTCHMMA consumes).
 struct MmaOff { uint32_t a, b; };
 __constant__ MmaOff c_mma_off[4][36];
 template <int CIN, int DD> struct ConvCfg {
@@ -341,6 +340,10 @@ __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
               if (xo >= fresh_lo) ptx::mma_f16_ss_lohi<0>(tm, a_lo_base + a0, kDescHi, bl, kDescHi, ptx::idesc_f16(128, 32));
               else ptx::mma_f16_ss_lohi<1>(tm, a_lo_base + a0, kDescHi, bl, kDescHi, ptx::idesc_f16(128, 32));
             }
+            // Operand offsets from a __constant__ table, rolled loop.  (r2i: a fully unrolled loop with immediate
+            // offsets made conv3 / conv5 17 % SLOWER -- the issuing thread blocks in UTCHMMA while the MMA queue is full, so
+            // instructions per MMA do not matter, code size does.  The clock64 timeline of r2j shows what bounds these
+            // kernels: the tensor pipe's shared-memory operand reads -- 4 KB of A + 3 KB of B per N = 96 MMA at 128 B/clk.)
             constexpr int kCfg = ConvCfg<CIN, DD>::id;
             constexpr int kNumMma = 9 * (CIN / 16);
             if (nr == 1) {
@@ -753,26 +756,33 @@ template <int CIN, int DD>
 static void launch_conv_tc(const ConvTc& c, const ActLayout& L, const uint4* xin, __half* out, int n_poses, cudaStream_t s,
                            uint4* out_planar = nullptr, int out_c8tot = 0, int out_c8off = 0, int out_lp = 0, int relu = 1) {
   using S = ConvTcSmem<CIN>;
-  std::unique_lock<std::mutex> init_lock(tc_init_mutex());
-  static bool attr_set = false;
-  if (!attr_set) {
-    GB_CUDA(cudaFuncSetAttribute(conv3_tc_kernel<CIN, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    attr_set = true;
-  }
   GB_CHECK(c.cin == CIN && L.D == DD, "conv shape");
-  static bool table_set = false;
-  if (!table_set) {
-    MmaOff h[36] = {};
-    const int P = DD + 2, SL = 128 + 2 * (P + 1), C8 = CIN / 8;
-    int m = 0;
-    for (int t9 = 0; t9 < 9; t9++)
-      for (int ks = 0; ks < CIN / 16; ks++, m++) {
-        h[m].a = (uint32_t)((P + 1) + (t9 / 3 - 1) * P + (t9 % 3 - 1) + 2 * ks * SL);
-        h[m].b = (uint32_t)((t9 * C8 + 2 * ks) * 96);
-      }
-    GB_CUDA(cudaMemcpyToSymbol(c_mma_off, h, sizeof(h), sizeof(MmaOff) * 36 * ConvCfg<CIN, DD>::id));
-    table_set = true;
+  // function attributes and occupancy are per DEVICE (one process may own handles on several GPUs)
+  static bool attr_set[64] = {};
+  static int ctas_per_sm_dev[64] = {}, n_sm_dev[64] = {};
+  int dev = 0;
+  GB_CUDA(cudaGetDevice(&dev));
+  GB_CHECK(dev >= 0 && dev < 64, "device index");
+  {
+    std::lock_guard<std::mutex> init_lock(tc_init_mutex());
+    if (!attr_set[dev]) {
+      GB_CUDA(cudaFuncSetAttribute(conv3_tc_kernel<CIN, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+      GB_CUDA(cudaDeviceGetAttribute(&n_sm_dev[dev], cudaDevAttrMultiProcessorCount, dev));
+      GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm_dev[dev], conv3_tc_kernel<CIN, DD>, 192, S::kTotal));
+      MmaOff h[36] = {};
+      const int P = DD + 2, SL = 128 + 2 * (P + 1), C8 = CIN / 8;
+      int m = 0;
+      for (int t9 = 0; t9 < 9; t9++)
+        for (int ks = 0; ks < CIN / 16; ks++, m++) {
+          h[m].a = (uint32_t)((P + 1) + (t9 / 3 - 1) * P + (t9 % 3 - 1) + 2 * ks * SL);
+          h[m].b = (uint32_t)((t9 * C8 + 2 * ks) * 96);
+        }
+      GB_CUDA(cudaMemcpyToSymbol(c_mma_off, h, sizeof(h), sizeof(MmaOff) * 36 * ConvCfg<CIN, DD>::id));
+      if (ctas_per_sm_dev[dev] < 1) ctas_per_sm_dev[dev] = 1;
+      attr_set[dev] = true;
+    }
   }
+  const int ctas_per_sm = ctas_per_sm_dev[dev], n_sm = n_sm_dev[dev];
   ConvTcParams p;
   p.xin = xin; p.wp = c.wp; p.bias = c.bias; p.out = out;
   p.D = L.D; p.P = L.P; p.G = L.G; p.T = L.T; p.NB = c.cout / 32; p.Lp = L.Lp; p.Cout = c.cout; p.n_poses = n_poses;
@@ -782,16 +792,7 @@ static void launch_conv_tc(const ConvTc& c, const ActLayout& L, const uint4* xin
   p.dbg = dbg;
   p.n_groups = (n_poses + L.G - 1) / L.G;
   const int n_items = p.n_groups * L.T * p.NB;
-  static int ctas_per_sm = 0, n_sm = 0;
-  if (!ctas_per_sm) {
-    int dev = 0;
-    GB_CUDA(cudaGetDevice(&dev));
-    GB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, conv3_tc_kernel<CIN, DD>, 192, S::kTotal));
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-  }
   int grid = n_sm * ctas_per_sm;
-  init_lock.unlock();
   static const int persist = getenv("GB_TC_PERSIST") ? atoi(getenv("GB_TC_PERSIST")) : (CIN == 64 ? 1 : 0);
   if (persist == 0) grid = n_items;            // experiment: one item per CTA
   else if (persist > 1) grid = n_sm * persist;  // experiment: force CTAs per SM

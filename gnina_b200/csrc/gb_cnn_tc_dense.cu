@@ -177,7 +177,6 @@ struct DenseConvParams {
   const float* corr;  // [27][16]
   int KS, C8tot, c8_off, G, T, Lp, n_poses, n_groups;
 };
-__constant__ uint32_t c_dense_aoff[3][9];  // per D config: slab start offset (16 B units) of each (dy,dz) tap
 
 constexpr int kDnStages = 4;
 constexpr int kDnWBytes = 9 * 2 * 48 * 16;  // 13,824 B per 16-channel K block
@@ -277,9 +276,11 @@ __global__ void __launch_bounds__(192) dense_conv_tc_kernel(const DenseConvParam
         const uint32_t a_lo_base = a_lo_fixed | (ptx::smem_u32(s_stage + (size_t)st * kStageBytes) >> 4);
         if (ptx::elect_one()) {
           if (hi >= lo) {
-#pragma unroll 1
+            // unrolled, compile-time operand offsets (the kernels are MMA-issue bound, see conv3_tc_kernel)
+#pragma unroll
             for (int t9 = 0; t9 < 9; t9++)
-              ptx::mma_f16_ss_lohi<1>(tm, a_lo_base + c_dense_aoff[DenseCfg<DD>::id][t9], kDescHi, bl + (uint32_t)(t9 * 2 * 48), kDescHi, idesc);
+              ptx::mma_f16_ss_lohi<1>(tm, a_lo_base + (uint32_t)((DD + 3) + (t9 / 3 - 1) * (DD + 2) + (t9 % 3 - 1)), kDescHi,
+                                      bl + (uint32_t)(t9 * 2 * 48), kDescHi, idesc);
           }
           ptx::tc_commit(&empty[st]);
           if (xi == xi_hi) ptx::tc_commit(&wempty[wb]);
@@ -339,16 +340,16 @@ static void launch_dense_conv(const DenseLayerTc& L, const ActLayout& A, uint4* 
   constexpr int P = DD + 2, SL = 128 + 2 * (P + 1);
   constexpr int kStageBytes = ((2 * SL * 16) + 127) / 128 * 128;
   constexpr int kSmem = 2 * kDnWBytes + kDnStages * kStageBytes + 16 * 8 + 16 + (16 + 27 * 16) * 4 + 64;
-  std::unique_lock<std::mutex> init_lock(tc_init_mutex());
-  static bool init = false;
-  if (!init) {
-    GB_CUDA(cudaFuncSetAttribute(dense_conv_tc_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    uint32_t h[9];
-    for (int t9 = 0; t9 < 9; t9++) h[t9] = (uint32_t)((P + 1) + (t9 / 3 - 1) * P + (t9 % 3 - 1));
-    GB_CUDA(cudaMemcpyToSymbol(c_dense_aoff, h, sizeof(h), sizeof(uint32_t) * 9 * DenseCfg<DD>::id));
-    init = true;
+  {
+    std::lock_guard<std::mutex> init_lock(tc_init_mutex());
+    static bool init[64] = {};   // per device
+    int dev = 0;
+    GB_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !init[dev]) {
+      GB_CUDA(cudaFuncSetAttribute(dense_conv_tc_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+      init[dev] = true;
+    }
   }
-  init_lock.unlock();
   DenseConvParams p;
   p.xin = buf; p.xout = buf; p.wp = L.wp; p.bias = L.bias; p.corr = L.corr;
   p.KS = L.cin / 16; p.C8tot = C8tot; p.c8_off = c8_off; p.G = A.G; p.T = A.T; p.Lp = A.Lp; p.n_poses = n_poses;
@@ -473,10 +474,12 @@ static void launch_bottleneck(const PointwiseGen& pw, const uint4* xin, const Ac
   const int smem = C * (C + 8) * (int)sizeof(__half) + C * (int)sizeof(float);
   {
     std::lock_guard<std::mutex> lk(tc_init_mutex());
-    static bool init = false;
-    if (!init) {
+    static bool init[64] = {};   // per device
+    int dev = 0;
+    GB_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !init[dev]) {
       GB_CUDA(cudaFuncSetAttribute(bottleneck_maxpool_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      init = true;
+      init[dev] = true;
     }
   }
   GB_CHECK(pw.c == C, "bottleneck channels");

@@ -25,6 +25,7 @@
 //   Y1 (0.88 MB per pose) never exists in HBM and the pointwise kernel is gone (round 1: 11 % of the step).
 //
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue.
+#include <cstdio>
 #include <cstdlib>
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -71,7 +72,14 @@ struct FusedParams {
   const float* bias2;  // [32]
   __half* xout;        // X2: chunk-planar D = 12 (make_layout(12, Gn, 32))
   int out_lp, out_G, n_poses, n_groups;
+  // timeline instrumentation (GB_TC_FUSED_TRACE=<file>): clock64 stamps of CTA 0's producer / MMA / epilogue warps for
+  // the first kTracePlanes planes: [role 3][plane][8]
+  unsigned long long* trace;
 };
+constexpr int kTracePlanes = 96;
+__device__ __forceinline__ void tr(unsigned long long* t, int role, uint32_t plane, int k) {
+  if (t && blockIdx.x == 0 && plane < (uint32_t)kTracePlanes && (threadIdx.x & 31) == 0) t[(role * kTracePlanes + plane) * 8 + k] = clock64();
+}
 
 __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -80,7 +88,10 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4],
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__constant__ uint32_t c_fused_off[18][2];  // per (tap, k step): A start offset, B row offset (16-byte units)
+// per MMA m = tap * 2 + k step (tap = (dy+1) * 3 + (dz+1)): start-address offsets of the A slab and of the B weight block,
+// in 16-byte units -- compile-time constants of the tile geometry
+__host__ __device__ constexpr uint32_t off_a(int m) { return (uint32_t)(((m >> 1) / 3) * kSlabZ + ((m >> 1) % 3) + 2 * (m & 1) * (kChunkBytes >> 4)); }
+__host__ __device__ constexpr uint32_t off_b(int m) { return (uint32_t)(((m >> 1) * 4 + 2 * (m & 1)) * 96); }
 
 template <bool kTcPw>
 __global__ void __launch_bounds__(192) conv1_pw2_pool_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
@@ -137,7 +148,9 @@ __global__ void __launch_bounds__(192) conv1_pw2_pool_kernel(const __grid_consta
       const int zb = item % kZBlocks, k = (item / kZBlocks) % kRowTiles, g = item / (kZBlocks * kRowTiles);
       for (int it = 0; it < kD; it++, gp++) {
         const uint32_t st = gp % kStages, ph = (gp / kStages) & 1;
+        tr(p.trace, 0, gp, 0);
         ptx::mbar_wait(&empty[st], ph ^ 1);
+        tr(p.trace, 0, gp, 1);
         if (ptx::elect_one()) {
           ptx::mbar_expect_tx(&full[st], kStageBytes);
           // box = {10 z x 8 ch, 18 rows, 4 chunks, 1 plane} at (z0 - 1, R0 - 1) = (8 zb, 16 k); rows past the group are zero-filled
@@ -177,7 +190,9 @@ __global__ void __launch_bounds__(192) conv1_pw2_pool_kernel(const __grid_consta
       for (int it = 0; it < kD; it++, gp++) {
         // planes committed at least one input plane ago are complete (or about to be) and staged: their pointwise MMAs go
         // into the queue now, ahead of this input plane's convolution MMAs; the most recent commit is left for next time
+        tr(p.trace, 1, gp, 0);
         if (kTcPw && committed > 0) issue_pw_until(committed - 1);
+        tr(p.trace, 1, gp, 1);
         const int xi = it + 1;
         const uint32_t st = gp % kStages, ph = (gp / kStages) & 1;
         const int lo = xi > 1 ? xi - 1 : 1, hi = xi < kD ? xi + 1 : kD;
@@ -201,7 +216,9 @@ __global__ void __launch_bounds__(192) conv1_pw2_pool_kernel(const __grid_consta
             }
           }
         }
+        tr(p.trace, 1, gp, 2);
         wait_service(&full[st], ph);
+        tr(p.trace, 1, gp, 3);
         ptx::tc_fence_after();
         const uint32_t a_lo_base = a_lo_fixed | (ptx::smem_u32(s_stage + (size_t)st * kStageBytes) >> 4);
         if (ptx::elect_one()) {
@@ -214,18 +231,21 @@ __global__ void __launch_bounds__(192) conv1_pw2_pool_kernel(const __grid_consta
           }
           // the issue loop stays inside ONE elected region (ptxas then keeps UTCHMMA on the uniform datapath without
           // re-electing per instruction; r2d: electing per MMA cost ~1 ms per 10 k poses)
+          // Fully unrolled with compile-time operand offsets: per MMA the uniform datapath executes two adds and the
+          // UTCHMMA.  (r2h: with the offsets in a __constant__ table the loop cost ~14 uniform instructions per MMA, a
+          // dependent chain through a constant load, and the ISSUE of the MMAs -- not the tensor pipe, not memory -- bounded
+          // the kernel: two extra instructions per MMA cost 25 %, issuing every MMA twice only 24 %.)
           if (nr == 1) {
             const uint32_t tm0 = r_tm[0], id0 = r_idesc[0], bl0 = b_lo_base + r_boff[0];
-#pragma unroll 1
-            for (int m = 1; m < 18; m++) ptx::mma_f16_ss_lohi<1>(tm0, a_lo_base + c_fused_off[m][0], kDescHiA, bl0 + c_fused_off[m][1], kDescHiB, id0);
+#pragma unroll
+            for (int m = 1; m < 18; m++) ptx::mma_f16_ss_lohi<1>(tm0, a_lo_base + off_a(m), kDescHiA, bl0 + off_b(m), kDescHiB, id0);
           } else {
             const uint32_t tm0 = r_tm[0], id0 = r_idesc[0], bl0 = b_lo_base + r_boff[0];
             const uint32_t tm1 = r_tm[1], id1 = r_idesc[1], bl1 = b_lo_base + r_boff[1];
-#pragma unroll 1
+#pragma unroll
             for (int m = 1; m < 18; m++) {
-              const uint32_t oa = c_fused_off[m][0], ob = c_fused_off[m][1];
-              ptx::mma_f16_ss_lohi<1>(tm0, a_lo_base + oa, kDescHiA, bl0 + ob, kDescHiB, id0);
-              ptx::mma_f16_ss_lohi<1>(tm1, a_lo_base + oa, kDescHiA, bl1 + ob, kDescHiB, id1);
+              ptx::mma_f16_ss_lohi<1>(tm0, a_lo_base + off_a(m), kDescHiA, bl0 + off_b(m), kDescHiB, id0);
+              ptx::mma_f16_ss_lohi<1>(tm1, a_lo_base + off_a(m), kDescHiA, bl1 + off_b(m), kDescHiB, id1);
             }
           }
           ptx::tc_commit(&empty[st]);                                     // slab consumed
@@ -233,6 +253,7 @@ __global__ void __launch_bounds__(192) conv1_pw2_pool_kernel(const __grid_consta
           if (xi == kD) ptx::tc_commit(&accf[(go_base + kD - 1) % kR]);
         }
         __syncwarp();
+        tr(p.trace, 1, gp, 4);
         committed += (xi >= 2) + (xi == kD);
       }
     }
@@ -253,7 +274,9 @@ __global__ void __launch_bounds__(192) conv1_pw2_pool_kernel(const __grid_consta
       if (j < n_planes) {
         // ---- step 1 (plane j): conv accumulator -> bias, ReLU, fp16 -> A operand buffer j & 1 ----
         const uint32_t slot = j % kR, u = j / kR, b = j & 1;
+        if (warp == 2) tr(p.trace, 2, j, 0);
         ptx::mbar_wait(&accf[slot], u & 1);
+        if (warp == 2) tr(p.trace, 2, j, 1);
         ptx::tc_fence_after();
         uint32_t v[32];
         ptx::tmem_ld32(tmem_base + tm_lane + slot * 32u, v);
@@ -275,11 +298,13 @@ __global__ void __launch_bounds__(192) conv1_pw2_pool_kernel(const __grid_consta
         }
         ptx::fence_proxy_async();   // generic-proxy stores -> visible to the tensor core
         ptx::mbar_arrive(&a2_full[b]);
+        if (warp == 2) tr(p.trace, 2, j, 2);
       }
       if (j == 0) continue;
       // ---- step 2 (plane j - 1): pointwise accumulator -> bias, ReLU, 2x2x2 average ----
       const uint32_t jj = j - 1, b = jj & 1;
       ptx::mbar_wait(&d2_full[b], (jj >> 1) & 1);
+      if (warp == 2) tr(p.trace, 2, j, 3);
       ptx::tc_fence_after();
       uint32_t v[32];
       ptx::tmem_ld32(tmem_base + tm_lane + (uint32_t)(kR * 32) + b * 32u, v);
@@ -488,13 +513,6 @@ void launch_conv1_pw2_pool(const ConvTc& conv1, const __half* w2, const uint4* w
     if (!attr_set[dev]) {
       GB_CUDA(cudaFuncSetAttribute(conv1_pw2_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
       GB_CUDA(cudaFuncSetAttribute(conv1_pw2_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-      uint32_t h[18][2];
-      for (int t9 = 0; t9 < 9; t9++)
-        for (int ks = 0; ks < 2; ks++) {
-          h[t9 * 2 + ks][0] = (uint32_t)((t9 / 3) * kSlabZ + (t9 % 3) + 2 * ks * (kChunkBytes >> 4));
-          h[t9 * 2 + ks][1] = (uint32_t)((t9 * 4 + 2 * ks) * 96);
-        }
-      GB_CUDA(cudaMemcpyToSymbol(c_fused_off, h, sizeof(h)));
       GB_CUDA(cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev));
       attr_set[dev] = true;
     }
@@ -514,6 +532,16 @@ void launch_conv1_pw2_pool(const ConvTc& conv1, const __half* w2, const uint4* w
   FusedParams p;
   p.wp = conv1.wp; p.bias1 = conv1.bias; p.w2 = w2; p.w2p = w2p; p.bias2 = bias2; p.xout = reinterpret_cast<__half*>(x2); p.out_lp = L2.Lp; p.out_G = L2.G;
   p.n_poses = n_poses; p.n_groups = n_groups;
+  p.trace = nullptr;
+  static const char* trace_path = getenv("GB_TC_FUSED_TRACE");
+  static unsigned long long* d_trace = nullptr;
+  static int trace_left = 2;   // the second launch of the process is traced (warm caches)
+  if (trace_path && trace_left > 0 && --trace_left == 0) {
+    GB_CUDA(cudaMalloc(&d_trace, sizeof(unsigned long long) * 3 * kTracePlanes * 8));
+    GB_CUDA(cudaMemsetAsync(d_trace, 0, sizeof(unsigned long long) * 3 * kTracePlanes * 8, s));
+    p.trace = d_trace;
+  }
+
   const int n_items = n_groups * kRowTiles * kZBlocks;
   static const int persist = getenv("GB_TC_FUSED_PERSIST") ? atoi(getenv("GB_TC_FUSED_PERSIST")) : 2;
   static const int tc_pw = getenv("GB_TC_FUSED_PW") ? atoi(getenv("GB_TC_FUSED_PW")) : 1;   // 1 (default): pointwise conv as a second tcgen05.mma;
@@ -521,6 +549,20 @@ void launch_conv1_pw2_pool(const ConvTc& conv1, const __half* w2, const uint4* w
   int grid = persist > 0 ? std::min(n_items, n_sm[dev] * persist) : n_items;
   if (tc_pw) conv1_pw2_pool_kernel<true><<<grid, 192, kSmemTotal, s>>>(tmap, p);
   else conv1_pw2_pool_kernel<false><<<grid, 192, kSmemTotal, s>>>(tmap, p);
+  if (p.trace) {
+    std::vector<unsigned long long> h(3 * kTracePlanes * 8);
+    GB_CUDA(cudaStreamSynchronize(s));
+    GB_CUDA(cudaMemcpy(h.data(), d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int r = 0; r < 3; r++)
+        for (int pl = 0; pl < kTracePlanes; pl++) {
+          fprintf(f, "%d %d", r, pl);
+          for (int k = 0; k < 8; k++) fprintf(f, " %llu", h[(r * kTracePlanes + pl) * 8 + k]);
+          fprintf(f, "\n");
+        }
+      fclose(f);
+    }
+  }
 }
 
 }  // namespace gb

@@ -211,6 +211,10 @@ class CNNScorer:
         capi.check(capi.lib().gb_cnn_fetch(self._h, *[_fp(o) for o in out]))
         return tuple(out)
 
+    def fetch_device(self, device_ptr):
+        """results [4][n_staged] -> caller-owned DEVICE buffer (raw pointer, >= 16 n bytes): no host bounce (gather via NCCL)"""
+        capi.check(capi.lib().gb_cnn_fetch_device(self._h, C.cast(C.c_void_p(int(device_ptr)), C.POINTER(C.c_float))))
+
     def stream_ptr(self):
         return capi.lib().gb_cnn_stream(self._h)
 

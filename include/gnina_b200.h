@@ -136,6 +136,10 @@ int gb_cnn_stage_poses(gb_cnn* h, const float* lig_xyz, const int32_t* lig_type,
                        int n_poses, const float* centers);
 int gb_cnn_run_staged(gb_cnn* h);
 int gb_cnn_fetch(gb_cnn* h, float* score, float* affinity, float* loss, float* variance);
+/* the same four arrays [4][n_staged] (score, affinity, loss, variance) copied device-to-device into a caller-owned DEVICE
+ * buffer on the handle's stream (then synchronised): the multi-GPU score gather (NCCL) reads the results where they are,
+ * without a host bounce */
+int gb_cnn_fetch_device(gb_cnn* h, float* device_dst);
 void* gb_cnn_stream(gb_cnn* h);            /* cudaStream_t of the handle (for CUDA-event timing)            */
 int64_t gb_cnn_kernel_launches(gb_cnn* h); /* kernels launched by this handle so far                        */
 

@@ -131,9 +131,11 @@ def test_fast_gradient_matches_reference_autograd(kat, golden_dir):
     scale = np.abs(g["lig_grad"]).max()
     assert np.abs(grad - g["lig_grad"]).max() < FAST_GRAD_TOL * scale
     assert np.abs(grad[t <= 1]).max() == 0.0
-    # the forward outputs of the gradient call are the fast scoring path's
+    # the forward outputs of the gradient call are the fast scoring path's up to fp16 round-off: scoring runs the fused
+    # unit1_conv/unit2_conv/pool kernel (pooling in fp32 straight from the accumulator), the gradient call keeps Y1 and pools
+    # fp16-rounded unit2 outputs
     plain = s.score_batch(x, t, offs)
-    assert np.abs(plain[0] - sc).max() < 1e-6 and np.abs(plain[1] - aff).max() < 1e-5
+    assert np.abs(plain[0] - sc).max() < 1e-4 and np.abs(plain[1] - aff).max() < 1e-3
 
 
 def test_fast_gradient_matches_validation_path_on_a_ragged_multi_chunk_batch(kat):
