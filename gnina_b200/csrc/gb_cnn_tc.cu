@@ -114,9 +114,10 @@ static PointwiseTc prep_pw(TcWeights& tw, const Model& m, const std::string& key
 }
 
 bool tc_supported(const Model& m) {
+  if (m.arch == GB_ARCH_DEFAULT2017) return m.n_channels > 32 && m.n_channels <= 48 && m.npts == 48;
   return (m.arch == GB_ARCH_DEFAULT2018 || m.arch == GB_ARCH_DENSE) && m.n_channels == 28 && m.npts == 48;
 }
-int tc_pool_kind(const Model& m) { return m.arch == GB_ARCH_DEFAULT2018 ? 0 : 1; }
+int tc_pool_kind(const Model& m) { return m.arch == GB_ARCH_DEFAULT2018 ? 0 : m.arch == GB_ARCH_DEFAULT2017 ? 3 : 1; }
 bool tc_fused_enabled() {
   static const bool on = !(getenv("GB_TC_FUSED") && atoi(getenv("GB_TC_FUSED")) == 0);
   return on;
@@ -136,12 +137,18 @@ std::shared_ptr<TcWeights> get_tc_weights(const Model& m) {
   Model& mm = const_cast<Model&>(m);
   if (mm.tc) return mm.tc;
   auto tw = std::make_shared<TcWeights>();
+  if (m.arch == GB_ARCH_DEFAULT2017) {   // maxpool -> conv -> ReLU, three times; no 1x1x1 convolutions
+    tw->conv1 = prep_conv(*tw, m, "unit1_conv1");
+    tw->conv3 = prep_conv(*tw, m, "unit2_conv1");
+    tw->conv5 = prep_conv(*tw, m, "unit3_conv1");
+  } else {
   tw->conv1 = prep_conv(*tw, m, "unit1_conv");
   tw->pw2 = prep_pw(*tw, m, "unit2_conv");
   tw->pw2_packed = pack_pointwise_tc(tw->allocs, m.t("unit2_conv.weight").data, 32);
   tw->conv3 = prep_conv(*tw, m, "unit3_conv");
   tw->pw4 = prep_pw(*tw, m, "unit4_conv");
   tw->conv5 = prep_conv(*tw, m, "unit5_conv");
+  }
   // FC heads read the NCDHW flatten idx = c*216 + pos (view(-1, 27648)); the device keeps conv5's output
   // channels-last ([pos][c]), so permute the weights once.
   const HostTensor &pw = m.t("pose_output.weight"), &pb = m.t("pose_output.bias"), &aw = m.t("affinity_output.weight"),
@@ -210,9 +217,9 @@ struct ConvTcSmem {
 // Per-MMA start-address offsets (16-byte units) of the A slab and the B weight block, one table per kernel
 // configuration, in constant memory (uniform loads straight into the uniform registers UTCHMMA consumes).
 struct MmaOff { uint32_t a, b; };
-__constant__ MmaOff c_mma_off[4][36];
+__constant__ MmaOff c_mma_off[5][36];
 template <int CIN, int DD> struct ConvCfg {
-  static constexpr int id = (CIN == 32 && DD == 24) ? 0 : (CIN == 32 && DD == 12) ? 1 : (CIN == 64 && DD == 6) ? 2 : 3;
+  static constexpr int id = (CIN == 32 && DD == 24) ? 0 : (CIN == 32 && DD == 12) ? 1 : (CIN == 64 && DD == 6) ? 2 : (CIN == 48) ? 4 : 3;
 };
 
 template <int CIN, int DD>
@@ -818,7 +825,8 @@ void launch_conv_tc_32_24_planar(const ConvTc& c, const uint4* xin, uint4* xout,
 }
 void launch_conv_tc_any(int cin, int D, const ConvTc& c, const ActLayout& L, const uint4* xin, __half* out, int n_poses,
                         cudaStream_t s, uint4* out_planar, int out_c8tot, int out_c8off, int out_lp, int relu) {
-  if (cin == 32 && D == 24) launch_conv_tc<32, 24>(c, L, xin, out, n_poses, s, out_planar, out_c8tot, out_c8off, out_lp, relu);
+  if (cin == 48 && D == 24) launch_conv_tc<48, 24>(c, L, xin, out, n_poses, s, out_planar, out_c8tot, out_c8off, out_lp, relu);
+  else if (cin == 32 && D == 24) launch_conv_tc<32, 24>(c, L, xin, out, n_poses, s, out_planar, out_c8tot, out_c8off, out_lp, relu);
   else if (cin == 32 && D == 12) launch_conv_tc<32, 12>(c, L, xin, out, n_poses, s, out_planar, out_c8tot, out_c8off, out_lp, relu);
   else if (cin == 64 && D == 6) launch_conv_tc<64, 6>(c, L, xin, out, n_poses, s, out_planar, out_c8tot, out_c8off, out_lp, relu);
   else if (cin == 64 && D == 12) launch_conv_tc<64, 12>(c, L, xin, out, n_poses, s, out_planar, out_c8tot, out_c8off, out_lp, relu);
@@ -830,10 +838,70 @@ const void* tc_debug_buffer(int i, size_t* bytes) {
   return t_debug.ptr[i];
 }
 
+// default2017: 2x2x2 MAX pool of a channels-last conv output (already ReLU'd) + re-layout into the chunk-planar padded
+// input of the next convolution.  One thread per (pooled voxel, 8-channel chunk): eight 16-byte loads, one 16-byte store.
+template <int C>
+__global__ void __launch_bounds__(256) maxpool_relayout_kernel(const __half* __restrict__ yin, uint4* __restrict__ xout, int D,
+                                                               int n_poses, int Gn, int Lpn) {
+  constexpr int C8 = C / 8;
+  const int Dn = D / 2, Pn = Dn + 2;
+  const long long total = (long long)n_poses * Dn * Dn * Dn * C8;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(e % C8);
+    long long r = e / C8;
+    const int z0 = (int)(r % Dn); r /= Dn;
+    const int y0 = (int)(r % Dn); r /= Dn;
+    const int x0 = (int)(r % Dn);
+    const int pose = (int)(r / Dn);
+    __half2 m[4];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int xi = 2 * x0 + (k >> 2), yi = 2 * y0 + ((k >> 1) & 1), zi = 2 * z0 + (k & 1);
+      const uint4 v = *reinterpret_cast<const uint4*>(yin + ((((size_t)pose * D + xi) * D + yi) * D + zi) * C + c8 * 8);
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int q = 0; q < 4; q++) m[q] = k == 0 ? h[q] : __hmax2(m[q], h[q]);
+    }
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&m[0]); o.y = *reinterpret_cast<uint32_t*>(&m[1]);
+    o.z = *reinterpret_cast<uint32_t*>(&m[2]); o.w = *reinterpret_cast<uint32_t*>(&m[3]);
+    xout[(((size_t)(pose / Gn) * Dn + x0) * C8 + c8) * Lpn + (size_t)(pose % Gn) * Pn * Pn + (size_t)(y0 + 1) * Pn + (z0 + 1)] = o;
+  }
+}
+
+// default2017 (N3 of SURVEY.md §8a): maxpool2 (in the voxeliser) -> conv3^3(35(48)->32)+ReLU -> maxpool2 -> conv3^3(32->64)+ReLU
+// -> maxpool2 -> conv3^3(64->128)+ReLU -> FC heads, the three convolutions on tcgen05
+static int tc_forward_2017(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspace& ws, float* out3, cudaStream_t s,
+                           Profiler* prof, cudaEvent_t x0_consumed) {
+  auto tw = get_tc_weights(m);
+  const int nb = pb.n_poses, nb_alloc = std::max(nb, 64);
+  const ActLayout L1 = make_layout(24, 1, 48), L3 = make_layout(12, 2, 32), L5 = make_layout(6, 2, 64);
+  ws.ensure(0, (size_t)nb_alloc * 24 * 24 * 24 * 32 * sizeof(__half) + 1024);
+  ws.ensure(1, act_bytes(L3, nb_alloc));
+  ws.ensure(2, act_bytes(L5, nb_alloc));
+  ws.ensure(3, (size_t)nb_alloc * 216 * 128 * sizeof(__half) + 1024);
+  __half* Y = reinterpret_cast<__half*>(ws.buf[0]);
+  uint4* X2 = reinterpret_cast<uint4*>(ws.buf[1]);
+  uint4* X4 = reinterpret_cast<uint4*>(ws.buf[2]);
+  __half* Y5 = reinterpret_cast<__half*>(ws.buf[3]);
+  { ProfScope ps(prof, "tc17_conv1_3x3x3_35x32_d24", s); launch_conv_tc<48, 24>(tw->conv1, L1, reinterpret_cast<const uint4*>(x0v), Y, nb, s); }
+  if (x0_consumed) GB_CUDA(cudaEventRecord(x0_consumed, s));
+  { ProfScope ps(prof, "tc17_maxpool_d24", s); maxpool_relayout_kernel<32><<<148 * 8, 256, 0, s>>>(Y, X2, 24, nb, L3.G, L3.Lp); }
+  { ProfScope ps(prof, "tc17_conv2_3x3x3_32x64_d12", s); launch_conv_tc<32, 12>(tw->conv3, L3, X2, Y, nb, s); }
+  { ProfScope ps(prof, "tc17_maxpool_d12", s); maxpool_relayout_kernel<64><<<148 * 8, 256, 0, s>>>(Y, X4, 12, nb, L5.G, L5.Lp); }
+  { ProfScope ps(prof, "tc17_conv3_3x3x3_64x128_d6", s); launch_conv_tc<64, 6>(tw->conv5, L5, X4, Y5, nb, s); }
+  { ProfScope ps(prof, "tc_fc_heads", s); fc_heads_f16_kernel<<<nb, 256, 0, s>>>(Y5, tw->fcw, tw->fcb, out3); }
+  return 6;
+}
+
 int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspace& ws, float* out3, cudaStream_t s,
                Profiler* prof, cudaEvent_t x0_consumed, bool keep_activations) {
   GB_CHECK(tc_supported(m), "model has no tensor-core path");
   if (m.arch == GB_ARCH_DENSE) return tc_forward_dense(m, pb, x0v, ws, out3, s, prof, x0_consumed);
+  if (m.arch == GB_ARCH_DEFAULT2017) {
+    GB_CHECK(!keep_activations, "the fast gradient path covers the default2018 family");
+    return tc_forward_2017(m, pb, x0v, ws, out3, s, prof, x0_consumed);
+  }
   auto tw = get_tc_weights(m);
   int launches = 0;
   const int nb = pb.n_poses;

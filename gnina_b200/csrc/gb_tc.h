@@ -23,8 +23,9 @@ struct TcGridWorkspace {
   // [kind][double buffer]; kind 0 = average pool, one pose per group (gradient path, gb_cnn_tc_grad.cu), 1 = max pool
   // (dense family), 2 = average pool in row groups of kFusedGroup poses (scoring path, gb_cnn_tc_fused.cu).  The layouts
   // differ in where their zero borders are, so every kind owns its buffers.
-  void* x0[3][2] = {};
-  size_t cap[3][2] = {};
+  // kind 3 = max pool with 48 (35 used) channels: default2017
+  void* x0[4][2] = {};
+  size_t cap[4][2] = {};
   cudaEvent_t ready[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr}, started[2] = {nullptr, nullptr};
   bool started_valid = false;
   bool consumed_valid[2] = {false, false};
@@ -89,7 +90,7 @@ struct PointwiseTc {
 };
 struct TcWeights {
   ConvTc conv1, conv3, conv5;
-  PointwiseTc pw2, pw4;
+  PointwiseTc pw2, pw4;   // (unused by default2017: no 1x1x1 convolutions)
   uint4* pw2_packed = nullptr;  // unit2_conv as the K-major B operand of the fused kernel's second tcgen05.mma
   float* fcw = nullptr;      // [3][216*128] channels-last order
   float* fcb = nullptr;

@@ -119,16 +119,18 @@ __device__ __forceinline__ float gap2(float x, float lo, float hi) {
   return g * g;
 }
 
-struct VoxSmem {
+template <int kC8>
+struct VoxSmemT {
   float4 A[kVoxChunk];       // (-bx w', -by w', -bz w', vs w'), b = atom - tile origin, w' = sqrt(kappa)/r, vs = 2 res
   float4 B[kVoxChunk];       // (bx, by, bz, reach) in Angstrom, reach = 1.5 r
   float thr2[kVoxChunk];     // kappa (1.5 + half-diagonal/r)^2 : pooled-centre test in scaled units
   int ch[kVoxChunk];
-  uint32_t out[16 * 512];    // [channel pair][pooled voxel] half2
+  uint32_t out[kC8 * 4 * 512];   // [channel pair][pooled voxel] half2
   int counts[16];
 };
+using VoxSmem = VoxSmemT<4>;
 
-template <bool kMax, int kMinBlocks>
+template <bool kMax, int kMinBlocks, int kC8 = 4>
 __global__ void __launch_bounds__(512, kMinBlocks) voxelize_pool_f16_kernel(const float4* __restrict__ list_xyzr,
                                                                 const int* __restrict__ list_ch,
                                                                 const int* __restrict__ list_n, int cap,
@@ -136,9 +138,10 @@ __global__ void __launch_bounds__(512, kMinBlocks) voxelize_pool_f16_kernel(cons
                                                                 float dimension, uint4* __restrict__ x0, int Lp, int G) {
   // the pooled grid of every supported model is 24^3 x 32 channels (48^3 fine voxels, 28 channels padded): compile-time
   // dimensions keep the index arithmetic free of integer divisions (ncu r2a: the prologue was 11 % of the instructions)
-  constexpr int D = 24, P = D + 2, C8 = 4, tiles = D / 8;
+  // (kC8 = 6: the 35 channels of default2017, padded to 48)
+  constexpr int D = 24, P = D + 2, C8 = kC8, tiles = D / 8;
   extern __shared__ __align__(16) uint8_t vox_smem_raw[];
-  VoxSmem& S = *reinterpret_cast<VoxSmem*>(vox_smem_raw);
+  VoxSmemT<kC8>& S = *reinterpret_cast<VoxSmemT<kC8>*>(vox_smem_raw);
   const int p = blockIdx.y;
   const int t = blockIdx.x;
   const int tx = t / (tiles * tiles), ty = (t / tiles) % tiles, tz = t % tiles;
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(512, kMinBlocks) voxelize_pool_f16_kernel(cons
   const int pv = (px * 8 + py) * 8 + pz;
   // zero this thread's own voxel (channels without atoms in reach are never flushed): 16 channel-pair words
 #pragma unroll
-  for (int e = 0; e < 16; e++) S.out[e * 512 + pv] = 0u;
+  for (int e = 0; e < 4 * kC8; e++) S.out[e * 512 + pv] = 0u;
   const float half = dimension * 0.5f;
   const float vs = 2.f * resolution, hres = 0.5f * resolution;
   // tile origin = centre of the tile's pooled voxel (0,0,0), i.e. between fine voxels 16 t and 16 t + 1
@@ -301,7 +304,7 @@ TcGridWorkspace::~TcGridWorkspace() {
 
 int tc_prepare_grid(const TcPoseBatch& pb, TcGridWorkspace& gw, int buf, int kinds_mask, cudaStream_t s, Profiler* prof) {
   const int nb = pb.n_poses;
-  const ActLayout L1 = make_layout(24, 1, 32), LF = make_fused_x0_layout();
+  const ActLayout L1 = make_layout(24, 1, 32), LF = make_fused_x0_layout(), L48 = make_layout(24, 1, 48);
   const int cap = std::max(1, pb.n_rec + pb.max_pose_atoms);
   // allocation sizes have a floor (64 poses, 128 ligand atoms) so that small batches of varying size -- the kept
   // poses of one docked ligand -- never re-allocate: cudaFree / cudaMemset synchronise the whole device and would
@@ -324,8 +327,8 @@ int tc_prepare_grid(const TcPoseBatch& pb, TcGridWorkspace& gw, int buf, int kin
     GB_CUDA(cudaMalloc(&gw.list_n, (size_t)nb_alloc * sizeof(int)));
     gw.listn_cap = nb_alloc;
   }
-  for (int kind = 0; kind < 3; kind++) {
-    const size_t need0 = act_bytes(kind == 2 ? LF : L1, nb_alloc);
+  for (int kind = 0; kind < 4; kind++) {
+    const size_t need0 = act_bytes(kind == 2 ? LF : kind == 3 ? L48 : L1, nb_alloc);
     if (!(kinds_mask & (1 << kind)) || gw.cap[kind][buf] >= need0) continue;
     // growing the pooled-grid buffer: only kernels of THIS handle (its two streams) can still be using the old one
     GB_CUDA(cudaStreamSynchronize(s));
@@ -361,26 +364,39 @@ int tc_prepare_grid(const TcPoseBatch& pb, TcGridWorkspace& gw, int buf, int kin
     if (dev < 64 && !attr_set[dev]) {
       GB_CUDA(cudaFuncSetAttribute(kern(false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VoxSmem)));
       GB_CUDA(cudaFuncSetAttribute(kern(true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VoxSmem)));
+      GB_CUDA(cudaFuncSetAttribute(voxelize_pool_f16_kernel<true, 3, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VoxSmemT<6>)));
       attr_set[dev] = true;
     }
   }
   int launches = 1;
+  // (r2m: a load-balanced variant -- every in-reach (atom, voxel) pair pushed into a per-warp queue, popped 32 at a time,
+  // sums accumulated with integer shared-memory atomics in fixed point -- was correct and bit-reproducible but SLOWER, 6.18 vs
+  // 5.15 ms per 10 k poses: 549 k instead of 464 k warp instructions per pose.  The 32 KB accumulator forced two channel halves,
+  // each with its own partial queue drain, and the int -> half conversion of the output; profiles/README.md has the numbers.)
+  auto launch_avg = [&](void* dst, int lp, int grp) {
+    kern(false)<<<dim3(27, nb), 512, sizeof(VoxSmem), s>>>(gw.list_xyzr, gw.list_ch, gw.list_n, cap, pb.centers, pb.resolution,
+                                                          pb.dimension, reinterpret_cast<uint4*>(dst), lp, grp);
+  };
   if (kinds_mask & 1) {
     ProfScope ps(prof, "tc_voxelize_pool", s);
-    kern(false)<<<dim3(27, nb), 512, sizeof(VoxSmem), s>>>(gw.list_xyzr, gw.list_ch, gw.list_n, cap, pb.centers, pb.resolution,
-                                                          pb.dimension, reinterpret_cast<uint4*>(gw.x0[0][buf]), L1.Lp, 1);
+    launch_avg(gw.x0[0][buf], L1.Lp, 1);
     launches++;
   }
   if (kinds_mask & 4) {
     ProfScope ps(prof, "tc_voxelize_pool", s);
-    kern(false)<<<dim3(27, nb), 512, sizeof(VoxSmem), s>>>(gw.list_xyzr, gw.list_ch, gw.list_n, cap, pb.centers, pb.resolution,
-                                                          pb.dimension, reinterpret_cast<uint4*>(gw.x0[2][buf]), LF.Lp, LF.G);
+    launch_avg(gw.x0[2][buf], LF.Lp, LF.G);
     launches++;
   }
   if (kinds_mask & 2) {
     ProfScope ps(prof, "tc_voxelize_maxpool", s);
     kern(true)<<<dim3(27, nb), 512, sizeof(VoxSmem), s>>>(gw.list_xyzr, gw.list_ch, gw.list_n, cap, pb.centers, pb.resolution,
                                                          pb.dimension, reinterpret_cast<uint4*>(gw.x0[1][buf]), L1.Lp, 1);
+    launches++;
+  }
+  if (kinds_mask & 8) {   // default2017: max pool, 35 channels in 6 chunks
+    ProfScope ps(prof, "tc_voxelize_maxpool48", s);
+    voxelize_pool_f16_kernel<true, 3, 6><<<dim3(27, nb), 512, sizeof(VoxSmemT<6>), s>>>(
+        gw.list_xyzr, gw.list_ch, gw.list_n, cap, pb.centers, pb.resolution, pb.dimension, reinterpret_cast<uint4*>(gw.x0[3][buf]), L48.Lp, 1);
     launches++;
   }
   return launches;

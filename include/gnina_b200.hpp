@@ -20,6 +20,8 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <exception>
+#include <thread>
 #include <vector>
 #include "gnina_b200.h"
 
@@ -131,6 +133,64 @@ class CNNScorer {
       check(gb_cnn_score_batch(h_, lig_xyz, lig_type, offs, 1, center, &s, &affinity, &loss, &variance));
     }
     return s;
+  }
+};
+
+// ---- one process, several GPUs (poses are independent units, no exchange step): one CNNScorer per device,
+// the poses of a batch cut into contiguous shards, every shard scored by its own host thread on its own device, results
+// concatenated in pose order.  The reference has nothing like it (one scorer, one GPU); this is the C++-side counterpart
+// of the torchrun pose sharding the benchmark uses.
+class MultiDeviceScorer {
+  std::vector<std::unique_ptr<CNNScorer>> scorers_;
+
+ public:
+  // devices may repeat (two handles on one GPU overlap their kernels); empty = every visible device
+  MultiDeviceScorer(const std::string& weights_dir, const std::vector<std::string>& names, std::vector<int> devices = {}) {
+    if (devices.empty())
+      for (int d = 0; d < gb_device_count(); d++) devices.push_back(d);
+    if (devices.empty()) throw internal_error("no usable CUDA device (gnina_b200 has no CPU fallback)");
+    for (int d : devices) scorers_.emplace_back(new CNNScorer(weights_dir, names, d));
+  }
+  size_t n_devices() const { return scorers_.size(); }
+  CNNScorer& scorer(size_t i) { return *scorers_.at(i); }
+  void set_option(const char* key, double v) { for (auto& s : scorers_) s->set_option(key, v); }
+  void set_receptor(const float* xyz, const int32_t* smina_type, int n) {
+    for (auto& s : scorers_) s->set_receptor(xyz, smina_type, n);   // replicated: <= 128 KB per device
+  }
+  // shard boundaries: pose p of n goes to device p * D / n (contiguous, sizes differ by at most one)
+  static std::vector<int> shard_bounds(int n_poses, int n_dev) {
+    std::vector<int> b(n_dev + 1);
+    for (int d = 0; d <= n_dev; d++) b[d] = (int)((long long)n_poses * d / n_dev);
+    return b;
+  }
+  Scores score_batch(const float* lig_xyz, const int32_t* lig_type, const int32_t* pose_offsets, int n_poses,
+                     const float* centers = nullptr) {
+    const int D = (int)scorers_.size();
+    const std::vector<int> b = shard_bounds(n_poses, D);
+    Scores out;
+    out.score.resize(n_poses); out.affinity.resize(n_poses); out.loss.resize(n_poses); out.variance.resize(n_poses);
+    std::vector<std::exception_ptr> err(D);
+    std::vector<std::thread> th;
+    for (int d = 0; d < D; d++) {
+      th.emplace_back([&, d] {
+        try {
+          const int p0 = b[d], np = b[d + 1] - b[d];
+          if (np == 0) return;
+          std::vector<int32_t> off(np + 1);
+          for (int i = 0; i <= np; i++) off[i] = pose_offsets[p0 + i] - pose_offsets[p0];
+          const int a0 = pose_offsets[p0];
+          Scores s = scorers_[d]->score_batch(lig_xyz + 3 * (size_t)a0, lig_type + a0, off.data(), np, centers ? centers + 3 * (size_t)p0 : nullptr);
+          std::copy(s.score.begin(), s.score.end(), out.score.begin() + p0);
+          std::copy(s.affinity.begin(), s.affinity.end(), out.affinity.begin() + p0);
+          std::copy(s.loss.begin(), s.loss.end(), out.loss.begin() + p0);
+          std::copy(s.variance.begin(), s.variance.end(), out.variance.begin() + p0);
+        } catch (...) { err[d] = std::current_exception(); }
+      });
+    }
+    for (auto& t : th) t.join();
+    for (auto& e : err)
+      if (e) std::rethrow_exception(e);
+    return out;
   }
 };
 

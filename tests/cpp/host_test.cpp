@@ -118,6 +118,18 @@ int main(int argc, char** argv) {
     const float e = nc.eval(lig_xyz.data(), lig_t.data(), offs[1], &mf);
     const float e0 = nc.eval(lig_xyz.data(), lig_t.data(), offs[1]);
     printf("noncache %.5f %.5f forces %zu\n", e, e0, mf.size());
+    {  // gb::MultiDeviceScorer: poses sharded over devices (here every visible device, twice -- also exercises two
+       // handles per GPU); same results as the single scorer, in pose order
+      std::vector<int> devs;
+      for (int d = 0; d < gb_device_count(); d++) { devs.push_back(d); devs.push_back(d); }
+      gb::MultiDeviceScorer md(argv[1], {"crossdock_default2018"}, devs);
+      md.set_receptor(rec_xyz.data(), rec_t.data(), hdr[0]);
+      auto r2 = md.score_batch(lig_xyz.data(), lig_t.data(), offs.data(), hdr[2]);
+      double worst = 0;
+      for (int p2 = 0; p2 < hdr[2]; p2++) worst = std::max(worst, (double)std::fabs(r2.score[p2] - r.score[p2]) + std::fabs(r2.affinity[p2] - r.affinity[p2]));
+      const auto sb = gb::MultiDeviceScorer::shard_bounds(10, 4);
+      printf("multidevice %zu maxdiff %.3g shards %d %d %d %d %d\n", md.n_devices(), worst, sb[0], sb[1], sb[2], sb[3], sb[4]);
+    }
     {  // --cnn_mix_emp_force / --cnn_mix_emp_energy (lib/non_cache_cnn.cpp:113-166): with a box that contains the ligand
        // the blended energy is (CNN loss + w * empirical) / (1 + w), the identity test/gnina/test_min.py:45-61 checks
       gb::GridDims wide;

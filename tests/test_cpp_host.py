@@ -63,6 +63,8 @@ def test_cpp_host_scores_match_oracle(golden_dir, tmp_path):
     loss0 = om.score(kat["rec_xyz"], kat["rec_types"], lx[:offs[1]], lt[:offs[1]], offs[:2], dtype=torch.float64)[2][0]
     heavy = lx[:offs[1]][lt[:offs[1]] > 1]
     pen = 10.0 * (np.clip(np.abs(heavy) - 1.0, 0, None).sum() + np.clip(np.abs(heavy) - 11.75, 0, None).sum())
+    md = by_tag["multidevice"]                                            # sharded over 2 handles per device == single scorer
+    assert int(md[1]) >= 2 and float(md[3]) < 1e-6 and md[5:] == ["0", "2", "5", "7", "10"]
     # empirical mixing: total = (CNN loss + w * empirical) / (1 + w), forces blended the same way (test_min.py:45-61, 1e-3)
     e_plain, e_mixed, emp, worst = (float(x) for x in by_tag["mixing"][1:5])
     assert abs(e_mixed - (e_plain + 0.5 * emp) / 1.5) < 1e-3 * max(1.0, abs(e_mixed)) and worst < 1e-5

@@ -86,6 +86,27 @@ def test_dense_fast_scores_match_reference_pt(kat, name):
     assert np.abs(aff - kat[name + "_aff_f64"]).max() < TOL_AFF
 
 
+def test_default2017_fast_path_matches_reference_pt(kat):
+    """N3: default2017 (35 channels, max pooling, three 3x3x3 convolutions) on the tensor-core path -- 48-channel max-pool
+    voxeliser, conv3_tc_kernel<48,24>, max-pool re-layout kernels -- against the reference's own default2017.pt (fp64)"""
+    from gnina_b200 import CNNScorer
+    s = CNNScorer(["default2017"])
+    assert s.get_option("precision") == 1                      # the fast path is the default now
+    s.set_receptor(kat["rec_xyz"], kat["rec_types"])
+    pose, aff, loss, var = s.score_batch(kat["lig_xyz"], kat["lig_types"], kat["pose_offsets"])
+    assert np.abs(pose - kat["default2017_pose_f64"]).max() < TOL_SCORE
+    assert np.abs(aff - kat["default2017_aff_f64"]).max() < TOL_AFF
+    v = CNNScorer(["default2017"], precision=0)
+    v.set_receptor(kat["rec_xyz"], kat["rec_types"])
+    ref = v.score_batch(kat["lig_xyz"], kat["lig_types"], kat["pose_offsets"])
+    assert np.abs(pose - ref[0]).max() < TOL_SCORE and np.abs(aff - ref[1]).max() < TOL_AFF
+    # ragged batch sizes (pose groups of two for the 12^3 and 6^3 layouts)
+    n = 5
+    offs = kat["pose_offsets"][:n + 1]
+    sub = s.score_batch(kat["lig_xyz"][:offs[-1]], kat["lig_types"][:offs[-1]], offs)
+    assert np.abs(sub[0] - pose[:n]).max() < 1e-6
+
+
 def test_dense_fast_intermediates_match_oracle(kat):
     import tc_layout as tl
     from gnina_b200 import model_blob
