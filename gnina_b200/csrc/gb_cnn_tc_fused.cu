@@ -9,19 +9,21 @@
 //   the epilogue (partners are lanes ^1 and ^8).  In shared memory the A slab is a dense [chunk][18 rows][10 z][8 ch]
 //   box: MMA row group g (8 consecutive z) sits at g * 160 B, so the UMMA descriptor simply uses SBO = 160 B and a tap
 //   (dy, dz) is again a constant start-address offset, (1+dy) * 10 + (1+dz) elements.  The box is fetched by ONE
-//   tensor-map TMA instruction per input plane (cp.async.bulk.tensor.5d, zero fill outside the tensor): this is the
+//   tensor-map TMA instruction per input plane (cp.async.bulk.tensor.4d, zero fill outside the tensor): this is the
 //   "TMA im2col" of the north star -- the halo is part of the box, nothing is materialised.  Valid rows: 24 of every 26
 //   (92 %; the flat tiling had 576 / 640 = 90 %).
 //
-//   Epilogue, per output plane: TMEM -> registers, + bias, ReLU, fp16 -> this warp's 32 rows of a shared-memory tile
-//   (channels-last, 16-byte chunks XOR-swizzled so that both the row-wise stores and the fragment loads are conflict
-//   free).  After the second plane of a pair (x odd, x even) the warp holds 2 x 4 x 8 fine voxels = 8 complete pooling
-//   windows and runs unit2_conv on them with mma.sync straight from shared memory (the formulation of
-//   pointwise_pool_mma_kernel: weights resident as A fragments, 16 voxels as the B operand with the reduction index
-//   permuted so that a lane's 16-byte load IS its fragment, bias + ReLU on the accumulators, the 2x2x2 average as a second
-//   MMA against a constant 1/8 matrix) and writes the 12^3 input of unit3_conv.  No warp outside the epilogue is involved
-//   (a first version issued the pointwise GEMM as a second tcgen05.mma from the MMA warp: it queued behind up to three
-//   planes of convolution MMAs and the epilogue ran at the queue's latency -- 62 ms instead of 8 per 10 k poses, r2c).
+//   After the accumulator (default, variant B of the template parameter below): unit2_conv is a SECOND tcgen05.mma.  The
+//   epilogue warps turn an accumulator plane into relu(conv + bias) fp16 and store it as a K-major A tile in shared memory
+//   (double buffered); the MMA warp issues D2 = A2 x W2^T (M = 128, N = 32, K = 32) on a fixed schedule -- the pointwise
+//   MMA of output plane j enters the queue right before the convolution MMAs of the input plane two commits later --
+//   and the epilogue runs one plane behind itself: stage plane j, then finish plane j - 1 (bias, ReLU, keep; after the
+//   second plane of an (odd, even) x pair the 2x2x2 average = two shfl.xor levels, lanes ^1 and ^8, plus the kept plane)
+//   and write the 12^3 input of unit3_conv with 16-byte stores.  (r2c: issuing the pointwise MMA opportunistically
+//   queued it behind up to three planes of convolution MMAs -- 62 ms instead of 7.7 per 10 k poses.)
+//   Variant A keeps the pointwise stage inside the epilogue warps on mma.sync (the formulation of
+//   pointwise_pool_mma_kernel, operands from an XOR-swizzled shared-memory tile); bit-identical scores, 9.9 ms: HMMA
+//   contends with tcgen05 for the tensor pipe.  It stays as the cross-check of variant B (GB_TC_FUSED_PW=0).
 //   Y1 (0.88 MB per pose) never exists in HBM and the pointwise kernel is gone (round 1: 11 % of the step).
 //
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue.

@@ -619,20 +619,22 @@ struct WarpWs {
 };
 __host__ __device__ inline int dk_ws_floats(int na, int ns, int np) {
   const int n = 6 + ns - 1;
-  int f = 6 * na + 25 * ns + 3 * (n + 2) + 6 * n + n * (n + 1) / 2 + 2 * (n + 2) + na + np;
+  const int n4 = (n + 3) & ~3;
+  int f = 2 * ((3 * na + 3) & ~3) + 25 * ns + 3 * (n + 2) + 6 * n4 + n * (n + 1) / 2 + 2 * (n + 2) + ((na + 3) & ~3) + ((np + 3) & ~3);
   return (f + 3) & ~3;  // 16-byte multiple
 }
 __device__ inline void dk_ws_carve(WarpWs& W, float* base, int na, int ns, int np) {
   const int n = 6 + ns - 1;
   float* p = base;
   auto take = [&](int k) { float* r = p; p += k; return r; };
-  W.coords = take(3 * na); W.forces = take(3 * na);
+  W.ea = take((na + 3) & ~3); W.pe = take((np + 3) & ~3);   // first: 16-byte aligned for the vector loads of dk_sum_seq
+  W.coords = take((3 * na + 3) & ~3); W.forces = take((3 * na + 3) & ~3);
+  const int n4 = (n + 3) & ~3;
+  W.g = take(n4); W.g_new = take(n4); W.g_orig = take(n4); W.p = take(n4); W.y = take(n4); W.mhy = take(n4);
   W.so = take(3 * ns); W.sa = take(3 * ns); W.sq = take(4 * ns); W.sm = take(9 * ns); W.ft = take(6 * ns);
   W.x = take(n + 2); W.x_new = take(n + 2); W.x_orig = take(n + 2);
-  W.g = take(n); W.g_new = take(n); W.g_orig = take(n); W.p = take(n); W.y = take(n); W.mhy = take(n);
   W.h = take(n * (n + 1) / 2);
   W.cand = take(n + 2); W.tmp = take(n + 2);
-  W.ea = take(na); W.pe = take(np);
 }
 // sin / cos of a float argument, correctly rounded (evaluated in double): what glibc's sinf / cosf return in all but
 // ~1e-4 of the cases, so that the torsion-tree kinematics reproduce the CPU restatement bit for bit.  B200 has a full-rate
@@ -644,14 +646,37 @@ __device__ inline void dk_sincos(float a, float* s, float* c) {
 }
 // sum_{k<n} a[k] (or a[k] b[k]) in index order, every lane computing the same chain: the reference's sequential
 // float association (lib/model.cu:38-60, lib/bfgs.h), not a butterfly -- a different order changes line-search decisions
+// a is 16-byte aligned (W.ea, W.pe): one 128-bit shared load per four additions
 __device__ inline float dk_sum_seq(const float* a, int n) {
   float s = 0.f;
-  for (int k = 0; k < n; k++) s += a[k];
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const int n4 = n >> 2;
+  if (n4 > 0) {
+    float4 v = a4[0];
+#pragma unroll 1
+    for (int k = 0; k < n4; k++) {
+      const float4 nxt = a4[k + 1 < n4 ? k + 1 : k];   // the next quad is in flight while this one is added
+      s += v.x; s += v.y; s += v.z; s += v.w;
+      v = nxt;
+    }
+  }
+#pragma unroll 1
+  for (int k = n4 << 2; k < n; k++) s += a[k];
   return s;
 }
+// a, b 16-byte aligned (the BFGS vectors of the workspace)
 __device__ inline float dk_dot_seq(const float* a, const float* b, int n) {
   float s = 0.f;
-  for (int k = 0; k < n; k++) s += a[k] * b[k];
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  const int n4 = n >> 2;
+#pragma unroll 1
+  for (int k = 0; k < n4; k++) {
+    const float4 u = a4[k], v = b4[k];
+    s += u.x * v.x; s += u.y * v.y; s += u.z * v.z; s += u.w * v.w;
+  }
+#pragma unroll 1
+  for (int k = n4 << 2; k < n; k++) s += a[k] * b[k];
   return s;
 }
 
@@ -721,6 +746,7 @@ __device__ void dk_set_conf(const LigPtrs& L, WarpWs& W, const float* xc, int la
     dk_normalize_angle(ang);
     dk_sincos(ang / 2, &tors_s, &tors_c);
   }
+  #pragma unroll 1
   for (int d = 0; d <= L.max_depth; d++) {
     if (lane < L.n_seg) {
       const int4 sg = L.seg[lane];
@@ -748,6 +774,7 @@ __device__ void dk_set_conf(const LigPtrs& L, WarpWs& W, const float* xc, int la
     }
     __syncwarp();
   }
+  #pragma unroll 1
   for (int i = lane; i < L.n_atoms; i += 32) {
     const int sgi = L.atom_seg[i];
     const float4 a = L.local[i];
@@ -795,6 +822,7 @@ __device__ float dk_noncache_atom(const DockField& F, int t1, float ax, float ay
   }
   pen *= F.slope;
   float e = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
+  #pragma unroll 1
   for (int b = 0; b < F.n_rec; b++) {
     const float4 rb = F.rec[b];
     const float r0 = adj[0] - rb.x, r1 = adj[1] - rb.y, r2c = adj[2] - rb.z;
@@ -823,37 +851,39 @@ __device__ __forceinline__ float dk_atom_field(const LigPtrs& L, const DockField
   return grid_evaluate_dev(F.gp.g[t], F.G, W.coords[3 * i], W.coords[3 * i + 1], W.coords[3 * i + 2], F.slope, v1, d);
 }
 
-// update_energy: cache::eval (intermolecular energy only), atoms summed in index order
-__device__ float dk_eval_grid(const LigPtrs& L, const DockField& F, WarpWs& W, const float* xc, float v1, int lane) {
-  dk_set_conf(L, W, xc, lane);
-  for (int i = lane; i < L.n_atoms; i += 32) W.ea[i] = dk_atom_field(L, F, W, i, v1, nullptr);
-  __syncwarp();
-  const float e = dk_sum_seq(W.ea, L.n_atoms);
-  __syncwarp();
-  return e;
-}
-
 // model::eval_deriv (lib/model.cu:202-225): returns e (all lanes), writes change[6+T] to gout.  Every sum follows the
 // reference's association -- atom energies in atom order, pair energies in pair order, the forces on an atom in the
 // order its pairs appear in the pair list, children folded into their parent in ascending order -- so that the result
 // agrees with the sequential CPU code to round-off of the transcendental functions only (north_star: 1e-6).
-__device__ float dk_eval_deriv(const LigPtrs& L, const DockField& F, WarpWs& W, const float* xc, const float* v, float* gout, int lane) {
+// grid_only: update_energy's cache::eval (lib/monte_carlo.cpp:113,135) -- the intermolecular energy alone, atoms summed in
+// index order; nothing is written to gout.  It shares the kinematics and the per-atom field code with the full evaluation
+// (ONE copy of this function per kernel: the chain kernel's instruction footprint is what bounds it, profiles/README.md r2o).
+__device__ float dk_eval_deriv(const LigPtrs& L, const DockField& F, WarpWs& W, const float* xc, const float* v, float* gout, int lane,
+                               bool grid_only = false) {
   dk_set_conf(L, W, xc, lane);
+  #pragma unroll 1
   for (int i = lane; i < L.n_atoms; i += 32) {
     float d[3] = {0.f, 0.f, 0.f};
     W.ea[i] = dk_atom_field(L, F, W, i, v[1], d);
     W.forces[3 * i] = d[0]; W.forces[3 * i + 1] = d[1]; W.forces[3 * i + 2] = d[2];
   }
   __syncwarp();
+  if (grid_only) {
+    const float eg = dk_sum_seq(W.ea, L.n_atoms);
+    __syncwarp();
+    return eg;
+  }
   // V6 intramolecular pairs, atom by atom: lane i walks atom i's partners (CSR over the pair list, both directions, in
   // pair order) and continues the force sum of ITS atom in registers, starting from the grid force -- exactly the
   // sequence of additions the reference performs on minus_forces[i].  Every pair is evaluated from both ends (2x the
   // table lookups, no shared-memory atomics: ncu r1l); the end that is the pair's first atom records the pair energy.
+  #pragma unroll 1
   for (int i = lane; i < L.n_atoms; i += 32) {
     const float xi = W.coords[3 * i], yi = W.coords[3 * i + 1], zi = W.coords[3 * i + 2];
     const int ti = (int)L.local[i].w;
     float fxs = W.forces[3 * i], fys = W.forces[3 * i + 1], fzs = W.forces[3 * i + 2];
     const int q1 = L.adj_off[i + 1];
+    #pragma unroll 1
     for (int q = L.adj_off[i]; q < q1; q++) {
       const int code = L.adj[q];
       const int j = code & 0xff, k = (code >> 8) & 0x3fffff;
@@ -883,21 +913,25 @@ __device__ float dk_eval_deriv(const LigPtrs& L, const DockField& F, WarpWs& W, 
   if (lane < L.n_seg) {
     const int4 sg = L.seg[lane];
     float f[6] = {0, 0, 0, 0, 0, 0};
+    #pragma unroll 1
     for (int i = sg.y; i < sg.z; i++) {
       const float rx = W.coords[3 * i] - W.so[3 * lane], ry = W.coords[3 * i + 1] - W.so[3 * lane + 1], rz = W.coords[3 * i + 2] - W.so[3 * lane + 2];
       const float qx = W.forces[3 * i], qy = W.forces[3 * i + 1], qz = W.forces[3 * i + 2];
       f[0] += qx; f[1] += qy; f[2] += qz;
       f[3] += ry * qz - rz * qy; f[4] += rz * qx - rx * qz; f[5] += rx * qy - ry * qx;
     }
+    #pragma unroll 1
     for (int k = 0; k < 6; k++) W.ft[6 * lane + k] = f[k];
   }
   __syncwarp();
   // ... then every parent gathers its children in ascending order, deepest parents first (branches_derivative,
   // lib/tree.h:300-310): no atomics, the reference's order
+  #pragma unroll 1
   for (int d = L.max_depth - 1; d >= 0; d--) {
     if (lane < L.n_seg && L.seg[lane].w == d) {
       float* ft = W.ft + 6 * lane;
       const int c1 = L.child_off[lane + 1];
+      #pragma unroll 1
       for (int q = L.child_off[lane]; q < c1; q++) {
         const int ch = L.child[q];
         const float* c = W.ft + 6 * ch;
@@ -924,6 +958,7 @@ __device__ void dk_conf_increment(float* x, const float* p, float f, int T, int 
     const float rot[3] = {f * p[3], f * p[4], f * p[5]};
     dk_quaternion_increment(x + 3, rot);
   }
+  #pragma unroll 1
   for (int t = lane; t < T; t += 32) {
     float a = f * p[6 + t];
     dk_normalize_angle(a);
@@ -934,77 +969,126 @@ __device__ void dk_conf_increment(float* x, const float* p, float f, int T, int 
   __syncwarp();
 }
 
-// bfgs (lib/bfgs.h:358-502), fast_line_search; W.x in/out, W.g out; returns f0 (all lanes)
-__device__ float dk_bfgs(const LigPtrs& L, const DockField& F, WarpWs& W, int maxiters, const float* v, int lane, int* n_evals) {
+// bfgs (lib/bfgs.h:358-502), fast_line_search; W.x in/out, W.g out; returns f0 (all lanes).
+// Written around ONE evaluation site: the initial evaluation, every line-search trial and (grid_e != nullptr) the chain's
+// update_energy after the minimisation -- cache::eval at the final conformation with curl cap grid_v1 -- are iterations of
+// the same loop, so a kernel holds one copy of dk_eval_deriv (the arithmetic and its order are those of the reference).
+__device__ float dk_bfgs(const LigPtrs& L, const DockField& F, WarpWs& W, int maxiters, const float* v, int lane, int* n_evals,
+                         float* grid_e = nullptr, float grid_v1 = 0.f) {
   const int T = L.n_seg - 1, n = 6 + T, nx = 7 + T;
+  #pragma unroll 1
   for (int k = lane; k < n * (n + 1) / 2; k += 32) W.h[k] = 0.f;
   __syncwarp();
+  #pragma unroll 1
   for (int i = lane; i < n; i += 32) W.h[dk_tri(i, i)] = 1.f;
-  int evals = 1;
-  float f0 = dk_eval_deriv(L, F, W, W.x, v, W.g, lane);
-  const float f_orig = f0;
-  for (int i = lane; i < nx; i += 32) W.x_orig[i] = W.x[i];
-  for (int i = lane; i < n; i += 32) W.g_orig[i] = W.g[i];
-  __syncwarp();
-  bool didreset = false;
-  for (int step = 0; step < maxiters; step++) {
-    for (int i = lane; i < n; i += 32) {
-      float s = 0.f;
-      for (int j2 = 0; j2 < n; j2++) s += W.h[dk_tri(i, j2)] * W.g[j2];
-      W.p[i] = -s;
-    }
-    __syncwarp();
-    const float pg = dk_dot_seq(W.p, W.g, n);
-    float f1 = 0.f, alpha = 1.f;
-    for (int trial = 0; trial < 10; trial++) {
-      for (int i = lane; i < nx; i += 32) W.x_new[i] = W.x[i];
+  int evals = 0, step = -1, trial = 0;   // step -1: the initial evaluation; phase 2: the final grid-only evaluation
+  float f0 = 0.f, f1 = 0.f, f_orig = 0.f, alpha = 1.f, pg = 0.f;
+  bool didreset = false, finishing = false;
+  const float vg[3] = {grid_v1, grid_v1, grid_v1};
+  #pragma unroll 1
+  for (;;) {
+    const bool init = step < 0;
+    const float fe = dk_eval_deriv(L, F, W, (init || finishing) ? W.x : W.x_new, finishing ? vg : v, init ? W.g : W.g_new, lane, finishing);
+    if (finishing) { *grid_e = fe; break; }
+    evals++;
+    bool new_iter = false, done = false;
+    if (init) {
+      f0 = fe; f_orig = fe;
+      #pragma unroll 1
+      for (int i = lane; i < nx; i += 32) W.x_orig[i] = W.x[i];
+      #pragma unroll 1
+      for (int i = lane; i < n; i += 32) W.g_orig[i] = W.g[i];
       __syncwarp();
-      dk_conf_increment(W.x_new, W.p, alpha, T, lane);
-      f1 = dk_eval_deriv(L, F, W, W.x_new, v, W.g_new, lane);
-      evals++;
-      if (f1 - f0 < 0.0001f * alpha * pg) break;
-      alpha *= 0.5f;
-    }
-    if (alpha == 0.f) break;
-    for (int i = lane; i < n; i += 32) W.y[i] = W.g_new[i] - W.g[i];
-    f0 = f1;
-    for (int i = lane; i < nx; i += 32) W.x[i] = W.x_new[i];
-    __syncwarp();
-    for (int i = lane; i < n; i += 32) W.g[i] = W.g_new[i];
-    __syncwarp();
-    const float gn = dk_dot_seq(W.g, W.g, n), yy = dk_dot_seq(W.y, W.y, n), yp = dk_dot_seq(W.y, W.p, n);
-    if (!(gn >= 1e-4f)) break;
-    if (step == 0 || didreset) {
-      didreset = false;
-      if (fabsf(yy) > 1.1920929e-07f)
-        for (int i = lane; i < n; i += 32) W.h[dk_tri(i, i)] = alpha * yp / yy;
-      __syncwarp();
-    }
-    if (!(alpha * yp < 1.1920929e-07f)) {  // bfgs_update
-      for (int i = lane; i < n; i += 32) {
-        float s = 0.f;
-        for (int j2 = 0; j2 < n; j2++) s += W.h[dk_tri(i, j2)] * W.y[j2];
-        W.mhy[i] = -s;
+      new_iter = true;
+    } else {
+      f1 = fe;
+      const bool accepted = f1 - f0 < 0.0001f * alpha * pg;
+      if (!accepted) { alpha *= 0.5f; trial++; }
+      if (accepted || trial >= 10) {
+        // the line search is over (alpha has been halved after the tenth failure too, as the reference's loop does)
+        if (alpha == 0.f) done = true;
+        else {
+          #pragma unroll 1
+          for (int i = lane; i < n; i += 32) W.y[i] = W.g_new[i] - W.g[i];
+          f0 = f1;
+          #pragma unroll 1
+          for (int i = lane; i < nx; i += 32) W.x[i] = W.x_new[i];
+          __syncwarp();
+          #pragma unroll 1
+          for (int i = lane; i < n; i += 32) W.g[i] = W.g_new[i];
+          __syncwarp();
+          const float gn = dk_dot_seq(W.g, W.g, n), yy = dk_dot_seq(W.y, W.y, n), yp = dk_dot_seq(W.y, W.p, n);
+          if (!(gn >= 1e-4f)) done = true;
+          else {
+            if (step == 0 || didreset) {
+              didreset = false;
+              if (fabsf(yy) > 1.1920929e-07f) {
+                #pragma unroll 1
+                for (int i = lane; i < n; i += 32) W.h[dk_tri(i, i)] = alpha * yp / yy;
+              }
+              __syncwarp();
+            }
+            if (!(alpha * yp < 1.1920929e-07f)) {  // bfgs_update
+              #pragma unroll 1
+              for (int i = lane; i < n; i += 32) {
+                float s = 0.f;
+                #pragma unroll 1
+                for (int j2 = 0; j2 < n; j2++) s += W.h[dk_tri(i, j2)] * W.y[j2];
+                W.mhy[i] = -s;
+              }
+              __syncwarp();
+              const float yhy = -dk_dot_seq(W.y, W.mhy, n);
+              const float r = 1 / (alpha * yp);
+              #pragma unroll 1
+              for (int k = lane; k < n * (n + 1) / 2; k += 32) {
+                // invert k = i + j(j+1)/2, i <= j
+                int j2 = (int)((sqrtf(8.f * k + 1.f) - 1.f) * 0.5f);
+                while (j2 * (j2 + 1) / 2 > k) j2--;
+                while ((j2 + 1) * (j2 + 2) / 2 <= k) j2++;
+                const int i = k - j2 * (j2 + 1) / 2;
+                W.h[k] += alpha * r * (W.mhy[i] * W.p[j2] + W.mhy[j2] * W.p[i]) + alpha * alpha * (r * r * yhy + r) * W.p[i] * W.p[j2];
+              }
+              __syncwarp();
+            }
+            new_iter = true;
+          }
+        }
       }
-      __syncwarp();
-      const float yhy = -dk_dot_seq(W.y, W.mhy, n);
-      const float r = 1 / (alpha * yp);
-      for (int k = lane; k < n * (n + 1) / 2; k += 32) {
-        // invert k = i + j(j+1)/2, i <= j
-        int j2 = (int)((sqrtf(8.f * k + 1.f) - 1.f) * 0.5f);
-        while (j2 * (j2 + 1) / 2 > k) j2--;
-        while ((j2 + 1) * (j2 + 2) / 2 <= k) j2++;
-        const int i = k - j2 * (j2 + 1) / 2;
-        W.h[k] += alpha * r * (W.mhy[i] * W.p[j2] + W.mhy[j2] * W.p[i]) + alpha * alpha * (r * r * yhy + r) * W.p[i] * W.p[j2];
-      }
-      __syncwarp();
     }
-  }
-  if (!(f0 <= f_orig)) {
-    f0 = f_orig;
-    for (int i = lane; i < nx; i += 32) W.x[i] = W.x_orig[i];
-    for (int i = lane; i < n; i += 32) W.g[i] = W.g_orig[i];
+    if (new_iter) {
+      step++;
+      if (step >= maxiters) done = true;
+      else {
+        #pragma unroll 1
+        for (int i = lane; i < n; i += 32) {
+          float s = 0.f;
+          #pragma unroll 1
+          for (int j2 = 0; j2 < n; j2++) s += W.h[dk_tri(i, j2)] * W.g[j2];
+          W.p[i] = -s;
+        }
+        __syncwarp();
+        pg = dk_dot_seq(W.p, W.g, n);
+        alpha = 1.f; trial = 0;
+      }
+    }
+    if (done) {
+      if (!(f0 <= f_orig)) {
+        f0 = f_orig;
+        #pragma unroll 1
+        for (int i = lane; i < nx; i += 32) W.x[i] = W.x_orig[i];
+        #pragma unroll 1
+        for (int i = lane; i < n; i += 32) W.g[i] = W.g_orig[i];
+        __syncwarp();
+      }
+      if (!grid_e) break;
+      finishing = true;
+      continue;
+    }
+    // next trial point: x_new = x (+) alpha p
+    #pragma unroll 1
+    for (int i = lane; i < nx; i += 32) W.x_new[i] = W.x[i];
     __syncwarp();
+    dk_conf_increment(W.x_new, W.p, alpha, T, lane);
   }
   if (n_evals) *n_evals = evals;
   return f0;
@@ -1154,30 +1238,46 @@ __global__ void __launch_bounds__(32 * kDkWarps) dock_mc_kernel(LigPtrs L, DockF
       } else W.cand[7 + which - 2] = dk_rng_fl(rs, -pi, pi);
     }
     __syncwarp();
-    for (int i = lane; i < nx; i += 32) W.x[i] = W.cand[i];
-    __syncwarp();
-    dk_bfgs(L, F, W, P.maxiters, P.hunt_cap, lane, nullptr);
-    for (int i = lane; i < nx; i += 32) W.cand[i] = W.x[i];
-    __syncwarp();
-    const float cand_e = dk_eval_grid(L, F, W, W.cand, av[1], lane);
-    int accept = (step == 0 || cand_e < tmp_e) ? 1 : 0;
-    if (!accept) {
-      float u = 0.f;
-      if (lane == 0) u = dk_rng_fl(rs, 0, 1);
-      u = __shfl_sync(0xffffffffu, u, 0);
-      accept = u < (float)exp((double)((tmp_e - cand_e) / P.temperature));  // correctly rounded, like glibc's expf
-    }
-    if (accept) {
-      for (int i = lane; i < nx; i += 32) W.tmp[i] = W.cand[i];
+    // Two quasi-Newton runs per step at most -- the hunt with hunt_cap, then, for an accepted candidate that is promising,
+    // the full-cap run (monte_carlo.cpp:111-137) -- through ONE dk_bfgs call site (pass 0 / pass 1), each followed by
+    // update_energy = the grid-only evaluation folded into dk_bfgs.
+    bool promising = false;
+    #pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+      const float* src = pass == 0 ? W.cand : W.tmp;
+      #pragma unroll 1
+      for (int i = lane; i < nx; i += 32) W.x[i] = src[i];
       __syncwarp();
-      tmp_e = cand_e;
-      if (tmp_e < best_e || n_out < S) {
-        for (int i = lane; i < nx; i += 32) W.x[i] = W.tmp[i];
+      float ge = 0.f;
+      dk_bfgs(L, F, W, P.maxiters, pass == 0 ? P.hunt_cap : av, lane, nullptr, &ge, av[1]);
+      if (pass == 0) {
+        #pragma unroll 1
+        for (int i = lane; i < nx; i += 32) W.cand[i] = W.x[i];
         __syncwarp();
-        dk_bfgs(L, F, W, P.maxiters, av, lane, nullptr);
+        const float cand_e = ge;
+        int accept = (step == 0 || cand_e < tmp_e) ? 1 : 0;
+        if (!accept) {
+          float u = 0.f;
+          if (lane == 0) u = dk_rng_fl(rs, 0, 1);
+          u = __shfl_sync(0xffffffffu, u, 0);
+          accept = u < (float)exp((double)((tmp_e - cand_e) / P.temperature));  // correctly rounded, like glibc's expf
+        }
+        if (!accept) break;
+        #pragma unroll 1
+        for (int i = lane; i < nx; i += 32) W.tmp[i] = W.cand[i];
+        __syncwarp();
+        tmp_e = cand_e;
+        if (!(tmp_e < best_e || n_out < S)) break;
+      } else {
+        #pragma unroll 1
         for (int i = lane; i < nx; i += 32) W.tmp[i] = W.x[i];
         __syncwarp();
-        tmp_e = dk_eval_grid(L, F, W, W.tmp, av[1], lane);  // leaves the coordinates in W.coords
+        tmp_e = ge;   // the evaluation left the pose's coordinates in W.coords
+        promising = true;
+      }
+    }
+    if (promising) {
+      {
         // add_to_output_container: rmsd of the heavy atoms to every kept pose
         int ci = n_out;
         float cr = 3.402823466e+38f;
