@@ -799,7 +799,7 @@ def rows_main():
     # --- config 3 at the REFERENCE's Monte-Carlo length: num_steps = 105 (50 + N_atoms + 10 DOF) per chain (main/main.cpp:
     # 442-443), exhaustiveness 64, search -> merge -> refine_structure -> CNN rescoring -> exact affinity.  A bounded sample of
     # ligands, all in flight at once (one Vina handle + CNN clone per host thread), extrapolated to BASELINE's 1k ligands.
-    n_full, workers_full = 32, 32
+    n_full, workers_full = 64, 64
     ligs_full = [synth.make_flexible_ligand(n_heavy=20 + (i % 8), n_tors=3 + i % 4, seed=300 + i) for i in range(n_full)]
     steps_ref = [docking.reference_num_steps(len(l["types"]), 6 + len(l["seg_parent"]) - 1) for l in ligs_full]
     with docking.DockingPool(rec_xyz, rec_t, ["crossdock_default2018"], n_workers=workers_full) as pool:

@@ -650,18 +650,19 @@ __device__ inline void dk_sincos(float a, float* s, float* c) {
 __device__ inline float dk_sum_seq(const float* a, int n) {
   float s = 0.f;
   const float4* a4 = reinterpret_cast<const float4*>(a);
-  const int n4 = n >> 2;
-  if (n4 > 0) {
-    float4 v = a4[0];
+  const int n16 = n >> 4;
+  // 16 elements per trip: four 128-bit loads issued together, then the sixteen dependent additions (r2s: with one quad per
+  // trip the loop bookkeeping was 40 % of this function, and this function 20 % of the chain kernel's instructions)
 #pragma unroll 1
-    for (int k = 0; k < n4; k++) {
-      const float4 nxt = a4[k + 1 < n4 ? k + 1 : k];   // the next quad is in flight while this one is added
-      s += v.x; s += v.y; s += v.z; s += v.w;
-      v = nxt;
-    }
+  for (int k = 0; k < n16; k++) {
+    const float4 v0 = a4[4 * k], v1 = a4[4 * k + 1], v2 = a4[4 * k + 2], v3 = a4[4 * k + 3];
+    s += v0.x; s += v0.y; s += v0.z; s += v0.w;
+    s += v1.x; s += v1.y; s += v1.z; s += v1.w;
+    s += v2.x; s += v2.y; s += v2.z; s += v2.w;
+    s += v3.x; s += v3.y; s += v3.z; s += v3.w;
   }
 #pragma unroll 1
-  for (int k = n4 << 2; k < n; k++) s += a[k];
+  for (int k = n16 << 4; k < n; k++) s += a[k];
   return s;
 }
 // a, b 16-byte aligned (the BFGS vectors of the workspace)
@@ -1189,7 +1190,7 @@ __global__ void noncache_atoms_kernel(const float4* __restrict__ atoms, int n, D
 struct McDev { int num_steps, maxiters, num_saved_mins; float temperature, mutation_amplitude, min_rmsd; float hunt_cap[3]; };
 
 // no min-blocks hint: capping the chain kernel at 64 registers measured 17 % slower (621 k vs 750 k MC steps/s)
-__global__ void __launch_bounds__(32 * kDkWarps) dock_mc_kernel(LigPtrs L, DockField F, McDev P, float c1x, float c1y, float c1z, float c2x,
+__global__ void __launch_bounds__(32 * kDkWarps, 7) dock_mc_kernel(LigPtrs L, DockField F, McDev P, float c1x, float c1y, float c1z, float c2x,
                                                                 float c2y, float c2z, const uint32_t* __restrict__ seeds, int n_chains,
                                                                 float* __restrict__ out_e, float* __restrict__ out_conf,
                                                                 float* __restrict__ out_heavy, int* __restrict__ n_out_arr,
