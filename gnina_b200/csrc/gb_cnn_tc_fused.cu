@@ -63,8 +63,11 @@ constexpr int kSmemTotal = kOffBar + 512;
 //              a FIXED schedule -- the pointwise MMA of output plane j goes into the queue right before the convolution
 //              MMAs of the input plane two commits later, when plane j's accumulator has long been complete and staged --
 //              and an epilogue that runs one plane behind itself (stage plane j, then finish plane j - 1), so neither side
-//              ever waits for the other's latency.  TMEM ring of 6 plane slots + 2 x 32 columns.
-template <bool kTcPw> struct Var { static constexpr int kR = kTcPw ? 6 : 8; };
+//              ever waits for the other's latency.  The pointwise accumulator of plane j is written INTO plane j's own ring
+//              slot (the epilogue has drained it by then), so all 256 TMEM columns form a ring of 8 plane slots: with 24
+//              planes per item the ring wraps at item boundaries and an N = 96 MMA has to be split at a wrap (two MMAs that
+//              both read the 4 KB A tile) for 4 of 24 planes instead of 8 of 24 with a 6-slot ring + separate D2 columns.
+template <bool kTcPw> struct Var { static constexpr int kR = 8; };
 
 struct FusedParams {
   const uint4* wp;     // conv1: [9][4][96] x 16 B (make_conv_tc)
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(192) conv1_pw2_pool_kernel(const __grid_consta
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint32_t a2_lo = ((uint32_t)(2048 >> 4) << 16) | (ptx::smem_u32(s_y + b * 8192) >> 4);   // LBO = 128 rows x 16 B
-          const uint32_t tm_d2 = tmem_base + kR * 32 + b * 32;
+          const uint32_t tm_d2 = tmem_base + (pw_issued % kR) * 32u;   // plane j's own slot, drained before a2_full[b] completed
           ptx::mma_f16_ss_lohi<0>(tm_d2, a2_lo, kDescHiB, w2_lo, kDescHiB, ptx::idesc_f16(128, 32));
           ptx::mma_f16_ss_lohi<1>(tm_d2, a2_lo + 2 * (2048 >> 4), kDescHiB, w2_lo + 2 * (512 >> 4), kDescHiB, ptx::idesc_f16(128, 32));
           ptx::tc_commit(&d2_full[b]);
@@ -283,8 +286,7 @@ __global__ void __launch_bounds__(192) conv1_pw2_pool_kernel(const __grid_consta
         uint32_t v[32];
         ptx::tmem_ld32(tmem_base + tm_lane + slot * 32u, v);
         ptx::tmem_ld_wait();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&acce[slot]);
+        ptx::tc_fence_before();   // ordered before the a2_full arrival below: the pointwise MMA may then overwrite the slot
 #pragma unroll
         for (int c8 = 0; c8 < 4; c8++) {
           uint32_t w[4];
@@ -309,9 +311,10 @@ __global__ void __launch_bounds__(192) conv1_pw2_pool_kernel(const __grid_consta
       if (warp == 2) tr(p.trace, 2, j, 3);
       ptx::tc_fence_after();
       uint32_t v[32];
-      ptx::tmem_ld32(tmem_base + tm_lane + (uint32_t)(kR * 32) + b * 32u, v);
+      ptx::tmem_ld32(tmem_base + tm_lane + (jj % kR) * 32u, v);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
+      ptx::mbar_arrive(&acce[jj % kR]);   // the slot is free for the convolution of plane jj + kR
       const int xo = (int)(jj % kD) + 1;
       if (xo & 1) {
 #pragma unroll
