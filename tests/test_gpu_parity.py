@@ -271,3 +271,25 @@ def test_chunk_boundaries_and_big_ligands(kat):
     a = s.score_batch(lx, lt, [0, len(lt)])
     b = v0.score_batch(lx, lt, [0, len(lt)])
     assert abs(a[0][0] - b[0][0]) < 3e-3 and abs(a[1][0] - b[1][0]) < 1e-2 * max(1.0, abs(b[1][0]))   # fast-mode tolerance
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ens,n", [("crossdock_default2018_ensemble", 15), ("general_default2018_ensemble", 10), ("redock_default2018_ensemble", 15)])
+def test_every_packaged_default2018_ensemble_matches_the_oracle(kat, ens, n):
+    """All 64 embedded models of the reference are packaged: the ensemble names expand over the reference's table
+    (cnn_torch_scorer.cpp:37-60) and every member's fast-path result agrees with the CPU restatement on its own blob."""
+    from gnina_b200 import model_blob
+    from oracle import pipeline
+    s = _scorer([ens], 1)
+    assert len(s.model_names) == n
+    s.set_receptor(kat["rec_xyz"], kat["rec_types"])
+    k = 3
+    offs = kat["pose_offsets"][:k + 1]
+    lx, lt = kat["lig_xyz"][:offs[k]], kat["lig_types"][:offs[k]]
+    sc, aff, loss, var = s.score_batch(lx, lt, offs)
+    pm, am, lm = s.score_batch_models(lx, lt, offs)
+    assert pm.shape == (n, k) and np.abs(pm.mean(0) - sc).max() < 1e-6 and np.abs(am.mean(0) - aff).max() < 1e-5
+    for mi in (0, n - 1):   # first and last member against the oracle
+        om = pipeline.OracleModel(model_blob.load_model(s.model_names[mi]))
+        po, ao, _ = om.score(kat["rec_xyz"], kat["rec_types"], lx, lt, offs)
+        assert np.abs(pm[mi] - po).max() < 2e-3 and np.abs(am[mi] - ao).max() < 1e-2

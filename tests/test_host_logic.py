@@ -40,6 +40,23 @@ def test_blob_reader_roundtrip():
         model_blob.load_model("nope")
 
 
+def test_all_64_reference_models_are_packaged():
+    """Every model the reference embeds (gninasrc/CMakeLists.txt:95-188) has its blob; architecture and head shapes are read
+    from each (cheap header + shape checks; the numerics are the GPU tests')."""
+    assert sorted(scorer.builtin_models()) == sorted(scorer.REFERENCE_MODELS)
+    archs = {}
+    for name in scorer.REFERENCE_MODELS:
+        b = model_blob.load_model(name)
+        archs[b.arch] = archs.get(b.arch, 0) + 1
+        assert b.resolution == 0.5 and b.dimension == 23.5
+        if b.arch == "default2018":
+            assert b.tensors["unit1_conv.weight"].shape == (32, 28, 3, 3, 3) and b.tensors["affinity_output.weight"].shape == (1, 27648)
+        elif b.arch == "dense":
+            assert b.tensors["pose_output.weight"].shape == (2, 224)
+    assert archs == {"default2018": 48, "dense": 15, "default2017": 1}
+    assert len(scorer.expand_model_names(["crossdock_default2018_ensemble"])) == 15
+
+
 def test_synth_is_deterministic_and_shaped():
     x1, t1 = synth.make_receptor(200, box=30)
     x2, t2 = synth.make_receptor(200, box=30)

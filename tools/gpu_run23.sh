@@ -1,0 +1,4 @@
+set -x
+timeout 300 python -m pytest tests/test_gpu_tc.py -m gpu -q --tb=short -x 2>&1 | tail -8 > gpurun_out/r2w_pytest.log
+timeout 200 python bench.py --no-cpu-baseline --no-gpu-reference > gpurun_out/r2w_bench.json 2> gpurun_out/r2w_bench.err
+GB_TC_FUSED_TRACE=gpurun_out/r2w_trace.txt timeout 120 python tools/ncu_score.py 2048 > gpurun_out/r2w_t1.log 2>&1
