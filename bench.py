@@ -701,8 +701,23 @@ def rows_main():
         e = CNNScorer(names, precision=0)
         e.set_receptor(rec_xyz, rec_t)
         dt = timed(lambda: e.score_batch(lx[:offs[n2]], lt[:offs[n2]], offs[:n2 + 1]), reps=2)
-        out.append({"row": tag, "value": n2 / dt, "unit": "poses/s", "mode": "fp32 validation kernels",
+        out.append({"row": tag + " [fp32 validation kernels]", "value": n2 / dt, "unit": "poses/s", "mode": "fp32 validation kernels",
                     "models": e.model_names})
+    # gnina's default (--cnn unset): the 3-model ensemble on the fast path, and its score + atom-gradient call (config 5 as gnina
+    # runs it by default; the two dense members' backward runs on the fp32 kernels)
+    e3 = CNNScorer([], precision=1)
+    e3.set_receptor(rec_xyz, rec_t)
+    n3 = 4096
+    lx3, offs3 = synth.make_poses(lx0, n3, seed=8)
+    lt3 = np.tile(lt0, n3)
+    dt = timed(lambda: e3.score_batch(lx3, lt3, offs3), reps=2)
+    out.append({"row": "default_ensemble 3 models (N1+N2, S1), fast path", "value": n3 / dt, "unit": "poses/s", "mode": "fp16 tcgen05",
+                "models": e3.model_names})
+    ng = 128
+    dt = timed(lambda: e3.score_grad_batch(lx3[:offs3[ng]], lt3[:offs3[ng]], offs3[:ng + 1]), reps=2)
+    out.append({"row": "default_ensemble 3 models, score + atom gradients (config 5 default)", "value": ng / dt, "unit": "poses/s",
+                "mode": "default2018 member: tcgen05 forward + backward; dense members: fp32 kernels", "models": e3.model_names})
+    del e3
 
     # --- Vina rows ---
     v, o = VinaScorer(), VinaOracle()
