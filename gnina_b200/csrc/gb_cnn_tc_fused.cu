@@ -32,6 +32,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <mutex>
+#include <type_traits>
 #include "gb_ptx.cuh"
 #include "gb_tc.h"
 
@@ -469,6 +470,323 @@ __global__ void __launch_bounds__(192) conv1_pw2_pool_kernel(const __grid_consta
   }
 }
 
+// ======================================================================================================================
+// "v2" of the fused kernel (GB_TC_FUSED_V2=1): ONE CTA per SM with all 512 TMEM columns.
+//   * ring of 8 plane slots + 2 GHOST slots (columns 256..319): the window of input plane xi always writes three CONSECUTIVE
+//     slots starting at slot((xi - 2) & 7); when that runs past slot 7 the planes that belong in slots 0 / 1 receive their
+//     first contributions in the ghosts, their remaining ones in their own slot, and the epilogue adds the two.  No N = 96 MMA
+//     is ever split at a ring wrap (a split pair reads the 4 KB A tile twice: 88 instead of 56 cycles of operand fetch)
+//   * 16 epilogue warps in two TEAMS that own alternate plane pairs (a 2x2x2 pooling window needs both planes of a pair);
+//     inside a team two warps per TMEM lane quarter, 16 of the 32 channels each.  One plane is a ~1250-cycle chain of
+//     dependent latencies for a warp (barrier, tcgen05.ld, shared stores, proxy fence, barrier, tcgen05.ld, shuffles): r2y, with
+//     one team the epilogue bounded the kernel however the columns were split; two planes in flight remove that
+//   * 6 TMA stages, the issue loop unrolled over the ring period (slot numbers and accumulate patterns are compile-time)
+// Same arithmetic as variant B above (pointwise tcgen05.mma into the plane's own slot on the fixed schedule).
+constexpr int k2Stages = 6;
+constexpr int k2Ncg = 2;                  // column groups: epilogue warps per TMEM lane quarter and team
+constexpr int k2Cw = 32 / k2Ncg;          // channels per epilogue warp
+constexpr int k2Teams = 2;                // epilogue teams; team t owns the plane PAIRS t, t + 2, t + 4, ...
+constexpr int k2TeamWarps = 4 * k2Ncg;
+constexpr int k2EpiWarps = k2Teams * k2TeamWarps;
+constexpr int k2Bufs = 2 * k2Teams;       // A-operand buffers of the pointwise MMA (one per plane in flight)
+constexpr int k2Threads = 32 * (3 + k2EpiWarps);   // producer, conv issuer, 8 epilogue warps, pointwise issuer
+constexpr int k2OffStage = kWBytes;
+constexpr int k2OffY = k2OffStage + k2Stages * kStageBytes;
+constexpr int k2OffW2 = k2OffY + k2Bufs * 8192;
+constexpr int k2OffBar = k2OffW2 + kW2Bytes;
+constexpr int k2SmemTotal = k2OffBar + 1024;
+
+__global__ void __launch_bounds__(k2Threads, 1) conv1_pw2_pool_v2_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
+  constexpr int kR = 8;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_w = smem;
+  uint8_t* s_stage = smem + k2OffStage;
+  uint8_t* s_y = smem + k2OffY;
+  uint8_t* s_w2 = smem + k2OffW2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k2OffBar);
+  uint64_t* full = bars;                   // [k2Stages]
+  uint64_t* empty = full + k2Stages;       // [k2Stages]
+  uint64_t* accf = empty + k2Stages;       // [kR] conv plane complete
+  uint64_t* acce = accf + kR;              // [kR] slot handed back (pointwise result read): one arrival per epilogue warp
+  uint64_t* wbar = acce + kR;
+  uint64_t* a2_full = wbar + 1;            // [k2Bufs]
+  uint64_t* d2_full = a2_full + k2Bufs;    // [k2Bufs]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(d2_full + k2Bufs);
+  float* s_bias = reinterpret_cast<float*>(s_tmem + 2);   // bias1[32], bias2[32]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = p.n_groups * kRowTiles * kZBlocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < k2Stages; s++) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kR; s++) { ptx::mbar_init(&accf[s], 1); ptx::mbar_init(&acce[s], k2TeamWarps); }   // one arrival per warp of the owning team
+    ptx::mbar_init(wbar, 1);
+    for (int b = 0; b < k2Bufs; b++) { ptx::mbar_init(&a2_full[b], k2TeamWarps); ptx::mbar_init(&d2_full[b], 1); }
+    ptx::fence_mbar_init();
+  }
+  if (threadIdx.x < 32) s_bias[threadIdx.x] = p.bias1[threadIdx.x];
+  else if (threadIdx.x < 64) s_bias[threadIdx.x] = p.bias2[threadIdx.x - 32];
+  if (warp == 1) {
+    ptx::tmem_alloc(s_tmem, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===== producer =====
+    if (ptx::elect_one()) {
+      ptx::prefetch_tmap(&tmap);
+      ptx::mbar_expect_tx(wbar, kWBytes + kW2Bytes);
+      for (int t9 = 0; t9 < 9; t9++)
+        ptx::bulk_g2s(s_w + t9 * (kWBytes / 9), reinterpret_cast<const uint8_t*>(p.wp) + t9 * (kWBytes / 9), kWBytes / 9, wbar);
+      ptx::bulk_g2s(s_w2, p.w2p, kW2Bytes, wbar);
+    }
+    __syncwarp();
+    uint32_t gp = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int zb = item % kZBlocks, k = (item / kZBlocks) % kRowTiles, g = item / (kZBlocks * kRowTiles);
+      for (int it = 0; it < kD; it++, gp++) {
+        const uint32_t st = gp % k2Stages, ph = (gp / k2Stages) & 1;
+        ptx::mbar_wait(&empty[st], ph ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(&full[st], kStageBytes);
+          ptx::tma_load_4d(s_stage + (size_t)st * kStageBytes, &tmap, 64 * zb, 16 * k, 0, g * kD + it, &full[st]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===== convolution MMA issuer: ONE thread does everything (waits included).  With a single CTA per SM nobody else
+    // fills the tensor-core queue while this thread is away, and the queue is only a few MMAs deep (r2y: every cycle this
+    // thread spent waiting was an idle cycle of the unit), so the barrier waits of the NEXT window are taken in the middle
+    // of the current window's MMAs, where a few queued MMAs cover their latency. =====
+    if (ptx::elect_one()) {
+      constexpr uint32_t kDescHiA = (uint32_t)(kSlabZ * 16 >> 4) | (1u << 14);
+      constexpr uint32_t kDescHiB = (128u >> 4) | (1u << 14);
+      const uint32_t a_lo_fixed = ((uint32_t)(kChunkBytes >> 4)) << 16;
+      const uint32_t b_lo_base = (96u << 16) | (ptx::smem_u32(s_w) >> 4);
+      ptx::mbar_wait(wbar, 0);
+      uint32_t gp = 0, pbase = 0;   // pbase: global index of this item's plane 1 (a multiple of 24, hence of the ring period)
+      // barrier waits of window (it8, r): the TMA box, and the slot of every output plane that receives its FIRST
+      // contribution there (handed back by the plane 8 earlier; a first contribution that lands in a ghost slot is covered
+      // by the same wait)
+      auto wait_window = [&](const int r, const int it8, const uint32_t gpw, const uint32_t pb) {
+        const int xi = 8 * it8 + r + 1;
+        if (xi != kD) {
+          const uint32_t gpl = pb + (uint32_t)xi, u = gpl >> 3;      // plane xi + 1
+          if (u > 0) ptx::mbar_wait(&acce[(r + 1) & 7], (u - 1) & 1);
+        }
+        if (xi == 1) {
+          const uint32_t u = pb >> 3;                                  // plane 1
+          if (u > 0) ptx::mbar_wait(&acce[0], (u - 1) & 1);
+        }
+        ptx::mbar_wait(&full[gpw % k2Stages], (gpw / k2Stages) & 1);
+      };
+      // one window = one input plane; r = (xi - 1) & 7 is a compile-time constant of the unrolled body
+      auto window = [&](auto rc, const int it8, const bool more) {
+        constexpr int r = decltype(rc)::value;
+        const bool first_w = (r == 0) && it8 == 0;   // xi == 1: output planes 1, 2 only
+        const bool last_w = (r == 7) && it8 == 2;    // xi == 24: output planes 23, 24 only
+        tr(p.trace, 1, gp, 0);
+        const uint32_t st = gp % k2Stages;
+        ptx::tc_fence_after();
+        const uint32_t a_lo_base = a_lo_fixed | (ptx::smem_u32(s_stage + (size_t)st * kStageBytes) >> 4);
+        constexpr uint32_t s0 = (uint32_t)((r + 7) & 7);   // slot of output plane xi - 1; s0 = 6, 7 run on into the ghosts
+        uint32_t tm, bl, idn;
+        if (first_w) { tm = tmem_base; bl = b_lo_base + 32u; idn = ptx::idesc_f16(128, 64); }
+        else if (last_w) { tm = tmem_base + 6 * 32u; bl = b_lo_base; idn = ptx::idesc_f16(128, 64); }
+        else { tm = tmem_base + s0 * 32u; bl = b_lo_base; idn = ptx::idesc_f16(128, 96); }
+        // first MMA of the window (tap 0, k step 0): who is fresh
+        if (first_w || (r == 1 && it8 > 0)) {
+          ptx::mma_f16_ss_lohi<0>(tm, a_lo_base, kDescHiA, bl, kDescHiB, idn);                       // every plane of the window is fresh
+        } else if (last_w) {
+          ptx::mma_f16_ss_lohi<1>(tm, a_lo_base, kDescHiA, bl, kDescHiB, idn);
+        } else {
+          ptx::mma_f16_ss_lohi<1>(tm, a_lo_base, kDescHiA, bl, kDescHiB, ptx::idesc_f16(128, 64));     // planes xi - 1, xi
+          ptx::mma_f16_ss_lohi<0>(tm + 64u, a_lo_base, kDescHiA, bl + 64u, kDescHiB, ptx::idesc_f16(128, 32));   // plane xi + 1: fresh
+        }
+#pragma unroll
+        for (int m = 1; m < 12; m++) ptx::mma_f16_ss_lohi<1>(tm, a_lo_base + off_a(m), kDescHiA, bl + off_b(m), kDescHiB, idn);
+        tr(p.trace, 1, gp, 1);
+        // the next window's waits, behind a dozen queued MMAs (the item loop passes the next item's plane base when r = 7 of
+        // the last period wraps around)
+        if (more) {
+          constexpr int rn = (r + 1) & 7;
+          const int it8n = (r == 7) ? (it8 == 2 ? 0 : it8 + 1) : it8;
+          wait_window(rn, it8n, gp + 1, (r == 7 && it8 == 2) ? pbase + kD : pbase);
+          ptx::tc_fence_after();
+        }
+        tr(p.trace, 1, gp, 2);
+#pragma unroll
+        for (int m = 12; m < 18; m++) ptx::mma_f16_ss_lohi<1>(tm, a_lo_base + off_a(m), kDescHiA, bl + off_b(m), kDescHiB, idn);
+        ptx::tc_commit(&empty[st]);
+        if (!first_w) ptx::tc_commit(&accf[s0]);        // output plane xi - 1 is complete
+        if (last_w) ptx::tc_commit(&accf[7]);           // ... and so is plane 24
+        tr(p.trace, 1, gp, 4);
+        gp++;
+      };
+      int n_my = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) n_my++;
+      if (n_my > 0) wait_window(0, 0, 0, 0);
+      for (int im = 0; im < n_my; im++, pbase += kD) {
+        const bool last_item = im + 1 == n_my;
+#pragma unroll 1
+        for (int it8 = 0; it8 < 3; it8++) {
+          window(std::integral_constant<int, 0>{}, it8, true); window(std::integral_constant<int, 1>{}, it8, true);
+          window(std::integral_constant<int, 2>{}, it8, true); window(std::integral_constant<int, 3>{}, it8, true);
+          window(std::integral_constant<int, 4>{}, it8, true); window(std::integral_constant<int, 5>{}, it8, true);
+          window(std::integral_constant<int, 6>{}, it8, true); window(std::integral_constant<int, 7>{}, it8, !(last_item && it8 == 2));
+        }
+      }
+    }
+  } else if (warp == 2 + k2EpiWarps) {
+    // ===== pointwise MMA issuer (one thread): D2(j) = A2[j & 1] (128 x 32, staged by the epilogue) x W2^T into plane j's own
+    // slot.  The two issuers never touch the same TMEM columns at the same time, so their relative order in the queue does
+    // not matter. =====
+    if (ptx::elect_one()) {
+      constexpr uint32_t kDescHiB = (128u >> 4) | (1u << 14);
+      ptx::mbar_wait(wbar, 0);
+      const uint32_t w2_lo = ((uint32_t)(512 >> 4) << 16) | (ptx::smem_u32(s_w2) >> 4);
+      int n_my = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) n_my++;
+      const uint32_t n_planes = (uint32_t)n_my * kD;
+      for (uint32_t j = 0; j < n_planes; j++) {
+        const uint32_t b = j % k2Bufs;
+        ptx::mbar_wait(&a2_full[b], (j / k2Bufs) & 1);
+        ptx::tc_fence_after();
+        const uint32_t a2_lo = ((uint32_t)(2048 >> 4) << 16) | (ptx::smem_u32(s_y + b * 8192) >> 4);
+        const uint32_t tm_d2 = tmem_base + (j & 7) * 32u;
+        ptx::mma_f16_ss_lohi<0>(tm_d2, a2_lo, kDescHiB, w2_lo, kDescHiB, ptx::idesc_f16(128, 32));
+        ptx::mma_f16_ss_lohi<1>(tm_d2, a2_lo + 2 * (2048 >> 4), kDescHiB, w2_lo + 2 * (512 >> 4), kDescHiB, ptx::idesc_f16(128, 32));
+        ptx::tc_commit(&d2_full[b]);
+      }
+    }
+  } else {
+    // ===== epilogue: k2Teams teams x (4 TMEM lane quarters x k2Ncg groups of k2Cw channels) =====
+    const int ew = warp - 2, team = ew / k2TeamWarps;
+    const int q4 = warp & 3, cg = (ew % k2TeamWarps) >> 2;
+    const int row = q4 * 32 + lane;
+    const int yrow = row >> 3, zz = row & 7;
+    const uint32_t tm_mine = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(cg * k2Cw);
+    constexpr int Dn = 12, Pn = 14;
+    int n_my = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) n_my++;
+    const uint32_t n_planes = (uint32_t)n_my * kD;
+    float keep[k2Cw];
+    uint4* xo4 = reinterpret_cast<uint4*>(p.xout);
+    const float* b1 = s_bias + cg * k2Cw;
+    const float* b2 = s_bias + 32 + cg * k2Cw;
+    const bool tracer = warp == 2;
+    // this team's planes in order: pairs team, team + k2Teams, ... ; the loop stages plane cur, then finishes plane prev
+    uint32_t prev = 0xffffffffu;
+    uint4* dst_base = nullptr;   // per item: this lane's pooled output voxel (nullptr: the lane stores nothing)
+    int dst_item = -1;
+    for (uint32_t t = 0;; t++) {
+      const uint32_t cur = 2u * (uint32_t)(team + (int)(t >> 1) * k2Teams) + (t & 1);
+      const bool have_cur = cur < n_planes;
+      if (have_cur) {
+        // ---- step 1 (plane cur): conv accumulator (+ ghost part) -> bias, ReLU, fp16 -> A operand buffer ----
+        const uint32_t j = cur, slot = j & 7, b = j % k2Bufs, pj = j % kD;
+        if (tracer) tr(p.trace, 2, j, 0);
+        ptx::mbar_wait(&accf[slot], (j >> 3) & 1);
+        if (tracer) tr(p.trace, 2, j, 1);
+        ptx::tc_fence_after();
+        uint32_t v[k2Cw];
+        ptx::tmem_ld_cols(tm_mine + slot * 32u, v);
+        if (pj >= 8 && (pj & 7) < 2) {   // planes 9, 10, 17, 18 of the item: first contributions sit in ghost (pj & 1)
+          uint32_t g[k2Cw];
+          ptx::tmem_ld_cols(tm_mine + 256u + (pj & 1) * 32u, g);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < k2Cw; c++) v[c] = __float_as_uint(__uint_as_float(g[c]) + __uint_as_float(v[c]));
+        } else {
+          ptx::tmem_ld_wait();
+        }
+        ptx::tc_fence_before();
+#pragma unroll
+        for (int c8 = 0; c8 < k2Cw / 8; c8++) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const int c = c8 * 8 + 2 * e;
+            const float f0 = fmaxf(__uint_as_float(v[c]) + b1[c], 0.f);
+            const float f1 = fmaxf(__uint_as_float(v[c + 1]) + b1[c + 1], 0.f);
+            const __half2 h = __floats2half2_rn(f0, f1);
+            w[e] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(s_y + b * 8192 + (cg * (k2Cw / 8) + c8) * 2048 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        ptx::fence_proxy_async();   // every lane: its stores -> visible to the tensor core; then one arrival for the warp
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&a2_full[b]);
+        if (tracer) tr(p.trace, 2, j, 2);
+      }
+      if (prev != 0xffffffffu) {
+        // ---- step 2 (plane prev): pointwise accumulator -> bias, ReLU, 2x2x2 average ----
+        const uint32_t jj = prev, b = jj % k2Bufs, slot = jj & 7;
+        ptx::mbar_wait(&d2_full[b], (jj / k2Bufs) & 1);
+        if (tracer) tr(p.trace, 2, jj, 3);
+        ptx::tc_fence_after();
+        uint32_t v[k2Cw];
+        ptx::tmem_ld_cols(tm_mine + slot * 32u, v);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&acce[slot]);
+        const uint32_t pj = jj % kD;
+        const int xo = (int)pj + 1;
+        if (xo & 1) {
+          if ((int)(jj / kD) != dst_item) {   // first plane of an item this team sees: where this lane's pooled voxels of the item go
+            dst_item = (int)(jj / kD);
+            const int item = blockIdx.x + dst_item * gridDim.x;
+            const int zb = item % kZBlocks, k = (item / kZBlocks) % kRowTiles, grp = item / (kZBlocks * kRowTiles);
+            const int R = 16 * k + 1 + yrow;
+            const int q = R / kP, yp = R - q * kP;
+            const int pose = grp * kG + q;
+            dst_base = nullptr;
+            if (((lane & 9) == 0) && q < kG && pose < p.n_poses && yp >= 1 && yp <= kD) {
+              const int yo = (yp - 1) >> 1, zo = 4 * zb + (zz >> 1);
+              dst_base = xo4 + ((size_t)(pose / p.out_G) * Dn * 4 + cg * (k2Cw / 8)) * p.out_lp + (size_t)(pose % p.out_G) * Pn * Pn +
+                         (size_t)(yo + 1) * Pn + (zo + 1);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < k2Cw; c++) keep[c] = fmaxf(__uint_as_float(v[c]) + b2[c], 0.f);
+        } else {
+          uint32_t o[k2Cw / 2];
+#pragma unroll
+          for (int c = 0; c < k2Cw; c += 2) {
+            float s0 = keep[c] + fmaxf(__uint_as_float(v[c]) + b2[c], 0.f);
+            float s1 = keep[c + 1] + fmaxf(__uint_as_float(v[c + 1]) + b2[c + 1], 0.f);
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 8);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+            const __half2 h = __floats2half2_rn(s0 * 0.125f, s1 * 0.125f);
+            o[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          if (dst_base) {
+            uint4* dst = dst_base + (size_t)((xo >> 1) - 1) * 4 * p.out_lp;
+#pragma unroll
+            for (int c8 = 0; c8 < k2Cw / 8; c8++) dst[(size_t)c8 * p.out_lp] = make_uint4(o[4 * c8], o[4 * c8 + 1], o[4 * c8 + 2], o[4 * c8 + 3]);
+          }
+        }
+      }
+      if (!have_cur) break;
+      prev = cur;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no direct libcuda symbol dependency)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -518,6 +836,7 @@ void launch_conv1_pw2_pool(const ConvTc& conv1, const __half* w2, const uint4* w
     if (!attr_set[dev]) {
       GB_CUDA(cudaFuncSetAttribute(conv1_pw2_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
       GB_CUDA(cudaFuncSetAttribute(conv1_pw2_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+      GB_CUDA(cudaFuncSetAttribute(conv1_pw2_pool_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemTotal));
       GB_CUDA(cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev));
       attr_set[dev] = true;
     }
@@ -552,7 +871,9 @@ void launch_conv1_pw2_pool(const ConvTc& conv1, const __half* w2, const uint4* w
   static const int tc_pw = getenv("GB_TC_FUSED_PW") ? atoi(getenv("GB_TC_FUSED_PW")) : 1;   // 1 (default): pointwise conv as a second tcgen05.mma;
                                                                                                   // 0: mma.sync in the epilogue (r2g: 9.9 vs 7.6 ms)
   int grid = persist > 0 ? std::min(n_items, n_sm[dev] * persist) : n_items;
-  if (tc_pw) conv1_pw2_pool_kernel<true><<<grid, 192, kSmemTotal, s>>>(tmap, p);
+  static const int v2 = getenv("GB_TC_FUSED_V2") ? atoi(getenv("GB_TC_FUSED_V2")) : 1;   // 0: the two-CTAs-per-SM kernel above (r2x: 6.9 ms per 10 k poses; v2: 5.5)
+  if (v2) conv1_pw2_pool_v2_kernel<<<std::min(n_items, n_sm[dev]), k2Threads, k2SmemTotal, s>>>(tmap, p);
+  else if (tc_pw) conv1_pw2_pool_kernel<true><<<grid, 192, kSmemTotal, s>>>(tmap, p);
   else conv1_pw2_pool_kernel<false><<<grid, 192, kSmemTotal, s>>>(tmap, p);
   if (p.trace) {
     std::vector<unsigned long long> h(3 * kTracePlanes * 8);
