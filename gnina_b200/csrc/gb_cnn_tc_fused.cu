@@ -31,6 +31,7 @@
 #include <cstdlib>
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <map>
 #include <mutex>
 #include <type_traits>
 #include "gb_ptx.cuh"
@@ -490,14 +491,28 @@ constexpr int k2TeamWarps = 4 * k2Ncg;
 constexpr int k2EpiWarps = k2Teams * k2TeamWarps;
 constexpr int k2Bufs = 2 * k2Teams;       // A-operand buffers of the pointwise MMA (one per plane in flight)
 constexpr int k2Threads = 32 * (3 + k2EpiWarps);   // producer, conv issuer, 8 epilogue warps, pointwise issuer
-constexpr int k2OffStage = kWBytes;
+// pair mode: per-rank B rows.  [0,96): 48 rows per (tap, chunk); [0,64) and [32,96): 32 rows; [64,96) of tap 0, chunks 0-1: 16 rows
+constexpr int kPairOffA64 = 9 * 4 * 48 * 16;                       // 27648
+constexpr int kPairOffB64 = kPairOffA64 + 9 * 4 * 32 * 16;         // 46080
+constexpr int kPairOffC32 = kPairOffB64 + 9 * 4 * 32 * 16;         // 64512
+constexpr int kPairWBytes = kPairOffC32 + 2 * 16 * 16 + 512;       // 65536 (padded: eight equal bulk copies)
+constexpr int kPairW2Bytes = 4 * 16 * 16;                          // 1024
+constexpr int k2OffStage = 65536;
 constexpr int k2OffY = k2OffStage + k2Stages * kStageBytes;
 constexpr int k2OffW2 = k2OffY + k2Bufs * 8192;
 constexpr int k2OffBar = k2OffW2 + kW2Bytes;
 constexpr int k2SmemTotal = k2OffBar + 1024;
 
+// kPair: a cluster of two CTAs (the two SMs of a TPC) works on two items in lockstep with tcgen05 ...cta_group::2: every MMA is
+// M = 256 (128 rows of each CTA's own A slab and TMEM) and reads only HALF of the B rows from each CTA's shared memory -- 5.5 KB
+// of operands per N = 96 MMA instead of 7, under the 48 cycles of math.  Only the leader CTA (rank 0) issues MMAs; its barriers
+// collect the arrivals of both CTAs' epilogue warps, tcgen05.commit multicasts completion to both.  The B rows are packed per
+// rank by pack_pair_weights(): the sub-ranges of N used at item edges and for the first-touch MMA need their own half-split
+// copies (a sub-range of a half-split array is not a half-split of the sub-range).
+template <bool kPair>
 __global__ void __launch_bounds__(k2Threads, 1) conv1_pw2_pool_v2_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
   constexpr int kR = 8;
+  constexpr uint32_t kM = kPair ? 256u : 128u;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_w = smem;
   uint8_t* s_stage = smem + k2OffStage;
@@ -511,42 +526,83 @@ __global__ void __launch_bounds__(k2Threads, 1) conv1_pw2_pool_v2_kernel(const _
   uint64_t* wbar = acce + kR;
   uint64_t* a2_full = wbar + 1;            // [k2Bufs]
   uint64_t* d2_full = a2_full + k2Bufs;    // [k2Bufs]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(d2_full + k2Bufs);
+  uint64_t* pfull = d2_full + k2Bufs;      // [k2Stages] pair mode, leader: the peer's TMA box has landed (relayed)
+  uint64_t* pwbar = pfull + k2Stages;      // pair mode, leader: the peer's weights have landed
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(pwbar + 1);
   float* s_bias = reinterpret_cast<float*>(s_tmem + 2);   // bias1[32], bias2[32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = p.n_groups * kRowTiles * kZBlocks;
+  // work units: items, or pairs of items (unit u = items 2u, 2u + 1; an odd tail lets rank 1 redo item 2u without storing)
+  const uint32_t rank = kPair ? ptx::cluster_ctarank() : 0u;
+  const int n_units = kPair ? (n_items + 1) / 2 : n_items;
+  const int u0 = kPair ? (int)ptx::cluster_id_x() : (int)blockIdx.x, ustride = kPair ? (int)ptx::cluster_nctaid_x() : (int)gridDim.x;
+  int n_my = 0;
+  for (int u = u0; u < n_units; u += ustride) n_my++;
+  auto item_of = [&](int i, bool& valid) {   // i-th unit of this CTA -> its item
+    const int u = u0 + i * ustride;
+    if (!kPair) { valid = true; return u; }
+    const int it = 2 * u + (int)rank;
+    valid = it < n_items;
+    return valid ? it : 2 * u;
+  };
+  constexpr uint32_t kArr = kPair ? 2u * k2TeamWarps : (uint32_t)k2TeamWarps;   // arrivals on the leader's acce / a2_full barriers
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < k2Stages; s++) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
-    for (int s = 0; s < kR; s++) { ptx::mbar_init(&accf[s], 1); ptx::mbar_init(&acce[s], k2TeamWarps); }   // one arrival per warp of the owning team
+    for (int s = 0; s < kR; s++) { ptx::mbar_init(&accf[s], 1); ptx::mbar_init(&acce[s], kArr); }   // one arrival per warp of the owning team(s)
     ptx::mbar_init(wbar, 1);
-    for (int b = 0; b < k2Bufs; b++) { ptx::mbar_init(&a2_full[b], k2TeamWarps); ptx::mbar_init(&d2_full[b], 1); }
+    ptx::mbar_init(pwbar, 1);
+    for (int s = 0; s < k2Stages; s++) ptx::mbar_init(&pfull[s], 1);
+    for (int b = 0; b < k2Bufs; b++) { ptx::mbar_init(&a2_full[b], kArr); ptx::mbar_init(&d2_full[b], 1); }
     ptx::fence_mbar_init();
   }
   if (threadIdx.x < 32) s_bias[threadIdx.x] = p.bias1[threadIdx.x];
   else if (threadIdx.x < 64) s_bias[threadIdx.x] = p.bias2[threadIdx.x - 32];
   if (warp == 1) {
-    ptx::tmem_alloc(s_tmem, 512);
-    ptx::tmem_relinquish();
+    if constexpr (kPair) { ptx::tmem_alloc2(s_tmem, 512); ptx::tmem_relinquish2(); }
+    else { ptx::tmem_alloc(s_tmem, 512); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) ptx::cluster_sync_all();   // both CTAs' barriers are initialised before anyone signals across
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  // leader-side barrier wait / peer-side arrival that work in both modes
+  auto wait_x = [&](uint64_t* bar, uint32_t parity) {
+    if constexpr (kPair) ptx::mbar_wait_cluster(bar, parity);
+    else ptx::mbar_wait(bar, parity);
+  };
+  auto arrive_x = [&](uint64_t* bar) {   // on the LEADER's barrier
+    if (kPair && rank != 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(bar), 0));
+    else ptx::mbar_arrive(bar);
+  };
+  auto commit_x = [&](uint64_t* bar) {
+    if constexpr (kPair) ptx::tc_commit2(bar);
+    else ptx::tc_commit(bar);
+  };
 
   if (warp == 0) {
     // ===== producer =====
     if (ptx::elect_one()) {
       ptx::prefetch_tmap(&tmap);
-      ptx::mbar_expect_tx(wbar, kWBytes + kW2Bytes);
-      for (int t9 = 0; t9 < 9; t9++)
-        ptx::bulk_g2s(s_w + t9 * (kWBytes / 9), reinterpret_cast<const uint8_t*>(p.wp) + t9 * (kWBytes / 9), kWBytes / 9, wbar);
-      ptx::bulk_g2s(s_w2, p.w2p, kW2Bytes, wbar);
+      if constexpr (kPair) {
+        ptx::mbar_expect_tx(wbar, kPairWBytes + kPairW2Bytes);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wp) + (size_t)rank * kPairWBytes;
+        for (int t8 = 0; t8 < 8; t8++) ptx::bulk_g2s(s_w + t8 * (kPairWBytes / 8), src + t8 * (kPairWBytes / 8), kPairWBytes / 8, wbar);
+        ptx::bulk_g2s(s_w2, reinterpret_cast<const uint8_t*>(p.w2p) + (size_t)rank * kPairW2Bytes, kPairW2Bytes, wbar);
+      } else {
+        ptx::mbar_expect_tx(wbar, kWBytes + kW2Bytes);
+        for (int t9 = 0; t9 < 9; t9++)
+          ptx::bulk_g2s(s_w + t9 * (kWBytes / 9), reinterpret_cast<const uint8_t*>(p.wp) + t9 * (kWBytes / 9), kWBytes / 9, wbar);
+        ptx::bulk_g2s(s_w2, p.w2p, kW2Bytes, wbar);
+      }
     }
     __syncwarp();
     uint32_t gp = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int im = 0; im < n_my; im++) {
+      bool valid;
+      const int item = item_of(im, valid);
       const int zb = item % kZBlocks, k = (item / kZBlocks) % kRowTiles, g = item / (kZBlocks * kRowTiles);
       for (int it = 0; it < kD; it++, gp++) {
         const uint32_t st = gp % k2Stages, ph = (gp / k2Stages) & 1;
@@ -563,12 +619,33 @@ __global__ void __launch_bounds__(k2Threads, 1) conv1_pw2_pool_v2_kernel(const _
     // fills the tensor-core queue while this thread is away, and the queue is only a few MMAs deep (r2y: every cycle this
     // thread spent waiting was an idle cycle of the unit), so the barrier waits of the NEXT window are taken in the middle
     // of the current window's MMAs, where a few queued MMAs cover their latency. =====
-    if (ptx::elect_one()) {
+    if (kPair && rank != 0) {
+      // peer CTA: this warp only relays "my weights / my TMA box have landed" to the leader, which issues the MMAs that read them
+      if (ptx::elect_one()) {
+        ptx::mbar_wait(wbar, 0);
+        ptx::fence_proxy_async_all();
+        ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(pwbar), 0));
+        const uint32_t n_planes = (uint32_t)n_my * kD;
+        for (uint32_t gp = 0; gp < n_planes; gp++) {
+          const uint32_t st = gp % k2Stages;
+          ptx::mbar_wait(&full[st], (gp / k2Stages) & 1);
+          ptx::fence_proxy_async_all();
+          ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&pfull[st]), 0));
+        }
+      }
+    } else if (ptx::elect_one()) {
       constexpr uint32_t kDescHiA = (uint32_t)(kSlabZ * 16 >> 4) | (1u << 14);
       constexpr uint32_t kDescHiB = (128u >> 4) | (1u << 14);
       const uint32_t a_lo_fixed = ((uint32_t)(kChunkBytes >> 4)) << 16;
-      const uint32_t b_lo_base = (96u << 16) | (ptx::smem_u32(s_w) >> 4);
+      // B descriptors (lo words: LBO << 16 | address >> 4) and row strides of the N ranges [0,96) [0,64) [32,96) [64,96)
+      const uint32_t wbase = ptx::smem_u32(s_w) >> 4;
+      const uint32_t b_main = kPair ? ((48u << 16) | wbase) : ((96u << 16) | wbase);
+      const uint32_t b_a64 = kPair ? ((32u << 16) | (wbase + (kPairOffA64 >> 4))) : b_main;
+      const uint32_t b_b64 = kPair ? ((32u << 16) | (wbase + (kPairOffB64 >> 4))) : b_main + 32u;
+      const uint32_t b_c32 = kPair ? ((16u << 16) | (wbase + (kPairOffC32 >> 4))) : b_main + 64u;
+      constexpr uint32_t kS96 = kPair ? 48u : 96u, kS64 = kPair ? 32u : 96u;
       ptx::mbar_wait(wbar, 0);
+      if constexpr (kPair) ptx::mbar_wait_cluster(pwbar, 0);
       uint32_t gp = 0, pbase = 0;   // pbase: global index of this item's plane 1 (a multiple of 24, hence of the ring period)
       // barrier waits of window (it8, r): the TMA box, and the slot of every output plane that receives its FIRST
       // contribution there (handed back by the plane 8 earlier; a first contribution that lands in a ghost slot is covered
@@ -577,13 +654,14 @@ __global__ void __launch_bounds__(k2Threads, 1) conv1_pw2_pool_v2_kernel(const _
         const int xi = 8 * it8 + r + 1;
         if (xi != kD) {
           const uint32_t gpl = pb + (uint32_t)xi, u = gpl >> 3;      // plane xi + 1
-          if (u > 0) ptx::mbar_wait(&acce[(r + 1) & 7], (u - 1) & 1);
+          if (u > 0) wait_x(&acce[(r + 1) & 7], (u - 1) & 1);
         }
         if (xi == 1) {
           const uint32_t u = pb >> 3;                                  // plane 1
-          if (u > 0) ptx::mbar_wait(&acce[0], (u - 1) & 1);
+          if (u > 0) wait_x(&acce[0], (u - 1) & 1);
         }
         ptx::mbar_wait(&full[gpw % k2Stages], (gpw / k2Stages) & 1);
+        if constexpr (kPair) ptx::mbar_wait_cluster(&pfull[gpw % k2Stages], (gpw / k2Stages) & 1);
       };
       // one window = one input plane; r = (xi - 1) & 7 is a compile-time constant of the unrolled body
       auto window = [&](auto rc, const int it8, const bool more) {
@@ -595,21 +673,27 @@ __global__ void __launch_bounds__(k2Threads, 1) conv1_pw2_pool_v2_kernel(const _
         ptx::tc_fence_after();
         const uint32_t a_lo_base = a_lo_fixed | (ptx::smem_u32(s_stage + (size_t)st * kStageBytes) >> 4);
         constexpr uint32_t s0 = (uint32_t)((r + 7) & 7);   // slot of output plane xi - 1; s0 = 6, 7 run on into the ghosts
-        uint32_t tm, bl, idn;
-        if (first_w) { tm = tmem_base; bl = b_lo_base + 32u; idn = ptx::idesc_f16(128, 64); }
-        else if (last_w) { tm = tmem_base + 6 * 32u; bl = b_lo_base; idn = ptx::idesc_f16(128, 64); }
-        else { tm = tmem_base + s0 * 32u; bl = b_lo_base; idn = ptx::idesc_f16(128, 96); }
+        uint32_t tm, bl, bs, idn;   // D columns, B descriptor, its row stride, instruction descriptor of the window's MMAs
+        if (first_w) { tm = tmem_base; bl = b_b64; bs = kS64; idn = ptx::idesc_f16(kM, 64); }
+        else if (last_w) { tm = tmem_base + 6 * 32u; bl = b_a64; bs = kS64; idn = ptx::idesc_f16(kM, 64); }
+        else { tm = tmem_base + s0 * 32u; bl = b_main; bs = kS96; idn = ptx::idesc_f16(kM, 96); }
+        auto mma = [&](auto acc, uint32_t d, uint32_t alo, uint32_t blo, uint32_t idesc) {
+          if constexpr (kPair) ptx::mma2_f16_ss_lohi<decltype(acc)::value>(d, alo, kDescHiA, blo, kDescHiB, idesc);
+          else ptx::mma_f16_ss_lohi<decltype(acc)::value>(d, alo, kDescHiA, blo, kDescHiB, idesc);
+        };
+        constexpr std::integral_constant<int, 0> kFresh{};
+        constexpr std::integral_constant<int, 1> kAcc{};
         // first MMA of the window (tap 0, k step 0): who is fresh
         if (first_w || (r == 1 && it8 > 0)) {
-          ptx::mma_f16_ss_lohi<0>(tm, a_lo_base, kDescHiA, bl, kDescHiB, idn);                       // every plane of the window is fresh
+          mma(kFresh, tm, a_lo_base, bl, idn);                                   // every plane of the window is fresh
         } else if (last_w) {
-          ptx::mma_f16_ss_lohi<1>(tm, a_lo_base, kDescHiA, bl, kDescHiB, idn);
+          mma(kAcc, tm, a_lo_base, bl, idn);
         } else {
-          ptx::mma_f16_ss_lohi<1>(tm, a_lo_base, kDescHiA, bl, kDescHiB, ptx::idesc_f16(128, 64));     // planes xi - 1, xi
-          ptx::mma_f16_ss_lohi<0>(tm + 64u, a_lo_base, kDescHiA, bl + 64u, kDescHiB, ptx::idesc_f16(128, 32));   // plane xi + 1: fresh
+          mma(kAcc, tm, a_lo_base, b_a64, ptx::idesc_f16(kM, 64));             // planes xi - 1, xi
+          mma(kFresh, tm + 64u, a_lo_base, b_c32, ptx::idesc_f16(kM, 32));     // plane xi + 1: fresh
         }
 #pragma unroll
-        for (int m = 1; m < 12; m++) ptx::mma_f16_ss_lohi<1>(tm, a_lo_base + off_a(m), kDescHiA, bl + off_b(m), kDescHiB, idn);
+        for (int m = 1; m < 12; m++) mma(kAcc, tm, a_lo_base + off_a(m), bl + (uint32_t)(((m >> 1) * 4 + 2 * (m & 1))) * bs, idn);
         tr(p.trace, 1, gp, 1);
         // the next window's waits, behind a dozen queued MMAs (the item loop passes the next item's plane base when r = 7 of
         // the last period wraps around)
@@ -621,15 +705,13 @@ __global__ void __launch_bounds__(k2Threads, 1) conv1_pw2_pool_v2_kernel(const _
         }
         tr(p.trace, 1, gp, 2);
 #pragma unroll
-        for (int m = 12; m < 18; m++) ptx::mma_f16_ss_lohi<1>(tm, a_lo_base + off_a(m), kDescHiA, bl + off_b(m), kDescHiB, idn);
-        ptx::tc_commit(&empty[st]);
-        if (!first_w) ptx::tc_commit(&accf[s0]);        // output plane xi - 1 is complete
-        if (last_w) ptx::tc_commit(&accf[7]);           // ... and so is plane 24
+        for (int m = 12; m < 18; m++) mma(kAcc, tm, a_lo_base + off_a(m), bl + (uint32_t)(((m >> 1) * 4 + 2 * (m & 1))) * bs, idn);
+        commit_x(&empty[st]);
+        if (!first_w) commit_x(&accf[s0]);        // output plane xi - 1 is complete
+        if (last_w) commit_x(&accf[7]);           // ... and so is plane 24
         tr(p.trace, 1, gp, 4);
         gp++;
       };
-      int n_my = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) n_my++;
       if (n_my > 0) wait_window(0, 0, 0, 0);
       for (int im = 0; im < n_my; im++, pbase += kD) {
         const bool last_item = im + 1 == n_my;
@@ -646,22 +728,27 @@ __global__ void __launch_bounds__(k2Threads, 1) conv1_pw2_pool_v2_kernel(const _
     // ===== pointwise MMA issuer (one thread): D2(j) = A2[j & 1] (128 x 32, staged by the epilogue) x W2^T into plane j's own
     // slot.  The two issuers never touch the same TMEM columns at the same time, so their relative order in the queue does
     // not matter. =====
-    if (ptx::elect_one()) {
+    if ((!kPair || rank == 0) && ptx::elect_one()) {
       constexpr uint32_t kDescHiB = (128u >> 4) | (1u << 14);
+      constexpr uint32_t kW2Lbo = kPair ? 16u : 32u;   // rows of W2 in this CTA = chunk pitch in 16-byte units
       ptx::mbar_wait(wbar, 0);
-      const uint32_t w2_lo = ((uint32_t)(512 >> 4) << 16) | (ptx::smem_u32(s_w2) >> 4);
-      int n_my = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) n_my++;
+      if constexpr (kPair) ptx::mbar_wait_cluster(pwbar, 0);
+      const uint32_t w2_lo = (kW2Lbo << 16) | (ptx::smem_u32(s_w2) >> 4);
       const uint32_t n_planes = (uint32_t)n_my * kD;
       for (uint32_t j = 0; j < n_planes; j++) {
         const uint32_t b = j % k2Bufs;
-        ptx::mbar_wait(&a2_full[b], (j / k2Bufs) & 1);
+        wait_x(&a2_full[b], (j / k2Bufs) & 1);
         ptx::tc_fence_after();
         const uint32_t a2_lo = ((uint32_t)(2048 >> 4) << 16) | (ptx::smem_u32(s_y + b * 8192) >> 4);
         const uint32_t tm_d2 = tmem_base + (j & 7) * 32u;
-        ptx::mma_f16_ss_lohi<0>(tm_d2, a2_lo, kDescHiB, w2_lo, kDescHiB, ptx::idesc_f16(128, 32));
-        ptx::mma_f16_ss_lohi<1>(tm_d2, a2_lo + 2 * (2048 >> 4), kDescHiB, w2_lo + 2 * (512 >> 4), kDescHiB, ptx::idesc_f16(128, 32));
-        ptx::tc_commit(&d2_full[b]);
+        if constexpr (kPair) {
+          ptx::mma2_f16_ss_lohi<0>(tm_d2, a2_lo, kDescHiB, w2_lo, kDescHiB, ptx::idesc_f16(kM, 32));
+          ptx::mma2_f16_ss_lohi<1>(tm_d2, a2_lo + 2 * (2048 >> 4), kDescHiB, w2_lo + 2 * kW2Lbo, kDescHiB, ptx::idesc_f16(kM, 32));
+        } else {
+          ptx::mma_f16_ss_lohi<0>(tm_d2, a2_lo, kDescHiB, w2_lo, kDescHiB, ptx::idesc_f16(kM, 32));
+          ptx::mma_f16_ss_lohi<1>(tm_d2, a2_lo + 2 * (2048 >> 4), kDescHiB, w2_lo + 2 * kW2Lbo, kDescHiB, ptx::idesc_f16(kM, 32));
+        }
+        commit_x(&d2_full[b]);
       }
     }
   } else {
@@ -672,8 +759,6 @@ __global__ void __launch_bounds__(k2Threads, 1) conv1_pw2_pool_v2_kernel(const _
     const int yrow = row >> 3, zz = row & 7;
     const uint32_t tm_mine = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(cg * k2Cw);
     constexpr int Dn = 12, Pn = 14;
-    int n_my = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) n_my++;
     const uint32_t n_planes = (uint32_t)n_my * kD;
     float keep[k2Cw];
     uint4* xo4 = reinterpret_cast<uint4*>(p.xout);
@@ -719,9 +804,10 @@ __global__ void __launch_bounds__(k2Threads, 1) conv1_pw2_pool_v2_kernel(const _
           }
           *reinterpret_cast<uint4*>(s_y + b * 8192 + (cg * (k2Cw / 8) + c8) * 2048 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        ptx::fence_proxy_async();   // every lane: its stores -> visible to the tensor core; then one arrival for the warp
+        if constexpr (kPair) ptx::fence_proxy_async_all();   // every lane: its stores -> visible to the tensor core(s)
+        else ptx::fence_proxy_async();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&a2_full[b]);
+        if (lane == 0) arrive_x(&a2_full[b]);                 // one arrival for the warp
         if (tracer) tr(p.trace, 2, j, 2);
       }
       if (prev != 0xffffffffu) {
@@ -735,19 +821,20 @@ __global__ void __launch_bounds__(k2Threads, 1) conv1_pw2_pool_v2_kernel(const _
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&acce[slot]);
+        if (lane == 0) arrive_x(&acce[slot]);
         const uint32_t pj = jj % kD;
         const int xo = (int)pj + 1;
         if (xo & 1) {
           if ((int)(jj / kD) != dst_item) {   // first plane of an item this team sees: where this lane's pooled voxels of the item go
             dst_item = (int)(jj / kD);
-            const int item = blockIdx.x + dst_item * gridDim.x;
+            bool valid;
+            const int item = item_of(dst_item, valid);
             const int zb = item % kZBlocks, k = (item / kZBlocks) % kRowTiles, grp = item / (kZBlocks * kRowTiles);
             const int R = 16 * k + 1 + yrow;
             const int q = R / kP, yp = R - q * kP;
             const int pose = grp * kG + q;
             dst_base = nullptr;
-            if (((lane & 9) == 0) && q < kG && pose < p.n_poses && yp >= 1 && yp <= kD) {
+            if (valid && ((lane & 9) == 0) && q < kG && pose < p.n_poses && yp >= 1 && yp <= kD) {
               const int yo = (yp - 1) >> 1, zo = 4 * zb + (zz >> 1);
               dst_base = xo4 + ((size_t)(pose / p.out_G) * Dn * 4 + cg * (k2Cw / 8)) * p.out_lp + (size_t)(pose % p.out_G) * Pn * Pn +
                          (size_t)(yo + 1) * Pn + (zo + 1);
@@ -780,10 +867,12 @@ __global__ void __launch_bounds__(k2Threads, 1) conv1_pw2_pool_v2_kernel(const _
     }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) ptx::cluster_sync_all();   // the leader's MMAs read the peer's shared memory and write its TMEM until the end
+  else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    if constexpr (kPair) ptx::tmem_dealloc2(tmem_base, 512);
+    else ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -819,6 +908,39 @@ uint4* pack_pointwise_tc(std::vector<void*>& allocs, const float* w, int c) {
   return reinterpret_cast<uint4*>(d);
 }
 
+// pair mode (conv1_pw2_pool_v2_kernel<true>): the B rows each CTA of a pair holds, see the kernel's comment
+struct PairPack { uint8_t* w = nullptr; uint8_t* w2 = nullptr; };
+static PairPack pair_pack(const uint4* wp, const uint4* w2p) {
+  static std::mutex mu;
+  static std::map<const void*, PairPack> cache;   // keyed by the weight set (device pointer); lives as long as the process
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(wp);
+  if (it != cache.end()) return it->second;
+  std::vector<uint4> src(9 * 4 * 96), src2(4 * 32);
+  GB_CUDA(cudaMemcpy(src.data(), wp, src.size() * 16, cudaMemcpyDeviceToHost));
+  GB_CUDA(cudaMemcpy(src2.data(), w2p, src2.size() * 16, cudaMemcpyDeviceToHost));
+  std::vector<uint4> dst(2 * kPairWBytes / 16, make_uint4(0, 0, 0, 0)), dst2(2 * kPairW2Bytes / 16);
+  for (int r = 0; r < 2; r++) {
+    uint4* d = dst.data() + (size_t)r * kPairWBytes / 16;
+    for (int tc = 0; tc < 36; tc++) {   // (tap, chunk)
+      for (int j = 0; j < 48; j++) d[tc * 48 + j] = src[tc * 96 + 48 * r + j];
+      for (int j = 0; j < 32; j++) d[kPairOffA64 / 16 + tc * 32 + j] = src[tc * 96 + 32 * r + j];
+      for (int j = 0; j < 32; j++) d[kPairOffB64 / 16 + tc * 32 + j] = src[tc * 96 + 32 + 32 * r + j];
+    }
+    for (int c8 = 0; c8 < 2; c8++)
+      for (int j = 0; j < 16; j++) d[kPairOffC32 / 16 + c8 * 16 + j] = src[c8 * 96 + 64 + 16 * r + j];
+    for (int c8 = 0; c8 < 4; c8++)
+      for (int j = 0; j < 16; j++) dst2[(size_t)r * kPairW2Bytes / 16 + c8 * 16 + j] = src2[c8 * 32 + 16 * r + j];
+  }
+  PairPack pk;
+  GB_CUDA(cudaMalloc(&pk.w, dst.size() * 16));
+  GB_CUDA(cudaMalloc(&pk.w2, dst2.size() * 16));
+  GB_CUDA(cudaMemcpy(pk.w, dst.data(), dst.size() * 16, cudaMemcpyHostToDevice));
+  GB_CUDA(cudaMemcpy(pk.w2, dst2.data(), dst2.size() * 16, cudaMemcpyHostToDevice));
+  cache[wp] = pk;
+  return pk;
+}
+
 void launch_conv1_pw2_pool(const ConvTc& conv1, const __half* w2, const uint4* w2p, const float* bias2, const uint4* x0, const ActLayout& L0,
                            uint4* x2, const ActLayout& L2, int n_poses, cudaStream_t s) {
   GB_CHECK(conv1.cin == 32 && conv1.cout == 32 && L0.D == kD && L0.G == kG && L2.D == 12, "fused conv1 shape");
@@ -836,7 +958,8 @@ void launch_conv1_pw2_pool(const ConvTc& conv1, const __half* w2, const uint4* w
     if (!attr_set[dev]) {
       GB_CUDA(cudaFuncSetAttribute(conv1_pw2_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
       GB_CUDA(cudaFuncSetAttribute(conv1_pw2_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-      GB_CUDA(cudaFuncSetAttribute(conv1_pw2_pool_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemTotal));
+      GB_CUDA(cudaFuncSetAttribute(conv1_pw2_pool_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemTotal));
+      GB_CUDA(cudaFuncSetAttribute(conv1_pw2_pool_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemTotal));
       GB_CUDA(cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev));
       attr_set[dev] = true;
     }
@@ -872,7 +995,24 @@ void launch_conv1_pw2_pool(const ConvTc& conv1, const __half* w2, const uint4* w
                                                                                                   // 0: mma.sync in the epilogue (r2g: 9.9 vs 7.6 ms)
   int grid = persist > 0 ? std::min(n_items, n_sm[dev] * persist) : n_items;
   static const int v2 = getenv("GB_TC_FUSED_V2") ? atoi(getenv("GB_TC_FUSED_V2")) : 1;   // 0: the two-CTAs-per-SM kernel above (r2x: 6.9 ms per 10 k poses; v2: 5.5)
-  if (v2) conv1_pw2_pool_v2_kernel<<<std::min(n_items, n_sm[dev]), k2Threads, k2SmemTotal, s>>>(tmap, p);
+  if (v2 == 2) {
+    // CTA pairs: per-rank B rows packed once per weight set
+    const PairPack pk = pair_pack(conv1.wp, w2p);
+    p.wp = reinterpret_cast<const uint4*>(pk.w);
+    p.w2p = reinterpret_cast<const uint4*>(pk.w2);
+    const int n_units = (n_items + 1) / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * std::min(n_units, n_sm[dev] / 2));
+    cfg.blockDim = dim3(k2Threads);
+    cfg.dynamicSmemBytes = k2SmemTotal;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    GB_CUDA(cudaLaunchKernelEx(&cfg, conv1_pw2_pool_v2_kernel<true>, tmap, p));
+  } else if (v2) conv1_pw2_pool_v2_kernel<false><<<std::min(n_items, n_sm[dev]), k2Threads, k2SmemTotal, s>>>(tmap, p);
   else if (tc_pw) conv1_pw2_pool_kernel<true><<<grid, 192, kSmemTotal, s>>>(tmap, p);
   else conv1_pw2_pool_kernel<false><<<grid, 192, kSmemTotal, s>>>(tmap, p);
   if (p.trace) {
