@@ -145,6 +145,7 @@ std::shared_ptr<TcWeights> get_tc_weights(const Model& m) {
   tw->conv1 = prep_conv(*tw, m, "unit1_conv");
   tw->pw2 = prep_pw(*tw, m, "unit2_conv");
   tw->pw2_packed = pack_pointwise_tc(tw->allocs, m.t("unit2_conv.weight").data, 32);
+  pack_pair_weights(tw->allocs, tw->conv1.wp, tw->pw2_packed, &tw->pair_w, &tw->pair_w2);
   tw->conv3 = prep_conv(*tw, m, "unit3_conv");
   tw->pw4 = prep_pw(*tw, m, "unit4_conv");
   tw->conv5 = prep_conv(*tw, m, "unit5_conv");
@@ -928,7 +929,7 @@ int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspa
   if (fused) {
     // unit1_conv + ReLU + unit2_conv + ReLU + avg-pool in one kernel (x0 is in the row-group layout): straight to X2
     ProfScope ps(prof, "tc_conv1_pw2_pool_fused", s);
-    launch_conv1_pw2_pool(tw->conv1, tw->pw2.w, tw->pw2_packed, tw->pw2.bias, x0, make_fused_x0_layout(), X2, L3, nb, s);
+    launch_conv1_pw2_pool(tw->conv1, tw->pw2.w, tw->pw2_packed, tw->pw2.bias, tw->pair_w, tw->pair_w2, x0, make_fused_x0_layout(), X2, L3, nb, s);
   } else {
     ProfScope ps(prof, "tc_conv1_3x3x3_28x32_d24", s);
     launch_conv_tc<32, 24>(tw->conv1, L1, x0, Y, nb, s);

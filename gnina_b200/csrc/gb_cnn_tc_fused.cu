@@ -623,13 +623,11 @@ __global__ void __launch_bounds__(k2Threads, 1) conv1_pw2_pool_v2_kernel(const _
       // peer CTA: this warp only relays "my weights / my TMA box have landed" to the leader, which issues the MMAs that read them
       if (ptx::elect_one()) {
         ptx::mbar_wait(wbar, 0);
-        ptx::fence_proxy_async_all();
         ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(pwbar), 0));
         const uint32_t n_planes = (uint32_t)n_my * kD;
         for (uint32_t gp = 0; gp < n_planes; gp++) {
           const uint32_t st = gp % k2Stages;
           ptx::mbar_wait(&full[st], (gp / k2Stages) & 1);
-          ptx::fence_proxy_async_all();
           ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&pfull[st]), 0));
         }
       }
@@ -804,8 +802,8 @@ __global__ void __launch_bounds__(k2Threads, 1) conv1_pw2_pool_v2_kernel(const _
           }
           *reinterpret_cast<uint4*>(s_y + b * 8192 + (cg * (k2Cw / 8) + c8) * 2048 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        if constexpr (kPair) ptx::fence_proxy_async_all();   // every lane: its stores -> visible to the tensor core(s)
-        else ptx::fence_proxy_async();
+        ptx::fence_proxy_async();   // every lane: its shared-memory stores -> visible to the tensor core (r3b: the fence over all
+                                    // state spaces waits for this warp's global stores too: 1400 instead of 350 cycles)
         __syncwarp();
         if (lane == 0) arrive_x(&a2_full[b]);                 // one arrival for the warp
         if (tracer) tr(p.trace, 2, j, 2);
@@ -908,14 +906,9 @@ uint4* pack_pointwise_tc(std::vector<void*>& allocs, const float* w, int c) {
   return reinterpret_cast<uint4*>(d);
 }
 
-// pair mode (conv1_pw2_pool_v2_kernel<true>): the B rows each CTA of a pair holds, see the kernel's comment
-struct PairPack { uint8_t* w = nullptr; uint8_t* w2 = nullptr; };
-static PairPack pair_pack(const uint4* wp, const uint4* w2p) {
-  static std::mutex mu;
-  static std::map<const void*, PairPack> cache;   // keyed by the weight set (device pointer); lives as long as the process
-  std::lock_guard<std::mutex> lk(mu);
-  auto it = cache.find(wp);
-  if (it != cache.end()) return it->second;
+// pair mode (conv1_pw2_pool_v2_kernel<true>): the B rows each CTA of a pair holds, see the kernel's comment.  Built with the
+// weight set and freed with it (allocs).
+void pack_pair_weights(std::vector<void*>& allocs, const uint4* wp, const uint4* w2p, uint4** pair_w, uint4** pair_w2) {
   std::vector<uint4> src(9 * 4 * 96), src2(4 * 32);
   GB_CUDA(cudaMemcpy(src.data(), wp, src.size() * 16, cudaMemcpyDeviceToHost));
   GB_CUDA(cudaMemcpy(src2.data(), w2p, src2.size() * 16, cudaMemcpyDeviceToHost));
@@ -932,17 +925,19 @@ static PairPack pair_pack(const uint4* wp, const uint4* w2p) {
     for (int c8 = 0; c8 < 4; c8++)
       for (int j = 0; j < 16; j++) dst2[(size_t)r * kPairW2Bytes / 16 + c8 * 16 + j] = src2[c8 * 32 + 16 * r + j];
   }
-  PairPack pk;
-  GB_CUDA(cudaMalloc(&pk.w, dst.size() * 16));
-  GB_CUDA(cudaMalloc(&pk.w2, dst2.size() * 16));
-  GB_CUDA(cudaMemcpy(pk.w, dst.data(), dst.size() * 16, cudaMemcpyHostToDevice));
-  GB_CUDA(cudaMemcpy(pk.w2, dst2.data(), dst2.size() * 16, cudaMemcpyHostToDevice));
-  cache[wp] = pk;
-  return pk;
+  void *dw = nullptr, *dw2 = nullptr;
+  GB_CUDA(cudaMalloc(&dw, dst.size() * 16));
+  allocs.push_back(dw);
+  GB_CUDA(cudaMalloc(&dw2, dst2.size() * 16));
+  allocs.push_back(dw2);
+  GB_CUDA(cudaMemcpy(dw, dst.data(), dst.size() * 16, cudaMemcpyHostToDevice));
+  GB_CUDA(cudaMemcpy(dw2, dst2.data(), dst2.size() * 16, cudaMemcpyHostToDevice));
+  *pair_w = reinterpret_cast<uint4*>(dw);
+  *pair_w2 = reinterpret_cast<uint4*>(dw2);
 }
 
-void launch_conv1_pw2_pool(const ConvTc& conv1, const __half* w2, const uint4* w2p, const float* bias2, const uint4* x0, const ActLayout& L0,
-                           uint4* x2, const ActLayout& L2, int n_poses, cudaStream_t s) {
+void launch_conv1_pw2_pool(const ConvTc& conv1, const __half* w2, const uint4* w2p, const float* bias2, const uint4* pair_w, const uint4* pair_w2,
+                           const uint4* x0, const ActLayout& L0, uint4* x2, const ActLayout& L2, int n_poses, cudaStream_t s) {
   GB_CHECK(conv1.cin == 32 && conv1.cout == 32 && L0.D == kD && L0.G == kG && L2.D == 12, "fused conv1 shape");
   EncodeTiledFn enc = encode_tiled_fn();
   GB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available in this driver");
@@ -994,12 +989,16 @@ void launch_conv1_pw2_pool(const ConvTc& conv1, const __half* w2, const uint4* w
   static const int tc_pw = getenv("GB_TC_FUSED_PW") ? atoi(getenv("GB_TC_FUSED_PW")) : 1;   // 1 (default): pointwise conv as a second tcgen05.mma;
                                                                                                   // 0: mma.sync in the epilogue (r2g: 9.9 vs 7.6 ms)
   int grid = persist > 0 ? std::min(n_items, n_sm[dev] * persist) : n_items;
-  static const int v2 = getenv("GB_TC_FUSED_V2") ? atoi(getenv("GB_TC_FUSED_V2")) : 1;   // 0: the two-CTAs-per-SM kernel above (r2x: 6.9 ms per 10 k poses; v2: 5.5)
+  // read per launch (tests switch variants inside one process): 1 (default) v2, one CTA per SM; 0 the two-CTAs-per-SM kernel above
+  // (r2x: 6.9 ms per 10 k poses against 5.5); 2 v2 on CTA pairs (cta_group::2; r3c: 8.7 ms -- an M = 256, N = 96 MMA takes ~100
+  // cycles instead of 56 for M = 128: the half of B that lives in the other SM's shared memory costs more than it saves)
+  const char* v2env = getenv("GB_TC_FUSED_V2");
+  const int v2 = v2env ? atoi(v2env) : 1;
   if (v2 == 2) {
     // CTA pairs: per-rank B rows packed once per weight set
-    const PairPack pk = pair_pack(conv1.wp, w2p);
-    p.wp = reinterpret_cast<const uint4*>(pk.w);
-    p.w2p = reinterpret_cast<const uint4*>(pk.w2);
+    GB_CHECK(pair_w && pair_w2, "pair weights");
+    p.wp = pair_w;
+    p.w2p = pair_w2;
     const int n_units = (n_items + 1) / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * std::min(n_units, n_sm[dev] / 2));

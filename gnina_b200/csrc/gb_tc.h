@@ -92,6 +92,8 @@ struct TcWeights {
   ConvTc conv1, conv3, conv5;
   PointwiseTc pw2, pw4;   // (unused by default2017: no 1x1x1 convolutions)
   uint4* pw2_packed = nullptr;  // unit2_conv as the K-major B operand of the fused kernel's second tcgen05.mma
+  uint4* pair_w = nullptr;      // CTA-pair variant of the fused kernel: per-rank B rows of unit1_conv / unit2_conv (pack_pair_weights)
+  uint4* pair_w2 = nullptr;
   float* fcw = nullptr;      // [3][216*128] channels-last order
   float* fcb = nullptr;
   std::vector<void*> allocs;
@@ -109,8 +111,9 @@ void tc_debug_set(int i, const void* p, size_t bytes);
 // fused scoring kernel (gb_cnn_tc_fused.cu): x0 in the row-group layout -> X2 (input of unit3_conv)
 ActLayout make_fused_x0_layout();
 uint4* pack_pointwise_tc(std::vector<void*>& allocs, const float* w, int c);
-void launch_conv1_pw2_pool(const ConvTc& conv1, const __half* w2, const uint4* w2p, const float* bias2, const uint4* x0, const ActLayout& L0, uint4* x2,
-                           const ActLayout& L2, int n_poses, cudaStream_t s);
+void pack_pair_weights(std::vector<void*>& allocs, const uint4* wp, const uint4* w2p, uint4** pair_w, uint4** pair_w2);
+void launch_conv1_pw2_pool(const ConvTc& conv1, const __half* w2, const uint4* w2p, const float* bias2, const uint4* pair_w, const uint4* pair_w2,
+                           const uint4* x0, const ActLayout& L0, uint4* x2, const ActLayout& L2, int n_poses, cudaStream_t s);
 
 // test-only access to the buffers of the most recent tc_forward on this thread: 0 x0, 1 y(3), 2 x2, 3 x4, 4 y5
 const void* tc_debug_buffer(int i, size_t* bytes);

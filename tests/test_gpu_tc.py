@@ -197,6 +197,30 @@ def test_fused_conv1_kernel_equals_unfused_path(kat, n):
     assert np.abs(fused[0] - ref[0]).max() < TOL_SCORE and np.abs(fused[1] - ref[1]).max() < TOL_AFF
 
 
+def test_fused_kernel_variants_agree(kat, monkeypatch):
+    """The three builds of the fused unit1_conv + unit2_conv + pool kernel -- two CTAs per SM (0), one CTA per SM with ghost TMEM
+    slots (1, default), and the same on CTA pairs with tcgen05 cta_group::2 (2) -- are the same arithmetic: the single-CTA and
+    pair variants agree bit for bit, the older kernel to fp16 round-off (it accumulates the wrapped planes in one place)."""
+    from gnina_b200 import synth
+    rx, rt = synth.make_receptor(1500, box=44)
+    lx0, lt0 = synth.make_ligand(22, 3, seed=4)
+    n = 77                                     # ragged: 10 groups of 8 (390 items, even) ... and an odd item count below
+    lx, offs = synth.make_poses(lx0, n, trans_box=10, seed=3)
+    lt = np.tile(lt0, n)
+    s = _fast(["crossdock_default2018"])
+    s.set_receptor(rx, rt)
+    out = {}
+    for v in ("1", "2", "0"):
+        monkeypatch.setenv("GB_TC_FUSED_V2", v)
+        out[v] = s.score_batch(lx, lt, offs)
+        k = 5                                  # 1 group: 39 items, the pair variant's odd tail
+        out[v + "s"] = s.score_batch(lx[:offs[k]], lt[:offs[k]], offs[:k + 1])
+    monkeypatch.delenv("GB_TC_FUSED_V2")
+    for suf in ("", "s"):
+        assert np.array_equal(out["1" + suf][0], out["2" + suf][0]) and np.array_equal(out["1" + suf][1], out["2" + suf][1])
+        assert np.abs(out["1" + suf][0] - out["0" + suf][0]).max() < 5e-5 and np.abs(out["1" + suf][1] - out["0" + suf][1]).max() < 5e-4
+
+
 def test_dense_ensemble_matches_reference_pt(golden_dir):
     """BASELINE config 4: `--cnn dense_ensemble` = 20 models (15 dense + 5 default2018 architecture), ensemble
     statistics of CNNTorchScorer::score against the reference's own .pt files (tests/golden/ensemble_kat.npz)."""
