@@ -200,7 +200,11 @@ struct ConvTcParams {
   int dbg;  // experiment switches (GB_TC_DBG): 1 = no global stores, 2 = no slab loads, 4 = no MMAs
 };
 
-constexpr int kTcSlots = 8;       // TMEM ring: 8 plane slots x 32 fp32 columns = 256 columns
+// TMEM ring of plane slots x 32 fp32 columns (256 columns allocated): 8 slots, except D = 6 (conv5): there a 6-slot ring wraps
+// exactly on item boundaries, where the window is truncated anyway, so no N = 96 MMA ever has to be split at a wrap (two MMAs
+// that both read the 4 KB A tile; 2 of every 8 planes otherwise): 1.31 -> 1.25 ms per 10 k poses.  For D = 12 the same idea
+// (2 of 12 planes split instead of 3) loses more to the shallower ring than it gains: 2.0 -> 2.4 ms (r3f).
+template <int DD> struct TcRing { static constexpr int kSlots = (DD == 6) ? 6 : 8; };
 constexpr int kSlabMax = 128 + 2 * 27;
 
 template <int CIN>
@@ -227,7 +231,7 @@ template <int CIN, int DD>
 __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
   using S = ConvTcSmem<CIN>;
   constexpr int C8 = S::C8;
-  constexpr int R = kTcSlots;
+  constexpr int R = TcRing<DD>::kSlots;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_w = smem;
   uint8_t* s_stage = smem + S::kWBytes;
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
   }
   if (threadIdx.x < 32) s_bias[threadIdx.x] = p.bias[nb * 32 + threadIdx.x];
   if (warp == 1) {
-    ptx::tmem_alloc(s_tmem, R * 32);
+    ptx::tmem_alloc(s_tmem, 256);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -440,7 +444,7 @@ __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, R * 32);
+    ptx::tmem_dealloc(tmem_base, 256);
   }
 }
 
