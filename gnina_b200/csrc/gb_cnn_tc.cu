@@ -449,6 +449,232 @@ __global__ void __launch_bounds__(192) conv3_tc_kernel(const ConvTcParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Kernel B, "v2" organisation (what r2y found for the fused conv1 kernel, applied to conv3 / conv5 of the scoring path):
+// ONE CTA per SM with all 512 TMEM columns.  The ring has as many slots as an item has planes (12 or 6), so slot = plane
+// and no window ever wraps: no N = 96 MMA is split in two.  The issuer is ONE thread inside one elected region, its
+// per-window MMAs unrolled with compile-time operand offsets, and it takes the NEXT window's barrier waits after two
+// thirds of the current window's MMAs (with a single CTA nobody else fills the tensor-core queue while it waits).
+// Channels-last output with bias + ReLU only (the gradient / dense paths keep conv3_tc_kernel).
+template <int CIN, int DD>
+struct ConvTcV2Smem {
+  static constexpr int C8 = CIN / 8;
+  static constexpr int kWBytes = 9 * C8 * 96 * 16;
+  static constexpr int kSL = 128 + 2 * (DD + 3);
+  static constexpr int kStageBytes = ((C8 * kSL * 16) + 127) / 128 * 128;
+  static constexpr int kStages = (CIN == 32) ? 6 : 4;
+  static constexpr int kBarOff = kWBytes + kStages * kStageBytes;
+  static constexpr int kTotal = kBarOff + 512;
+};
+
+template <int CIN, int DD>
+__global__ void __launch_bounds__(192, 1) conv3_tc_v2_kernel(const ConvTcParams p) {
+  using S = ConvTcV2Smem<CIN, DD>;
+  constexpr int C8 = S::C8, R = DD, D = DD, P = DD + 2, SL = S::kSL;
+  constexpr int kNumMma = 9 * (CIN / 16);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_w = smem;
+  uint8_t* s_stage = smem + S::kWBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
+  uint64_t* full = bars;                          // [kStages]
+  uint64_t* empty = full + S::kStages;            // [kStages]
+  uint64_t* accf = empty + S::kStages;            // [R]
+  uint64_t* acce = accf + R;                      // [R] one arrival per epilogue warp
+  uint64_t* wbar = acce + R;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(wbar + 1);
+  float* s_bias = reinterpret_cast<float*>(s_tmem + 2);   // 32 floats
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = blockIdx.x % p.NB;
+  const int n_items = p.n_groups * p.T * p.NB;
+  constexpr uint32_t slab_row = (uint32_t)SL * 16u;
+  int n_my = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) n_my++;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S::kStages; s++) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < R; s++) { ptx::mbar_init(&accf[s], 1); ptx::mbar_init(&acce[s], 4); }
+    ptx::mbar_init(wbar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (threadIdx.x < 32) s_bias[threadIdx.x] = p.bias[nb * 32 + threadIdx.x];
+  if (warp == 1) {
+    ptx::tmem_alloc(s_tmem, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===== producer =====
+    if (ptx::elect_one()) {
+      ptx::mbar_expect_tx(wbar, S::kWBytes);
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wp) + (size_t)nb * S::kWBytes;
+      for (int t9 = 0; t9 < 9; t9++) ptx::bulk_g2s(s_w + t9 * (S::kWBytes / 9), wsrc + t9 * (S::kWBytes / 9), S::kWBytes / 9, wbar);
+    }
+    __syncwarp();
+    uint32_t gp = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int j = (item / p.NB) % p.T, g = item / (p.NB * p.T);
+      const uint4* xg = p.xin + (size_t)g * D * C8 * p.Lp + (size_t)128 * j;
+      for (int it = 0; it < D; it++, gp++) {
+        const uint32_t st = gp % S::kStages, ph = (gp / S::kStages) & 1;
+        ptx::mbar_wait(&empty[st], ph ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(&full[st], (uint32_t)C8 * slab_row);
+          uint8_t* dst = s_stage + (size_t)st * S::kStageBytes;
+#pragma unroll
+          for (int c8 = 0; c8 < C8; c8++) ptx::bulk_g2s(dst + (size_t)c8 * slab_row, xg + ((size_t)it * C8 + c8) * p.Lp, slab_row, &full[st]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread =====
+    if (ptx::elect_one()) {
+      constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+      const uint32_t a_lo_fixed = ((uint32_t)SL & 0x3FFFu) << 16;
+      const uint32_t b_lo_base = (96u << 16) | (ptx::smem_u32(s_w) >> 4);
+      ptx::mbar_wait(wbar, 0);
+      // waits of window (item sequence number iq, input plane xi): the slab, and the slot of every output plane that gets
+      // its first contribution there -- slot = plane, previous occupant = the same plane of the previous item
+      auto wait_window = [&](const int xi, const uint32_t iq, const uint32_t gpw) {
+        if (iq > 0) {
+          if (xi < D) ptx::mbar_wait(&acce[xi], (iq - 1) & 1);       // plane xi + 1
+          if (xi == 1) ptx::mbar_wait(&acce[0], (iq - 1) & 1);       // plane 1
+        }
+        ptx::mbar_wait(&full[gpw % S::kStages], (gpw / S::kStages) & 1);
+      };
+      uint32_t gp = 0;
+      if (n_my > 0) wait_window(1, 0, 0);
+      for (uint32_t iq = 0; iq < (uint32_t)n_my; iq++) {
+#pragma unroll 1
+        for (int xi = 1; xi <= D; xi++, gp++) {
+          const uint32_t st = gp % S::kStages;
+          ptx::tc_fence_after();
+          const uint32_t a_lo_base = a_lo_fixed | (ptx::smem_u32(s_stage + (size_t)st * S::kStageBytes) >> 4);
+          uint32_t tm, bl, idn;
+          if (xi == 1) { tm = tmem_base; bl = b_lo_base + 32u; idn = ptx::idesc_f16(128, 64); }
+          else if (xi == D) { tm = tmem_base + (uint32_t)(D - 2) * 32u; bl = b_lo_base; idn = ptx::idesc_f16(128, 64); }
+          else { tm = tmem_base + (uint32_t)(xi - 2) * 32u; bl = b_lo_base; idn = ptx::idesc_f16(128, 96); }
+          // per MMA m = tap * (CIN / 16) + k step: A start = flat offset of the tap + k step * 2 slab rows, B = weight block
+          constexpr uint32_t a0 = 0;   // tap (dy, dz) = (-1, -1), k step 0: (P + 1) - P - 1
+          if (xi == 1) ptx::mma_f16_ss_lohi<0>(tm, a_lo_base + a0, kDescHi, bl, kDescHi, idn);                 // planes 1, 2: fresh
+          else if (xi == D) ptx::mma_f16_ss_lohi<1>(tm, a_lo_base + a0, kDescHi, bl, kDescHi, idn);
+          else {
+            ptx::mma_f16_ss_lohi<1>(tm, a_lo_base + a0, kDescHi, bl, kDescHi, ptx::idesc_f16(128, 64));         // planes xi - 1, xi
+            ptx::mma_f16_ss_lohi<0>(tm + 64u, a_lo_base + a0, kDescHi, bl + 64u, kDescHi, ptx::idesc_f16(128, 32));   // plane xi + 1: fresh
+          }
+          constexpr int kSplit = (2 * kNumMma) / 3;
+#pragma unroll
+          for (int m = 1; m < kNumMma; m++) {
+            if (m == kSplit) {
+              // the next window's waits, behind a third of this window's MMAs still queued
+              const bool last = xi == D && iq + 1 == (uint32_t)n_my;
+              if (!last) {
+                if (xi == D) wait_window(1, iq + 1, gp + 1);
+                else wait_window(xi + 1, iq, gp + 1);
+                ptx::tc_fence_after();
+              }
+            }
+            constexpr int kKs = CIN / 16;
+            const int t9 = m / kKs, ks = m % kKs;
+            const uint32_t oa = (uint32_t)((P + 1) + (t9 / 3 - 1) * P + (t9 % 3 - 1) + 2 * ks * SL);
+            const uint32_t ob = (uint32_t)((t9 * C8 + 2 * ks) * 96);
+            ptx::mma_f16_ss_lohi<1>(tm, a_lo_base + oa, kDescHi, bl + ob, kDescHi, idn);
+          }
+          ptx::tc_commit(&empty[st]);
+          if (xi >= 2) ptx::tc_commit(&accf[xi - 2]);     // output plane xi - 1 is complete
+          if (xi == D) ptx::tc_commit(&accf[D - 1]);
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> bias / ReLU -> fp16 -> global (channels-last) =====
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    uint32_t iq = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, iq++) {
+      const int j = (item / p.NB) % p.T, g = item / (p.NB * p.T);
+      const int m = (P + 1) + 128 * j + row;
+      const int qpose = m / (P * P), rem = m % (P * P);
+      const int y = rem / P, z = rem % P;
+      const int pose = g * p.G + qpose;
+      const bool valid = qpose < p.G && pose < p.n_poses && y >= 1 && y <= D && z >= 1 && z <= D;
+      __half* obase = p.out + (((size_t)pose * D * D + (size_t)(y - 1)) * D + (z - 1)) * p.Cout + nb * 32;
+      const size_t plane_stride = (size_t)D * D * p.Cout;
+      for (int xo = 1; xo <= D; xo++) {
+        const uint32_t slot = (uint32_t)(xo - 1);
+        ptx::mbar_wait(&accf[slot], iq & 1);
+        ptx::tc_fence_after();
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + slot * 32u, v);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&acce[slot]);
+        if (valid) {
+          uint4 o[4];
+          uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+          for (int c = 0; c < 16; c++) {
+            const float f0 = fmaxf(__uint_as_float(v[2 * c]) + s_bias[2 * c], 0.f);
+            const float f1 = fmaxf(__uint_as_float(v[2 * c + 1]) + s_bias[2 * c + 1], 0.f);
+            const __half2 h = __floats2half2_rn(f0, f1);
+            ow[c] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(obase + (size_t)(xo - 1) * plane_stride);
+          dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2]; dst[3] = o[3];
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// GB_TC_CONV_V2 (read per call): bit 0 conv3, bit 1 conv5 through conv3_tc_v2_kernel (default both: 2.00 -> 1.81 and
+// 1.25 -> 1.07 ms per 10 k poses, bit-identical results; 0 = conv3_tc_kernel for both)
+static int tc_conv_v2() {
+  const char* e = getenv("GB_TC_CONV_V2");
+  return e ? atoi(e) : 3;
+}
+
+template <int CIN, int DD>
+static void launch_conv_tc_v2(const ConvTc& c, const ActLayout& L, const uint4* xin, __half* out, int n_poses, cudaStream_t s) {
+  using S = ConvTcV2Smem<CIN, DD>;
+  GB_CHECK(c.cin == CIN && L.D == DD, "conv shape");
+  static bool attr_set[64] = {};
+  static int n_sm_dev[64] = {};
+  int dev = 0;
+  GB_CUDA(cudaGetDevice(&dev));
+  GB_CHECK(dev >= 0 && dev < 64, "device index");
+  {
+    std::lock_guard<std::mutex> init_lock(tc_init_mutex());
+    if (!attr_set[dev]) {
+      GB_CUDA(cudaFuncSetAttribute(conv3_tc_v2_kernel<CIN, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+      GB_CUDA(cudaDeviceGetAttribute(&n_sm_dev[dev], cudaDevAttrMultiProcessorCount, dev));
+      attr_set[dev] = true;
+    }
+  }
+  ConvTcParams p = {};
+  p.xin = xin; p.wp = c.wp; p.bias = c.bias; p.out = out;
+  p.D = L.D; p.P = L.P; p.G = L.G; p.T = L.T; p.NB = c.cout / 32; p.Lp = L.Lp; p.Cout = c.cout; p.n_poses = n_poses;
+  p.relu = 1;
+  p.n_groups = (n_poses + L.G - 1) / L.G;
+  const int n_items = p.n_groups * L.T * p.NB;
+  int grid = n_sm_dev[dev];
+  grid -= grid % p.NB;                  // a CTA keeps one Cout block
+  if (grid > n_items) grid = n_items;
+  conv3_tc_v2_kernel<CIN, DD><<<grid, 192, S::kTotal, s>>>(p);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Kernel C: pointwise (1x1x1) convolution + bias + ReLU + 2x2x2 average pool + re-layout for the next conv.
 // in : Y [pose][D][D][D][C] fp16 (already ReLU'd output of the preceding 3^3 conv)
 // out: chunk-planar padded grouped layout with Dn = D/2.
@@ -950,7 +1176,8 @@ int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspa
   }
   {
     ProfScope ps(prof, "tc_conv3_3x3x3_32x64_d12", s);
-    launch_conv_tc<32, 12>(tw->conv3, L3, X2, Y3, nb, s);
+    if (tc_conv_v2() & 1) launch_conv_tc_v2<32, 12>(tw->conv3, L3, X2, Y3, nb, s);
+    else launch_conv_tc<32, 12>(tw->conv3, L3, X2, Y3, nb, s);
   }
   {
     ProfScope ps(prof, "tc_pw4_pool", s);
@@ -963,7 +1190,8 @@ int tc_forward(const Model& m, const TcPoseBatch& pb, const void* x0v, TcWorkspa
   }
   {
     ProfScope ps(prof, "tc_conv5_3x3x3_64x128_d6", s);
-    launch_conv_tc<64, 6>(tw->conv5, L5, X4, Y5, nb, s);
+    if (tc_conv_v2() & 2) launch_conv_tc_v2<64, 6>(tw->conv5, L5, X4, Y5, nb, s);
+    else launch_conv_tc<64, 6>(tw->conv5, L5, X4, Y5, nb, s);
   }
   {
     ProfScope ps(prof, "tc_fc_heads", s);
