@@ -221,6 +221,25 @@ def test_fused_kernel_variants_agree(kat, monkeypatch):
         assert np.abs(out["1" + suf][0] - out["0" + suf][0]).max() < 5e-5 and np.abs(out["1" + suf][1] - out["0" + suf][1]).max() < 5e-4
 
 
+def test_conv3_conv5_organisations_agree(kat, monkeypatch):
+    """unit3_conv / unit5_conv on conv3_tc_kernel (two CTAs per SM, 8-slot ring) and on conv3_tc_v2_kernel (one CTA per SM,
+    slot = plane) issue the same MMAs in the same order: identical scores, ragged pose counts included."""
+    from gnina_b200 import synth
+    rx, rt = synth.make_receptor(1500, box=44)
+    lx0, lt0 = synth.make_ligand(22, 3, seed=4)
+    s = _fast(["crossdock_default2018"])
+    s.set_receptor(rx, rt)
+    for n in (1, 3, 77, 300):
+        lx, offs = synth.make_poses(lx0, n, trans_box=10, seed=n)
+        lt = np.tile(lt0, n)
+        out = {}
+        for v in ("0", "3"):
+            monkeypatch.setenv("GB_TC_CONV_V2", v)
+            out[v] = s.score_batch(lx, lt, offs)
+        monkeypatch.delenv("GB_TC_CONV_V2")
+        assert np.array_equal(out["0"][0], out["3"][0]) and np.array_equal(out["0"][1], out["3"][1])
+
+
 def test_dense_ensemble_matches_reference_pt(golden_dir):
     """BASELINE config 4: `--cnn dense_ensemble` = 20 models (15 dense + 5 default2018 architecture), ensemble
     statistics of CNNTorchScorer::score against the reference's own .pt files (tests/golden/ensemble_kat.npz)."""
