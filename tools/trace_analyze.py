@@ -1,24 +1,37 @@
-"""Analyse the clock64 timeline written by GB_TC_FUSED_TRACE (CTA 0 of conv1_pw2_pool_kernel): python tools/trace_analyze.py <file>"""
+"""Analyse the clock64 timeline written by GB_TC_FUSED_TRACE=<file> (CTA 0 of the fused conv kernel, second launch of the process):
+    python tools/trace_analyze.py <file>
+Rows: role (0 producer, 1 convolution issuer, 2 first epilogue warp), plane, 8 stamps.
+v2 kernel (default): issuer stamps 0 window start, 1 after the first 12 MMAs, 2 after the NEXT window's barrier waits, 4 after
+the last MMA + commits; epilogue stamps 0 before the accumulator wait, 1 accumulator ready, 2 operand staged, 3 pointwise result ready.
+Two-CTAs-per-SM kernel (GB_TC_FUSED_V2=0): issuer stamps 0 start, 1 pointwise MMAs issued, 2 slot waits done, 3 TMA box there, 4 issued."""
 import sys
 import numpy as np
 rows = [list(map(int, l.split())) for l in open(sys.argv[1])]
-T = {}
-for r in rows:
-    T[(r[0], r[1])] = np.array(r[2:], dtype=np.int64)
-def col(role, k, lo=8, hi=88):
-    return np.array([T[(role, p)][k] for p in range(lo, hi)], dtype=np.float64)
-t0 = min(T[(1, 8)][0], T[(0, 8)][0])
-print("planes 8..87 of CTA 0; cycles (SM clock)")
-m0, m1, m2, m3, m4 = (col(1, k) for k in range(5))
-print("MMA warp per plane: total %.0f | pw wait+issue %.0f | acce wait %.0f | full(TMA) wait %.0f | issue+commit %.0f" %
-      (np.diff(m0).mean(), (m1 - m0).mean(), (m2 - m1).mean(), (m3 - m2).mean(), (m4 - m3).mean()))
-p0, p1 = col(0, 0), col(0, 1)
-print("producer per plane: total %.0f | empty wait %.0f" % (np.diff(p0).mean(), (p1 - p0).mean()))
-e0, e1, e2, e3 = (col(2, k) for k in range(4))
-print("epilogue per plane: total %.0f | accf wait %.0f | step1 %.0f | to d2 ready %.0f | rest %.0f" %
-      (np.diff(e0).mean(), (e1 - e0).mean(), (e2 - e1).mean(), (e3 - e2).mean(), (np.roll(e0, -1) - e3)[:-1].mean()))
-# relative lags: TMA issue (p1) -> data seen by MMA warp (m3) for the same plane
-print("TMA issue -> MMA warp sees the slab: %.0f (same plane)" % (m3 - p1).mean())
-print("MMA issue done (m4, plane c) -> epilogue sees accf of plane c-1 (e1, index c-1): %.0f" % (e1[1:] - m4[1:] + 0 * 1).mean() if True else "")
-for p in range(8, 20):
-    print(p, "MMA", (T[(1, p)][:5] - t0).tolist(), "EPI", (T[(2, p)][:4] - t0).tolist(), "PROD", (T[(0, p)][:2] - t0).tolist())
+T = {(r[0], r[1]): np.array(r[2:], dtype=np.int64) for r in rows}
+n = max(p for (role, p) in T if role == 1 and T[(role, p)][0] > 0) + 1
+v2 = all(T[(1, p)][3] == 0 for p in range(min(n, 24)))
+per = 24
+m0 = np.array([T[(1, p)][0] for p in range(n)], dtype=np.float64)
+print("%s kernel, %d planes traced; cycles (SM clock)" % ("v2" if v2 else "two-CTA", n))
+d = np.diff(m0)
+for i in range(0, n - 1, per):
+    print("issuer period per plane:", d[i:i + per].astype(int).tolist())
+lo, hi = per, (n // per) * per
+def seg(role, k0, k1):
+    a = np.array([T[(role, p)][k1] - T[(role, p)][k0] for p in range(lo, hi)], dtype=np.float64)
+    return a.reshape(-1, per).mean(0).astype(int).tolist()
+if hi > lo:
+    if v2:
+        print("issuer: first 12 MMAs      ", seg(1, 0, 1))
+        print("issuer: next window's waits", seg(1, 1, 2))
+        print("issuer: last 6 + commits   ", seg(1, 2, 4))
+    else:
+        print("issuer: pointwise wait+issue", seg(1, 0, 1))
+        print("issuer: slot waits          ", seg(1, 1, 2))
+        print("issuer: TMA box wait        ", seg(1, 2, 3))
+        print("issuer: issue + commit      ", seg(1, 3, 4))
+    e = [p for p in range(lo, hi) if T[(2, p)][1] > 0]
+    if e:
+        a = np.array([[T[(2, p)][k] for k in range(4)] for p in e], dtype=np.float64)
+        print("epilogue (traced warp's planes): accumulator wait %.0f | step 1 %.0f | to pointwise result %.0f" %
+              ((a[:, 1] - a[:, 0]).mean(), (a[:, 2] - a[:, 1]).mean(), (a[:, 3] - a[:, 2]).mean()))
