@@ -6,7 +6,7 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 txt = subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv"], text=True, stderr=subprocess.DEVNULL)
 rows = list(csv.reader(io.StringIO(txt)))
 h, units = rows[0], rows[1]
-KEYS = {"conv1_pw2_pool": "tc_conv1_pw2_pool_fused", "conv3_tc_kernel<32, 12>": "tc_conv3_3x3x3_32x64_d12", "conv3_tc_kernel<64, 6>": "tc_conv5_3x3x3_64x128_d6", "pointwise_pool_mma_kernel<64, 12>": "tc_pw4_pool", "voxelize_pool_f16_kernel<0": "tc_voxelize_pool"}
+KEYS = {"conv1_pw2_pool": "tc_conv1_pw2_pool_fused", "conv3_tc_v2_kernel<32, 12>": "tc_conv3_3x3x3_32x64_d12", "conv3_tc_v2_kernel<64, 6>": "tc_conv5_3x3x3_64x128_d6", "pointwise_pool_mma_kernel<64, 12>": "tc_pw4_pool", "voxelize_pool_f16_kernel<0": "tc_voxelize_pool"}
 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 path = os.path.join(ROOT, "profiles", "traffic.json")
 out = json.load(open(path)) if os.path.exists(path) else {}
