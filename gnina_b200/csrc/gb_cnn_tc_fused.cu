@@ -27,6 +27,11 @@
 //   Y1 (0.88 MB per pose) never exists in HBM and the pointwise kernel is gone (round 1: 11 % of the step).
 //
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue.
+//
+// This file holds two organisations of that arithmetic: conv1_pw2_pool_kernel (two CTAs per SM, 256 TMEM columns each; round 2's
+// first version, 6.9 ms per 10 k poses) and conv1_pw2_pool_v2_kernel further down (one CTA per SM, all 512 TMEM columns, ghost
+// slots, single-thread issuers, two epilogue teams: 5.4 ms; the default -- and, as a template variant, the same on CTA pairs with
+// tcgen05 cta_group::2, which is slower).  launch_conv1_pw2_pool() picks by GB_TC_FUSED_V2; the tests run all of them.
 #include <cstdio>
 #include <cstdlib>
 #include <cuda.h>
