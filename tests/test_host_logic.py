@@ -13,8 +13,8 @@ def test_expand_model_names_like_reference():
     # cnn_torch_scorer.cpp:28-62
     assert scorer.expand_model_names([]) == ["dense_1_3", "dense_1_3_PT_KD_3", "crossdock_default2018_KD_4"]
     assert scorer.expand_model_names(["fast"]) == ["all_default_to_default_1_3_1"]
-    assert scorer.expand_model_names(["default1.0"], check=False) == ["dense", "general_default2018_3", "dense_3",
-                                                                      "crossdock_default2018", "redock_default2018_2"]
+    assert scorer.expand_model_names(["default1.0"]) == ["dense", "general_default2018_3", "dense_3",   # all packaged
+                                                         "crossdock_default2018", "redock_default2018_2"]
     assert scorer.expand_model_names(["dense_1.3"]) == ["dense_1_3"]
     # an ensemble expands over the REFERENCE's table (64 models), not over whatever happens to be packaged
     assert len(scorer.REFERENCE_MODELS) == 64
