@@ -96,7 +96,8 @@ def make_flexible_ligand(n_heavy=24, n_tors=5, n_branch=3, seed=11):
     local frame of their segment (identity orientation): coords = segment origin + local.  A linear chain with
     `n_tors` rotatable bonds plus one side branch of `n_branch` atoms hanging off the root.
     -> dict(local_xyz, types, seg_parent, seg_begin, seg_end, seg_rel_origin, seg_rel_axis, pair_a, pair_b,
-            conf0 [7+T] reproducing the generated coordinates, xyz0, gyration_radius)"""
+            conf0 [7+T] reproducing the generated coordinates, xyz0, gyration_radius, axis_root = per segment the atom at the
+            begin of its rotation axis)"""
     rs = np.random.RandomState(seed)
     xyz = [np.zeros(3)]
     while len(xyz) < n_heavy:
@@ -158,7 +159,7 @@ def make_flexible_ligand(n_heavy=24, n_tors=5, n_branch=3, seed=11):
                 seg_begin=np.array(seg_begin, np.int32), seg_end=np.array(seg_end, np.int32),
                 seg_rel_origin=rel_origin.astype(np.float32), seg_rel_axis=rel_axis.astype(np.float32),
                 pair_a=np.array(pa, np.int32), pair_b=np.array(pb, np.int32), conf0=conf0, xyz0=pos.astype(np.float32),
-                gyration_radius=gr)
+                gyration_radius=gr, axis_root=np.array([0] + axis_root[1:], np.int32))
 
 
 def make_gninacheck_mol(rs, natoms=0, min_atoms=200, max_atoms=500, max_x=25.0, max_y=25.0, max_z=25.0):

@@ -68,9 +68,14 @@ static void normalize_angle(float *x) { /* quaternion.h:261-281 */
  * measured) and a GPU has no glibc.  The correctly rounded value is what every libm approximates and what both this
  * restatement and the device code can compute identically, so that BFGS and Monte-Carlo trajectories can be compared
  * step by step instead of statistically. */
-static float sin_cr(float x) { return (float)sin((double)x); }
-static float cos_cr(float x) { return (float)cos((double)x); }
-static float exp_cr(float x) { return (float)exp((double)x); }
+/* gvo_use_libm(1): call this host's sinf / cosf / expf instead -- what the reference compiled HERE (oracle/_ref) executes -- so
+ * that the comparison with oracle/_ref can demand bit-identical coordinates and energies; the default (0) is the correctly
+ * rounded value that the device kernels reproduce. */
+static int g_use_libm = 0;
+void gvo_use_libm(int on) { g_use_libm = on; }
+static float sin_cr(float x) { return g_use_libm ? sinf(x) : (float)sin((double)x); }
+static float cos_cr(float x) { return g_use_libm ? cosf(x) : (float)cos((double)x); }
+static float exp_cr(float x) { return g_use_libm ? expf(x) : (float)exp((double)x); }
 static void angle_to_q(const float *axis, float angle, float *q) {
   normalize_angle(&angle);
   float c = cos_cr(angle / 2), s = sin_cr(angle / 2);

@@ -1,0 +1,252 @@
+"""ctypes front-end to oracle/_ref/libgnina_vina_ref.so = the REFERENCE's own Vina sources compiled where they lie under
+/root/reference (oracle/Makefile.ref + oracle/ref_driver.cpp + the Boost/OpenBabel stand-in headers of oracle/ref_shim/).
+Test infrastructure only: it pins the restatement (oracle/vina_ref.c, vina_mc_ref.c) and generates tests/golden/vina_ref_kat.npz.
+`available()` is False where neither the built library nor /root/reference exists (the GPU box has the prebuilt .so)."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_ref", "libgnina_vina_ref.so")
+_fp, _ip, _vp = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_void_p
+_lib = None
+
+
+def build():
+    """compile the reference sources (only where /root/reference is present); returns True when the library exists"""
+    if os.path.isdir("/root/reference/gninasrc/lib"):
+        subprocess.check_call(["make", "-s", "-f", "Makefile.ref", "-j", "16"], cwd=_HERE)
+    return os.path.exists(_SO)
+
+
+def available():
+    return os.path.exists(_SO)
+
+
+def _f(a): return a.ctypes.data_as(_fp)
+def _i(a): return a.ctypes.data_as(_ip)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(_SO, mode=os.RTLD_NOW)
+        L.gref_last_error.restype = C.c_char_p
+        L.gref_sf_create.argtypes = [C.c_float, C.c_float]; L.gref_sf_create.restype = _vp
+        L.gref_sf_destroy.argtypes = [_vp]
+        L.gref_cutoff_sqr.argtypes = [_vp]; L.gref_cutoff_sqr.restype = C.c_float
+        L.gref_terms_eval.argtypes = [_vp, C.c_int, C.c_int, C.c_float]; L.gref_terms_eval.restype = C.c_float
+        L.gref_prec_eval.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_float]; L.gref_prec_eval.restype = C.c_float
+        L.gref_prec_eval_deriv.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_float, _fp]
+        L.gref_model_create.argtypes = [C.c_int, _fp, _ip, C.c_int, _ip, _ip, _ip, _ip, C.c_int, _ip, _ip, C.c_int, _fp, _ip]
+        L.gref_model_create.restype = _vp
+        L.gref_model_destroy.argtypes = [_vp]
+        L.gref_model_export.argtypes = [_vp, _fp, _fp, _fp]
+        L.gref_model_set.argtypes = [_vp, _fp, _fp]
+        L.gref_model_put_coords.argtypes = [_vp, _fp]
+        L.gref_model_get_coords.argtypes = [_vp, _fp]
+        L.gref_gyration_radius.argtypes = [_vp]; L.gref_gyration_radius.restype = C.c_float
+        L.gref_tree_derivative.argtypes = [_vp, _fp, _fp]
+        for nm in ("gref_cache_create", "gref_noncache_create"):
+            getattr(L, nm).argtypes = [_vp, C.c_int, _vp, _fp, _fp, _ip, C.c_float]; getattr(L, nm).restype = _vp
+        L.gref_cache_grid.argtypes = [_vp, C.c_int, _fp]
+        L.gref_noncache_set_slope.argtypes = [_vp, C.c_float]
+        L.gref_noncache_within.argtypes = [_vp, _vp, C.c_float]
+        L.gref_naive_create.argtypes = [_vp, C.c_int]; L.gref_naive_create.restype = _vp
+        L.gref_grid_destroy.argtypes = [_vp]
+        L.gref_ig_eval.argtypes = [_vp, _vp, C.c_float, _fp]
+        L.gref_ig_eval_deriv.argtypes = [_vp, _vp, C.c_float, _fp, _fp]
+        L.gref_model_eval_deriv.argtypes = [_vp, _vp, C.c_int, _vp, _fp, _fp, _fp, _fp]
+        L.gref_model_affinity.argtypes = [_vp, _vp, _fp, _fp, _fp, _fp]
+        L.gref_num_tors_div.argtypes = [_vp, C.c_float, C.c_float, _fp]
+        L.gref_bfgs.argtypes = [_vp, _vp, C.c_int, _vp, _fp, C.c_int, _fp, _fp, _fp]
+        L.gref_random_conf.argtypes = [_vp, C.c_uint32, _fp, _fp, _fp, C.POINTER(C.c_uint32)]
+        L.gref_mc.argtypes = [_vp, _vp, C.c_int, _vp, _fp, _fp, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                              _fp, C.c_int, _fp, _fp, C.POINTER(C.c_int)]
+        L.gref_container_replay.argtypes = [C.c_int, C.c_int, _fp, _fp, C.c_float, C.c_int, _fp, C.POINTER(C.c_int)]
+        _lib = L
+    return _lib
+
+
+def _ok(rc):
+    if rc:
+        raise RuntimeError("reference code raised: " + lib().gref_last_error().decode())
+
+
+LINEAR, SPLINES, EXACT = 0, 1, 2
+
+
+class RefScoring:
+    """custom_terms + weighted_terms with gnina's default Vina weights (main/main.cpp:1324-1329) and the three precalculate
+    flavours: LINEAR (factor 32, docking), SPLINES (factor 10, --minimize), EXACT (final score)"""
+
+    def __init__(self, factor_linear=32.0, factor_splines=10.0):
+        self.p = lib().gref_sf_create(factor_linear, factor_splines)
+        if not self.p:
+            raise RuntimeError(lib().gref_last_error().decode())
+
+    def __del__(self):
+        try:
+            lib().gref_sf_destroy(self.p)
+        except Exception:
+            pass
+
+    def cutoff_sqr(self): return lib().gref_cutoff_sqr(self.p)
+    def terms(self, t1, t2, r): return lib().gref_terms_eval(self.p, t1, t2, r)
+    def eval(self, kind, t1, t2, r2): return lib().gref_prec_eval(self.p, kind, t1, t2, r2)
+
+    def eval_deriv(self, kind, t1, t2, r2):
+        o = np.empty(2, np.float32)
+        lib().gref_prec_eval_deriv(self.p, kind, t1, t2, r2, _f(o))
+        return float(o[0]), float(o[1])
+
+    def num_tors_div(self, e, num_tors):
+        o = np.empty(1, np.float32)
+        _ok(lib().gref_num_tors_div(self.p, e, num_tors, _f(o)))
+        return float(o[0])
+
+
+class RefModel:
+    """a reference `model` built by hand from a ligand description (gnina_b200.synth.make_flexible_ligand's dict: xyz0, types,
+    seg_parent / seg_begin / seg_end, axis_root, pair_a / pair_b) and receptor atoms"""
+
+    def __init__(self, lig, rec_xyz=None, rec_types=None):
+        k = lambda a, dt: np.ascontiguousarray(a, dt)
+        self.na, self.ns = len(lig["types"]), len(lig["seg_parent"])
+        self.T = self.ns - 1
+        xyz, ty = k(lig["xyz0"], np.float32), k(lig["types"], np.int32)
+        sp, sb, se = (k(lig[q], np.int32) for q in ("seg_parent", "seg_begin", "seg_end"))
+        ar = k(lig["axis_root"], np.int32)
+        pa, pb = k(lig["pair_a"], np.int32), k(lig["pair_b"], np.int32)
+        rx = k(rec_xyz if rec_xyz is not None else np.zeros((0, 3)), np.float32)
+        rt = k(rec_types if rec_types is not None else np.zeros(0), np.int32)
+        self.p = lib().gref_model_create(self.na, _f(xyz), _i(ty), self.ns, _i(sp), _i(sb), _i(se), _i(ar), len(pa), _i(pa), _i(pb),
+                                         len(rt), _f(rx), _i(rt))
+        if not self.p:
+            raise RuntimeError(lib().gref_last_error().decode())
+
+    def __del__(self):
+        try:
+            lib().gref_model_destroy(self.p)
+        except Exception:
+            pass
+
+    def export(self):
+        """-> (local_xyz, seg_rel_origin, seg_rel_axis) as the reference's constructors computed them"""
+        lo, ro, ra = np.empty((self.na, 3), np.float32), np.empty((self.ns, 3), np.float32), np.empty((self.ns, 3), np.float32)
+        lib().gref_model_export(self.p, _f(lo), _f(ro), _f(ra))
+        return lo, ro, ra
+
+    def set(self, conf):
+        x = np.ascontiguousarray(conf, np.float32); o = np.empty((self.na, 3), np.float32)
+        _ok(lib().gref_model_set(self.p, _f(x), _f(o)))
+        return o
+
+    def put_coords(self, xyz):
+        lib().gref_model_put_coords(self.p, _f(np.ascontiguousarray(xyz, np.float32)))
+
+    def coords(self):
+        o = np.empty((self.na, 3), np.float32)
+        lib().gref_model_get_coords(self.p, _f(o))
+        return o
+
+    def gyration_radius(self): return lib().gref_gyration_radius(self.p)
+
+    def tree_derivative(self, forces):
+        f = np.ascontiguousarray(forces, np.float32); g = np.empty(6 + self.T, np.float32)
+        _ok(lib().gref_tree_derivative(self.p, _f(f), _f(g)))
+        return g
+
+
+class RefGrid:
+    """an igrid of the reference: cache (populated), non_cache or naive_non_cache"""
+
+    def __init__(self, p, model):
+        if not p:
+            raise RuntimeError(lib().gref_last_error().decode())
+        self.p, self.m = p, model
+
+    @classmethod
+    def cache(cls, sf, kind, model, begin, end, n, slope):
+        b, e, nn = (np.ascontiguousarray(a, dt) for a, dt in ((begin, np.float32), (end, np.float32), (n, np.int32)))
+        g = cls(lib().gref_cache_create(sf.p, kind, model.p, _f(b), _f(e), _i(nn), slope), model)
+        g.n = nn
+        return g
+
+    @classmethod
+    def non_cache(cls, sf, kind, model, begin, end, n, slope):
+        b, e, nn = (np.ascontiguousarray(a, dt) for a, dt in ((begin, np.float32), (end, np.float32), (n, np.int32)))
+        return cls(lib().gref_noncache_create(sf.p, kind, model.p, _f(b), _f(e), _i(nn), slope), model)
+
+    @classmethod
+    def naive(cls, sf, kind, model):
+        return cls(lib().gref_naive_create(sf.p, kind), model)
+
+    def __del__(self):
+        try:
+            lib().gref_grid_destroy(self.p)
+        except Exception:
+            pass
+
+    def grid(self, t):
+        out = np.empty((self.n[2] + 1, self.n[1] + 1, self.n[0] + 1), np.float32)
+        return out if lib().gref_cache_grid(self.p, t, _f(out)) else None
+
+    def set_slope(self, s): lib().gref_noncache_set_slope(self.p, s)
+    def within(self, margin=1e-4): return bool(lib().gref_noncache_within(self.p, self.m.p, margin))
+
+    def eval(self, v):
+        e = np.empty(1, np.float32)
+        _ok(lib().gref_ig_eval(self.p, self.m.p, v, _f(e)))
+        return float(e[0])
+
+    def eval_deriv(self, v):
+        e = np.empty(1, np.float32); f = np.empty((self.m.na, 3), np.float32)
+        _ok(lib().gref_ig_eval_deriv(self.p, self.m.p, v, _f(e), _f(f)))
+        return float(e[0]), f
+
+
+def model_eval_deriv(model, sf, kind, grid, conf, v=(1000, 1000, 1000)):
+    x = np.ascontiguousarray(conf, np.float32); vv = np.ascontiguousarray(v, np.float32)
+    e = np.empty(1, np.float32); g = np.empty(6 + model.T, np.float32)
+    _ok(lib().gref_model_eval_deriv(model.p, sf.p, kind, grid.p, _f(vv), _f(x), _f(e), _f(g)))
+    return float(e[0]), g
+
+
+def model_affinity(model, sf, conf, v=(1000, 1000, 1000)):
+    """-> (intramolecular energy, eval_adjusted = the printed Affinity), exact terms (main/main.cpp:219-232)"""
+    x = np.ascontiguousarray(conf, np.float32); vv = np.ascontiguousarray(v, np.float32)
+    a, b = np.empty(1, np.float32), np.empty(1, np.float32)
+    _ok(lib().gref_model_affinity(model.p, sf.p, _f(vv), _f(x), _f(a), _f(b)))
+    return float(a[0]), float(b[0])
+
+
+def bfgs(model, sf, kind, grid, conf, maxiters, v=(1000, 1000, 1000)):
+    x = np.array(conf, np.float32); vv = np.ascontiguousarray(v, np.float32)
+    e = np.empty(1, np.float32); g = np.empty(6 + model.T, np.float32)
+    _ok(lib().gref_bfgs(model.p, sf.p, kind, grid.p, _f(x), maxiters, _f(vv), _f(e), _f(g)))
+    return float(e[0]), x, g
+
+
+def random_conf(model, seed, c1, c2):
+    x = np.empty(7 + model.T, np.float32); st = C.c_uint32()
+    _ok(lib().gref_random_conf(model.p, seed, _f(np.ascontiguousarray(c1, np.float32)), _f(np.ascontiguousarray(c2, np.float32)), _f(x),
+                               C.byref(st)))
+    return x, st.value
+
+
+def mc(model, sf, kind, grid, seed, c1, c2, num_steps, maxiters, num_saved_mins=50, temperature=1.2, amplitude=2.0, min_rmsd=1.0,
+       hunt_cap=(10, 10, 10)):
+    e = np.zeros(num_saved_mins, np.float32); x = np.zeros((num_saved_mins, 7 + model.T), np.float32); n = C.c_int()
+    hc = np.ascontiguousarray(hunt_cap, np.float32)
+    _ok(lib().gref_mc(model.p, sf.p, kind, grid.p, _f(np.ascontiguousarray(c1, np.float32)), _f(np.ascontiguousarray(c2, np.float32)), seed,
+                      num_steps, maxiters, num_saved_mins, temperature, amplitude, min_rmsd, _f(hc), num_saved_mins, _f(e), _f(x), C.byref(n)))
+    return e[:n.value], x[:n.value]
+
+
+def container_replay(e, coords, min_rmsd, max_size):
+    e = np.ascontiguousarray(e, np.float32); c = np.ascontiguousarray(coords, np.float32)
+    out = np.empty(len(e), np.float32); n = C.c_int()
+    _ok(lib().gref_container_replay(len(e), c.shape[1], _f(e), _f(c), min_rmsd, max_size, _f(out), C.byref(n)))
+    return out[:n.value]
