@@ -559,7 +559,9 @@ int gb_vina_score_exact(gb_vina* h, const float* lig_xyz, const int32_t* lig_typ
     if (affinity) {
       // num_tors_div (everything.h:804-809) with smooth_div (:52-56)
       const float w = (float)(0.1 * ((double)v.w[5] + 1));
-      const float y = (float)(1 + (double)w * (double)(num_tors ? num_tors[p] : 0.f) / 5.0);
+      // "1 + w * in.num_tors / 5.0" with fl w, fl num_tors: the product is a FLOAT product, then double arithmetic (pinned by oracle/_ref)
+      const float wnt = w * (num_tors ? num_tors[p] : 0.f);
+      const float y = (float)(1 + (double)wnt / 5.0);
       const float x = e[p];
       const float eps = 1.1920929e-07f, maxfl = 3.402823466e+38f;
       affinity[p] = std::fabs(x) < eps ? 0.f : (std::fabs(y) < eps ? ((x * y > 0) ? maxfl : -maxfl) : x / y);
@@ -856,12 +858,17 @@ __device__ __forceinline__ float dk_atom_field(const LigPtrs& L, const DockField
 // reference's association -- atom energies in atom order, pair energies in pair order, the forces on an atom in the
 // order its pairs appear in the pair list, children folded into their parent in ascending order -- so that the result
 // agrees with the sequential CPU code to round-off of the transcendental functions only (north_star: 1e-6).
-// grid_only: update_energy's cache::eval (lib/monte_carlo.cpp:113,135) -- the intermolecular energy alone, atoms summed in
-// index order; nothing is written to gout.  It shares the kinematics and the per-atom field code with the full evaluation
-// (ONE copy of this function per kernel: the chain kernel's instruction footprint is what bounds it, profiles/README.md r2o).
+// mode kEvGridHere: update_energy's cache::eval (lib/monte_carlo.cpp:44-47,113,135) -- the intermolecular energy alone, atoms
+// summed in index order, ON THE COORDINATES THE WORKSPACE HOLDS (no set_conf: the reference's model object keeps the coordinates of
+// the last conformation that was set, and igrid::eval reads those); nothing is written to gout.  mode kEvSetOnly: model::set(conf)
+// alone.  Both share the kinematics and the per-atom field code with the full evaluation (ONE copy of this function per kernel:
+// the chain kernel's instruction footprint is what bounds it, profiles/README.md r2o).
+enum { kEvFull = 0, kEvGridHere = 1, kEvSetOnly = 2 };
 __device__ float dk_eval_deriv(const LigPtrs& L, const DockField& F, WarpWs& W, const float* xc, const float* v, float* gout, int lane,
-                               bool grid_only = false) {
-  dk_set_conf(L, W, xc, lane);
+                               int mode = kEvFull) {
+  if (mode != kEvGridHere) dk_set_conf(L, W, xc, lane);
+  if (mode == kEvSetOnly) return 0.f;
+  const bool grid_only = mode == kEvGridHere;
   #pragma unroll 1
   for (int i = lane; i < L.n_atoms; i += 32) {
     float d[3] = {0.f, 0.f, 0.f};
@@ -974,23 +981,55 @@ __device__ void dk_conf_increment(float* x, const float* p, float f, int T, int 
 // Written around ONE evaluation site: the initial evaluation, every line-search trial and (grid_e != nullptr) the chain's
 // update_energy after the minimisation -- cache::eval at the final conformation with curl cap grid_v1 -- are iterations of
 // the same loop, so a kernel holds one copy of dk_eval_deriv (the arithmetic and its order are those of the reference).
+// model::gyration_radius (lib/model.cpp:1002-1014) of the coordinates the workspace holds: heavy atoms about the root origin, summed
+// in atom order (W.ea is free between evaluations; a hydrogen contributes an exact zero)
+__device__ inline float dk_gyration_radius(const LigPtrs& L, WarpWs& W, int lane) {
+  #pragma unroll 1
+  for (int i = lane; i < L.n_atoms; i += 32) {
+    float d2 = 0.f;
+    if ((int)L.local[i].w >= 2) {
+      const float a = W.coords[3 * i] - W.so[0], b = W.coords[3 * i + 1] - W.so[1], c = W.coords[3 * i + 2] - W.so[2];
+      d2 = a * a + b * b + c * c;
+    }
+    W.ea[i] = d2;
+  }
+  __syncwarp();
+  const float acc = dk_sum_seq(W.ea, L.n_atoms);
+  __syncwarp();
+  return L.n_heavy > 0 ? sqrtf(acc / (float)L.n_heavy) : 0.f;
+}
+
 __device__ float dk_bfgs(const LigPtrs& L, const DockField& F, WarpWs& W, int maxiters, const float* v, int lane, int* n_evals,
-                         float* grid_e = nullptr, float grid_v1 = 0.f) {
+                         float* grid_e = nullptr, float grid_v1 = 0.f, float* gr_state = nullptr, float* gr_final = nullptr) {
   const int T = L.n_seg - 1, n = 6 + T, nx = 7 + T;
   #pragma unroll 1
   for (int k = lane; k < n * (n + 1) / 2; k += 32) W.h[k] = 0.f;
   __syncwarp();
   #pragma unroll 1
   for (int i = lane; i < n; i += 32) W.h[dk_tri(i, i)] = 1.f;
-  int evals = 0, step = -1, trial = 0;   // step -1: the initial evaluation; phase 2: the final grid-only evaluation
+  int evals = 0, step = -1, trial = 0;   // step -1: the initial evaluation
+  // finishing (chain kernel only, grid_e != nullptr) = what monte_carlo.cpp does around quasi_newton: 1 = update_energy, the grid
+  // energy of the coordinates the LAST evaluation left in the model (bfgs.h does not re-evaluate at the x it returns: after ten
+  // failed line-search trials, or when x_orig is restored, those are another conformation's); 2 = m.set(x) of the returned x
   float f0 = 0.f, f1 = 0.f, f_orig = 0.f, alpha = 1.f, pg = 0.f;
-  bool didreset = false, finishing = false;
+  bool didreset = false;
+  int finishing = 0;
   const float vg[3] = {grid_v1, grid_v1, grid_v1};
   #pragma unroll 1
   for (;;) {
     const bool init = step < 0;
-    const float fe = dk_eval_deriv(L, F, W, (init || finishing) ? W.x : W.x_new, finishing ? vg : v, init ? W.g : W.g_new, lane, finishing);
-    if (finishing) { *grid_e = fe; break; }
+    const float fe = dk_eval_deriv(L, F, W, (init || finishing) ? W.x : W.x_new, finishing ? vg : v, init ? W.g : W.g_new, lane,
+                                   finishing == 1 ? kEvGridHere : finishing == 2 ? kEvSetOnly : kEvFull);
+    if (finishing == 1) {
+      *grid_e = fe;
+      if (gr_state) *gr_state = dk_gyration_radius(L, W, lane);
+      finishing = 2;
+      continue;
+    }
+    if (finishing == 2) {
+      if (gr_final) *gr_final = dk_gyration_radius(L, W, lane);
+      break;
+    }
     evals++;
     bool new_iter = false, done = false;
     if (init) {
@@ -1082,7 +1121,7 @@ __device__ float dk_bfgs(const LigPtrs& L, const DockField& F, WarpWs& W, int ma
         __syncwarp();
       }
       if (!grid_e) break;
-      finishing = true;
+      finishing = 1;
       continue;
     }
     // next trial point: x_new = x (+) alpha p
@@ -1222,6 +1261,10 @@ __global__ void __launch_bounds__(32 * kDkWarps, 7) dock_mc_kernel(LigPtrs L, Do
   __syncwarp();
   float tmp_e = 0.f, best_e = 3.402823466e+38f;
   int n_out = 0;
+  // mutate_conf rotates by amplitude / model::gyration_radius, and the model object holds the coordinates of the LAST conformation that
+  // was set (mutate.cpp:55, model.cpp:1002-1014): the input pose when the chain starts (L.gyration_radius, from the host), afterwards
+  // whatever quasi_newton's last evaluation or monte_carlo's explicit m.set left there -- followed step by step below
+  float gr = L.gyration_radius;
   for (int step = 0; step < P.num_steps; step++) {
     for (int i = lane; i < nx; i += 32) W.cand[i] = W.tmp[i];
     __syncwarp();
@@ -1230,10 +1273,9 @@ __global__ void __launch_bounds__(32 * kDkWarps, 7) dock_mc_kernel(LigPtrs L, Do
       float r[3];
       if (which == 0) { dk_rng_sphere(rs, r); for (int k = 0; k < 3; k++) W.cand[k] += P.mutation_amplitude * r[k]; }
       else if (which == 1) {
-        if (L.gyration_radius > 1.1920929e-07f) {
+        if (gr > 1.1920929e-07f) {
           dk_rng_sphere(rs, r);
-          const float rot[3] = {P.mutation_amplitude / L.gyration_radius * r[0], P.mutation_amplitude / L.gyration_radius * r[1],
-                                P.mutation_amplitude / L.gyration_radius * r[2]};
+          const float rot[3] = {P.mutation_amplitude / gr * r[0], P.mutation_amplitude / gr * r[1], P.mutation_amplitude / gr * r[2]};
           dk_quaternion_increment(W.cand + 3, rot);
         }
       } else W.cand[7 + which - 2] = dk_rng_fl(rs, -pi, pi);
@@ -1241,7 +1283,9 @@ __global__ void __launch_bounds__(32 * kDkWarps, 7) dock_mc_kernel(LigPtrs L, Do
     __syncwarp();
     // Two quasi-Newton runs per step at most -- the hunt with hunt_cap, then, for an accepted candidate that is promising,
     // the full-cap run (monte_carlo.cpp:111-137) -- through ONE dk_bfgs call site (pass 0 / pass 1), each followed by
-    // update_energy = the grid-only evaluation folded into dk_bfgs.
+    // update_energy (the grid energy of the coordinates the last evaluation left) and m.set of the returned conformation, both
+    // folded into dk_bfgs.  A rejected candidate leaves the last evaluation's coordinates in the model (gr_state), an accepted one
+    // is set explicitly (monte_carlo.cpp:126,134: gr_final).
     bool promising = false;
     #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
@@ -1249,8 +1293,9 @@ __global__ void __launch_bounds__(32 * kDkWarps, 7) dock_mc_kernel(LigPtrs L, Do
       #pragma unroll 1
       for (int i = lane; i < nx; i += 32) W.x[i] = src[i];
       __syncwarp();
-      float ge = 0.f;
-      dk_bfgs(L, F, W, P.maxiters, pass == 0 ? P.hunt_cap : av, lane, nullptr, &ge, av[1]);
+      float ge = 0.f, gr_state = 0.f, gr_final = 0.f;
+      dk_bfgs(L, F, W, P.maxiters, pass == 0 ? P.hunt_cap : av, lane, nullptr, &ge, av[1], &gr_state, &gr_final);
+      gr = gr_state;
       if (pass == 0) {
         #pragma unroll 1
         for (int i = lane; i < nx; i += 32) W.cand[i] = W.x[i];
@@ -1268,12 +1313,14 @@ __global__ void __launch_bounds__(32 * kDkWarps, 7) dock_mc_kernel(LigPtrs L, Do
         for (int i = lane; i < nx; i += 32) W.tmp[i] = W.cand[i];
         __syncwarp();
         tmp_e = cand_e;
+        gr = gr_final;   // m.set(tmp.c)
         if (!(tmp_e < best_e || n_out < S)) break;
       } else {
         #pragma unroll 1
         for (int i = lane; i < nx; i += 32) W.tmp[i] = W.x[i];
         __syncwarp();
-        tmp_e = ge;   // the evaluation left the pose's coordinates in W.coords
+        tmp_e = ge;
+        gr = gr_final;   // m.set(tmp.c): W.coords hold the pose's coordinates for the container
         promising = true;
       }
     }

@@ -154,12 +154,26 @@ def make_flexible_ligand(n_heavy=24, n_tors=5, n_branch=3, seed=11):
                 pa.append(i); pb.append(j2)
     conf0 = np.zeros(7 + ns - 1, np.float32)
     conf0[:3] = origin[0]; conf0[3] = 1.0
-    gr = float(np.sqrt(((pos - origin[0]) ** 2).sum(1).mean()))
+    gr = gyration_radius(pos.astype(np.float32), types, origin[0].astype(np.float32))
     return dict(local_xyz=local.astype(np.float32), types=types, seg_parent=np.array(seg_parent, np.int32),
                 seg_begin=np.array(seg_begin, np.int32), seg_end=np.array(seg_end, np.int32),
                 seg_rel_origin=rel_origin.astype(np.float32), seg_rel_axis=rel_axis.astype(np.float32),
                 pair_a=np.array(pa, np.int32), pair_b=np.array(pb, np.int32), conf0=conf0, xyz0=pos.astype(np.float32),
                 gyration_radius=gr, axis_root=np.array([0] + axis_root[1:], np.int32))
+
+
+def gyration_radius(xyz, types, origin):
+    """model::gyration_radius (lib/model.cpp:1002-1014): root-mean-square distance of the HEAVY atoms (smina type >= 2) from the
+    root origin, accumulated in float32 in atom order.  gb_ligand_topology.gyration_radius wants this number for the pose the
+    search starts from (mutate_conf's first rotation uses it; afterwards the kernels follow the conformation the model holds)."""
+    acc, cnt = np.float32(0), 0
+    o = np.asarray(origin, np.float32)
+    for p, t in zip(np.asarray(xyz, np.float32), types):
+        if t >= 2:
+            d = p - o
+            acc = np.float32(acc + np.float32(np.float32(np.float32(d[0] * d[0]) + np.float32(d[1] * d[1])) + np.float32(d[2] * d[2])))
+            cnt += 1
+    return float(np.sqrt(np.float32(acc / np.float32(cnt)))) if cnt else 0.0
 
 
 def make_gninacheck_mol(rs, natoms=0, min_atoms=200, max_atoms=500, max_x=25.0, max_y=25.0, max_z=25.0):

@@ -210,7 +210,9 @@ typedef struct {
   const float* seg_rel_axis;     /* [n_segments][3] */
   const int32_t* pair_a;         /* [n_pairs] */
   const int32_t* pair_b;
-  float gyration_radius;
+  float gyration_radius;         /* model::gyration_radius of the pose the search starts from (heavy atoms about the root origin):
+                                  * mutate_conf's rotation amplitude until the first evaluation; after that the chains take it from
+                                  * the conformation the model holds, as mutate.cpp:55 does */
 } gb_ligand_topology;
 /* monte_carlo members (lib/monte_carlo.h:29-41): defaults temperature 1.2, hunt_cap (10, 1.5, 10), min_rmsd 0.5,
  * num_saved_mins 50, mutation_amplitude 2; num_steps and maxiters as main/main.cpp:442-457 derives them. */

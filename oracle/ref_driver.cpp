@@ -400,10 +400,10 @@ int gref_random_conf(void* mp, unsigned seed, const float* c1, const float* c2, 
     *state_after = gen.state();
   });
 }
-// monte_carlo::operator() (lib/monte_carlo.cpp:99-148) -> the sorted output container: energies, confs [n][7+T], heavy coords
+// monte_carlo::operator() (lib/monte_carlo.cpp:99-148) -> the sorted output container: energies, confs [n][7+T]
 int gref_mc(void* mp, void* sf, int kind, void* gp, const float* c1, const float* c2, unsigned seed, int num_steps, int maxiters,
-            int num_saved_mins, float temperature, float amplitude, float min_rmsd, const float* hunt_cap, int max_out, float* out_e,
-            float* out_conf, int* n_out) {
+            int num_saved_mins, float temperature, float amplitude, float min_rmsd, const float* hunt_cap, const float* state_conf,
+            int max_out, float* out_e, float* out_conf, int* n_out) {
   RefModel* R = (RefModel*)mp; RefSF* S = (RefSF*)sf;
   return guarded([&] {
     monte_carlo mc;
@@ -418,6 +418,7 @@ int gref_mc(void* mp, void* sf, int kind, void* gp, const float* c1, const float
     output_container out;
     grid user_grid;
     igrid& ig = *((RefGrid*)gp)->ig;
+    R->m.set(make_conf(R->m, state_conf));  // the conformation the model object holds when the chain starts (mutate_conf reads it)
     mc(R->m, out, *S->prec[kind], ig, vec(c1[0], c1[1], c1[2]), vec(c2[0], c2[1], c2[2]), nullptr, gen, user_grid, ig);
     const int T = R->n_seg - 1;
     *n_out = (int)std::min<sz>(out.size(), (sz)max_out);

@@ -39,6 +39,7 @@ class DockOracle:
         L.gvo_bfgs.argtypes = [C.POINTER(_Field), C.POINTER(_Lig), _fp, _fp, C.c_int, _fp, C.POINTER(C.c_int)]; L.gvo_bfgs.restype = C.c_float
         L.gvo_mc_run.argtypes = [C.POINTER(_Field), C.POINTER(_Lig), C.POINTER(_McParams), _fp, _fp, C.c_uint32, _fp, _fp]
         L.gvo_mc_run_traced.argtypes = [C.POINTER(_Field), C.POINTER(_Lig), C.POINTER(_McParams), _fp, _fp, C.c_uint32, _fp, _fp, _fp]
+        L.gvo_mc_run_ex.argtypes = [C.POINTER(_Field), C.POINTER(_Lig), C.POINTER(_McParams), _fp, _fp, C.c_uint32, _fp, _fp, _fp, _fp, _fp]
         L.gvo_random_conf.argtypes = [C.POINTER(C.c_uint32), _fp, _fp, C.c_int, _fp]
         self.L = L
         self.keep = []
@@ -141,4 +142,23 @@ class DockOracle:
         tr = np.zeros(num_steps, np.float32)
         n = self.L.gvo_mc_run_traced(C.byref(self.field), C.byref(self.lig), C.byref(P), _f(np.ascontiguousarray(c1, np.float32)),
                                      _f(np.ascontiguousarray(c2, np.float32)), seed, _f(e), _f(x), _f(tr))
+        return (e[:n], x[:n], tr) if trace else (e[:n], x[:n])
+
+    def gyration_radius(self, conf):
+        """model::gyration_radius (lib/model.cpp:1002-1014) of a conformation: heavy atoms about the root origin"""
+        self.L.gvo_gyration_radius.argtypes = [C.POINTER(_Lig), _fp]; self.L.gvo_gyration_radius.restype = C.c_float
+        return self.L.gvo_gyration_radius(C.byref(self.lig), _f(np.ascontiguousarray(conf, np.float32)))
+
+    def mc_ex(self, seed, c1, c2, num_steps, maxiters, num_saved_mins=50, temperature=1.2, amplitude=2.0, min_rmsd=1.0,
+              hunt_cap=(10, 10, 10), init_conf=None, state_conf=None, trace=False):
+        """monte_carlo::operator() with an optional given start (init_conf, `seed` = generator state after the start was drawn)
+        and, with state_conf, in MODEL-STATE mode (vina_mc_ref.c mc_impl): the mode that follows the reference's code to the letter"""
+        P = _McParams(num_steps, maxiters, num_saved_mins, temperature, amplitude, min_rmsd, (C.c_float * 3)(*hunt_cap), self.gr)
+        e = np.zeros(num_saved_mins, np.float32); x = np.zeros((num_saved_mins, 7 + self.T), np.float32)
+        ic = None if init_conf is None else np.ascontiguousarray(init_conf, np.float32)
+        sc = None if state_conf is None else np.ascontiguousarray(state_conf, np.float32)
+        tr = np.zeros(num_steps, np.float32)
+        n = self.L.gvo_mc_run_ex(C.byref(self.field), C.byref(self.lig), C.byref(P), _f(np.ascontiguousarray(c1, np.float32)),
+                                 _f(np.ascontiguousarray(c2, np.float32)), seed, _f(e), _f(x), _f(tr),
+                                 None if ic is None else _f(ic), None if sc is None else _f(sc))
         return (e[:n], x[:n], tr) if trace else (e[:n], x[:n])

@@ -288,7 +288,14 @@ static void conf_increment(float *x, const float *p, float f, int T) {
 static int tri(int i, int j) { return i <= j ? i + j * (j + 1) / 2 : j + i * (i + 1) / 2; }
 
 /* bfgs (lib/bfgs.h:358-502) with fast_line_search; x in/out (7+T floats), g out (6+T); returns f0 */
+static float bfgs_impl(const gvo_field *F, const gvo_lig *L, float *x, float *g, int maxiters, const float *v, int *n_evals, float *x_last);
 float gvo_bfgs(const gvo_field *F, const gvo_lig *L, float *x, float *g, int maxiters, const float *v, int *n_evals) {
+  return bfgs_impl(F, L, x, g, maxiters, v, n_evals, 0);
+}
+/* x_last (nullable, 7+T): the conformation of the LAST function evaluation = what model::set left in the model's coordinates
+ * when quasi_newton returns. bfgs does not re-evaluate at the x it returns: after a line search that used up its 10 trials,
+ * or when x_orig is restored (:494-498), the model holds another conformation than the returned one. */
+static float bfgs_impl(const gvo_field *F, const gvo_lig *L, float *x, float *g, int maxiters, const float *v, int *n_evals, float *x_last) {
   const int T = L->n_seg - 1, n = 6 + T, nx = 7 + T;
   float *h = (float *)calloc((size_t)n * (n + 1) / 2, 4), *g_new = (float *)malloc(4 * n), *x_new = (float *)malloc(4 * nx),
         *p = (float *)malloc(4 * n), *y = (float *)malloc(4 * n), *mhy = (float *)malloc(4 * n), *x_orig = (float *)malloc(4 * nx),
@@ -296,6 +303,7 @@ float gvo_bfgs(const gvo_field *F, const gvo_lig *L, float *x, float *g, int max
   for (int i = 0; i < n; i++) h[tri(i, i)] = 1;
   int evals = 0;
   float f0 = gvo_lig_eval_deriv(F, L, x, v, g, 0); evals++;
+  if (x_last) memcpy(x_last, x, 4 * nx);
   const float f_orig = f0;
   memcpy(g_orig, g, 4 * n); memcpy(x_orig, x, 4 * nx);
   int didreset = 0;
@@ -307,6 +315,7 @@ float gvo_bfgs(const gvo_field *F, const gvo_lig *L, float *x, float *g, int max
       memcpy(x_new, x, 4 * nx);
       conf_increment(x_new, p, alpha, T);
       f1 = gvo_lig_eval_deriv(F, L, x_new, v, g_new, 0); evals++;
+      if (x_last) memcpy(x_last, x_new, 4 * nx);
       if (f1 - f0 < 0.0001f * alpha * pg) break;
       alpha *= 0.5f;
     }
@@ -408,9 +417,48 @@ static void mutate_conf(float *x, int T, float amplitude, float gr, uint32_t *s)
   x[7 + which - 2] = rng_fl(s, -PI_F, PI_F);
 }
 
-/* output container entry: e, conf[7+T], heavy coords.  Returns the number of entries kept (sorted by e). */
-int gvo_mc_run_traced(const gvo_field *F, const gvo_lig *L, const gvo_mc_params *P, const float *corner1, const float *corner2,
-                      uint32_t seed, float *out_e, float *out_conf /* [num_saved_mins][7+T] */, float *trace /* [num_steps] or NULL */) {
+/* model::gyration_radius (lib/model.cpp:1002-1014) of the conformation the model currently holds: heavy atoms, about the root origin */
+static float gyration_radius_of(const gvo_lig *L, const float *x_state, float *coords, float *so, float *sa) {
+  gvo_lig_set_conf(L, x_state, coords, so, sa);
+  float acc = 0; int cnt = 0;
+  for (int i = 0; i < L->n_atoms; i++) if (!is_h(L->type[i])) {
+    const float a = coords[3 * i] - x_state[0], b = coords[3 * i + 1] - x_state[1], c = coords[3 * i + 2] - x_state[2];
+    acc += a * a + b * b + c * c; cnt++;
+  }
+  return cnt > 0 ? sqrtf(acc / cnt) : 0;
+}
+float gvo_gyration_radius(const gvo_lig *L, const float *conf) {
+  float *coords = (float *)malloc(12 * L->n_atoms), *so = (float *)malloc(12 * L->n_seg), *sa = (float *)malloc(12 * L->n_seg);
+  const float r = gyration_radius_of(L, conf, coords, so, sa);
+  free(coords); free(so); free(sa);
+  return r;
+}
+/* cache::eval / non_cache::eval on given coordinates (update_energy, monte_carlo.cpp:44-47, evaluates whatever the model holds) */
+static float grid_energy_on(const gvo_field *F, const gvo_lig *L, const float *coords, float v1) {
+  float e = 0;
+  for (int i = 0; i < L->n_atoms; i++) {
+    const int t = L->type[i];
+    if (t < 0 || t >= 28 || is_h(t)) continue;
+    if (F->rec_xyz) e += gvo_noncache_atom(F, t, coords + 3 * i, v1, 0);
+    else e += gvo_grid_evaluate(F->grids[t], F->begin, F->end, F->n, coords + 3 * i, F->slope, v1, 0);
+  }
+  return e;
+}
+
+/* monte_carlo::operator() (lib/monte_carlo.cpp:99-148).  output container entry: e, conf[7+T], heavy coords; returns the number of
+ * entries kept (sorted by e).
+ *   init_conf  (nullable): start from this conformation with generator state `seed` instead of drawing conf::randomize here
+ *              (the reference's random_orientation draws normals; oracle/_ref hands over its own draw);
+ *   state_conf (nullable): MODEL-STATE mode, what the reference's code does to the letter: the model object keeps the coordinates
+ *              of the last conformation that was SET (by an evaluation inside quasi_newton or by an explicit m.set), and
+ *              (1) mutate_conf takes the gyration radius of THOSE coordinates (mutate.cpp:55, model.cpp:1002-1014),
+ *              (2) update_energy evaluates the grid on THOSE coordinates, which are the last line-search trial's, not always the
+ *                  returned conformation's (bfgs.h does not re-evaluate at the x it returns).
+ *              state_conf is the conformation the model holds on entry.  NULL = the stateless variant the device kernels
+ *              implement: constant gyration radius P->gyration_radius, energies re-evaluated at the returned conformation. */
+static int mc_impl(const gvo_field *F, const gvo_lig *L, const gvo_mc_params *P, const float *corner1, const float *corner2,
+                   uint32_t seed, float *out_e, float *out_conf /* [num_saved_mins][7+T] */, float *trace /* [num_steps] or NULL */,
+                   const float *init_conf, const float *state_conf) {
   const int T = L->n_seg - 1, nx = 7 + T, n = 6 + T, na = L->n_atoms;
   int nh = 0;
   for (int i = 0; i < na; i++) nh += !is_h(L->type[i]);
@@ -418,14 +466,25 @@ int gvo_mc_run_traced(const gvo_field *F, const gvo_lig *L, const gvo_mc_params 
   const float av[3] = {1000, 1000, 1000};
   float *tmp = (float *)malloc(4 * nx), *cand = (float *)malloc(4 * nx), *g = (float *)malloc(4 * n), *coords = (float *)malloc(12 * na);
   float *oc = (float *)malloc((size_t)4 * P->num_saved_mins * (3 * nh)), *hv = (float *)malloc(12 * nh);
+  float *xs = (float *)malloc(4 * nx), *so = (float *)malloc(12 * L->n_seg), *sa = (float *)malloc(12 * L->n_seg);
+  const int stateful = state_conf != 0;
+  if (stateful) memcpy(xs, state_conf, 4 * nx);
   int n_out = 0;
-  gvo_random_conf(&s, corner1, corner2, T, tmp);
+  if (init_conf) memcpy(tmp, init_conf, 4 * nx);
+  else gvo_random_conf(&s, corner1, corner2, T, tmp);
   float tmp_e = 0, best_e = kMax;
   for (int step = 0; step < P->num_steps; step++) {
     memcpy(cand, tmp, 4 * nx);
-    mutate_conf(cand, T, P->mutation_amplitude, P->gyration_radius, &s);
-    gvo_bfgs(F, L, cand, g, P->maxiters, P->hunt_cap, 0);
-    float cand_e = gvo_lig_eval_grid(F, L, cand, av[1], 0);
+    mutate_conf(cand, T, P->mutation_amplitude, stateful ? gyration_radius_of(L, xs, coords, so, sa) : P->gyration_radius, &s);
+    float cand_e;
+    if (stateful) {
+      bfgs_impl(F, L, cand, g, P->maxiters, P->hunt_cap, 0, xs);
+      gvo_lig_set_conf(L, xs, coords, so, sa);
+      cand_e = grid_energy_on(F, L, coords, av[1]);
+    } else {
+      gvo_bfgs(F, L, cand, g, P->maxiters, P->hunt_cap, 0);
+      cand_e = gvo_lig_eval_grid(F, L, cand, av[1], 0);
+    }
     int accept = step == 0 || cand_e < tmp_e;
     if (!accept) { /* metropolis_accept :38-42 */
       const float pr = exp_cr((tmp_e - cand_e) / P->temperature);
@@ -433,9 +492,18 @@ int gvo_mc_run_traced(const gvo_field *F, const gvo_lig *L, const gvo_mc_params 
     }
     if (accept) {
       memcpy(tmp, cand, 4 * nx); tmp_e = cand_e;
+      if (stateful) memcpy(xs, tmp, 4 * nx); /* m.set(tmp.c) :126 */
       if (tmp_e < best_e || n_out < P->num_saved_mins) {
-        gvo_bfgs(F, L, tmp, g, P->maxiters, av, 0);
-        tmp_e = gvo_lig_eval_grid(F, L, tmp, av[1], coords);
+        if (stateful) {
+          bfgs_impl(F, L, tmp, g, P->maxiters, av, 0, xs);
+          gvo_lig_set_conf(L, xs, coords, so, sa);
+          tmp_e = grid_energy_on(F, L, coords, av[1]);
+          memcpy(xs, tmp, 4 * nx);                 /* m.set(tmp.c) :134 */
+          gvo_lig_set_conf(L, tmp, coords, so, sa); /* get_heavy_atom_movable_coords :136 */
+        } else {
+          gvo_bfgs(F, L, tmp, g, P->maxiters, av, 0);
+          tmp_e = gvo_lig_eval_grid(F, L, tmp, av[1], coords);
+        }
         int k = 0;
         for (int i = 0; i < na; i++) if (!is_h(L->type[i])) { memcpy(hv + 3 * k, coords + 3 * i, 12); k++; }
         /* add_to_output_container, lib/coords.cpp:43-56 */
@@ -465,8 +533,16 @@ int gvo_mc_run_traced(const gvo_field *F, const gvo_lig *L, const gvo_mc_params 
     }
     if (trace) trace[step] = tmp_e; /* the chain's current energy (monte_carlo.cpp's tmp.e) after this step */
   }
-  free(tmp); free(cand); free(g); free(coords); free(oc); free(hv);
+  free(tmp); free(cand); free(g); free(coords); free(oc); free(hv); free(xs); free(so); free(sa);
   return n_out;
+}
+int gvo_mc_run_traced(const gvo_field *F, const gvo_lig *L, const gvo_mc_params *P, const float *corner1, const float *corner2,
+                      uint32_t seed, float *out_e, float *out_conf, float *trace) {
+  return mc_impl(F, L, P, corner1, corner2, seed, out_e, out_conf, trace, 0, 0);
+}
+int gvo_mc_run_ex(const gvo_field *F, const gvo_lig *L, const gvo_mc_params *P, const float *corner1, const float *corner2,
+                  uint32_t seed, float *out_e, float *out_conf, float *trace, const float *init_conf, const float *state_conf) {
+  return mc_impl(F, L, P, corner1, corner2, seed, out_e, out_conf, trace, init_conf, state_conf);
 }
 int gvo_mc_run(const gvo_field *F, const gvo_lig *L, const gvo_mc_params *P, const float *corner1, const float *corner2,
                uint32_t seed, float *out_e, float *out_conf) {

@@ -247,7 +247,8 @@ float gvo_naive_exact(const gvo_prec *p, int n_rec, const float *rec_xyz, const 
 }
 float gvo_num_tors_div(const gvo_prec *p, float e, float num_tors) { /* everything.h:804-809, smooth_div :52-56 */
   const float w = (float)(0.1 * ((double)p->w[5] + 1)); /* "fl w = 0.1 * (read_iterator(i) + 1)": double product, float store */
-  const float y = (float)(1 + (double)w * (double)num_tors / 5.0);
+  const float wnt = w * num_tors;                 /* "1 + w * in.num_tors / 5.0": fl * fl is a float product, the rest double */
+  const float y = (float)(1 + (double)wnt / 5.0);
   if (fabsf(e) < kEps) return 0;
   if (fabsf(y) < kEps) return (e * y > 0) ? kMaxFl : -kMaxFl;
   return e / y;

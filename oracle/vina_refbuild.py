@@ -63,7 +63,7 @@ def lib():
         L.gref_bfgs.argtypes = [_vp, _vp, C.c_int, _vp, _fp, C.c_int, _fp, _fp, _fp]
         L.gref_random_conf.argtypes = [_vp, C.c_uint32, _fp, _fp, _fp, C.POINTER(C.c_uint32)]
         L.gref_mc.argtypes = [_vp, _vp, C.c_int, _vp, _fp, _fp, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
-                              _fp, C.c_int, _fp, _fp, C.POINTER(C.c_int)]
+                              _fp, _fp, C.c_int, _fp, _fp, C.POINTER(C.c_int)]
         L.gref_container_replay.argtypes = [C.c_int, C.c_int, _fp, _fp, C.c_float, C.c_int, _fp, C.POINTER(C.c_int)]
         _lib = L
     return _lib
@@ -236,12 +236,14 @@ def random_conf(model, seed, c1, c2):
     return x, st.value
 
 
-def mc(model, sf, kind, grid, seed, c1, c2, num_steps, maxiters, num_saved_mins=50, temperature=1.2, amplitude=2.0, min_rmsd=1.0,
-       hunt_cap=(10, 10, 10)):
+def mc(model, sf, kind, grid, seed, c1, c2, num_steps, maxiters, state_conf, num_saved_mins=50, temperature=1.2, amplitude=2.0,
+       min_rmsd=1.0, hunt_cap=(10, 10, 10)):
+    """monte_carlo::operator(); state_conf = the conformation the model object holds when the chain starts"""
     e = np.zeros(num_saved_mins, np.float32); x = np.zeros((num_saved_mins, 7 + model.T), np.float32); n = C.c_int()
-    hc = np.ascontiguousarray(hunt_cap, np.float32)
+    hc = np.ascontiguousarray(hunt_cap, np.float32); sc = np.ascontiguousarray(state_conf, np.float32)
     _ok(lib().gref_mc(model.p, sf.p, kind, grid.p, _f(np.ascontiguousarray(c1, np.float32)), _f(np.ascontiguousarray(c2, np.float32)), seed,
-                      num_steps, maxiters, num_saved_mins, temperature, amplitude, min_rmsd, _f(hc), num_saved_mins, _f(e), _f(x), C.byref(n)))
+                      num_steps, maxiters, num_saved_mins, temperature, amplitude, min_rmsd, _f(hc), _f(sc), num_saved_mins, _f(e), _f(x),
+                      C.byref(n)))
     return e[:n.value], x[:n.value]
 
 
