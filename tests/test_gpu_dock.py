@@ -179,3 +179,58 @@ def test_unbuilt_grid_type_is_rejected(setup):
         v.set_ligand(lig)
     e, _ = v.eval_deriv(lig["conf0"][None])                            # the handle is still usable
     assert np.isfinite(e).all()
+
+
+def test_device_matches_reference_known_answers():
+    """The device kernels against KNOWN ANSWERS OF THE REFERENCE'S OWN CODE (tests/golden/vina_ref_kat.npz, produced by oracle/_ref =
+    the reference's Vina sources compiled where they lie; tests/golden/make_vina_ref_golden.py): affinity grids (cache::populate),
+    model::set, model::eval_deriv on the cache and on non_cache, quasi_newton, exact final scoring with num_tors_div.  north_star's
+    1e-6 where the pose is inside the grid; the device evaluates sin / cos / exp correctly rounded, the reference build called glibc's
+    sinf / cosf (last-bit differences in ~1 % of the arguments move atoms by <= 1e-5 A, and an atom outside the grid pays
+    1e3 x distance)."""
+    import os
+    from gnina_b200.vina import VinaScorer
+    k = np.load(os.path.join(os.path.dirname(__file__), "golden", "vina_ref_kat.npz"))
+    lig = {q: k["lig_" + q] for q in ("xyz0", "types", "seg_parent", "seg_begin", "seg_end", "pair_a", "pair_b", "conf0", "local_xyz",
+                                      "seg_rel_origin", "seg_rel_axis")}
+    lig["gyration_radius"] = 1.0
+    needed = sorted(set(int(t) for t in lig["types"] if t > 1))
+    v = VinaScorer()
+    v.set_receptor(k["rec_xyz"], k["rec_types"])
+    v.cache_build(k["begin"], k["end"], k["n"], needed)
+    v.set_ligand(lig)
+    for t, g in zip(k["grid_types"], k["grids"]):                       # V4
+        mine = v.cache_grid(int(t))
+        assert np.abs(mine - g).max() <= 1e-6 * max(1.0, np.abs(g).max())
+    X = k["confs"]
+    for name, caps in (("full", (1000, 1000, 1000)), ("hunt", (10, 1.5, 10))):   # V5-V8
+        e, g, c = v.eval_deriv(X, caps, coords=True)
+        assert np.abs(c - k["coords"]).max() <= 2e-5
+        inside = ((k["coords"] > k["begin"]) & (k["coords"] < k["end"])).all(axis=(1, 2))
+        er, gr = k["e_" + name], k["g_" + name]
+        tol = np.where(inside, 1e-6, 3e-5) * np.maximum(1.0, np.abs(er))
+        assert (np.abs(e - er) <= tol).all(), np.abs(e - er).max()
+        assert (np.abs(g - gr).max(1) <= 1e-5 * np.maximum(1.0, np.abs(gr).max(1))).all()
+        assert inside.sum() >= 10
+    for slope in (10.0, 1000.0):                                        # non_cache (refine_structure's field)
+        e, g = v.eval_deriv_noncache(k["nc_confs"], k["begin"], k["end"], slope=slope)
+        er, gr = k["nc_e_%d" % slope], k["nc_g_%d" % slope]
+        assert (np.abs(e - er) <= 3e-5 * np.maximum(1.0, np.abs(er))).all(), np.abs(e - er).max()
+        assert (np.abs(g - gr).max(1) <= 2e-5 * np.maximum(1.0, np.abs(gr).max(1))).all()
+    # V9: a last-bit difference (correctly rounded vs glibc sine) can flip one line-search comparison, after which two minimisations
+    # from a clashing random start walk apart; the CPU restatement shows the same sensitivity when it switches between the two
+    # sine flavours (94 / 88 % of these starts end at the reference's energy after 3 iterations, 47 / 50 % after 12), while with
+    # the SAME flavour it is bit-identical to the reference (tests/test_oracle_vina_golden.py) and the device to it (above)
+    for it, frac in ((3, 0.8), (12, 0.35)):
+        for name, caps in (("full", (1000, 1000, 1000)), ("hunt", (10, 10, 10))):
+            e, x, g, ne = v.bfgs(X[:32], it, caps)
+            er = k["bfgs%d_%s_e" % (it, name)]
+            same = np.abs(e - er) <= 1e-5 * np.maximum(1.0, np.abs(er))
+            assert same.mean() >= frac, (it, name, same.mean())
+    # V12
+    offs = np.arange(33, dtype=np.int32) * len(lig["types"])
+    ei, aff = v.score_exact(k["coords"][:32].reshape(-1, 3), np.tile(lig["types"], 32), offs, num_tors=k["num_tors"])
+    assert (np.abs(ei - k["exact_inter"]) <= 1e-6 * np.maximum(1.0, np.abs(k["exact_inter"]))).all()
+    # the reference's num_tors_div applied to the reference's intermolecular energy
+    assert (np.abs(aff - k["num_tors_div"]) <= 1e-6 * np.maximum(1.0, np.abs(k["num_tors_div"]))).all()
+    v.close()
