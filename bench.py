@@ -645,6 +645,36 @@ def timed(fn, reps=3):
     return (time.perf_counter() - t0) / reps
 
 
+def reference_vina_rates(lig, rec_xyz, rec_t, begin, end, ng, confs, mc_steps=40, mc_maxiters=12, mc_saved=8):
+    """The reference's OWN Vina code (oracle/_ref: gnina's sources compiled where they lie, one host thread) timed on the inputs of the
+    docking rows: cache::populate, model::eval_deriv, quasi_newton (12 iterations), monte_carlo::operator().  None where the
+    library is absent (it is built in the development container and travels with the snapshot)."""
+    from oracle import vina_refbuild as R
+    if not R.available():
+        return None
+    sf = R.RefScoring()
+    rm = R.RefModel(lig, rec_xyz, rec_t)
+    t0 = time.perf_counter()
+    cg = R.RefGrid.cache(sf, R.LINEAR, rm, begin, end, ng, 1e3)
+    needed = sorted(set(int(t) for t in lig["types"] if t > 1))
+    out = {"populate_point_types_per_s": float(np.prod(np.asarray(ng) + 1)) * len(needed) / (time.perf_counter() - t0)}
+    t0 = time.perf_counter()
+    for x in confs[:400]:
+        R.model_eval_deriv(rm, sf, R.LINEAR, cg, x)
+    out["eval_deriv_per_s"] = 400 / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    for x in confs[:40]:
+        R.bfgs(rm, sf, R.LINEAR, cg, x, 12)
+    out["bfgs12_per_s"] = 40 / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    for c in range(3):
+        R.mc(rm, sf, R.LINEAR, cg, 1000 + c, [-6, -6, -6], [6, 6, 6], mc_steps, mc_maxiters, lig["conf0"], num_saved_mins=mc_saved,
+             min_rmsd=0.5, hunt_cap=(10, 1.5, 10))
+    out["mc_steps_per_s"] = 3 * mc_steps / (time.perf_counter() - t0)
+    out["kind"] = "reference (gnina's own lib/*.cpp via oracle/_ref), 1 thread"
+    return out
+
+
 def rows_main():
     """python bench.py --rows: the hot-path rows that are not the headline, one JSON line per row:
     device throughput, and where cheap the CPU oracle timed beside it on a bounded sample (the cpu_baseline leg of these
@@ -765,8 +795,11 @@ def rows_main():
     for x in X[:200]:
         d.eval_deriv(x)
     cpu = 200 / (time.perf_counter() - t0)
+    ref = reference_vina_rates(lig, rec_xyz, rec_t, begin, end, ng, X)
     out.append({"row": "dock_eval_deriv (V5+V6+V7+V8)", "value": len(Xb) / dt, "unit": "eval_deriv/s", "cpu_oracle": cpu,
-                "cpu_sample": "200 conformations, scalar C", "ligand": "27 heavy atoms, 6 torsions, %d pairs" % len(lig["pair_a"])})
+                "cpu_sample": "200 conformations, scalar C", "ligand": "27 heavy atoms, 6 torsions, %d pairs" % len(lig["pair_a"]),
+                "cpu_reference": ref and ref["eval_deriv_per_s"], "cpu_reference_kind": ref and ref["kind"],
+                "cpu_reference_cache_populate_point_types_per_s": ref and ref["populate_point_types_per_s"]})
     res = {}
     def run_bfgs():
         res["ne"] = v.bfgs(Xb[:8192], 12)[3]
@@ -775,7 +808,8 @@ def rows_main():
     ner = sum(d.bfgs(x, 12)[3] for x in X[:40])
     cdt = time.perf_counter() - t0
     out.append({"row": "dock_bfgs 12 iterations (V9)", "value": 8192 / dt, "unit": "minimisations/s",
-                "device_eval_deriv_per_s": float(res["ne"].sum()) / dt, "cpu_oracle": 40 / cdt, "cpu_eval_deriv_per_s": ner / cdt})
+                "device_eval_deriv_per_s": float(res["ne"].sum()) / dt, "cpu_oracle": 40 / cdt, "cpu_eval_deriv_per_s": ner / cdt,
+                "cpu_reference": ref and ref["bfgs12_per_s"]})
     n_chains, steps = 4096, 40
     seeds = (np.arange(1, n_chains + 1, dtype=np.uint32) * 2654435761) & 0xFFFFFFFF
     dt = timed(lambda: v.mc(seeds, [-6, -6, -6], [6, 6, 6], steps, 12, 8), reps=1)
@@ -785,7 +819,8 @@ def rows_main():
     cpu = 3 * steps / (time.perf_counter() - t0)
     out.append({"row": "dock_monte_carlo chains (V10+V11)", "value": n_chains * steps / dt, "unit": "MC steps/s",
                 "chains": n_chains, "steps_per_chain": steps, "ligands_per_s_at_exhaustiveness_64": n_chains / 64 / dt,
-                "cpu_oracle": cpu, "cpu_sample": "3 chains, scalar C, 1 thread"})
+                "cpu_oracle": cpu, "cpu_sample": "3 chains, scalar C, 1 thread", "cpu_reference": ref and ref["mc_steps_per_s"],
+                "cpu_reference_kind": ref and ref["kind"]})
     # --- config 3 glue: cache build -> 64 chains -> merge -> CNN rescoring -> exact affinity -> ranked modes ---
     from gnina_b200 import docking
     cs = CNNScorer(["crossdock_default2018"], precision=1)
@@ -836,7 +871,9 @@ def rows_main():
                 "ligands": n_full, "in_flight": workers_full, "mc_steps_per_chain_mean": float(np.mean(steps_ref)),
                 "mc_steps_per_s": mc_steps / dt, "seconds_for_1k_ligands": 1000.0 * dt / n_full, "modes_out_mean": float(np.mean([len(r) for r in res])),
                 "cpu_oracle_mc_steps_per_s_1_thread": cpu_steps_per_s,
-                "cpu_oracle_ligands_per_s_per_thread": cpu_steps_per_s / (64 * float(np.mean(steps_ref)))})
+                "cpu_oracle_ligands_per_s_per_thread": cpu_steps_per_s / (64 * float(np.mean(steps_ref))),
+                "cpu_reference_mc_steps_per_s_1_thread": ref and ref["mc_steps_per_s"],
+                "cpu_reference_ligands_per_s_per_thread": ref and ref["mc_steps_per_s"] / (64 * float(np.mean(steps_ref)))})
     for r in out:
         print(json.dumps(r))
 

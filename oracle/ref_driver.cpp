@@ -142,6 +142,17 @@ extern "C" {
 
 const char* gref_last_error() { return g_err.c_str(); }
 
+// ---- G0: the smina type table (lib/atom_constants.h:45-133, the `data` array the typers and xs_radius() read) ------------------
+// flags: bit 0 xs_hydrophobe, 1 xs_donor, 2 xs_acceptor, 3 ad_heteroatom; returns the type string_to_smina_type(name) maps back to
+int gref_type_info(int t, char* name64, float* xs_radius_out, float* covalent_radius_out, int* flags) {
+  const smina_atom_type::info& d = smina_atom_type::data[t];
+  std::strncpy(name64, d.smina_name, 63); name64[63] = 0;
+  *xs_radius_out = xs_radius((smt)t);
+  *covalent_radius_out = covalent_radius((smt)t);
+  *flags = (d.xs_hydrophobe ? 1 : 0) | (d.xs_donor ? 2 : 0) | (d.xs_acceptor ? 4 : 0) | (d.ad_heteroatom ? 8 : 0);
+  return (int)string_to_smina_type(d.smina_name);
+}
+
 // ---- scoring function: the default Vina terms and weights of main/main.cpp:1324-1329 (= test_cache.cu:30-36) ----------------
 void* gref_sf_create(float factor_linear, float factor_splines) {
   RefSF* s = new RefSF;

@@ -33,6 +33,7 @@ def lib():
     if _lib is None:
         L = C.CDLL(_SO, mode=os.RTLD_NOW)
         L.gref_last_error.restype = C.c_char_p
+        L.gref_type_info.argtypes = [C.c_int, C.c_char_p, _fp, _fp, _ip]
         L.gref_sf_create.argtypes = [C.c_float, C.c_float]; L.gref_sf_create.restype = _vp
         L.gref_sf_destroy.argtypes = [_vp]
         L.gref_cutoff_sqr.argtypes = [_vp]; L.gref_cutoff_sqr.restype = C.c_float
@@ -75,6 +76,13 @@ def _ok(rc):
 
 
 LINEAR, SPLINES, EXACT = 0, 1, 2
+
+
+def type_info(t):
+    """smina type t -> (name, xs_radius, covalent_radius, flags: 1 hydrophobe | 2 donor | 4 acceptor | 8 heteroatom, round-trip type)"""
+    nm = C.create_string_buffer(64); r = np.empty(2, np.float32); fl = np.empty(1, np.int32)
+    back = lib().gref_type_info(t, nm, _f(r[:1]), _f(r[1:]), _i(fl))
+    return nm.value.decode(), float(r[0]), float(r[1]), int(fl[0]), back
 
 
 class RefScoring:

@@ -42,6 +42,12 @@ def main():
         out["lig_" + k] = np.asarray(lig[k])
     out["lig_local_xyz"], out["lig_seg_rel_origin"], out["lig_seg_rel_axis"] = lo, ro, ra
 
+    # G0: the smina type table (names, xs_radius, donor / acceptor / hydrophobe flags) as the reference's `data` array holds it
+    ti = [R.type_info(t) for t in range(28)]
+    assert all(back == t for t, (_, _, _, _, back) in enumerate(ti))
+    out["type_names"] = np.array([a for a, _, _, _, _ in ti]); out["type_xs_radius"] = np.float32([b for _, b, _, _, _ in ti])
+    out["type_flags"] = np.int32([d for _, _, _, d, _ in ti])
+
     # V1 / V2 / V3 / exact: terms and tables at random (t1, t2, r)
     K = 4000
     t12 = rs.randint(0, 28, (K, 2)).astype(np.int32)

@@ -61,6 +61,13 @@ def test_voxeliser_matches_oracle(kat, name):
     from oracle import gridmaker as gm
     rc, rr = gm.type_atoms(lt, om.lig_t2c, om.n_rec)
     assert np.array_equal(ch, rc) and np.array_equal(rad, rr)
+    # ... and its radii are the reference's own table (xs_radius of every smina type as oracle/_ref reports it)
+    import os
+    ref_tab = np.load(os.path.join(os.path.dirname(__file__), "golden", "vina_ref_kat.npz"))["type_xs_radius"]
+    all_t = np.arange(28, dtype=np.int32)
+    for is_lig in (False, True):
+        ch28, rad28 = s.type_atoms(all_t, is_lig)
+        assert np.array_equal(rad28[ch28 >= 0], ref_tab[ch28 >= 0])
 
 
 @pytest.mark.parametrize("name,tol_p,tol_a", [("crossdock_default2018", 2e-5, 1e-4), ("dense_1_3", 2e-5, 1e-4),

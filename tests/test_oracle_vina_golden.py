@@ -47,6 +47,21 @@ def libm():
     vlib().gvo_use_libm(0)
 
 
+def test_smina_type_table(kat):
+    """G0: names, xs_radius and the donor / acceptor / hydrophobe flags of the 28 smina types (lib/atom_constants.h:101-133) in the
+    voxeliser oracle's typing and in the Vina oracle's terms"""
+    import ctypes as C
+    from oracle import gridmaker as gm
+    for t in range(28):
+        assert gm.lib().gbo_smina_name(t).decode() == str(kat["type_names"][t])
+        assert np.float32(gm.lib().gbo_smina_radius(t)) == kat["type_xs_radius"][t]
+        r, h, d, a = C.c_float(), C.c_int(), C.c_int(), C.c_int()
+        vlib().gvo_type_props.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        vlib().gvo_type_props(t, C.byref(r), C.byref(h), C.byref(d), C.byref(a))
+        f = int(kat["type_flags"][t])
+        assert np.float32(r.value) == kat["type_xs_radius"][t] and (h.value, d.value, a.value) == (f & 1, (f >> 1) & 1, (f >> 2) & 1)
+
+
 def test_terms_and_tables_are_bit_identical(kat, vo):
     """V1 weighted_terms::eval_fast, V2 precalculate_linear (eval_fast and eval_deriv), precalculate_exact"""
     w = np.array([-0.035579, -0.005156, 0.840245, -0.035069, -0.587439], np.float32)
