@@ -362,6 +362,50 @@ __global__ void __launch_bounds__(128) naive_exact_kernel(const float4* __restri
   atom_e[i] = this_e;
 }
 
+// non_cache::eval (lib/non_cache.cpp:52-83): the intermolecular energy of the DOCKING branch's final score (main/main.cpp:340-344:
+// eval_adjusted with ig = nc_new).  Per heavy ligand atom: coordinates clamped to the search box (check_bounds :32-50), pair terms
+// from the search's precalculate through precalculate::eval = eval_fast (the piecewise-constant table the affinity grids are built
+// from), receptor atoms in index order, curl, + slope x distance outside the box.
+__global__ void __launch_bounds__(128) noncache_eval_kernel(const float4* __restrict__ lig, int n_atoms, const float4* __restrict__ rec,
+                                                            int n_rec, const float* __restrict__ fast, int n_samples, float factor,
+                                                            float cutoff_sqr, float v, float slope, float b0, float b1, float b2,
+                                                            float e0, float e1, float e2, float* __restrict__ atom_e) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_atoms) return;
+  const float4 a = lig[i];
+  const int t1 = (int)a.w;
+  float out = 0.f;
+  if (t1 >= 2 && t1 < kNumSminaTypes) {
+    const float c[3] = {a.x, a.y, a.z}, bb[3] = {b0, b1, b2}, be[3] = {e0, e1, e2};
+    float adj[3], pen = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      adj[j] = c[j];
+      if (c[j] < bb[j]) { adj[j] = bb[j]; pen = __fadd_rn(pen, fabsf(c[j] - bb[j])); }
+      else if (c[j] > be[j]) { adj[j] = be[j]; pen = __fadd_rn(pen, fabsf(c[j] - be[j])); }
+    }
+    pen = __fmul_rn(pen, slope);
+    float this_e = 0.f;
+    for (int j = 0; j < n_rec; j++) {
+      const float4 b = rec[j];
+      const int t2 = (int)b.w;
+      if (t2 < 2 || t2 >= kNumSminaTypes) continue;
+      const float dx = adj[0] - b.x, dy = adj[1] - b.y, dz = adj[2] - b.z;
+      const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      if (r2 < cutoff_sqr) {
+        const int pair = t1 <= t2 ? t1 + t2 * (t2 + 1) / 2 : t2 + t1 * (t1 + 1) / 2;
+        this_e = __fadd_rn(this_e, fast[(size_t)pair * n_samples + (size_t)(__fmul_rn(factor, r2))]);
+      }
+    }
+    if (this_e > 0 && v < 0.1f * 3.402823466e+38f) {
+      const float tmp = (v < 1.1920929e-07f) ? 0.f : __fdiv_rn(v, __fadd_rn(v, this_e));
+      this_e = __fmul_rn(this_e, tmp);
+    }
+    out = __fadd_rn(this_e, pen);
+  }
+  atom_e[i] = out;
+}
+
 }  // namespace gb
 
 using namespace gb;
@@ -538,6 +582,25 @@ int gb_vina_cache_eval(gb_vina* h, const float* lig_xyz, const int32_t* lig_type
   GBV_END
 }
 
+// poses -> per-pose intermolecular energy (ordered atom sum) -> num_tors_div; mode 0 = naive_non_cache with the exact terms
+// (--score_only / --minimize, main/main.cpp:233-236,282-285), mode 1 = non_cache with the search's tables (docking, :340-344)
+static void score_poses_common(Vina& v, const float* lig_xyz, const int32_t* lig_type, const int32_t* pose_offsets, int n_poses,
+                               const float* num_tors, float vcap, int mode, float slope, const float* bb, const float* be, float* e_inter,
+                               float* affinity);
+
+int gb_vina_score_noncache(gb_vina* h, const float* lig_xyz, const int32_t* lig_type, const int32_t* pose_offsets, int n_poses,
+                           const float* num_tors, float vcap, float slope, const float* box_begin, const float* box_end, float* e_inter,
+                           float* affinity) {
+  GBV_BEGIN
+  GB_CHECK(h && n_poses >= 0 && box_begin && box_end, "bad arguments");
+  Vina& v = h->v;
+  GB_CUDA(cudaSetDevice(v.device));
+  GB_CHECK(v.d_rec && v.n_rec > 0, "gb_vina_set_receptor has not been called");
+  if (n_poses == 0) return GB_OK;
+  score_poses_common(v, lig_xyz, lig_type, pose_offsets, n_poses, num_tors, vcap, 1, slope, box_begin, box_end, e_inter, affinity);
+  GBV_END
+}
+
 int gb_vina_score_exact(gb_vina* h, const float* lig_xyz, const int32_t* lig_type, const int32_t* pose_offsets, int n_poses,
                         const float* num_tors, float vcap, float* e_inter, float* affinity) {
   GBV_BEGIN
@@ -545,10 +608,23 @@ int gb_vina_score_exact(gb_vina* h, const float* lig_xyz, const int32_t* lig_typ
   Vina& v = h->v;
   GB_CUDA(cudaSetDevice(v.device));
   if (n_poses == 0) return GB_OK;
+  score_poses_common(v, lig_xyz, lig_type, pose_offsets, n_poses, num_tors, vcap, 0, 0.f, nullptr, nullptr, e_inter, affinity);
+  GBV_END
+}
+
+}  // extern "C"
+
+static void score_poses_common(Vina& v, const float* lig_xyz, const int32_t* lig_type, const int32_t* pose_offsets, int n_poses,
+                               const float* num_tors, float vcap, int mode, float slope, const float* bb, const float* be, float* e_inter,
+                               float* affinity) {
   stage_poses(v, lig_xyz, lig_type, pose_offsets, n_poses);
   const int n_atoms = pose_offsets[n_poses];
-  if (n_atoms) naive_exact_kernel<<<(n_atoms + 127) / 128, 128, 0, v.stream>>>(v.d_lig, n_atoms, v.d_rec, v.n_rec, v.cutoff_sqr,
-                                                                               vcap, v.d_atom_e);
+  if (n_atoms && mode == 0)
+    naive_exact_kernel<<<(n_atoms + 127) / 128, 128, 0, v.stream>>>(v.d_lig, n_atoms, v.d_rec, v.n_rec, v.cutoff_sqr, vcap, v.d_atom_e);
+  if (n_atoms && mode == 1)
+    noncache_eval_kernel<<<(n_atoms + 127) / 128, 128, 0, v.stream>>>(v.d_lig, n_atoms, v.d_rec, v.n_rec, v.d_fast, v.n, v.factor,
+                                                                     v.cutoff_sqr, vcap, slope, bb[0], bb[1], bb[2], be[0], be[1], be[2],
+                                                                     v.d_atom_e);
   pose_sum_kernel<<<(n_poses + 127) / 128, 128, 0, v.stream>>>(v.d_atom_e, v.d_off, n_poses, v.d_pose_e);
   std::vector<float> e(n_poses);
   GB_CUDA(cudaMemcpyAsync(e.data(), v.d_pose_e, (size_t)n_poses * sizeof(float), cudaMemcpyDeviceToHost, v.stream));
@@ -567,10 +643,7 @@ int gb_vina_score_exact(gb_vina* h, const float* lig_xyz, const int32_t* lig_typ
       affinity[p] = std::fabs(x) < eps ? 0.f : (std::fabs(y) < eps ? ((x * y > 0) ? maxfl : -maxfl) : x / y);
     }
   }
-  GBV_END
 }
-
-}  // extern "C"
 
 // =================================================================================================================
 // Docking inner loop as a batched kernel: ONE WARP PER CHAIN / CONFORMATION.

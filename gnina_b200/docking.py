@@ -94,19 +94,31 @@ def reference_num_steps(n_movable_atoms, n_dof):
 MAX_FL = 3.4028234663852886e+38
 
 
+def search_box(corner1, corner2, granularity=0.375):
+    """setup_grid_dims (main/main.cpp:625-634): the search box = ONE grid_dims object that serves as the affinity-grid extent, as the
+    box conf::randomize draws from (corner1/2 = gd begin/end, :438-439) and as non_cache's check_bounds box: per axis
+    n = ceil(size / 0.375) intervals, real_span = 0.375 n centred on the requested centre.  float32 like the reference.
+    -> (begin[3], end[3], n[3])"""
+    c1, c2 = np.asarray(corner1, np.float32), np.asarray(corner2, np.float32)
+    center, span = (c1 + c2) / np.float32(2), c2 - c1
+    n = np.ceil(span / np.float32(granularity)).astype(np.int32)
+    real = np.float32(granularity) * n.astype(np.float32)
+    begin = (center - real / np.float32(2)).astype(np.float32)
+    return begin, (begin + real).astype(np.float32), n
+
+
 def dock_ligand(vina, cnn, lig, corner1, corner2, exhaustiveness=8, seed=1, num_steps=None, maxiters=None,
-                num_saved_mins=50, num_modes=9, out_min_rmsd=1.0, sort_order="cnnscore", grid_spacing=0.375,
-                grid_margin=4.0, refine=True):
-    """vina: VinaScorer with the receptor set; cnn: CNNScorer with the same receptor set; lig: ligand topology dict.
+                num_saved_mins=50, num_modes=9, out_min_rmsd=1.0, sort_order="cnnscore", grid_spacing=0.375, refine=True):
+    """vina: VinaScorer with the receptor set; cnn: CNNScorer with the same receptor set; lig: ligand topology dict; corner1/2: the
+    requested search box (what --center / --size or --autobox_ligand + autobox_add describe).
     -> list of dicts (conf, coords, e = final Vina affinity, search_e, cnnscore, cnnaffinity, cnnvariance), ranked."""
     types = np.asarray(lig["types"], np.int32)
-    corner1 = np.asarray(corner1, np.float32); corner2 = np.asarray(corner2, np.float32)
     vina.set_ligand(lig)
     T = vina.T
-    # grid over the search box plus a margin, granularity 0.375 A (main.cpp:622)
-    begin = corner1 - grid_margin
-    n = np.ceil((corner2 + grid_margin - begin) / grid_spacing).astype(np.int32)
-    end = begin + n * grid_spacing
+    # ONE box for the affinity grids, the random starts and the out-of-box penalties, as in the reference (search_box above): an atom
+    # that leaves the search box pays slope x distance at once, in the grid term of the search and in non_cache afterwards
+    begin, end, n = search_box(corner1, corner2, grid_spacing)
+    corner1, corner2 = begin, end
     vina.cache_build(begin.tolist(), end.tolist(), n.tolist(), sorted(set(int(t) for t in types if t > 1)))
     if num_steps is None:
         num_steps = reference_num_steps(len(types), 6 + T)
@@ -130,13 +142,15 @@ def dock_ligand(vina, cnn, lig, corner1, corner2, exhaustiveness=8, seed=1, num_
     else:
         e_ref, ok = np.array([m["e"] for m in merged], np.float32), np.ones(len(merged), bool)
     _, _, all_coords = vina.eval_deriv(confs, coords=True)
-    # one CNN batch call and one exact-scoring call over all kept poses
+    # one CNN batch call and one final-scoring call over all kept poses
     xyz = all_coords.reshape(-1, 3).astype(np.float32)
     offs = (np.arange(len(merged) + 1) * len(types)).astype(np.int32)
     tt = np.tile(types, len(merged))
     sc, aff, _, var = cnn.score_batch(xyz, tt, offs)
     num_tors = float(lig.get("num_tors", T))                        # conf_independent_inputs (lib/terms.cpp:74-106)
-    _, affin = vina.score_exact(xyz, tt, offs, num_tors=np.full(len(merged), num_tors, np.float32))
+    # the docking branch scores with eval_adjusted(..., ig = nc_new) = non_cache::eval on the search box with the search's tables
+    # (main/main.cpp:340-344), not with the exact terms of --score_only
+    _, affin = vina.score_noncache(xyz, tt, offs, corner1, corner2, num_tors=np.full(len(merged), num_tors, np.float32))
     for i, m in enumerate(merged):
         m["search_e"] = m["e"]
         m["conf"] = confs[i]; m["all_coords"] = all_coords[i]; m["coords"] = all_coords[i][heavy]

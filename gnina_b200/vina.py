@@ -61,6 +61,17 @@ class VinaScorer:
         capi.check(capi.lib().gb_vina_score_exact(self._h, _fp(x), _ip(t), _ip(o), n, _fp(nt), v, _fp(e), _fp(a)))
         return e, a
 
+    def score_noncache(self, lig_xyz, lig_types, pose_offsets, box_begin, box_end, num_tors=None, v=1000.0, slope=1e3):
+        """the docking branch's final score (main/main.cpp:340-344): non_cache::eval on the search box with the search's tables, then
+        num_tors_div -> (intermolecular energy, Affinity) per pose"""
+        x, t, o = self._poses(lig_xyz, lig_types, pose_offsets)
+        n = len(o) - 1
+        nt = None if num_tors is None else np.ascontiguousarray(num_tors, np.float32)
+        b, en = np.ascontiguousarray(box_begin, np.float32), np.ascontiguousarray(box_end, np.float32)
+        e, a = np.empty(n, np.float32), np.empty(n, np.float32)
+        capi.check(capi.lib().gb_vina_score_noncache(self._h, _fp(x), _ip(t), _ip(o), n, _fp(nt), v, slope, _fp(b), _fp(en), _fp(e), _fp(a)))
+        return e, a
+
     def spline_table(self, t1, t2):
         n = capi.lib().gb_vina_spline_size(self._h)
         out = np.empty((n, 4), np.float32)

@@ -191,6 +191,13 @@ int gb_vina_cache_eval(gb_vina* h, const float* lig_xyz, const int32_t* lig_type
  * conf_independent_inputs computes it (lib/terms.cpp:74-106); e_inter / affinity: n_poses floats (nullable). */
 int gb_vina_score_exact(gb_vina* h, const float* lig_xyz, const int32_t* lig_type, const int32_t* pose_offsets, int n_poses,
                         const float* num_tors, float v, float* e_inter, float* affinity);
+/* The DOCKING branch's final score (main/main.cpp:340-344): eval_adjusted with ig = nc_new = non_cache(grid_cache, gd, &prec, slope),
+ * i.e. non_cache::eval (lib/non_cache.cpp:52-83) -- coordinates clamped to the search box [box_begin, box_end], pair terms from the
+ * SEARCH's precalculate through precalculate::eval (= eval_fast, the piecewise-constant table), curl with vcap, + slope x distance
+ * outside the box -- then num_tors_div.  (--score_only and --minimize use gb_vina_score_exact: naive_non_cache + exact terms.) */
+int gb_vina_score_noncache(gb_vina* h, const float* lig_xyz, const int32_t* lig_type, const int32_t* pose_offsets, int n_poses,
+                           const float* num_tors, float vcap, float slope, const float* box_begin, const float* box_end, float* e_inter,
+                           float* affinity);
 
 /* ---- docking inner loop: conformation -> energy/gradient, BFGS, Monte-Carlo chains (one warp per chain) --------
  * The ligand as gnina's model holds it (lib/tree.h, lib/model.h): atoms in the local frame of their torsion-tree

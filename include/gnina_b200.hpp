@@ -399,6 +399,14 @@ class VinaScorer {
     return a;
   }
 
+  // the docking branch's final score (main/main.cpp:340-344): non_cache::eval on the search box with the search's tables + num_tors_div
+  std::vector<float> docking_affinity(const float* xyz, const int32_t* t, const int32_t* offs, int n_poses, const float* num_tors,
+                                      const float box_begin[3], const float box_end[3], float v = 1000.f, float slope = 1e3f) {
+    std::vector<float> a(n_poses);
+    check(gb_vina_score_noncache(h_, xyz, t, offs, n_poses, num_tors, v, slope, box_begin, box_end, nullptr, a.data()));
+    return a;
+  }
+
   // ---- docking inner loop (model::set / eval_deriv, quasi_newton, parallel_mc) --------------------------------------
   void set_ligand(const gb_ligand_topology& t) {
     check(gb_vina_set_ligand(h_, &t));

@@ -24,6 +24,8 @@ def lib():
         L.gvo_cache_eval.argtypes = [C.POINTER(_fp), _fp, _fp, _ip, C.c_int, _fp, _ip, C.c_float, C.c_float, _fp]
         L.gvo_cache_eval.restype = C.c_float
         L.gvo_naive_exact.argtypes = [_vp, C.c_int, _fp, _ip, C.c_int, _fp, _ip, C.c_float]; L.gvo_naive_exact.restype = C.c_float
+        L.gvo_noncache_eval.argtypes = [_vp, C.c_int, _fp, _ip, C.c_int, _fp, _ip, C.c_float, C.c_float, _fp, _fp]
+        L.gvo_noncache_eval.restype = C.c_float
         L.gvo_num_tors_div.argtypes = [_vp, C.c_float, C.c_float]; L.gvo_num_tors_div.restype = C.c_float
         _ready = True
     return L
@@ -106,5 +108,12 @@ class VinaOracle:
         rx, rt = np.ascontiguousarray(rec_xyz, np.float32), np.ascontiguousarray(rec_types, np.int32)
         lx, lt = np.ascontiguousarray(lig_xyz, np.float32), np.ascontiguousarray(lig_types, np.int32)
         return lib().gvo_naive_exact(self.p, len(rt), _f(rx), _i(rt), len(lt), _f(lx), _i(lt), v)
+
+    def noncache_eval(self, rec_xyz, rec_types, lig_xyz, lig_types, begin, end, slope=1e3, v=1000.0):
+        """non_cache::eval (lib/non_cache.cpp:52-83): the docking branch's intermolecular energy (table terms, box clamp + penalty)"""
+        rx, rt = np.ascontiguousarray(rec_xyz, np.float32), np.ascontiguousarray(rec_types, np.int32)
+        lx, lt = np.ascontiguousarray(lig_xyz, np.float32), np.ascontiguousarray(lig_types, np.int32)
+        b, e = np.ascontiguousarray(begin, np.float32), np.ascontiguousarray(end, np.float32)
+        return lib().gvo_noncache_eval(self.p, len(rt), _f(rx), _i(rt), len(lt), _f(lx), _i(lt), v, slope, _f(b), _f(e))
 
     def num_tors_div(self, e, num_tors): return lib().gvo_num_tors_div(self.p, e, num_tors)

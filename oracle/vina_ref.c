@@ -245,6 +245,37 @@ float gvo_naive_exact(const gvo_prec *p, int n_rec, const float *rec_xyz, const 
   }
   return e;
 }
+/* non_cache::eval (lib/non_cache.cpp:52-83) -- what the DOCKING branch's final "Affinity" goes through (main/main.cpp:340-344:
+ * eval_adjusted with ig = nc_new = non_cache(grid_cache, gd, &prec, slope)): per heavy ligand atom the coordinates are clamped to the
+ * box (check_bounds :32-50), the pair terms come from the search's precalculate through precalculate::eval = eval_FAST (the
+ * piecewise-constant table, precalculate.h:70-74,90-95 -- not the exact terms of --score_only), curl, plus slope x distance outside. */
+float gvo_noncache_eval(const gvo_prec *p, int n_rec, const float *rec_xyz, const int32_t *rec_type, int n_lig, const float *lig_xyz,
+                        const int32_t *lig_type, float v, float slope, const float *begin, const float *end) {
+  float e = 0;
+  for (int i = 0; i < n_lig; i++) {
+    const int t1 = lig_type[i];
+    if (t1 < 0 || t1 >= NT || is_h(t1)) continue;
+    float adj[3], pen = 0;
+    for (int j = 0; j < 3; j++) {
+      const float a = lig_xyz[3 * i + j];
+      adj[j] = a;
+      if (a < begin[j]) { adj[j] = begin[j]; pen += fabsf(a - begin[j]); }
+      else if (a > end[j]) { adj[j] = end[j]; pen += fabsf(a - end[j]); }
+    }
+    pen *= slope;
+    float this_e = 0;
+    for (int j = 0; j < n_rec; j++) {
+      const int t2 = rec_type[j];
+      if (t2 < 0 || t2 >= NT || is_h(t2)) continue; /* the szv_grid lists hold heavy receptor atoms (szv_grid.h:84-93) */
+      const float dx = adj[0] - rec_xyz[3 * j], dy = adj[1] - rec_xyz[3 * j + 1], dz = adj[2] - rec_xyz[3 * j + 2];
+      const float r2 = dx * dx + dy * dy + dz * dz;
+      if (r2 < p->cutoff_sqr) this_e += gvo_prec_eval_fast(p, t1, t2, r2);
+    }
+    if (this_e > 0 && not_max(v)) { float tmp = (v < kEps) ? 0 : (v / (v + this_e)); this_e *= tmp; }
+    e += this_e + pen;
+  }
+  return e;
+}
 float gvo_num_tors_div(const gvo_prec *p, float e, float num_tors) { /* everything.h:804-809, smooth_div :52-56 */
   const float w = (float)(0.1 * ((double)p->w[5] + 1)); /* "fl w = 0.1 * (read_iterator(i) + 1)": double product, float store */
   const float wnt = w * num_tors;                 /* "1 + w * in.num_tors / 5.0": fl * fl is a float product, the rest double */

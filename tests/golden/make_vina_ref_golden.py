@@ -80,10 +80,12 @@ def main():
         nc = R.RefGrid.non_cache(sf, R.LINEAR, rm, BEGIN, END, N, slope)
         eg = [R.model_eval_deriv(rm, sf, R.LINEAR, nc, x, (1000, 1000, 1000)) for x in Xn]
         out["nc_e_%d" % slope] = np.float32([a for a, _ in eg]); out["nc_g_%d" % slope] = np.stack([b for _, b in eg])
-        w = []
+        w, ev = [], []
         for x in Xn:
-            rm.set(x); w.append(nc.within())
+            rm.set(x); w.append(nc.within()); ev.append(nc.eval(1000.0))
         out["nc_within"] = np.array(w)
+        out["nc_eval_%d" % slope] = np.float32(ev)      # non_cache::eval: the docking branch's final intermolecular energy
+    out["nc_coords"] = np.stack([rm.set(x) for x in Xn])
     # V9: quasi_newton (bfgs.h, fast line search)
     Xb = X[:32]
     for it in (3, 12):

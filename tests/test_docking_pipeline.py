@@ -48,6 +48,15 @@ def test_merge_chains_uses_rmsd_2_and_remove_redundant_is_strict():
     assert len(docking.remove_redundant(items, min_rmsd=d01 * 0.99)) == 3
 
 
+def test_search_box_is_the_reference_grid_dims():
+    """setup_grid_dims (main/main.cpp:625-634): n = ceil(size / 0.375), the real span is centred on the requested centre"""
+    b, e, n = docking.search_box([-6, -6, -6], [6, 6, 6])
+    assert n.tolist() == [32, 32, 32] and np.allclose(b, -6) and np.allclose(e, 6)
+    b, e, n = docking.search_box([1.0, -2.0, 0.5], [11.3, 9.0, 16.1])
+    assert n.tolist() == [28, 30, 42]
+    assert np.allclose((b + e) / 2, [6.15, 3.5, 8.3], atol=1e-5) and np.allclose(e - b, 0.375 * n, atol=1e-5)
+
+
 def test_reference_num_steps():
     assert docking.reference_num_steps(27, 12) == 70 * 3 * (50 + 27 + 120) // 2
 
@@ -74,11 +83,15 @@ def test_dock_and_rescore_pipeline():
         one = c.score_batch(p["all_coords"], lig["types"], [0, len(lig["types"])])
         assert abs(one[0][0] - p["cnnscore"]) < 1e-6
         if p["within"]:
-            e_aff = v.score_exact(p["all_coords"], lig["types"], [0, len(lig["types"])], num_tors=np.array([v.T], np.float32))[1][0]
+            b, e_, _ = docking.search_box([-6, -6, -6], [6, 6, 6])
+            e_aff = v.score_noncache(p["all_coords"], lig["types"], [0, len(lig["types"])], b, e_, num_tors=np.array([v.T], np.float32))[1][0]
             assert abs(e_aff - p["e"]) < 1e-5 * max(1.0, abs(p["e"]))
+            # the exact terms of --score_only give nearly the same number (tables vs closed forms)
+            e_ex = v.score_exact(p["all_coords"], lig["types"], [0, len(lig["types"])], num_tors=np.array([v.T], np.float32))[1][0]
+            assert abs(e_ex - p["e"]) < 0.05 * max(1.0, abs(p["e"]))
             # refine_structure left every heavy atom inside the search box (non_cache::within)
             hv = p["coords"]
-            assert (hv >= -6 - 1e-3).all() and (hv <= 6 + 1e-3).all()
+            assert (hv >= b - 1e-3).all() and (hv <= e_ + 1e-3).all()
     again = docking.dock_ligand(v, c, lig, [-6, -6, -6], [6, 6, 6], exhaustiveness=8, seed=3, num_steps=60, num_saved_mins=20)
     assert [p["cnnscore"] for p in again] == sc                                            # same seed, same result
 

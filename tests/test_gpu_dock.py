@@ -217,6 +217,13 @@ def test_device_matches_reference_known_answers():
         er, gr = k["nc_e_%d" % slope], k["nc_g_%d" % slope]
         assert (np.abs(e - er) <= 3e-5 * np.maximum(1.0, np.abs(er))).all(), np.abs(e - er).max()
         assert (np.abs(g - gr).max(1) <= 2e-5 * np.maximum(1.0, np.abs(gr).max(1))).all()
+    # non_cache::eval on the reference's own coordinates: the docking branch's final intermolecular energy
+    no = np.arange(len(k["nc_coords"]) + 1, dtype=np.int32) * len(lig["types"])
+    for slope in (10.0, 1000.0):
+        e, _ = v.score_noncache(k["nc_coords"].reshape(-1, 3), np.tile(lig["types"], len(k["nc_coords"])), no, k["begin"], k["end"],
+                                slope=slope)
+        er = k["nc_eval_%d" % slope]
+        assert (np.abs(e - er) <= 1e-6 * np.maximum(1.0, np.abs(er))).all(), np.abs(e - er).max()
     # V9: a last-bit difference (correctly rounded vs glibc sine) can flip one line-search comparison, after which two minimisations
     # from a clashing random start walk apart; the CPU restatement shows the same sensitivity when it switches between the two
     # sine flavours (94 / 88 % of these starts end at the reference's energy after 3 iterations, 47 / 50 % after 12), while with

@@ -135,6 +135,15 @@ def test_non_cache_eval_deriv_and_within(kat, dock, libm):
     assert kat["nc_within"].any() and not kat["nc_within"].all()
 
 
+def test_non_cache_eval_is_bit_identical(kat, vo):
+    """non_cache::eval (lib/non_cache.cpp:52-83), the intermolecular energy behind the docking branch's printed Affinity
+    (main/main.cpp:340-344): table terms (eval_fast), box clamp, slope x distance outside"""
+    for slope in (10.0, 1000.0):
+        for i, c in enumerate(kat["nc_coords"]):
+            e = vo.noncache_eval(kat["rec_xyz"], kat["rec_types"], c, kat["lig_types"], kat["begin"], kat["end"], slope, 1000.0)
+            assert e == kat["nc_eval_%d" % slope][i]
+
+
 def test_bfgs_is_bit_identical(kat, dock, libm):
     """V9 quasi_newton / bfgs.h with the fast line search: energies and conformations after 3 and 12 iterations"""
     d, lig = dock

@@ -97,11 +97,45 @@ def test_non_cache_and_exact_scoring(libm):
                 assert nc.within() == d.within(x)
     finally:
         d.use_noncache(None); d.set_box(None)
+    nc = R.RefGrid.non_cache(sf, R.LINEAR, rm, BEGIN, END, N, 1e3)
     for x in X[:8]:
         c = rm.set(x)
-        assert nn.eval(1000.0) == vo.naive_exact(rx, rt, c, lig["types"], 1000.0)
+        assert nn.eval(1000.0) == vo.naive_exact(rx, rt, c, lig["types"], 1000.0)                       # --score_only's energy
+        assert nc.eval(1000.0) == vo.noncache_eval(rx, rt, c, lig["types"], BEGIN, END, 1e3, 1000.0)   # the docking branch's
     for e, nt in ((-7.25, 0.0), (-7.25, 3.5), (-11.0, 10.5), (2.0, 7.0)):
         assert sf.num_tors_div(e, nt) == vo.num_tors_div(e, nt)
+
+
+def test_refine_structure_composed_from_reference_parts(libm):
+    """refine_structure lives in main/main.cpp:131-171 (not a library source): its loop -- slope 10, 100, ...; quasi_newton on the
+    non_cache field; m.set; stop when non_cache::within -- is replayed here with the REFERENCE's quasi_newton / non_cache / within and
+    compared with the restatement's gvo_refine_structure"""
+    lig = synth.make_flexible_ligand(n_heavy=22, n_tors=4, n_branch=3, seed=41)
+    sf, vo, rm, cg, d, lig2, rx, rt = _setup(lig, seed=41)
+    rs = np.random.RandomState(41)
+    box_b, box_e, box_n = [-5.3] * 3, [5.2] * 3, [28, 28, 28]
+    X = _confs(rs, lig, d.T, 10, spread=7.0)
+    nc = R.RefGrid.non_cache(sf, R.LINEAR, rm, box_b, box_e, box_n, 1e3)
+    maxit = (25 + len(lig["types"])) // 3
+    left_box = 0
+    try:
+        d.use_noncache(rx, rt); d.set_box(box_b, box_e, 1e3)
+        for x in X:
+            xr, slope, er, ok, passes = x.copy(), 10.0, 0.0, False, 0
+            for p in range(5):
+                nc.set_slope(slope)
+                er, xr, _ = R.bfgs(rm, sf, R.LINEAR, nc, xr, maxit)
+                rm.set(xr); passes += 1
+                ok = nc.within()
+                if ok:
+                    break
+                slope *= 10
+            e, xo, ne, ok_o = d.refine_structure(x, maxit)
+            assert ok_o == ok and e == er and np.array_equal(xo, xr)
+            left_box += passes > 1
+    finally:
+        d.use_noncache(None); d.set_box(None)
+    assert left_box >= 1          # the escalation of the slope was exercised
 
 
 def test_grid_aligned_to_three_angstrom_shows_the_reference_cell_list_quirk():
