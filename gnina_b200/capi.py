@@ -12,7 +12,7 @@ SYMBOLS = ["gb_last_error", "gb_version", "gb_initialize_cuda", "gb_device_count
            "gb_cnn_destroy", "gb_cnn_num_models", "gb_cnn_set_option", "gb_cnn_get_option", "gb_cnn_set_receptor",
            "gb_cnn_score_batch", "gb_cnn_score_batch_models", "gb_cnn_get_rotation", "gb_cnn_score_grad", "gb_cnn_stage_poses", "gb_cnn_run_staged",
            "gb_cnn_fetch", "gb_cnn_fetch_device", "gb_cnn_profile_read", "gb_cnn_profile_reset", "gb_cnn_debug_read", "gb_cnn_stream", "gb_cnn_kernel_launches", "gb_cnn_voxelize", "gb_vina_create", "gb_vina_destroy", "gb_vina_table_size", "gb_vina_prec_table",
-           "gb_vina_set_receptor", "gb_vina_cache_build", "gb_vina_cache_read", "gb_vina_cache_eval", "gb_vina_score_exact", "gb_vina_score_noncache", "gb_vina_set_ligand", "gb_vina_eval_deriv",
+           "gb_vina_set_receptor", "gb_vina_cache_build", "gb_vina_cache_read", "gb_vina_cache_eval", "gb_vina_score_exact", "gb_vina_score_noncache", "gb_vina_minimize", "gb_vina_refine_minimize", "gb_vina_set_ligand", "gb_vina_eval_deriv",
            "gb_vina_bfgs", "gb_vina_mc", "gb_vina_mc_traced", "gb_vina_eval_deriv_noncache", "gb_vina_refine", "gb_vina_noncache_atoms", "gb_vina_merge_outputs", "gb_vina_spline_size", "gb_vina_spline_table", "gb_vina_set_precalc"]
 
 
@@ -28,6 +28,10 @@ class LigandTopology(C.Structure):
 class McParams(C.Structure):
     _fields_ = [("num_steps", C.c_int32), ("maxiters", C.c_int32), ("num_saved_mins", C.c_int32), ("temperature", C.c_float),
                 ("mutation_amplitude", C.c_float), ("min_rmsd", C.c_float), ("hunt_cap", C.c_float * 3)]
+
+
+class MinimizationParams(C.Structure):
+    _fields_ = [("maxiters", C.c_int32), ("accurate_line_search", C.c_int32), ("early_term", C.c_int32)]
 
 
 class GbError(RuntimeError):
@@ -101,6 +105,8 @@ def lib():
     L.gb_vina_cache_read.argtypes = [vp, C.c_int, fp]
     L.gb_vina_cache_eval.argtypes = [vp, fp, ip, ip, C.c_int, C.c_float, C.c_float, fp, fp]
     L.gb_vina_score_exact.argtypes = [vp, fp, ip, ip, C.c_int, fp, C.c_float, fp, fp]
+    L.gb_vina_minimize.argtypes = [vp, fp, C.c_int, C.POINTER(MinimizationParams), fp, C.c_float, fp, fp, ip]
+    L.gb_vina_refine_minimize.argtypes = [vp, fp, C.c_int, C.POINTER(MinimizationParams), fp, fp, fp, fp, ip, ip]
     L.gb_vina_score_noncache.argtypes = [vp, fp, ip, ip, C.c_int, fp, C.c_float, C.c_float, fp, fp, fp, fp]
     up = C.POINTER(C.c_uint32)
     L.gb_vina_spline_size.argtypes = [vp]

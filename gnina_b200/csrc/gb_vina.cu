@@ -1050,10 +1050,6 @@ __device__ void dk_conf_increment(float* x, const float* p, float f, int T, int 
   __syncwarp();
 }
 
-// bfgs (lib/bfgs.h:358-502), fast_line_search; W.x in/out, W.g out; returns f0 (all lanes).
-// Written around ONE evaluation site: the initial evaluation, every line-search trial and (grid_e != nullptr) the chain's
-// update_energy after the minimisation -- cache::eval at the final conformation with curl cap grid_v1 -- are iterations of
-// the same loop, so a kernel holds one copy of dk_eval_deriv (the arithmetic and its order are those of the reference).
 // model::gyration_radius (lib/model.cpp:1002-1014) of the coordinates the workspace holds: heavy atoms about the root origin, summed
 // in atom order (W.ea is free between evaluations; a hydrogen contributes an exact zero)
 __device__ inline float dk_gyration_radius(const LigPtrs& L, WarpWs& W, int lane) {
@@ -1072,8 +1068,42 @@ __device__ inline float dk_gyration_radius(const LigPtrs& L, WarpWs& W, int lane
   return L.n_heavy > 0 ? sqrtf(acc / (float)L.n_heavy) : 0.f;
 }
 
+// compute_lambdamin (lib/bfgs.h:93-102) with conf::operator()(i) (lib/conf.h:459-473: position, quaternion_to_angle(orientation),
+// torsions; lib/quaternion.cu:46-62); acos / sin correctly rounded like every transcendental of this file.  All lanes, same value.
+__device__ inline float dk_lambdamin(const float* x, const float* p, int n) {
+  float ang[3] = {0.f, 0.f, 0.f};
+  const float c = x[3];
+  if (c > -1 && c < 1) {
+    const float pi = 3.14159265358979323846f;
+    float angle = 2 * (float)acos((double)c);
+    if (angle > pi) angle -= 2 * pi;
+    const float sn = (float)sin((double)(angle / 2));
+    if (!(fabsf(sn) < 1.1920929e-07f)) {
+      const float f = angle / sn;
+      ang[0] = x[4] * f; ang[1] = x[5] * f; ang[2] = x[6] * f;
+    }
+  }
+  float test = 0.f;
+  #pragma unroll 1
+  for (int i = 0; i < n; i++) {
+    const float xi = i < 3 ? x[i] : (i < 6 ? ang[i - 3] : x[7 + i - 6]);
+    const float temp = fabsf(p[i]) / fmaxf(fabsf(xi), 1.0f);
+    if (temp > test) test = temp;
+  }
+  return test;
+}
+
+// bfgs (lib/bfgs.h:358-502); W.x in/out, W.g out; returns f0 (all lanes).
+// Written around ONE evaluation site: the initial evaluation, every line-search trial and (grid_e != nullptr) the chain's
+// update_energy after the minimisation are iterations of the same loop, so a kernel holds one copy of dk_eval_deriv (the
+// arithmetic and its order are those of the reference).
+// kMinimize = false: fast_line_search (:73-91), what the Monte-Carlo search uses -- the chain kernel's instantiation.
+// kMinimize = true:  minimization_params at run time: `accurate` = accurate_line_search (:107-180, after Numerical Recipes' lnsrch; what
+//                    --minimize selects, main/main.cpp:1160,1186), `early_term` = --minimize_early_term (:455-462).
+template <bool kMinimize>
 __device__ float dk_bfgs(const LigPtrs& L, const DockField& F, WarpWs& W, int maxiters, const float* v, int lane, int* n_evals,
-                         float* grid_e = nullptr, float grid_v1 = 0.f, float* gr_state = nullptr, float* gr_final = nullptr) {
+                         float* grid_e = nullptr, float grid_v1 = 0.f, float* gr_state = nullptr, float* gr_final = nullptr,
+                         bool accurate = false, bool early_term = false) {
   const int T = L.n_seg - 1, n = 6 + T, nx = 7 + T;
   #pragma unroll 1
   for (int k = lane; k < n * (n + 1) / 2; k += 32) W.h[k] = 0.f;
@@ -1085,6 +1115,7 @@ __device__ float dk_bfgs(const LigPtrs& L, const DockField& F, WarpWs& W, int ma
   // energy of the coordinates the LAST evaluation left in the model (bfgs.h does not re-evaluate at the x it returns: after ten
   // failed line-search trials, or when x_orig is restored, those are another conformation's); 2 = m.set(x) of the returned x
   float f0 = 0.f, f1 = 0.f, f_orig = 0.f, alpha = 1.f, pg = 0.f;
+  float alpha2 = 0.f, f2 = 0.f, alamin = 0.f;   // accurate line search: previous trial, smallest step
   bool didreset = false;
   int finishing = 0;
   const float vg[3] = {grid_v1, grid_v1, grid_v1};
@@ -1115,23 +1146,56 @@ __device__ float dk_bfgs(const LigPtrs& L, const DockField& F, WarpWs& W, int ma
       new_iter = true;
     } else {
       f1 = fe;
-      const bool accepted = f1 - f0 < 0.0001f * alpha * pg;
-      if (!accepted) { alpha *= 0.5f; trial++; }
-      if (accepted || trial >= 10) {
-        // the line search is over (alpha has been halved after the tenth failure too, as the reference's loop does)
+      bool ls_over;
+      if (kMinimize && accurate) {
+        // accurate_line_search: fl = float, the literals 2.0 / 3.0 / .5 are double (pg is the slope g.p)
+        if (alpha < alamin || !isfinite(alpha)) { alpha = 0.f; ls_over = true; }          // too small a step
+        else if (f1 <= f0 + 1.0e-4f * alpha * pg) ls_over = true;                          // sufficient decrease
+        else {
+          float tmplam;
+          if (alpha == 1.0f) tmplam = (float)(-pg / (2.0 * (f1 - f0 - pg)));
+          else {
+            const float rhs1 = f1 - f0 - alpha * pg, rhs2 = f2 - f0 - alpha2 * pg;
+            const float a = (rhs1 / (alpha * alpha) - rhs2 / (alpha2 * alpha2)) / (alpha - alpha2);
+            const float b = (-alpha2 * rhs1 / (alpha * alpha) + alpha * rhs2 / (alpha2 * alpha2)) / (alpha - alpha2);
+            if (a == 0.0f) tmplam = (float)(-pg / (2.0 * b));
+            else {
+              const float disc = (float)(b * b - 3.0 * a * pg);
+              if (disc < 0) tmplam = (float)(0.5 * alpha);
+              else if (b <= 0) tmplam = (float)((-b + sqrtf(disc)) / (3.0 * a));
+              else tmplam = -pg / (b + sqrtf(disc));
+            }
+            if (tmplam > .5 * alpha) tmplam = (float)(.5 * alpha);
+          }
+          alpha2 = alpha; f2 = f1;
+          alpha = fmaxf(tmplam, 0.1f * alpha);
+          ls_over = false;
+        }
+      } else {
+        const bool accepted = f1 - f0 < 0.0001f * alpha * pg;
+        if (!accepted) { alpha *= 0.5f; trial++; }
+        // over after ten trials too (alpha has been halved after the tenth failure as well, as the reference's loop does)
+        ls_over = accepted || trial >= 10;
+      }
+      if (ls_over) {
         if (alpha == 0.f) done = true;
         else {
           #pragma unroll 1
           for (int i = lane; i < n; i += 32) W.y[i] = W.g_new[i] - W.g[i];
+          const float prevf0 = f0;
           f0 = f1;
           #pragma unroll 1
           for (int i = lane; i < nx; i += 32) W.x[i] = W.x_new[i];
           __syncwarp();
-          #pragma unroll 1
-          for (int i = lane; i < n; i += 32) W.g[i] = W.g_new[i];
+          // --minimize_early_term: stop on a small decrease, BEFORE g is replaced (bfgs.h:455-464)
+          const bool stop_early = kMinimize && early_term && fabs((double)(prevf0 - f0)) < 1e-5;
+          if (!stop_early) {
+            #pragma unroll 1
+            for (int i = lane; i < n; i += 32) W.g[i] = W.g_new[i];
+          }
           __syncwarp();
           const float gn = dk_dot_seq(W.g, W.g, n), yy = dk_dot_seq(W.y, W.y, n), yp = dk_dot_seq(W.y, W.p, n);
-          if (!(gn >= 1e-4f)) done = true;
+          if (stop_early || !(gn >= 1e-4f)) done = true;
           else {
             if (step == 0 || didreset) {
               didreset = false;
@@ -1182,6 +1246,11 @@ __device__ float dk_bfgs(const LigPtrs& L, const DockField& F, WarpWs& W, int ma
         __syncwarp();
         pg = dk_dot_seq(W.p, W.g, n);
         alpha = 1.f; trial = 0;
+        if (kMinimize && accurate) {
+          alpha2 = 0.f; f2 = 0.f;
+          if (pg >= 0) done = true;   // not a descent direction: accurate_line_search returns 0 without evaluating, bfgs gives up
+          else alamin = 1.1920929e-07f / dk_lambdamin(W.x, W.p, n);
+        }
       }
     }
     if (done) {
@@ -1221,7 +1290,7 @@ __global__ void __launch_bounds__(32 * kDkWarps) dock_eval_kernel(LigPtrs L, Doc
                                                                   float v0, float v1, float v2, float* __restrict__ e_out,
                                                                   float* __restrict__ change_out, float* __restrict__ coords_out,
                                                                   int mode, int maxiters, float* __restrict__ confs_out,
-                                                                  int* __restrict__ evals_out) {
+                                                                  int* __restrict__ evals_out, int accurate, int early_term) {
   extern __shared__ __align__(16) float dk_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * kDkWarps + warp;
@@ -1240,7 +1309,7 @@ __global__ void __launch_bounds__(32 * kDkWarps) dock_eval_kernel(LigPtrs L, Doc
       for (int i = lane; i < 3 * L.n_atoms; i += 32) coords_out[(size_t)c * 3 * L.n_atoms + i] = W.coords[i];
   } else {
     int ne = 0;
-    const float e = dk_bfgs(L, F, W, maxiters, v, lane, &ne);
+    const float e = dk_bfgs<true>(L, F, W, maxiters, v, lane, &ne, nullptr, 0.f, nullptr, nullptr, accurate != 0, early_term != 0);
     if (lane == 0) { e_out[c] = e; if (evals_out) evals_out[c] = ne; }
     for (int i = lane; i < nx; i += 32) confs_out[(size_t)c * nx + i] = W.x[i];
     if (change_out)
@@ -1252,7 +1321,8 @@ __global__ void __launch_bounds__(32 * kDkWarps) dock_eval_kernel(LigPtrs L, Doc
 // 10, 100, ... until every heavy atom is inside the box (non_cache::within, margin 1e-4); e = max_fl if it never is
 __global__ void __launch_bounds__(32 * kDkWarps) dock_refine_kernel(LigPtrs L, DockField F0, float* __restrict__ confs, int n, float v0,
                                                                     float v1, float v2, int maxiters, float* __restrict__ e_out,
-                                                                    int* __restrict__ within_out, int* __restrict__ evals_out) {
+                                                                    int* __restrict__ within_out, int* __restrict__ evals_out,
+                                                                    int accurate, int early_term) {
   extern __shared__ __align__(16) float dk_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * kDkWarps + warp;
@@ -1269,7 +1339,7 @@ __global__ void __launch_bounds__(32 * kDkWarps) dock_refine_kernel(LigPtrs L, D
   for (int p = 0; p < 5; p++) {
     F.slope = slope;
     int ne = 0;
-    e = dk_bfgs(L, F, W, maxiters, v, lane, &ne);
+    e = dk_bfgs<true>(L, F, W, maxiters, v, lane, &ne, nullptr, 0.f, nullptr, nullptr, accurate != 0, early_term != 0);
     evals += ne;
     dk_set_conf(L, W, W.x, lane);  // m.set(out.c)
     int inside = 1;
@@ -1367,7 +1437,7 @@ __global__ void __launch_bounds__(32 * kDkWarps, 7) dock_mc_kernel(LigPtrs L, Do
       for (int i = lane; i < nx; i += 32) W.x[i] = src[i];
       __syncwarp();
       float ge = 0.f, gr_state = 0.f, gr_final = 0.f;
-      dk_bfgs(L, F, W, P.maxiters, pass == 0 ? P.hunt_cap : av, lane, nullptr, &ge, av[1], &gr_state, &gr_final);
+      dk_bfgs<false>(L, F, W, P.maxiters, pass == 0 ? P.hunt_cap : av, lane, nullptr, &ge, av[1], &gr_state, &gr_final);
       gr = gr_state;
       if (pass == 0) {
         #pragma unroll 1
@@ -1606,7 +1676,7 @@ static void make_noncache_field(const Vina& v, float slope, const float* bb, con
 
 static int dock_eval_common(gb_vina* h, const float* confs, int n, const float* vcap, float slope, int mode, int maxiters, float* e,
                             float* change, float* coords, float* confs_out, int32_t* evals, const float* nc_begin = nullptr,
-                            const float* nc_end = nullptr) {
+                            const float* nc_end = nullptr, int accurate = 0, int early_term = 0) {
   GBV_BEGIN
   GB_CHECK(h && confs && vcap && e && n >= 0, "bad arguments");
   Vina& v = h->v;
@@ -1631,7 +1701,7 @@ static int dock_eval_common(gb_vina* h, const float* confs, int n, const float* 
   else make_field(v, slope, F);
   const size_t dk_smem_bytes = dock_smem_bytes(v);
   dock_eval_kernel<<<(n + kDkWarps - 1) / kDkWarps, 32 * kDkWarps, dk_smem_bytes, v.stream>>>(lig_ptrs(v), F, d_conf, n, vcap[0], vcap[1], vcap[2], d_e, d_g,
-                                                                                  d_c, mode, maxiters, d_xo, d_ev);
+                                                                                  d_c, mode, maxiters, d_xo, d_ev, accurate, early_term);
   GB_CUDA(cudaGetLastError());
   float* p_e = v.pin<float>(1, n);
   float* p_g = change ? v.pin<float>(2, (size_t)n * NGA) : nullptr;
@@ -1657,6 +1727,12 @@ int gb_vina_eval_deriv(gb_vina* h, const float* confs, int n, const float* v3, f
 }
 int gb_vina_bfgs(gb_vina* h, float* confs, int n, int maxiters, const float* v3, float slope, float* e, float* change, int32_t* n_evals) {
   return dock_eval_common(h, confs, n, v3, slope, 1, maxiters, e, change, nullptr, confs, n_evals);
+}
+int gb_vina_minimize(gb_vina* h, float* confs, int n, const gb_minimization_params* mp, const float* v3, float slope, float* e,
+                     float* change, int32_t* n_evals) {
+  if (!mp) { gb::set_last_error("gb_vina_minimize: null params"); return GB_ERR_USAGE; }
+  return dock_eval_common(h, confs, n, v3, slope, 1, mp->maxiters, e, change, nullptr, confs, n_evals, nullptr, nullptr,
+                          mp->accurate_line_search, mp->early_term);
 }
 
 int gb_vina_eval_deriv_noncache(gb_vina* h, const float* confs, int n, const float* v3, float slope, const float* box_begin,
@@ -1684,8 +1760,19 @@ int gb_vina_noncache_atoms(gb_vina* h, const float* xyz, const int32_t* smina_ty
   GBV_END
 }
 
+static int refine_common(gb_vina* h, float* confs, int n, int maxiters, int accurate, int early_term, const float* v3,
+                         const float* box_begin, const float* box_end, float* e, int32_t* within, int32_t* n_evals);
 int gb_vina_refine(gb_vina* h, float* confs, int n, int maxiters, const float* v3, const float* box_begin, const float* box_end,
                    float* e, int32_t* within, int32_t* n_evals) {
+  return refine_common(h, confs, n, maxiters, 0, 0, v3, box_begin, box_end, e, within, n_evals);
+}
+int gb_vina_refine_minimize(gb_vina* h, float* confs, int n, const gb_minimization_params* mp, const float* v3, const float* box_begin,
+                            const float* box_end, float* e, int32_t* within, int32_t* n_evals) {
+  if (!mp) { gb::set_last_error("gb_vina_refine_minimize: null params"); return GB_ERR_USAGE; }
+  return refine_common(h, confs, n, mp->maxiters, mp->accurate_line_search, mp->early_term, v3, box_begin, box_end, e, within, n_evals);
+}
+static int refine_common(gb_vina* h, float* confs, int n, int maxiters, int accurate, int early_term, const float* v3,
+                         const float* box_begin, const float* box_end, float* e, int32_t* within, int32_t* n_evals) {
   GBV_BEGIN
   GB_CHECK(h && confs && v3 && box_begin && box_end && e && n >= 0, "bad arguments");
   Vina& v = h->v;
@@ -1705,7 +1792,7 @@ int gb_vina_refine(gb_vina* h, float* confs, int n, int maxiters, const float* v
   make_noncache_field(v, 10.f, box_begin, box_end, F);
   const size_t smem = dock_smem_bytes(v);
   dock_refine_kernel<<<(n + kDkWarps - 1) / kDkWarps, 32 * kDkWarps, smem, v.stream>>>(lig_ptrs(v), F, d_conf, n, v3[0], v3[1], v3[2], maxiters,
-                                                                                    d_e, d_in, d_ev);
+                                                                                    d_e, d_in, d_ev, accurate, early_term);
   GB_CUDA(cudaGetLastError());
   float* p_e = v.pin<float>(1, n);
   int* p_in = v.pin<int>(5, n);

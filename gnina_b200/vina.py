@@ -103,12 +103,17 @@ class VinaScorer:
         capi.check(capi.lib().gb_vina_eval_deriv(self._h, _fp(x), n, _fp(v), slope, _fp(e), _fp(g), _fp(c)))
         return (e, g, c) if coords else (e, g)
 
-    def bfgs(self, confs, maxiters, v=(1000, 1000, 1000), slope=1e3):
+    def bfgs(self, confs, maxiters, v=(1000, 1000, 1000), slope=1e3, accurate=False, early_term=False):
+        """quasi_newton on the cache field; accurate / early_term = the --minimize flavours (gb_vina_minimize)"""
         x = np.array(confs, np.float32).reshape(-1, 7 + self.T)
         n = len(x)
         v = np.ascontiguousarray(v, np.float32)
         e = np.empty(n, np.float32); g = np.empty((n, 6 + self.T), np.float32); ne = np.empty(n, np.int32)
-        capi.check(capi.lib().gb_vina_bfgs(self._h, _fp(x), n, maxiters, _fp(v), slope, _fp(e), _fp(g), _ip(ne)))
+        if accurate or early_term:
+            mp = capi.MinimizationParams(int(maxiters), int(accurate), int(early_term))
+            capi.check(capi.lib().gb_vina_minimize(self._h, _fp(x), n, C.byref(mp), _fp(v), slope, _fp(e), _fp(g), _ip(ne)))
+        else:
+            capi.check(capi.lib().gb_vina_bfgs(self._h, _fp(x), n, maxiters, _fp(v), slope, _fp(e), _fp(g), _ip(ne)))
         return e, x, g, ne
 
     def eval_deriv_noncache(self, confs, box_begin, box_end, v=(1000, 1000, 1000), slope=1e3):
@@ -129,14 +134,18 @@ class VinaScorer:
         capi.check(capi.lib().gb_vina_noncache_atoms(self._h, _fp(x), _ip(t), len(t), _fp(b), _fp(en), v, _fp(e), _fp(d)))
         return e, d
 
-    def refine(self, confs, maxiters, box_begin, box_end, v=(1000, 1000, 1000)):
-        """refine_structure (main/main.cpp:131-171) -> (e, refined confs, within, n_evals)"""
+    def refine(self, confs, maxiters, box_begin, box_end, v=(1000, 1000, 1000), accurate=False, early_term=False):
+        """refine_structure (main/main.cpp:131-171) -> (e, refined confs, within, n_evals); accurate / early_term: --minimize"""
         x = np.array(confs, np.float32).reshape(-1, 7 + self.T)
         n = len(x)
         v = np.ascontiguousarray(v, np.float32)
         b, en = np.ascontiguousarray(box_begin, np.float32), np.ascontiguousarray(box_end, np.float32)
         e = np.empty(n, np.float32); ok = np.empty(n, np.int32); ne = np.empty(n, np.int32)
-        capi.check(capi.lib().gb_vina_refine(self._h, _fp(x), n, maxiters, _fp(v), _fp(b), _fp(en), _fp(e), _ip(ok), _ip(ne)))
+        if accurate or early_term:
+            mp = capi.MinimizationParams(int(maxiters), int(accurate), int(early_term))
+            capi.check(capi.lib().gb_vina_refine_minimize(self._h, _fp(x), n, C.byref(mp), _fp(v), _fp(b), _fp(en), _fp(e), _ip(ok), _ip(ne)))
+        else:
+            capi.check(capi.lib().gb_vina_refine(self._h, _fp(x), n, maxiters, _fp(v), _fp(b), _fp(en), _fp(e), _ip(ok), _ip(ne)))
         return e, x, ok.astype(bool), ne
 
     def mc(self, seeds, corner1, corner2, num_steps, maxiters, num_saved_mins=20, temperature=1.2, amplitude=2.0, min_rmsd=0.5,

@@ -273,6 +273,16 @@ int gb_vina_noncache_atoms(gb_vina* h, const float* xyz, const int32_t* smina_ty
  * n_evals[n] nullable.  Needs gb_vina_set_receptor + gb_vina_set_ligand, no cache. */
 int gb_vina_refine(gb_vina* h, float* confs, int n, int maxiters, const float* v3, const float* box_begin, const float* box_end,
                    float* e, int32_t* within, int32_t* n_evals);
+/* minimization_params (lib/common.h:50-60) for the --minimize flows: BFGSAccurateLineSearch (bfgs.h:107-180; main/main.cpp:1160,1186
+ * select it, with maxiters 10000 when the user gives none, :1157-1158) and --minimize_early_term (bfgs.h:455-462).  With both flags 0
+ * these two calls equal gb_vina_bfgs / gb_vina_refine (fast_line_search, what the docking search uses). */
+typedef struct { int32_t maxiters, accurate_line_search, early_term; } gb_minimization_params;
+/* quasi_newton::operator() (lib/quasi_newton.cpp:49-83) with these parameters on the cache field: confs in/out */
+int gb_vina_minimize(gb_vina* h, float* confs, int n, const gb_minimization_params* mp, const float* v3, float slope, float* e,
+                     float* change, int32_t* n_evals);
+/* refine_structure (main/main.cpp:131-171) with these parameters: the --local_only / --minimize branch (:264-268) */
+int gb_vina_refine_minimize(gb_vina* h, float* confs, int n, const gb_minimization_params* mp, const float* v3, const float* box_begin,
+                            const float* box_end, float* e, int32_t* within, int32_t* n_evals);
 /* merge_output_containers over the chains' containers (lib/parallel_mc.cpp:165-181 -> add_to_output_container,
  * lib/coords.cpp:43-56, find_closest / rmsd_upper_bound :24-41): chains in order, each chain's minima in order;
  * a pose closer than min_rmsd (RMSD over the n_atoms coordinates given) to a kept one replaces it if better,

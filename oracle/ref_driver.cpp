@@ -385,11 +385,14 @@ int gref_num_tors_div(void* sf, float e, float num_tors, float* out) {
   });
 }
 // quasi_newton::operator() (lib/quasi_newton.cpp:49-83 -> bfgs.h:358-502, fast line search) from conf x; x is updated
-int gref_bfgs(void* mp, void* sf, int kind, void* gp, float* x, int maxiters, const float* v3, float* e, float* out_change) {
+int gref_bfgs(void* mp, void* sf, int kind, void* gp, float* x, int maxiters, const float* v3, float* e, float* out_change, int accurate,
+              int early_term) {
   RefModel* R = (RefModel*)mp; RefSF* S = (RefSF*)sf;
   return guarded([&] {
     minimization_params mp_;
     mp_.maxiters = (unsigned)maxiters;
+    mp_.type = accurate ? minimization_params::BFGSAccurateLineSearch : minimization_params::BFGSFastLineSearch;
+    mp_.early_term = early_term != 0;
     quasi_newton qn(mp_);
     output_type out(make_conf(R->m, x), 0);
     change g(R->m.get_size(), false);

@@ -39,6 +39,8 @@ class DockOracle:
         L.gvo_bfgs.argtypes = [C.POINTER(_Field), C.POINTER(_Lig), _fp, _fp, C.c_int, _fp, C.POINTER(C.c_int)]; L.gvo_bfgs.restype = C.c_float
         L.gvo_mc_run.argtypes = [C.POINTER(_Field), C.POINTER(_Lig), C.POINTER(_McParams), _fp, _fp, C.c_uint32, _fp, _fp]
         L.gvo_mc_run_traced.argtypes = [C.POINTER(_Field), C.POINTER(_Lig), C.POINTER(_McParams), _fp, _fp, C.c_uint32, _fp, _fp, _fp]
+        L.gvo_bfgs_ex.argtypes = [C.POINTER(_Field), C.POINTER(_Lig), _fp, _fp, C.c_int, _fp, C.POINTER(C.c_int), C.c_int, C.c_int]
+        L.gvo_bfgs_ex.restype = C.c_float
         L.gvo_mc_run_ex.argtypes = [C.POINTER(_Field), C.POINTER(_Lig), C.POINTER(_McParams), _fp, _fp, C.c_uint32, _fp, _fp, _fp, _fp, _fp]
         L.gvo_random_conf.argtypes = [C.POINTER(C.c_uint32), _fp, _fp, C.c_int, _fp]
         self.L = L
@@ -57,6 +59,7 @@ class DockOracle:
         L.gvo_within.argtypes = [C.POINTER(_Field), C.POINTER(_Lig), _fp, C.c_float]
         L.gvo_refine_structure.argtypes = [C.POINTER(_Field), C.POINTER(_Lig), _fp, _fp, C.c_int, _fp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.gvo_refine_structure.restype = C.c_float
+        L.gvo_refine_structure_ex.argtypes = L.gvo_refine_structure.argtypes + [C.c_int, C.c_int]; L.gvo_refine_structure_ex.restype = C.c_float
         self.vo = vina_oracle
         self.T = len(lig["seg_parent"]) - 1
         self.na = len(lig["types"])
@@ -96,11 +99,12 @@ class DockOracle:
         conf = np.ascontiguousarray(conf, np.float32)
         return bool(self.L.gvo_within(C.byref(self.field), C.byref(self.lig), _f(conf), margin))
 
-    def refine_structure(self, conf, maxiters, v=(1000, 1000, 1000)):
+    def refine_structure(self, conf, maxiters, v=(1000, 1000, 1000), accurate=False, early_term=False):
         """main/main.cpp:131-171 -> (energy, refined conf, n_evals, within)"""
         x = np.array(conf, np.float32); v = np.ascontiguousarray(v, np.float32)
         g = np.empty(6 + self.T, np.float32); ne, ok = C.c_int(), C.c_int()
-        e = self.L.gvo_refine_structure(C.byref(self.field), C.byref(self.lig), _f(x), _f(g), maxiters, _f(v), C.byref(ne), C.byref(ok))
+        e = self.L.gvo_refine_structure_ex(C.byref(self.field), C.byref(self.lig), _f(x), _f(g), maxiters, _f(v), C.byref(ne), C.byref(ok),
+                                           int(accurate), int(early_term))
         return e, x, ne.value, bool(ok.value)
 
     def use_splines(self, on=True):
@@ -123,10 +127,12 @@ class DockOracle:
         conf = np.ascontiguousarray(conf, np.float32)
         return self.L.gvo_lig_eval_grid(C.byref(self.field), C.byref(self.lig), _f(conf), v1, None)
 
-    def bfgs(self, conf, maxiters, v=(1000, 1000, 1000)):
+    def bfgs(self, conf, maxiters, v=(1000, 1000, 1000), accurate=False, early_term=False):
+        """quasi_newton (bfgs.h:358-502); accurate = BFGSAccurateLineSearch (--minimize), early_term = --minimize_early_term"""
         x = np.array(conf, np.float32); v = np.ascontiguousarray(v, np.float32)
         g = np.empty(6 + self.T, np.float32); ne = C.c_int()
-        e = self.L.gvo_bfgs(C.byref(self.field), C.byref(self.lig), _f(x), _f(g), maxiters, _f(v), C.byref(ne))
+        e = self.L.gvo_bfgs_ex(C.byref(self.field), C.byref(self.lig), _f(x), _f(g), maxiters, _f(v), C.byref(ne), int(accurate),
+                               int(early_term))
         return e, x, g, ne.value
 
     def random_conf(self, seed, c1, c2):

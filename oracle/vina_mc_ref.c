@@ -10,10 +10,16 @@
  *   V9  bfgs + fast_line_search + bfgs_update, conf::increment                      lib/bfgs.h:52-91,358-502, lib/conf.h:54-59,113-118
  *   V10 monte_carlo::operator(), mutate_conf, metropolis_accept, add_to_output_container
  *                                     lib/monte_carlo.cpp:38-47,99-148, lib/mutate.cpp:35-73, lib/coords.cpp:25-56
+ *       non_cache::eval_deriv / within, refine_structure                           lib/non_cache.cpp:84-174, main/main.cpp:131-171
  * The reference draws from boost::mt19937 through Boost distributions (lib/random.cpp), whose sources are not in the
- * tree: trajectories cannot be reproduced, so this oracle (and the device code, identically) uses a small
- * counter-free generator (xorshift32) — parity is asserted on single evaluations, on BFGS from identical starts and
- * on whole chains driven by the same generator.  No golden in the reference's tests: "parity unpinned".
+ * tree: its random STREAM cannot be reproduced, so this oracle (and the device code, identically) uses a small
+ * counter-free generator (xorshift32).
+ * PINNED against the reference's own code compiled here (oracle/_ref; oracle/Makefile.ref, ref_driver.cpp), which runs on the
+ * same generator through the stand-in oracle/ref_shim/boost/random.hpp: with this host's sinf / cosf / expf (gvo_use_libm(1))
+ * model::set, model::eval_deriv (cache and non_cache), quasi_newton after any number of iterations, refine_structure and WHOLE
+ * Monte-Carlo chains (model-state mode of mc_impl) are BIT-IDENTICAL to the reference: tests/test_oracle_vs_reference_build.py
+ * (live) and tests/test_oracle_vina_golden.py (tests/golden/vina_ref_kat.npz, generated from that build).  Not pinned: Boost's
+ * random stream itself.
  */
 #include <math.h>
 #include <stdint.h>
@@ -288,14 +294,38 @@ static void conf_increment(float *x, const float *p, float f, int T) {
 static int tri(int i, int j) { return i <= j ? i + j * (j + 1) / 2 : j + i * (i + 1) / 2; }
 
 /* bfgs (lib/bfgs.h:358-502) with fast_line_search; x in/out (7+T floats), g out (6+T); returns f0 */
-static float bfgs_impl(const gvo_field *F, const gvo_lig *L, float *x, float *g, int maxiters, const float *v, int *n_evals, float *x_last);
+static float bfgs_impl(const gvo_field *F, const gvo_lig *L, float *x, float *g, int maxiters, const float *v, int *n_evals, float *x_last,
+                       int accurate, int early_term);
 float gvo_bfgs(const gvo_field *F, const gvo_lig *L, float *x, float *g, int maxiters, const float *v, int *n_evals) {
-  return bfgs_impl(F, L, x, g, maxiters, v, n_evals, 0);
+  return bfgs_impl(F, L, x, g, maxiters, v, n_evals, 0, 0, 0);
 }
+/* minimization_params (lib/common.h:50-60): accurate = BFGSAccurateLineSearch (what --minimize selects, main/main.cpp:1160,1186),
+ * early_term = --minimize_early_term */
+float gvo_bfgs_ex(const gvo_field *F, const gvo_lig *L, float *x, float *g, int maxiters, const float *v, int *n_evals, int accurate,
+                  int early_term) {
+  return bfgs_impl(F, L, x, g, maxiters, v, n_evals, 0, accurate, early_term);
+}
+static float acos_cr(float x) { return g_use_libm ? acosf(x) : (float)acos((double)x); }
+/* quaternion_to_angle (lib/quaternion.cu:46-62) */
+static void q_to_angle(const float *q, float *out) {
+  const float c = q[0];
+  out[0] = out[1] = out[2] = 0;
+  if (c > -1 && c < 1) {
+    float angle = 2 * acos_cr(c);
+    if (angle > PI_F) angle -= 2 * PI_F;
+    const float s = sin_cr(angle / 2);
+    if (fabsf(s) < kEps) return;
+    const float f = angle / s;
+    out[0] = q[1] * f; out[1] = q[2] * f; out[2] = q[3] * f;
+  }
+}
+/* conf::operator()(index) (lib/conf.h:459-473): position, orientation as a rotation vector, torsions */
+static float conf_at(const float *x, int i, const float *ang) { return i < 3 ? x[i] : (i < 6 ? ang[i - 3] : x[7 + i - 6]); }
 /* x_last (nullable, 7+T): the conformation of the LAST function evaluation = what model::set left in the model's coordinates
  * when quasi_newton returns. bfgs does not re-evaluate at the x it returns: after a line search that used up its 10 trials,
  * or when x_orig is restored (:494-498), the model holds another conformation than the returned one. */
-static float bfgs_impl(const gvo_field *F, const gvo_lig *L, float *x, float *g, int maxiters, const float *v, int *n_evals, float *x_last) {
+static float bfgs_impl(const gvo_field *F, const gvo_lig *L, float *x, float *g, int maxiters, const float *v, int *n_evals, float *x_last,
+                       int accurate, int early_term) {
   const int T = L->n_seg - 1, n = 6 + T, nx = 7 + T;
   float *h = (float *)calloc((size_t)n * (n + 1) / 2, 4), *g_new = (float *)malloc(4 * n), *x_new = (float *)malloc(4 * nx),
         *p = (float *)malloc(4 * n), *y = (float *)malloc(4 * n), *mhy = (float *)malloc(4 * n), *x_orig = (float *)malloc(4 * nx),
@@ -310,19 +340,63 @@ static float bfgs_impl(const gvo_field *F, const gvo_lig *L, float *x, float *g,
   for (int step = 0; step < maxiters; step++) {
     for (int i = 0; i < n; i++) { float s = 0; for (int j = 0; j < n; j++) s += h[tri(i, j)] * g[j]; p[i] = -s; }
     float f1 = 0, alpha = 1, pg = 0;
-    for (int i = 0; i < n; i++) pg += p[i] * g[i];
-    for (int trial = 0; trial < 10; trial++) { /* fast_line_search :73-91 */
-      memcpy(x_new, x, 4 * nx);
-      conf_increment(x_new, p, alpha, T);
-      f1 = gvo_lig_eval_deriv(F, L, x_new, v, g_new, 0); evals++;
-      if (x_last) memcpy(x_last, x_new, 4 * nx);
-      if (f1 - f0 < 0.0001f * alpha * pg) break;
-      alpha *= 0.5f;
+    if (!accurate) {
+      for (int i = 0; i < n; i++) pg += p[i] * g[i];
+      for (int trial = 0; trial < 10; trial++) { /* fast_line_search :73-91 */
+        memcpy(x_new, x, 4 * nx);
+        conf_increment(x_new, p, alpha, T);
+        f1 = gvo_lig_eval_deriv(F, L, x_new, v, g_new, 0); evals++;
+        if (x_last) memcpy(x_last, x_new, 4 * nx);
+        if (f1 - f0 < 0.0001f * alpha * pg) break;
+        alpha *= 0.5f;
+      }
+    } else { /* accurate_line_search :107-180 (after lnsrch of Numerical Recipes); fl = float, the literals 2.0 / 3.0 / .5 are double */
+      float a, alpha2 = 0, alamin, b, disc, f2 = 0, rhs1, rhs2, slope = 0, test = 0, tmplam = 0, ang[3];
+      const float ALF = (float)1.0e-4, FIRST = 1.0f;
+      for (int i = 0; i < n; i++) slope += g[i] * p[i];
+      if (slope >= 0) { /* not a descent direction */
+        memcpy(x_new, x, 4 * nx); memset(g_new, 0, 4 * n); alpha = 0;
+      } else {
+        q_to_angle(x + 3, ang);
+        for (int i = 0; i < n; i++) { /* compute_lambdamin :93-102 */
+          const float temp = fabsf(p[i]) / fmaxf(fabsf(conf_at(x, i, ang)), 1.0f);
+          if (temp > test) test = temp;
+        }
+        alamin = kEps / test;
+        alpha = FIRST;
+        for (;;) {
+          memcpy(x_new, x, 4 * nx);
+          conf_increment(x_new, p, alpha, T);
+          f1 = gvo_lig_eval_deriv(F, L, x_new, v, g_new, 0); evals++;
+          if (x_last) memcpy(x_last, x_new, 4 * nx);
+          if (alpha < alamin || !isfinite(alpha)) { memcpy(x_new, x, 4 * nx); memset(g_new, 0, 4 * n); alpha = 0; break; }
+          if (f1 <= f0 + ALF * alpha * slope) break;
+          if (alpha == FIRST) tmplam = (float)(-slope / (2.0 * (f1 - f0 - slope)));
+          else {
+            rhs1 = f1 - f0 - alpha * slope;
+            rhs2 = f2 - f0 - alpha2 * slope;
+            a = (rhs1 / (alpha * alpha) - rhs2 / (alpha2 * alpha2)) / (alpha - alpha2);
+            b = (-alpha2 * rhs1 / (alpha * alpha) + alpha * rhs2 / (alpha2 * alpha2)) / (alpha - alpha2);
+            if (a == 0.0) tmplam = (float)(-slope / (2.0 * b));
+            else {
+              disc = (float)(b * b - 3.0 * a * slope);
+              if (disc < 0) tmplam = (float)(0.5 * alpha);
+              else if (b <= 0) tmplam = (float)((-b + sqrtf(disc)) / (3.0 * a));
+              else tmplam = -slope / (b + sqrtf(disc));
+            }
+            if (tmplam > .5 * alpha) tmplam = (float)(.5 * alpha);
+          }
+          alpha2 = alpha; f2 = f1;
+          alpha = fmaxf(tmplam, 0.1f * alpha);
+        }
+      }
     }
     if (alpha == 0) break;
     for (int i = 0; i < n; i++) y[i] = g_new[i] - g[i];
+    const float prevf0 = f0;
     f0 = f1;
     memcpy(x, x_new, 4 * nx);
+    if (early_term && fabs((double)(prevf0 - f0)) < 1e-5) break; /* :455-462, before g is replaced */
     memcpy(g, g_new, 4 * n);
     float gn = 0;
     for (int i = 0; i < n; i++) gn += g[i] * g[i];
@@ -359,15 +433,22 @@ static float bfgs_impl(const gvo_field *F, const gvo_lig *L, float *x, float *g,
  * lib/quasi_newton.cpp:49-83) with the out-of-box slope 10, 100, ... until every heavy atom is within the box
  * (non_cache::within, margin 1e-4); returns the last run's energy, x is refined in place, *within_out tells whether the
  * final pose is inside (the reference sets out.e = max_fl otherwise). */
+float gvo_refine_structure_ex(const gvo_field *F0, const gvo_lig *L, float *x, float *g, int maxiters, const float *v, int *n_evals,
+                              int *within_out, int accurate, int early_term);
 float gvo_refine_structure(const gvo_field *F0, const gvo_lig *L, float *x, float *g, int maxiters, const float *v, int *n_evals,
                            int *within_out) {
+  return gvo_refine_structure_ex(F0, L, x, g, maxiters, v, n_evals, within_out, 0, 0);
+}
+/* with the minimization_params of --minimize / --local_only (main/main.cpp:264-268 passes par.mc.ssd_par.minparm = the user's) */
+float gvo_refine_structure_ex(const gvo_field *F0, const gvo_lig *L, float *x, float *g, int maxiters, const float *v, int *n_evals,
+                              int *within_out, int accurate, int early_term) {
   gvo_field F = *F0;
   float slope = 10.f, e = 0;
   int evals = 0, ok = 0;
   for (int p = 0; p < 5; p++) {
     int ne = 0;
     F.slope = slope;
-    e = gvo_bfgs(&F, L, x, g, maxiters, v, &ne);
+    e = gvo_bfgs_ex(&F, L, x, g, maxiters, v, &ne, accurate, early_term);
     evals += ne;
     ok = gvo_within(&F, L, x, 0.0001f);
     if (ok) break;
@@ -478,7 +559,7 @@ static int mc_impl(const gvo_field *F, const gvo_lig *L, const gvo_mc_params *P,
     mutate_conf(cand, T, P->mutation_amplitude, stateful ? gyration_radius_of(L, xs, coords, so, sa) : P->gyration_radius, &s);
     float cand_e;
     if (stateful) {
-      bfgs_impl(F, L, cand, g, P->maxiters, P->hunt_cap, 0, xs);
+      bfgs_impl(F, L, cand, g, P->maxiters, P->hunt_cap, 0, xs, 0, 0);
       gvo_lig_set_conf(L, xs, coords, so, sa);
       cand_e = grid_energy_on(F, L, coords, av[1]);
     } else {
@@ -495,7 +576,7 @@ static int mc_impl(const gvo_field *F, const gvo_lig *L, const gvo_mc_params *P,
       if (stateful) memcpy(xs, tmp, 4 * nx); /* m.set(tmp.c) :126 */
       if (tmp_e < best_e || n_out < P->num_saved_mins) {
         if (stateful) {
-          bfgs_impl(F, L, tmp, g, P->maxiters, av, 0, xs);
+          bfgs_impl(F, L, tmp, g, P->maxiters, av, 0, xs, 0, 0);
           gvo_lig_set_conf(L, xs, coords, so, sa);
           tmp_e = grid_energy_on(F, L, coords, av[1]);
           memcpy(xs, tmp, 4 * nx);                 /* m.set(tmp.c) :134 */

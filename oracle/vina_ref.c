@@ -11,8 +11,14 @@
  *                                                                                lib/curl.h:30-42
  *   V12 naive_non_cache::eval (exact terms, per-atom curl) + num_tors_div        lib/naive_non_cache.cpp:29-57,
  *                                                                                lib/everything.h:795-809
- * The reference's tests hold NO absolute numbers for these functions (gninacheck compares two live
- * implementations, test_gnina.py only inequalities): "parity unpinned" — this restatement is the pin.
+ *       non_cache::eval (the docking branch's final intermolecular energy)     lib/non_cache.cpp:52-83
+ * PINNED: the reference's tests hold no absolute numbers for these functions (gninacheck compares two live implementations,
+ * test_gnina.py only inequalities), but the reference's own sources compile here with stand-in Boost / OpenBabel headers
+ * (oracle/Makefile.ref, oracle/ref_driver.cpp -> oracle/_ref).  Against that build every function of this file is BIT-IDENTICAL
+ * (terms, precalculate_linear, precalculate_exact, cache::populate, grid evaluation, naive_non_cache::eval, non_cache::eval,
+ * num_tors_div) except the spline coefficients (Thomas solve in double vs the reference's dense float inverse: 1e-6):
+ * tests/test_oracle_vs_reference_build.py (live, where /root/reference exists) and tests/test_oracle_vina_golden.py (against
+ * tests/golden/vina_ref_kat.npz, known answers generated from that build, everywhere).
  */
 #include <math.h>
 #include <stdint.h>

@@ -61,7 +61,7 @@ def lib():
         L.gref_model_eval_deriv.argtypes = [_vp, _vp, C.c_int, _vp, _fp, _fp, _fp, _fp]
         L.gref_model_affinity.argtypes = [_vp, _vp, _fp, _fp, _fp, _fp]
         L.gref_num_tors_div.argtypes = [_vp, C.c_float, C.c_float, _fp]
-        L.gref_bfgs.argtypes = [_vp, _vp, C.c_int, _vp, _fp, C.c_int, _fp, _fp, _fp]
+        L.gref_bfgs.argtypes = [_vp, _vp, C.c_int, _vp, _fp, C.c_int, _fp, _fp, _fp, C.c_int, C.c_int]
         L.gref_random_conf.argtypes = [_vp, C.c_uint32, _fp, _fp, _fp, C.POINTER(C.c_uint32)]
         L.gref_mc.argtypes = [_vp, _vp, C.c_int, _vp, _fp, _fp, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                               _fp, _fp, C.c_int, _fp, _fp, C.POINTER(C.c_int)]
@@ -230,10 +230,10 @@ def model_affinity(model, sf, conf, v=(1000, 1000, 1000)):
     return float(a[0]), float(b[0])
 
 
-def bfgs(model, sf, kind, grid, conf, maxiters, v=(1000, 1000, 1000)):
+def bfgs(model, sf, kind, grid, conf, maxiters, v=(1000, 1000, 1000), accurate=False, early_term=False):
     x = np.array(conf, np.float32); vv = np.ascontiguousarray(v, np.float32)
     e = np.empty(1, np.float32); g = np.empty(6 + model.T, np.float32)
-    _ok(lib().gref_bfgs(model.p, sf.p, kind, grid.p, _f(x), maxiters, _f(vv), _f(e), _f(g)))
+    _ok(lib().gref_bfgs(model.p, sf.p, kind, grid.p, _f(x), maxiters, _f(vv), _f(e), _f(g), int(accurate), int(early_term)))
     return float(e[0]), x, g
 
 

@@ -93,6 +93,10 @@ def main():
             res = [R.bfgs(rm, sf, R.LINEAR, cg, x, it, caps) for x in Xb]
             out["bfgs%d_%s_e" % (it, name)] = np.float32([a for a, _, _ in res])
             out["bfgs%d_%s_x" % (it, name)] = np.stack([b for _, b, _ in res])
+    # V9, the --minimize flavours: accurate_line_search (bfgs.h:107-180) and --minimize_early_term
+    for tag, acc, et, it in (("acc", True, False, 30), ("acc_et", True, True, 300), ("fast_et", False, True, 60)):
+        res = [R.bfgs(rm, sf, R.LINEAR, cg, x, it, (1000, 1000, 1000), accurate=acc, early_term=et) for x in Xb]
+        out["min_%s_e" % tag] = np.float32([a for a, _, _ in res]); out["min_%s_x" % tag] = np.stack([b for _, b, _ in res])
     # V12: naive_non_cache::eval with precalculate_exact, num_tors_div, eval_adjusted
     nn = R.RefGrid.naive(sf, R.EXACT, rm)
     e_inter, aff = [], []

@@ -129,6 +129,41 @@ def test_bfgs_from_identical_starts(setup):
     assert (ne >= 2).all()
 
 
+def test_minimize_flavours_follow_the_oracle(setup):
+    """gb_vina_minimize / gb_vina_refine_minimize: accurate_line_search (bfgs.h:107-180; what --minimize selects) and
+    --minimize_early_term.  The restatement of both is bit-identical to the compiled reference (tests/test_oracle_vina_golden.py); the
+    device follows the restatement's trajectory -- same number of evaluations, same final conformation -- for most starts (the
+    fractions fall with the iteration count as in test_bfgs_from_identical_starts: one flipped comparison separates two runs for good;
+    a wrong line search would agree for none)"""
+    v, d, lig = setup
+    X = _confs(d, 40, seed0=900)
+    for acc, et, iters, frac in ((True, False, 1, 0.9), (True, False, 3, 0.85), (True, False, 25, 0.5), (True, True, 200, 0.4), (False, True, 40, 0.5)):
+        e, Xo, g, ne = v.bfgs(X, iters, accurate=acc, early_term=et)
+        same = 0
+        for i in range(len(X)):
+            er, xr, gr, ner = d.bfgs(X[i], iters, accurate=acc, early_term=et)
+            same += bool(abs(e[i] - er) <= 1e-5 * max(1.0, abs(er)) and ne[i] == ner and np.abs(Xo[i] - xr).max() < 1e-4)
+        assert same >= frac * len(X), (acc, et, iters, same)
+        e0, _ = v.eval_deriv(X)
+        assert (e <= e0 + 1e-4 * np.maximum(1.0, np.abs(e0))).all()
+    # refine_structure with the accurate line search (the --minimize / --local_only branch, main/main.cpp:264-268)
+    from gnina_b200 import synth
+    rx, rt = synth.make_receptor(900, box=34)
+    begin, end = [-6.0] * 3, [6.0] * 3
+    Xr = _confs(d, 12, seed0=1300); Xr[:3, :3] += 5.0
+    d.use_noncache(rx, rt)
+    try:
+        d.set_box(begin, end)
+        e, Xo, ok, ne = v.refine(Xr, 60, begin, end, accurate=True)
+        same = 0
+        for i in range(len(Xr)):
+            er, xr, ner, okr = d.refine_structure(Xr[i], 60, accurate=True)
+            same += bool(ok[i]) == okr and ne[i] == ner and np.abs(Xo[i] - xr).max() < 1e-4
+        assert same >= 0.5 * len(Xr), same
+    finally:
+        d.set_box(None); d.use_noncache(None)
+
+
 def test_monte_carlo_chains(setup):
     """Chain by chain: same xorshift stream, same evaluations -> the device chain must accept the same moves as the oracle
     chain.  The per-step trace of the chain's current energy is compared; a chain counts as identical when every one of its

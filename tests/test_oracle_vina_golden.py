@@ -154,6 +154,16 @@ def test_bfgs_is_bit_identical(kat, dock, libm):
                 assert e == kat["bfgs%d_%s_e" % (it, name)][i] and np.array_equal(xo, kat["bfgs%d_%s_x" % (it, name)][i])
 
 
+def test_minimize_flavours_are_bit_identical(kat, dock, libm):
+    """V9 for --minimize: accurate_line_search (bfgs.h:107-180, after Numerical Recipes' lnsrch, with its float / double mix) and
+    --minimize_early_term (:455-462)"""
+    d, lig = dock
+    for tag, acc, et, it in (("acc", True, False, 30), ("acc_et", True, True, 300), ("fast_et", False, True, 60)):
+        for i, x in enumerate(kat["confs"][:32]):
+            e, xo, g, ne = d.bfgs(x, it, accurate=acc, early_term=et)
+            assert e == kat["min_%s_e" % tag][i] and np.array_equal(xo, kat["min_%s_x" % tag][i])
+
+
 def test_exact_scoring(kat, vo, dock, libm):
     """V12: naive_non_cache::eval with precalculate_exact and num_tors_div bit-identical; the printed Affinity = eval_adjusted is
     conf_independent((inter + intra) - intra) in float, the restatement's conf_independent(inter): 2e-7"""

@@ -61,6 +61,11 @@ def test_evaluation_minimisation_and_chains_are_bit_identical(lig_kw, libm):
         for it, caps in ((2, (10, 10, 10)), (15, (1000, 1000, 1000))):
             e, xo, g, _ = d.bfgs(x, it, caps); er, xr, gr = R.bfgs(rm, sf, R.LINEAR, cg, x, it, caps)
             assert e == er and np.array_equal(xo, xr) and np.array_equal(g, gr)
+    for x in X[:8]:                                      # V9, --minimize: accurate line search, early termination
+        for acc, et, it in ((True, False, 40), (True, True, 400), (False, True, 40)):
+            e, xo, g, _ = d.bfgs(x, it, accurate=acc, early_term=et)
+            er, xr, gr = R.bfgs(rm, sf, R.LINEAR, cg, x, it, accurate=acc, early_term=et)
+            assert e == er and np.array_equal(xo, xr) and np.array_equal(g, gr)
     maxit = (25 + len(lig["types"])) // 3                # V10: main/main.cpp:454
     for seed in (17, 4242):
         x0, st = R.random_conf(rm, seed, [-4] * 3, [4] * 3)
