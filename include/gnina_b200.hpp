@@ -427,6 +427,12 @@ class VinaScorer {
     check(gb_vina_bfgs(h_, confs_inout, n, maxiters, v3, slope, e.data(), nullptr, nullptr));
     return e;
   }
+  // quasi_newton with the --minimize parameters (BFGSAccurateLineSearch, --minimize_early_term; lib/common.h:50-60)
+  std::vector<float> minimize(float* confs_inout, int n, const gb_minimization_params& mp, const float v3[3], float slope) {
+    std::vector<float> e(n);
+    check(gb_vina_minimize(h_, confs_inout, n, &mp, v3, slope, e.data(), nullptr, nullptr));
+    return e;
+  }
   // model::eval_deriv with ig = non_cache (lib/non_cache.cpp:126-174): direct receptor sums, box = [begin, end]
   std::vector<float> eval_deriv_noncache(const float* confs, int n, const float v3[3], float slope, const float begin[3],
                                          const float end[3], std::vector<float>* change = nullptr) {
@@ -441,6 +447,15 @@ class VinaScorer {
     std::vector<float> e(n);
     std::vector<int32_t> ok(n);
     check(gb_vina_refine(h_, confs_inout, n, maxiters, v3, begin, end, e.data(), ok.data(), nullptr));
+    if (within) *within = std::move(ok);
+    return e;
+  }
+  // the --minimize / --local_only branch's refine_structure (main/main.cpp:264-268): the user's minimization_params
+  std::vector<float> refine_minimize(float* confs_inout, int n, const gb_minimization_params& mp, const float v3[3], const float begin[3],
+                                     const float end[3], std::vector<int32_t>* within = nullptr) {
+    std::vector<float> e(n);
+    std::vector<int32_t> ok(n);
+    check(gb_vina_refine_minimize(h_, confs_inout, n, &mp, v3, begin, end, e.data(), ok.data(), nullptr));
     if (within) *within = std::move(ok);
     return e;
   }
