@@ -854,13 +854,18 @@ def rows_main():
         # --- config 3 at the REFERENCE's Monte-Carlo length: num_steps = 105 (50 + N_atoms + 10 DOF) per chain (main/main.cpp:
         # 442-443), exhaustiveness 64, search -> merge -> refine_structure -> CNN rescoring -> exact affinity.  A bounded sample of
         # ligands, all in flight at once (one Vina handle + CNN clone per host thread), extrapolated to BASELINE's 1k ligands.
+        # search box: what --autobox_ligand with the default --autobox_add 4 gives for these ligands (extent ~12 A + 4 A on every side).
+        # The reference uses ONE box for grids, random starts and penalties (docking.search_box); a box as tight as the ligand keeps the
+        # output containers from ever filling (few RMSD-distinct poses fit), which makes every accepted step a "promising" one
+        # (second quasi-Newton run): measured 0.50 ligands/s with +-6 A, profiles/README.md r5z
+        AB1, AB2 = [-10, -10, -10], [10, 10, 10]
         n_full, workers_full = 64, 64
         ligs_full = [synth.make_flexible_ligand(n_heavy=20 + (i % 8), n_tors=3 + i % 4, seed=300 + i) for i in range(n_full)]
         steps_ref = [docking.reference_num_steps(len(l["types"]), 6 + len(l["seg_parent"]) - 1) for l in ligs_full]
         with docking.DockingPool(rec_xyz, rec_t, ["crossdock_default2018"], n_workers=workers_full) as pool:
-            pool.dock(ligs_full, [-6, -6, -6], [6, 6, 6], exhaustiveness=64, num_steps=50)   # warm-up: tables, workspaces
+            pool.dock(ligs_full, AB1, AB2, exhaustiveness=64, num_steps=50)   # warm-up: tables, workspaces
             t0 = time.perf_counter()
-            res = pool.dock(ligs_full, [-6, -6, -6], [6, 6, 6], exhaustiveness=64)             # num_steps=None -> reference formula
+            res = pool.dock(ligs_full, AB1, AB2, exhaustiveness=64)             # num_steps=None -> reference formula
             dt = time.perf_counter() - t0
         mc_steps = 64 * float(np.sum(steps_ref))
         # the CPU oracle beside it: one chain of one ligand for a few hundred steps, scaled to the full length
@@ -873,7 +878,7 @@ def rows_main():
         d0.mc(12345, [-6, -6, -6], [6, 6, 6], 150, int((25 + len(lig0["types"])) // 3), 50, min_rmsd=1.0, hunt_cap=(10, 10, 10))
         cpu_steps_per_s = 150 / (time.perf_counter() - t0)
         out.append({"row": "config 3 at the reference's step count: dock + refine + rescore, exhaustiveness 64", "value": n_full / dt, "unit": "ligands/s",
-                    "ligands": n_full, "in_flight": workers_full, "mc_steps_per_chain_mean": float(np.mean(steps_ref)),
+                    "ligands": n_full, "in_flight": workers_full, "search_box": "+-10 A (autobox_add 4)", "mc_steps_per_chain_mean": float(np.mean(steps_ref)),
                     "mc_steps_per_s": mc_steps / dt, "seconds_for_1k_ligands": 1000.0 * dt / n_full, "modes_out_mean": float(np.mean([len(r) for r in res])),
                     "cpu_oracle_mc_steps_per_s_1_thread": cpu_steps_per_s,
                     "cpu_oracle_ligands_per_s_per_thread": cpu_steps_per_s / (64 * float(np.mean(steps_ref))),
