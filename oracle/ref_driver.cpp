@@ -64,6 +64,7 @@
 #include "quasi_newton.h"
 #include "szv_grid.h"
 #include "weighted_terms.h"
+#include "docking_b200.h"   // integration/: the model -> gb_ligand_topology adapter a gnina maintainer adds; exercised below
 
 // read access to private data members: an explicit template instantiation may name them ([temp.spec]/6)
 template <class Tag, typename Tag::type M> struct Peek { friend typename Tag::type peek(Tag) { return M; } };
@@ -287,6 +288,27 @@ int gref_tree_derivative(void* p, const float* forces, float* out_change) {
     change g(m.get_size(), false);
     m.ligands.derivative(m.coords, m.minus_forces, g.ligands);
     read_change(g, out_change);
+  });
+}
+
+// integration/docking_b200.h's B200Ligand run on this reference model: -> counts {n_atoms, n_segments, n_pairs, n_heavy}; arrays may be null
+int gref_adapter_topology(void* p, int* counts, float* local_xyz, int* type, int* parent, int* begin, int* end, float* rel_origin,
+                          float* rel_axis, int* pair_a, int* pair_b, float* gyration_radius) {
+  RefModel* R = (RefModel*)p;
+  return guarded([&] {
+    b200::B200Ligand L(R->m);
+    counts[0] = L.topo.n_atoms; counts[1] = L.topo.n_segments; counts[2] = L.topo.n_pairs; counts[3] = L.n_heavy;
+    if (!local_xyz) return;
+    std::copy(L.local_xyz.begin(), L.local_xyz.end(), local_xyz);
+    std::copy(L.type.begin(), L.type.end(), type);
+    std::copy(L.parent.begin(), L.parent.end(), parent);
+    std::copy(L.begin.begin(), L.begin.end(), begin);
+    std::copy(L.end.begin(), L.end.end(), end);
+    std::copy(L.rel_origin.begin(), L.rel_origin.end(), rel_origin);
+    std::copy(L.rel_axis.begin(), L.rel_axis.end(), rel_axis);
+    std::copy(L.pair_a.begin(), L.pair_a.end(), pair_a);
+    std::copy(L.pair_b.begin(), L.pair_b.end(), pair_b);
+    *gyration_radius = L.topo.gyration_radius;
   });
 }
 

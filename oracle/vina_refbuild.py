@@ -34,6 +34,7 @@ def lib():
         L = C.CDLL(_SO, mode=os.RTLD_NOW)
         L.gref_last_error.restype = C.c_char_p
         L.gref_type_info.argtypes = [C.c_int, C.c_char_p, _fp, _fp, _ip]
+        L.gref_adapter_topology.argtypes = [_vp, _ip, _fp, _ip, _ip, _ip, _ip, _fp, _fp, _ip, _ip, _fp]
         L.gref_sf_create.argtypes = [C.c_float, C.c_float]; L.gref_sf_create.restype = _vp
         L.gref_sf_destroy.argtypes = [_vp]
         L.gref_cutoff_sqr.argtypes = [_vp]; L.gref_cutoff_sqr.restype = C.c_float
@@ -160,6 +161,22 @@ class RefModel:
         return o
 
     def gyration_radius(self): return lib().gref_gyration_radius(self.p)
+
+    def adapter_topology(self):
+        """integration/docking_b200.h::B200Ligand (the model -> gb_ligand_topology adapter) run on this reference model -> dict"""
+        cnt = np.zeros(4, np.int32)
+        _ok(lib().gref_adapter_topology(self.p, _i(cnt), None, None, None, None, None, None, None, None, None, None))
+        na, ns, npair, nh = (int(v) for v in cnt)
+        o = dict(local_xyz=np.empty((na, 3), np.float32), types=np.empty(na, np.int32), seg_parent=np.empty(ns, np.int32),
+                 seg_begin=np.empty(ns, np.int32), seg_end=np.empty(ns, np.int32), seg_rel_origin=np.empty((ns, 3), np.float32),
+                 seg_rel_axis=np.empty((ns, 3), np.float32), pair_a=np.empty(max(npair, 1), np.int32), pair_b=np.empty(max(npair, 1), np.int32))
+        gr = np.empty(1, np.float32)
+        _ok(lib().gref_adapter_topology(self.p, _i(cnt), _f(o["local_xyz"]), _i(o["types"]), _i(o["seg_parent"]), _i(o["seg_begin"]),
+                                        _i(o["seg_end"]), _f(o["seg_rel_origin"]), _f(o["seg_rel_axis"]), _i(o["pair_a"]), _i(o["pair_b"]),
+                                        _f(gr)))
+        o["pair_a"], o["pair_b"] = o["pair_a"][:npair], o["pair_b"][:npair]
+        o["gyration_radius"], o["n_heavy"] = float(gr[0]), nh
+        return o
 
     def tree_derivative(self, forces):
         f = np.ascontiguousarray(forces, np.float32); g = np.empty(6 + self.T, np.float32)
