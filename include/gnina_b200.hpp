@@ -295,15 +295,18 @@ using GridDims = std::array<GridDim, 3>;
 
 class VinaScorer;
 // per-atom empirical term used by NonCacheCNN's mixing (defined after VinaScorer)
-inline void vina_noncache_atoms(VinaScorer& v, const float* xyz, const int32_t* type, int n, const float begin[3], const float end[3],
-                                float cap, std::vector<float>& e, std::vector<float>& deriv);
-
-class NonCacheCNN {
-  CNNScorer& scorer_;
+// Scorer: score(xyz, types, n, want_gradient, affinity, loss, variance, gradient*) and info(model) like gb::CNNScorer; Emp:
+// noncache_atoms(xyz, types, n, begin, end, cap, e, deriv) like gb::VinaScorer.  The class is a template so that its logic -- the
+// part of non_cache_cnn.cpp that is host code here -- can be run against the REFERENCE's non_cache_cnn with test doubles on a
+// machine without a GPU (oracle/ref_driver.cpp gref_noncache_cnn_*, tests/test_oracle_vs_reference_build.py); gb::NonCacheCNN below
+// is the product instantiation.
+template <class Scorer, class Emp>
+class NonCacheCNNT {
+  Scorer& scorer_;
   GridDims gd_, cnn_gd_;
   float slope_;
   // cnn_options::mix_emp_force / mix_emp_energy / empirical_weight (lib/non_cache_cnn.cpp:113-166)
-  VinaScorer* vina_ = nullptr;
+  Emp* vina_ = nullptr;
   float emp_weight_ = 1.f;
   bool mix_force_ = false, mix_energy_ = false;
 
@@ -323,7 +326,7 @@ class NonCacheCNN {
  public:
   // search box gd; the CNN box is centred on `cnn_center` with the model's dimension (set_bounding_box,
   // cnn_torch_scorer.cpp:229-241)
-  NonCacheCNN(CNNScorer& s, const GridDims& gd, const float cnn_center[3], float slope) : scorer_(s), gd_(gd), slope_(slope) {
+  NonCacheCNNT(Scorer& s, const GridDims& gd, const float cnn_center[3], float slope) : scorer_(s), gd_(gd), slope_(slope) {
     const gb_model_info inf = s.info(0);
     for (int i = 0; i < 3; i++) {
       cnn_gd_[i].begin = cnn_center[i] - inf.dimension / 2.0f;
@@ -333,7 +336,7 @@ class NonCacheCNN {
   }
   // --cnn_mix_emp_force / --cnn_mix_emp_energy / --cnn_empirical_weight: the empirical (smina) term evaluated directly over
   // the receptor (vina must have the receptor set) is blended into the forces / the energy of eval_deriv
-  void set_empirical(VinaScorer* vina, float weight, bool mix_force, bool mix_energy) {
+  void set_empirical(Emp* vina, float weight, bool mix_force, bool mix_energy) {
     vina_ = vina; emp_weight_ = weight; mix_force_ = mix_force && vina; mix_energy_ = mix_energy && vina;
   }
   // eval (minus_forces == nullptr, lib/non_cache_cnn.cpp:33-54): loss + penalties.
@@ -349,7 +352,7 @@ class NonCacheCNN {
     const bool mixing = minus_forces && mix_force_;
     if (mixing) {
       const float b[3] = {gd_[0].begin, gd_[1].begin, gd_[2].begin}, en[3] = {gd_[0].end, gd_[1].end, gd_[2].end};
-      vina_noncache_atoms(*vina_, lig_xyz, lig_type, n, b, en, v, emp_e, emp_d);
+      vina_->noncache_atoms(lig_xyz, lig_type, n, b, en, v, emp_e, emp_d);
     }
     if (minus_forces) minus_forces->assign(3 * (size_t)n, 0.f);
     for (int i = 0; i < n; i++) {
@@ -495,9 +498,7 @@ class VinaScorer {
   int n_tors_ = 0, n_atoms_ = 0;
 };
 
-inline void vina_noncache_atoms(VinaScorer& v, const float* xyz, const int32_t* type, int n, const float begin[3], const float end[3],
-                                float cap, std::vector<float>& e, std::vector<float>& deriv) {
-  v.noncache_atoms(xyz, type, n, begin, end, cap, e, deriv);
-}
+// non_cache_cnn (lib/non_cache_cnn.h) over the library's CNN scorer and, for --cnn_mix_emp_*, its Vina scorer
+using NonCacheCNN = NonCacheCNNT<CNNScorer, VinaScorer>;
 
 }  // namespace gb

@@ -64,6 +64,8 @@
 #include "quasi_newton.h"
 #include "szv_grid.h"
 #include "weighted_terms.h"
+#include "non_cache_cnn.h"
+#include "gnina_b200.hpp"   // this repo's host-side C++ (header only): gb::NonCacheCNNT is run against non_cache_cnn below
 #include "docking_b200.h"   // integration/: the model -> gb_ligand_topology adapter a gnina maintainer adds; exercised below
 
 // read access to private data members: an explicit template instantiation may name them ([temp.spec]/6)
@@ -139,7 +141,132 @@ template <class F> int guarded(F&& f) {
 
 }  // namespace
 
+// ---- S3: test doubles so that the REFERENCE's non_cache_cnn and this repo's gb::NonCacheCNNT see the same "network" --------------
+// loss = k * sum over heavy movable atoms |x_i - target|^2, gradient 2 k (x_i - target), hydrogens untouched: any smooth function
+// would do -- what is compared is the code AROUND the network (out-of-box penalties of the search box and of the CNN box, hydrogen
+// handling, the empirical mixing of --cnn_mix_emp_force / --cnn_mix_emp_energy)
+namespace {
+struct AnalyticLoss {
+  float k = 0.01f;
+  float target[3] = {0, 0, 0};
+  float eval(const float* xyz, const int32_t* types, int n, float* grad) const {
+    float loss = 0;
+    for (int i = 0; i < n; i++) {
+      const bool heavy = types[i] >= 2;
+      for (int j = 0; j < 3; j++) {
+        const float d = xyz[3 * i + j] - target[j];
+        if (heavy) loss += k * d * d;
+        if (grad) grad[3 * i + j] = heavy ? 2 * k * d : 0.f;
+      }
+    }
+    return loss;
+  }
+};
+class FakeDLScorer : public DLScorer {
+  AnalyticLoss L;
+  fl dim, res;
+ public:
+  FakeDLScorer(const cnn_options& o, const AnalyticLoss& l, fl dim_, fl res_) : DLScorer(o), L(l), dim(dim_), res(res_) {}
+  bool initialized() const override { return true; }
+  bool has_affinity() const override { return true; }
+  float score(model& m, float& variance) override { float a, l; return score(m, false, a, l, variance); }
+  float score(model& m, bool compute_gradient, float& affinity, float& loss, float& variance) override {
+    const int n = (int)m.num_movable_atoms();
+    std::vector<float> xyz(3 * (size_t)n), g(3 * (size_t)n);
+    std::vector<int32_t> t(n);
+    for (int i = 0; i < n; i++) { t[i] = (int32_t)m.atoms[i].sm; for (int j = 0; j < 3; j++) xyz[3 * i + j] = m.coords[i][j]; }
+    m.clear_minus_forces();                                                  // CNNTorchScorer::score does (cnn_torch_scorer.cpp:115)
+    loss = L.eval(xyz.data(), t.data(), n, compute_gradient ? g.data() : nullptr);
+    if (compute_gradient) for (int i = 0; i < n; i++) m.minus_forces[i] = vec(g[3 * i], g[3 * i + 1], g[3 * i + 2]);
+    affinity = 0; variance = 0;
+    return std::exp(-loss);
+  }
+  void set_bounding_box(grid_dims& box) const override {                     // as cnn_torch_scorer.cpp:229-241
+    const vec center = get_center();
+    const fl n = dim / res, half = dim / 2.0;
+    for (unsigned i = 0; i < 3; i++) { box[i].begin = center[i] - half; box[i].end = center[i] + half; box[i].n = n; }
+  }
+  std::shared_ptr<DLScorer> fresh_copy() const override { return nullptr; }
+};
+struct FakeScorer {                                                          // the Scorer of gb::NonCacheCNNT
+  AnalyticLoss L;
+  gb_model_info inf{};
+  gb_model_info info(int = 0) const { return inf; }
+  float score(const float* xyz, const int32_t* t, int n, bool want_gradient, float& affinity, float& loss, float& variance,
+              std::vector<float>* gradient = nullptr) {
+    std::vector<float> g(3 * (size_t)n);
+    loss = L.eval(xyz, t, n, want_gradient ? g.data() : nullptr);
+    if (gradient) *gradient = g;
+    affinity = 0; variance = 0;
+    return std::exp(-loss);
+  }
+};
+// the Emp of gb::NonCacheCNNT with gb_vina_noncache_atoms's contract (include/gnina_b200.h), computed from the REFERENCE's precalculate
+// and the model's receptor atoms in index order: per heavy atom the eval_deriv sum at the position clamped to [begin, end], then curl
+struct RefEmp {
+  const precalculate* p;
+  const model* m;
+  void noncache_atoms(const float* xyz, const int32_t* type, int n, const float* b, const float* en, float cap, std::vector<float>& e,
+                      std::vector<float>& d) {
+    e.assign(n, 0.f); d.assign(3 * (size_t)n, 0.f);
+    for (int i = 0; i < n; i++) {
+      if (type[i] < 2 || type[i] >= 28) continue;
+      vec a(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+      for (int j = 0; j < 3; j++) { if (a[j] < b[j]) a[j] = b[j]; else if (a[j] > en[j]) a[j] = en[j]; }
+      fl emp_e = 0; vec emp_d(0, 0, 0);
+      atom_base A = typed(type[i]);
+      for (const atom& g : m->grid_atoms) {
+        if (g.is_hydrogen()) continue;
+        vec r; r = a - g.coords;
+        const fl r2 = sqr(r);
+        if (r2 < p->cutoff_sqr()) { pr ed = p->eval_deriv(A, g, r2); emp_e += ed.first; emp_d += ed.second * r; }
+      }
+      curl(emp_e, emp_d, (fl)cap);
+      e[i] = emp_e; for (int j = 0; j < 3; j++) d[3 * i + j] = emp_d[j];
+    }
+  }
+};
+}  // namespace
+
 extern "C" {
+
+// non_cache_cnn::eval / eval_deriv (lib/non_cache_cnn.cpp:33-54,79-169) of the REFERENCE on the model's current coordinates, and
+// gb::NonCacheCNNT (include/gnina_b200.hpp) on the same atoms, both around the same analytic "network": -> e and minus_forces of both
+int gref_noncache_cnn_compare(void* mp, void* sf, int kind, const float* begin, const float* end, const int* n, float slope, float dim,
+                              float res, float k, const float* target, int mix_force, int mix_energy, float weight, float v,
+                              int with_deriv, float* e_ref, float* f_ref, float* e_mine, float* f_mine) {
+  RefModel* R = (RefModel*)mp; RefSF* S = (RefSF*)sf;
+  return guarded([&] {
+    model& m = R->m;
+    AnalyticLoss L; L.k = k; for (int j = 0; j < 3; j++) L.target[j] = target[j];
+    cnn_options o; o.mix_emp_force = mix_force != 0; o.mix_emp_energy = mix_energy != 0; o.empirical_weight = weight;
+    FakeDLScorer dl(o, L, dim, res);
+    const grid_dims gd = make_dims(begin, end, n);
+    non_cache_cnn nc(*R->gcache, gd, S->prec[kind].get(), slope, dl);
+    const vecv saved = m.coords;
+    nc.adjust_center(m);                                     // set_center_from_model + set_bounding_box, as refine_structure does (main.cpp:136)
+    const int na = (int)m.num_movable_atoms();
+    grid user_grid;
+    if (with_deriv) {
+      *e_ref = nc.eval_deriv(m, v, user_grid);
+      for (int i = 0; i < na; i++) for (int j = 0; j < 3; j++) f_ref[3 * i + j] = m.minus_forces[i][j];
+    } else *e_ref = nc.eval(m, v);
+    // this repo's host code on the same atoms
+    FakeScorer fs; fs.L = L; fs.inf.dimension = dim; fs.inf.resolution = res;
+    RefEmp emp{S->prec[kind].get(), &m};
+    gb::GridDims g3;
+    for (int i = 0; i < 3; i++) { g3[i].begin = begin[i]; g3[i].end = end[i]; g3[i].n = n[i]; }
+    const vec c = dl.get_center();
+    const float ctr[3] = {(float)c[0], (float)c[1], (float)c[2]};
+    gb::NonCacheCNNT<FakeScorer, RefEmp> mine(fs, g3, ctr, slope);
+    mine.set_empirical(&emp, weight, mix_force != 0, mix_energy != 0);
+    std::vector<float> xyz(3 * (size_t)na), forces;
+    std::vector<int32_t> t(na);
+    for (int i = 0; i < na; i++) { t[i] = (int32_t)m.atoms[i].sm; for (int j = 0; j < 3; j++) xyz[3 * i + j] = saved[i][j]; }
+    *e_mine = mine.eval(xyz.data(), t.data(), na, with_deriv ? &forces : nullptr, v);
+    if (with_deriv) std::copy(forces.begin(), forces.end(), f_mine);
+  });
+}
 
 const char* gref_last_error() { return g_err.c_str(); }
 

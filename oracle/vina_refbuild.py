@@ -35,6 +35,8 @@ def lib():
         L.gref_last_error.restype = C.c_char_p
         L.gref_type_info.argtypes = [C.c_int, C.c_char_p, _fp, _fp, _ip]
         L.gref_adapter_topology.argtypes = [_vp, _ip, _fp, _ip, _ip, _ip, _ip, _fp, _fp, _ip, _ip, _fp]
+        L.gref_noncache_cnn_compare.argtypes = [_vp, _vp, C.c_int, _fp, _fp, _ip, C.c_float, C.c_float, C.c_float, C.c_float, _fp, C.c_int,
+                                                C.c_int, C.c_float, C.c_float, C.c_int, _fp, _fp, _fp, _fp]
         L.gref_sf_create.argtypes = [C.c_float, C.c_float]; L.gref_sf_create.restype = _vp
         L.gref_sf_destroy.argtypes = [_vp]
         L.gref_cutoff_sqr.argtypes = [_vp]; L.gref_cutoff_sqr.restype = C.c_float
@@ -230,6 +232,20 @@ class RefGrid:
         e = np.empty(1, np.float32); f = np.empty((self.m.na, 3), np.float32)
         _ok(lib().gref_ig_eval_deriv(self.p, self.m.p, v, _f(e), _f(f)))
         return float(e[0]), f
+
+
+def noncache_cnn_compare(model, sf, kind, begin, end, n, slope=10.0, dim=23.5, res=0.5, k=0.01, target=(0, 0, 0), mix_force=False,
+                         mix_energy=False, weight=1.0, v=1000.0, deriv=True):
+    """the REFERENCE's non_cache_cnn::eval / eval_deriv on the model's current coordinates vs this repo's gb::NonCacheCNNT
+    (include/gnina_b200.hpp) on the same atoms, both around the same analytic stand-in for the network
+    -> (e_ref, forces_ref, e_mine, forces_mine)"""
+    b, e, nn = (np.ascontiguousarray(a, dt) for a, dt in ((begin, np.float32), (end, np.float32), (n, np.int32)))
+    tg = np.ascontiguousarray(target, np.float32)
+    er, em = np.empty(1, np.float32), np.empty(1, np.float32)
+    fr, fm = np.zeros((model.na, 3), np.float32), np.zeros((model.na, 3), np.float32)
+    _ok(lib().gref_noncache_cnn_compare(model.p, sf.p, kind, _f(b), _f(e), _i(nn), slope, dim, res, k, _f(tg), int(mix_force),
+                                        int(mix_energy), weight, v, int(deriv), _f(er), _f(fr), _f(em), _f(fm)))
+    return float(er[0]), fr, float(em[0]), fm
 
 
 def model_eval_deriv(model, sf, kind, grid, conf, v=(1000, 1000, 1000)):

@@ -143,6 +143,32 @@ def test_refine_structure_composed_from_reference_parts(libm):
     assert left_box >= 1          # the escalation of the slope was exercised
 
 
+def test_non_cache_cnn_host_logic_matches_the_reference():
+    """S3: the product's host-side gb::NonCacheCNNT (include/gnina_b200.hpp) against the REFERENCE's non_cache_cnn::eval / eval_deriv
+    (lib/non_cache_cnn.cpp:33-54,79-169) around the same analytic stand-in for the network: out-of-box penalties of the search box
+    and of the CNN box (adjust_center / set_bounding_box), hydrogens, and the empirical mixing of --cnn_mix_emp_force /
+    --cnn_mix_emp_energy / --cnn_empirical_weight.  Same sums in another order: 1e-6."""
+    lig = dict(synth.make_flexible_ligand())
+    ty = np.array(lig["types"]).copy(); ty[5] = 1; ty[17] = 1; lig["types"] = ty        # two polar hydrogens
+    rx, rt = synth.make_receptor(600, box=30)
+    sf = R.RefScoring(); rm = R.RefModel(lig, rx, rt)
+    rs = np.random.RandomState(0)
+    begin, end, n = [-6.1] * 3, [5.9] * 3, [32, 32, 32]
+    outside = 0
+    for x in _confs(rs, lig, rm.T, 30, spread=9.0):
+        c = rm.set(x)
+        outside += bool(((c < -6.1) | (c > 5.9)).any())
+        for mf, me in ((False, False), (True, False), (True, True), (False, True)):
+            for deriv in (True, False):
+                er, fr, em, fm = R.noncache_cnn_compare(rm, sf, R.LINEAR, begin, end, n, slope=10.0, dim=12.0, res=0.5, k=0.02,
+                                                        target=(0.5, -0.3, 0.2), mix_force=mf, mix_energy=me, weight=0.7, deriv=deriv)
+                assert abs(er - em) <= 1e-6 * max(1.0, abs(er)), (mf, me, deriv, er, em)
+                assert np.abs(fr - fm).max() <= 1e-6 * max(1.0, np.abs(fr).max())
+                if deriv:
+                    assert (fm[[5, 17]] == 0).all() and (fr[[5, 17]] == 0).all()       # hydrogens carry no force
+    assert outside >= 5
+
+
 def test_grid_aligned_to_three_angstrom_shows_the_reference_cell_list_quirk():
     """szv_grid_cache::get (lib/szv_grid.h:124-150) sizes a 3 A cell's atom list by the brick [floor(c/3)*3, ceil(c/3)*3] of the FIRST
     probe point that touches the cell: when that coordinate is an exact multiple of 3 the brick collapses and the list misses atoms
