@@ -658,8 +658,10 @@ static void score_poses_common(Vina& v, const float* lig_xyz, const int32_t* lig
 //       add_to_output_container (lib/coords.cpp:25-56); V11: chains are independent -> one launch for all of them
 //       (the reference farms them to a boost thread pool, lib/parallel_mc.cpp:183-214)
 // Random numbers: xorshift32 exactly as oracle/vina_mc_ref.c (Boost's distributions are not reproducible here).
-// Summation order inside one evaluation differs from the sequential reference (warp reductions, shared-memory
-// atomics), so energies agree to float round-off, and long BFGS / MC trajectories are compared statistically.
+// Every sum follows the reference's sequential float association (atom energies in atom order, pair energies in pair order, forces
+// per atom in pair-list order, children folded into parents in ascending order; no FMA contraction in this file), so single
+// evaluations agree with the restatement to the last bits of the transcendentals and BFGS / Monte-Carlo trajectories are compared step
+// by step; the restatement itself is bit-identical to the reference's own code compiled in oracle/_ref.
 // =================================================================================================================
 namespace gb {
 
@@ -1087,7 +1089,8 @@ __device__ inline float dk_lambdamin(const float* x, const float* p, int n) {
   #pragma unroll 1
   for (int i = 0; i < n; i++) {
     const float xi = i < 3 ? x[i] : (i < 6 ? ang[i - 3] : x[7 + i - 6]);
-    const float temp = fabsf(p[i]) / fmaxf(fabsf(xi), 1.0f);
+    const float ax = fabsf(xi);
+    const float temp = fabsf(p[i]) / ((ax < 1.0f) ? 1.0f : ax);   // std::max(std::fabs(x(i)), 1.0f)
     if (temp > test) test = temp;
   }
   return test;
@@ -1168,7 +1171,7 @@ __device__ float dk_bfgs(const LigPtrs& L, const DockField& F, WarpWs& W, int ma
             if (tmplam > .5 * alpha) tmplam = (float)(.5 * alpha);
           }
           alpha2 = alpha; f2 = f1;
-          alpha = fmaxf(tmplam, 0.1f * alpha);
+          { const float tenth = 0.1f * alpha; alpha = (tmplam < tenth) ? tenth : tmplam; }   // std::max: a NaN tmplam stays NaN
           ls_over = false;
         }
       } else {

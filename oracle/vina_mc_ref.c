@@ -359,7 +359,8 @@ static float bfgs_impl(const gvo_field *F, const gvo_lig *L, float *x, float *g,
       } else {
         q_to_angle(x + 3, ang);
         for (int i = 0; i < n; i++) { /* compute_lambdamin :93-102 */
-          const float temp = fabsf(p[i]) / fmaxf(fabsf(conf_at(x, i, ang)), 1.0f);
+          const float ax = fabsf(conf_at(x, i, ang));
+          const float temp = fabsf(p[i]) / ((ax < 1.0f) ? 1.0f : ax); /* std::max(std::fabs(x(i)), 1.0f) */
           if (temp > test) test = temp;
         }
         alamin = kEps / test;
@@ -387,7 +388,7 @@ static float bfgs_impl(const gvo_field *F, const gvo_lig *L, float *x, float *g,
             if (tmplam > .5 * alpha) tmplam = (float)(.5 * alpha);
           }
           alpha2 = alpha; f2 = f1;
-          alpha = fmaxf(tmplam, 0.1f * alpha);
+          { const float tenth = 0.1f * alpha; alpha = (tmplam < tenth) ? tenth : tmplam; } /* std::max: a NaN tmplam stays NaN */
         }
       }
     }
