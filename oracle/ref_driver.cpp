@@ -65,6 +65,7 @@
 #include "szv_grid.h"
 #include "weighted_terms.h"
 #include "non_cache_cnn.h"
+#include "parallel_mc.h"
 #include "gnina_b200.hpp"   // this repo's host-side C++ (header only): gb::NonCacheCNNT is run against non_cache_cnn below
 #include "docking_b200.h"   // integration/: the model -> gb_ligand_topology adapter a gnina maintainer adds; exercised below
 
@@ -583,6 +584,32 @@ int gref_mc(void* mp, void* sf, int kind, void* gp, const float* c1, const float
     igrid& ig = *((RefGrid*)gp)->ig;
     R->m.set(make_conf(R->m, state_conf));  // the conformation the model object holds when the chain starts (mutate_conf reads it)
     mc(R->m, out, *S->prec[kind], ig, vec(c1[0], c1[1], c1[2]), vec(c2[0], c2[1], c2[2]), nullptr, gen, user_grid, ig);
+    const int T = R->n_seg - 1;
+    *n_out = (int)std::min<sz>(out.size(), (sz)max_out);
+    for (int i = 0; i < *n_out; i++) { out_e[i] = out[i].e; read_conf(out[i].c, out_conf + (size_t)i * (7 + T)); }
+  });
+}
+// parallel_mc::operator() (lib/parallel_mc.cpp:183-214): task seeds random_int(0, 1000000, generator), one monte_carlo chain per task on
+// the reference's own thread pool (lib/parallel.h), merge_output_containers (min_rmsd forced to 2) and the final sort
+int gref_parallel_mc(void* mp, void* sf, int kind, void* gp, const float* c1, const float* c2, unsigned seed, int num_tasks, int num_threads,
+                     int num_steps, int maxiters, int num_saved_mins, float temperature, float amplitude, float min_rmsd, const float* hunt_cap,
+                     const float* state_conf, const float* box_begin, const float* box_end, const int* box_n, int max_out, float* out_e,
+                     float* out_conf, int* n_out) {
+  RefModel* R = (RefModel*)mp; RefSF* S = (RefSF*)sf;
+  return guarded([&] {
+    parallel_mc par;
+    par.num_tasks = (sz)num_tasks; par.num_threads = (sz)num_threads; par.display_progress = false;
+    par.mc.num_steps = (unsigned)num_steps; par.mc.temperature = temperature;
+    par.mc.hunt_cap = vec(hunt_cap[0], hunt_cap[1], hunt_cap[2]);
+    par.mc.min_rmsd = min_rmsd; par.mc.num_saved_mins = (sz)num_saved_mins; par.mc.mutation_amplitude = amplitude;
+    par.mc.ssd_par.minparm.maxiters = (unsigned)maxiters;
+    rng gen(seed);
+    output_container out;
+    grid user_grid;
+    igrid& ig = *((RefGrid*)gp)->ig;
+    R->m.set(make_conf(R->m, state_conf));
+    non_cache nc(*R->gcache, make_dims(box_begin, box_end, box_n), S->prec[kind].get(), 1e3);   // only passed through (no CNN)
+    par(R->m, out, *S->prec[kind], ig, vec(c1[0], c1[1], c1[2]), vec(c2[0], c2[1], c2[2]), gen, user_grid, nc);
     const int T = R->n_seg - 1;
     *n_out = (int)std::min<sz>(out.size(), (sz)max_out);
     for (int i = 0; i < *n_out; i++) { out_e[i] = out[i].e; read_conf(out[i].c, out_conf + (size_t)i * (7 + T)); }

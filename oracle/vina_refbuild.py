@@ -68,6 +68,8 @@ def lib():
         L.gref_random_conf.argtypes = [_vp, C.c_uint32, _fp, _fp, _fp, C.POINTER(C.c_uint32)]
         L.gref_mc.argtypes = [_vp, _vp, C.c_int, _vp, _fp, _fp, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                               _fp, _fp, C.c_int, _fp, _fp, C.POINTER(C.c_int)]
+        L.gref_parallel_mc.argtypes = [_vp, _vp, C.c_int, _vp, _fp, _fp, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                       C.c_float, C.c_float, _fp, _fp, _fp, _fp, _ip, C.c_int, _fp, _fp, C.POINTER(C.c_int)]
         L.gref_container_replay.argtypes = [C.c_int, C.c_int, _fp, _fp, C.c_float, C.c_int, _fp, C.POINTER(C.c_int)]
         _lib = L
     return _lib
@@ -286,6 +288,29 @@ def mc(model, sf, kind, grid, seed, c1, c2, num_steps, maxiters, state_conf, num
                       num_steps, maxiters, num_saved_mins, temperature, amplitude, min_rmsd, _f(hc), _f(sc), num_saved_mins, _f(e), _f(x),
                       C.byref(n)))
     return e[:n.value], x[:n.value]
+
+
+def parallel_mc(model, sf, kind, grid, seed, c1, c2, num_tasks, num_steps, maxiters, state_conf, box, num_threads=2, num_saved_mins=50,
+                temperature=1.2, amplitude=2.0, min_rmsd=1.0, hunt_cap=(10, 10, 10)):
+    """parallel_mc::operator() (lib/parallel_mc.cpp:183-214) on the reference's own thread pool -> merged, sorted container (e, confs);
+    box = (begin, end, n) of the non_cache that is passed through"""
+    e = np.zeros(num_saved_mins, np.float32); x = np.zeros((num_saved_mins, 7 + model.T), np.float32); n = C.c_int()
+    k = lambda a, dt: np.ascontiguousarray(a, dt)
+    hc, sc = k(hunt_cap, np.float32), k(state_conf, np.float32)
+    bb, be, bn = k(box[0], np.float32), k(box[1], np.float32), k(box[2], np.int32)
+    _ok(lib().gref_parallel_mc(model.p, sf.p, kind, grid.p, _f(k(c1, np.float32)), _f(k(c2, np.float32)), seed, num_tasks, num_threads,
+                               num_steps, maxiters, num_saved_mins, temperature, amplitude, min_rmsd, _f(hc), _f(sc), _f(bb), _f(be), _i(bn),
+                               num_saved_mins, _f(e), _f(x), C.byref(n)))
+    return e[:n.value], x[:n.value]
+
+
+def task_seeds(seed, num_tasks):
+    """the seeds parallel_mc draws for its tasks: random_int(0, 1000000, generator) on the stand-in generator (xorshift32, a + next % range)"""
+    s, out = (seed or 1) & 0xFFFFFFFF, []
+    for _ in range(num_tasks):
+        s ^= (s << 13) & 0xFFFFFFFF; s ^= s >> 17; s ^= (s << 5) & 0xFFFFFFFF
+        out.append(s % 1000001)
+    return out
 
 
 def container_replay(e, coords, min_rmsd, max_size):

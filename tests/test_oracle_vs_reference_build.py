@@ -143,6 +143,35 @@ def test_refine_structure_composed_from_reference_parts(libm):
     assert left_box >= 1          # the escalation of the slope was exercised
 
 
+def test_parallel_mc_fan_out_and_merge(libm):
+    """V11: the REFERENCE's parallel_mc::operator() (lib/parallel_mc.cpp:183-214) on its own thread pool (lib/parallel.h) -- task seeds
+    random_int(0, 1000000, generator), one chain per task, merge_output_containers with min_rmsd forced to 2, final sort -- against the
+    restatement's chains merged by the host-side rule (Python statement and the library's gb_vina_merge_outputs)"""
+    from gnina_b200 import docking
+    lig = synth.make_flexible_ligand()
+    sf, vo, rm, cg, d, lig2, rx, rt = _setup(lig)
+    c1, c2 = [-5] * 3, [5] * 3
+    maxit, S = (25 + len(lig["types"])) // 3, 20
+    heavy = np.flatnonzero(np.asarray(lig["types"]) > 1)
+    for seed, tasks, steps in ((4242, 4, 40), (777, 6, 60)):
+        er, xr = R.parallel_mc(rm, sf, R.LINEAR, cg, seed, c1, c2, tasks, steps, maxit, lig["conf0"], (BEGIN, END, N), num_threads=3,
+                               num_saved_mins=S)
+        oc = docking.OutputContainer(2.0, S)
+        E, X, C, n_out = np.zeros((tasks, S), np.float32), np.zeros((tasks, S, 7 + d.T), np.float32), np.zeros((tasks, S, len(heavy), 3), np.float32), []
+        for c, ts in enumerate(R.task_seeds(seed, tasks)):
+            x0, st = R.random_conf(rm, ts, c1, c2)
+            e, x = d.mc_ex(st, c1, c2, steps, maxit, num_saved_mins=S, init_conf=x0, state_conf=lig["conf0"])
+            n_out.append(len(e))
+            for k in range(len(e)):
+                hv = d.coords(x[k])[heavy]
+                oc.add(e[k], hv, x[k])
+                E[c, k], X[c, k], C[c, k] = e[k], x[k], hv
+        em, xm = np.float32([o["e"] for o in oc.items]), np.stack([o["conf"] for o in oc.items])
+        assert len(er) == len(em) and np.array_equal(er, em) and np.array_equal(xr, xm)
+        nat = docking.merge_chains_native(E, X, C, np.int32(n_out), S)
+        assert np.array_equal(np.float32([o["e"] for o in nat]), er) and np.array_equal(np.stack([o["conf"] for o in nat]), xr)
+
+
 def test_non_cache_cnn_host_logic_matches_the_reference():
     """S3: the product's host-side gb::NonCacheCNNT (include/gnina_b200.hpp) against the REFERENCE's non_cache_cnn::eval / eval_deriv
     (lib/non_cache_cnn.cpp:33-54,79-169) around the same analytic stand-in for the network: out-of-box penalties of the search box
