@@ -269,6 +269,33 @@ int gref_noncache_cnn_compare(void* mp, void* sf, int kind, const float* begin, 
   });
 }
 
+// quasi_newton::operator() with ig = non_cache_cnn around the analytic test double: what --minimize --cnn_scoring all runs per pose
+// (main/main.cpp:264-268 -> refine_structure -> quasi_newton; here ONE quasi-Newton run, no slope escalation); x is updated
+int gref_minimize_cnn(void* mp, void* sf, int kind, const float* begin, const float* end, const int* n, float slope, float dim, float res,
+                      float k, const float* target, float* x, int maxiters, int accurate, int early_term, float* e) {
+  RefModel* R = (RefModel*)mp; RefSF* S = (RefSF*)sf;
+  return guarded([&] {
+    model& m = R->m;
+    AnalyticLoss L; L.k = k; for (int j = 0; j < 3; j++) L.target[j] = target[j];
+    cnn_options o;
+    FakeDLScorer dl(o, L, dim, res);
+    non_cache_cnn nc(*R->gcache, make_dims(begin, end, n), S->prec[kind].get(), slope, dl);
+    m.set(make_conf(m, x));
+    nc.adjust_center(m);
+    minimization_params mp_;
+    mp_.maxiters = (unsigned)maxiters;
+    mp_.type = accurate ? minimization_params::BFGSAccurateLineSearch : minimization_params::BFGSFastLineSearch;
+    mp_.early_term = early_term != 0;
+    quasi_newton qn(mp_);
+    output_type out(make_conf(m, x), 0);
+    change g(m.get_size(), false);
+    grid user_grid;
+    qn(m, *S->prec[kind], nc, out, g, vec(1000, 1000, 1000), user_grid);
+    *e = out.e;
+    read_conf(out.c, x);
+  });
+}
+
 const char* gref_last_error() { return g_err.c_str(); }
 
 // ---- G0: the smina type table (lib/atom_constants.h:45-133, the `data` array the typers and xs_radius() read) ------------------

@@ -37,6 +37,8 @@ def lib():
         L.gref_adapter_topology.argtypes = [_vp, _ip, _fp, _ip, _ip, _ip, _ip, _fp, _fp, _ip, _ip, _fp]
         L.gref_noncache_cnn_compare.argtypes = [_vp, _vp, C.c_int, _fp, _fp, _ip, C.c_float, C.c_float, C.c_float, C.c_float, _fp, C.c_int,
                                                 C.c_int, C.c_float, C.c_float, C.c_int, _fp, _fp, _fp, _fp]
+        L.gref_minimize_cnn.argtypes = [_vp, _vp, C.c_int, _fp, _fp, _ip, C.c_float, C.c_float, C.c_float, C.c_float, _fp, _fp, C.c_int,
+                                        C.c_int, C.c_int, _fp]
         L.gref_sf_create.argtypes = [C.c_float, C.c_float]; L.gref_sf_create.restype = _vp
         L.gref_sf_destroy.argtypes = [_vp]
         L.gref_cutoff_sqr.argtypes = [_vp]; L.gref_cutoff_sqr.restype = C.c_float
@@ -248,6 +250,17 @@ def noncache_cnn_compare(model, sf, kind, begin, end, n, slope=10.0, dim=23.5, r
     _ok(lib().gref_noncache_cnn_compare(model.p, sf.p, kind, _f(b), _f(e), _i(nn), slope, dim, res, k, _f(tg), int(mix_force),
                                         int(mix_energy), weight, v, int(deriv), _f(er), _f(fr), _f(em), _f(fm)))
     return float(er[0]), fr, float(em[0]), fm
+
+
+def minimize_cnn(model, sf, kind, begin, end, n, conf, maxiters, slope=10.0, dim=23.5, res=0.5, k=0.01, target=(0, 0, 0), accurate=True,
+                 early_term=False):
+    """the REFERENCE's quasi_newton with ig = non_cache_cnn around the analytic stand-in for the network (one --minimize run of one
+    pose) -> (e, conf)"""
+    b, e_, nn = (np.ascontiguousarray(a, dt) for a, dt in ((begin, np.float32), (end, np.float32), (n, np.int32)))
+    x = np.array(conf, np.float32); tg = np.ascontiguousarray(target, np.float32); e = np.empty(1, np.float32)
+    _ok(lib().gref_minimize_cnn(model.p, sf.p, kind, _f(b), _f(e_), _i(nn), slope, dim, res, k, _f(tg), _f(x), maxiters, int(accurate),
+                                int(early_term), _f(e)))
+    return float(e[0]), x
 
 
 def model_eval_deriv(model, sf, kind, grid, conf, v=(1000, 1000, 1000)):

@@ -198,6 +198,60 @@ def test_non_cache_cnn_host_logic_matches_the_reference():
     assert outside >= 5
 
 
+def _host_libm():
+    import ctypes
+    m = ctypes.CDLL("libm.so.6")
+
+    def wrap(name):
+        f = getattr(m, name); f.argtypes = [ctypes.c_float]; f.restype = ctypes.c_float
+        return lambda a: np.array([f(float(v)) for v in np.asarray(a, np.float32).ravel()], np.float32).reshape(np.shape(a))
+    return wrap("sinf"), wrap("cosf"), wrap("acosf")
+
+
+def test_lock_step_minimiser_reproduces_the_reference_pose_by_pose():
+    """gnina_b200/minimize.py (BASELINE config 5: --minimize --cnn_scoring all over many poses): ALL poses advance together, one batched
+    energy call per round, and every pose ends exactly where the REFERENCE's quasi_newton + non_cache_cnn takes it when it minimises that
+    pose alone (lib/quasi_newton.cpp:49-83, bfgs.h with the accurate and the fast line search, --minimize_early_term, both out-of-box
+    penalties, torsion-tree kinematics) -- energies and conformations bit for bit, around the same analytic stand-in for the network"""
+    from gnina_b200 import minimize
+    lig = dict(synth.make_flexible_ligand())
+    ty = np.array(lig["types"]).copy(); ty[5] = 1; lig["types"] = ty
+    rx, rt = synth.make_receptor(300, box=30)
+    sf = R.RefScoring(); rm = R.RefModel(lig, rx, rt)
+    lo, ro, ra = rm.export()
+    lig2 = dict(lig); lig2["local_xyz"], lig2["seg_rel_origin"], lig2["seg_rel_axis"] = lo, ro, ra
+    tree = minimize.TorsionTree(lig2)
+    heavy = np.asarray(lig["types"]) >= 2
+    k, target = np.float32(0.02), np.float32([0.5, -0.3, 0.2])
+    begin, end, nn, slope, dim = [-8.0] * 3, [8.0] * 3, [43, 43, 43], 10.0, 20.0
+    X = _confs(np.random.RandomState(3), lig, tree.T, 16, spread=6.0)
+    minimize.set_transcendentals(*_host_libm())              # the reference build executes this host's sinf / cosf / acosf
+    try:
+        centers = minimize.heavy_centers(tree.set_conf(X)[0], heavy)
+        half = np.float32(dim) / np.float32(2)
+        calls = [0]
+
+        def energy(coords, idx):
+            calls[0] += 1
+            d = coords - target
+            loss = np.zeros(len(coords), np.float32)
+            for a in np.flatnonzero(heavy):
+                for j in range(3):
+                    loss = (loss + k * d[:, a, j] * d[:, a, j]).astype(np.float32)
+            c = centers[idx][:, None, :]
+            return minimize.with_box_penalties(loss, (2 * k * d).astype(np.float32), coords, heavy, (begin, end), (c - half, c + half), slope)
+        for acc, et, iters in ((True, False, 10000), (False, True, 200)):
+            calls[0] = 0
+            e, x, ev, rounds = minimize.minimize_poses(tree, energy, X, maxiters=iters, accurate=acc, early_term=et)
+            for i in range(len(X)):
+                er, xr = R.minimize_cnn(rm, sf, R.LINEAR, begin, end, nn, X[i], iters, slope=slope, dim=dim, res=0.5, k=float(k),
+                                        target=target, accurate=acc, early_term=et)
+                assert er == e[i] and np.array_equal(xr, x[i]), (acc, et, i)
+            assert calls[0] == rounds + 1 and calls[0] < 0.5 * ev.sum()      # batched: far fewer energy calls than evaluations
+    finally:
+        minimize.set_transcendentals()
+
+
 def test_grid_aligned_to_three_angstrom_shows_the_reference_cell_list_quirk():
     """szv_grid_cache::get (lib/szv_grid.h:124-150) sizes a 3 A cell's atom list by the brick [floor(c/3)*3, ceil(c/3)*3] of the FIRST
     probe point that touches the cell: when that coordinate is an exact multiple of 3 the brick collapses and the list misses atoms
