@@ -360,6 +360,50 @@ def minimize_poses(tree, energy_and_forces, X0, maxiters=10000, accurate=True, e
     return f0, x, evals, rounds
 
 
+MAX_FL = F(3.4028234663852886e+38)
+
+
+def refine_structure_poses(tree, make_energy, within, X0, maxiters, accurate=False, early_term=False):
+    """refine_structure (main/main.cpp:131-171) for many poses in lock step: up to five quasi-Newton runs with the out-of-box slope 10,
+    100, ... ; after each run the poses that are `within` the box are finished, the others go on with the slope x 10; a pose that never
+    gets inside ends with e = max_fl (:163-164).  make_energy(slope) -> energy_and_forces(coords, idx) (e.g. cnn_energy with that
+    slope: --cnn_scoring refinement), within(coords [k,na,3], idx) -> bool [k] (non_cache_cnn::within, within_boxes below).
+    -> (e [n], X [n, 7+T], inside [n], function evaluations [n])"""
+    x = np.ascontiguousarray(X0, F).copy()
+    n = len(x)
+    e, evals = np.zeros(n, F), np.zeros(n, np.int64)
+    todo = np.arange(n)
+    slope = 10.0
+    for _ in range(5):
+        energy = make_energy(slope)
+        ee, xx, ev, _ = minimize_poses(tree, lambda c, i, t=todo: energy(c, t[i]), x[todo], maxiters, accurate, early_term)
+        e[todo], x[todo] = ee, xx
+        evals[todo] += ev
+        ok = within(tree.set_conf(xx)[0], todo)
+        todo = todo[~ok]
+        if not len(todo):
+            break
+        slope *= 10
+    inside = np.ones(n, bool); inside[todo] = False
+    e[todo] = MAX_FL
+    return e, x, inside, evals
+
+
+def within_boxes(heavy, boxes, margin=1e-4):
+    """non_cache_cnn::within (lib/non_cache_cnn.cpp:73-76) = inside ANY of the boxes (the CNN grid or the search box); every box is
+    (begin, end) with arrays broadcastable to [k,1,3] after indexing by idx (per-pose CNN boxes) or plain [3]"""
+    def f(coords, idx):
+        res = np.zeros(len(coords), bool)
+        for b, e in boxes:
+            b, e = np.asarray(b, F), np.asarray(e, F)
+            if b.ndim == 2:
+                b, e = b[idx][:, None, :], e[idx][:, None, :]
+            inside = ((coords >= b - F(margin)) & (coords <= e + F(margin))).all(axis=2)      # gd_within: every heavy atom
+            res |= (inside | ~heavy[None, :]).all(axis=1)
+        return res
+    return f
+
+
 def box_penalty(coords, heavy, begin, end, slope):
     """non_cache::check_bounds_deriv (lib/non_cache.cpp:102-123) for every atom of every pose -> (penalty [n, na], derivative [n,na,3]);
     zero for hydrogens"""

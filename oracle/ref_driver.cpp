@@ -296,6 +296,42 @@ int gref_minimize_cnn(void* mp, void* sf, int kind, const float* begin, const fl
   });
 }
 
+// refine_structure (main/main.cpp:131-171, which is not a library source) replayed with the REFERENCE's parts on ig = non_cache_cnn:
+// adjust_center once, then up to five quasi_newton runs with the slope 10, 100, ... until non_cache_cnn::within -- the refinement of
+// --cnn_scoring refinement / all.  x is updated; *inside tells whether the pose ended within
+int gref_refine_cnn(void* mp, void* sf, int kind, const float* begin, const float* end, const int* n, float dim, float res, float k,
+                    const float* target, float* x, int maxiters, int accurate, int early_term, float* e, int* inside) {
+  RefModel* R = (RefModel*)mp; RefSF* S = (RefSF*)sf;
+  return guarded([&] {
+    model& m = R->m;
+    AnalyticLoss L; L.k = k; for (int j = 0; j < 3; j++) L.target[j] = target[j];
+    cnn_options o;
+    FakeDLScorer dl(o, L, dim, res);
+    non_cache_cnn nc(*R->gcache, make_dims(begin, end, n), S->prec[kind].get(), 1e3, dl);
+    m.set(make_conf(m, x));
+    nc.adjust_center(m);
+    minimization_params mp_;
+    mp_.maxiters = (unsigned)maxiters;
+    mp_.type = accurate ? minimization_params::BFGSAccurateLineSearch : minimization_params::BFGSFastLineSearch;
+    mp_.early_term = early_term != 0;
+    quasi_newton qn(mp_);
+    output_type out(make_conf(m, x), 0);
+    change g(m.get_size(), false);
+    grid user_grid;
+    fl slope = 10;
+    for (int p = 0; p < 5; p++) {
+      nc.setSlope(slope);
+      qn(m, *S->prec[kind], nc, out, g, vec(1000, 1000, 1000), user_grid);
+      m.set(out.c);
+      if (nc.within(m)) break;
+      slope *= 10;
+    }
+    *inside = nc.within(m) ? 1 : 0;
+    *e = *inside ? out.e : max_fl;
+    read_conf(out.c, x);
+  });
+}
+
 const char* gref_last_error() { return g_err.c_str(); }
 
 // ---- G0: the smina type table (lib/atom_constants.h:45-133, the `data` array the typers and xs_radius() read) ------------------

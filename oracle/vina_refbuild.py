@@ -39,6 +39,8 @@ def lib():
                                                 C.c_int, C.c_float, C.c_float, C.c_int, _fp, _fp, _fp, _fp]
         L.gref_minimize_cnn.argtypes = [_vp, _vp, C.c_int, _fp, _fp, _ip, C.c_float, C.c_float, C.c_float, C.c_float, _fp, _fp, C.c_int,
                                         C.c_int, C.c_int, _fp]
+        L.gref_refine_cnn.argtypes = [_vp, _vp, C.c_int, _fp, _fp, _ip, C.c_float, C.c_float, C.c_float, _fp, _fp, C.c_int, C.c_int, C.c_int,
+                                      _fp, _ip]
         L.gref_sf_create.argtypes = [C.c_float, C.c_float]; L.gref_sf_create.restype = _vp
         L.gref_sf_destroy.argtypes = [_vp]
         L.gref_cutoff_sqr.argtypes = [_vp]; L.gref_cutoff_sqr.restype = C.c_float
@@ -261,6 +263,16 @@ def minimize_cnn(model, sf, kind, begin, end, n, conf, maxiters, slope=10.0, dim
     _ok(lib().gref_minimize_cnn(model.p, sf.p, kind, _f(b), _f(e_), _i(nn), slope, dim, res, k, _f(tg), _f(x), maxiters, int(accurate),
                                 int(early_term), _f(e)))
     return float(e[0]), x
+
+
+def refine_cnn(model, sf, kind, begin, end, n, conf, maxiters, dim=23.5, res=0.5, k=0.01, target=(0, 0, 0), accurate=False, early_term=False):
+    """refine_structure (main/main.cpp:131-171) replayed with the reference's quasi_newton / non_cache_cnn / within around the analytic
+    stand-in for the network -> (e or max_fl, conf, inside)"""
+    b, e_, nn = (np.ascontiguousarray(a, dt) for a, dt in ((begin, np.float32), (end, np.float32), (n, np.int32)))
+    x = np.array(conf, np.float32); tg = np.ascontiguousarray(target, np.float32); e = np.empty(1, np.float32); ins = np.zeros(1, np.int32)
+    _ok(lib().gref_refine_cnn(model.p, sf.p, kind, _f(b), _f(e_), _i(nn), dim, res, k, _f(tg), _f(x), maxiters, int(accurate), int(early_term),
+                              _f(e), _i(ins)))
+    return float(e[0]), x, bool(ins[0])
 
 
 def model_eval_deriv(model, sf, kind, grid, conf, v=(1000, 1000, 1000)):

@@ -252,6 +252,47 @@ def test_lock_step_minimiser_reproduces_the_reference_pose_by_pose():
         minimize.set_transcendentals()
 
 
+def test_lock_step_cnn_refinement_reproduces_refine_structure():
+    """--cnn_scoring refinement: refine_structure (main/main.cpp:131-171) on ig = non_cache_cnn for many poses at once
+    (minimize.refine_structure_poses) vs the reference's parts replayed pose by pose: the slope escalates 10, 100, ... while a spring
+    pulls the ligand out of both boxes; energies (max_fl for a pose that stays outside), conformations and the within flag coincide"""
+    from gnina_b200 import minimize
+    lig = dict(synth.make_flexible_ligand())
+    ty = np.array(lig["types"]).copy(); ty[5] = 1; lig["types"] = ty
+    rx, rt = synth.make_receptor(300, box=30)
+    sf = R.RefScoring(); rm = R.RefModel(lig, rx, rt)
+    lo, ro, ra = rm.export()
+    lig2 = dict(lig); lig2["local_xyz"], lig2["seg_rel_origin"], lig2["seg_rel_axis"] = lo, ro, ra
+    tree = minimize.TorsionTree(lig2)
+    heavy = np.asarray(lig["types"]) >= 2
+    k, target = np.float32(0.2), np.float32([14.0, 0.0, 0.0])
+    begin, end, nn, dim = [-7.0] * 3, [7.0] * 3, [38, 38, 38], 12.0
+    X = _confs(np.random.RandomState(7), lig, tree.T, 10, spread=3.0)
+    minimize.set_transcendentals(*_host_libm())
+    try:
+        centers = minimize.heavy_centers(tree.set_conf(X)[0], heavy)
+        half = np.float32(dim) / np.float32(2)
+
+        def make_energy(slope):
+            def energy(coords, idx):
+                d = coords - target
+                loss = np.zeros(len(coords), np.float32)
+                for a in np.flatnonzero(heavy):
+                    for j in range(3):
+                        loss = (loss + k * d[:, a, j] * d[:, a, j]).astype(np.float32)
+                c = centers[idx][:, None, :]
+                return minimize.with_box_penalties(loss, (2 * k * d).astype(np.float32), coords, heavy, (begin, end), (c - half, c + half), slope)
+            return energy
+        within = minimize.within_boxes(heavy, [(centers - half, centers + half), (np.float32(begin), np.float32(end))])
+        e, x, inside, ev = minimize.refine_structure_poses(tree, make_energy, within, X, 30)
+        for i in range(len(X)):
+            er, xr, ins = R.refine_cnn(rm, sf, R.LINEAR, begin, end, nn, X[i], 30, dim=dim, res=0.5, k=float(k), target=target)
+            assert er == e[i] and np.array_equal(xr, x[i]) and ins == bool(inside[i]), i
+        assert ev.max() > 3 * ev.min()          # some poses needed several passes
+    finally:
+        minimize.set_transcendentals()
+
+
 def test_grid_aligned_to_three_angstrom_shows_the_reference_cell_list_quirk():
     """szv_grid_cache::get (lib/szv_grid.h:124-150) sizes a 3 A cell's atom list by the brick [floor(c/3)*3, ceil(c/3)*3] of the FIRST
     probe point that touches the cell: when that coordinate is an exact multiple of 3 the brick collapses and the list misses atoms
