@@ -99,6 +99,7 @@ class CNNScorer {
     return c;
   }
   void set_option(const char* key, double v) { check(gb_cnn_set_option(h_, key, v)); }
+  gb_cnn* handle() const { return h_; }   // for the C-ABI level helpers (gnina_b200_minimize.hpp's CnnBatchEnergy)
   gb_model_info info(int i = 0) const { gb_model_info x; check(gb_model_get_info(models_.at(i), &x)); return x; }
   void set_receptor(const float* xyz, const int32_t* smina_type, int n) {
     check(gb_cnn_set_receptor(h_, xyz, smina_type, n));
@@ -363,7 +364,7 @@ class NonCacheCNNT {
       e += pen;
       if (minus_forces) {
         for (int k = 0; k < 3; k++) {
-          float f = grad[3 * i + k] + d_emp_box[k] + d_cnn_box[k];
+          float f = grad[3 * i + k] + (d_emp_box[k] + d_cnn_box[k]);   // the reference adds (0 + oob + cnn_oob) to the CNN force
           if (mixing) f = (f + emp_weight_ * (emp_d[3 * i + k] + d_emp_box[k])) / (1.0f + emp_weight_);
           (*minus_forces)[3 * i + k] = f;
         }

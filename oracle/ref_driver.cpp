@@ -67,6 +67,7 @@
 #include "non_cache_cnn.h"
 #include "parallel_mc.h"
 #include "gnina_b200.hpp"   // this repo's host-side C++ (header only): gb::NonCacheCNNT is run against non_cache_cnn below
+#include "gnina_b200_minimize.hpp"   // gb::minimize_poses (lock-step quasi-Newton) is run against quasi_newton + non_cache_cnn below
 #include "docking_b200.h"   // integration/: the model -> gb_ligand_topology adapter a gnina maintainer adds; exercised below
 
 // read access to private data members: an explicit template instantiation may name them ([temp.spec]/6)
@@ -293,6 +294,53 @@ int gref_minimize_cnn(void* mp, void* sf, int kind, const float* begin, const fl
     qn(m, *S->prec[kind], nc, out, g, vec(1000, 1000, 1000), user_grid);
     *e = out.e;
     read_conf(out.c, x);
+  });
+}
+
+// this repo's C++ lock-step minimiser (include/gnina_b200_minimize.hpp) on n conformations of the model's ligand at once, with
+// gb::NonCacheCNNT around the same analytic stand-in as the energy of every pose (its CNN box centred on the pose's start conformation, as
+// adjust_center does); the kinematics use this host's sinf / cosf / acosf like the reference build.  confs [n][7+T] in/out
+int gref_lockstep_minimize(void* mp, const float* begin, const float* end, const int* nbox, float slope, float dim, float res, float k,
+                           const float* target, float* confs, int n, int maxiters, int accurate, int early_term, float* e_out, int* evals_out,
+                           int* rounds_out, int* energy_calls_out) {
+  RefModel* R = (RefModel*)mp;
+  return guarded([&] {
+    b200::B200Ligand BL(R->m);
+    gb::LigandTree tree(BL.topo);
+    gb::Transcendentals saved = gb::transcendentals();
+    gb::transcendentals().sin = [](float x) { return sinf(x); };
+    gb::transcendentals().cos = [](float x) { return cosf(x); };
+    gb::transcendentals().acos = [](float x) { return acosf(x); };
+    const int na = tree.n_atoms, ns = tree.n_seg, nx = tree.conf_floats();
+    FakeScorer fs; fs.L.k = k; for (int j = 0; j < 3; j++) fs.L.target[j] = target[j];
+    fs.inf.dimension = dim; fs.inf.resolution = res;
+    gb::GridDims g3;
+    for (int i = 0; i < 3; i++) { g3[i].begin = begin[i]; g3[i].end = end[i]; g3[i].n = nbox[i]; }
+    // DLScorer::set_center_from_model (lib/dl_scorer.cpp:196-217) for every pose's start conformation
+    std::vector<float> centers(3 * (size_t)n), c(3 * (size_t)na), so(3 * (size_t)ns), sa(3 * (size_t)ns);
+    for (int i = 0; i < n; i++) {
+      tree.set_conf(confs + (size_t)i * nx, c.data(), so.data(), sa.data());
+      float cen[3] = {0, 0, 0}; unsigned cnt = 0;
+      for (int a = 0; a < na; a++) if (tree.heavy(a)) { for (int j = 0; j < 3; j++) cen[j] += c[3 * a + j]; cnt++; }
+      for (int j = 0; j < 3; j++) centers[3 * i + j] = cen[j] / (float)cnt;
+    }
+    int calls = 0;
+    auto energy = [&](const float* coords, const int* pose, int kk, float* e, float* forces) {
+      calls++;
+      for (int j = 0; j < kk; j++) {
+        gb::NonCacheCNNT<FakeScorer, RefEmp> nc(fs, g3, &centers[3 * pose[j]], slope);
+        std::vector<float> f;
+        e[j] = nc.eval(coords + (size_t)j * na * 3, tree.type.data(), na, &f);
+        std::copy(f.begin(), f.end(), forces + (size_t)j * na * 3);
+      }
+    };
+    gb::MinimizeParams mpar; mpar.maxiters = maxiters; mpar.accurate_line_search = accurate != 0; mpar.early_term = early_term != 0;
+    std::vector<int> ev; int rounds = 0;
+    std::vector<float> e = gb::minimize_poses(tree, energy, confs, n, mpar, &ev, &rounds);
+    gb::transcendentals() = saved;
+    std::copy(e.begin(), e.end(), e_out);
+    std::copy(ev.begin(), ev.end(), evals_out);
+    *rounds_out = rounds; *energy_calls_out = calls;
   });
 }
 

@@ -41,6 +41,8 @@ def lib():
                                         C.c_int, C.c_int, _fp]
         L.gref_refine_cnn.argtypes = [_vp, _vp, C.c_int, _fp, _fp, _ip, C.c_float, C.c_float, C.c_float, _fp, _fp, C.c_int, C.c_int, C.c_int,
                                       _fp, _ip]
+        L.gref_lockstep_minimize.argtypes = [_vp, _fp, _fp, _ip, C.c_float, C.c_float, C.c_float, C.c_float, _fp, _fp, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, _fp, _ip, _ip, _ip]
         L.gref_sf_create.argtypes = [C.c_float, C.c_float]; L.gref_sf_create.restype = _vp
         L.gref_sf_destroy.argtypes = [_vp]
         L.gref_cutoff_sqr.argtypes = [_vp]; L.gref_cutoff_sqr.restype = C.c_float
@@ -273,6 +275,18 @@ def refine_cnn(model, sf, kind, begin, end, n, conf, maxiters, dim=23.5, res=0.5
     _ok(lib().gref_refine_cnn(model.p, sf.p, kind, _f(b), _f(e_), _i(nn), dim, res, k, _f(tg), _f(x), maxiters, int(accurate), int(early_term),
                               _f(e), _i(ins)))
     return float(e[0]), x, bool(ins[0])
+
+
+def lockstep_minimize_cpp(model, begin, end, n, confs, maxiters, slope=10.0, dim=23.5, res=0.5, k=0.01, target=(0, 0, 0), accurate=True,
+                          early_term=False):
+    """this repo's C++ lock-step minimiser (include/gnina_b200_minimize.hpp: gb::minimize_poses over gb::LigandTree, energy =
+    gb::NonCacheCNNT around the analytic stand-in) on all conformations at once -> (e [n], confs [n, 7+T], evals [n], rounds, energy calls)"""
+    b, e_, nn = (np.ascontiguousarray(a, dt) for a, dt in ((begin, np.float32), (end, np.float32), (n, np.int32)))
+    x = np.array(confs, np.float32); tg = np.ascontiguousarray(target, np.float32)
+    e = np.empty(len(x), np.float32); ev = np.zeros(len(x), np.int32); rr = np.zeros(2, np.int32)
+    _ok(lib().gref_lockstep_minimize(model.p, _f(b), _f(e_), _i(nn), slope, dim, res, k, _f(tg), _f(x), len(x), maxiters, int(accurate),
+                                     int(early_term), _f(e), _i(ev), _i(rr[:1]), _i(rr[1:])))
+    return e, x, ev, int(rr[0]), int(rr[1])
 
 
 def model_eval_deriv(model, sf, kind, grid, conf, v=(1000, 1000, 1000)):

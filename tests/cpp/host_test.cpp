@@ -1,6 +1,9 @@
 // C++ host-side check: builds against include/gnina_b200.hpp + libgnina_b200.so.
 //   host_test --names                      : model-name expansion only (no device needed)
 //   host_test --host <tmp.gninatypes>      : PoseBatcher with a stub runner + gninatypes round trip (no device needed)
+//   host_test --minimize-host              : gb::minimize_poses (lock-step quasi-Newton, include/gnina_b200_minimize.hpp) on a small built-in
+//                                            ligand with an analytic energy (no device needed)
+//   host_test --minimize <weights_dir>     : the same driver over gb::CnnBatchEnergy = gb_cnn_score_grad (device; not part of the suite yet)
 //   host_test <weights_dir> <case.bin>     : score the poses in case.bin through gb::CNNScorer / gb::NonCacheCNN and
 //                                            print the results as text (compared with the oracle by the pytest)
 // case.bin (little endian): int32 n_rec, n_lig_atoms, n_poses; float rec_xyz[3 n_rec]; int32 rec_type[n_rec];
@@ -11,6 +14,31 @@
 #include <cstring>
 #include <fstream>
 #include "gnina_b200.hpp"
+#include "gnina_b200_minimize.hpp"
+
+// a 9-atom ligand with two torsions: root (atoms 0-3), a segment hanging off atom 3 (atoms 4-6) and one off atom 6 (atoms 7-8)
+struct TinyLigand {
+  std::vector<float> local{0, 0, 0, 1.5f, 0, 0, 2.2f, 1.3f, 0, 3.7f, 1.4f, 0.2f, 0, 0, 0, 0.8f, 1.2f, 0.4f, 2.2f, 1.0f, 0.9f, 0, 0, 0, 1.1f, -0.9f, 0.5f};
+  std::vector<int32_t> type{2, 2, 6, 2, 2, 10, 2, 2, 1}, parent{-1, 0, 1}, begin{0, 4, 7}, end{4, 7, 9};
+  std::vector<float> rel_origin{0, 0, 0, 4.6f, 2.4f, 0.5f, 3.0f, 1.9f, 1.4f}, rel_axis{0, 0, 0, 0.6f, 0.8f, 0, 0, 0.6f, 0.8f};
+  gb_ligand_topology topo{};
+  TinyLigand() {
+    topo.n_atoms = 9; topo.n_segments = 3; topo.n_pairs = 0;
+    topo.local_xyz = local.data(); topo.smina_type = type.data(); topo.seg_parent = parent.data(); topo.seg_atom_begin = begin.data();
+    topo.seg_atom_end = end.data(); topo.seg_rel_origin = rel_origin.data(); topo.seg_rel_axis = rel_axis.data();
+    topo.pair_a = nullptr; topo.pair_b = nullptr; topo.gyration_radius = 2.f;
+  }
+};
+static std::vector<float> tiny_starts(const gb::LigandTree& tree, int n) {
+  std::vector<float> x((size_t)n * tree.conf_floats(), 0.f);
+  for (int i = 0; i < n; i++) {
+    float* c = &x[(size_t)i * tree.conf_floats()];
+    c[0] = 3.f * std::sin(1.3f * i); c[1] = 2.f * std::cos(0.7f * i); c[2] = 0.5f * i - 2.f;
+    const float a = 0.4f * i; c[3] = std::cos(a / 2); c[4] = std::sin(a / 2) * 0.6f; c[5] = std::sin(a / 2) * 0.8f; c[6] = 0;
+    c[7] = 0.3f * i - 1.f; c[8] = 1.f - 0.25f * i;
+  }
+  return x;
+}
 
 template <typename T>
 static std::vector<T> rd(std::ifstream& f, size_t n) {
@@ -20,6 +48,63 @@ static std::vector<T> rd(std::ifstream& f, size_t n) {
 }
 
 int main(int argc, char** argv) {
+  if (argc >= 2 && !strcmp(argv[1], "--minimize-host")) {
+    TinyLigand L;
+    gb::LigandTree tree(L.topo);
+    const int n = 8, na = tree.n_atoms;
+    std::vector<float> x = tiny_starts(tree, n), x1 = x;
+    int calls = 0;
+    auto energy = [&](const float* coords, const int*, int k, float* e, float* f) {      // springs to the origin on the heavy atoms
+      calls++;
+      for (int j = 0; j < k; j++) {
+        float en = 0;
+        for (int a = 0; a < na; a++)
+          for (int q = 0; q < 3; q++) {
+            const float d = coords[((size_t)j * na + a) * 3 + q];
+            const bool heavy = tree.heavy(a);
+            if (heavy) en += 0.05f * d * d;
+            f[((size_t)j * na + a) * 3 + q] = heavy ? 0.1f * d : 0.f;
+          }
+        e[j] = en;
+      }
+    };
+    std::vector<float> c0((size_t)3 * na), so(9), sa(9), e0(n), f0((size_t)3 * na);
+    for (int i = 0; i < n; i++) { tree.set_conf(&x[(size_t)i * tree.conf_floats()], c0.data(), so.data(), sa.data()); int z = i; energy(c0.data(), &z, 1, &e0[i], f0.data()); }
+    calls = 0;
+    gb::MinimizeParams mp;
+    std::vector<int> ev; int rounds = 0;
+    std::vector<float> e = gb::minimize_poses(tree, energy, x.data(), n, mp, &ev, &rounds);
+    int total = 0; bool down = true, alone = true;
+    float sum0 = 0, sum1 = 0;
+    for (int i = 0; i < n; i++) { total += ev[i]; down = down && e[i] <= e0[i]; sum0 += e0[i]; sum1 += e[i]; }
+    down = down && sum1 < 0.6f * sum0;                                                      // the rigid shape keeps a floor
+    for (int i : {0, 5}) {                                                                  // a pose minimised alone ends at the same point
+      std::vector<float> xi(x1.begin() + (size_t)i * tree.conf_floats(), x1.begin() + (size_t)(i + 1) * tree.conf_floats());
+      std::vector<float> ei = gb::minimize_poses(tree, energy, xi.data(), 1, mp);
+      alone = alone && ei[0] == e[i] && !memcmp(xi.data(), &x[(size_t)i * tree.conf_floats()], 4 * (size_t)tree.conf_floats());
+    }
+    printf("minimize poses %d rounds %d evaluations %d descended %d same_alone %d batched %d\n", n, rounds, total, (int)down, (int)alone,
+           (int)(rounds + 1 < total));
+    return 0;
+  }
+  if (argc >= 3 && !strcmp(argv[1], "--minimize")) {                                       // device: CNN minimisation of 64 poses in lock step
+    gb::CNNScorer s(argv[2], {"crossdock_default2018"});
+    TinyLigand L;
+    gb::LigandTree tree(L.topo);
+    const float rec[6] = {8, 0, 0, -8, 0, 0}; const int32_t rt[2] = {2, 10};
+    s.set_receptor(rec, rt, 2);
+    const int n = 64;
+    std::vector<float> x = tiny_starts(tree, n);
+    const float b[3] = {-12, -12, -12}, en[3] = {12, 12, 12};
+    gb::CnnBatchEnergy energy(s.handle(), tree, b, en, 10.f, s.info(0).dimension);
+    energy.set_centers(x.data(), n);
+    gb::MinimizeParams mp; mp.maxiters = 50;
+    std::vector<int> ev; int rounds = 0;
+    std::vector<float> e = gb::minimize_poses(tree, energy, x.data(), n, mp, &ev, &rounds);
+    int total = 0; for (int v : ev) total += v;
+    printf("cnn_minimize poses %d rounds %d evaluations %d loss0 %g\n", n, rounds, total, e[0]);
+    return 0;
+  }
   if (argc >= 2 && !strcmp(argv[1], "--names")) {
     auto d = gb::expand_model_names({});
     auto f = gb::expand_model_names({"fast"});

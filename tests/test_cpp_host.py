@@ -17,7 +17,8 @@ def build_exe():
         __graft_entry__.build()
     src = os.path.join(ROOT, "tests", "cpp", "host_test.cpp")
     if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(src),
-                                                              os.path.getmtime(os.path.join(ROOT, "include", "gnina_b200.hpp"))):
+                                                              os.path.getmtime(os.path.join(ROOT, "include", "gnina_b200.hpp")),
+                                                              os.path.getmtime(os.path.join(ROOT, "include", "gnina_b200_minimize.hpp"))):
         libdir = os.path.join(ROOT, "gnina_b200")
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), src, "-o", EXE,
                                "-L" + libdir, "-lgnina_b200", "-Wl,-rpath," + libdir])
@@ -27,6 +28,15 @@ def build_exe():
 def test_cpp_host_builds_and_expands_names():
     out = subprocess.check_output([build_exe(), "--names"], text=True)
     assert out.strip() == "dense_1_3 dense_1_3_PT_KD_3 crossdock_default2018_KD_4 | all_default_to_default_1_3_1 | 2"
+
+
+def test_cpp_lock_step_minimiser_on_the_host():
+    """gb::minimize_poses (include/gnina_b200_minimize.hpp) with an analytic energy: every pose descends, a pose minimised alone ends at
+    the same point as inside the batch, and the energy functor is called once per round, not once per evaluation (the bit-for-bit
+    comparison with the reference's quasi_newton is tests/test_oracle_vs_reference_build.py)"""
+    out = subprocess.check_output([build_exe(), "--minimize-host"], text=True).split()
+    kv = dict(zip(out[1::2], out[2::2]))
+    assert kv["descended"] == "1" and kv["same_alone"] == "1" and kv["batched"] == "1" and int(kv["evaluations"]) > 8 * 5
 
 
 @pytest.mark.gpu

@@ -252,6 +252,26 @@ def test_lock_step_minimiser_reproduces_the_reference_pose_by_pose():
         minimize.set_transcendentals()
 
 
+def test_cpp_lock_step_minimiser_reproduces_the_reference_pose_by_pose():
+    """the C++ host side of the same driver (include/gnina_b200_minimize.hpp: gb::minimize_poses over gb::LigandTree, energy =
+    gb::NonCacheCNNT around the analytic stand-in, topology from the integration adapter b200::B200Ligand) on 48 poses at once: every
+    pose ends bit for bit where the reference's quasi_newton + non_cache_cnn takes it alone, in all four line-search / termination modes"""
+    lig = dict(synth.make_flexible_ligand())
+    ty = np.array(lig["types"]).copy(); ty[5] = 1; lig["types"] = ty
+    rx, rt = synth.make_receptor(300, box=30)
+    sf = R.RefScoring(); rm = R.RefModel(lig, rx, rt)
+    begin, end, nn, slope, dim, k, target = [-8.0] * 3, [8.0] * 3, [43, 43, 43], 10.0, 20.0, 0.02, np.float32([0.5, -0.3, 0.2])
+    X = _confs(np.random.RandomState(3), lig, rm.T, 48, spread=6.0)
+    for acc, et, iters in ((True, False, 10000), (True, True, 10000), (False, False, 40), (False, True, 200)):
+        e, x, ev, rounds, calls = R.lockstep_minimize_cpp(rm, begin, end, nn, X, iters, slope=slope, dim=dim, res=0.5, k=k, target=target,
+                                                          accurate=acc, early_term=et)
+        for i in range(len(X)):
+            er, xr = R.minimize_cnn(rm, sf, R.LINEAR, begin, end, nn, X[i], iters, slope=slope, dim=dim, res=0.5, k=k, target=target,
+                                    accurate=acc, early_term=et)
+            assert er == e[i] and np.array_equal(xr, x[i]), (acc, et, i)
+        assert calls == rounds + 1 and calls < 0.2 * ev.sum()
+
+
 def test_lock_step_cnn_refinement_reproduces_refine_structure():
     """--cnn_scoring refinement: refine_structure (main/main.cpp:131-171) on ig = non_cache_cnn for many poses at once
     (minimize.refine_structure_poses) vs the reference's parts replayed pose by pose: the slope escalates 10, 100, ... while a spring
