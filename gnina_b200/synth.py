@@ -162,6 +162,72 @@ def make_flexible_ligand(n_heavy=24, n_tors=5, n_branch=3, seed=11):
                 gyration_radius=gr, axis_root=np.array([0] + axis_root[1:], np.int32))
 
 
+def make_tree_ligand(seed, max_children=3, n_seg_target=7):
+    """A synthetic ligand with a RANDOM torsion tree (nodes with several children, nested branches) in the same representation as
+    make_flexible_ligand: segments in DFS pre-order, every segment a short chain of 2-5 heavy atoms, children attached to a random atom
+    of their parent (that atom is the begin point of the child's rotation axis).  Exercises the child-ordering rules of
+    heterotree::set_conf / derivative (lib/tree.h:300-310,361-382) beyond a chain."""
+    rs = np.random.RandomState(seed)
+    pos, seg_of, bonds = [], [], []
+    seg_parent, seg_begin, seg_end, axis_root = [], [], [], []
+    budget = [n_seg_target - 1]
+
+    def place(near):
+        for _ in range(200):
+            d = rs.randn(3); d /= np.linalg.norm(d)
+            cand = near + 1.5 * d
+            if all(np.linalg.norm(cand - q) > 1.25 for q in pos):
+                return cand
+        raise RuntimeError("could not place an atom")
+
+    def build(parent, attach_atom):
+        s = len(seg_parent)
+        seg_parent.append(parent); seg_begin.append(len(pos)); axis_root.append(attach_atom if attach_atom is not None else 0)
+        first = np.zeros(3) if attach_atom is None else place(pos[attach_atom])
+        pos.append(first); seg_of.append(s)
+        if attach_atom is not None:
+            bonds.append((attach_atom, len(pos) - 1))
+        for _ in range(rs.randint(1, 5)):
+            pos.append(place(pos[-1])); seg_of.append(s); bonds.append((len(pos) - 2, len(pos) - 1))
+        seg_end.append(len(pos))
+        own = list(range(seg_begin[s], seg_end[s]))
+        kids = min(budget[0], rs.randint(0, max_children + 1) if parent >= 0 else rs.randint(1, max_children + 1))
+        budget[0] -= kids
+        for _ in range(kids):
+            build(s, int(rs.choice(own)))
+    build(-1, None)
+    pos = np.array(pos, np.float64)
+    n, ns = len(pos), len(seg_parent)
+    types = rs.choice(LIG_HEAVY_TYPES, size=n).astype(np.int32)
+    origin = np.array([pos[seg_begin[s]] for s in range(ns)])
+    rel_origin, rel_axis = np.zeros((ns, 3)), np.zeros((ns, 3))
+    for s in range(1, ns):
+        rel_origin[s] = origin[s] - origin[seg_parent[s]]
+        a = origin[s] - pos[axis_root[s]]
+        rel_axis[s] = a / np.linalg.norm(a)
+    seg_of = np.array(seg_of)
+    nbr = {i: set() for i in range(n)}
+    for a, b in bonds:
+        nbr[a].add(b); nbr[b].add(a)
+    pa, pb = [], []
+    for i in range(n):
+        seen, front = {i}, {i}
+        for _ in range(3):
+            front = set(q for f in front for q in nbr[f]) - seen
+            seen |= front
+        for j in range(i + 1, n):
+            if seg_of[i] != seg_of[j] and j not in seen:
+                pa.append(i); pb.append(j)
+    conf0 = np.zeros(7 + ns - 1, np.float32)
+    conf0[:3] = origin[0]; conf0[3] = 1.0
+    return dict(local_xyz=(pos - origin[seg_of]).astype(np.float32), types=types, seg_parent=np.array(seg_parent, np.int32),
+                seg_begin=np.array(seg_begin, np.int32), seg_end=np.array(seg_end, np.int32),
+                seg_rel_origin=rel_origin.astype(np.float32), seg_rel_axis=rel_axis.astype(np.float32),
+                pair_a=np.array(pa, np.int32), pair_b=np.array(pb, np.int32), conf0=conf0, xyz0=pos.astype(np.float32),
+                gyration_radius=gyration_radius(pos.astype(np.float32), types, origin[0].astype(np.float32)),
+                axis_root=np.array(axis_root, np.int32))
+
+
 def gyration_radius(xyz, types, origin):
     """model::gyration_radius (lib/model.cpp:1002-1014): root-mean-square distance of the HEAVY atoms (smina type >= 2) from the
     root origin, accumulated in float32 in atom order.  gb_ligand_topology.gyration_radius wants this number for the pose the

@@ -74,6 +74,44 @@ def test_evaluation_minimisation_and_chains_are_bit_identical(lig_kw, libm):
         assert len(e) == len(er) and np.array_equal(e, er) and np.array_equal(x, xr)
 
 
+@pytest.mark.parametrize("seed", [0, 2, 4, 5])
+def test_random_torsion_trees(seed, libm):
+    """nodes with several children and nested branches (synth.make_tree_ligand): kinematics, energy + change, quasi_newton and one whole
+    Monte-Carlo chain of the restatement against the reference; the model -> topology adapter and both host-side minimisers' kinematics
+    on the same trees"""
+    from gnina_b200 import minimize
+    lig = synth.make_tree_ligand(seed)
+    sf, vo, rm, cg, d, lig2, rx, rt = _setup(lig, seed=seed + 50)
+    t = rm.adapter_topology()
+    for k in ("seg_parent", "seg_begin", "seg_end", "pair_a", "pair_b"):
+        assert np.array_equal(t[k], np.asarray(lig[k], np.int32)), k
+    rs = np.random.RandomState(seed)
+    X = _confs(rs, lig, d.T, 12)
+    minimize.set_transcendentals(*_host_libm())
+    try:
+        tree = minimize.TorsionTree(lig2)
+        coords, so, sa = tree.set_conf(X)
+        forces = rs.uniform(-10, 10, coords.shape).astype(np.float32)
+        change = tree.derivative(coords, forces, so, sa)
+        for i, x in enumerate(X):
+            c = rm.set(x)
+            assert np.array_equal(d.coords(x), c) and np.array_equal(coords[i], c)
+            assert np.array_equal(change[i], rm.tree_derivative(forces[i]))
+            e, g = d.eval_deriv(x, (10, 1.5, 10)); er, gr = R.model_eval_deriv(rm, sf, R.LINEAR, cg, x, (10, 1.5, 10))
+            assert e == er and np.array_equal(g, gr)
+    finally:
+        minimize.set_transcendentals()
+    for x in X[:6]:
+        for acc in (False, True):
+            e, xo, g, _ = d.bfgs(x, 20, accurate=acc); er, xr, gr = R.bfgs(rm, sf, R.LINEAR, cg, x, 20, accurate=acc)
+            assert e == er and np.array_equal(xo, xr) and np.array_equal(g, gr)
+    maxit = (25 + len(lig["types"])) // 3
+    x0, st = R.random_conf(rm, 31337, [-4] * 3, [4] * 3)
+    er, xr = R.mc(rm, sf, R.LINEAR, cg, 31337, [-4] * 3, [4] * 3, 40, maxit, lig["conf0"])
+    e, x = d.mc_ex(st, [-4] * 3, [4] * 3, 40, maxit, init_conf=x0, state_conf=lig["conf0"])
+    assert len(e) == len(er) and np.array_equal(e, er) and np.array_equal(x, xr)
+
+
 def test_stateless_chain_variant_is_not_the_reference(libm):
     """what round 1's kernels did -- constant gyration radius, energies re-evaluated at the returned conformation -- leaves the
     reference's trajectory within a few steps: the model-state rules are part of the algorithm, not noise"""
