@@ -1,0 +1,9 @@
+# What the next GPU session should run first (written after round 2's GPU minutes were spent): the suite, then the measurements and
+# checks of the code that was validated on the CPU only -- lock-step minimiser (Python and C++), random torsion trees on the device
+T=${1:-r6a}
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q --tb=short 2>&1 | grep -v "^$" | cut -c1-400 | tail -40 > gpurun_out/${T}_pytest.log
+python tools/device_tree_check.py > gpurun_out/${T}_tree_check.json 2> gpurun_out/${T}_tree_check.err
+python tools/minimize_demo.py 1000 200 > gpurun_out/${T}_minimize.json 2> gpurun_out/${T}_minimize.err
+./tests/cpp/host_test --minimize gnina_b200/weights > gpurun_out/${T}_cpp_minimize.log 2>&1
+tail -3 gpurun_out/${T}_pytest.log; cat gpurun_out/${T}_tree_check.json gpurun_out/${T}_minimize.json gpurun_out/${T}_cpp_minimize.log
