@@ -160,7 +160,8 @@ def dock_ligand(vina, cnn, lig, corner1, corner2, exhaustiveness=8, seed=1, num_
         m["cnnscore"] = float(sc[i]); m["cnnaffinity"] = float(aff[i]); m["cnnvariance"] = float(var[i])
     key = {"cnnscore": lambda o: -o["cnnscore"], "cnnaffinity": lambda o: -o["cnnaffinity"], "energy": lambda o: o["e"]}[sort_order]
     merged.sort(key=key)
-    return remove_redundant(merged, out_min_rmsd)[:num_modes]
+    # main/main.cpp:371-378: poses that never entered the search box (e = max_fl) are skipped, not counted towards num_modes
+    return [o for o in remove_redundant(merged, out_min_rmsd) if o["e"] < 0.1 * MAX_FL][:num_modes]
 
 
 class DockingPool:
