@@ -4,6 +4,8 @@
 //   host_test --minimize-host              : gb::minimize_poses (lock-step quasi-Newton, include/gnina_b200_minimize.hpp) on a small built-in
 //                                            ligand with an analytic energy (no device needed)
 //   host_test --minimize <weights_dir>     : the same driver over gb::CnnBatchEnergy = gb_cnn_score_grad (device; not part of the suite yet)
+//   host_test --dock <weights_dir>         : gb::DockingPool / gb::dock_ligand (include/gnina_b200_dock.hpp) on the built-in ligand (device;
+//                                            not part of the suite yet)
 //   host_test <weights_dir> <case.bin>     : score the poses in case.bin through gb::CNNScorer / gb::NonCacheCNN and
 //                                            print the results as text (compared with the oracle by the pytest)
 // case.bin (little endian): int32 n_rec, n_lig_atoms, n_poses; float rec_xyz[3 n_rec]; int32 rec_type[n_rec];
@@ -15,6 +17,7 @@
 #include <fstream>
 #include "gnina_b200.hpp"
 #include "gnina_b200_minimize.hpp"
+#include "gnina_b200_dock.hpp"
 
 // a 9-atom ligand with two torsions: root (atoms 0-3), a segment hanging off atom 3 (atoms 4-6) and one off atom 6 (atoms 7-8)
 struct TinyLigand {
@@ -85,6 +88,26 @@ int main(int argc, char** argv) {
     }
     printf("minimize poses %d rounds %d evaluations %d descended %d same_alone %d batched %d\n", n, rounds, total, (int)down, (int)alone,
            (int)(rounds + 1 < total));
+    return 0;
+  }
+  if (argc >= 3 && !strcmp(argv[1], "--dock")) {                                           // device: config 3 glue from C++ host threads
+    gb::CNNScorer s(argv[2], {"crossdock_default2018"});
+    std::vector<float> rec; std::vector<int32_t> rt;
+    for (int i = 0; i < 200; i++) {                                                         // a shell of receptor atoms around the box
+      const float a = 0.7f * i, b = 0.37f * i;
+      rec.push_back(11.f * std::cos(a) * std::sin(b)); rec.push_back(11.f * std::sin(a) * std::sin(b)); rec.push_back(11.f * std::cos(b));
+      rt.push_back(i % 3 == 0 ? 10 : 2);
+    }
+    s.set_receptor(rec.data(), rt.data(), (int)rt.size());
+    TinyLigand L;
+    gb::DockingPool pool(s, rec.data(), rt.data(), (int)rt.size(), 4);
+    std::vector<const gb_ligand_topology*> ligs(8, &L.topo);
+    const float c1[3] = {-6, -6, -6}, c2[3] = {6, 6, 6};
+    gb::DockParams dp; dp.exhaustiveness = 8; dp.num_steps = 40; dp.num_saved_mins = 10;
+    auto res = pool.dock(ligs, c1, c2, dp);
+    for (size_t i = 0; i < res.size(); i++)
+      printf("dock ligand %zu modes %zu best_cnnscore %g affinity %g\n", i, res[i].size(), res[i].empty() ? -1.f : res[i][0].cnnscore,
+             res[i].empty() ? 0.f : res[i][0].e);
     return 0;
   }
   if (argc >= 3 && !strcmp(argv[1], "--minimize")) {                                       // device: CNN minimisation of 64 poses in lock step

@@ -18,7 +18,8 @@ def build_exe():
     src = os.path.join(ROOT, "tests", "cpp", "host_test.cpp")
     if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(src),
                                                               os.path.getmtime(os.path.join(ROOT, "include", "gnina_b200.hpp")),
-                                                              os.path.getmtime(os.path.join(ROOT, "include", "gnina_b200_minimize.hpp"))):
+                                                              os.path.getmtime(os.path.join(ROOT, "include", "gnina_b200_minimize.hpp")),
+                                                              os.path.getmtime(os.path.join(ROOT, "include", "gnina_b200_dock.hpp"))):
         libdir = os.path.join(ROOT, "gnina_b200")
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), src, "-o", EXE,
                                "-L" + libdir, "-lgnina_b200", "-Wl,-rpath," + libdir])
