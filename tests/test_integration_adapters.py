@@ -21,6 +21,22 @@ def test_adapters_compile_against_the_reference_headers():
     assert r.returncode == 0, r.stderr[-4000:]
 
 
+@pytest.mark.skipif(not os.path.isdir(REF), reason="/root/reference is absent")
+def test_end_to_end_program_links_and_runs_the_reference_side():
+    """integration/e2e_docking.cpp: gnina's own classes (linked from oracle/_ref), the adapters and libgnina_b200.so in ONE executable --
+    every symbol the adapters need exists on both sides; its `cpu` mode (reference parallel_mc on the host + the topology adapter) runs"""
+    from oracle import vina_refbuild as R
+    assert R.build()
+    import __graft_entry__  # noqa: F401  (libgnina_b200.so must exist for the link)
+    from gnina_b200 import build as b
+    b.build()
+    subprocess.check_call(["make", "-s", "-f", "Makefile.ref", "_ref/e2e_docking"], cwd=os.path.join(ROOT, "oracle"))
+    out = subprocess.check_output([os.path.join(ROOT, "oracle", "_ref", "e2e_docking"), "cpu"], text=True).splitlines()
+    assert out[0].startswith("topology atoms 9 segments 3 pairs 8 heavy 9") and out[-1] == "cpu ok"
+    e = [float(l.split()[-1]) for l in out if l.startswith("reference pose")]
+    assert len(e) >= 3 and e == sorted(e) and e[0] < -3.0
+
+
 def test_model_to_topology_adapter_on_reference_models():
     """B200Ligand(const model&) walks the reference's heterotree: atoms, segments (DFS pre-order), parents, relative origins / axes,
     interacting pairs and gyration radius come out exactly as the reference's constructors stored them"""

@@ -7,4 +7,5 @@ python tools/device_tree_check.py > gpurun_out/${T}_tree_check.json 2> gpurun_ou
 python tools/minimize_demo.py 1000 200 > gpurun_out/${T}_minimize.json 2> gpurun_out/${T}_minimize.err
 ./tests/cpp/host_test --minimize gnina_b200/weights > gpurun_out/${T}_cpp_minimize.log 2>&1
 ./tests/cpp/host_test --dock gnina_b200/weights > gpurun_out/${T}_cpp_dock.log 2>&1
-tail -3 gpurun_out/${T}_pytest.log; cat gpurun_out/${T}_tree_check.json gpurun_out/${T}_minimize.json gpurun_out/${T}_cpp_minimize.log gpurun_out/${T}_cpp_dock.log
+./oracle/_ref/e2e_docking gpu > gpurun_out/${T}_e2e_docking.log 2>&1   # the reference's classes + the adapters + the device in one program
+tail -3 gpurun_out/${T}_pytest.log; cat gpurun_out/${T}_tree_check.json gpurun_out/${T}_minimize.json gpurun_out/${T}_cpp_minimize.log gpurun_out/${T}_cpp_dock.log gpurun_out/${T}_e2e_docking.log
