@@ -394,15 +394,18 @@ int gref_type_info(int t, char* name64, float* xs_radius_out, float* covalent_ra
 }
 
 // ---- scoring function: the default Vina terms and weights of main/main.cpp:1324-1329 (= test_cache.cu:30-36) ----------------
-void* gref_sf_create(float factor_linear, float factor_splines) {
+void* gref_sf_create_weights(float factor_linear, float factor_splines, const float* w6);
+void* gref_sf_create(float factor_linear, float factor_splines) { return gref_sf_create_weights(factor_linear, factor_splines, nullptr); }
+// w6 (nullable): the five term weights and the num_tors_div weight of a custom scoring function (--custom_scoring style), same term set
+void* gref_sf_create_weights(float factor_linear, float factor_splines, const float* w6) {
   RefSF* s = new RefSF;
   int rc = guarded([&] {
-    s->t.add("gauss(o=0,_w=0.5,_c=8)", -0.035579);
-    s->t.add("gauss(o=3,_w=2,_c=8)", -0.005156);
-    s->t.add("repulsion(o=0,_c=8)", 0.840245);
-    s->t.add("hydrophobic(g=0.5,_b=1.5,_c=8)", -0.035069);
-    s->t.add("non_dir_h_bond(g=-0.7,_b=0,_c=8)", -0.587439);
-    s->t.add("num_tors_div", 5 * 0.05846 / 0.1 - 1);
+    s->t.add("gauss(o=0,_w=0.5,_c=8)", w6 ? (fl)w6[0] : (fl)-0.035579);
+    s->t.add("gauss(o=3,_w=2,_c=8)", w6 ? (fl)w6[1] : (fl)-0.005156);
+    s->t.add("repulsion(o=0,_c=8)", w6 ? (fl)w6[2] : (fl)0.840245);
+    s->t.add("hydrophobic(g=0.5,_b=1.5,_c=8)", w6 ? (fl)w6[3] : (fl)-0.035069);
+    s->t.add("non_dir_h_bond(g=-0.7,_b=0,_c=8)", w6 ? (fl)w6[4] : (fl)-0.587439);
+    s->t.add("num_tors_div", w6 ? (fl)w6[5] : (fl)(5 * 0.05846 / 0.1 - 1));
     s->wt.reset(new weighted_terms(&s->t, s->t.weights()));
     s->prec[0].reset(new precalculate_linear(*s->wt, factor_linear));
     s->prec[1].reset(new precalculate_splines(*s->wt, factor_splines));

@@ -199,7 +199,8 @@ float gvo_noncache_atom(const gvo_field *F, int t1, const float *a, float v, flo
     const float r2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
     if (r2 < 64.f) {
       float pe, dor;
-      gvo_prec_eval_deriv(F->prec, t1, t2, r2, &pe, &dor);
+      if (F->splines) gvo_splines_eval_deriv(F->splines, t1, t2, r2, &pe, &dor); /* non_cache holds the run's precalculate: --minimize's splines */
+      else gvo_prec_eval_deriv(F->prec, t1, t2, r2, &pe, &dor);
       e += pe;
       for (int q = 0; q < 3; q++) d[q] += dor * r[q];
     }

@@ -44,6 +44,7 @@ def lib():
         L.gref_lockstep_minimize.argtypes = [_vp, _fp, _fp, _ip, C.c_float, C.c_float, C.c_float, C.c_float, _fp, _fp, C.c_int, C.c_int, C.c_int,
                                              C.c_int, _fp, _ip, _ip, _ip]
         L.gref_sf_create.argtypes = [C.c_float, C.c_float]; L.gref_sf_create.restype = _vp
+        L.gref_sf_create_weights.argtypes = [C.c_float, C.c_float, _fp]; L.gref_sf_create_weights.restype = _vp
         L.gref_sf_destroy.argtypes = [_vp]
         L.gref_cutoff_sqr.argtypes = [_vp]; L.gref_cutoff_sqr.restype = C.c_float
         L.gref_terms_eval.argtypes = [_vp, C.c_int, C.c_int, C.c_float]; L.gref_terms_eval.restype = C.c_float
@@ -100,8 +101,9 @@ class RefScoring:
     """custom_terms + weighted_terms with gnina's default Vina weights (main/main.cpp:1324-1329) and the three precalculate
     flavours: LINEAR (factor 32, docking), SPLINES (factor 10, --minimize), EXACT (final score)"""
 
-    def __init__(self, factor_linear=32.0, factor_splines=10.0):
-        self.p = lib().gref_sf_create(factor_linear, factor_splines)
+    def __init__(self, factor_linear=32.0, factor_splines=10.0, weights6=None):
+        w = None if weights6 is None else np.ascontiguousarray(weights6, np.float32)
+        self.p = lib().gref_sf_create_weights(factor_linear, factor_splines, None if w is None else _f(w))
         if not self.p:
             raise RuntimeError(lib().gref_last_error().decode())
 

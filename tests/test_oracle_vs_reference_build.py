@@ -149,6 +149,37 @@ def test_non_cache_and_exact_scoring(libm):
         assert sf.num_tors_div(e, nt) == vo.num_tors_div(e, nt)
 
 
+def test_custom_weights_table_factor_and_the_minimize_flavour(libm):
+    """other term weights (--custom_scoring style) and another table factor: grids and model::eval_deriv stay bit-identical.  The
+    --minimize flavour -- precalculate_splines (factor 10) for the receptor terms of non_cache AND the intramolecular pairs
+    (main/main.cpp:1162-1165,1387) -- agrees to the round-off of the spline coefficients (Thomas solve in double vs Eigen's float inverse)"""
+    lig = synth.make_flexible_ligand()
+    rx, rt = synth.make_receptor(500, box=30)
+    w6 = np.float32([-0.03, -0.006, 0.9, -0.04, -0.5, 1.5])
+    sf, vo = R.RefScoring(factor_linear=48.0, weights6=w6), VinaOracle(weights6=w6, factor=48.0)
+    rm = R.RefModel(lig, rx, rt)
+    lo, ro, ra = rm.export()
+    lig2 = dict(lig); lig2["local_xyz"], lig2["seg_rel_origin"], lig2["seg_rel_axis"] = lo, ro, ra
+    needed = sorted(set(int(t) for t in lig["types"] if t > 1))
+    cg = R.RefGrid.cache(sf, R.LINEAR, rm, BEGIN, END, N, 1e3)
+    grids = {t: vo.cache_populate(BEGIN, END, N, rx, rt, t) for t in needed}
+    assert all(np.array_equal(grids[t], cg.grid(t)) for t in needed)
+    d = DockOracle(vo, grids, BEGIN, END, N, lig2, slope=1e3)
+    rs = np.random.RandomState(5)
+    X = _confs(rs, lig, d.T, 16)
+    for x in X:
+        e, g = d.eval_deriv(x); er, gr = R.model_eval_deriv(rm, sf, R.LINEAR, cg, x)
+        assert e == er and np.array_equal(g, gr)
+    assert sf.num_tors_div(-7.5, 3.5) == vo.num_tors_div(-7.5, 3.5)
+    sf2, vo2 = R.RefScoring(), VinaOracle()
+    nc = R.RefGrid.non_cache(sf2, R.SPLINES, rm, BEGIN, END, N, 1e3)
+    d2 = DockOracle(vo2, {}, BEGIN, END, N, lig2, slope=1e3)
+    d2.use_noncache(rx, rt); d2.set_box(BEGIN, END, 1e3); d2.use_splines(True)
+    for x in X:
+        e, g = d2.eval_deriv(x); er, gr = R.model_eval_deriv(rm, sf2, R.SPLINES, nc, x)
+        assert abs(e - er) <= 1e-6 * max(1.0, abs(er)) and np.abs(g - gr).max() <= 2e-6 * max(1.0, np.abs(gr).max())
+
+
 def test_refine_structure_composed_from_reference_parts(libm):
     """refine_structure lives in main/main.cpp:131-171 (not a library source): its loop -- slope 10, 100, ...; quasi_newton on the
     non_cache field; m.set; stop when non_cache::within -- is replayed here with the REFERENCE's quasi_newton / non_cache / within and
