@@ -108,7 +108,8 @@ def search_box(corner1, corner2, granularity=0.375):
 
 
 def dock_ligand(vina, cnn, lig, corner1, corner2, exhaustiveness=8, seed=1, num_steps=None, maxiters=None,
-                num_saved_mins=50, num_modes=9, out_min_rmsd=1.0, sort_order="cnnscore", grid_spacing=0.375, refine=True):
+                num_saved_mins=50, num_modes=9, out_min_rmsd=1.0, sort_order="cnnscore", grid_spacing=0.375, refine=True,
+                skip_outside=True):
     """vina: VinaScorer with the receptor set; cnn: CNNScorer with the same receptor set; lig: ligand topology dict; corner1/2: the
     requested search box (what --center / --size or --autobox_ligand + autobox_add describe).
     -> list of dicts (conf, coords, e = final Vina affinity, search_e, cnnscore, cnnaffinity, cnnvariance), ranked."""
@@ -161,7 +162,11 @@ def dock_ligand(vina, cnn, lig, corner1, corner2, exhaustiveness=8, seed=1, num_
     key = {"cnnscore": lambda o: -o["cnnscore"], "cnnaffinity": lambda o: -o["cnnaffinity"], "energy": lambda o: o["e"]}[sort_order]
     merged.sort(key=key)
     # main/main.cpp:371-378: poses that never entered the search box (e = max_fl) are skipped, not counted towards num_modes
-    return [o for o in remove_redundant(merged, out_min_rmsd) if o["e"] < 0.1 * MAX_FL][:num_modes]
+    # (skip_outside=False keeps them, with e = max_fl and within = False, for inspection)
+    ranked = remove_redundant(merged, out_min_rmsd)
+    if skip_outside:
+        ranked = [o for o in ranked if o["e"] < 0.1 * MAX_FL]
+    return ranked[:num_modes]
 
 
 class DockingPool:

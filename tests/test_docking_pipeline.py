@@ -69,7 +69,10 @@ def test_dock_and_rescore_pipeline():
     lig = synth.make_flexible_ligand()
     v = VinaScorer(); v.set_receptor(rec_xyz, rec_t)
     c = CNNScorer(["crossdock_default2018"]); c.set_receptor(rec_xyz, rec_t)
-    poses = docking.dock_ligand(v, c, lig, [-6, -6, -6], [6, 6, 6], exhaustiveness=8, seed=3, num_steps=60, num_saved_mins=20)
+    # skip_outside=False: a 12 A box is tight for this ligand; poses that refine_structure could not pull inside stay in the list
+    # (e = max_fl, within = False) instead of being dropped as the reference's ranked output drops them
+    poses = docking.dock_ligand(v, c, lig, [-6, -6, -6], [6, 6, 6], exhaustiveness=8, seed=3, num_steps=60, num_saved_mins=20,
+                                skip_outside=False)
     assert 1 <= len(poses) <= 9
     sc = [p["cnnscore"] for p in poses]
     assert sc == sorted(sc, reverse=True) and all(0.0 <= s <= 1.0 for s in sc)       # ranked by CNNscore
@@ -92,7 +95,8 @@ def test_dock_and_rescore_pipeline():
             # refine_structure left every heavy atom inside the search box (non_cache::within)
             hv = p["coords"]
             assert (hv >= b - 1e-3).all() and (hv <= e_ + 1e-3).all()
-    again = docking.dock_ligand(v, c, lig, [-6, -6, -6], [6, 6, 6], exhaustiveness=8, seed=3, num_steps=60, num_saved_mins=20)
+    again = docking.dock_ligand(v, c, lig, [-6, -6, -6], [6, 6, 6], exhaustiveness=8, seed=3, num_steps=60, num_saved_mins=20,
+                                skip_outside=False)
     assert [p["cnnscore"] for p in again] == sc                                            # same seed, same result
 
 
@@ -104,7 +108,7 @@ def test_concurrent_ligands_equal_sequential_docking():
     from gnina_b200.vina import VinaScorer
     rec_xyz, rec_t = synth.make_receptor()
     ligs = [synth.make_flexible_ligand(n_heavy=18 + 2 * i, n_tors=3 + i % 3, seed=20 + i) for i in range(6)]
-    kw = dict(exhaustiveness=4, num_steps=30, num_saved_mins=10)
+    kw = dict(exhaustiveness=4, num_steps=30, num_saved_mins=10, skip_outside=False)
     many = docking.dock_many(ligs, rec_xyz, rec_t, ["crossdock_default2018"], [-6, -6, -6], [6, 6, 6], n_workers=3, **kw)
     v = VinaScorer(); v.set_receptor(rec_xyz, rec_t)
     c = CNNScorer(["crossdock_default2018"]); c.set_receptor(rec_xyz, rec_t)
