@@ -107,6 +107,19 @@ def search_box(corner1, corner2, granularity=0.375):
     return begin, (begin + real).astype(np.float32), n
 
 
+def autobox(xyz, add=4.0, granularity=0.375):
+    """model::movable_atoms_box (lib/model.cpp:751-776; --autobox_ligand with --autobox_add 4, and the per-ligand box of --minimize,
+    main/main.cpp:1464-1466): the bounding box of the atoms widened by `add` on every side, as grid_dims.  -> (begin[3], end[3], n[3])"""
+    xyz = np.asarray(xyz, np.float32).reshape(-1, 3)
+    c1 = (xyz.min(axis=0) - np.float32(add)).astype(np.float32)
+    c2 = (xyz.max(axis=0) + np.float32(add)).astype(np.float32)
+    center = (np.float32(0.5) * (c2 + c1)).astype(np.float32)
+    n = np.ceil((c2 - c1) / np.float32(granularity)).astype(np.int32)
+    real = (np.float32(granularity) * n.astype(np.float32)).astype(np.float32)
+    begin = (center - real / np.float32(2)).astype(np.float32)
+    return begin, (begin + real).astype(np.float32), n
+
+
 def dock_ligand(vina, cnn, lig, corner1, corner2, exhaustiveness=8, seed=1, num_steps=None, maxiters=None,
                 num_saved_mins=50, num_modes=9, out_min_rmsd=1.0, sort_order="cnnscore", grid_spacing=0.375, refine=True,
                 skip_outside=True):

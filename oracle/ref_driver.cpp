@@ -521,6 +521,11 @@ void gref_model_get_coords(void* p, float* xyz) {
   for (sz i = 0; i < R->m.coords.size(); i++) for (int k = 0; k < 3; k++) xyz[3 * i + k] = R->m.coords[i][k];
 }
 float gref_gyration_radius(void* p) { return ((RefModel*)p)->m.gyration_radius(0); }
+// model::movable_atoms_box (lib/model.cpp:751-776) of the coordinates the model holds -> begin, end, n
+void gref_movable_atoms_box(void* p, float add, float granularity, float* begin, float* end, int* n) {
+  const grid_dims gd = ((RefModel*)p)->m.movable_atoms_box(add, granularity);
+  for (int i = 0; i < 3; i++) { begin[i] = gd[i].begin; end[i] = gd[i].end; n[i] = (int)gd[i].n; }
+}
 // heterotree::derivative on given coordinates and forces (tree.h:374-382) -> change [6 + T]
 int gref_tree_derivative(void* p, const float* forces, float* out_change) {
   RefModel* R = (RefModel*)p;

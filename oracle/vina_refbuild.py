@@ -59,6 +59,7 @@ def lib():
         L.gref_model_get_coords.argtypes = [_vp, _fp]
         L.gref_gyration_radius.argtypes = [_vp]; L.gref_gyration_radius.restype = C.c_float
         L.gref_tree_derivative.argtypes = [_vp, _fp, _fp]
+        L.gref_movable_atoms_box.argtypes = [_vp, C.c_float, C.c_float, _fp, _fp, _ip]
         for nm in ("gref_cache_create", "gref_noncache_create"):
             getattr(L, nm).argtypes = [_vp, C.c_int, _vp, _fp, _fp, _ip, C.c_float]; getattr(L, nm).restype = _vp
         L.gref_cache_grid.argtypes = [_vp, C.c_int, _fp]
@@ -173,6 +174,11 @@ class RefModel:
         return o
 
     def gyration_radius(self): return lib().gref_gyration_radius(self.p)
+
+    def movable_atoms_box(self, add=4.0, granularity=0.375):
+        b, e, n = np.empty(3, np.float32), np.empty(3, np.float32), np.empty(3, np.int32)
+        lib().gref_movable_atoms_box(self.p, add, granularity, _f(b), _f(e), _i(n))
+        return b, e, n
 
     def adapter_topology(self):
         """integration/docking_b200.h::B200Ligand (the model -> gb_ligand_topology adapter) run on this reference model -> dict"""

@@ -180,6 +180,20 @@ def test_custom_weights_table_factor_and_the_minimize_flavour(libm):
         assert abs(e - er) <= 1e-6 * max(1.0, abs(er)) and np.abs(g - gr).max() <= 2e-6 * max(1.0, np.abs(gr).max())
 
 
+def test_autobox_is_movable_atoms_box():
+    """docking.autobox vs model::movable_atoms_box (lib/model.cpp:751-776): --autobox_ligand / the per-ligand box of --minimize"""
+    from gnina_b200 import docking
+    for seed in (0, 3, 5):
+        lig = synth.make_tree_ligand(seed)
+        rm = R.RefModel(lig)
+        x = _confs(np.random.RandomState(seed), lig, rm.T, 1, spread=20.0)[0]
+        c = rm.set(x)
+        for add in (4.0, 0.0, 7.3):
+            b, e, n = docking.autobox(c, add)
+            br, er, nr = rm.movable_atoms_box(add)
+            assert np.array_equal(n, nr) and np.array_equal(b, br) and np.array_equal(e, er)
+
+
 def test_refine_structure_composed_from_reference_parts(libm):
     """refine_structure lives in main/main.cpp:131-171 (not a library source): its loop -- slope 10, 100, ...; quasi_newton on the
     non_cache field; m.set; stop when non_cache::within -- is replayed here with the REFERENCE's quasi_newton / non_cache / within and
