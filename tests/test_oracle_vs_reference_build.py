@@ -112,6 +112,23 @@ def test_random_torsion_trees(seed, libm):
     assert len(e) == len(er) and np.array_equal(e, er) and np.array_equal(x, xr)
 
 
+def test_ligand_with_hydrogens(libm):
+    """polar and non-polar hydrogens among the movable atoms: skipped by the grid term, zero force, absent from the gyration radius and
+    from the containers' RMSD (lib/cache.cpp:65-83, lib/model.cpp:1002-1014, get_heavy_atom_movable_coords) -- evaluation and whole chains"""
+    lig = dict(synth.make_flexible_ligand())
+    ty = np.array(lig["types"]).copy(); ty[5] = 1; ty[17] = 1; ty[26] = 0; lig["types"] = ty
+    sf, vo, rm, cg, d, lig2, rx, rt = _setup(lig, seed=9)
+    for x in _confs(np.random.RandomState(9), lig, d.T, 16):
+        e, g = d.eval_deriv(x, (10, 1.5, 10)); er, gr = R.model_eval_deriv(rm, sf, R.LINEAR, cg, x, (10, 1.5, 10))
+        assert e == er and np.array_equal(g, gr)
+    maxit = (25 + len(lig["types"])) // 3
+    for seed in (5, 901):
+        x0, st = R.random_conf(rm, seed, [-4] * 3, [4] * 3)
+        er, xr = R.mc(rm, sf, R.LINEAR, cg, seed, [-4] * 3, [4] * 3, 50, maxit, lig["conf0"])
+        e, x = d.mc_ex(st, [-4] * 3, [4] * 3, 50, maxit, init_conf=x0, state_conf=lig["conf0"])
+        assert len(e) == len(er) and np.array_equal(e, er) and np.array_equal(x, xr)
+
+
 def test_stateless_chain_variant_is_not_the_reference(libm):
     """what round 1's kernels did -- constant gyration radius, energies re-evaluated at the returned conformation -- leaves the
     reference's trajectory within a few steps: the model-state rules are part of the algorithm, not noise"""
