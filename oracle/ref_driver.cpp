@@ -521,6 +521,15 @@ void gref_model_get_coords(void* p, float* xyz) {
   for (sz i = 0; i < R->m.coords.size(); i++) for (int k = 0; k < 3; k++) xyz[3 * i + k] = R->m.coords[i][k];
 }
 float gref_gyration_radius(void* p) { return ((RefModel*)p)->m.gyration_radius(0); }
+// model::clear_minus_forces + model::add_minus_forces (lib/model.cu:232-259) with a per-movable-atom force list -> what each atom received
+void gref_add_minus_forces(void* p, const float* forces, int n, float* out) {
+  model& m = ((RefModel*)p)->m;
+  std::vector<gfloat3> f;
+  for (int i = 0; i < n; i++) f.push_back(gfloat3(forces[3 * i], forces[3 * i + 1], forces[3 * i + 2]));
+  m.clear_minus_forces();
+  m.add_minus_forces(f);
+  for (sz i = 0; i < m.minus_forces.size(); i++) for (int k = 0; k < 3; k++) out[3 * i + k] = m.minus_forces[i][k];
+}
 // model::movable_atoms_box (lib/model.cpp:751-776) of the coordinates the model holds -> begin, end, n
 void gref_movable_atoms_box(void* p, float add, float granularity, float* begin, float* end, int* n) {
   const grid_dims gd = ((RefModel*)p)->m.movable_atoms_box(add, granularity);

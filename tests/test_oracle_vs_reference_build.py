@@ -129,6 +129,21 @@ def test_ligand_with_hydrogens(libm):
         assert len(e) == len(er) and np.array_equal(e, er) and np.array_equal(x, xr)
 
 
+def test_add_minus_forces_consumes_its_list_compactly():
+    """what the DLScorer adapter inherits (INTEGRATION.md): model::add_minus_forces (lib/model.cu:247-259) gives list entry j to the j-th
+    NON-hydrogen movable atom, although CNNTorchScorer::getGradient indexes the list by movable-atom index"""
+    import ctypes as C
+    lig = dict(synth.make_flexible_ligand())
+    ty = np.array(lig["types"]).copy(); ty[2] = 1; lig["types"] = ty
+    rm = R.RefModel(lig)
+    fp = C.POINTER(C.c_float)
+    R.lib().gref_add_minus_forces.argtypes = [C.c_void_p, fp, C.c_int, fp]
+    f = np.zeros((rm.na, 3), np.float32); f[:, 0] = np.arange(rm.na)
+    out = np.zeros((rm.na, 3), np.float32)
+    R.lib().gref_add_minus_forces(rm.p, f.ctypes.data_as(fp), rm.na, out.ctypes.data_as(fp))
+    assert out[:6, 0].tolist() == [0.0, 1.0, 0.0, 2.0, 3.0, 4.0]
+
+
 def test_stateless_chain_variant_is_not_the_reference(libm):
     """what round 1's kernels did -- constant gyration radius, energies re-evaluated at the returned conformation -- leaves the
     reference's trajectory within a few steps: the model-state rules are part of the algorithm, not noise"""
