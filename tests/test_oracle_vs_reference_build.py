@@ -428,6 +428,47 @@ def test_lock_step_cnn_refinement_reproduces_refine_structure():
         minimize.set_transcendentals()
 
 
+@pytest.mark.parametrize("seed", [3, 91])
+def test_gninacheck_random_molecules_against_the_compiled_reference(seed, libm):
+    """the reference's own `gninacheck` inputs (test/gnina/test_utils.cpp:13-44; synth.make_gninacheck_mol): atoms of EVERY smina type --
+    hydrogens, metals, the generic types -- at uniform random positions, overlaps allowed, as receptor and as a one-torsion ligand with
+    pairs across the torsion.  gninacheck itself compares the reference's CPU and GPU flavours to 0.01; here cache::populate for every
+    type the ligand needs, model::eval_deriv, non_cache::eval and the exact terms of the restatement are bit-identical to the CPU one."""
+    rs = np.random.RandomState(seed)
+    rx, rt = synth.make_gninacheck_mol(rs, 0, 200, 500, 14, 14, 14)
+    lx, lt = synth.make_gninacheck_mol(rs, 0, 20, 60, 5, 5, 5)
+    na, h = len(lt), len(lt) // 2
+    heavy = [i for i in range(na) if lt[i] > 1]
+    pa = [a for a in heavy if a < h for b in heavy if b >= h][:200]
+    pb = [b for a in heavy if a < h for b in heavy if b >= h][:200]
+    lig = dict(xyz0=lx, types=lt, seg_parent=np.array([-1, 0], np.int32), seg_begin=np.array([0, h], np.int32),
+               seg_end=np.array([h, na], np.int32), axis_root=np.array([0, h - 1], np.int32), pair_a=np.array(pa, np.int32),
+               pair_b=np.array(pb, np.int32), conf0=np.array([*lx[0], 1, 0, 0, 0, 0], np.float32),
+               gyration_radius=synth.gyration_radius(lx, lt, lx[0]))
+    sf, vo = R.RefScoring(), VinaOracle()
+    rm = R.RefModel(lig, rx, rt)
+    lig["local_xyz"], lig["seg_rel_origin"], lig["seg_rel_axis"] = rm.export()
+    cg = R.RefGrid.cache(sf, R.LINEAR, rm, BEGIN, END, N, 1e3)
+    needed = sorted(set(int(t) for t in lt if t > 1))
+    assert len(needed) >= 18                             # metals and generic types among them
+    grids = {t: vo.cache_populate(BEGIN, END, N, rx, rt, t) for t in needed}
+    for t in needed:
+        assert np.array_equal(grids[t], cg.grid(t)), "cache::populate, type %d" % t
+    d = DockOracle(vo, grids, BEGIN, END, N, lig, slope=1e3)
+    X = _confs(rs, lig, 1, 16, spread=3.0)
+    nn, nc = R.RefGrid.naive(sf, R.EXACT, rm), R.RefGrid.non_cache(sf, R.LINEAR, rm, BEGIN, END, N, 1e3)
+    for x in X:
+        c = rm.set(x)
+        assert np.array_equal(d.coords(x), c)
+        e, g = d.eval_deriv(x); er, gr = R.model_eval_deriv(rm, sf, R.LINEAR, cg, x)
+        assert e == er and np.array_equal(g, gr)
+        assert nn.eval(1000.0) == vo.naive_exact(rx, rt, c, lt, 1000.0)
+        assert nc.eval(1000.0) == vo.noncache_eval(rx, rt, c, lt, BEGIN, END, 1e3, 1000.0)
+    for x in X[:4]:
+        e, xo, g, _ = d.bfgs(x, 10); er, xr, gr = R.bfgs(rm, sf, R.LINEAR, cg, x, 10)
+        assert e == er and np.array_equal(xo, xr) and np.array_equal(g, gr)
+
+
 def test_grid_aligned_to_three_angstrom_shows_the_reference_cell_list_quirk():
     """szv_grid_cache::get (lib/szv_grid.h:124-150) sizes a 3 A cell's atom list by the brick [floor(c/3)*3, ceil(c/3)*3] of the FIRST
     probe point that touches the cell: when that coordinate is an exact multiple of 3 the brick collapses and the list misses atoms
