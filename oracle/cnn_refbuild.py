@@ -1,0 +1,92 @@
+"""ctypes front-end to oracle/_ref/libgnina_cnn_ref.so: the REFERENCE's own CNN scoring host code (lib/torch_model.cpp,
+lib/cnn_torch_scorer.cpp, lib/dl_scorer.cpp) compiled where it lies, running the reference's own TorchScript files with libtorch on the
+CPU; libmolgrid (third party, absent) is replaced by a stand-in over oracle/gridmaker_ref.c (oracle/ref_shim/libmolgrid).  TEST
+INFRASTRUCTURE: pins oracle/pipeline.py and generates tests/golden/cnn_ref_kat.npz.  Exists only where /root/reference does (the
+TorchScript files are read from there), i.e. in the build container -- not on the GPU box."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+from . import vina_refbuild as V
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_ref", "libgnina_cnn_ref.so")
+MODELS_DIR = "/root/reference/gninasrc/lib/models"
+_LIB = None
+
+
+def available():
+    return os.path.exists(_SO) and os.path.isdir(MODELS_DIR)
+
+
+def build():
+    """-> True if the library exists afterwards (needs /root/reference)"""
+    if not os.path.isdir(MODELS_DIR) or not V.build():
+        return False
+    from . import gridmaker
+    gridmaker.lib()
+    subprocess.check_call(["make", "-s", "-f", "Makefile.ref", "cnn"], cwd=_HERE)
+    return os.path.exists(_SO)
+
+
+def _f(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        import torch  # noqa: F401  (libtorch's shared objects are resolved through the interpreter's copy)
+        V.lib()
+        L = C.CDLL(_SO, mode=C.RTLD_GLOBAL)
+        fp = C.POINTER(C.c_float)
+        L.gcref_last_error.restype = C.c_char_p
+        L.gcref_load_models.argtypes = [C.c_char_p]
+        L.gcref_scorer_create.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_uint, C.c_uint, fp]
+        L.gcref_scorer_create.restype = C.c_void_p
+        L.gcref_scorer_destroy.argtypes = [C.c_void_p]
+        L.gcref_grid_dim.argtypes = [C.c_void_p]; L.gcref_grid_dim.restype = C.c_float
+        L.gcref_grid_res.argtypes = [C.c_void_p]; L.gcref_grid_res.restype = C.c_float
+        L.gcref_score.argtypes = [C.c_void_p, C.c_void_p, C.c_int, fp, fp]
+        L.gcref_center_and_box.argtypes = [C.c_void_p, C.c_void_p, fp, fp, fp, C.POINTER(C.c_int)]
+        if L.gcref_load_models(MODELS_DIR.encode()) <= 0:
+            raise RuntimeError("no TorchScript files under " + MODELS_DIR)
+        _LIB = L
+    return _LIB
+
+
+class RefCNNScorer:
+    """CNNTorchScorer<false>(cnn_options{cnn_model_names = names, cnn_models = files})"""
+
+    def __init__(self, names=(), files=(), rotations=0, seed=0, cnn_center=None):
+        L = lib()
+        na = (C.c_char_p * max(1, len(names)))(*[n.encode() for n in names])
+        fa = (C.c_char_p * max(1, len(files)))(*[f.encode() for f in files])
+        cc = None if cnn_center is None else _f(np.ascontiguousarray(cnn_center, np.float32))
+        self.p = L.gcref_scorer_create(na, len(names), fa, len(files), rotations, seed, cc)
+        if not self.p:
+            raise RuntimeError(L.gcref_last_error().decode())
+
+    def __del__(self):
+        try:
+            lib().gcref_scorer_destroy(self.p)
+        except Exception:
+            pass
+
+    def grid(self):
+        return lib().gcref_grid_dim(self.p), lib().gcref_grid_res(self.p)
+
+    def score(self, ref_model, gradient=False):
+        """score(m, compute_gradient, affinity, loss, variance) on the coordinates `ref_model` (vina_refbuild.RefModel) holds
+        -> (score, affinity, loss, variance, minus_forces[n_movable,3] as left in the model)"""
+        o = np.zeros(4, np.float32); mf = np.zeros((ref_model.na, 3), np.float32)
+        if lib().gcref_score(self.p, ref_model.p, int(gradient), _f(o), _f(mf)):
+            raise RuntimeError(lib().gcref_last_error().decode())
+        return float(o[0]), float(o[1]), float(o[2]), float(o[3]), mf
+
+    def center_and_box(self, ref_model):
+        c, b, e = (np.zeros(3, np.float32) for _ in range(3)); n = (C.c_int * 3)()
+        if lib().gcref_center_and_box(self.p, ref_model.p, _f(c), _f(b), _f(e), n):
+            raise RuntimeError(lib().gcref_last_error().decode())
+        return c, b, e, np.array(list(n))

@@ -44,7 +44,9 @@ def score_grad(models, rec_xyz, rec_types, lig_xyz, lig_types, pose_offsets, cen
     (TorchModel::forward autograd + GridMaker::backward, torch_model.cpp:197-221; 1/cnt scaling
     cnn_torch_scorer.cpp:176-179)."""
     n = len(pose_offsets) - 1
-    grad = np.zeros((len(lig_types), 3), np.float64)
+    # the reference accumulates the models' atom gradients in the model's float minus_forces (model::add_minus_forces) and scales the
+    # sum once by fl(1.0 / cnt) (scale_minus_forces, cnn_torch_scorer.cpp:176-179): the same association here
+    grad = np.zeros((len(lig_types), 3), np.float32)
     rgrad = np.zeros((len(rec_types), 3), np.float64)   # getReceptorGradient (torch_model.cpp:226-232), summed over poses
     per = []
     for m in models:
@@ -61,10 +63,12 @@ def score_grad(models, rec_xyz, rec_types, lig_xyz, lig_types, pose_offsets, cen
             g = gm.grid_forward(c, xyz, ch, rad, m.n_channels, b.resolution, b.dimension, b.radius_scaling)
             pose, aff, loss, dg = cnn_ref.loss_grid_gradient(b, g[None], dtype)
             ag = gm.grid_backward(c, xyz, ch, rad, dg[0].astype(np.float32), b.resolution, b.dimension, b.radius_scaling)
-            grad[sl] += ag[len(rec_xyz):] / len(models)
+            grad[sl] += ag[len(rec_xyz):].astype(np.float32)
             rgrad += ag[:len(rec_xyz)] / len(models)
             P.append(pose[0]); A.append(aff[0]); L.append(loss[0])
         per.append((P, A, L))
+    if len(models) > 1:
+        grad *= np.float32(1.0 / len(models))
     out = np.zeros((4, n))
     for i in range(n):
         out[:, i] = cnn_ref.ensemble([q[0][i] for q in per], [q[1][i] for q in per], [q[2][i] for q in per])

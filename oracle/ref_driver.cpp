@@ -496,6 +496,8 @@ void* gref_model_create(int n_atoms, const float* xyz, const int* types, int n_s
   return R;
 }
 void gref_model_destroy(void* p) { delete (RefModel*)p; }
+// the `model` inside the handle, for oracle/ref_cnn_driver.cpp (the reference's CNN scorer takes a model&)
+void* gref_model_ptr(void* p) { return &((RefModel*)p)->m; }
 // what the reference's constructors computed: atom coordinates in their segment frames, segment origin relative to the parent
 // origin, unit rotation axis
 void gref_model_export(void* p, float* local_xyz, float* rel_origin, float* rel_axis) {
