@@ -430,12 +430,28 @@ def with_box_penalties(loss, grad, coords, heavy, search_box, cnn_box, slope):
     return e, (g + (d1 + d2)).astype(F)
 
 
-def cnn_energy(scorer, types, search_box, slope=10.0, cnn_center=None):
+def route_forces_like_the_reference(grad, heavy):
+    """What CNNTorchScorer::score leaves in the model: getGradient builds a list indexed by movable atom (cnn_torch_scorer.cpp:209-227)
+    and model::add_minus_forces consumes it COMPACTLY over the non-hydrogen atoms (lib/model.cu:247-259) -- the j-th heavy atom receives
+    entry j.  With no hydrogens among the movable atoms this is the identity; with hydrogens the heavy atoms after the first hydrogen
+    receive their predecessors' gradients.  Confirmed on the reference's own code with real networks
+    (tests/test_oracle_cnn_vs_reference_build.py); grad [k, na, 3] by atom -> [k, na, 3] as the reference's minimiser sees it"""
+    hv = np.flatnonzero(heavy)
+    if len(hv) == len(heavy):
+        return grad
+    out = np.zeros_like(grad)
+    out[:, hv] = grad[:, :len(hv)]
+    return out
+
+
+def cnn_energy(scorer, types, search_box, slope=10.0, cnn_center=None, reference_force_routing=True):
     """non_cache_cnn::eval_deriv for a batch of poses of ONE ligand: the CNN loss and its atom gradients from ONE gb_cnn_score_grad call,
     plus the out-of-box penalties of the search box and of the CNN's cubic grid.  The grid centre of every pose is the mean of ITS
     heavy atoms in its start conformation -- adjust_center sets it once before a pose's minimisation (lib/non_cache_cnn.cpp:57-68,
     lib/dl_scorer.cpp:196-217) -- unless cnn_centers [n,3] are given; the network itself centres its grid on the pose (--cnn_center
-    unset), as TorchModel::forward does.  -> energy_and_forces(coords, idx) for minimize_poses"""
+    unset), as TorchModel::forward does.  reference_force_routing: hand the minimiser the forces the reference's scorer leaves in the
+    model (route_forces_like_the_reference) so that ligands WITH hydrogens move exactly as under gnina; False = the true per-atom
+    gradient.  -> energy_and_forces(coords, idx) for minimize_poses"""
     types = np.ascontiguousarray(types, np.int32)
     heavy = types >= 2
     half = F(scorer.model_info(0).dimension) / F(2)
@@ -448,6 +464,8 @@ def cnn_energy(scorer, types, search_box, slope=10.0, cnn_center=None):
         offs = (np.arange(k + 1) * na).astype(np.int32)
         out = scorer.score_grad_batch(coords.reshape(-1, 3), np.tile(types, k), offs)
         loss, grad = np.asarray(out[2], F), np.asarray(out[4], F).reshape(k, na, 3)
+        if reference_force_routing:
+            grad = route_forces_like_the_reference(grad, heavy)
         c = state["centers"][idx][:, None, :]
         return with_box_penalties(loss, grad, coords, heavy, search_box, (c - half, c + half), slope)
     return energy_and_forces

@@ -339,6 +339,7 @@ class CnnBatchEnergy {
   gb_cnn* h_;
   const LigandTree& tree_;
   float begin_[3], end_[3], slope_, half_;
+  bool reference_force_routing_ = true;
   std::vector<float> centers_, loss_, grad_;
   std::vector<int32_t> types_, offs_;
 
@@ -357,6 +358,12 @@ class CnnBatchEnergy {
     for (int j = 0; j < 3; j++) { begin_[j] = box_begin[j]; end_[j] = box_end[j]; }
   }
   void set_slope(float s) { slope_ = s; }               // refine_structure escalates it (main/main.cpp:145-154)
+  // true (default): the minimiser sees the forces CNNTorchScorer::score leaves in the model -- getGradient's by-atom list consumed
+  // COMPACTLY over the non-hydrogen atoms by model::add_minus_forces (lib/cnn_torch_scorer.cpp:209-227, lib/model.cu:247-259): the
+  // j-th heavy atom receives entry j.  Identity for ligands without hydrogens; with hydrogens it is what makes a pose move exactly
+  // as under gnina (checked against the reference's own code with real networks, tests/test_oracle_cnn_vs_reference_build.py).
+  // false: the true per-atom gradient.
+  void set_reference_force_routing(bool on) { reference_force_routing_ = on; }
   // the CNN box of every pose from its start conformation
   void set_centers(const float* confs, int n) {
     const int na = tree_.n_atoms, ns = tree_.n_seg, nx = tree_.conf_floats();
@@ -380,15 +387,18 @@ class CnnBatchEnergy {
       const float* cen = &centers_[3 * (size_t)pose[j]];
       const float lo[3] = {cen[0] - half_, cen[1] - half_, cen[2] - half_}, hi[3] = {cen[0] + half_, cen[1] + half_, cen[2] + half_};
       float en = loss_[j];
+      int n_heavy_before = 0;
       for (int a = 0; a < na; a++) {
         float* f = forces + ((size_t)j * na + a) * 3;
         if (!tree_.heavy(a)) { f[0] = f[1] = f[2] = 0; continue; }
+        const int src = reference_force_routing_ ? n_heavy_before : a;   // which entry of the by-atom gradient this atom receives
+        n_heavy_before++;
         const float* x = coords + ((size_t)j * na + a) * 3;
         float d1[3] = {0, 0, 0}, d2[3] = {0, 0, 0};
         float pen = bounds(begin_, end_, x, d1);
         pen += bounds(lo, hi, x, d2);
         en += pen;
-        for (int q = 0; q < 3; q++) f[q] = grad_[((size_t)j * na + a) * 3 + q] + (d1[q] + d2[q]);
+        for (int q = 0; q < 3; q++) f[q] = grad_[((size_t)j * na + src) * 3 + q] + (d1[q] + d2[q]);
       }
       e[j] = en;
     }

@@ -46,6 +46,7 @@ def lib():
         L.gcref_scorer_create.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_uint, C.c_uint, fp]
         L.gcref_scorer_create.restype = C.c_void_p
         L.gcref_scorer_destroy.argtypes = [C.c_void_p]
+        L.gcref_scorer_dl.argtypes = [C.c_void_p]; L.gcref_scorer_dl.restype = C.c_void_p
         L.gcref_grid_dim.argtypes = [C.c_void_p]; L.gcref_grid_dim.restype = C.c_float
         L.gcref_grid_res.argtypes = [C.c_void_p]; L.gcref_grid_res.restype = C.c_float
         L.gcref_score.argtypes = [C.c_void_p, C.c_void_p, C.c_int, fp, fp]
@@ -73,6 +74,10 @@ class RefCNNScorer:
             lib().gcref_scorer_destroy(self.p)
         except Exception:
             pass
+
+    def dl(self):
+        """the scorer as a DLScorer* for vina_refbuild.minimize_dl / refine_dl"""
+        return lib().gcref_scorer_dl(self.p)
 
     def grid(self):
         return lib().gcref_grid_dim(self.p), lib().gcref_grid_res(self.p)

@@ -75,6 +75,8 @@ void* gcref_scorer_create(const char** names, int n_names, const char** files, i
   return R;
 }
 void gcref_scorer_destroy(void* p) { delete (RefCNN*)p; }
+// as a DLScorer*, for libgnina_vina_ref.so's gref_minimize_dl / gref_refine_dl (quasi_newton + non_cache_cnn over any DLScorer)
+void* gcref_scorer_dl(void* p) { return static_cast<DLScorer*>(((RefCNN*)p)->s.get()); }
 
 // the model names the constructor resolved (aliases and ensembles expanded) are private; the expansion is observable through
 // the number of evaluations only, so the driver reports what the public interface offers

@@ -272,29 +272,37 @@ int gref_noncache_cnn_compare(void* mp, void* sf, int kind, const float* begin, 
 
 // quasi_newton::operator() with ig = non_cache_cnn around the analytic test double: what --minimize --cnn_scoring all runs per pose
 // (main/main.cpp:264-268 -> refine_structure -> quasi_newton; here ONE quasi-Newton run, no slope escalation); x is updated
+static void minimize_over(RefModel* R, RefSF* S, int kind, const float* begin, const float* end, const int* n, float slope, DLScorer& dl,
+                          float* x, int maxiters, int accurate, int early_term, float* e) {
+  model& m = R->m;
+  non_cache_cnn nc(*R->gcache, make_dims(begin, end, n), S->prec[kind].get(), slope, dl);
+  m.set(make_conf(m, x));
+  nc.adjust_center(m);
+  minimization_params mp_;
+  mp_.maxiters = (unsigned)maxiters;
+  mp_.type = accurate ? minimization_params::BFGSAccurateLineSearch : minimization_params::BFGSFastLineSearch;
+  mp_.early_term = early_term != 0;
+  quasi_newton qn(mp_);
+  output_type out(make_conf(m, x), 0);
+  change g(m.get_size(), false);
+  grid user_grid;
+  qn(m, *S->prec[kind], nc, out, g, vec(1000, 1000, 1000), user_grid);
+  *e = out.e;
+  read_conf(out.c, x);
+}
 int gref_minimize_cnn(void* mp, void* sf, int kind, const float* begin, const float* end, const int* n, float slope, float dim, float res,
                       float k, const float* target, float* x, int maxiters, int accurate, int early_term, float* e) {
-  RefModel* R = (RefModel*)mp; RefSF* S = (RefSF*)sf;
   return guarded([&] {
-    model& m = R->m;
     AnalyticLoss L; L.k = k; for (int j = 0; j < 3; j++) L.target[j] = target[j];
     cnn_options o;
     FakeDLScorer dl(o, L, dim, res);
-    non_cache_cnn nc(*R->gcache, make_dims(begin, end, n), S->prec[kind].get(), slope, dl);
-    m.set(make_conf(m, x));
-    nc.adjust_center(m);
-    minimization_params mp_;
-    mp_.maxiters = (unsigned)maxiters;
-    mp_.type = accurate ? minimization_params::BFGSAccurateLineSearch : minimization_params::BFGSFastLineSearch;
-    mp_.early_term = early_term != 0;
-    quasi_newton qn(mp_);
-    output_type out(make_conf(m, x), 0);
-    change g(m.get_size(), false);
-    grid user_grid;
-    qn(m, *S->prec[kind], nc, out, g, vec(1000, 1000, 1000), user_grid);
-    *e = out.e;
-    read_conf(out.c, x);
+    minimize_over((RefModel*)mp, (RefSF*)sf, kind, begin, end, n, slope, dl, x, maxiters, accurate, early_term, e);
   });
+}
+// the same run over ANY DLScorer -- oracle/ref_cnn_driver.cpp passes the reference's own CNNTorchScorer (real networks on libtorch)
+int gref_minimize_dl(void* mp, void* sf, int kind, const float* begin, const float* end, const int* n, float slope, void* dl, float* x,
+                     int maxiters, int accurate, int early_term, float* e) {
+  return guarded([&] { minimize_over((RefModel*)mp, (RefSF*)sf, kind, begin, end, n, slope, *(DLScorer*)dl, x, maxiters, accurate, early_term, e); });
 }
 
 // this repo's C++ lock-step minimiser (include/gnina_b200_minimize.hpp) on n conformations of the model's ligand at once, with
@@ -347,37 +355,44 @@ int gref_lockstep_minimize(void* mp, const float* begin, const float* end, const
 // refine_structure (main/main.cpp:131-171, which is not a library source) replayed with the REFERENCE's parts on ig = non_cache_cnn:
 // adjust_center once, then up to five quasi_newton runs with the slope 10, 100, ... until non_cache_cnn::within -- the refinement of
 // --cnn_scoring refinement / all.  x is updated; *inside tells whether the pose ended within
+static void refine_over(RefModel* R, RefSF* S, int kind, const float* begin, const float* end, const int* n, DLScorer& dl, float* x, int maxiters,
+                        int accurate, int early_term, float* e, int* inside) {
+  model& m = R->m;
+  non_cache_cnn nc(*R->gcache, make_dims(begin, end, n), S->prec[kind].get(), 1e3, dl);
+  m.set(make_conf(m, x));
+  nc.adjust_center(m);
+  minimization_params mp_;
+  mp_.maxiters = (unsigned)maxiters;
+  mp_.type = accurate ? minimization_params::BFGSAccurateLineSearch : minimization_params::BFGSFastLineSearch;
+  mp_.early_term = early_term != 0;
+  quasi_newton qn(mp_);
+  output_type out(make_conf(m, x), 0);
+  change g(m.get_size(), false);
+  grid user_grid;
+  fl slope = 10;
+  for (int p = 0; p < 5; p++) {
+    nc.setSlope(slope);
+    qn(m, *S->prec[kind], nc, out, g, vec(1000, 1000, 1000), user_grid);
+    m.set(out.c);
+    if (nc.within(m)) break;
+    slope *= 10;
+  }
+  *inside = nc.within(m) ? 1 : 0;
+  *e = *inside ? out.e : max_fl;
+  read_conf(out.c, x);
+}
 int gref_refine_cnn(void* mp, void* sf, int kind, const float* begin, const float* end, const int* n, float dim, float res, float k,
                     const float* target, float* x, int maxiters, int accurate, int early_term, float* e, int* inside) {
-  RefModel* R = (RefModel*)mp; RefSF* S = (RefSF*)sf;
   return guarded([&] {
-    model& m = R->m;
     AnalyticLoss L; L.k = k; for (int j = 0; j < 3; j++) L.target[j] = target[j];
     cnn_options o;
     FakeDLScorer dl(o, L, dim, res);
-    non_cache_cnn nc(*R->gcache, make_dims(begin, end, n), S->prec[kind].get(), 1e3, dl);
-    m.set(make_conf(m, x));
-    nc.adjust_center(m);
-    minimization_params mp_;
-    mp_.maxiters = (unsigned)maxiters;
-    mp_.type = accurate ? minimization_params::BFGSAccurateLineSearch : minimization_params::BFGSFastLineSearch;
-    mp_.early_term = early_term != 0;
-    quasi_newton qn(mp_);
-    output_type out(make_conf(m, x), 0);
-    change g(m.get_size(), false);
-    grid user_grid;
-    fl slope = 10;
-    for (int p = 0; p < 5; p++) {
-      nc.setSlope(slope);
-      qn(m, *S->prec[kind], nc, out, g, vec(1000, 1000, 1000), user_grid);
-      m.set(out.c);
-      if (nc.within(m)) break;
-      slope *= 10;
-    }
-    *inside = nc.within(m) ? 1 : 0;
-    *e = *inside ? out.e : max_fl;
-    read_conf(out.c, x);
+    refine_over((RefModel*)mp, (RefSF*)sf, kind, begin, end, n, dl, x, maxiters, accurate, early_term, e, inside);
   });
+}
+int gref_refine_dl(void* mp, void* sf, int kind, const float* begin, const float* end, const int* n, void* dl, float* x, int maxiters,
+                   int accurate, int early_term, float* e, int* inside) {
+  return guarded([&] { refine_over((RefModel*)mp, (RefSF*)sf, kind, begin, end, n, *(DLScorer*)dl, x, maxiters, accurate, early_term, e, inside); });
 }
 
 const char* gref_last_error() { return g_err.c_str(); }

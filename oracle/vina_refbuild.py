@@ -41,6 +41,8 @@ def lib():
                                         C.c_int, C.c_int, _fp]
         L.gref_refine_cnn.argtypes = [_vp, _vp, C.c_int, _fp, _fp, _ip, C.c_float, C.c_float, C.c_float, _fp, _fp, C.c_int, C.c_int, C.c_int,
                                       _fp, _ip]
+        L.gref_minimize_dl.argtypes = [_vp, _vp, C.c_int, _fp, _fp, _ip, C.c_float, _vp, _fp, C.c_int, C.c_int, C.c_int, _fp]
+        L.gref_refine_dl.argtypes = [_vp, _vp, C.c_int, _fp, _fp, _ip, _vp, _fp, C.c_int, C.c_int, C.c_int, _fp, _ip]
         L.gref_lockstep_minimize.argtypes = [_vp, _fp, _fp, _ip, C.c_float, C.c_float, C.c_float, C.c_float, _fp, _fp, C.c_int, C.c_int, C.c_int,
                                              C.c_int, _fp, _ip, _ip, _ip]
         L.gref_sf_create.argtypes = [C.c_float, C.c_float]; L.gref_sf_create.restype = _vp
@@ -273,6 +275,23 @@ def minimize_cnn(model, sf, kind, begin, end, n, conf, maxiters, slope=10.0, dim
     _ok(lib().gref_minimize_cnn(model.p, sf.p, kind, _f(b), _f(e_), _i(nn), slope, dim, res, k, _f(tg), _f(x), maxiters, int(accurate),
                                 int(early_term), _f(e)))
     return float(e[0]), x
+
+
+def minimize_dl(model, sf, kind, begin, end, n, conf, maxiters, dl, slope=10.0, accurate=True, early_term=False):
+    """the REFERENCE's quasi_newton with ig = non_cache_cnn around ANY DLScorer* (dl: e.g. cnn_refbuild.RefCNNScorer.dl(), the
+    reference's own CNNTorchScorer) -> (e, conf)"""
+    b, e_, nn = (np.ascontiguousarray(a, dt) for a, dt in ((begin, np.float32), (end, np.float32), (n, np.int32)))
+    x = np.array(conf, np.float32); e = np.empty(1, np.float32)
+    _ok(lib().gref_minimize_dl(model.p, sf.p, kind, _f(b), _f(e_), _i(nn), slope, dl, _f(x), maxiters, int(accurate), int(early_term), _f(e)))
+    return float(e[0]), x
+
+
+def refine_dl(model, sf, kind, begin, end, n, conf, maxiters, dl, accurate=False, early_term=False):
+    """refine_structure replayed with the reference's parts around ANY DLScorer* -> (e or max_fl, conf, inside)"""
+    b, e_, nn = (np.ascontiguousarray(a, dt) for a, dt in ((begin, np.float32), (end, np.float32), (n, np.int32)))
+    x = np.array(conf, np.float32); e = np.empty(1, np.float32); ins = np.zeros(1, np.int32)
+    _ok(lib().gref_refine_dl(model.p, sf.p, kind, _f(b), _f(e_), _i(nn), dl, _f(x), maxiters, int(accurate), int(early_term), _f(e), _i(ins)))
+    return float(e[0]), x, bool(ins[0])
 
 
 def refine_cnn(model, sf, kind, begin, end, n, conf, maxiters, dim=23.5, res=0.5, k=0.01, target=(0, 0, 0), accurate=False, early_term=False):

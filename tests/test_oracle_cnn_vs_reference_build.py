@@ -70,3 +70,70 @@ def test_unknown_names_are_usage_errors_on_both_sides():
         CR.RefCNNScorer(names=["nonesuch"])
     with pytest.raises(FileNotFoundError, match="Invalid model name"):
         model_blob.load_model("nonesuch")
+
+
+class _OracleNetwork:
+    """the CNNScorer interface minimize.cnn_energy uses, served by oracle/pipeline.py on the CPU"""
+
+    def __init__(self, names, rx, rt):
+        self.oms = [pipeline.OracleModel(model_blob.load_model(n)) for n in names]
+        self.rx, self.rt, self.calls = rx, rt, 0
+
+    def model_info(self, i):
+        class Info:
+            dimension, resolution = 23.5, 0.5
+        return Info
+
+    def score_grad_batch(self, xyz, types, offs):
+        self.calls += 1
+        return pipeline.score_grad(self.oms, self.rx, self.rt, xyz, types, offs, dtype=torch.float32)
+
+
+def _host_libm():
+    import ctypes
+    m = ctypes.CDLL("libm.so.6")
+
+    def wrap(name):
+        f = getattr(m, name); f.argtypes = [ctypes.c_float]; f.restype = ctypes.c_float
+        return lambda a: np.array([f(float(v)) for v in np.asarray(a, np.float32).ravel()], np.float32).reshape(np.shape(a))
+    return wrap("sinf"), wrap("cosf"), wrap("acosf")
+
+
+@pytest.mark.parametrize("hydrogens", [False, True])
+def test_config5_minimisation_with_real_networks(hydrogens):
+    """BASELINE config 5 end to end on the CPU: the REFERENCE's quasi_newton (accurate line search, what --minimize selects) over its
+    non_cache_cnn over its CNNTorchScorer running the real crossdock_default2018 TorchScript file, one pose at a time -- against this
+    repo's lock-step minimiser (gnina_b200/minimize.py: minimize_poses + cnn_energy) over the restated network, all poses in one batch.
+    Energies and conformations are EQUAL.  With hydrogens among the ligand atoms that needs the reference's force routing
+    (add_minus_forces consumes getGradient's by-atom list compactly, lib/model.cu:247-259): with the true per-atom gradient the
+    minimiser ends elsewhere -- at lower energies, which is what one expects of the correct gradient."""
+    from gnina_b200 import minimize as M
+    begin, end, nn = [-9.7] * 3, [10.55] * 3, [54] * 3
+    lig = dict(synth.make_flexible_ligand(n_heavy=14, n_tors=3, n_branch=2, seed=8))
+    if hydrogens:
+        ty = lig["types"].copy(); ty[3] = 1; ty[8] = 0; lig["types"] = ty
+    rx, rt = synth.make_receptor(400, box=24, seed=5)
+    sf, rm = R.RefScoring(), R.RefModel(lig, rx, rt)
+    lig2 = dict(lig); lig2["local_xyz"], lig2["seg_rel_origin"], lig2["seg_rel_axis"] = rm.export()
+    tree = M.TorsionTree(lig2)
+    rs = np.random.RandomState(1)
+    X = np.tile(lig["conf0"], (3, 1)).astype(np.float32)
+    X[:, :3] += rs.uniform(-1, 1, (3, 3)); X[:, 7:] = rs.uniform(-1, 1, (3, X.shape[1] - 7))
+    X = X.astype(np.float32)
+    s = CR.RefCNNScorer(names=["crossdock_default2018"])
+    ref = [R.minimize_dl(rm, sf, R.LINEAR, begin, end, nn, x, 4, s.dl(), accurate=True) for x in X]
+    M.set_transcendentals(*_host_libm())                 # the reference build executes this host's sinf / cosf / acosf
+    try:
+        net = _OracleNetwork(["crossdock_default2018"], rx, rt)
+        energy = M.cnn_energy(net, lig["types"], (np.float32(begin), np.float32(end)), slope=10.0)
+        e, x, ev, rounds = M.minimize_poses(tree, energy, X, maxiters=4, accurate=True)
+        for i in range(len(X)):
+            assert float(e[i]) == ref[i][0] and np.array_equal(x[i], ref[i][1])
+        assert net.calls == rounds + 1 and net.calls < ev.sum()          # one batched network call per round
+        if hydrogens:
+            net2 = _OracleNetwork(["crossdock_default2018"], rx, rt)
+            true_grad = M.cnn_energy(net2, lig["types"], (np.float32(begin), np.float32(end)), slope=10.0, reference_force_routing=False)
+            e2, x2, _, _ = M.minimize_poses(tree, true_grad, X, maxiters=4, accurate=True)
+            assert not np.array_equal(x2, x) and e2.sum() < e.sum()
+    finally:
+        M.set_transcendentals()
