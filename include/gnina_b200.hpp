@@ -310,6 +310,7 @@ class NonCacheCNNT {
   Emp* vina_ = nullptr;
   float emp_weight_ = 1.f;
   bool mix_force_ = false, mix_energy_ = false;
+  bool reference_force_routing_ = true;
 
   static bool is_hydrogen(int32_t t) { return t == 0 || t == 1; }
   // non_cache::check_bounds_deriv, lib/non_cache.cpp:102-123
@@ -340,6 +341,10 @@ class NonCacheCNNT {
   void set_empirical(Emp* vina, float weight, bool mix_force, bool mix_energy) {
     vina_ = vina; emp_weight_ = weight; mix_force_ = mix_force && vina; mix_energy_ = mix_energy && vina;
   }
+  // true (default): the CNN forces are routed as CNNTorchScorer::score leaves them in the model -- getGradient's by-atom list consumed
+  // compactly over the non-hydrogen atoms by model::add_minus_forces (cnn_torch_scorer.cpp:209-227, model.cu:247-259): the j-th heavy
+  // atom receives entry j.  Identity without hydrogens.  false: the true per-atom gradient.
+  void set_reference_force_routing(bool on) { reference_force_routing_ = on; }
   // eval (minus_forces == nullptr, lib/non_cache_cnn.cpp:33-54): loss + penalties.
   // eval_deriv (:79-169): additionally fills minus_forces[n_atoms][3] (zero for hydrogens); v = curl cap of the empirical
   // term.  With mix_emp_force the forces are (cnn + oob + w (emp + oob_search_box)) / (1 + w); with mix_emp_energy the
@@ -356,15 +361,19 @@ class NonCacheCNNT {
       vina_->noncache_atoms(lig_xyz, lig_type, n, b, en, v, emp_e, emp_d);
     }
     if (minus_forces) minus_forces->assign(3 * (size_t)n, 0.f);
+    int n_heavy_before = 0;
     for (int i = 0; i < n; i++) {
-      if (lig_type[i] < 0 || lig_type[i] >= 28 || is_hydrogen(lig_type[i])) continue;
+      if (is_hydrogen(lig_type[i])) continue;
+      const int src = reference_force_routing_ ? n_heavy_before : i;   // which entry of the by-atom gradient atom i receives
+      n_heavy_before++;
+      if (lig_type[i] < 0 || lig_type[i] >= 28) continue;
       float d_emp_box[3] = {0, 0, 0}, d_cnn_box[3] = {0, 0, 0};
       float pen = check_bounds(gd_, lig_xyz + 3 * i, minus_forces ? d_emp_box : nullptr);
       pen += check_bounds(cnn_gd_, lig_xyz + 3 * i, minus_forces ? d_cnn_box : nullptr);
       e += pen;
       if (minus_forces) {
         for (int k = 0; k < 3; k++) {
-          float f = grad[3 * i + k] + (d_emp_box[k] + d_cnn_box[k]);   // the reference adds (0 + oob + cnn_oob) to the CNN force
+          float f = grad[3 * src + k] + (d_emp_box[k] + d_cnn_box[k]);   // the reference adds (0 + oob + cnn_oob) to the CNN force
           if (mixing) f = (f + emp_weight_ * (emp_d[3 * i + k] + d_emp_box[k])) / (1.0f + emp_weight_);
           (*minus_forces)[3 * i + k] = f;
         }

@@ -179,7 +179,11 @@ class FakeDLScorer : public DLScorer {
     for (int i = 0; i < n; i++) { t[i] = (int32_t)m.atoms[i].sm; for (int j = 0; j < 3; j++) xyz[3 * i + j] = m.coords[i][j]; }
     m.clear_minus_forces();                                                  // CNNTorchScorer::score does (cnn_torch_scorer.cpp:115)
     loss = L.eval(xyz.data(), t.data(), n, compute_gradient ? g.data() : nullptr);
-    if (compute_gradient) for (int i = 0; i < n; i++) m.minus_forces[i] = vec(g[3 * i], g[3 * i + 1], g[3 * i + 2]);
+    if (compute_gradient) {                                                  // by-atom list -> add_minus_forces, as :167-173, 209-227
+      std::vector<gfloat3> list(n);
+      for (int i = 0; i < n; i++) list[i] = gfloat3(g[3 * i], g[3 * i + 1], g[3 * i + 2]);
+      m.add_minus_forces(list);
+    }
     affinity = 0; variance = 0;
     return std::exp(-loss);
   }

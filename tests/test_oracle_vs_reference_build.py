@@ -313,6 +313,15 @@ def test_non_cache_cnn_host_logic_matches_the_reference():
     assert outside >= 5
 
 
+def _routed(grad, heavy):
+    """the analytic network's by-atom gradient (zero for hydrogens) as the reference's scorer leaves it in the model: consumed compactly
+    over the heavy atoms by model::add_minus_forces (minimize.route_forces_like_the_reference)"""
+    from gnina_b200 import minimize
+    g = np.asarray(grad, np.float32).copy()
+    g[:, ~heavy] = 0
+    return minimize.route_forces_like_the_reference(g, heavy)
+
+
 def _host_libm():
     import ctypes
     m = ctypes.CDLL("libm.so.6")
@@ -354,7 +363,7 @@ def test_lock_step_minimiser_reproduces_the_reference_pose_by_pose():
                 for j in range(3):
                     loss = (loss + k * d[:, a, j] * d[:, a, j]).astype(np.float32)
             c = centers[idx][:, None, :]
-            return minimize.with_box_penalties(loss, (2 * k * d).astype(np.float32), coords, heavy, (begin, end), (c - half, c + half), slope)
+            return minimize.with_box_penalties(loss, _routed(2 * k * d, heavy), coords, heavy, (begin, end), (c - half, c + half), slope)
         for acc, et, iters in ((True, False, 10000), (False, True, 200)):
             calls[0] = 0
             e, x, ev, rounds = minimize.minimize_poses(tree, energy, X, maxiters=iters, accurate=acc, early_term=et)
@@ -416,7 +425,7 @@ def test_lock_step_cnn_refinement_reproduces_refine_structure():
                     for j in range(3):
                         loss = (loss + k * d[:, a, j] * d[:, a, j]).astype(np.float32)
                 c = centers[idx][:, None, :]
-                return minimize.with_box_penalties(loss, (2 * k * d).astype(np.float32), coords, heavy, (begin, end), (c - half, c + half), slope)
+                return minimize.with_box_penalties(loss, _routed(2 * k * d, heavy), coords, heavy, (begin, end), (c - half, c + half), slope)
             return energy
         within = minimize.within_boxes(heavy, [(centers - half, centers + half), (np.float32(begin), np.float32(end))])
         e, x, inside, ev = minimize.refine_structure_poses(tree, make_energy, within, X, 30)
