@@ -65,6 +65,7 @@ struct Scores { std::vector<float> score, affinity, loss, variance; };
 class CNNScorer {
   gb_cnn* h_ = nullptr;
   std::vector<gb_model*> models_;
+  std::vector<gb_model_info> infos_;   // per model; kept by fresh copies too (they share the handle's models, not models_)
   int device_ = 0;
   int n_rec_ = 0;
   CNNScorer() = default;
@@ -79,6 +80,9 @@ class CNNScorer {
       if (rc == GB_ERR_USAGE) throw usage_error("Invalid model name: " + n);  // cnn_torch_scorer.cpp:70-72
       check(rc);
       models_.push_back(m);
+      gb_model_info inf;
+      check(gb_model_get_info(m, &inf));
+      infos_.push_back(inf);
     }
     check(gb_cnn_create(models_.data(), (int)models_.size(), device, &h_));
   }
@@ -95,12 +99,13 @@ class CNNScorer {
     std::unique_ptr<CNNScorer> c(new CNNScorer);
     c->device_ = device_;
     c->n_rec_ = n_rec_;
+    c->infos_ = infos_;
     check(gb_cnn_clone(h_, &c->h_));
     return c;
   }
   void set_option(const char* key, double v) { check(gb_cnn_set_option(h_, key, v)); }
   gb_cnn* handle() const { return h_; }   // for the C-ABI level helpers (gnina_b200_minimize.hpp's CnnBatchEnergy)
-  gb_model_info info(int i = 0) const { gb_model_info x; check(gb_model_get_info(models_.at(i), &x)); return x; }
+  gb_model_info info(int i = 0) const { return infos_.at(i); }
   void set_receptor(const float* xyz, const int32_t* smina_type, int n) {
     check(gb_cnn_set_receptor(h_, xyz, smina_type, n));
     n_rec_ = n;

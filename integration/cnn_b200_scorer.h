@@ -20,6 +20,7 @@
 class CNNB200Scorer : public DLScorer {
   gb_cnn* h = nullptr;
   std::vector<gb_model*> models;
+  gb_model_info info0{};                       // grid dimension / resolution of the first model (get_grid_dim / get_grid_res); copies keep it
   int device = 0;
   std::string blob_dir;                        // where the converted model blobs live (tools/extract_models.py output)
   std::vector<float> uploaded_receptor;        // coordinates of the last gb_cnn_set_receptor: re-upload only when flex atoms moved
@@ -66,6 +67,7 @@ class CNNB200Scorer : public DLScorer {
   CNNB200Scorer(const cnn_options& opts, int device_, const std::string& blob_dir_) : DLScorer(opts), device(device_), blob_dir(blob_dir_) {
     if (cnnopts.cnn_scoring == CNNnone) return;                                  // cnn_torch_scorer.cpp:25-26
     load_models();
+    if (!models.empty()) check(gb_model_get_info(models[0], &info0));
     check(gb_cnn_create(models.data(), (int)models.size(), device, &h));
     check(gb_cnn_set_option(h, "cnn_rotation", (double)cnnopts.cnn_rotations));  // :127-163
     check(gb_cnn_set_option(h, "rotation_seed", (double)cnnopts.seed));
@@ -121,18 +123,16 @@ class CNNB200Scorer : public DLScorer {
   // fresh_copy (lib/cnn_torch_scorer.h:54): an independent handle for another thread that shares the device weights
   std::shared_ptr<DLScorer> fresh_copy() const override {
     std::shared_ptr<CNNB200Scorer> c = std::make_shared<CNNB200Scorer>();
-    c->cnnopts = cnnopts; c->device = device; c->blob_dir = blob_dir;
+    c->cnnopts = cnnopts; c->device = device; c->blob_dir = blob_dir; c->info0 = info0;
     if (h) check(gb_cnn_clone(h, &c->h));
     return c;
   }
 
   // lib/cnn_torch_scorer.cpp:229-241
   void set_bounding_box(grid_dims& box) const override {
-    if (models.empty()) return;
-    gb_model_info inf;
-    check(gb_model_get_info(models[0], &inf));
+    if (!h) return;
     const vec center = get_center();
-    const fl dim = inf.dimension, n = dim / inf.resolution, half = dim / 2.0;
+    const fl dim = info0.dimension, n = dim / info0.resolution, half = dim / 2.0;
     for (unsigned i = 0; i < 3; i++) {
       box[i].begin = center[i] - half;
       box[i].end = center[i] + half;

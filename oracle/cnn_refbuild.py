@@ -47,6 +47,8 @@ def lib():
         L.gcref_scorer_create.restype = C.c_void_p
         L.gcref_scorer_destroy.argtypes = [C.c_void_p]
         L.gcref_scorer_dl.argtypes = [C.c_void_p]; L.gcref_scorer_dl.restype = C.c_void_p
+        L.gcref_adapter_create.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_char_p, fp, C.c_int]
+        L.gcref_adapter_create.restype = C.c_void_p
         L.gcref_grid_dim.argtypes = [C.c_void_p]; L.gcref_grid_dim.restype = C.c_float
         L.gcref_grid_res.argtypes = [C.c_void_p]; L.gcref_grid_res.restype = C.c_float
         L.gcref_score.argtypes = [C.c_void_p, C.c_void_p, C.c_int, fp, fp]
@@ -68,6 +70,22 @@ class RefCNNScorer:
         self.p = L.gcref_scorer_create(na, len(names), fa, len(files), rotations, seed, cc)
         if not self.p:
             raise RuntimeError(L.gcref_last_error().decode())
+
+    @classmethod
+    def adapter(cls, names=(), files=(), cnn_center=None, blob_dir=None, fresh_copy=False):
+        """integration/cnn_b200_scorer.h's CNNB200Scorer -- the class a gnina maintainer adds -- constructed over a stand-in for the twelve
+        C-ABI entry points it calls (oracle/ref_cnn_driver.cpp: the ABI's contract with the reference's TorchModel as the network), so
+        that the adapter's own code runs on the CPU inside the reference's classes.  Same methods as the reference scorer."""
+        L = lib()
+        self = cls.__new__(cls)
+        na = (C.c_char_p * max(1, len(names)))(*[n.encode() for n in names])
+        fa = (C.c_char_p * max(1, len(files)))(*[f.encode() for f in files])
+        cc = None if cnn_center is None else _f(np.ascontiguousarray(cnn_center, np.float32))
+        bd = blob_dir or os.path.join(os.path.dirname(_HERE), "gnina_b200", "weights")
+        self.p = L.gcref_adapter_create(na, len(names), fa, len(files), bd.encode(), cc, int(fresh_copy))
+        if not self.p:
+            raise RuntimeError(L.gcref_last_error().decode())
+        return self
 
     def __del__(self):
         try:

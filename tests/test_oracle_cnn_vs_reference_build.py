@@ -137,3 +137,34 @@ def test_config5_minimisation_with_real_networks(hydrogens):
             assert not np.array_equal(x2, x) and e2.sum() < e.sum()
     finally:
         M.set_transcendentals()
+
+
+@pytest.mark.parametrize("fresh_copy", [False, True])
+def test_the_integration_adapter_is_a_drop_in_for_cnn_torch_scorer(fresh_copy):
+    """integration/cnn_b200_scorer.h (CNNB200Scorer : DLScorer -- the class a gnina maintainer adds) EXECUTED, not only compiled: its
+    twelve C-ABI calls are served by a stand-in that honours include/gnina_b200.h's contract with the reference's own TorchModel as the
+    network, so that the adapter's code -- name resolution against the packaged blobs, setLigand / setReceptor reuse, receptor upload,
+    centre option, by-atom gradient scatter + add_minus_forces, set_center_from_model / set_bounding_box, fresh_copy -- runs inside the
+    reference's classes.  Scores, forces (hydrogens among the ligand atoms), boxes and a whole quasi_newton + non_cache_cnn minimisation
+    equal CNNTorchScorer's."""
+    lig = dict(synth.make_flexible_ligand(n_heavy=14, n_tors=3, n_branch=2, seed=8))
+    ty = lig["types"].copy(); ty[3] = 1; ty[8] = 0; lig["types"] = ty
+    rx, rt = synth.make_receptor(400, box=24, seed=5)
+    sf, rm = R.RefScoring(), R.RefModel(lig, rx, rt)
+    x = lig["conf0"].copy(); x[:3] += [0.4, -0.2, 0.3]
+    for names, kw in (([], {}), (["fast"], {}), (["crossdock_default2018"], dict(cnn_center=[0.5, 0.25, -0.5])), (["default2017"], {})):
+        ref = CR.RefCNNScorer(names=names, **kw)
+        mine = CR.RefCNNScorer.adapter(names=names, fresh_copy=fresh_copy, **kw)
+        rm.set(x)
+        for grad in (True, False):
+            a, b = ref.score(rm, grad), mine.score(rm, grad)
+            assert a[:4] == b[:4] and np.array_equal(a[4], b[4]), (names, grad)
+        ca, cb = ref.center_and_box(rm), mine.center_and_box(rm)
+        assert all(np.array_equal(p, q) for p, q in zip(ca, cb))
+    with pytest.raises(RuntimeError, match="Invalid model name"):
+        CR.RefCNNScorer.adapter(names=["nonesuch"])
+    begin, end, nn = [-9.7] * 3, [10.55] * 3, [54] * 3
+    ref, mine = CR.RefCNNScorer(names=["crossdock_default2018"]), CR.RefCNNScorer.adapter(names=["crossdock_default2018"], fresh_copy=fresh_copy)
+    ea, xa = R.minimize_dl(rm, sf, R.LINEAR, begin, end, nn, x, 3, ref.dl(), accurate=True)
+    eb, xb = R.minimize_dl(rm, sf, R.LINEAR, begin, end, nn, x, 3, mine.dl(), accurate=True)
+    assert ea == eb and np.array_equal(xa, xb)
