@@ -87,6 +87,7 @@ class CNNScorer:
         self._h = C.c_void_p()
         self._models = []
         self._n_rec = 0
+        self._parent = _clone_of                       # a clone shares the parent's models: model_info() asks the parent
         if _clone_of is not None:
             capi.check(L.gb_cnn_clone(_clone_of._h, C.byref(self._h)))
             self.model_names = list(_clone_of.model_names)
@@ -135,6 +136,8 @@ class CNNScorer:
         return capi.lib().gb_cnn_get_option(self._h, key.encode())
 
     def model_info(self, i=0):
+        if not self._models and self._parent is not None:
+            return self._parent.model_info(i)
         info = capi.ModelInfo()
         capi.check(capi.lib().gb_model_get_info(self._models[i], C.byref(info)))
         return info
