@@ -26,7 +26,7 @@ def build():
         return False
     from . import gridmaker
     gridmaker.lib()
-    subprocess.check_call(["make", "-s", "-f", "Makefile.ref", "cnn"], cwd=_HERE)
+    subprocess.check_call(["make", "-s", "-f", "Makefile.ref", "-j", "4", "cnn"], cwd=_HERE)
     return os.path.exists(_SO)
 
 
