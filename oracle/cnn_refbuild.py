@@ -49,6 +49,12 @@ def lib():
         L.gcref_scorer_dl.argtypes = [C.c_void_p]; L.gcref_scorer_dl.restype = C.c_void_p
         L.gcref_adapter_create.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_char_p, fp, C.c_int]
         L.gcref_adapter_create.restype = C.c_void_p
+        ip = C.POINTER(C.c_int)
+        L.gadp_vina_create.argtypes = [fp, ip, C.c_int]; L.gadp_vina_create.restype = C.c_void_p
+        L.gadp_vina_destroy.argtypes = [C.c_void_p]
+        L.gadp_cache_b200.argtypes = [C.c_void_p, fp, fp, ip, C.c_float, ip, C.c_int]; L.gadp_cache_b200.restype = C.c_void_p
+        L.gadp_score_docked.argtypes = [C.c_void_p, C.c_void_p, fp, C.c_int, fp, fp, ip, C.c_float, fp, C.c_float, fp]
+        L.gadp_last_error.restype = C.c_char_p
         L.gcref_grid_dim.argtypes = [C.c_void_p]; L.gcref_grid_dim.restype = C.c_float
         L.gcref_grid_res.argtypes = [C.c_void_p]; L.gcref_grid_res.restype = C.c_float
         L.gcref_score.argtypes = [C.c_void_p, C.c_void_p, C.c_int, fp, fp]
@@ -113,3 +119,41 @@ class RefCNNScorer:
         if lib().gcref_center_and_box(self.p, ref_model.p, _f(c), _f(b), _f(e), n):
             raise RuntimeError(lib().gcref_last_error().decode())
         return c, b, e, np.array(list(n))
+
+
+class VinaAdapters:
+    """integration/docking_b200.h's docking-side adapters EXECUTED on the CPU (oracle/ref_adapters_driver.cpp): their C-ABI calls are served
+    by a stand-in that honours include/gnina_b200.h's contract with the oracle's C restatement, so that b200::cache_b200 (an `igrid`) and
+    b200::score_docked_b200 run inside the reference's own classes"""
+
+    def __init__(self, rec_xyz, rec_types):
+        rx, rt = np.ascontiguousarray(rec_xyz, np.float32), np.ascontiguousarray(rec_types, np.int32)
+        self.h = lib().gadp_vina_create(_f(rx), rt.ctypes.data_as(C.POINTER(C.c_int)), len(rt))
+
+    def __del__(self):
+        try:
+            lib().gadp_vina_destroy(self.h)
+        except Exception:
+            pass
+
+    def cache_b200(self, ref_model, begin, end, n, slope, needed):
+        """b200::cache_b200 as a vina_refbuild.RefGrid: model_eval_deriv / bfgs / mc of the reference take it in place of `cache`"""
+        b, e = np.ascontiguousarray(begin, np.float32), np.ascontiguousarray(end, np.float32)
+        nn, nd = np.ascontiguousarray(n, np.int32), np.ascontiguousarray(needed, np.int32)
+        ip = C.POINTER(C.c_int)
+        p = lib().gadp_cache_b200(self.h, _f(b), _f(e), nn.ctypes.data_as(ip), slope, nd.ctypes.data_as(ip), len(nd))
+        if not p:
+            raise RuntimeError(lib().gadp_last_error().decode())
+        g = V.RefGrid(p, ref_model)
+        g.keep = self
+        return g
+
+    def score_docked(self, ref_model, pose_xyz, begin, end, n, slope, cap3, num_tors, e_in):
+        b, e = np.ascontiguousarray(begin, np.float32), np.ascontiguousarray(end, np.float32)
+        nn = np.ascontiguousarray(n, np.int32)
+        xyz = np.ascontiguousarray(pose_xyz, np.float32); out = np.array(e_in, np.float32)
+        cap = np.ascontiguousarray(cap3, np.float32)
+        if lib().gadp_score_docked(self.h, ref_model.p, _f(xyz), len(out), _f(b), _f(e), nn.ctypes.data_as(C.POINTER(C.c_int)), slope,
+                                   _f(cap), num_tors, _f(out)):
+            raise RuntimeError(lib().gadp_last_error().decode())
+        return out

@@ -1,0 +1,126 @@
+// oracle/ref_adapters_driver.cpp -- the docking-side integration adapters (integration/docking_b200.h) EXECUTED on the CPU inside the
+// reference's own classes.  b200::cache_b200 is an `igrid` (lib/igrid.h) over gb_vina_cache_build / gb_vina_cache_eval, and
+// b200::score_docked_b200 forwards the docking branch's final score to gb_vina_score_noncache.  Here those C-ABI names are redirected to
+// a stand-in that honours include/gnina_b200.h's contract with the oracle's C restatement (oracle/vina_ref.c -- what the device kernels
+// are checked against on the GPU), so that the adapter code itself (coordinate / type marshalling, minus_forces hand-back, box and
+// num_tors plumbing) runs inside the reference's model::eval_deriv, quasi_newton and monte_carlo in place of its `cache`.
+// TEST INFRASTRUCTURE (oracle/); linked into oracle/_ref/libgnina_cnn_ref.so (which already links liboracle.so and the Vina build).
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cache.h"
+#include "igrid.h"
+#include "model.h"
+#include "gnina_b200.h"
+
+extern "C" {
+typedef struct gvo_prec gvo_prec;
+gvo_prec* gvo_prec_create(const float* weights6, float factor);
+void gvo_prec_free(gvo_prec* p);
+void gvo_cache_populate(const gvo_prec* p, const float* begin, const float* end, const int32_t* n, int n_rec, const float* rec_xyz,
+                        const int32_t* rec_type, int t2, float* out);
+float gvo_cache_eval(float* const* grids, const float* begin, const float* end, const int32_t* n, int n_lig, const float* lig_xyz,
+                     const int32_t* lig_type, float slope, float v, float* deriv);
+float gvo_noncache_eval(const gvo_prec* p, int n_rec, const float* rec_xyz, const int32_t* rec_type, int n_lig, const float* lig_xyz,
+                        const int32_t* lig_type, float v, float slope, const float* begin, const float* end);
+float gvo_num_tors_div(const gvo_prec* p, float e, float num_tors);
+void* gref_model_ptr(void* p);
+void* gref_grid_wrap(void* ig);
+}
+
+struct gb_vina {
+  gvo_prec* prec = nullptr;
+  std::vector<float> rec; std::vector<int32_t> rec_t;
+  float begin[3], end[3]; int32_t n[3];
+  std::vector<std::vector<float>> grids = std::vector<std::vector<float>>(28);
+};
+static std::string g_mock_err;
+extern "C" {
+const char* mockgbv_last_error(void) { return g_mock_err.c_str(); }
+int mockgb_vina_cache_build(gb_vina* h, const float* begin, const float* end, const int32_t* n, const int32_t* types, int n_types) {
+  for (int i = 0; i < 3; i++) { h->begin[i] = begin[i]; h->end[i] = end[i]; h->n[i] = n[i]; }
+  const size_t pts = (size_t)(n[0] + 1) * (n[1] + 1) * (n[2] + 1);
+  for (auto& g : h->grids) g.clear();
+  for (int k = 0; k < n_types; k++) {
+    if (types[k] < 0 || types[k] >= 28) { g_mock_err = "bad atom type"; return GB_ERR_USAGE; }
+    h->grids[types[k]].resize(pts);
+    gvo_cache_populate(h->prec, begin, end, n, (int)h->rec_t.size(), h->rec.data(), h->rec_t.data(), types[k], h->grids[types[k]].data());
+  }
+  return GB_OK;
+}
+int mockgb_vina_cache_eval(gb_vina* h, const float* xyz, const int32_t* t, const int32_t* offs, int n_poses, float slope, float v,
+                           float* energy, float* deriv) {
+  float* gp[28];
+  for (int i = 0; i < 28; i++) gp[i] = h->grids[i].empty() ? nullptr : h->grids[i].data();
+  for (int p = 0; p < n_poses; p++) {
+    const int a = offs[p], n = offs[p + 1] - offs[p];
+    for (int i = 0; i < n; i++)
+      if (t[a + i] > 1 && t[a + i] < 28 && !gp[t[a + i]]) { g_mock_err = "no grid for a ligand atom type"; return GB_ERR_USAGE; }
+    energy[p] = gvo_cache_eval(gp, h->begin, h->end, h->n, n, xyz + 3 * a, t + a, slope, v, deriv ? deriv + 3 * a : nullptr);
+  }
+  return GB_OK;
+}
+int mockgb_vina_score_noncache(gb_vina* h, const float* xyz, const int32_t* t, const int32_t* offs, int n_poses, const float* num_tors,
+                               float vcap, float slope, const float* bb, const float* be, float* e_inter, float* affinity) {
+  for (int p = 0; p < n_poses; p++) {
+    const int a = offs[p], n = offs[p + 1] - offs[p];
+    const float e = gvo_noncache_eval(h->prec, (int)h->rec_t.size(), h->rec.data(), h->rec_t.data(), n, xyz + 3 * a, t + a, vcap, slope, bb, be);
+    if (e_inter) e_inter[p] = e;
+    if (affinity) affinity[p] = gvo_num_tors_div(h->prec, e, num_tors[p]);
+  }
+  return GB_OK;
+}
+}
+#define gb_last_error mockgbv_last_error
+#define gb_vina_cache_build mockgb_vina_cache_build
+#define gb_vina_cache_eval mockgb_vina_cache_eval
+#define gb_vina_score_noncache mockgb_vina_score_noncache
+#include "docking_b200.h"
+
+static grid_dims dims_of(const float* begin, const float* end, const int* n) {
+  grid_dims gd;
+  for (int i = 0; i < 3; i++) { gd[i].begin = begin[i]; gd[i].end = end[i]; gd[i].n = (sz)n[i]; }
+  return gd;
+}
+
+extern "C" {
+// gb_vina_create + gb_vina_set_receptor of the stand-in: default weights, table factor 32, hydrogens dropped like the library does
+void* gadp_vina_create(const float* rec_xyz, const int* rec_t, int n) {
+  gb_vina* h = new gb_vina;
+  h->prec = gvo_prec_create(nullptr, 32.f);
+  for (int i = 0; i < n; i++) {
+    if (rec_t[i] < 2) continue;
+    h->rec_t.push_back(rec_t[i]);
+    for (int k = 0; k < 3; k++) h->rec.push_back(rec_xyz[3 * i + k]);
+  }
+  return h;
+}
+void gadp_vina_destroy(void* p) { gb_vina* h = (gb_vina*)p; gvo_prec_free(h->prec); delete h; }
+// b200::cache_b200(h, gd, slope, needed) as a grid handle of oracle/ref_driver.cpp (gref_model_eval_deriv, gref_bfgs, gref_mc take it)
+void* gadp_cache_b200(void* h, const float* begin, const float* end, const int* n, float slope, const int* needed, int n_needed) {
+  try {
+    std::vector<smt> nd;
+    for (int i = 0; i < n_needed; i++) nd.push_back((smt)needed[i]);
+    return gref_grid_wrap(static_cast<igrid*>(new b200::cache_b200((gb_vina*)h, dims_of(begin, end, n), slope, nd)));
+  } catch (const std::exception& e) { g_mock_err = e.what(); return nullptr; }
+}
+// b200::score_docked_b200 on n poses given by their coordinates; e [n] in (what refine_structure left: max_fl = never inside) / out
+int gadp_score_docked(void* h, void* model_handle, const float* pose_xyz, int n_poses, const float* begin, const float* end, const int* n,
+                      float slope, const float* cap3, float num_tors, float* e) {
+  try {
+    model& m = *(model*)gref_model_ptr(model_handle);
+    const int na = (int)m.num_movable_atoms();
+    output_container out;
+    std::vector<std::vector<float>> xyz(n_poses);
+    for (int i = 0; i < n_poses; i++) {
+      out.push_back(new output_type(conf(m.get_size(), false), e[i]));
+      xyz[i].assign(pose_xyz + (size_t)i * na * 3, pose_xyz + (size_t)(i + 1) * na * 3);
+    }
+    b200::score_docked_b200((gb_vina*)h, m, out, xyz, vec(cap3[0], cap3[1], cap3[2]), dims_of(begin, end, n), slope, num_tors);
+    for (int i = 0; i < n_poses; i++) e[i] = out[i].e;
+    return 0;
+  } catch (const std::exception& ex) { g_mock_err = ex.what(); return 1; }
+}
+const char* gadp_last_error() { return g_mock_err.c_str(); }
+}

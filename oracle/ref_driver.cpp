@@ -591,6 +591,8 @@ int gref_adapter_topology(void* p, int* counts, float* local_xyz, int* type, int
 
 // ---- grids -----------------------------------------------------------------------------------------------------------------
 // cache: ctor + populate for the movable atom types of the model (lib/cache.cpp:104-184)
+// an igrid made elsewhere (oracle/ref_adapters_driver.cpp: the integration adapter cache_b200) as a grid handle of this driver; takes it over
+void* gref_grid_wrap(void* ig) { RefGrid* G = new RefGrid; G->ig.reset((igrid*)ig); G->kind = 3; return G; }
 void* gref_cache_create(void* sf, int kind, void* mp, const float* begin, const float* end, const int* n, float slope) {
   RefSF* S = (RefSF*)sf; RefModel* R = (RefModel*)mp;
   RefGrid* G = new RefGrid;
