@@ -35,7 +35,8 @@ def _confs(rs, lig, k, spread):
 def test_cache_b200_is_a_drop_in_igrid(libm):
     """b200::cache_b200 : igrid in place of the reference's `cache` (lib/cache.cpp) as the `ig` of model::eval_deriv, of quasi_newton and
     of a whole monte_carlo chain: energies, gradients, conformations and the chain's output container are EQUAL"""
-    lig = synth.make_flexible_ligand(n_heavy=20, n_tors=4, n_branch=2, seed=8)
+    lig = dict(synth.make_flexible_ligand(n_heavy=20, n_tors=4, n_branch=2, seed=8))
+    ty = lig["types"].copy(); ty[3] = 1; ty[11] = 0; lig["types"] = ty           # a polar and a non-polar hydrogen among the movable atoms
     rx, rt = synth.make_receptor(500, box=30, seed=5)
     sf, rm = R.RefScoring(), R.RefModel(lig, rx, rt)
     theirs = R.RefGrid.cache(sf, R.LINEAR, rm, BEGIN, END, N, 1e3)
