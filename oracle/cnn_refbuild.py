@@ -54,6 +54,7 @@ def lib():
         L.gadp_vina_destroy.argtypes = [C.c_void_p]
         L.gadp_cache_b200.argtypes = [C.c_void_p, fp, fp, ip, C.c_float, ip, C.c_int]; L.gadp_cache_b200.restype = C.c_void_p
         L.gadp_score_docked.argtypes = [C.c_void_p, C.c_void_p, fp, C.c_int, fp, fp, ip, C.c_float, fp, C.c_float, fp]
+        L.gadp_refine_structure.argtypes = [C.c_void_p, C.c_void_p, fp, C.c_int, fp, fp, ip, fp, C.c_int, C.c_int, C.c_int, fp]
         L.gadp_last_error.restype = C.c_char_p
         L.gcref_grid_dim.argtypes = [C.c_void_p]; L.gcref_grid_dim.restype = C.c_float
         L.gcref_grid_res.argtypes = [C.c_void_p]; L.gcref_grid_res.restype = C.c_float
@@ -157,3 +158,13 @@ class VinaAdapters:
                                    _f(cap), num_tors, _f(out)):
             raise RuntimeError(lib().gadp_last_error().decode())
         return out
+
+    def refine_structure(self, ref_model, confs, begin, end, n, cap3, maxiters, accurate=False, early_term=False):
+        """b200::refine_structure_b200 on all conformations at once -> (e [k] (max_fl = never inside), confs [k, 7+T])"""
+        b, e_ = np.ascontiguousarray(begin, np.float32), np.ascontiguousarray(end, np.float32)
+        nn, cap = np.ascontiguousarray(n, np.int32), np.ascontiguousarray(cap3, np.float32)
+        x = np.array(confs, np.float32); e = np.zeros(len(x), np.float32)
+        if lib().gadp_refine_structure(self.h, ref_model.p, _f(x), len(x), _f(b), _f(e_), nn.ctypes.data_as(C.POINTER(C.c_int)), _f(cap),
+                                       maxiters, int(accurate), int(early_term), _f(e)):
+            raise RuntimeError(lib().gadp_last_error().decode())
+        return e, x

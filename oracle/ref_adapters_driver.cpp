@@ -25,6 +25,17 @@ float gvo_cache_eval(float* const* grids, const float* begin, const float* end, 
 float gvo_noncache_eval(const gvo_prec* p, int n_rec, const float* rec_xyz, const int32_t* rec_type, int n_lig, const float* lig_xyz,
                         const int32_t* lig_type, float v, float slope, const float* begin, const float* end);
 float gvo_num_tors_div(const gvo_prec* p, float e, float num_tors);
+typedef struct {                     /* oracle/vina_mc_ref.c */
+  int n_atoms, n_seg, n_pairs;
+  const float* local_xyz; const int32_t* type; const int32_t* seg_parent; const int32_t *seg_begin, *seg_end;
+  const float *seg_rel_origin, *seg_rel_axis; const int32_t *pair_a, *pair_b;
+} gvo_lig;
+typedef struct {
+  float* const* grids; const float *begin, *end; const int32_t* n; float slope; const gvo_prec* prec; const void* splines;
+  const float* rec_xyz; const int32_t* rec_type; int n_rec;
+} gvo_field;
+float gvo_refine_structure_ex(const gvo_field* F0, const gvo_lig* L, float* x, float* g, int maxiters, const float* v, int* n_evals,
+                              int* within_out, int accurate, int early_term);
 void* gref_model_ptr(void* p);
 void* gref_grid_wrap(void* ig);
 }
@@ -34,6 +45,7 @@ struct gb_vina {
   std::vector<float> rec; std::vector<int32_t> rec_t;
   float begin[3], end[3]; int32_t n[3];
   std::vector<std::vector<float>> grids = std::vector<std::vector<float>>(28);
+  gvo_lig lig{};
 };
 static std::string g_mock_err;
 extern "C" {
@@ -72,6 +84,31 @@ int mockgb_vina_score_noncache(gb_vina* h, const float* xyz, const int32_t* t, c
   return GB_OK;
 }
 }
+extern "C" {
+int mockgb_vina_set_ligand(gb_vina* h, const gb_ligand_topology* t) {
+  h->lig = gvo_lig{t->n_atoms, t->n_segments, t->n_pairs, t->local_xyz, t->smina_type, t->seg_parent, t->seg_atom_begin, t->seg_atom_end,
+                   t->seg_rel_origin, t->seg_rel_axis, t->pair_a, t->pair_b};
+  return GB_OK;
+}
+// refine_structure on the non_cache field (direct sums over the receptor, search box = [bb, be]); e = the last run's energy, within[i]
+int mockgb_vina_refine_minimize(gb_vina* h, float* confs, int n, const gb_minimization_params* mp, const float* v3, const float* bb,
+                                const float* be, float* e, int32_t* within, int32_t* n_evals) {
+  float* no_grids[28] = {};
+  const int32_t nn[3] = {1, 1, 1};
+  const int nx = 7 + h->lig.n_seg - 1;
+  std::vector<float> g(6 + h->lig.n_seg - 1);
+  for (int i = 0; i < n; i++) {
+    gvo_field F{no_grids, bb, be, nn, 10.f, h->prec, nullptr, h->rec.data(), h->rec_t.data(), (int)h->rec_t.size()};
+    int ne = 0, ok = 0;
+    e[i] = gvo_refine_structure_ex(&F, &h->lig, confs + (size_t)i * nx, g.data(), mp->maxiters, v3, &ne, &ok, mp->accurate_line_search, mp->early_term);
+    if (within) within[i] = ok;
+    if (n_evals) n_evals[i] = ne;
+  }
+  return GB_OK;
+}
+}
+#define gb_vina_set_ligand mockgb_vina_set_ligand
+#define gb_vina_refine_minimize mockgb_vina_refine_minimize
 #define gb_last_error mockgbv_last_error
 #define gb_vina_cache_build mockgb_vina_cache_build
 #define gb_vina_cache_eval mockgb_vina_cache_eval
@@ -119,6 +156,30 @@ int gadp_score_docked(void* h, void* model_handle, const float* pose_xyz, int n_
     }
     b200::score_docked_b200((gb_vina*)h, m, out, xyz, vec(cap3[0], cap3[1], cap3[2]), dims_of(begin, end, n), slope, num_tors);
     for (int i = 0; i < n_poses; i++) e[i] = out[i].e;
+    return 0;
+  } catch (const std::exception& ex) { g_mock_err = ex.what(); return 1; }
+}
+// b200::refine_structure_b200 on n conformations of the model's ligand (topology through b200::B200Ligand, as parallel_mc_b200 sets it):
+// confs [n][7+T] in/out, e [n] out (max_fl = never inside the box)
+int gadp_refine_structure(void* h, void* model_handle, float* confs, int n_confs, const float* begin, const float* end, const int* n,
+                          const float* cap3, int maxiters, int accurate, int early_term, float* e) {
+  try {
+    model& m = *(model*)gref_model_ptr(model_handle);
+    b200::B200Ligand L(m);
+    b200::check(gb_vina_set_ligand((gb_vina*)h, &L.topo));
+    const int nx = 7 + L.topo.n_segments - 1;
+    output_container out;
+    for (int i = 0; i < n_confs; i++) {
+      conf c(m.get_size(), false);
+      b200::unpack_conf(confs + (size_t)i * nx, c);
+      out.push_back(new output_type(c, 0));
+    }
+    minimization_params mp;
+    mp.maxiters = (unsigned)maxiters;
+    mp.type = accurate ? minimization_params::BFGSAccurateLineSearch : minimization_params::BFGSFastLineSearch;
+    mp.early_term = early_term != 0;
+    b200::refine_structure_b200((gb_vina*)h, out, vec(cap3[0], cap3[1], cap3[2]), mp, dims_of(begin, end, n));
+    for (int i = 0; i < n_confs; i++) { b200::pack_conf(out[i].c, confs + (size_t)i * nx); e[i] = out[i].e; }
     return 0;
   } catch (const std::exception& ex) { g_mock_err = ex.what(); return 1; }
 }

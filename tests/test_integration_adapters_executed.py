@@ -69,3 +69,35 @@ def test_score_docked_b200_is_the_docking_branch_affinity(libm):
         rm.set(x)
         want = MAX_FL if e_in[i] == MAX_FL else sf.num_tors_div(nc.eval(1000.0), 3.5)
         assert out[i] == np.float32(want), i
+
+
+@pytest.mark.parametrize("accurate", [False, True])
+def test_refine_structure_b200_is_refine_structure(libm, accurate):
+    """b200::refine_structure_b200 for ALL kept poses in one call (topology through b200::B200Ligand) vs refine_structure
+    (main/main.cpp:131-171) replayed pose by pose with the reference's own quasi_newton / non_cache / within: slope 10, 100, ... until the
+    pose is inside the box; conformations and energies are EQUAL, a pose that never gets inside ends with max_fl"""
+    lig = synth.make_flexible_ligand(n_heavy=22, n_tors=4, n_branch=3, seed=41)
+    rx, rt = synth.make_receptor(500, box=30, seed=41)
+    sf, rm = R.RefScoring(), R.RefModel(lig, rx, rt)
+    box_b, box_e, box_n = [-5.3] * 3, [5.2] * 3, [28, 28, 28]
+    X = _confs(np.random.RandomState(41), lig, 8, 7.0)
+    maxit = (25 + len(lig["types"])) // 3
+    nc = R.RefGrid.non_cache(sf, R.LINEAR, rm, box_b, box_e, box_n, 1e3)
+    want_e, want_x, escalated = [], [], 0
+    for x in X:
+        xr, slope, er, ok = x.copy(), 10.0, 0.0, False
+        for p in range(5):
+            nc.set_slope(slope)
+            er, xr, _ = R.bfgs(rm, sf, R.LINEAR, nc, xr, maxit, accurate=accurate)
+            rm.set(xr)
+            ok = nc.within()
+            if ok:
+                break
+            slope *= 10
+            escalated += 1
+        want_e.append(er if ok else MAX_FL); want_x.append(xr)
+    rm.set(X[0])
+    e, x = CR.VinaAdapters(rx, rt).refine_structure(rm, X, box_b, box_e, box_n, (1000, 1000, 1000), maxit, accurate=accurate)
+    assert escalated >= 1
+    for i in range(len(X)):
+        assert e[i] == np.float32(want_e[i]) and np.array_equal(x[i], want_x[i]), i
