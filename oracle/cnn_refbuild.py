@@ -55,6 +55,8 @@ def lib():
         L.gadp_cache_b200.argtypes = [C.c_void_p, fp, fp, ip, C.c_float, ip, C.c_int]; L.gadp_cache_b200.restype = C.c_void_p
         L.gadp_score_docked.argtypes = [C.c_void_p, C.c_void_p, fp, C.c_int, fp, fp, ip, C.c_float, fp, C.c_float, fp]
         L.gadp_refine_structure.argtypes = [C.c_void_p, C.c_void_p, fp, C.c_int, fp, fp, ip, fp, C.c_int, C.c_int, C.c_int, fp]
+        L.gadp_parallel_mc.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, fp, fp, C.c_int,
+                                       C.c_int, fp, fp, ip]
         L.gadp_last_error.restype = C.c_char_p
         L.gcref_grid_dim.argtypes = [C.c_void_p]; L.gcref_grid_dim.restype = C.c_float
         L.gcref_grid_res.argtypes = [C.c_void_p]; L.gcref_grid_res.restype = C.c_float
@@ -168,3 +170,16 @@ class VinaAdapters:
                                        maxiters, int(accurate), int(early_term), _f(e)):
             raise RuntimeError(lib().gadp_last_error().decode())
         return e, x
+
+    def parallel_mc(self, ref_model, seed, c1, c2, num_tasks, num_steps, maxiters, state_conf, num_saved_mins=50, min_rmsd=1.0,
+                    hunt_cap=(10, 10, 10)):
+        """b200::parallel_mc_b200::operator() (needs cache_b200 built on this handle; the model must hold state_conf)
+        -> (e [k], confs [k, 7+T]) of the merged container"""
+        a, b = np.ascontiguousarray(c1, np.float32), np.ascontiguousarray(c2, np.float32)
+        hc, st = np.ascontiguousarray(hunt_cap, np.float32), np.ascontiguousarray(state_conf, np.float32)
+        cap = num_saved_mins
+        e = np.zeros(cap, np.float32); x = np.zeros((cap, len(st)), np.float32); n = (C.c_int * 1)()
+        if lib().gadp_parallel_mc(self.h, ref_model.p, seed, _f(a), _f(b), num_tasks, num_steps, maxiters, num_saved_mins, min_rmsd, _f(hc),
+                                  _f(st), len(st), cap, _f(e), _f(x), n):
+            raise RuntimeError(lib().gadp_last_error().decode())
+        return e[:n[0]].copy(), x[:n[0]].copy()

@@ -34,6 +34,13 @@ typedef struct {
   float* const* grids; const float *begin, *end; const int32_t* n; float slope; const gvo_prec* prec; const void* splines;
   const float* rec_xyz; const int32_t* rec_type; int n_rec;
 } gvo_field;
+typedef struct { int num_steps, maxiters, num_saved_mins; float temperature, mutation_amplitude, min_rmsd; float hunt_cap[3]; float gyration_radius; } gvo_mc_params;
+int gvo_mc_run_ex(const gvo_field* F, const gvo_lig* L, const gvo_mc_params* P, const float* corner1, const float* corner2, uint32_t seed,
+                  float* out_e, float* out_conf, float* trace, const float* init_conf, const float* state_conf);
+void gvo_lig_set_conf(const gvo_lig* L, const float* x, float* coords, float* seg_origin, float* seg_axis);
+int gref_random_conf(void* mp, unsigned seed, const float* c1, const float* c2, float* x, unsigned* state_after);
+int gb_vina_merge_outputs(const float* e, const float* coords, const int32_t* n_out, int n_chains, int S, int n_atoms, float min_rmsd,
+                          int max_size, int32_t* kept, int32_t* n_kept);   /* the library's own host-side merge (libgnina_b200.so) */
 float gvo_refine_structure_ex(const gvo_field* F0, const gvo_lig* L, float* x, float* g, int maxiters, const float* v, int* n_evals,
                               int* within_out, int accurate, int early_term);
 void* gref_model_ptr(void* p);
@@ -46,6 +53,9 @@ struct gb_vina {
   float begin[3], end[3]; int32_t n[3];
   std::vector<std::vector<float>> grids = std::vector<std::vector<float>>(28);
   gvo_lig lig{};
+  float gyration_radius = 0;
+  void* model_handle = nullptr;      // for the reference-style start conformations of the chains (see mockgb_vina_mc)
+  std::vector<float> state_conf;     // the conformation the model holds when the search starts (model-state semantics of the chains)
 };
 static std::string g_mock_err;
 extern "C" {
@@ -88,6 +98,7 @@ extern "C" {
 int mockgb_vina_set_ligand(gb_vina* h, const gb_ligand_topology* t) {
   h->lig = gvo_lig{t->n_atoms, t->n_segments, t->n_pairs, t->local_xyz, t->smina_type, t->seg_parent, t->seg_atom_begin, t->seg_atom_end,
                    t->seg_rel_origin, t->seg_rel_axis, t->pair_a, t->pair_b};
+  h->gyration_radius = t->gyration_radius;
   return GB_OK;
 }
 // refine_structure on the non_cache field (direct sums over the receptor, search box = [bb, be]); e = the last run's energy, within[i]
@@ -107,6 +118,38 @@ int mockgb_vina_refine_minimize(gb_vina* h, float* confs, int n, const gb_minimi
   return GB_OK;
 }
 }
+extern "C" {
+// every chain = the restatement's monte_carlo chain on the cache grids.  The library draws a chain's start conformation itself (unit-ball
+// orientation); HERE the start is drawn the reference's way (conf::randomize on the chain's generator, lib/conf.h) so that what the
+// adapter builds can be compared with parallel_mc::operator() pose by pose -- the adapter's plumbing is what this stand-in is for.
+int mockgb_vina_mc(gb_vina* h, const gb_mc_params* P, const float* c1, const float* c2, const uint32_t* seeds, int n_chains, float slope,
+                   float* e, float* confs, int32_t* n_out) {
+  float* gp[28];
+  for (int i = 0; i < 28; i++) gp[i] = h->grids[i].empty() ? nullptr : h->grids[i].data();
+  gvo_field F{gp, h->begin, h->end, h->n, slope, h->prec, nullptr, nullptr, nullptr, 0};
+  gvo_mc_params Q{P->num_steps, P->maxiters, P->num_saved_mins, P->temperature, P->mutation_amplitude, P->min_rmsd,
+                  {P->hunt_cap[0], P->hunt_cap[1], P->hunt_cap[2]}, h->gyration_radius};
+  const int S = P->num_saved_mins, nx = 7 + h->lig.n_seg - 1;
+  std::vector<float> x0(nx);
+  for (int c = 0; c < n_chains; c++) {
+    unsigned state = 0;
+    if (gref_random_conf(h->model_handle, seeds[c], c1, c2, x0.data(), &state)) { g_mock_err = "random_conf failed"; return GB_ERR_INTERNAL; }
+    n_out[c] = gvo_mc_run_ex(&F, &h->lig, &Q, c1, c2, state, e + (size_t)c * S, confs + (size_t)c * S * nx, nullptr, x0.data(),
+                             h->state_conf.empty() ? nullptr : h->state_conf.data());
+  }
+  return GB_OK;
+}
+// only the coordinates are asked for by parallel_mc_b200 (model::set of every minimum)
+int mockgb_vina_eval_deriv(gb_vina* h, const float* confs, int n, const float*, float, float* e, float* change, float* coords) {
+  if (change) { g_mock_err = "the stand-in returns coordinates only"; return GB_ERR_USAGE; }
+  const int nx = 7 + h->lig.n_seg - 1, na = h->lig.n_atoms;
+  std::vector<float> so(3 * (size_t)h->lig.n_seg), sa(3 * (size_t)h->lig.n_seg);
+  for (int i = 0; i < n; i++) { gvo_lig_set_conf(&h->lig, confs + (size_t)i * nx, coords + (size_t)i * na * 3, so.data(), sa.data()); if (e) e[i] = 0; }
+  return GB_OK;
+}
+}
+#define gb_vina_mc mockgb_vina_mc
+#define gb_vina_eval_deriv mockgb_vina_eval_deriv
 #define gb_vina_set_ligand mockgb_vina_set_ligand
 #define gb_vina_refine_minimize mockgb_vina_refine_minimize
 #define gb_last_error mockgbv_last_error
@@ -180,6 +223,30 @@ int gadp_refine_structure(void* h, void* model_handle, float* confs, int n_confs
     mp.early_term = early_term != 0;
     b200::refine_structure_b200((gb_vina*)h, out, vec(cap3[0], cap3[1], cap3[2]), mp, dims_of(begin, end, n));
     for (int i = 0; i < n_confs; i++) { b200::pack_conf(out[i].c, confs + (size_t)i * nx); e[i] = out[i].e; }
+    return 0;
+  } catch (const std::exception& ex) { g_mock_err = ex.what(); return 1; }
+}
+// b200::parallel_mc_b200::operator() with the reference's generator type seeded like parallel_mc's caller; the model holds state_conf.
+// -> the merged container (sorted by energy as parallel_mc::operator() leaves it): e, confs [n][7+T]
+int gadp_parallel_mc(void* hv, void* model_handle, unsigned seed, const float* c1, const float* c2, int num_tasks, int num_steps, int maxiters,
+                     int num_saved_mins, float min_rmsd, const float* hunt_cap, const float* state_conf, int nx_state, int max_out, float* out_e,
+                     float* out_conf, int* n_out) {
+  try {
+    gb_vina* h = (gb_vina*)hv;
+    h->model_handle = model_handle;
+    h->state_conf.assign(state_conf, state_conf + nx_state);
+    model& m = *(model*)gref_model_ptr(model_handle);
+    b200::parallel_mc_b200 par;
+    par.h = h; par.num_tasks = (sz)num_tasks;
+    par.mc.num_steps = (unsigned)num_steps; par.mc.ssd_par.minparm.maxiters = (unsigned)maxiters; par.mc.num_saved_mins = (sz)num_saved_mins;
+    par.mc.min_rmsd = min_rmsd; par.mc.hunt_cap = vec(hunt_cap[0], hunt_cap[1], hunt_cap[2]);
+    rng gen(seed);
+    output_container out;
+    par(m, out, vec(c1[0], c1[1], c1[2]), vec(c2[0], c2[1], c2[2]), gen);
+    out.sort();                                                   // parallel_mc.cpp:213
+    const int nx = b200::conf_floats(out.empty() ? m.get_initial_conf(false) : out[0].c);
+    *n_out = (int)std::min<sz>(out.size(), (sz)max_out);
+    for (int i = 0; i < *n_out; i++) { out_e[i] = out[i].e; b200::pack_conf(out[i].c, out_conf + (size_t)i * nx); }
     return 0;
   } catch (const std::exception& ex) { g_mock_err = ex.what(); return 1; }
 }

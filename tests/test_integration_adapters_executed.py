@@ -101,3 +101,26 @@ def test_refine_structure_b200_is_refine_structure(libm, accurate):
     assert escalated >= 1
     for i in range(len(X)):
         assert e[i] == np.float32(want_e[i]) and np.array_equal(x[i], want_x[i]), i
+
+
+def test_parallel_mc_b200_is_parallel_mc(libm):
+    """b200::parallel_mc_b200::operator() vs the REFERENCE's parallel_mc::operator() (lib/parallel_mc.cpp:183-214, own thread pool): task
+    seeds from the caller's generator, Monte-Carlo parameters, every chain, conformation -> heavy-atom coordinates, the merge through the
+    library's own host-side gb_vina_merge_outputs, the output container.  The stand-in runs the restatement's chain and draws each chain's
+    START the reference's way (the device library draws its own starts, which is why the two are compared as search results on the GPU):
+    with that, the merged containers are EQUAL -- energies and conformations."""
+    lig = synth.make_flexible_ligand()
+    rx, rt = synth.make_receptor(500, box=30, seed=5)
+    sf, rm = R.RefScoring(), R.RefModel(lig, rx, rt)
+    theirs = R.RefGrid.cache(sf, R.LINEAR, rm, BEGIN, END, N, 1e3)
+    adapters = CR.VinaAdapters(rx, rt)
+    mine = adapters.cache_b200(rm, BEGIN, END, N, 1e3, sorted(set(int(t) for t in lig["types"] if t > 1)))
+    c1, c2 = [-5] * 3, [5] * 3
+    maxit, S = (25 + len(lig["types"])) // 3, 20
+    for seed, tasks, steps in ((4242, 4, 40), (777, 6, 60)):
+        er, xr = R.parallel_mc(rm, sf, R.LINEAR, theirs, seed, c1, c2, tasks, steps, maxit, lig["conf0"], (BEGIN, END, N), num_threads=3,
+                               num_saved_mins=S)
+        rm.set(lig["conf0"])
+        e, x = adapters.parallel_mc(rm, seed, c1, c2, tasks, steps, maxit, lig["conf0"], num_saved_mins=S)
+        assert len(e) == len(er) > 0 and np.array_equal(e, er) and np.array_equal(x, xr)
+    del mine
