@@ -168,3 +168,38 @@ def test_the_integration_adapter_is_a_drop_in_for_cnn_torch_scorer(fresh_copy):
     ea, xa = R.minimize_dl(rm, sf, R.LINEAR, begin, end, nn, x, 3, ref.dl(), accurate=True)
     eb, xb = R.minimize_dl(rm, sf, R.LINEAR, begin, end, nn, x, 3, mine.dl(), accurate=True)
     assert ea == eb and np.array_equal(xa, xb)
+
+
+def test_cnn_refinement_with_real_networks():
+    """--cnn_scoring refinement: refine_structure (main/main.cpp:131-171) on ig = non_cache_cnn over the reference's CNNTorchScorer (real
+    crossdock_default2018 file; fast line search, ssd_par's iteration count), pose by pose, vs minimize.refine_structure_poses +
+    cnn_energy over the restated network for all poses at once: energies, conformations and the `within` flag are EQUAL"""
+    from gnina_b200 import minimize as M
+    begin, end, nn = [-6.1] * 3, [6.3] * 3, [34] * 3
+    lig = dict(synth.make_flexible_ligand(n_heavy=14, n_tors=3, n_branch=2, seed=8))
+    ty = lig["types"].copy(); ty[3] = 1; lig["types"] = ty
+    rx, rt = synth.make_receptor(400, box=24, seed=5)
+    sf, rm = R.RefScoring(), R.RefModel(lig, rx, rt)
+    lig2 = dict(lig); lig2["local_xyz"], lig2["seg_rel_origin"], lig2["seg_rel_axis"] = rm.export()
+    tree = M.TorsionTree(lig2)
+    heavy = np.asarray(lig["types"]) >= 2
+    rs = np.random.RandomState(5)
+    X = np.tile(lig["conf0"], (3, 1)).astype(np.float32)
+    X[:, :3] += rs.uniform(-3, 3, (3, 3)); X[:, 7:] = rs.uniform(-1, 1, (3, X.shape[1] - 7))
+    X = X.astype(np.float32)
+    maxit = (25 + len(lig["types"])) // 3
+    s = CR.RefCNNScorer(names=["crossdock_default2018"])
+    ref = [R.refine_dl(rm, sf, R.LINEAR, begin, end, nn, x, maxit, s.dl()) for x in X]
+    M.set_transcendentals(*_host_libm())
+    try:
+        net = _OracleNetwork(["crossdock_default2018"], rx, rt)
+        centers = M.heavy_centers(tree.set_conf(X)[0], heavy)
+        half = np.float32(23.5) / np.float32(2)
+        within = M.within_boxes(heavy, [(centers - half, centers + half), (np.float32(begin), np.float32(end))])
+        e, x, inside, ev = M.refine_structure_poses(
+            tree, lambda slope: M.cnn_energy(net, lig["types"], (np.float32(begin), np.float32(end)), slope=slope, cnn_center=centers),
+            within, X, maxit)
+        for i in range(len(X)):
+            assert float(e[i]) == ref[i][0] and np.array_equal(x[i], ref[i][1]) and bool(inside[i]) == ref[i][2], i
+    finally:
+        M.set_transcendentals()
