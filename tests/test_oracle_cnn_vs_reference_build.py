@@ -203,3 +203,19 @@ def test_cnn_refinement_with_real_networks():
             assert float(e[i]) == ref[i][0] and np.array_equal(x[i], ref[i][1]) and bool(inside[i]) == ref[i][2], i
     finally:
         M.set_transcendentals()
+
+
+@pytest.mark.parametrize("name", ["crossdock_default2018", "default2017", "dense"])
+def test_receptor_of_every_smina_type(name):
+    """setReceptor (lib/dl_scorer.cpp:93-193) hands EVERY fixed atom to the typer -- hydrogens, metals, the generic types of the
+    gninacheck generator (test/gnina/test_utils.cpp:13-44), overlapping atoms; the model file's recmap decides which of them get a
+    channel.  Outputs and forces equal the restatement's."""
+    rs = np.random.RandomState(77)
+    rx, rt = synth.make_gninacheck_mol(rs, 0, 300, 400, 11, 11, 11)
+    assert len(set(rt.tolist())) >= 26
+    lig = synth.make_flexible_ligand(n_heavy=16, n_tors=3, n_branch=2, seed=13)
+    rm = R.RefModel(lig, rx, rt)
+    xyz = rm.set(lig["conf0"])
+    r = CR.RefCNNScorer(names=[name]).score(rm, True)
+    o, g = _oracle([name], rx, rt, xyz, lig["types"])
+    assert r[:4] == o and np.array_equal(r[4], g)
