@@ -219,3 +219,28 @@ def test_receptor_of_every_smina_type(name):
     r = CR.RefCNNScorer(names=[name]).score(rm, True)
     o, g = _oracle([name], rx, rt, xyz, lig["types"])
     assert r[:4] == o and np.array_equal(r[4], g)
+
+
+def test_every_packaged_model_equals_its_torchscript_source():
+    """all built-in models (gnina_b200/weights/*.gbw, converted by tools/extract_models.py) against the TorchScript files the reference
+    embeds, each run by the reference's own TorchModel: metadata (grid dimension / resolution, both type maps, head flags) and weights
+    of every blob reproduce the source's score, affinity and loss on a pose"""
+    lig, rx, rt, rm, xyz = _case(31)
+    names = scorer.builtin_models()
+    assert len(names) >= 64
+    worst = 0.0
+    for name in names:
+        s = CR.RefCNNScorer(names=[name])
+        r = s.score(rm, False)
+        blob = model_blob.load_model(name)
+        assert s.grid() == (np.float32(blob.dimension), np.float32(blob.resolution))
+        o, _ = _oracle_score_only(blob, rx, rt, xyz, lig["types"])
+        assert np.allclose(r[:3], o, rtol=1e-6, atol=1e-7), (name, r[:3], o)
+        worst = max(worst, float(np.abs(np.float32(r[:3]) - np.float32(o)).max()))
+    assert worst <= 1e-5
+
+
+def _oracle_score_only(blob, rx, rt, xyz, types):
+    om = pipeline.OracleModel(blob)
+    p, a, l = om.score(rx, rt, xyz, types, np.array([0, len(types)], np.int32))
+    return (float(p[0]), float(a[0]), float(l[0])), None
