@@ -358,7 +358,9 @@ class NonCacheCNNT {
     float e = 0, aff = 0, loss = 0, var = 0;
     std::vector<float> grad;
     scorer_.score(lig_xyz, lig_type, n, minus_forces != nullptr, aff, loss, var, minus_forces ? &grad : nullptr);
-    e += loss;
+    // eval_deriv starts from the loss and adds the penalties atom by atom (:100-111); eval sums the penalties first and adds the loss
+    // last (:36-52) -- the same float association here
+    if (minus_forces) e += loss;
     std::vector<float> emp_e, emp_d;
     const bool mixing = minus_forces && mix_force_;
     if (mixing) {
@@ -385,6 +387,7 @@ class NonCacheCNNT {
         if (mixing && mix_energy_) e += emp_weight_ * emp_e[i];
       }
     }
+    if (!minus_forces) e += loss;
     if (minus_forces && mix_energy_) e /= (1.0f + emp_weight_);
     return e;
   }

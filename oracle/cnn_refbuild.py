@@ -58,6 +58,8 @@ def lib():
         L.gadp_parallel_mc.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, fp, fp, C.c_int,
                                        C.c_int, fp, fp, ip]
         L.gadp_last_error.restype = C.c_char_p
+        L.gcref_product_noncache_cnn.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_void_p, fp, fp, ip, C.c_float, fp, C.c_float,
+                                                 C.c_int, C.c_int, fp, fp]
         L.gcref_grid_dim.argtypes = [C.c_void_p]; L.gcref_grid_dim.restype = C.c_float
         L.gcref_grid_res.argtypes = [C.c_void_p]; L.gcref_grid_res.restype = C.c_float
         L.gcref_score.argtypes = [C.c_void_p, C.c_void_p, C.c_int, fp, fp]
@@ -122,6 +124,21 @@ class RefCNNScorer:
         if lib().gcref_center_and_box(self.p, ref_model.p, _f(c), _f(b), _f(e), n):
             raise RuntimeError(lib().gcref_last_error().decode())
         return c, b, e, np.array(list(n))
+
+
+def product_noncache_cnn(names, ref_model, begin, end, n, center, slope=10.0, v=1000.0, deriv=True, reference_force_routing=True):
+    """the product's own C++ host classes -- gb::CNNScorer + gb::NonCacheCNN of include/gnina_b200.hpp -- run on the CPU over the stand-in
+    C ABI (network = the reference's TorchModel) on the pose `ref_model` holds -> (e, forces [n_movable, 3] or None)"""
+    L = lib()
+    na = (C.c_char_p * max(1, len(names)))(*[x.encode() for x in names])
+    b, e_, c = (np.ascontiguousarray(a, np.float32) for a in (begin, end, center))
+    nn = np.ascontiguousarray(n, np.int32)
+    e = np.empty(1, np.float32); f = np.zeros((ref_model.na, 3), np.float32)
+    wd = os.path.join(os.path.dirname(_HERE), "gnina_b200", "weights")
+    if L.gcref_product_noncache_cnn(na, len(names), wd.encode(), ref_model.p, _f(b), _f(e_), nn.ctypes.data_as(C.POINTER(C.c_int)), slope,
+                                    _f(c), v, int(deriv), int(reference_force_routing), _f(e), _f(f)):
+        raise RuntimeError(L.gcref_last_error().decode())
+    return float(e[0]), (f if deriv else None)
 
 
 class VinaAdapters:

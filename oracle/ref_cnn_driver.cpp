@@ -213,6 +213,8 @@ int mockgb_cnn_score_grad(gb_cnn* h, const float* xyz, const int32_t* t, const i
   catch (const std::exception& e) { g_mock_err = e.what(); return GB_ERR_INTERNAL; }
 }
 }
+extern "C" int mockgb_initialize_cuda(int) { return 0; }
+#define gb_initialize_cuda mockgb_initialize_cuda
 #define gb_last_error mockgb_last_error
 #define gb_model_load mockgb_model_load
 #define gb_model_release mockgb_model_release
@@ -262,4 +264,31 @@ void* gcref_adapter_create(const char** names, int n_names, const char** files, 
   if (rc) { delete R; return nullptr; }
   return R;
 }
+}
+
+// ---- the product's own C++ host classes on the CPU: gb::CNNScorer + gb::NonCacheCNN (include/gnina_b200.hpp) over the same stand-in --
+// non_cache_cnn's counterpart evaluated on the pose the model holds, CNN box centred on `center` (what adjust_center gave the
+// reference side): -> e, forces [n_movable][3]
+extern "C" int gcref_product_noncache_cnn(const char** names, int n_names, const char* weights_dir, void* model_handle, const float* begin,
+                                          const float* end, const int* n, float slope, const float* center, float v, int with_deriv,
+                                          int reference_force_routing, float* e, float* forces) {
+  return guarded([&] {
+    model& m = *(model*)gref_model_ptr(model_handle);
+    std::vector<std::string> nm;
+    for (int i = 0; i < n_names; i++) nm.push_back(names[i]);
+    gb::CNNScorer scorer(weights_dir, nm, 0);
+    std::vector<float> rx; std::vector<int32_t> rt;
+    for (const atom& a : m.get_fixed_atoms()) { rt.push_back((int32_t)a.sm); for (int k = 0; k < 3; k++) rx.push_back((float)a.coords[k]); }
+    scorer.set_receptor(rx.data(), rt.data(), (int)rt.size());
+    gb::GridDims gd;
+    for (int i = 0; i < 3; i++) { gd[i].begin = begin[i]; gd[i].end = end[i]; gd[i].n = n[i]; }
+    gb::NonCacheCNN nc(scorer, gd, center, slope);
+    nc.set_reference_force_routing(reference_force_routing != 0);
+    const int na = (int)m.num_movable_atoms();
+    std::vector<float> xyz(3 * (size_t)na), f;
+    std::vector<int32_t> t(na);
+    for (int i = 0; i < na; i++) { t[i] = (int32_t)m.atoms[i].sm; for (int k = 0; k < 3; k++) xyz[3 * i + k] = (float)m.coords[i][k]; }
+    *e = nc.eval(xyz.data(), t.data(), na, with_deriv ? &f : nullptr, v);
+    if (with_deriv) std::copy(f.begin(), f.end(), forces);
+  });
 }

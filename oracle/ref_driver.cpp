@@ -274,6 +274,26 @@ int gref_noncache_cnn_compare(void* mp, void* sf, int kind, const float* begin, 
   });
 }
 
+// non_cache_cnn::eval / eval_deriv (lib/non_cache_cnn.cpp:33-54, 79-169) around ANY DLScorer on the pose the model holds, after
+// adjust_center: -> e, minus_forces [n_movable][3], the CNN box centre
+int gref_noncache_dl_eval(void* mp, void* sf, int kind, const float* begin, const float* end, const int* n, float slope, void* dl, float v,
+                          int with_deriv, float* e, float* forces, float* center) {
+  RefModel* R = (RefModel*)mp; RefSF* S = (RefSF*)sf;
+  return guarded([&] {
+    model& m = R->m;
+    DLScorer& d = *(DLScorer*)dl;
+    non_cache_cnn nc(*R->gcache, make_dims(begin, end, n), S->prec[kind].get(), slope, d);
+    nc.adjust_center(m);
+    grid user_grid;
+    if (with_deriv) {
+      *e = nc.eval_deriv(m, v, user_grid);
+      for (sz i = 0; i < m.minus_forces.size(); i++) for (int j = 0; j < 3; j++) forces[3 * i + j] = m.minus_forces[i][j];
+    } else *e = nc.eval(m, v);
+    const vec c = d.get_center();
+    for (int j = 0; j < 3; j++) center[j] = c[j];
+  });
+}
+
 // quasi_newton::operator() with ig = non_cache_cnn around the analytic test double: what --minimize --cnn_scoring all runs per pose
 // (main/main.cpp:264-268 -> refine_structure -> quasi_newton; here ONE quasi-Newton run, no slope escalation); x is updated
 static void minimize_over(RefModel* R, RefSF* S, int kind, const float* begin, const float* end, const int* n, float slope, DLScorer& dl,

@@ -43,6 +43,7 @@ def lib():
                                       _fp, _ip]
         L.gref_minimize_dl.argtypes = [_vp, _vp, C.c_int, _fp, _fp, _ip, C.c_float, _vp, _fp, C.c_int, C.c_int, C.c_int, _fp]
         L.gref_refine_dl.argtypes = [_vp, _vp, C.c_int, _fp, _fp, _ip, _vp, _fp, C.c_int, C.c_int, C.c_int, _fp, _ip]
+        L.gref_noncache_dl_eval.argtypes = [_vp, _vp, C.c_int, _fp, _fp, _ip, C.c_float, _vp, C.c_float, C.c_int, _fp, _fp, _fp]
         L.gref_lockstep_minimize.argtypes = [_vp, _fp, _fp, _ip, C.c_float, C.c_float, C.c_float, C.c_float, _fp, _fp, C.c_int, C.c_int, C.c_int,
                                              C.c_int, _fp, _ip, _ip, _ip]
         L.gref_sf_create.argtypes = [C.c_float, C.c_float]; L.gref_sf_create.restype = _vp
@@ -284,6 +285,15 @@ def minimize_dl(model, sf, kind, begin, end, n, conf, maxiters, dl, slope=10.0, 
     x = np.array(conf, np.float32); e = np.empty(1, np.float32)
     _ok(lib().gref_minimize_dl(model.p, sf.p, kind, _f(b), _f(e_), _i(nn), slope, dl, _f(x), maxiters, int(accurate), int(early_term), _f(e)))
     return float(e[0]), x
+
+
+def noncache_dl_eval(model, sf, kind, begin, end, n, dl, slope=10.0, v=1000.0, deriv=True):
+    """non_cache_cnn::eval / eval_deriv around ANY DLScorer* on the pose the model holds (after adjust_center)
+    -> (e, minus_forces [n_movable, 3] or None, CNN box centre [3])"""
+    b, e_, nn = (np.ascontiguousarray(a, dt) for a, dt in ((begin, np.float32), (end, np.float32), (n, np.int32)))
+    e = np.empty(1, np.float32); f = np.zeros((model.na, 3), np.float32); c = np.zeros(3, np.float32)
+    _ok(lib().gref_noncache_dl_eval(model.p, sf.p, kind, _f(b), _f(e_), _i(nn), slope, dl, v, int(deriv), _f(e), _f(f), _f(c)))
+    return float(e[0]), (f if deriv else None), c
 
 
 def refine_dl(model, sf, kind, begin, end, n, conf, maxiters, dl, accurate=False, early_term=False):

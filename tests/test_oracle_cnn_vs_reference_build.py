@@ -244,3 +244,30 @@ def _oracle_score_only(blob, rx, rt, xyz, types):
     om = pipeline.OracleModel(blob)
     p, a, l = om.score(rx, rt, xyz, types, np.array([0, len(types)], np.int32))
     return (float(p[0]), float(a[0]), float(l[0])), None
+
+
+def test_product_cpp_classes_are_non_cache_cnn():
+    """S3 with the real network: the product's own C++ host classes -- gb::CNNScorer + gb::NonCacheCNN (include/gnina_b200.hpp), their
+    C-ABI calls served by the stand-in over the reference's TorchModel -- against the reference's non_cache_cnn::eval / eval_deriv over
+    its CNNTorchScorer, on poses inside and partly outside a tight search box, hydrogens among the ligand atoms: energy (loss + both
+    out-of-box penalties) and the forces the minimiser sees are EQUAL; with the routing switched off the forces are the by-atom ones"""
+    begin, end, nn = [-3.1] * 3, [3.3] * 3, [18] * 3
+    lig = dict(synth.make_flexible_ligand(n_heavy=16, n_tors=3, n_branch=2, seed=13))
+    ty = lig["types"].copy(); ty[2] = 1; ty[9] = 0; lig["types"] = ty
+    rx, rt = synth.make_receptor(400, box=24, seed=5)
+    sf, rm = R.RefScoring(), R.RefModel(lig, rx, rt)
+    s = CR.RefCNNScorer(names=["crossdock_default2018"])
+    rs = np.random.RandomState(9)
+    outside = 0
+    for k in range(4):
+        x = lig["conf0"].copy(); x[:3] += rs.uniform(-2.5, 2.5, 3)
+        xyz = rm.set(x.astype(np.float32))
+        outside += bool((np.abs(xyz[ty > 1]) > 3.3).any())
+        for deriv in (True, False):
+            e, f, c = R.noncache_dl_eval(rm, sf, R.LINEAR, begin, end, nn, s.dl(), slope=10.0, deriv=deriv)
+            rm.set(x.astype(np.float32))
+            e2, f2 = CR.product_noncache_cnn(["crossdock_default2018"], rm, begin, end, nn, c, slope=10.0, deriv=deriv)
+            assert e == e2 and (not deriv or np.array_equal(f, f2)), (k, deriv)
+        _, f3 = CR.product_noncache_cnn(["crossdock_default2018"], rm, begin, end, nn, c, slope=10.0, reference_force_routing=False)
+        assert not np.array_equal(f3, f2)
+    assert outside >= 2
