@@ -1,7 +1,7 @@
 """Device kernels vs the CPU restatement on ligands with RANDOM torsion trees (synth.make_tree_ligand: nested branches, several children
 per node) -- eval_deriv, quasi-Newton, one Monte-Carlo launch.  The restatement is bit-identical to the compiled reference on these trees
 (tests/test_oracle_vs_reference_build.py::test_random_torsion_trees); this script is the device half, to be run in the next GPU session
-and then turned into a -m gpu test: python tools/device_tree_check.py"""
+and then turned into a -m gpu test: python tests/device_tree_check.py"""
 import json, sys
 sys.path.insert(0, '.')
 import numpy as np

@@ -3,7 +3,7 @@
 T=${1:-r6a}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q --tb=short 2>&1 | grep -v "^$" | cut -c1-400 | tail -40 > gpurun_out/${T}_pytest.log
-python tools/device_tree_check.py > gpurun_out/${T}_tree_check.json 2> gpurun_out/${T}_tree_check.err
+python tests/device_tree_check.py > gpurun_out/${T}_tree_check.json 2> gpurun_out/${T}_tree_check.err
 python tools/minimize_demo.py 1000 200 > gpurun_out/${T}_minimize.json 2> gpurun_out/${T}_minimize.err
 ./tests/cpp/host_test --minimize gnina_b200/weights > gpurun_out/${T}_cpp_minimize.log 2>&1
 ./tests/cpp/host_test --dock gnina_b200/weights > gpurun_out/${T}_cpp_dock.log 2>&1
