@@ -60,6 +60,8 @@ def lib():
         L.gadp_last_error.restype = C.c_char_p
         L.gcref_product_noncache_cnn.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_void_p, fp, fp, ip, C.c_float, fp, C.c_float,
                                                  C.c_int, C.c_int, fp, fp]
+        L.gcref_product_lockstep_minimize.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_void_p, fp, fp, C.c_float, fp, C.c_int,
+                                                      C.c_int, C.c_int, C.c_int, C.c_int, fp, ip, ip]
         L.gcref_grid_dim.argtypes = [C.c_void_p]; L.gcref_grid_dim.restype = C.c_float
         L.gcref_grid_res.argtypes = [C.c_void_p]; L.gcref_grid_res.restype = C.c_float
         L.gcref_score.argtypes = [C.c_void_p, C.c_void_p, C.c_int, fp, fp]
@@ -139,6 +141,21 @@ def product_noncache_cnn(names, ref_model, begin, end, n, center, slope=10.0, v=
                                     _f(c), v, int(deriv), int(reference_force_routing), _f(e), _f(f)):
         raise RuntimeError(L.gcref_last_error().decode())
     return float(e[0]), (f if deriv else None)
+
+
+def product_lockstep_minimize(names, ref_model, begin, end, confs, maxiters, slope=10.0, accurate=True, early_term=False,
+                              reference_force_routing=True):
+    """config 5 through the product's C++ host code (gb::CNNScorer, gb::LigandTree, gb::CnnBatchEnergy, gb::minimize_poses) on the CPU over
+    the stand-in C ABI -> (e [n], confs [n, 7+T], evaluations [n], rounds)"""
+    L = lib()
+    na = (C.c_char_p * max(1, len(names)))(*[x.encode() for x in names])
+    b, e_ = (np.ascontiguousarray(a, np.float32) for a in (begin, end))
+    x = np.array(confs, np.float32); e = np.zeros(len(x), np.float32); ev = np.zeros(len(x), np.int32); rounds = (C.c_int * 1)()
+    wd = os.path.join(os.path.dirname(_HERE), "gnina_b200", "weights")
+    if L.gcref_product_lockstep_minimize(na, len(names), wd.encode(), ref_model.p, _f(b), _f(e_), slope, _f(x), len(x), maxiters, int(accurate),
+                                         int(early_term), int(reference_force_routing), _f(e), ev.ctypes.data_as(C.POINTER(C.c_int)), rounds):
+        raise RuntimeError(L.gcref_last_error().decode())
+    return e, x, ev, rounds[0]
 
 
 class VinaAdapters:

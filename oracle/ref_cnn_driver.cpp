@@ -179,10 +179,8 @@ int mockgb_cnn_set_receptor(gb_cnn* h, const float* xyz, const int32_t* t, int n
   for (int i = 0; i < n; i++) { h->rec[i] = make_float3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]); h->rec_t[i] = (smt)t[i]; }
   return GB_OK;
 }
-static int mock_score(gb_cnn* h, const float* xyz, const int32_t* t, const int32_t* offs, int n_poses, const float* centers, float* score,
-                      float* affinity, float* loss, float* variance, float* grad) {
-  if (n_poses != 1) { g_mock_err = "the stand-in scores one pose per call"; return GB_ERR_USAGE; }
-  const int n = offs[1] - offs[0];
+static int mock_score_one(gb_cnn* h, const float* xyz, const int32_t* t, int n, const float* centers, float* score, float* affinity,
+                          float* loss, float* variance, float* grad) {
   std::vector<float3> lig(n); std::vector<smt> lt(n);
   for (int i = 0; i < n; i++) { lig[i] = make_float3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]); lt[i] = (smt)t[i]; }
   const vec center = centers ? vec(centers[0], centers[1], centers[2]) : vec(NAN, NAN, NAN);
@@ -198,7 +196,22 @@ static int mock_score(gb_cnn* h, const float* xyz, const int32_t* t, const int32
   a /= cnt; l /= cnt; s /= cnt;
   float var = 0;
   if (affs.size() > 1) { float sum = 0; for (float q : affs) { float d = a - q; d *= d; sum += d; } var = sum / affs.size(); }
-  *score = (float)s; *affinity = a; *loss = l; *variance = var;
+  if (score) *score = (float)s;
+  if (affinity) *affinity = a;
+  if (loss) *loss = l;
+  if (variance) *variance = var;
+  return GB_OK;
+}
+// poses are independent: one after the other; every output array is nullable as in the C ABI
+static int mock_score(gb_cnn* h, const float* xyz, const int32_t* t, const int32_t* offs, int n_poses, const float* centers, float* score,
+                      float* affinity, float* loss, float* variance, float* grad) {
+  for (int p = 0; p < n_poses; p++) {
+    const int a = offs[p], n = offs[p + 1] - offs[p];
+    const int rc = mock_score_one(h, xyz + 3 * a, t + a, n, centers ? centers + 3 * p : nullptr, score ? score + p : nullptr,
+                                  affinity ? affinity + p : nullptr, loss ? loss + p : nullptr, variance ? variance + p : nullptr,
+                                  grad ? grad + 3 * a : nullptr);
+    if (rc != GB_OK) return rc;
+  }
   return GB_OK;
 }
 int mockgb_cnn_score_batch(gb_cnn* h, const float* xyz, const int32_t* t, const int32_t* offs, int n_poses, const float* centers, float* score,
@@ -228,6 +241,8 @@ extern "C" int mockgb_initialize_cuda(int) { return 0; }
 #define gb_cnn_score_batch mockgb_cnn_score_batch
 #define gb_cnn_score_grad mockgb_cnn_score_grad
 #include "cnn_b200_scorer.h"
+#include "gnina_b200_minimize.hpp"   // gb::LigandTree, gb::minimize_poses, gb::CnnBatchEnergy (redirected to the stand-in like the rest)
+#include "docking_b200.h"            // b200::B200Ligand: the model -> gb_ligand_topology adapter
 
 extern "C" {
 // CNNB200Scorer(cnn_options, device, blob_dir) over the stand-in; copy != 0: hand out fresh_copy() of it instead (what every
@@ -290,5 +305,38 @@ extern "C" int gcref_product_noncache_cnn(const char** names, int n_names, const
     for (int i = 0; i < na; i++) { t[i] = (int32_t)m.atoms[i].sm; for (int k = 0; k < 3; k++) xyz[3 * i + k] = (float)m.coords[i][k]; }
     *e = nc.eval(xyz.data(), t.data(), na, with_deriv ? &f : nullptr, v);
     if (with_deriv) std::copy(f.begin(), f.end(), forces);
+  });
+}
+
+// config 5 through the product's C++ host code: gb::CNNScorer + gb::LigandTree + gb::CnnBatchEnergy + gb::minimize_poses
+// (include/gnina_b200_minimize.hpp) on n conformations of the model's ligand at once; ONE gb_cnn_score_grad call per round.
+// confs [n][7+T] in/out; the kinematics use this host's sinf / cosf / acosf like the reference build
+extern "C" int gcref_product_lockstep_minimize(const char** names, int n_names, const char* weights_dir, void* model_handle, const float* begin,
+                                               const float* end, float slope, float* confs, int n, int maxiters, int accurate, int early_term,
+                                               int reference_force_routing, float* e_out, int* evals_out, int* rounds_out) {
+  return guarded([&] {
+    model& m = *(model*)gref_model_ptr(model_handle);
+    std::vector<std::string> nm;
+    for (int i = 0; i < n_names; i++) nm.push_back(names[i]);
+    gb::CNNScorer scorer(weights_dir, nm, 0);
+    std::vector<float> rx; std::vector<int32_t> rt;
+    for (const atom& a : m.get_fixed_atoms()) { rt.push_back((int32_t)a.sm); for (int k = 0; k < 3; k++) rx.push_back((float)a.coords[k]); }
+    scorer.set_receptor(rx.data(), rt.data(), (int)rt.size());
+    b200::B200Ligand BL(m);
+    gb::LigandTree tree(BL.topo);
+    gb::Transcendentals saved = gb::transcendentals();
+    gb::transcendentals().sin = [](float x) { return sinf(x); };
+    gb::transcendentals().cos = [](float x) { return cosf(x); };
+    gb::transcendentals().acos = [](float x) { return acosf(x); };
+    gb::CnnBatchEnergy energy(scorer.handle(), tree, begin, end, slope, scorer.info(0).dimension);
+    energy.set_reference_force_routing(reference_force_routing != 0);
+    energy.set_centers(confs, n);
+    gb::MinimizeParams mp; mp.maxiters = maxiters; mp.accurate_line_search = accurate != 0; mp.early_term = early_term != 0;
+    std::vector<int> ev; int rounds = 0;
+    std::vector<float> e = gb::minimize_poses(tree, energy, confs, n, mp, &ev, &rounds);
+    gb::transcendentals() = saved;
+    std::copy(e.begin(), e.end(), e_out);
+    std::copy(ev.begin(), ev.end(), evals_out);
+    *rounds_out = rounds;
   });
 }

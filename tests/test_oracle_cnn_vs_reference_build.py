@@ -271,3 +271,26 @@ def test_product_cpp_classes_are_non_cache_cnn():
         _, f3 = CR.product_noncache_cnn(["crossdock_default2018"], rm, begin, end, nn, c, slope=10.0, reference_force_routing=False)
         assert not np.array_equal(f3, f2)
     assert outside >= 2
+
+
+def test_config5_through_the_product_cpp_host_code():
+    """the C++ side of config 5 -- gb::CNNScorer, gb::LigandTree (topology through b200::B200Ligand), gb::CnnBatchEnergy and
+    gb::minimize_poses of include/gnina_b200_minimize.hpp, their C-ABI calls served by the stand-in over the reference's TorchModel -- on
+    all poses at once vs the reference's quasi_newton + non_cache_cnn + CNNTorchScorer pose by pose (hydrogens among the ligand atoms, so
+    the force routing of gb::CnnBatchEnergy is exercised): energies and conformations are EQUAL"""
+    begin, end, nn = [-9.7] * 3, [10.55] * 3, [54] * 3
+    lig = dict(synth.make_flexible_ligand(n_heavy=14, n_tors=3, n_branch=2, seed=8))
+    ty = lig["types"].copy(); ty[3] = 1; ty[8] = 0; lig["types"] = ty
+    rx, rt = synth.make_receptor(400, box=24, seed=5)
+    sf, rm = R.RefScoring(), R.RefModel(lig, rx, rt)
+    rs = np.random.RandomState(1)
+    X = np.tile(lig["conf0"], (3, 1)).astype(np.float32)
+    X[:, :3] += rs.uniform(-1, 1, (3, 3)); X[:, 7:] = rs.uniform(-1, 1, (3, X.shape[1] - 7))
+    X = X.astype(np.float32)
+    s = CR.RefCNNScorer(names=["crossdock_default2018"])
+    for accurate, iters in ((True, 4), (False, 6)):
+        ref = [R.minimize_dl(rm, sf, R.LINEAR, begin, end, nn, x, iters, s.dl(), accurate=accurate) for x in X]
+        e, x, ev, rounds = CR.product_lockstep_minimize(["crossdock_default2018"], rm, begin, end, X, iters, accurate=accurate)
+        for i in range(len(X)):
+            assert float(e[i]) == ref[i][0] and np.array_equal(x[i], ref[i][1]), (accurate, i)
+        assert rounds < ev.sum()
