@@ -294,3 +294,13 @@ def test_config5_through_the_product_cpp_host_code():
         for i in range(len(X)):
             assert float(e[i]) == ref[i][0] and np.array_equal(x[i], ref[i][1]), (accurate, i)
         assert rounds < ev.sum()
+
+
+def test_adapter_expands_prefix_ensembles_like_the_reference():
+    """`<prefix>_ensemble` through the adapter (gb::expand_model_names over the packaged blobs, sorted) vs CNNTorchScorer's walk over its
+    name table (unordered): the same members -- equal mean and variance up to the association of the float sums"""
+    lig, rx, rt, rm, xyz = _case(41)
+    for ens in ("general_default2018_ensemble", "dense_1_3_ensemble"):
+        a = CR.RefCNNScorer(names=[ens]).score(rm, False)
+        b = CR.RefCNNScorer.adapter(names=[ens]).score(rm, False)
+        assert a[3] > 0 and np.allclose(a[:4], b[:4], rtol=2e-6, atol=1e-7), (ens, a[:4], b[:4])
