@@ -1,7 +1,10 @@
 """ctypes front-end to oracle/_ref/libgnina_cnn_ref.so: the REFERENCE's own CNN scoring host code (lib/torch_model.cpp,
 lib/cnn_torch_scorer.cpp, lib/dl_scorer.cpp) compiled where it lies, running the reference's own TorchScript files with libtorch on the
 CPU; libmolgrid (third party, absent) is replaced by a stand-in over oracle/gridmaker_ref.c (oracle/ref_shim/libmolgrid).  TEST
-INFRASTRUCTURE: pins oracle/pipeline.py and generates tests/golden/cnn_ref_kat.npz.  Exists only where /root/reference does (the
+INFRASTRUCTURE: pins oracle/pipeline.py and generates tests/golden/cnn_ref_kat.npz.  The same library executes the integration adapters
+(integration/*.h) and the product's C++ host classes (include/*.hpp) on the CPU inside the reference's classes, their C-ABI calls
+served by stand-ins that honour include/gnina_b200.h's contract (ref_cnn_driver.cpp: the reference's TorchModel as the network;
+ref_adapters_driver.cpp: the C restatement of the Vina rows).  Exists only where /root/reference does (the
 TorchScript files are read from there), i.e. in the build container -- not on the GPU box."""
 import ctypes as C
 import os
